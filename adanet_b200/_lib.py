@@ -1,0 +1,112 @@
+"""ctypes binding of the C-ABI in include/adanet_b200.h.
+
+No torch types cross this boundary: tensors are passed as ``data_ptr()``
+integers and the CUDA stream as its raw handle.  The shared library is built
+in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a); if it is missing the
+import of any compute entry point fails loudly -- there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libadanet_b200.so")
+
+# constants mirrored from include/adanet_b200.h
+ACT_NONE, ACT_RELU = 0, 1
+HEAD_SOFTMAX_XENT, HEAD_MSE, HEAD_SIGMOID_XENT = 0, 1, 2
+MIX_SCALAR, MIX_VECTOR, MIX_MATRIX = 0, 1, 2
+OPT_SGD, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADAM = 0, 1, 2, 3
+PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+Q_VERSION, Q_DENSE_BWD_WS, Q_HEAD_WS, Q_DENSE_FWD_PATH, Q_SM_COUNT, Q_LAUNCH_COUNT, Q_DENSE_BWD_PATH = range(7)
+
+EXPORTS = (
+    "adn_last_error", "adn_init", "adn_query", "adn_set_dense_path", "adn_dense_fwd", "adn_dense_bwd", "adn_head_loss",
+    "adn_ensemble_head", "adn_opt_step", "adn_l1_norm", "adn_ema_update", "adn_record_scalars",
+    "adn_counter_add",
+)
+
+
+class AdnError(RuntimeError):
+  pass
+
+
+_lib = None
+
+
+def load():
+  """Loads (once) and returns the ctypes library, with prototypes set."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise AdnError(
+        "adanet_b200 CUDA extension not built: %s is missing. Run `python -c 'import __graft_entry__ as g; "
+        "g.build()'` at the repo root (needs nvcc). There is no CPU fallback." % LIB_PATH)
+  lib = ctypes.CDLL(LIB_PATH)
+  p, i64, f32 = c_void_p, c_int64, c_float
+  lib.adn_last_error.restype = c_char_p
+  lib.adn_last_error.argtypes = []
+  lib.adn_init.argtypes = []
+  lib.adn_query.argtypes = [c_int, i64, i64, i64, POINTER(i64)]
+  lib.adn_set_dense_path.argtypes = [c_int]
+  lib.adn_dense_fwd.argtypes = [p, p, p, p, i64, i64, i64, c_int, p]
+  lib.adn_dense_bwd.argtypes = [p, p, p, p, p, p, i64, i64, i64, c_int, p, i64, p]
+  lib.adn_head_loss.argtypes = [c_int, p, p, p, p, p, i64, i64, p, i64, p]
+  lib.adn_ensemble_head.argtypes = [c_int, c_int, POINTER(p), c_int, p, p, POINTER(f32), c_int, f32, p, p,
+                                    p, p, p, p, p, i64, i64, p, i64, p]
+  lib.adn_opt_step.argtypes = [c_int, POINTER(p), POINTER(p), POINTER(p), POINTER(p), POINTER(i64), c_int,
+                               POINTER(f32), p, p]
+  lib.adn_l1_norm.argtypes = [p, i64, p, p]
+  lib.adn_ema_update.argtypes = [p, p, f32, p]
+  lib.adn_record_scalars.argtypes = [POINTER(p), c_int, p, i64, p, i64, p]
+  lib.adn_counter_add.argtypes = [p, i64, p]
+  for name in EXPORTS:
+    if name != "adn_last_error":
+      getattr(lib, name).restype = c_int
+  _lib = lib
+  return lib
+
+
+def check(rc: int, what: str = ""):
+  if rc != 0:
+    msg = load().adn_last_error().decode("utf-8", "replace")
+    raise AdnError("%s failed (%d): %s" % (what or "adanet_b200 call", rc, msg))
+
+
+def query(key: int, a: int = 0, b: int = 0, c: int = 0) -> int:
+  out = c_int64(0)
+  check(load().adn_query(key, a, b, c, ctypes.byref(out)), "adn_query")
+  return int(out.value)
+
+
+def launch_count() -> int:
+  return query(Q_LAUNCH_COUNT)
+
+
+def set_dense_path(path: int):
+  check(load().adn_set_dense_path(path), "adn_set_dense_path")
+
+
+def ptr_array(ptrs):
+  arr = (c_void_p * len(ptrs))()
+  for i, v in enumerate(ptrs):
+    arr[i] = v
+  return arr
+
+
+def f32_array(vals):
+  arr = (c_float * len(vals))()
+  for i, v in enumerate(vals):
+    arr[i] = float(v)
+  return arr
+
+
+def i64_array(vals):
+  arr = (c_int64 * len(vals))()
+  for i, v in enumerate(vals):
+    arr[i] = int(v)
+  return arr

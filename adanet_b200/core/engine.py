@@ -1,0 +1,387 @@
+"""Per-GPU iteration plan: the replacement for one `session.run` of the
+reference's iteration graph.
+
+The reference builds a TF1 graph per AdaNet iteration
+(adanet/core/iteration.py:506-816) and executes every subnetwork's and every
+candidate ensemble's train op in one `session.run` per step through hooks
+(adanet/core/iteration.py:150-205,961-996).  Here an :class:`IterationPlan`
+owns, for the candidates placed on this GPU, all parameters, activations,
+gradients and bookkeeping in HBM and enqueues the hand-written sm_100a kernels
+of ``adanet_b200/csrc`` through the C ABI (include/adanet_b200.h):
+
+  frozen members  -> adn_dense_fwd (forward-only replay, shared by all candidates)
+  new subnetwork  -> adn_dense_fwd / adn_head_loss / adn_dense_bwd / adn_opt_step
+  candidate head  -> adn_ensemble_head (+ adn_opt_step on the mixture weights)
+  EMA / steps     -> adn_ema_update / adn_record_scalars / adn_counter_add
+
+Each candidate runs on its own CUDA stream (they are independent within an
+iteration) and, once shapes are fixed, the whole step is captured in a CUDA
+graph so a step is one graph launch.  PyTorch is used for device memory,
+streams and graphs only.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from adanet_b200 import _lib
+
+_HEAD_KIND = {"softmax_xent": _lib.HEAD_SOFTMAX_XENT, "mse": _lib.HEAD_MSE, "sigmoid_xent": _lib.HEAD_SIGMOID_XENT}
+_MIX_KIND = {"scalar": _lib.MIX_SCALAR, "vector": _lib.MIX_VECTOR, "matrix": _lib.MIX_MATRIX}
+_OPT_KIND = {"sgd": _lib.OPT_SGD, "momentum": _lib.OPT_MOMENTUM, "rmsprop": _lib.OPT_RMSPROP, "adam": _lib.OPT_ADAM}
+_OPT_DEFAULTS = {"sgd": (), "momentum": (), "rmsprop": (0.9, 0.0, 1e-10), "adam": (0.9, 0.999, 1e-8)}
+TRACE_FIELDS = ("sub_loss", "ens_loss", "adanet_loss", "ema")
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> int:
+  s = stream if stream is not None else torch.cuda.current_stream()
+  return s.cuda_stream
+
+
+def _require_cuda():
+  if not torch.cuda.is_available():
+    raise _lib.AdnError("adanet_b200 engine needs a CUDA device (sm_100a); there is no CPU fallback.")
+  lib = _lib.load()
+  _lib.check(lib.adn_init(), "adn_init")
+  return lib
+
+
+@dataclass
+class SubnetworkPlanSpec:
+  """What a Builder lowers to for the dense hot path.
+
+  name/complexity follow adanet/examples/simple_dnn.py:61-131; `dims` is
+  [d0, H, ..., H, logits_dim]; `optimizer` is ("sgd", lr) | ("momentum", lr, m)
+  | ("rmsprop", lr[, rho, mu, eps]) | ("adam", lr[, b1, b2, eps]) with TF1
+  semantics; `ws`/`bs` are the initial kernels W[in,out] / biases (NumPy fp32).
+  """
+  name: str
+  dims: Sequence[int]
+  complexity: float
+  optimizer: tuple
+  ws: List[np.ndarray]
+  bs: List[np.ndarray]
+  shared: Optional[dict] = None
+
+
+@dataclass
+class EnsemblerPlanSpec:
+  """ComplexityRegularizedEnsembler arguments (adanet/ensemble/weighted.py:228-251)."""
+  optimizer: Optional[tuple] = None
+  mixture_weight_type: str = "scalar"
+  adanet_lambda: float = 0.0
+  adanet_beta: float = 0.0
+  use_bias: bool = False
+  name: str = "complexity_regularized"
+  legacy_train_op: bool = False
+
+
+def _opt_hyper(spec: tuple) -> Tuple[int, List[float]]:
+  kind = spec[0]
+  vals = list(spec[1:])
+  defaults = _OPT_DEFAULTS[kind]
+  n_fixed = {"sgd": 1, "momentum": 2, "rmsprop": 1, "adam": 1}[kind]
+  extra = vals[n_fixed:]
+  vals = vals[:n_fixed] + list(extra) + list(defaults[len(extra):])
+  return _OPT_KIND[kind], [float(v) for v in vals]
+
+
+class _Optimizer:
+  """Device-resident optimizer state for one group of parameter tensors."""
+
+  def __init__(self, spec: tuple, params: List[torch.Tensor]):
+    self.kind, self.hyper = _opt_hyper(spec)
+    self.params = params
+    dev = params[0].device
+    n_slots = {_lib.OPT_SGD: 0, _lib.OPT_MOMENTUM: 1, _lib.OPT_RMSPROP: 2, _lib.OPT_ADAM: 2}[self.kind]
+    self.slot0 = [torch.zeros_like(p) for p in params] if n_slots >= 1 else None
+    self.slot1 = [torch.zeros_like(p) for p in params] if n_slots >= 2 else None
+    if self.kind == _lib.OPT_RMSPROP:
+      for s in self.slot0:
+        s.fill_(1.0)   # TF RMSProp: ms initialised to ones
+    self.step_dev = torch.zeros((), dtype=torch.int64, device=dev) if self.kind == _lib.OPT_ADAM else None
+    self._p = _lib.ptr_array([p.data_ptr() for p in params])
+    self._s0 = _lib.ptr_array([s.data_ptr() for s in self.slot0]) if self.slot0 else None
+    self._s1 = _lib.ptr_array([s.data_ptr() for s in self.slot1]) if self.slot1 else None
+    self._sizes = _lib.i64_array([p.numel() for p in params])
+    self._hyper = _lib.f32_array(self.hyper)
+
+  def apply(self, lib, grads: List[torch.Tensor], stream_ptr: int):
+    g = _lib.ptr_array([t.data_ptr() for t in grads])
+    _lib.check(lib.adn_opt_step(self.kind, self._p, g, self._s0, self._s1, self._sizes, len(self.params),
+                                self._hyper, self.step_dev.data_ptr() if self.step_dev is not None else None,
+                                stream_ptr), "adn_opt_step")
+
+
+class DenseNet:
+  """Parameters + activation buffers of one dense subnetwork on one GPU.
+
+  Forward: h_i = relu(h_{i-1} @ W_i + b_i), logits = h_L @ W_o + b_o
+  (adanet/examples/simple_dnn.py:70-86).  Used forward-only for frozen
+  members (adanet/core/iteration.py:568-579).
+  """
+
+  def __init__(self, name: str, dims: Sequence[int], ws, bs, complexity: float, batch: int,
+               device: torch.device, iteration: int = 0, shared: Optional[dict] = None):
+    self.name, self.dims, self.complexity, self.iteration = name, list(dims), float(complexity), iteration
+    self.shared = shared or {}
+    self.batch = batch
+    self.device = device
+    assert len(ws) == len(dims) - 1
+    self.ws = [torch.as_tensor(np.ascontiguousarray(w, dtype=np.float32)).to(device) for w in ws]
+    self.bs = [torch.as_tensor(np.ascontiguousarray(b, dtype=np.float32)).to(device) for b in bs]
+    for i, w in enumerate(self.ws):
+      if tuple(w.shape) != (dims[i], dims[i + 1]):
+        raise ValueError("kernel %d of %s has shape %s, want %s" % (i, name, tuple(w.shape), (dims[i], dims[i + 1])))
+    self.acts = [torch.empty((batch, d), dtype=torch.float32, device=device) for d in dims[1:]]
+
+  @property
+  def logits(self) -> torch.Tensor:
+    return self.acts[-1]
+
+  @property
+  def last_layer(self) -> torch.Tensor:
+    return self.acts[-2] if len(self.acts) >= 2 else None
+
+  def forward(self, lib, x: torch.Tensor, sp: int):
+    h = x
+    n = len(self.ws)
+    for i in range(n):
+      act = _lib.ACT_RELU if i < n - 1 else _lib.ACT_NONE
+      _lib.check(lib.adn_dense_fwd(h.data_ptr(), self.ws[i].data_ptr(), self.bs[i].data_ptr(),
+                                   self.acts[i].data_ptr(), self.batch, self.dims[i], self.dims[i + 1], act, sp),
+                 "adn_dense_fwd")
+      h = self.acts[i]
+
+  def numpy_params(self):
+    return [w.cpu().numpy() for w in self.ws], [b.cpu().numpy() for b in self.bs]
+
+
+class CandidatePlan:
+  """One `*_grow` candidate: its new subnetwork + its ensemble head + EMA.
+
+  Colocating the candidate ensemble with its new subnetwork is possible because
+  under GrowStrategy each candidate contains exactly one new subnetwork
+  (adanet/ensemble/strategy.py:97-106); SURVEY.md section 8e.
+  """
+
+  def __init__(self, lib, spec: SubnetworkPlanSpec, frozen: Sequence[DenseNet], ens: EnsemblerPlanSpec,
+               iteration: int, batch: int, logits_dim: int, head: str, decay: float, trace_capacity: int,
+               device: torch.device, index: int):
+    self.lib, self.spec, self.ens, self.index = lib, spec, ens, index
+    self.batch, self.C, self.head = batch, logits_dim, _HEAD_KIND[head]
+    self.name = "t{}_{}_grow_{}".format(iteration, spec.name, ens.name)   # iteration.py:633,691-693
+    self.net = DenseNet(spec.name, spec.dims, spec.ws, spec.bs, spec.complexity, batch, device, iteration,
+                        spec.shared)
+    self.frozen = list(frozen)
+    dims = self.net.dims
+    f32 = dict(dtype=torch.float32, device=device)
+    # gradients and backward scratch
+    self.dws = [torch.empty_like(w) for w in self.net.ws]
+    self.dbs = [torch.empty_like(b) for b in self.net.bs]
+    self.dlogits = torch.empty((batch, dims[-1]), **f32)
+    hid = max(dims[1:-1]) if len(dims) > 2 else 0
+    self.dz = [torch.empty((batch, hid), **f32) for _ in range(2)] if hid else []
+    ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_WS, batch, dims[i], dims[i + 1]) for i in range(len(dims) - 1))
+    n_members = len(frozen) + 1
+    ws_bytes = max(ws_bytes, _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, n_members))
+    self.workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
+    self.ws_bytes = ws_bytes
+    self.sub_loss = torch.zeros((1,), **f32)
+    params, self._grads = [], []
+    for w, b, dw, db in zip(self.net.ws, self.net.bs, self.dws, self.dbs):
+      params += [w, b]
+      self._grads += [dw, db]
+    self.sub_opt = _Optimizer(spec.optimizer, params)
+    # ensemble state (weighted.py:360-366,419-428,487-516)
+    self.mix = _MIX_KIND[ens.mixture_weight_type]
+    if self.mix == _lib.MIX_MATRIX:
+      raise NotImplementedError("MATRIX mixture weights are not wired into the iteration plan yet")
+    wshape = (n_members,) if self.mix == _lib.MIX_SCALAR else (n_members, logits_dim)
+    self.mix_w = torch.full(wshape, 1.0 / n_members, **f32)
+    self.bias = torch.zeros((logits_dim,), **f32)
+    self.d_mix_w = torch.zeros(wshape, **f32)
+    self.d_bias = torch.zeros((logits_dim,), **f32)
+    self.complexities = [f.complexity for f in frozen] + [spec.complexity]
+    lam, beta = float(ens.adanet_lambda), float(ens.adanet_beta)
+    self.reg_is_zero = int(lam == 0.0 and beta == 0.0)
+    # weighted.py:351-358 (_compute_adanet_gamma), evaluated in fp32 like the graph does
+    self.gammas = [float(np.float32(beta) if lam == 0.0 else np.float32(np.float32(lam) * np.float32(c) + np.float32(beta)))
+                   for c in self.complexities]
+    self.reg_multiplier = 1.0 if ens.legacy_train_op else 2.0
+    self.out3 = torch.zeros((3,), **f32)
+    self.ens_opt = None
+    if ens.optimizer is not None:
+      ens_params = [self.mix_w] + ([self.bias] if ens.use_bias else [])
+      self._ens_grads = [self.d_mix_w] + ([self.d_bias] if ens.use_bias else [])
+      self.ens_opt = _Optimizer(ens.optimizer, ens_params)
+    self.ema_state = torch.zeros((3,), **f32)   # {biased, n, value}; candidate.py:101-129
+    self.decay = float(decay)
+    self.trace = torch.zeros((trace_capacity, 4), **f32)
+    self.trace_capacity = trace_capacity
+    self._members = _lib.ptr_array([f.logits.data_ptr() for f in self.frozen] + [self.net.logits.data_ptr()])
+    self._gammas = _lib.f32_array(self.gammas)
+    self._trace_src = _lib.ptr_array([self.sub_loss.data_ptr(), self.out3.data_ptr(),
+                                      self.out3.data_ptr() + 8, self.ema_state.data_ptr() + 8])
+
+  def enqueue_train_step(self, x: torch.Tensor, labels: torch.Tensor, labels_f: Optional[torch.Tensor],
+                         step_dev: torch.Tensor, sp: int):
+    """SURVEY.md section 3.3 steps 1-13 for this candidate (frozen logits already computed)."""
+    lib, net, B, C = self.lib, self.net, self.batch, self.C
+    lab = labels.data_ptr() if labels is not None else None
+    labf = labels_f.data_ptr() if labels_f is not None else None
+    wsp = self.workspace.data_ptr()
+    # steps 1-2: subnetwork forward
+    net.forward(lib, x, sp)
+    # step 3: subnetwork loss + dlogits
+    _lib.check(lib.adn_head_loss(self.head, net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
+                                 self.dlogits.data_ptr(), B, C, wsp, self.ws_bytes, sp), "adn_head_loss")
+    # steps 6-11: ensemble head on pre-update values
+    train_ens = self.ens_opt is not None
+    _lib.check(lib.adn_ensemble_head(
+        self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
+        self._gammas, self.reg_is_zero, self.reg_multiplier, lab, labf, self.out3.data_ptr(),
+        self.d_mix_w.data_ptr() if train_ens else None,
+        self.d_bias.data_ptr() if (train_ens and self.ens.use_bias) else None,
+        None, None, B, C, wsp, self.ws_bytes, sp), "adn_ensemble_head")
+    # step 12: EMA of adanet_loss
+    _lib.check(lib.adn_ema_update(self.ema_state.data_ptr(), self.out3.data_ptr() + 8, self.decay, sp),
+               "adn_ema_update")
+    _lib.check(lib.adn_record_scalars(self._trace_src, 4, self.trace.data_ptr(), 4, step_dev.data_ptr(),
+                                      self.trace_capacity, sp), "adn_record_scalars")
+    # step 4: backward through the subnetwork's own variables only
+    n = len(net.ws)
+    dz = self.dlogits
+    for i in range(n - 1, -1, -1):
+      xin = x if i == 0 else net.acts[i - 1]
+      # dz ping-pong buffers are sized for the widest hidden layer; carve a contiguous [B, d_i] view
+      dx = self.dz[i % 2].view(-1)[:B * net.dims[i]].view(B, net.dims[i]) if i > 0 else None
+      _lib.check(lib.adn_dense_bwd(xin.data_ptr(), net.ws[i].data_ptr(), dz.data_ptr(),
+                                   dx.data_ptr() if dx is not None else None, self.dws[i].data_ptr(),
+                                   self.dbs[i].data_ptr(), B, net.dims[i], net.dims[i + 1], 1 if i > 0 else 0,
+                                   wsp, self.ws_bytes, sp), "adn_dense_bwd")
+      dz = dx
+    # step 11 (apply) then steps 4-5 (apply)
+    if train_ens:
+      self.ens_opt.apply(lib, self._ens_grads, sp)
+    self.sub_opt.apply(lib, self._grads, sp)
+
+  def enqueue_eval(self, x, labels, labels_f, ens_out: Optional[torch.Tensor], sp: int):
+    """Forward-only: subnetwork logits + ensemble logits/loss (evaluate / predict)."""
+    lib, net, B, C = self.lib, self.net, self.batch, self.C
+    net.forward(lib, x, sp)
+    _lib.check(lib.adn_ensemble_head(
+        self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
+        self._gammas, self.reg_is_zero, self.reg_multiplier,
+        labels.data_ptr() if labels is not None else None, labels_f.data_ptr() if labels_f is not None else None,
+        self.out3.data_ptr(), None, None, None, ens_out.data_ptr() if ens_out is not None else None, B, C,
+        self.workspace.data_ptr(), self.ws_bytes, sp), "adn_ensemble_head")
+
+
+class IterationPlan:
+  """All work of one AdaNet iteration placed on this GPU."""
+
+  def __init__(self, iteration: int, specs: Sequence[SubnetworkPlanSpec], frozen: Sequence[DenseNet],
+               ens: EnsemblerPlanSpec, batch: int, in_dim: int, logits_dim: int, head: str = "softmax_xent",
+               adanet_loss_decay: float = 0.9, trace_capacity: int = 4096, device: Optional[torch.device] = None,
+               candidate_indices: Optional[Sequence[int]] = None, use_cuda_graph: bool = True,
+               multi_stream: bool = True):
+    self.lib = _require_cuda()
+    self.device = device or torch.device("cuda", torch.cuda.current_device())
+    self.iteration, self.batch, self.in_dim, self.C, self.head = iteration, batch, in_dim, logits_dim, head
+    self.frozen = list(frozen)
+    for f in self.frozen:
+      if f.batch != batch:
+        raise ValueError("frozen member %s was built for batch %d, plan uses %d" % (f.name, f.batch, batch))
+    idx = list(candidate_indices) if candidate_indices is not None else list(range(len(specs)))
+    self.candidates = [CandidatePlan(self.lib, s, self.frozen, ens, iteration, batch, logits_dim, head,
+                                     adanet_loss_decay, trace_capacity, self.device, i)
+                       for i, s in zip(idx, specs)]
+    self.x = torch.empty((batch, in_dim), dtype=torch.float32, device=self.device)
+    self.labels = torch.empty((batch,), dtype=torch.int64, device=self.device) if head == "softmax_xent" else None
+    self.labels_f = (torch.empty((batch, logits_dim), dtype=torch.float32, device=self.device)
+                     if head != "softmax_xent" else None)
+    self.step_dev = torch.zeros((), dtype=torch.int64, device=self.device)
+    self.steps_done = 0
+    self.trace_capacity = trace_capacity
+    self.use_cuda_graph = use_cuda_graph
+    self.multi_stream = multi_stream and len(self.candidates) > 1
+    self.streams = [torch.cuda.Stream(device=self.device) for _ in self.candidates] if self.multi_stream else []
+    self._graph = None
+    self.launches_per_step = None
+
+  # -- staging -------------------------------------------------------------
+  def load_batch(self, x, y):
+    """Copies one minibatch into the plan's fixed staging buffers (H2D when the
+    source is host memory; pinned sources copy asynchronously)."""
+    x = torch.as_tensor(x)
+    y = torch.as_tensor(y)
+    self.x.copy_(x.reshape(self.batch, self.in_dim), non_blocking=True)
+    if self.labels is not None:
+      self.labels.copy_(y.reshape(self.batch), non_blocking=True)
+    else:
+      self.labels_f.copy_(y.reshape(self.batch, self.C), non_blocking=True)
+
+  # -- one step --------------------------------------------------------------
+  def _enqueue(self):
+    lib = self.lib
+    main = torch.cuda.current_stream(self.device)
+    sp = main.cuda_stream
+    for f in self.frozen:   # shared by every candidate ensemble on this GPU
+      f.forward(lib, self.x, sp)
+    if self.multi_stream:
+      for c, s in zip(self.candidates, self.streams):
+        s.wait_stream(main)
+        with torch.cuda.stream(s):
+          c.enqueue_train_step(self.x, self.labels, self.labels_f, self.step_dev, s.cuda_stream)
+      for s in self.streams:
+        main.wait_stream(s)
+    else:
+      for c in self.candidates:
+        c.enqueue_train_step(self.x, self.labels, self.labels_f, self.step_dev, sp)
+    _lib.check(lib.adn_counter_add(self.step_dev.data_ptr(), 1, sp), "adn_counter_add")
+
+  def train_step(self, x=None, y=None):
+    """One training step of every candidate on this GPU on one minibatch."""
+    if x is not None:
+      self.load_batch(x, y)
+    if not self.use_cuda_graph:
+      before = _lib.launch_count()
+      self._enqueue()
+      self.launches_per_step = _lib.launch_count() - before
+    else:
+      if self._graph is None:
+        before = _lib.launch_count()
+        g = torch.cuda.CUDAGraph()
+        # graph capture records the launches without running them: no state changes
+        with torch.cuda.graph(g):
+          self._enqueue()
+        self.launches_per_step = _lib.launch_count() - before
+        self._graph = g
+      self._graph.replay()
+    self.steps_done += 1
+
+  # -- read-back ---------------------------------------------------------------
+  def ema_losses(self) -> List[float]:
+    """EMA adanet loss of each local candidate (candidate.py:125-129), one D2H read."""
+    torch.cuda.current_stream(self.device).synchronize()
+    return [float(c.ema_state[2].item()) for c in self.candidates]
+
+  def traces(self) -> Dict[str, Dict[str, np.ndarray]]:
+    n = min(self.steps_done, self.trace_capacity)
+    out = {}
+    for c in self.candidates:
+      t = c.trace[:n].cpu().numpy()
+      out[c.name] = {f: t[:, i].copy() for i, f in enumerate(TRACE_FIELDS)}
+    return out
+
+  def last_losses(self) -> np.ndarray:
+    """[n_candidates, 4] (sub_loss, ens_loss, adanet_loss, ema) of the most recent step."""
+    row = (self.steps_done - 1) % self.trace_capacity
+    return torch.stack([c.trace[row] for c in self.candidates]).cpu().numpy()

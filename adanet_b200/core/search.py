@@ -1,0 +1,190 @@
+"""The AdaNet outer loop over the GPU iteration plan.
+
+Arithmetic/bookkeeping skeleton of `Estimator.train`
+(adanet/core/estimator.py:809-999) without the TF graph rebuilds: per
+iteration build the candidates' plans on the GPUs that own them, run
+`max_iteration_steps` steps, exchange the EMA losses, pick the best ensemble
+(adanet/core/estimator.py:1415-1517), freeze its new subnetwork and continue.
+`adanet_b200.Estimator` drives this class; `bench.py` and the parity tests use
+it directly.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from adanet_b200.core import engine as eng
+from adanet_b200.distributed import exchange as ex
+
+
+def select_best_index(losses: Sequence[float], iteration: int, force_grow: bool = False,
+                      replay_index: Optional[int] = None) -> int:
+  """Estimator._get_best_ensemble_index without an Evaluator
+  (adanet/core/estimator.py:1415-1517): replay override, single candidate -> 0,
+  force_grow with two candidates -> 1, else np.nanargmin over the EMA adanet
+  losses, dropping index 0 (the previous ensemble) under force_grow."""
+  if replay_index is not None:
+    return int(replay_index)
+  if len(losses) == 1:
+    return 0
+  if iteration > 0 and force_grow and len(losses) == 2:
+    return 1
+  arr = np.asarray(losses, dtype=np.float32)
+  if force_grow and iteration > 0:
+    return int(np.nanargmin(arr[1:])) + 1
+  return int(np.nanargmin(arr))
+
+
+def in_graph_best_index(losses: Sequence[float]) -> int:
+  """_IterationBuilder._best_candidate_index (adanet/core/iteration.py:1011-1046):
+  argmin with NaN mapped to -inf (a NaN candidate wins, surfacing the NaN)."""
+  arr = np.asarray(losses, dtype=np.float32).copy()
+  if arr.size == 1:
+    return 0
+  arr[np.isnan(arr)] = -np.inf
+  return int(np.argmin(arr))
+
+
+@dataclass
+class IterationReport:
+  iteration: int
+  candidate_names: List[str]          # [previous_ensemble?] + new candidates, reference order (iteration.py:603,725)
+  ema_losses: List[float]
+  best_index: int
+  architecture: List[Tuple[int, str]]  # winner's (iteration, builder name) list (architecture.py)
+  replay_indices: List[int]
+  mixture_weights: np.ndarray
+  bias: np.ndarray
+  steps: int
+  train_seconds: float                # device time of the train phase (CUDA events)
+  traces: Optional[Dict[str, Dict[str, np.ndarray]]] = None
+
+
+class AdaNetSearch:
+  """Runs AdaNet iterations on this process's GPU (rank r of G owns candidates i % G == r)."""
+
+  def __init__(self, search_space: Callable[[int, List[eng.DenseNet]], List[eng.SubnetworkPlanSpec]],
+               ensembler: eng.EnsemblerPlanSpec, in_dim: int, logits_dim: int, batch_size: int,
+               head: str = "softmax_xent", adanet_loss_decay: float = 0.9, force_grow: bool = False,
+               replay_indices: Optional[Sequence[int]] = None, device: Optional[torch.device] = None,
+               use_cuda_graph: bool = True, multi_stream: bool = True, keep_traces: bool = True,
+               trace_capacity: int = 4096):
+    self.search_space, self.ens = search_space, ensembler
+    self.in_dim, self.C, self.batch, self.head = in_dim, logits_dim, batch_size, head
+    self.decay, self.force_grow = adanet_loss_decay, force_grow
+    self.replay_indices = list(replay_indices) if replay_indices is not None else None
+    self.device = device or torch.device("cuda", torch.cuda.current_device())
+    self.use_cuda_graph, self.multi_stream = use_cuda_graph, multi_stream
+    self.keep_traces, self.trace_capacity = keep_traces, trace_capacity
+    self.frozen: List[eng.DenseNet] = []
+    self.iteration = 0
+    self.prev_best_ema: Optional[float] = None
+    self.architecture: List[Tuple[int, str]] = []
+    self.replay_trace: List[int] = []
+    self.mixture_weights: Optional[np.ndarray] = None
+    self.bias: Optional[np.ndarray] = None
+    self.reports: List[IterationReport] = []
+    self.plan: Optional[eng.IterationPlan] = None
+
+  # -- iteration assembly ------------------------------------------------------
+  def build_iteration(self) -> eng.IterationPlan:
+    specs = self.search_space(self.iteration, self.frozen)
+    names = [s.name for s in specs]
+    if len(set(names)) != len(names):
+      dup = [n for n in names if names.count(n) > 1][0]
+      raise ValueError("Two subnetworks have the same name '{}'".format(dup))   # iteration.py:621-623
+    if not specs:
+      raise ValueError("Each iteration must have at least one Builder.")      # iteration.py:564-565
+    self._specs = specs
+    g, r = ex.world(), ex.rank()
+    mine = ex.owned_indices(len(specs), r, g)
+    self.plan = eng.IterationPlan(self.iteration, [specs[i] for i in mine], self.frozen, self.ens, self.batch,
+                                  self.in_dim, self.C, self.head, self.decay, self.trace_capacity, self.device,
+                                  candidate_indices=mine, use_cuda_graph=self.use_cuda_graph,
+                                  multi_stream=self.multi_stream)
+    return self.plan
+
+  def train_iteration(self, batches: Iterator, steps: int) -> float:
+    """Runs `steps` training steps; returns device seconds (CUDA events) of the phase."""
+    plan = self.plan or self.build_iteration()
+    start = torch.cuda.Event(enable_timing=True)
+    end = torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+      x, y = next(batches)
+      plan.train_step(x, y)
+    end.record()
+    end.synchronize()
+    return start.elapsed_time(end) / 1e3
+
+  def finish_iteration(self, train_seconds: float = 0.0) -> IterationReport:
+    """Selection + growth (bookkeeping phase, estimator.py:1247-1283)."""
+    plan, specs, t = self.plan, self._specs, self.iteration
+    k = len(specs)
+    g = ex.world()
+    new_losses = ex.gather_candidate_losses(plan.ema_losses(), k, device=self.device)
+    ens_name = self.ens.name
+    names = ["t{}_{}_grow_{}".format(t, s.name, ens_name) for s in specs]
+    losses = list(new_losses)
+    if t > 0:
+      names = ["previous_ensemble"] + names
+      losses = [self.prev_best_ema] + losses
+    replay = None
+    if self.replay_indices is not None and t < len(self.replay_indices):
+      replay = self.replay_indices[t]
+    best = select_best_index(losses, t, self.force_grow, replay)
+    traces = plan.traces() if self.keep_traces else None
+    if t > 0 and best == 0:
+      pass   # previous ensemble kept; nothing grows
+    else:
+      ci = best - (1 if t > 0 else 0)
+      owner = ex.owner_of(ci, g)
+      spec = specs[ci]
+      # materialise the winner's subnetwork on every rank for frozen replay
+      if ex.rank() == owner:
+        cand = next(c for c in plan.candidates if c.index == ci)
+        member = cand.net
+        mix_w, bias = cand.mix_w, cand.bias
+      else:
+        member = eng.DenseNet(spec.name, spec.dims, spec.ws, spec.bs, spec.complexity, self.batch, self.device,
+                              t, spec.shared)
+        n_members = len(self.frozen) + 1
+        wshape = (n_members,) if self.ens.mixture_weight_type == "scalar" else (n_members, self.C)
+        mix_w = torch.empty(wshape, dtype=torch.float32, device=self.device)
+        bias = torch.empty((self.C,), dtype=torch.float32, device=self.device)
+      ex.broadcast_tensors(member.ws + member.bs + [mix_w, bias], src=owner)
+      self.frozen = self.frozen + [member]
+      self.architecture = self.architecture + [(t, spec.name)]
+      self.prev_best_ema = losses[best]
+      self.mixture_weights = mix_w.cpu().numpy().copy()
+      self.bias = bias.cpu().numpy().copy()
+    self.replay_trace = self.replay_trace + [best]
+    rep = IterationReport(t, names, [float(v) for v in losses], best, list(self.architecture),
+                          list(self.replay_trace), self.mixture_weights, self.bias, plan.steps_done,
+                          train_seconds, traces)
+    self.reports.append(rep)
+    self.iteration += 1
+    self.plan = None
+    return rep
+
+  def run(self, batches: Iterator, steps_per_iteration: int, iterations: int) -> List[IterationReport]:
+    for _ in range(iterations):
+      self.build_iteration()
+      secs = self.train_iteration(batches, steps_per_iteration)
+      self.finish_iteration(secs)
+    return self.reports
+
+
+def consecutive_batches(x_all, y_all, batch_size: int) -> Iterator:
+  """Consecutive slices in fixed order, wrapping at the end."""
+  n = x_all.shape[0]
+  cursor = 0
+  while True:
+    if cursor + batch_size > n:
+      cursor = 0
+    yield x_all[cursor:cursor + batch_size], y_all[cursor:cursor + batch_size]
+    cursor += batch_size

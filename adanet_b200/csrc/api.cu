@@ -1,0 +1,142 @@
+// C-ABI glue: error state, queries, dense path dispatch (SIMT fp32 vs tcgen05 3xTF32).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "dense_simt.cuh"
+#include "dense_tc.cuh"
+
+namespace adn {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+static std::atomic<int> g_path{ADN_PATH_AUTO};
+static std::atomic<int> g_sm_count{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  int v = g_sm_count.load();
+  if (v > 0) return v;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    n = 148;  // B200
+  }
+  g_sm_count.store(n);
+  return n;
+}
+
+int dense_path() {
+  static bool env_read = false;
+  if (!env_read) {
+    env_read = true;
+    const char* e = getenv("ADN_DENSE_PATH");
+    if (e) {
+      if (!strcmp(e, "simt")) g_path.store(ADN_PATH_SIMT);
+      else if (!strcmp(e, "tcgen05")) g_path.store(ADN_PATH_TCGEN05);
+      else if (!strcmp(e, "auto")) g_path.store(ADN_PATH_AUTO);
+    }
+  }
+  return g_path.load();
+}
+
+int64_t head_workspace_bytes_public(int64_t batch, int64_t dim, int64_t members);
+int heads_init();
+
+}  // namespace adn
+
+using namespace adn;
+
+extern "C" const char* adn_last_error(void) { return g_err; }
+
+extern "C" int adn_init(void) {
+  static std::atomic<int> done{0};
+  if (done.load()) return ADN_OK;
+  int rc = heads_init();
+  if (rc) return rc;
+  rc = tc::init();
+  if (rc) return rc;
+  (void)sm_count();
+  done.store(1);
+  return ADN_OK;
+}
+
+extern "C" int adn_set_dense_path(int path) {
+  if (path < ADN_PATH_AUTO || path > ADN_PATH_TCGEN05) return fail(ADN_ERR_INVALID, "adn_set_dense_path: bad path %d", path);
+  (void)dense_path();  // consume env first so an explicit call wins
+  g_path.store(path);
+  return ADN_OK;
+}
+
+static int pick_fwd_path(int64_t batch, int64_t in, int64_t out) {
+  const int p = dense_path();
+  if (p == ADN_PATH_SIMT) return ADN_PATH_SIMT;
+  return tc::fwd_supported(batch, in, out) ? ADN_PATH_TCGEN05 : (p == ADN_PATH_TCGEN05 ? -1 : ADN_PATH_SIMT);
+}
+
+static int pick_bwd_path(int64_t batch, int64_t in, int64_t out) {
+  const int p = dense_path();
+  if (p == ADN_PATH_SIMT) return ADN_PATH_SIMT;
+  return tc::bwd_supported(batch, in, out) ? ADN_PATH_TCGEN05 : (p == ADN_PATH_TCGEN05 ? -1 : ADN_PATH_SIMT);
+}
+
+extern "C" int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_host) {
+  if (!out_host) return fail(ADN_ERR_INVALID, "adn_query: null out");
+  switch (key) {
+    case ADN_Q_VERSION: *out_host = 100; return ADN_OK;
+    case ADN_Q_DENSE_BWD_WORKSPACE_BYTES: {
+      int64_t s = simt::dense_bwd_workspace_bytes(a, b, c);
+      int64_t t = tc::dense_bwd_workspace_bytes(a, b, c);
+      *out_host = s > t ? s : t;
+      return ADN_OK;
+    }
+    case ADN_Q_HEAD_WORKSPACE_BYTES: *out_host = head_workspace_bytes_public(a, b, c) + 256; return ADN_OK;
+    case ADN_Q_DENSE_FWD_PATH: *out_host = pick_fwd_path(a, b, c); return ADN_OK;
+    case ADN_Q_DENSE_BWD_PATH: *out_host = pick_bwd_path(a, b, c); return ADN_OK;
+    case ADN_Q_SM_COUNT: *out_host = sm_count(); return ADN_OK;
+    case ADN_Q_LAUNCH_COUNT: *out_host = g_launches.load(); return ADN_OK;
+    default: return fail(ADN_ERR_INVALID, "adn_query: unknown key %d", key);
+  }
+}
+
+extern "C" int adn_dense_fwd(const float* x, const float* w, const float* b, float* y, int64_t batch, int64_t in,
+                             int64_t out, int act, void* stream) {
+  if (!x || !w || !y) return fail(ADN_ERR_INVALID, "adn_dense_fwd: null pointer");
+  if (batch <= 0 || in <= 0 || out <= 0 || batch > INT32_MAX || in > INT32_MAX || out > INT32_MAX)
+    return fail(ADN_ERR_INVALID, "adn_dense_fwd: bad shape [%lld,%lld]x[%lld,%lld]", (long long)batch,
+                (long long)in, (long long)in, (long long)out);
+  if (act != ADN_ACT_NONE && act != ADN_ACT_RELU) return fail(ADN_ERR_INVALID, "adn_dense_fwd: bad act %d", act);
+  const int path = pick_fwd_path(batch, in, out);
+  if (path < 0)
+    return fail(ADN_ERR_UNSUPPORTED, "adn_dense_fwd: tcgen05 path forced but shape [%lld,%lld,%lld] unsupported",
+                (long long)batch, (long long)in, (long long)out);
+  if (path == ADN_PATH_TCGEN05) return tc::dense_fwd(x, w, b, y, batch, in, out, act, as_stream(stream));
+  return simt::dense_fwd(x, w, b, y, batch, in, out, act, as_stream(stream));
+}
+
+extern "C" int adn_dense_bwd(const float* x, const float* w, const float* dz, float* dx, float* dw, float* db,
+                             int64_t batch, int64_t in, int64_t out, int x_relu_mask, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  if (!x || !dz || !dw || !workspace) return fail(ADN_ERR_INVALID, "adn_dense_bwd: null pointer");
+  if (dx && !w) return fail(ADN_ERR_INVALID, "adn_dense_bwd: w required when dx requested");
+  if (batch <= 0 || in <= 0 || out <= 0 || batch > INT32_MAX || in > INT32_MAX || out > INT32_MAX)
+    return fail(ADN_ERR_INVALID, "adn_dense_bwd: bad shape");
+  const int path = pick_bwd_path(batch, in, out);
+  if (path < 0)
+    return fail(ADN_ERR_UNSUPPORTED, "adn_dense_bwd: tcgen05 path forced but shape [%lld,%lld,%lld] unsupported",
+                (long long)batch, (long long)in, (long long)out);
+  if (path == ADN_PATH_TCGEN05)
+    return tc::dense_bwd(x, w, dz, dx, dw, db, batch, in, out, x_relu_mask, workspace, workspace_bytes,
+                         as_stream(stream));
+  return simt::dense_bwd(x, w, dz, dx, dw, db, batch, in, out, x_relu_mask, workspace, workspace_bytes,
+                         as_stream(stream));
+}

@@ -1,0 +1,141 @@
+// Launchers for the CUDA-core fp32 dense path.  See dense_simt.cuh.
+#include "dense_simt.cuh"
+
+namespace adn {
+namespace simt {
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                       int64_t n, int S, int64_t stride) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += part[(size_t)s * stride + i];
+  out[i] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ dz, float* __restrict__ part, int rows, int N,
+                      int rows_per_slice) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
+  const int n = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_slice;
+  const int r1 = min(rows, r0 + rows_per_slice);
+  float acc = 0.f;
+  if (n < N)
+    for (int r = r0 + ry; r < r1; r += 8) acc += dz[(size_t)r * N + n];
+  sm[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    part[(size_t)blockIdx.y * N + n] = t;
+  }
+}
+
+// Tile configs: BIG for wide N, SKINNY for N <= 32 (logits layers).
+#define ADN_BIG 128, 128, 16, 8, 8
+#define ADN_SKINNY 128, 16, 16, 4, 2
+
+template <bool A_T, bool B_T, int EPI>
+static int launch_gemm(const GemmArgs& g, int splits, cudaStream_t st, const char* what) {
+  if (g.N <= 32) {
+    dim3 grid((unsigned)ceil_div(g.N, 16), (unsigned)ceil_div(g.M, 128), (unsigned)splits);
+    sgemm_kernel<ADN_SKINNY, A_T, B_T, EPI><<<grid, 256, 0, st>>>(g);
+  } else {
+    dim3 grid((unsigned)ceil_div(g.N, 128), (unsigned)ceil_div(g.M, 128), (unsigned)splits);
+    sgemm_kernel<ADN_BIG, A_T, B_T, EPI><<<grid, 256, 0, st>>>(g);
+  }
+  ADN_CHECK_LAUNCH(what);
+  return ADN_OK;
+}
+
+int dense_fwd(const float* x, const float* w, const float* b, float* y, int64_t batch, int64_t in,
+              int64_t out, int act, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = x; g.B = w; g.C = y;
+  g.M = (int)batch; g.N = (int)out; g.K = (int)in;
+  g.lda = (int)in; g.ldb = (int)out; g.ldc = (int)out;
+  g.bias = b; g.act = act;
+  return launch_gemm<false, false, EPI_BIAS_ACT>(g, 1, st, "simt dense_fwd");
+}
+
+int dw_splits(int64_t batch, int64_t in, int64_t out) {
+  int64_t bn = out <= 32 ? 16 : 128;
+  int64_t tiles = ceil_div(in, 128) * ceil_div(out, bn);
+  int64_t target = 2 * (int64_t)sm_count();
+  int64_t s = ceil_div(target, tiles);
+  int64_t max_s = ceil_div(batch, 256);
+  if (s > max_s) s = max_s;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+static const int kColsumRows = 512;
+
+static int64_t max_splits(int64_t batch) {
+  int64_t s = ceil_div(batch, 256);
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return s;
+}
+
+int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
+  // dW partials sized for the worst-case split count (64) so every dense path
+  // (SIMT or tcgen05) can share the buffer regardless of its own split choice.
+  int64_t s = max_splits(batch);
+  int64_t s2 = ceil_div(batch, kColsumRows);
+  return align_up((s * in * out + s2 * out) * (int64_t)sizeof(float), 256);
+}
+
+int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float* dw, float* db,
+              int64_t batch, int64_t in, int64_t out, int x_relu_mask, void* ws, int64_t ws_bytes,
+              cudaStream_t st) {
+  if (ws_bytes < dense_bwd_workspace_bytes(batch, in, out))
+    return fail(ADN_ERR_WORKSPACE, "dense_bwd: workspace %lld < %lld bytes", (long long)ws_bytes,
+                (long long)dense_bwd_workspace_bytes(batch, in, out));
+  float* wsf = reinterpret_cast<float*>(ws);
+  // ---- dW = x^T @ dz  (split-K over the batch, fixed-order reduction) ----
+  const int S = dw_splits(batch, in, out);
+  {
+    GemmArgs g{};
+    g.A = x; g.B = dz;
+    g.M = (int)in; g.N = (int)out; g.K = (int)batch;
+    g.lda = (int)in; g.ldb = (int)out; g.ldc = (int)out;
+    g.k_per_split = (int)align_up(ceil_div(batch, S), 16);
+    g.C = (S == 1) ? dw : wsf;
+    int rc = launch_gemm<true, false, EPI_PARTIAL>(g, S, st, "simt dense_bwd dW");
+    if (rc) return rc;
+    if (S > 1) {
+      int64_t n = in * out;
+      reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(wsf, dw, n, S, n);
+      ADN_CHECK_LAUNCH("simt dW reduce");
+    }
+  }
+  // ---- db = colsum(dz) ----
+  if (db) {
+    const int S2 = (int)ceil_div(batch, kColsumRows);
+    float* part = wsf + (size_t)max_splits(batch) * in * out;
+    dim3 grid((unsigned)ceil_div(out, 32), (unsigned)S2);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, part, (int)batch, (int)out, kColsumRows);
+    ADN_CHECK_LAUNCH("simt colsum");
+    reduce_partials_kernel<<<(unsigned)ceil_div(out, 256), 256, 0, st>>>(part, db, out, S2, out);
+    ADN_CHECK_LAUNCH("simt db reduce");
+  }
+  // ---- dx = (dz @ w^T) * relu_mask(x) ----
+  if (dx) {
+    GemmArgs g{};
+    g.A = dz; g.B = w; g.C = dx;
+    g.M = (int)batch; g.N = (int)in; g.K = (int)out;
+    g.lda = (int)out; g.ldb = (int)out; g.ldc = (int)in;
+    g.mask = x_relu_mask ? x : nullptr; g.ldmask = (int)in;
+    int rc = launch_gemm<false, true, EPI_MASK>(g, 1, st, "simt dense_bwd dX");
+    if (rc) return rc;
+  }
+  return ADN_OK;
+}
+
+}  // namespace simt
+}  // namespace adn

@@ -1,0 +1,394 @@
+// Fused AdaNet ensemble head (K4), plain head loss (K3), zero-debiased EMA (K6)
+// and L1 norm.  HBM-bound: every member-logit element is read from DRAM once
+// (pass 1), re-read from L2 for the mixture-weight gradient (pass 2), with
+// coalesced float4 loads over the flat [rows*dim] tile of each member.
+//
+// Reference arithmetic being replaced (file:line under /root/reference):
+//   weighted logits / sum    adanet/ensemble/weighted.py:433-453,545-561
+//   head loss                adanet/core/ensemble_builder.py:416-420,571-583
+//   complexity regulariser   adanet/ensemble/weighted.py:351-358,563-604
+//   adanet_loss              adanet/core/ensemble_builder.py:423-426
+//   mixture-weight gradient  adanet/ensemble/weighted.py:606-617
+//   EMA                      adanet/core/candidate.py:117-129
+#include "common.cuh"
+
+namespace adn {
+
+static constexpr int kRows = 128;       // rows (examples) per CTA == threads per CTA
+static constexpr int kMaxMembers = 64;
+static constexpr int kMaxDim = 64;
+
+struct HeadParams {
+  const float* members[kMaxMembers];
+  float gammas[kMaxMembers];
+  int n_members;
+  int head, mixture;
+  const float* w;        // SCALAR [N] / VECTOR [N,dim] / MATRIX l1 norms [N]; null => 1.0
+  const float* bias;     // [dim] or null
+  const int64_t* labels;
+  const float* labels_f;
+  float* dens;           // [B,dim] or null
+  float* ens_out;        // [B,dim] or null
+  float* part;           // workspace: per-CTA partials [n_cta][n_out]
+  int64_t batch;
+  int dim;
+  int n_out;             // 1 + dim + N*wdim
+  int want_grads;
+  int reg_is_zero;
+  float reg_multiplier;
+  float* out3;
+  float* dw;
+  float* dbias;
+};
+
+__device__ __forceinline__ float weight_of(const HeadParams& p, int k, int c) {
+  if (p.mixture == ADN_MIX_MATRIX || p.w == nullptr) return 1.f;
+  return p.mixture == ADN_MIX_SCALAR ? __ldg(p.w + k) : __ldg(p.w + (size_t)k * p.dim + c);
+}
+
+// smem layout (floats): ens[kRows*dim] | tile[kRows*dim] | red[kRows]
+__global__ void __launch_bounds__(kRows)
+ensemble_head_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = p.dim;
+  float* ens = smem;
+  float* tile = smem + kRows * C;
+  float* red = tile + kRows * C;
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * kRows;
+  const int rows = (int)min((int64_t)kRows, p.batch - r0);
+  const int valid = rows * C;           // flat elements of this CTA's tile
+  const size_t base = (size_t)r0 * C;
+  const int nvec = (kRows * C) / 4;     // kRows*C is a multiple of 4
+
+  // ---- pass 1: ens = bias + sum_k w_k (.) member_k   (flat, coalesced) ----
+  for (int i = tid; i < kRows * C; i += kRows) ens[i] = p.bias ? __ldg(p.bias + (i % C)) : 0.f;
+  // each thread only ever touches flat elements {4*(tid + j*kRows) .. +3}: no sync needed
+  __syncthreads();
+  for (int k = 0; k < p.n_members; ++k) {
+    const float* m = p.members[k] + base;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
+    for (int v = tid; v < nvec; v += kRows) {
+      const int i = v * 4;
+      if (i >= valid) break;
+      float x[4];
+      if (vec_ok && i + 3 < valid) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(m + i));
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = (i + q < valid) ? __ldg(m + i + q) : 0.f;
+      }
+      int c = i % C;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ens[i + q] += weight_of(p, k, c) * x[q];
+        c = (c + 1 == C) ? 0 : c + 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (p.ens_out) {
+    for (int i = tid; i < valid; i += kRows) p.ens_out[base + i] = ens[i];
+  }
+
+  // ---- per-row head: loss_r, g[r,:] = dLoss/d ens (overwrites ens in place) ----
+  float loss_r = 0.f;
+  if (tid < rows) {
+    float* e = ens + tid * C;
+    if (p.head == ADN_HEAD_SOFTMAX_XENT) {
+      const int y = (int)p.labels[r0 + tid];
+      float mx = e[0];
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, e[c]);
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += expf(e[c] - mx);
+      const float logs = logf(s);
+      loss_r = -((e[y] - mx) - logs);
+      const float inv = 1.f / s, invb = 1.f / (float)p.batch;
+      for (int c = 0; c < C; ++c) {
+        float pr = expf(e[c] - mx) * inv;
+        e[c] = (pr - (c == y ? 1.f : 0.f)) * invb;
+      }
+    } else if (p.head == ADN_HEAD_MSE) {
+      const float invn = 1.f / ((float)p.batch * (float)C);
+      for (int c = 0; c < C; ++c) {
+        float d = e[c] - p.labels_f[(size_t)(r0 + tid) * C + c];
+        loss_r += d * d;
+        e[c] = 2.f * d * invn;
+      }
+    } else {  // sigmoid cross-entropy, max(x,0) - x z + log1p(exp(-|x|))
+      const float invn = 1.f / ((float)p.batch * (float)C);
+      for (int c = 0; c < C; ++c) {
+        float x = e[c], z = p.labels_f[(size_t)(r0 + tid) * C + c];
+        loss_r += fmaxf(x, 0.f) - x * z + log1pf(expf(-fabsf(x)));
+        e[c] = (1.f / (1.f + expf(-x)) - z) * invn;
+      }
+    }
+  } else {
+    for (int c = 0; c < C; ++c) ens[tid * C + c] = 0.f;
+  }
+  red[tid] = loss_r;
+  __syncthreads();
+  float* part = p.part + (size_t)blockIdx.x * p.n_out;
+  if (tid == 0) {
+    float t = 0.f;
+    for (int r = 0; r < kRows; ++r) t += red[r];   // fixed order
+    part[0] = t;
+  }
+  if (p.dens) {
+    for (int i = tid; i < valid; i += kRows) p.dens[base + i] = ens[i];
+  }
+  if (!p.want_grads) return;
+
+  // ---- column sums of g -> dbias partial ----
+  if (tid < C) {
+    float t = 0.f;
+    for (int r = 0; r < kRows; ++r) t += ens[r * C + tid];
+    part[1 + tid] = t;
+  }
+  if (p.mixture == ADN_MIX_MATRIX) return;
+
+  // ---- pass 2: dw_k partials = sum_b g (.) member_k  (members re-read, L2-hot) ----
+  const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : C;
+  for (int k = 0; k < p.n_members; ++k) {
+    const float* m = p.members[k] + base;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
+    __syncthreads();   // previous column reduce finished reading tile
+    for (int v = tid; v < nvec; v += kRows) {
+      const int i = v * 4;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (i < valid) {
+        if (vec_ok && i + 3 < valid) {
+          float4 t = __ldg(reinterpret_cast<const float4*>(m + i));
+          x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[q] = (i + q < valid) ? __ldg(m + i + q) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tile[i + q] = ens[i + q] * x[q];
+    }
+    __syncthreads();
+    if (tid < C) {
+      float t = 0.f;
+      for (int r = 0; r < kRows; ++r) t += tile[r * C + tid];
+      red[tid] = t;
+    }
+    if (wdim == 1) {
+      __syncthreads();
+      if (tid == 0) {
+        float t = 0.f;
+        for (int c = 0; c < C; ++c) t += red[c];
+        part[1 + C + k] = t;
+      }
+    } else if (tid < C) {
+      part[1 + C + k * C + tid] = red[tid];
+    }
+  }
+}
+
+// Fixed-order reduction of the per-CTA partials + regulariser + adanet loss.
+__global__ void __launch_bounds__(256)
+ensemble_finalize_kernel(const __grid_constant__ HeadParams p, int n_cta) {
+  __shared__ float s_loss, s_reg;
+  const int C = p.dim;
+  const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : C;
+  const int n_w = (p.mixture == ADN_MIX_MATRIX) ? 0 : p.n_members * wdim;
+  const int n_red = p.want_grads ? (1 + C + n_w) : 1;
+  for (int j = threadIdx.x; j < n_red; j += blockDim.x) {
+    float t = 0.f;
+    for (int b = 0; b < n_cta; ++b) t += p.part[(size_t)b * p.n_out + j];
+    if (j == 0) {
+      float denom = (p.head == ADN_HEAD_SOFTMAX_XENT) ? (float)p.batch : (float)p.batch * (float)C;
+      s_loss = t / denom;
+    } else if (j < 1 + C) {
+      if (p.dbias) p.dbias[j - 1] = t;
+    } else if (p.dw) {
+      const int idx = j - 1 - C;
+      const int k = idx / wdim;
+      float g = t;
+      if (!p.reg_is_zero) {
+        const float w = p.w ? p.w[idx] : 1.f;
+        const float sgn = (w > 0.f) ? 1.f : ((w < 0.f) ? -1.f : 0.f);
+        g += p.reg_multiplier * p.gammas[k] * sgn;
+      }
+      p.dw[idx] = g;
+    }
+  }
+  if (threadIdx.x == 0) {
+    float reg = 0.f;
+    if (!p.reg_is_zero) {
+      for (int k = 0; k < p.n_members; ++k) {
+        float l1 = 0.f;
+        if (p.mixture == ADN_MIX_MATRIX) {
+          l1 = p.w[k];
+        } else if (p.w == nullptr) {
+          l1 = (float)wdim;
+        } else {
+          for (int c = 0; c < wdim; ++c) l1 += fabsf(p.w[k * wdim + c]);
+        }
+        reg += p.gammas[k] * l1;
+      }
+    }
+    s_reg = reg;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p.out3[0] = s_loss;
+    p.out3[1] = s_reg;
+    p.out3[2] = s_loss + s_reg;
+  }
+}
+
+__global__ void ema_update_kernel(float* state, const float* loss, float decay) {
+  // candidate.py:117-129 -> assign_moving_average(zero_debias=True) [TF]
+  float biased = state[0], n = state[1];
+  const float x = *loss;
+  biased = biased - (biased - x) * (1.f - decay);
+  n += 1.f;
+  const float factor = 1.f - powf(decay, n);
+  state[0] = biased;
+  state[1] = n;
+  state[2] = biased / factor;
+}
+
+__global__ void __launch_bounds__(1024) l1_norm_kernel(const float* x, int64_t n, float* out) {
+  __shared__ float sm[1024];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += fabsf(x[i]);
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+
+static int64_t head_workspace_bytes(int64_t batch, int64_t dim, int64_t members) {
+  int64_t n_cta = ceil_div(batch, kRows);
+  int64_t n_out = 1 + dim + members * dim;
+  return align_up(n_cta * n_out * (int64_t)sizeof(float), 256);
+}
+
+static int run_head(HeadParams& p, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (p.batch <= 0 || p.dim <= 0) return fail(ADN_ERR_INVALID, "head: empty batch/dim");
+  if (p.dim > kMaxDim) return fail(ADN_ERR_UNSUPPORTED, "head: dim %d > %d", p.dim, kMaxDim);
+  if (p.n_members < 1 || p.n_members > kMaxMembers)
+    return fail(ADN_ERR_UNSUPPORTED, "head: n_members %d not in [1,%d]", p.n_members, kMaxMembers);
+  if (p.head == ADN_HEAD_SOFTMAX_XENT ? p.labels == nullptr : p.labels_f == nullptr)
+    return fail(ADN_ERR_INVALID, "head: labels missing for head kind %d", p.head);
+  const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : p.dim;
+  p.n_out = 1 + p.dim + p.n_members * wdim;
+  if (ws_bytes < head_workspace_bytes(p.batch, p.dim, p.n_members))
+    return fail(ADN_ERR_WORKSPACE, "head: workspace %lld < %lld bytes", (long long)ws_bytes,
+                (long long)head_workspace_bytes(p.batch, p.dim, p.n_members));
+  p.part = reinterpret_cast<float*>(ws);
+  const int n_cta = (int)ceil_div(p.batch, kRows);
+  const size_t smem = (size_t)(2 * kRows * p.dim + kRows) * sizeof(float);
+  ensemble_head_kernel<<<n_cta, kRows, smem, st>>>(p);
+  ADN_CHECK_LAUNCH("ensemble_head");
+  ensemble_finalize_kernel<<<1, 256, 0, st>>>(p, n_cta);
+  ADN_CHECK_LAUNCH("ensemble_finalize");
+  return ADN_OK;
+}
+
+int heads_init() {
+  ADN_CUDA(cudaFuncSetAttribute(ensemble_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((2 * kRows * kMaxDim + kRows) * sizeof(float))));
+  return ADN_OK;
+}
+
+int64_t head_workspace_bytes_public(int64_t batch, int64_t dim, int64_t members) {
+  return head_workspace_bytes(batch, dim, members < 1 ? 1 : members);
+}
+
+}  // namespace adn
+
+using namespace adn;
+
+extern "C" int adn_head_loss(int head, const float* logits, const int64_t* labels, const float* labels_f,
+                             float* loss_out, float* dlogits, int64_t batch, int64_t dim,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!logits || !loss_out) return fail(ADN_ERR_INVALID, "adn_head_loss: null pointer");
+  if (head < 0 || head > 2) return fail(ADN_ERR_INVALID, "adn_head_loss: bad head %d", head);
+  // out3 needs 3 floats; the public contract is loss_out[0], so stage through workspace tail.
+  HeadParams p{};
+  p.members[0] = logits;
+  p.n_members = 1;
+  p.head = head;
+  p.mixture = ADN_MIX_SCALAR;
+  p.labels = labels;
+  p.labels_f = labels_f;
+  p.dens = dlogits;
+  p.batch = batch;
+  p.dim = (int)dim;
+  p.want_grads = 0;
+  p.reg_is_zero = 1;
+  const int64_t need = head_workspace_bytes_public(batch, dim, 1);
+  if (workspace_bytes < need + 16)
+    return fail(ADN_ERR_WORKSPACE, "adn_head_loss: workspace %lld < %lld bytes", (long long)workspace_bytes,
+                (long long)(need + 16));
+  float* out3 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + need);
+  p.out3 = out3;
+  int rc = run_head(p, workspace, need, as_stream(stream));
+  if (rc) return rc;
+  ADN_CUDA(cudaMemcpyAsync(loss_out, out3, sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return ADN_OK;
+}
+
+extern "C" int adn_ensemble_head(int head, int mixture_type, const float* const* members_host, int n_members,
+                                 const float* w, const float* bias, const float* gammas_host, int reg_is_zero,
+                                 float reg_multiplier, const int64_t* labels, const float* labels_f,
+                                 float* out3, float* dw, float* dbias, float* dens, float* ens_out,
+                                 int64_t batch, int64_t dim, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  if (!members_host || !out3) return fail(ADN_ERR_INVALID, "adn_ensemble_head: null pointer");
+  if (head < 0 || head > 2) return fail(ADN_ERR_INVALID, "adn_ensemble_head: bad head %d", head);
+  if (mixture_type < 0 || mixture_type > 2)
+    return fail(ADN_ERR_INVALID, "adn_ensemble_head: bad mixture type %d", mixture_type);
+  if (n_members < 1 || n_members > kMaxMembers)
+    return fail(ADN_ERR_UNSUPPORTED, "adn_ensemble_head: n_members %d not in [1,%d]", n_members, kMaxMembers);
+  if (mixture_type == ADN_MIX_MATRIX && dw)
+    return fail(ADN_ERR_INVALID, "adn_ensemble_head: dw must be NULL for MATRIX mixture weights");
+  if (!reg_is_zero && !gammas_host) return fail(ADN_ERR_INVALID, "adn_ensemble_head: gammas missing");
+  HeadParams p{};
+  for (int k = 0; k < n_members; ++k) {
+    if (!members_host[k]) return fail(ADN_ERR_INVALID, "adn_ensemble_head: member %d is null", k);
+    p.members[k] = members_host[k];
+    p.gammas[k] = gammas_host ? gammas_host[k] : 0.f;
+  }
+  p.n_members = n_members;
+  p.head = head;
+  p.mixture = mixture_type;
+  p.w = w;
+  p.bias = bias;
+  p.labels = labels;
+  p.labels_f = labels_f;
+  p.dens = dens;
+  p.ens_out = ens_out;
+  p.batch = batch;
+  p.dim = (int)dim;
+  p.want_grads = (dw || dbias) ? 1 : 0;
+  p.reg_is_zero = reg_is_zero;
+  p.reg_multiplier = reg_multiplier;
+  p.out3 = out3;
+  p.dw = dw;
+  p.dbias = dbias;
+  return run_head(p, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int adn_ema_update(float* state, const float* loss, float decay, void* stream) {
+  if (!state || !loss) return fail(ADN_ERR_INVALID, "adn_ema_update: null pointer");
+  ema_update_kernel<<<1, 1, 0, as_stream(stream)>>>(state, loss, decay);
+  ADN_CHECK_LAUNCH("ema_update");
+  return ADN_OK;
+}
+
+extern "C" int adn_l1_norm(const float* x, int64_t n, float* out, void* stream) {
+  if (!x || !out || n < 0) return fail(ADN_ERR_INVALID, "adn_l1_norm: bad argument");
+  l1_norm_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, out);
+  ADN_CHECK_LAUNCH("l1_norm");
+  return ADN_OK;
+}

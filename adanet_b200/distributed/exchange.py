@@ -1,0 +1,83 @@
+"""End-of-iteration exchange between GPU ranks.
+
+The reference synchronises workers through parameter servers and a shared
+`model_dir` (adanet/core/estimator.py:951-984, adanet/core/iteration.py:81-105)
+and has no collective at all.  On one NVSwitch box the only data that must
+cross GPUs is, once per AdaNet iteration:
+
+  1. the K candidates' EMA adanet losses  -> all_gather (K fp32) so every rank
+     computes the same nanargmin (adanet/core/estimator.py:1491-1495);
+  2. the winner's new parameters           -> broadcast from its owner rank,
+     replacing the reference's shared checkpoint (estimator.py:1357-1406).
+
+Both are microsecond-scale over NVLink; there is no data-path collective
+inside a training step.  The functions take plain torch tensors and a process
+group so the same code runs on NCCL (GPU) and gloo (CPU tests).
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> int:
+  return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+  return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def owner_of(candidate_index: int, world_size: int) -> int:
+  """Colocated placement: candidate i lives on rank i % G."""
+  return candidate_index % world_size
+
+
+def owned_indices(num_candidates: int, rank_: int, world_size: int) -> List[int]:
+  return [i for i in range(num_candidates) if owner_of(i, world_size) == rank_]
+
+
+def gather_candidate_losses(local_losses: Sequence[float], num_candidates: int, device=None, group=None) -> List[float]:
+  """all_gather of the per-candidate EMA losses, returned in candidate order.
+
+  local_losses[j] belongs to candidate owned_indices(...)[j].  Every rank pads
+  to ceil(K/G) slots with NaN, gathers, and un-interleaves.
+  """
+  g, r = world(), rank()
+  if g == 1:
+    return [float(v) for v in local_losses]
+  slots = (num_candidates + g - 1) // g
+  mine = torch.full((slots,), float("nan"), dtype=torch.float32, device=device)
+  for j, v in enumerate(local_losses):
+    mine[j] = float(v)
+  parts = [torch.empty_like(mine) for _ in range(g)]
+  dist.all_gather(parts, mine, group=group)   # ncclAllGather on GPU, gloo on CPU
+  out = torch.stack(parts).cpu()
+  return [float(out[owner_of(i, g), i // g]) for i in range(num_candidates)]
+
+
+def broadcast_tensors(tensors: Sequence[torch.Tensor], src: int, group=None) -> None:
+  """Broadcast the winner's parameters from its owner; one flat message."""
+  if world() == 1:
+    return
+  flat = torch.cat([t.reshape(-1) for t in tensors]) if rank() == src else \
+      torch.empty((sum(t.numel() for t in tensors),), dtype=tensors[0].dtype, device=tensors[0].device)
+  dist.broadcast(flat, src=src, group=group)
+  if rank() != src:
+    off = 0
+    for t in tensors:
+      n = t.numel()
+      t.copy_(flat[off:off + n].view_as(t))
+      off += n
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+  """Timing reduction used by bench.py (max over ranks of a device-measured time)."""
+  if world() == 1:
+    return float(value)
+  t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+  dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+  return float(t.item())

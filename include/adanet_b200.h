@@ -1,0 +1,183 @@
+/*
+ * adanet_b200.h -- C ABI of the B200-native AdaNet candidate-training engine.
+ *
+ * The reference (tensorflow/adanet v0.9.0) has NO FFI boundary: its hot path is
+ * Python that builds a TF1 graph, executed by TensorFlow's stock CPU kernels
+ * (SURVEY.md section 8b).  These entry points are therefore *new*; each one
+ * names the reference code whose per-step arithmetic it replaces
+ * (file:line relative to /root/reference).  INTEGRATION.md shows the ctypes
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     its name ends in _host; the caller (PyTorch) owns every buffer;
+ *   - all work is enqueued on the caller-supplied cudaStream_t (passed as
+ *     void*); no call synchronises the device or allocates device memory;
+ *   - all matrices are dense row-major fp32; labels are int64;
+ *   - returns 0 on success, negative errno-style code otherwise, and
+ *     adn_last_error() returns a thread-local human-readable message;
+ *   - re-entrant across streams; the only process-global state is a cache of
+ *     TMA descriptors / kernel attributes keyed by shape and pointer.
+ *   - reductions (loss means, bias/weight gradients) use a fixed summation
+ *     order: results are run-to-run deterministic.
+ */
+#ifndef ADANET_B200_H_
+#define ADANET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADN_OK 0
+#define ADN_ERR_INVALID (-22)     /* EINVAL: bad shape / null pointer / bad enum */
+#define ADN_ERR_CUDA (-5)         /* EIO: a CUDA runtime/driver call failed     */
+#define ADN_ERR_UNSUPPORTED (-95) /* EOPNOTSUPP: shape not supported by a path  */
+#define ADN_ERR_WORKSPACE (-12)   /* ENOMEM: caller workspace too small         */
+
+/* activation fused into adn_dense_fwd (simple_dnn.py:72-78 uses relu) */
+#define ADN_ACT_NONE 0
+#define ADN_ACT_RELU 1
+
+/* head / loss kinds  [TF heads called at adanet/core/ensemble_builder.py:571-583] */
+#define ADN_HEAD_SOFTMAX_XENT 0 /* MultiClassHead: mean sparse softmax-CE      */
+#define ADN_HEAD_MSE 1          /* RegressionHead: mean squared error          */
+#define ADN_HEAD_SIGMOID_XENT 2 /* BinaryClassHead: mean sigmoid-CE            */
+
+/* mixture weight types: adanet/ensemble/weighted.py:139-147 */
+#define ADN_MIX_SCALAR 0
+#define ADN_MIX_VECTOR 1
+#define ADN_MIX_MATRIX 2 /* members arrive already multiplied by their matrix */
+
+/* optimizers (TF1 update rules; call sites simple_dnn.py:110, weighted.py:616) */
+#define ADN_OPT_SGD 0
+#define ADN_OPT_MOMENTUM 1
+#define ADN_OPT_RMSPROP 2
+#define ADN_OPT_ADAM 3
+
+/* compute paths for the dense kernels (adn_set_dense_path / adn_query) */
+#define ADN_PATH_AUTO 0    /* tcgen05 3xTF32 where shapes allow, SIMT fp32 otherwise */
+#define ADN_PATH_SIMT 1    /* CUDA-core fp32 FMA everywhere                         */
+#define ADN_PATH_TCGEN05 2 /* force tensor path; unsupported shapes return an error  */
+
+/* adn_query keys */
+#define ADN_Q_VERSION 0
+#define ADN_Q_DENSE_BWD_WORKSPACE_BYTES 1 /* a=batch b=in c=out */
+#define ADN_Q_HEAD_WORKSPACE_BYTES 2      /* a=batch b=classes c=members */
+#define ADN_Q_DENSE_FWD_PATH 3            /* a=batch b=in c=out -> ADN_PATH_* that AUTO picks */
+#define ADN_Q_SM_COUNT 4
+#define ADN_Q_LAUNCH_COUNT 5              /* kernels launched by this library so far */
+#define ADN_Q_DENSE_BWD_PATH 6            /* a=batch b=in c=out */
+
+const char* adn_last_error(void);
+/* One-time, idempotent host-side initialisation (kernel attributes, driver entry
+ * points).  Must be called once outside any CUDA-graph capture; the Python
+ * binding does so when the library is loaded on a machine with a GPU. */
+int adn_init(void);
+int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_host);
+int adn_set_dense_path(int path);
+
+/*
+ * y[batch,out] = act(x[batch,in] @ w[in,out] + b[out])      (b may be NULL)
+ * Replaces tf.layers.dense + tf.nn.relu of
+ *   adanet/examples/simple_dnn.py:72-86 (_SimpleDNNBuilder.build_subnetwork),
+ * and the forward-only replay of frozen members,
+ *   adanet/core/estimator.py:1785-1882 / adanet/core/iteration.py:568-579.
+ */
+int adn_dense_fwd(const float* x, const float* w, const float* b, float* y,
+                  int64_t batch, int64_t in, int64_t out, int act, void* stream);
+
+/*
+ * Backward of one dense layer given dz = dLoss/d(pre-activation) [batch,out]:
+ *   dw[in,out] = x^T @ dz          db[out] = colsum(dz)
+ *   dx[batch,in] = (dz @ w^T) * (x_relu_mask ? (x > 0) : 1)   (skipped if dx NULL)
+ * With x_relu_mask=1, x is the ReLU output of the previous layer, so dx is that
+ * layer's dz directly.  Replaces the gradient half of optimizer.minimize(loss,
+ * var_list) at adanet/examples/simple_dnn.py:103-110 (var_list isolation:
+ * adanet/core/ensemble_builder.py:754,783).
+ * workspace: adn_query(ADN_Q_DENSE_BWD_WORKSPACE_BYTES) bytes, 16B aligned.
+ */
+int adn_dense_bwd(const float* x, const float* w, const float* dz,
+                  float* dx, float* dw, float* db,
+                  int64_t batch, int64_t in, int64_t out, int x_relu_mask,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Head loss on [batch,dim] logits: loss_out[0] = mean loss; dlogits (nullable)
+ * = dLoss/dlogits.  labels: int64[batch] class ids (softmax), or float
+ * [batch,dim] targets passed through labels_f (mse / sigmoid).
+ * Replaces head.create_estimator_spec(...).loss on subnetwork logits,
+ *   adanet/core/ensemble_builder.py:756-758 (+ :571-583).
+ * workspace: adn_query(ADN_Q_HEAD_WORKSPACE_BYTES, batch, dim, 1).
+ */
+int adn_head_loss(int head, const float* logits, const int64_t* labels, const float* labels_f,
+                  float* loss_out, float* dlogits, int64_t batch, int64_t dim,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Fused AdaNet ensemble head for one candidate ensemble of n_members:
+ *   ens[b,c]  = bias[c] + sum_k w_k (.) member_k[b,c]         weighted.py:433-453,545-561
+ *   loss      = head(ens, labels)                              ensemble_builder.py:416-420
+ *   reg       = sum_k gamma_k * ||w_k||_1                      weighted.py:563-604
+ *   adanet    = loss + reg                                     ensemble_builder.py:423-426
+ *   dw_k      = d(loss + reg_multiplier*reg)/dw_k, dbias       weighted.py:606-617
+ *               (reg_multiplier = 2 reproduces the reference's double-counted
+ *                regulariser on the Ensembler.build_train_op path; 1 = legacy path)
+ * members_host: host array of n_members device pointers to [batch,dim] logits.
+ * w: device [n_members] (SCALAR) or [n_members,dim] (VECTOR).  MATRIX: members
+ *    arrive pre-multiplied (last_layer_k @ W_k via adn_dense_fwd) and w is device
+ *    float[n_members] holding ||W_k||_1 (adn_l1_norm); dw must be NULL and the
+ *    caller forms dW_k = last_layer_k^T @ dens with adn_dense_bwd.
+ * gammas_host: host array of lambda*r(h_k)+beta.  reg_is_zero: lambda==beta==0.
+ * out3: device float[3] = {loss, reg, adanet_loss}.
+ * dw (nullable): same shape as w.  dbias (nullable): [dim].
+ * dens (nullable): [batch,dim] dLoss/d(ens) (needed for MATRIX weight grads).
+ * ens_out (nullable): [batch,dim] ensemble logits (predict / evaluate).
+ */
+int adn_ensemble_head(int head, int mixture_type, const float* const* members_host, int n_members,
+                      const float* w, const float* bias, const float* gammas_host, int reg_is_zero,
+                      float reg_multiplier, const int64_t* labels, const float* labels_f,
+                      float* out3, float* dw, float* dbias, float* dens, float* ens_out,
+                      int64_t batch, int64_t dim, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * TF1 optimizer update over n_tensors parameter tensors of one candidate.
+ * params/grads/slot0/slot1: host arrays of device pointers; sizes_host: element
+ * counts.  hyper_host: SGD {lr}; MOMENTUM {lr, momentum}; RMSPROP {lr, rho, mu,
+ * eps}; ADAM {lr, beta1, beta2, eps}.  step_dev (nullable; required for ADAM):
+ * device int64 count of updates already applied; the kernel uses *step_dev+1
+ * for Adam's bias correction and the call increments it afterwards on the same
+ * stream, so a captured CUDA graph replays correctly.  n_tensors <= 32.
+ * Replaces optimizer.minimize's apply half at
+ *   adanet/examples/simple_dnn.py:110 and adanet/ensemble/weighted.py:616.
+ */
+int adn_opt_step(int kind, float* const* params_host, const float* const* grads_host,
+                 float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
+                 int n_tensors, const float* hyper_host, int64_t* step_dev, void* stream);
+
+/* out[0] = sum_i |x[i]| over n elements (tf.norm(ord=1), weighted.py:573), fixed order. */
+int adn_l1_norm(const float* x, int64_t n, float* out, void* stream);
+
+/*
+ * Zero-debiased EMA of the AdaNet loss (adanet/core/candidate.py:117-129 ->
+ * assign_moving_average(zero_debias=True)).  state: device float[3] =
+ * {biased, n, value}; loss: device float*.
+ */
+int adn_ema_update(float* state, const float* loss, float decay, void* stream);
+
+/*
+ * Step bookkeeping that must live on the device so a whole training step can be
+ * captured in a CUDA graph (replaces the per-spec `step` variables and hooks of
+ * adanet/core/iteration.py:150-205,961-996):
+ *   adn_record_scalars: trace[(*step_dev % capacity)*stride + i] = *src_host[i], i < n (n <= 16)
+ *   adn_counter_add:    *counter_dev += delta
+ */
+int adn_record_scalars(const float* const* src_host, int n, float* trace, int64_t stride,
+                       const int64_t* step_dev, int64_t capacity, void* stream);
+int adn_counter_add(int64_t* counter_dev, int64_t delta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADANET_B200_H_ */

@@ -1,0 +1,82 @@
+"""Shared parity helpers: drive the CUDA path through the C ABI and the CPU oracle
+on the same seeded inputs.  Imported by tests/, __graft_entry__.smoke() and
+bench.py only (the oracle is test infrastructure)."""
+
+from __future__ import annotations
+
+import os
+import sys
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+from oracle import adanet_oracle as orc  # noqa: E402
+
+
+def dnn_dims(in_dim: int, width: int, depth: int, classes: int) -> List[int]:
+  return [in_dim] + [width] * depth + [classes]
+
+
+def make_specs(cfgs: Sequence[tuple], in_dim: int, classes: int, iteration: int, optimizer: tuple,
+               base_seed: int = 1000):
+  """cfgs: [(depth, width)] -> (oracle SubnetworkSpec list, engine SubnetworkPlanSpec list)
+  with identical injected glorot-uniform weights (seed = 1000 + 100*t + i)."""
+  from adanet_b200.core import engine as eng
+  o_specs, e_specs = [], []
+  names = set()
+  for i, (depth, width) in enumerate(cfgs):
+    dims = dnn_dims(in_dim, width, depth, classes)
+    ws, bs = orc.init_mlp(dims, base_seed + 100 * iteration + i)
+    name = orc.dnn_name(depth)
+    if name in names:
+      name = "{}_w{}".format(name, width)
+    names.add(name)
+    cx = float(np.sqrt(np.float32(depth)))   # simple_dnn.py:88-90
+    o_specs.append(orc.SubnetworkSpec(name, dims, cx, optimizer, ws=ws, bs=bs))
+    e_specs.append(eng.SubnetworkPlanSpec(name, dims, cx, optimizer, [w.copy() for w in ws], [b.copy() for b in bs],
+                                          shared={"num_layers": depth}))
+  return o_specs, e_specs
+
+
+def rel_err(a, b) -> float:
+  a = np.asarray(a, dtype=np.float64)
+  b = np.asarray(b, dtype=np.float64)
+  return float(np.abs(a - b).max() / max(1e-30, np.abs(b).max()))
+
+
+def run_smoke():
+  """One tiny AdaNet iteration step on cuda:0, checked against the oracle."""
+  import torch
+  from adanet_b200.core import engine as eng
+  from adanet_b200.core import search as srch
+  assert torch.cuda.is_available(), "smoke() needs a GPU"
+  torch.cuda.set_device(0)
+  B, D, C = 256, 100, 10
+  x, y = orc.make_tabular(B * 4, D, C, seed=77)
+  cfgs = [(1, 64), (2, 128)]
+  opt = ("sgd", 0.05)
+  ens_o = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+  ens_e = eng.EnsemblerPlanSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+
+  def o_space(t, frozen):
+    return make_specs(cfgs, D, C, t, opt)[0]
+
+  def e_space(t, frozen):
+    return make_specs(cfgs, D, C, t, opt)[1]
+
+  o_res, _ = orc.run_adanet(o_space, x, y, B, 4, 1, ens_o, C)
+  s = srch.AdaNetSearch(e_space, ens_e, D, C, B)
+  reps = s.run(srch.consecutive_batches(x, y, B), 4, 1)
+  for name, tr in o_res[0].traces.items():
+    got = reps[0].traces[name]
+    for f in ("sub_loss", "adanet_loss", "ema"):
+      want = np.asarray(tr[f], dtype=np.float64)
+      err = np.abs(got[f].astype(np.float64) - want).max()
+      assert err < 1e-5, "smoke parity %s/%s: max abs err %.3g" % (name, f, err)
+  assert reps[0].best_index == o_res[0].best_index
+  from adanet_b200 import _lib
+  assert _lib.launch_count() > 0

@@ -1,0 +1,74 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes exercise the end-of-iteration
+exchange (loss all_gather + winner broadcast) and the candidate sharding."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  p = s.getsockname()[1]
+  s.close()
+  return p
+
+
+def _worker(rank, world, port, k, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from adanet_b200.core import search as srch
+    from adanet_b200.distributed import exchange as ex
+    mine = ex.owned_indices(k, rank, world)
+    # each rank reports loss = 1 / (1 + candidate index); candidate 3 diverged (NaN)
+    local = [float("nan") if i == 3 else 1.0 / (1 + i) for i in mine]
+    losses = ex.gather_candidate_losses(local, k)
+    best = srch.select_best_index(losses, 0)
+    # winner broadcast: the owner holds the real parameters
+    owner = ex.owner_of(best, world)
+    params = [torch.full((4, 3), float(best + 1)) if rank == owner else torch.zeros((4, 3)),
+              torch.arange(5, dtype=torch.float32) * (best + 1) if rank == owner else torch.zeros(5)]
+    ex.broadcast_tensors(params, src=owner)
+    t = ex.max_over_ranks(10.0 + rank)
+    q.put((rank, mine, losses, best, [p.numpy().copy() for p in params], t))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k", [5, 8])
+def test_exchange_world2_gloo(k):
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, k, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  out = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+  for p in procs:
+    p.join(60)
+    assert p.exitcode == 0
+  (r0, mine0, l0, b0, p0, t0), (r1, mine1, l1, b1, p1, t1) = out
+  assert mine0 == list(range(0, k, 2)) and mine1 == list(range(1, k, 2))
+  want = [float("nan") if i == 3 else 1.0 / (1 + i) for i in range(k)]
+  np.testing.assert_allclose(l0, want, equal_nan=True, rtol=1e-6)
+  np.testing.assert_allclose(l1, want, equal_nan=True, rtol=1e-6)
+  assert b0 == b1 == k - 1           # smallest loss = last candidate; the NaN one never wins
+  for a, b in zip(p0, p1):
+    np.testing.assert_array_equal(a, b)
+  assert float(p0[0][0, 0]) == k
+  assert t0 == t1 == 11.0
+
+
+def test_single_process_passthrough():
+  from adanet_b200.distributed import exchange as ex
+  assert ex.world() == 1 and ex.rank() == 0
+  assert ex.gather_candidate_losses([0.3, 0.1], 2) == [pytest.approx(0.3), pytest.approx(0.1)]
+  ex.broadcast_tensors([torch.zeros(3)], src=0)
+  assert ex.max_over_ranks(2.5) == 2.5

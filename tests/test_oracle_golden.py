@@ -1,0 +1,202 @@
+"""Pins the CPU oracle against the reference's own known-answer tests and against
+fixtures produced by executing the reference's TF-free modules
+(tests/golden/make_golden.py).  CPU only."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import adanet_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+  with open(os.path.join(GOLD, name)) as f:
+    return json.load(f)
+
+
+KNOWN = _load("known_answers.json")
+
+
+def test_ema_matches_candidate_test():
+  # adanet/core/candidate_test.py:83-132: losses 1, .5, .25 with decay .999 -> [1., .750, .583]
+  k = KNOWN["ema"]
+  ema = orc.ZeroDebiasEMA(k["decay"])
+  assert float(ema.value) == k["eval_mode_want"]      # never-updated variable reads 0 (eval mode)
+  got = [float(ema.update(l)) for l in k["losses"]]
+  np.testing.assert_allclose(got, k["want"], atol=10 ** -k["places"])
+
+
+@pytest.mark.parametrize("case", KNOWN["complexity_regularization"]["cases"], ids=lambda c: c["name"])
+def test_complexity_regularization_matches_weighted_test(case):
+  # adanet/ensemble/weighted_test.py:147-481
+  cx = KNOWN["complexity_regularization"]["complexity"]
+  ws = [np.float32(w) for w in case["weights"]]
+  reg = orc.complexity_regularization(ws, [cx] * len(ws), case["lambda"], case["beta"])
+  assert abs(float(reg) - case["want"]) < 1e-6
+  norms, fracs = orc.mixture_weight_norms(ws)
+  np.testing.assert_allclose(norms, case["norms"], atol=1e-6)
+  np.testing.assert_allclose(fracs, case["fractions"], atol=1e-6)
+
+
+def test_default_mixture_weights_are_uniform():
+  # weighted.py:360-366: SCALAR/VECTOR -> 1/N, MATRIX -> zeros
+  for n in (1, 2, 3, 4):
+    assert float(orc.default_mixture_weight(orc.SCALAR, n, 7, 3)) == pytest.approx(1.0 / n)
+    np.testing.assert_allclose(orc.default_mixture_weight(orc.VECTOR, n, 7, 3), np.full(3, 1.0 / n, np.float32))
+  assert not orc.default_mixture_weight(orc.MATRIX, 2, 7, 3).any()
+
+
+def test_mixture_weight_sgd_step():
+  # adanet/ensemble/weighted_test.py:588-627: SGD(.1) on loss = 2*w from w=0 -> -0.2
+  k = KNOWN["mixture_weight_sgd"]
+  w = [np.array(k["w0"], dtype=np.float32)]
+  orc.SGD(k["lr"]).apply(w, [np.array(2.0, dtype=np.float32)])
+  assert float(w[0]) == pytest.approx(k["want_w"])
+
+
+def test_simple_dnn_names_and_complexities():
+  # adanet/examples/simple_dnn_test.py:54-81
+  k = KNOWN["simple_dnn_names"]
+  for init, key in ((0, "initial_num_layers_0"), (1, "initial_num_layers_1")):
+    names = [orc.dnn_name(init), orc.dnn_name(init + 1)]
+    cx = [float(np.sqrt(np.float32(init))), float(np.sqrt(np.float32(init + 1)))]
+    assert names == k[key]["names"]
+    np.testing.assert_allclose(cx, k[key]["complexities"], atol=1e-3)
+
+
+def test_softmax_xent_against_fp64_restatement():
+  # multi-class head is unpinned by the reference: pin against an fp64 restatement of
+  # TF's sparse_softmax_cross_entropy_with_logits + mean, and against torch's cross_entropy.
+  rng = np.random.default_rng(0)
+  logits = (rng.standard_normal((64, 10)) * 3).astype(np.float32)
+  labels = rng.integers(0, 10, size=(64, 1))
+  loss, g = orc.softmax_xent_mean(logits, labels)
+  l64 = logits.astype(np.float64)
+  lse = np.log(np.exp(l64 - l64.max(1, keepdims=True)).sum(1)) + l64.max(1)
+  want = float((lse - l64[np.arange(64), labels[:, 0]]).mean())
+  assert abs(float(loss) - want) < 1e-6
+  import torch
+  tl = torch.tensor(l64, requires_grad=True)
+  tloss = torch.nn.functional.cross_entropy(tl, torch.tensor(labels[:, 0]), reduction="mean")
+  tloss.backward()
+  assert abs(float(loss) - float(tloss)) < 1e-6
+  np.testing.assert_allclose(g, tl.grad.numpy(), atol=1e-7)
+
+
+def test_regression_and_binary_heads():
+  rng = np.random.default_rng(1)
+  x = rng.standard_normal((32, 1)).astype(np.float32)
+  y = rng.standard_normal((32, 1)).astype(np.float32)
+  loss, g = orc.mse_mean(x, y)
+  assert float(loss) == pytest.approx(float(((x - y) ** 2).mean()), rel=1e-6)
+  np.testing.assert_allclose(g, 2 * (x - y) / 32, rtol=1e-6)
+  z = (rng.random((32, 1)) > 0.5).astype(np.float32)
+  loss, g = orc.sigmoid_xent_mean(x, z)
+  import torch
+  want = torch.nn.functional.binary_cross_entropy_with_logits(torch.tensor(x, dtype=torch.float64),
+                                                              torch.tensor(z, dtype=torch.float64))
+  assert float(loss) == pytest.approx(float(want), rel=1e-6)
+
+
+def test_backward_matches_torch_autograd():
+  import torch
+  dims = [20, 16, 16, 5]
+  ws, bs = orc.init_mlp(dims, 3)
+  rng = np.random.default_rng(2)
+  x = rng.standard_normal((12, 20)).astype(np.float32)
+  y = rng.integers(0, 5, 12)
+  acts = orc.mlp_forward(ws, bs, x)
+  loss, dl = orc.softmax_xent_mean(acts[-1], y)
+  dws, dbs = orc.mlp_backward(ws, acts, dl)
+  tw = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in ws]
+  tb = [torch.tensor(b, dtype=torch.float64, requires_grad=True) for b in bs]
+  h = torch.tensor(x, dtype=torch.float64)
+  for i in range(3):
+    h = h @ tw[i] + tb[i]
+    if i < 2:
+      h = torch.relu(h)
+  torch.nn.functional.cross_entropy(h, torch.tensor(y)).backward()
+  for a, b in zip(dws, tw):
+    np.testing.assert_allclose(a, b.grad.numpy(), atol=2e-6)
+  for a, b in zip(dbs, tb):
+    np.testing.assert_allclose(a, b.grad.numpy(), atol=2e-6)
+
+
+def test_tf1_optimizer_rules():
+  p = [np.array([1.0, -2.0], dtype=np.float32)]
+  g = [np.array([0.5, 0.25], dtype=np.float32)]
+  m = orc.Momentum(0.1, 0.9)
+  m.apply(p, g)
+  np.testing.assert_allclose(p[0], [0.95, -2.025], rtol=1e-6)
+  m.apply(p, g)   # acc = .9*.5+.5 = .95
+  np.testing.assert_allclose(p[0], [0.95 - 0.095, -2.025 - 0.0475], rtol=1e-6)
+  p = [np.array([1.0], dtype=np.float32)]
+  r = orc.RMSProp(0.1)    # ms starts at 1: ms = .9 + .1*g^2
+  r.apply(p, [np.array([2.0], dtype=np.float32)])
+  assert float(p[0][0]) == pytest.approx(1.0 - 0.1 * 2.0 / np.sqrt(0.9 + 0.1 * 4.0 + 1e-10), rel=1e-6)
+  p = [np.array([1.0], dtype=np.float32)]
+  a = orc.Adam(0.001)
+  a.apply(p, [np.array([3.0], dtype=np.float32)])   # first Adam step moves by ~lr
+  assert float(p[0][0]) == pytest.approx(1.0 - 0.001, abs=1e-6)
+
+
+def test_ensemble_gradient_double_counts_regulariser():
+  # weighted.py:616-617 adds complexity_regularization to an already regularised loss
+  rng = np.random.default_rng(5)
+  m = [rng.standard_normal((8, 3)).astype(np.float32) for _ in range(2)]
+  y = rng.integers(0, 3, 8)
+  w = [np.float32(0.5), np.float32(0.5)]
+  bias = np.zeros(3, np.float32)
+  ens = orc.ensemble_logits(orc.SCALAR, w, bias, m, None)
+  _, g = orc.softmax_xent_mean(ens, y)
+  d2, _ = orc.ensemble_grads(orc.SCALAR, w, [1.0, 2.0], 0.1, 0.01, 2.0, g, m, None, False)
+  d1, _ = orc.ensemble_grads(orc.SCALAR, w, [1.0, 2.0], 0.1, 0.01, 1.0, g, m, None, False)
+  np.testing.assert_allclose([float(a - b) for a, b in zip(d2, d1)], [0.11, 0.21], rtol=1e-5)
+
+
+def test_selection_rules():
+  # adanet/core/estimator.py:1415-1517
+  assert orc.select_best([0.3], 0) == 0
+  assert orc.select_best([0.3, 0.2, 0.25], 0) == 1
+  assert orc.select_best([0.1, 0.2, 0.25], 1) == 0                      # previous ensemble kept
+  assert orc.select_best([0.1, 0.2, 0.25], 1, force_grow=True) == 1     # index 0 dropped
+  assert orc.select_best([0.1, 0.5], 1, force_grow=True) == 1
+  assert orc.select_best([0.1, float("nan"), 0.05], 0) == 2             # nanargmin
+  assert orc.select_best([0.1, 0.2], 3, replay_index=1) == 1
+  assert orc.in_graph_best_index([0.1, float("nan"), 0.05]) == 1        # NaN -> -inf wins in-graph
+  for idx in KNOWN["replay"]["indices"]:
+    assert orc.select_best([0.0, 1.0, 2.0, 3.0], 1, replay_index=idx) == idx
+
+
+def test_identical_candidates_tie_to_first():
+  # estimator_test.py:3002-3078 relies on "identical candidates tie": nanargmin returns the first minimum
+  assert orc.select_best([0.5, 0.5, 0.5], 0) == 0
+
+
+def test_run_adanet_small_end_to_end():
+  x, y = orc.make_tabular(512, 20, 4, seed=9)
+
+  def space(t, frozen):
+    depth = 1 if not frozen else len(frozen[-1].ws) - 1
+    out = []
+    for i, d in enumerate((depth, depth + 1)):
+      dims = [20] + [16] * d + [4]
+      out.append(orc.SubnetworkSpec(orc.dnn_name(d), dims, float(np.sqrt(d)), ("sgd", 0.05), seed=10 * t + i))
+    return out
+
+  ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+  res, frozen = orc.run_adanet(space, x, y, 64, 20, 3, ens, 4)
+  assert len(res) == 3
+  assert res[0].candidate_names == ["t0_1_layer_dnn_grow_complexity_regularized",
+                                    "t0_2_layer_dnn_grow_complexity_regularized"]
+  assert res[1].candidate_names[0] == "previous_ensemble"
+  assert len(frozen) == len(res[-1].architecture)
+  for r in res:
+    assert np.isfinite(r.ema_losses).all()
+  # loss decreases within the first iteration
+  tr = res[0].traces[res[0].candidate_names[0]]["sub_loss"]
+  assert tr[-1] < tr[0]
