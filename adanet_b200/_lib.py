@@ -21,7 +21,8 @@ HEAD_SOFTMAX_XENT, HEAD_MSE, HEAD_SIGMOID_XENT = 0, 1, 2
 MIX_SCALAR, MIX_VECTOR, MIX_MATRIX = 0, 1, 2
 OPT_SGD, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADAM = 0, 1, 2, 3
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
-Q_VERSION, Q_DENSE_BWD_WS, Q_HEAD_WS, Q_DENSE_FWD_PATH, Q_SM_COUNT, Q_LAUNCH_COUNT, Q_DENSE_BWD_PATH = range(7)
+(Q_VERSION, Q_DENSE_BWD_WS, Q_HEAD_WS, Q_DENSE_FWD_PATH, Q_SM_COUNT, Q_LAUNCH_COUNT, Q_DENSE_BWD_PATH,
+ Q_DENSE_FWD_WS) = range(8)
 
 EXPORTS = (
     "adn_last_error", "adn_init", "adn_query", "adn_set_dense_path", "adn_dense_fwd", "adn_dense_bwd", "adn_head_loss",
@@ -53,7 +54,7 @@ def load():
   lib.adn_init.argtypes = []
   lib.adn_query.argtypes = [c_int, i64, i64, i64, POINTER(i64)]
   lib.adn_set_dense_path.argtypes = [c_int]
-  lib.adn_dense_fwd.argtypes = [p, p, p, p, i64, i64, i64, c_int, p]
+  lib.adn_dense_fwd.argtypes = [p, p, p, p, i64, i64, i64, c_int, p, i64, p]
   lib.adn_dense_bwd.argtypes = [p, p, p, p, p, p, i64, i64, i64, c_int, p, i64, p]
   lib.adn_head_loss.argtypes = [c_int, p, p, p, p, p, i64, i64, p, i64, p]
   lib.adn_ensemble_head.argtypes = [c_int, c_int, POINTER(p), c_int, p, p, POINTER(f32), c_int, f32, p, p,

@@ -140,6 +140,9 @@ class DenseNet:
       if tuple(w.shape) != (dims[i], dims[i + 1]):
         raise ValueError("kernel %d of %s has shape %s, want %s" % (i, name, tuple(w.shape), (dims[i], dims[i + 1])))
     self.acts = [torch.empty((batch, d), dtype=torch.float32, device=device) for d in dims[1:]]
+    fwd_ws = max(_lib.query(_lib.Q_DENSE_FWD_WS, batch, dims[i], dims[i + 1]) for i in range(len(dims) - 1))
+    self.fwd_ws_bytes = fwd_ws
+    self.fwd_ws = torch.empty((max(fwd_ws, 16),), dtype=torch.uint8, device=device)
 
   @property
   def logits(self) -> torch.Tensor:
@@ -155,7 +158,8 @@ class DenseNet:
     for i in range(n):
       act = _lib.ACT_RELU if i < n - 1 else _lib.ACT_NONE
       _lib.check(lib.adn_dense_fwd(h.data_ptr(), self.ws[i].data_ptr(), self.bs[i].data_ptr(),
-                                   self.acts[i].data_ptr(), self.batch, self.dims[i], self.dims[i + 1], act, sp),
+                                   self.acts[i].data_ptr(), self.batch, self.dims[i], self.dims[i + 1], act,
+                                   self.fwd_ws.data_ptr(), self.fwd_ws_bytes, sp),
                  "adn_dense_fwd")
       h = self.acts[i]
 

@@ -99,6 +99,9 @@ extern "C" int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_
       *out_host = s > t ? s : t;
       return ADN_OK;
     }
+    case ADN_Q_DENSE_FWD_WORKSPACE_BYTES:
+      *out_host = (pick_fwd_path(a, b, c) == ADN_PATH_TCGEN05) ? tc::dense_fwd_workspace_bytes(a, b, c) : 0;
+      return ADN_OK;
     case ADN_Q_HEAD_WORKSPACE_BYTES: *out_host = head_workspace_bytes_public(a, b, c) + 256; return ADN_OK;
     case ADN_Q_DENSE_FWD_PATH: *out_host = pick_fwd_path(a, b, c); return ADN_OK;
     case ADN_Q_DENSE_BWD_PATH: *out_host = pick_bwd_path(a, b, c); return ADN_OK;
@@ -109,7 +112,7 @@ extern "C" int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_
 }
 
 extern "C" int adn_dense_fwd(const float* x, const float* w, const float* b, float* y, int64_t batch, int64_t in,
-                             int64_t out, int act, void* stream) {
+                             int64_t out, int act, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!x || !w || !y) return fail(ADN_ERR_INVALID, "adn_dense_fwd: null pointer");
   if (batch <= 0 || in <= 0 || out <= 0 || batch > INT32_MAX || in > INT32_MAX || out > INT32_MAX)
     return fail(ADN_ERR_INVALID, "adn_dense_fwd: bad shape [%lld,%lld]x[%lld,%lld]", (long long)batch,
@@ -119,7 +122,8 @@ extern "C" int adn_dense_fwd(const float* x, const float* w, const float* b, flo
   if (path < 0)
     return fail(ADN_ERR_UNSUPPORTED, "adn_dense_fwd: tcgen05 path forced but shape [%lld,%lld,%lld] unsupported",
                 (long long)batch, (long long)in, (long long)out);
-  if (path == ADN_PATH_TCGEN05) return tc::dense_fwd(x, w, b, y, batch, in, out, act, as_stream(stream));
+  if (path == ADN_PATH_TCGEN05)
+    return tc::dense_fwd(x, w, b, y, batch, in, out, act, workspace, workspace_bytes, as_stream(stream));
   return simt::dense_fwd(x, w, b, y, batch, in, out, act, as_stream(stream));
 }
 

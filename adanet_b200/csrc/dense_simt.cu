@@ -4,7 +4,7 @@
 namespace adn {
 namespace simt {
 
-__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
+static __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
                                        int64_t n, int S, int64_t stride) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -13,7 +13,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __
   out[i] = acc;
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ dz, float* __restrict__ part, int rows, int N,
                       int rows_per_slice) {
   __shared__ float sm[8][33];
@@ -32,6 +32,22 @@ colsum_partial_kernel(const float* __restrict__ dz, float* __restrict__ part, in
     for (int i = 0; i < 8; ++i) t += sm[i][cx];
     part[(size_t)blockIdx.y * N + n] = t;
   }
+}
+
+static const int kColsumRows = 512;
+
+int reduce_partials(const float* part, float* out, int64_t n, int S, int64_t stride, cudaStream_t st) {
+  reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(part, out, n, S, stride);
+  ADN_CHECK_LAUNCH("reduce_partials");
+  return ADN_OK;
+}
+
+int colsum(const float* dz, float* db, int64_t rows, int64_t N, float* part, cudaStream_t st) {
+  const int S2 = (int)ceil_div(rows, kColsumRows);
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)S2);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, part, (int)rows, (int)N, kColsumRows);
+  ADN_CHECK_LAUNCH("colsum");
+  return reduce_partials(part, db, N, S2, N, st);
 }
 
 // Tile configs: BIG for wide N, SKINNY for N <= 32 (logits layers).
@@ -73,8 +89,6 @@ int dw_splits(int64_t batch, int64_t in, int64_t out) {
   return (int)s;
 }
 
-static const int kColsumRows = 512;
-
 static int64_t max_splits(int64_t batch) {
   int64_t s = ceil_div(batch, 256);
   if (s > 64) s = 64;
@@ -108,21 +122,13 @@ int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float*
     g.C = (S == 1) ? dw : wsf;
     int rc = launch_gemm<true, false, EPI_PARTIAL>(g, S, st, "simt dense_bwd dW");
     if (rc) return rc;
-    if (S > 1) {
-      int64_t n = in * out;
-      reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(wsf, dw, n, S, n);
-      ADN_CHECK_LAUNCH("simt dW reduce");
-    }
+    if (S > 1 && (rc = reduce_partials(wsf, dw, in * out, S, in * out, st))) return rc;
   }
   // ---- db = colsum(dz) ----
   if (db) {
-    const int S2 = (int)ceil_div(batch, kColsumRows);
     float* part = wsf + (size_t)max_splits(batch) * in * out;
-    dim3 grid((unsigned)ceil_div(out, 32), (unsigned)S2);
-    colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, part, (int)batch, (int)out, kColsumRows);
-    ADN_CHECK_LAUNCH("simt colsum");
-    reduce_partials_kernel<<<(unsigned)ceil_div(out, 256), 256, 0, st>>>(part, db, out, S2, out);
-    ADN_CHECK_LAUNCH("simt db reduce");
+    int rc = colsum(dz, db, batch, out, part, st);
+    if (rc) return rc;
   }
   // ---- dx = (dz @ w^T) * relu_mask(x) ----
   if (dx) {

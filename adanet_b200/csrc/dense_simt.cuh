@@ -142,12 +142,9 @@ sgemm_kernel(GemmArgs g) {
 }
 
 // out[i] = sum_{s<S} part[s*stride + i]   (fixed order -> deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                       int64_t n, int S, int64_t stride);
-
-// part[s*N + n] = sum over rows of slice s of dz[row*N + n]   (fixed order)
-__global__ void colsum_partial_kernel(const float* __restrict__ dz, float* __restrict__ part,
-                                      int rows, int N, int rows_per_slice);
+int reduce_partials(const float* part, float* out, int64_t n, int S, int64_t stride, cudaStream_t st);
+// db[n] = sum_rows dz[row*N + n] via fixed-order partials in `part` (ceil(rows/512)*N floats)
+int colsum(const float* dz, float* db, int64_t rows, int64_t N, float* part, cudaStream_t st);
 
 int dense_fwd(const float* x, const float* w, const float* b, float* y, int64_t batch, int64_t in,
               int64_t out, int act, cudaStream_t st);

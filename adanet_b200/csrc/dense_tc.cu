@@ -1,18 +1,568 @@
-// placeholder until the tcgen05 kernels land (next commit): nothing is supported,
-// so ADN_PATH_AUTO resolves to the SIMT fp32 path for every shape.
+// tcgen05 dense path: fp32-accurate GEMM on the 5th-gen tensor cores via a
+// 3xTF32 split, TMA-fed, accumulators in TMEM.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T      (both operands K-major, fp32)
+//   a = a_hi + a_lo,  a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi)   (same for b)
+//   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi      (dropped a_lo*b_lo ~ 2^-22 |ab|)
+//
+// Pipeline per GEMM (warp-specialised, one 128x128 output tile per CTA):
+//   warp 0  TMA producer : 4 tiles/stage (A_hi, A_lo, B_hi, B_lo; 128 rows x 32 fp32,
+//                          SWIZZLE_128B) into a 3-stage smem ring, mbarrier expect_tx
+//   warp 1  MMA issuer   : 12 x tcgen05.mma.kind::tf32 (M128 N128 K8) per stage into a
+//                          128-column fp32 TMEM accumulator; tcgen05.commit frees the stage
+//   warps 2-5 epilogue   : tcgen05.ld (32 lanes x 32 columns) -> bias/ReLU | ReLU-mask |
+//                          split-K partial -> float4 global stores
+// The hi/lo planes are produced by a pre-pass (split / split+transpose kernels below),
+// which also zero-pads K to a multiple of 32 and lays every operand out K-major so only
+// the best-trodden UMMA descriptor form (K-major, SWIZZLE_128B) is used.
+//
+// Reference arithmetic being replaced: tf.layers.dense / tf.matmul and their gradients,
+//   adanet/examples/simple_dnn.py:72-86,103-110.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "dense_simt.cuh"
 #include "dense_tc.cuh"
+
 namespace adn {
 namespace tc {
-int init() { return ADN_OK; }
-bool fwd_supported(int64_t, int64_t, int64_t) { return false; }
-bool bwd_supported(int64_t, int64_t, int64_t) { return false; }
-int64_t dense_bwd_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-int dense_fwd(const float*, const float*, const float*, float*, int64_t, int64_t, int64_t, int, cudaStream_t) {
-  return fail(ADN_ERR_UNSUPPORTED, "tcgen05 dense_fwd not built");
+
+static constexpr int BM = 128, BN = 128, BK = 32;
+static constexpr int STAGES = 3;
+static constexpr int TILE_BYTES = 128 * BK * 4;       // 16 KiB
+static constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi A_lo B_hi B_lo
+static constexpr int BAR_BYTES = 256;
+static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+static constexpr int NUM_THREADS = 192;
+static constexpr int TMEM_COLS = 128;
+
+enum { EPI_BIAS_ACT = 0, EPI_MASK = 1, EPI_PARTIAL = 2 };
+
+struct GemmParams {
+  float* out;
+  int M, N, ldc;
+  int total_kb;        // K blocks of 32 over the whole (padded) K
+  int kb_per_split;    // K blocks per blockIdx.z
+  const float* bias;   // EPI_BIAS_ACT
+  int act;
+  const float* mask;   // EPI_MASK (nullable)
+  int ldmask;
+};
+
+// ---------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int dense_bwd(const float*, const float*, const float*, float*, float*, float*, int64_t, int64_t, int64_t, int,
-              void*, int64_t, cudaStream_t) {
-  return fail(ADN_ERR_UNSUPPORTED, "tcgen05 dense_bwd not built");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Bounded spin: a broken pipeline traps (CUDA error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((it & 1023u) == 1023u) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major)
+//   [32,46) SBO >> 4 (8 rows * 128 B = 1024 B -> 64) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
+// a_major=b_major=K (0), n_dim=N>>3 [17,23), m_dim=M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// GEMM kernel
+// ---------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const GemmParams g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  const int kb1 = min(g.total_kb, kb0 + g.kb_per_split);
+  const int nkb = max(0, kb1 - kb0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi);
+    tma_prefetch_desc(&map_b_lo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(tmem_full_bar), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+        const int kc = (kb0 + kb) * BK;
+        tma_load_2d(&map_a_hi, fb, base + 0 * TILE_BYTES, kc, m0);
+        tma_load_2d(&map_a_lo, fb, base + 1 * TILE_BYTES, kc, m0);
+        tma_load_2d(&map_b_hi, fb, base + 2 * TILE_BYTES, kc, n0);
+        tma_load_2d(&map_b_lo, fb, base + 3 * TILE_BYTES, kc, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t a_hi = make_desc(base + 0 * TILE_BYTES), a_lo = make_desc(base + 1 * TILE_BYTES);
+        const uint64_t b_hi = make_desc(base + 2 * TILE_BYTES), b_lo = make_desc(base + 3 * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {          // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (>>4) address field
+          const uint64_t adv = (uint64_t)(2 * k);
+          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);   // small terms first
+          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));        // frees this smem stage when the MMAs retire
+      }
+      if (nkb > 0) umma_commit(smem_u32(tmem_full_bar));
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int m = m0 + row;
+    if (nkb > 0) {
+      mbar_wait(smem_u32(tmem_full_bar), 0);
+      tc_fence_after();
+    }
+    float* out = g.out;
+    if (EPI == EPI_PARTIAL) out += (size_t)blockIdx.z * g.M * g.N;
+    const bool vec = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                     (EPI != EPI_MASK || g.mask == nullptr ||
+                      (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      if (nkb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      const int nbase = n0 + c0;
+      if (m < g.M && nbase < g.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (g.bias && nbase + j < g.N) v[j] += __ldg(g.bias + nbase + j);
+            if (g.act == ADN_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+          }
+        }
+        float* dst = out + (size_t)m * g.ldc + nbase;
+        if (vec && nbase + 32 <= g.N) {
+          if (EPI == EPI_MASK && g.mask) {
+            const float4* mk = reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldmask + nbase);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 t = __ldg(mk + q);
+              if (!(t.x > 0.f)) v[4 * q + 0] = 0.f;
+              if (!(t.y > 0.f)) v[4 * q + 1] = 0.f;
+              if (!(t.z > 0.f)) v[4 * q + 2] = 0.f;
+              if (!(t.w > 0.f)) v[4 * q + 3] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nbase + j < g.N) {
+              float x = v[j];
+              if (EPI == EPI_MASK && g.mask && !(__ldg(g.mask + (size_t)m * g.ldmask + nbase + j) > 0.f)) x = 0.f;
+              dst[j] = x;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// hi/lo split pre-pass (also pads K to a multiple of 32 with zeros)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  lo = __uint_as_float(l);
+}
+
+// src[rows, cols] (ld = cols) -> hi/lo[rows, ldk]
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int rows, int cols,
+             int ldk) {
+  const int64_t nvec = (int64_t)rows * (ldk / 4);
+  const bool vec_src = ((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (ldk / 4));
+    const int c = (int)(i % (ldk / 4)) * 4;
+    float v[4];
+    if (vec_src && c + 3 < cols) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * cols + c));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = (c + q < cols) ? __ldg(src + (size_t)r * cols + c + q) : 0.f;
+    }
+    float h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
+    *reinterpret_cast<float4*>(hi + (size_t)r * ldk + c) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo + (size_t)r * ldk + c) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// src[rows, cols] -> hiT/loT[cols, ldk] with ldk = align_up(rows, 32); pad columns zeroed.
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ src, float* __restrict__ hiT, float* __restrict__ loT, int rows,
+                       int cols, int ldk) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? __ldg(src + (size_t)r * cols + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;     // output row = source column
+    if (c < cols && r < ldk) {
+      float h, l;
+      split_tf32(tile[tx][i], h, l);
+      hiT[(size_t)c * ldk + r] = h;
+      loT[(size_t)c * ldk + r] = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+
+int init() {
+  static std::once_flag once;
+  static int rc = ADN_OK;
+  std::call_once(once, []() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) {
+      (void)cudaGetLastError();
+      rc = fail(ADN_ERR_CUDA, "tc::init: cuTensorMapEncodeTiled entry point unavailable");
+      return;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    cudaError_t e1 = cudaFuncSetAttribute(tc_gemm_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(tc_gemm_kernel<EPI_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_kernel<EPI_PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+      (void)cudaGetLastError();
+      rc = fail(ADN_ERR_CUDA, "tc::init: cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
+    }
+  });
+  return rc;
+}
+
+static inline int64_t pad32(int64_t k) { return align_up(k, 32); }
+
+// thresholds: the tensor path pays a split pre-pass; skinny layers stay on CUDA cores
+bool fwd_supported(int64_t batch, int64_t in, int64_t out) { return batch >= 128 && in >= 32 && out >= 64; }
+bool bwd_supported(int64_t batch, int64_t in, int64_t out) { return batch >= 128 && in >= 32 && out >= 64; }
+
+static int make_map(CUtensorMap* map, const float* plane, int64_t rows, int64_t ldk) {
+  if (!g_encode) return fail(ADN_ERR_CUDA, "tc: adn_init() was not called");
+  cuuint64_t gdim[2] = {(cuuint64_t)ldk, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ldk * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(plane), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ADN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld ldk=%lld", (int)r,
+                                     (long long)rows, (long long)ldk);
+  return ADN_OK;
+}
+
+struct Planes {
+  float* hi;
+  float* lo;
+  int64_t rows, ldk;
+};
+
+static int do_split(const float* src, int64_t rows, int64_t cols, Planes& p, cudaStream_t st) {
+  const int64_t nvec = rows * (p.ldk / 4);
+  int blocks = (int)std::min<int64_t>(ceil_div(nvec, 256), (int64_t)sm_count() * 16);
+  split_kernel<<<blocks, 256, 0, st>>>(src, p.hi, p.lo, (int)rows, (int)cols, (int)p.ldk);
+  ADN_CHECK_LAUNCH("tc split");
+  return ADN_OK;
+}
+
+static int do_split_T(const float* src, int64_t rows, int64_t cols, Planes& p, cudaStream_t st) {
+  dim3 grid((unsigned)(p.ldk / 32), (unsigned)ceil_div(cols, 32));
+  split_transpose_kernel<<<grid, 256, 0, st>>>(src, p.hi, p.lo, (int)rows, (int)cols, (int)p.ldk);
+  ADN_CHECK_LAUNCH("tc split_transpose");
+  return ADN_OK;
+}
+
+template <int EPI>
+static int launch_gemm(const Planes& a, const Planes& b, GemmParams g, int splits, cudaStream_t st, const char* what) {
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, a.hi, a.rows, a.ldk))) return rc;
+  if ((rc = make_map(&ma_lo, a.lo, a.rows, a.ldk))) return rc;
+  if ((rc = make_map(&mb_hi, b.hi, b.rows, b.ldk))) return rc;
+  if ((rc = make_map(&mb_lo, b.lo, b.rows, b.ldk))) return rc;
+  dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), (unsigned)splits);
+  tc_gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
+  ADN_CHECK_LAUNCH(what);
+  return ADN_OK;
+}
+
+// carve 256B-aligned plane pairs out of the caller's workspace
+struct Carver {
+  char* p;
+  char* end;
+  bool ok = true;
+  Planes planes(int64_t rows, int64_t ldk) {
+    Planes pl{nullptr, nullptr, rows, ldk};
+    const int64_t bytes = align_up(rows * ldk * (int64_t)sizeof(float), 256);
+    if (p + 2 * bytes > end) { ok = false; return pl; }
+    pl.hi = reinterpret_cast<float*>(p);
+    pl.lo = reinterpret_cast<float*>(p + bytes);
+    p += 2 * bytes;
+    return pl;
+  }
+  float* floats(int64_t n) {
+    const int64_t bytes = align_up(n * (int64_t)sizeof(float), 256);
+    if (p + bytes > end) { ok = false; return nullptr; }
+    float* r = reinterpret_cast<float*>(p);
+    p += bytes;
+    return r;
+  }
+};
+
+static inline int64_t plane_pair_bytes(int64_t rows, int64_t ldk) {
+  return 2 * align_up(rows * ldk * (int64_t)sizeof(float), 256);
+}
+
+int64_t dense_fwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
+  if (!fwd_supported(batch, in, out)) return 0;
+  return plane_pair_bytes(batch, pad32(in)) + plane_pair_bytes(out, pad32(in)) + 1024;
+}
+
+// dW split-K: pick S in [1,16] maximising SM wave efficiency with at least ~1 wave of CTAs
+static int dw_splits(int64_t tiles, int64_t kblocks) {
+  const int sms = sm_count();
+  int best = 1;
+  double best_score = -1.0;
+  for (int s = 1; s <= 16 && s <= kblocks; ++s) {
+    const int64_t ctas = tiles * s;
+    const double waves = (double)ctas / sms;
+    const double eff = waves / (double)ceil_div(ctas, sms);
+    const double score = eff * std::min(1.0, waves) - 0.01 * s;   // prefer fewer splits on ties
+    if (score > best_score) { best_score = score; best = s; }
+  }
+  return best;
+}
+
+int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
+  if (!bwd_supported(batch, in, out)) return 0;
+  const int64_t kb = pad32(batch);
+  int64_t b = plane_pair_bytes(batch, pad32(out))   // dz       [B, out]   (A of dX)
+              + plane_pair_bytes(in, pad32(out))    // w        [in, out]  (B of dX)
+              + plane_pair_bytes(in, kb)            // x^T      [in, B]    (A of dW)
+              + plane_pair_bytes(out, kb);          // dz^T     [out, B]   (B of dW)
+  b += align_up(16 * in * out * (int64_t)sizeof(float), 256);          // dW split-K partials
+  b += align_up(ceil_div(batch, 512) * out * (int64_t)sizeof(float), 256);  // db partials
+  return b + 1024;
+}
+
+int dense_fwd(const float* x, const float* w, const float* b, float* y, int64_t batch, int64_t in, int64_t out,
+              int act, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < dense_fwd_workspace_bytes(batch, in, out))
+    return fail(ADN_ERR_WORKSPACE, "tc dense_fwd: workspace %lld < %lld bytes", (long long)ws_bytes,
+                (long long)dense_fwd_workspace_bytes(batch, in, out));
+  Carver c{reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255),
+           reinterpret_cast<char*>(ws) + ws_bytes};
+  const int64_t ldk = pad32(in);
+  Planes px = c.planes(batch, ldk);   // A = x        [M=B,   K=in]
+  Planes pw = c.planes(out, ldk);     // B = w^T      [N=out, K=in]
+  if (!c.ok) return fail(ADN_ERR_WORKSPACE, "tc dense_fwd: workspace carve failed");
+  int rc;
+  if ((rc = do_split(x, batch, in, px, st))) return rc;
+  if ((rc = do_split_T(w, in, out, pw, st))) return rc;
+  GemmParams g{};
+  g.out = y; g.M = (int)batch; g.N = (int)out; g.ldc = (int)out;
+  g.total_kb = (int)(ldk / BK); g.kb_per_split = g.total_kb;
+  g.bias = b; g.act = act;
+  return launch_gemm<EPI_BIAS_ACT>(px, pw, g, 1, st, "tc dense_fwd gemm");
+}
+
+int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float* dw, float* db, int64_t batch,
+              int64_t in, int64_t out, int x_relu_mask, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < dense_bwd_workspace_bytes(batch, in, out))
+    return fail(ADN_ERR_WORKSPACE, "tc dense_bwd: workspace %lld < %lld bytes", (long long)ws_bytes,
+                (long long)dense_bwd_workspace_bytes(batch, in, out));
+  Carver c{reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255),
+           reinterpret_cast<char*>(ws) + ws_bytes};
+  const int64_t ldo = pad32(out), ldb = pad32(batch);
+  Planes pdz = c.planes(batch, ldo);
+  Planes pw = c.planes(in, ldo);
+  Planes pxT = c.planes(in, ldb);
+  Planes pdzT = c.planes(out, ldb);
+  float* part = c.floats(16 * in * out);
+  float* dbpart = c.floats(ceil_div(batch, 512) * out);
+  if (!c.ok) return fail(ADN_ERR_WORKSPACE, "tc dense_bwd: workspace carve failed");
+  int rc;
+  // ---- dW[in,out] = x^T[in,B] * (dz^T[out,B])^T, split-K over the batch ----
+  if ((rc = do_split_T(x, batch, in, pxT, st))) return rc;
+  if ((rc = do_split_T(dz, batch, out, pdzT, st))) return rc;
+  {
+    const int total_kb = (int)(ldb / BK);
+    const int S = dw_splits(ceil_div(in, BM) * ceil_div(out, BN), total_kb);
+    GemmParams g{};
+    g.M = (int)in; g.N = (int)out; g.ldc = (int)out;
+    g.total_kb = total_kb; g.kb_per_split = (int)ceil_div(total_kb, S);
+    const int S_eff = (int)ceil_div(total_kb, g.kb_per_split);
+    g.out = (S_eff == 1) ? dw : part;
+    if ((rc = launch_gemm<EPI_PARTIAL>(pxT, pdzT, g, S_eff, st, "tc dW gemm"))) return rc;
+    if (S_eff > 1 && (rc = simt::reduce_partials(part, dw, in * out, S_eff, in * out, st))) return rc;
+  }
+  if (db && (rc = simt::colsum(dz, db, batch, out, dbpart, st))) return rc;
+  // ---- dX[B,in] = dz[B,out] * (w[in,out])^T, ReLU mask from x ----
+  if (dx) {
+    if ((rc = do_split(dz, batch, out, pdz, st))) return rc;
+    if ((rc = do_split(w, in, out, pw, st))) return rc;
+    GemmParams g{};
+    g.out = dx; g.M = (int)batch; g.N = (int)in; g.ldc = (int)in;
+    g.total_kb = (int)(ldo / BK); g.kb_per_split = g.total_kb;
+    g.mask = x_relu_mask ? x : nullptr; g.ldmask = (int)in;
+    if ((rc = launch_gemm<EPI_MASK>(pdz, pw, g, 1, st, "tc dX gemm"))) return rc;
+  }
+  return ADN_OK;
+}
+
 }  // namespace tc
 }  // namespace adn

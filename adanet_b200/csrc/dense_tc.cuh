@@ -10,8 +10,9 @@ int init();
 bool fwd_supported(int64_t batch, int64_t in, int64_t out);
 bool bwd_supported(int64_t batch, int64_t in, int64_t out);
 int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out);
+int64_t dense_fwd_workspace_bytes(int64_t batch, int64_t in, int64_t out);
 int dense_fwd(const float* x, const float* w, const float* b, float* y, int64_t batch, int64_t in,
-              int64_t out, int act, cudaStream_t st);
+              int64_t out, int act, void* ws, int64_t ws_bytes, cudaStream_t st);
 int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float* dw, float* db,
               int64_t batch, int64_t in, int64_t out, int x_relu_mask, void* ws, int64_t ws_bytes,
               cudaStream_t st);

@@ -180,6 +180,8 @@ def measure_dominant_kernel(lib, torch, reps=20):
   w = torch.randn((I, O), device="cuda") * 0.03
   b = torch.zeros((O,), device="cuda")
   y = torch.empty((B, O), device="cuda")
+  ws_bytes = _lib.query(_lib.Q_DENSE_FWD_WS, B, I, O)
+  ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device="cuda")
   st = torch.cuda.current_stream()
   flush = torch.empty((256 * 1024 * 1024 // 4,), device="cuda")   # 256 MB > 126 MB L2
   times = []
@@ -187,8 +189,8 @@ def measure_dominant_kernel(lib, torch, reps=20):
     flush.fill_(float(i))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    _lib.check(lib.adn_dense_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, I, O, 1, st.cuda_stream),
-               "adn_dense_fwd")
+    _lib.check(lib.adn_dense_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, I, O, 1, ws.data_ptr(),
+                                 ws_bytes, st.cuda_stream), "adn_dense_fwd")
     e1.record(st)
     e1.synchronize()
     if i >= 3:

@@ -69,6 +69,7 @@ extern "C" {
 #define ADN_Q_SM_COUNT 4
 #define ADN_Q_LAUNCH_COUNT 5              /* kernels launched by this library so far */
 #define ADN_Q_DENSE_BWD_PATH 6            /* a=batch b=in c=out */
+#define ADN_Q_DENSE_FWD_WORKSPACE_BYTES 7 /* a=batch b=in c=out (0 when the SIMT path is taken) */
 
 const char* adn_last_error(void);
 /* One-time, idempotent host-side initialisation (kernel attributes, driver entry
@@ -84,9 +85,12 @@ int adn_set_dense_path(int path);
  *   adanet/examples/simple_dnn.py:72-86 (_SimpleDNNBuilder.build_subnetwork),
  * and the forward-only replay of frozen members,
  *   adanet/core/estimator.py:1785-1882 / adanet/core/iteration.py:568-579.
+ * workspace: adn_query(ADN_Q_DENSE_FWD_WORKSPACE_BYTES) bytes (hi/lo TF32 operand
+ * planes of the tcgen05 path); may be NULL/0 when that query returns 0.
  */
 int adn_dense_fwd(const float* x, const float* w, const float* b, float* y,
-                  int64_t batch, int64_t in, int64_t out, int act, void* stream);
+                  int64_t batch, int64_t in, int64_t out, int act,
+                  void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Backward of one dense layer given dz = dLoss/d(pre-activation) [batch,out]:

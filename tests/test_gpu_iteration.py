@@ -1,6 +1,16 @@
 """Iteration-level parity: per-step losses, EMA, selection and growth of the GPU
 engine vs the CPU oracle on identical seeded data and injected weights.
-Tolerance: north_star's 1e-5 (fp32) on per-step loss."""
+
+Tolerance: north_star's 1e-5 (fp32) on every per-step loss.  Training is a
+chaotic map: two *correct* fp32 implementations that merely sum in a different
+order drift apart, for some configurations by far more than 1e-5 (e.g. the
+uncentred U[0,1) 784-feature data of SURVEY.md 8d at lr 0.05: the oracle
+against itself with permuted feature order differs by 1.8e-4 after 40 steps).
+So every parity configuration below is first shown to be well conditioned
+(`test_parity_configs_are_well_conditioned`, CPU): the oracle's own
+summation-order sensitivity must be < 3.3e-6, leaving the 1e-5 budget to the
+GPU path.
+"""
 
 import numpy as np
 import pytest
@@ -8,31 +18,111 @@ import pytest
 from tests import parity_util as pu
 from tests.parity_util import orc
 
-pytestmark = pytest.mark.gpu
 TOL = 1e-5
+SENS_TOL = 3.3e-6
+ENS = dict(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
 
 
-def _run_pair(cfgs_fn, x, y, B, steps, iters, opt, ens_kw, head="softmax_xent", C=10, use_graph=True,
-              multi_stream=True, force_grow=False, replay=None):
-  import torch
+def _data(kind, n, d, c, seed):
+  if kind == "tabular":
+    return orc.make_tabular(n, d, c, seed=seed)
+  if kind == "uniform_centered":      # BASELINE configs[1] shape, centred so that training is well conditioned
+    x, y = orc.make_uniform(n, d, c, seed=seed)
+    return (x - np.float32(0.5)).astype(np.float32), y
+  if kind == "regression":
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    y = (x[:, :1] * 0.5 - x[:, 1:2] + 0.1 * rng.standard_normal((n, 1))).astype(np.float32)
+    return x, y
+  raise ValueError(kind)
+
+
+# name -> dict(data=(kind, n, d, C, seed), cfgs=[(depth,width)], B, steps, iters, opt, ens, head, extra)
+CONFIGS = {
+    # BASELINE configs[1]: 784x10, 4 candidates (depth 1..2 x width 64/128), 3 iterations
+    "config2": dict(data=("uniform_centered", 8192, 784, 10, 2234), cfgs=[(1, 64), (2, 64), (1, 128), (2, 128)],
+                    B=1024, steps=40, iters=3, opt=("sgd", 0.05), ens=ENS),
+    # north_star target: 100-feature 10-class tabular, 4-candidate DNN search, >= 100 steps
+    "tabular4": dict(data=("tabular", 65536, 100, 10, 1234), cfgs=[(1, 64), (2, 128), (2, 256), (3, 512)],
+                     B=512, steps=120, iters=2, opt=("sgd", 0.01), ens=ENS),
+    "adam": dict(data=("tabular", 16384, 100, 10, 4321), cfgs=[(1, 128), (2, 128)], B=256, steps=60, iters=2,
+                 opt=("adam", 0.0005),
+                 ens=dict(optimizer=("adam", 0.0005), adanet_lambda=0.01, adanet_beta=0.001, use_bias=True,
+                          mixture_weight_type="vector")),
+    "rmsprop": dict(data=("tabular", 16384, 100, 10, 4321), cfgs=[(1, 128), (2, 128)], B=256, steps=60, iters=2,
+                    opt=("rmsprop", 0.0005),
+                    ens=dict(optimizer=("rmsprop", 0.0005), adanet_lambda=0.01, adanet_beta=0.001, use_bias=True,
+                             mixture_weight_type="vector")),
+    "momentum": dict(data=("tabular", 16384, 100, 10, 4321), cfgs=[(1, 128), (2, 128)], B=256, steps=60, iters=2,
+                     opt=("momentum", 0.005, 0.9),
+                     ens=dict(optimizer=("momentum", 0.005, 0.9), adanet_lambda=0.01, adanet_beta=0.001,
+                              use_bias=True, mixture_weight_type="vector")),
+    "default_ensembler": dict(data=("tabular", 8192, 100, 10, 99), cfgs=[(1, 64), (2, 64)], B=256, steps=30, iters=2,
+                              opt=("sgd", 0.01), ens=dict(optimizer=None)),
+    "force_grow": dict(data=("tabular", 8192, 100, 10, 5), cfgs=[(1, 32), (2, 32)], B=256, steps=10, iters=3,
+                       opt=("sgd", 0.01), ens=ENS, force_grow=True),
+    "replay": dict(data=("tabular", 8192, 100, 10, 5), cfgs=[(1, 32), (2, 32)], B=256, steps=10, iters=3,
+                   opt=("sgd", 0.01), ens=ENS, replay=[1, 2, 1]),
+    "regression": dict(data=("regression", 4096, 20, 1, 8), cfgs=[(1, 32), (2, 32)], B=128, steps=40, iters=2,
+                       opt=("sgd", 0.02), ens=ENS, head="mse"),
+    # edge cases: batch not a multiple of any tile, widths 3, single candidate, 3 classes
+    "ragged": dict(data=("tabular", 1000, 7, 3, 3), cfgs=[(1, 3)], B=37, steps=15, iters=2, opt=("sgd", 0.05),
+                   ens=ENS),
+}
+
+
+def _oracle_run(cfg, perm=None):
+  kind, n, d, c, seed = cfg["data"]
+  x, y = _data(kind, n, d, c, seed)
+  if perm is not None:
+    x = np.ascontiguousarray(x[:, perm])
+
+  def space(t, frozen):
+    specs = pu.make_specs(cfg["cfgs"], d, c, t, cfg["opt"])[0]
+    if perm is not None:
+      for s in specs:
+        s.ws[0] = np.ascontiguousarray(s.ws[0][perm])
+    return specs
+
+  res, _ = orc.run_adanet(space, x, y, cfg["B"], cfg["steps"], cfg["iters"], orc.EnsemblerSpec(**cfg["ens"]), c,
+                          head=cfg.get("head", "softmax_xent"), force_grow=cfg.get("force_grow", False),
+                          replay_indices=cfg.get("replay"))
+  return res
+
+
+def _max_trace_diff(a, b):
+  worst = 0.0
+  for ra, rb in zip(a, b):
+    for name in ra.traces:
+      for f in ("sub_loss", "ens_loss", "adanet_loss", "ema"):
+        worst = max(worst, float(np.abs(np.asarray(ra.traces[name][f], np.float64) -
+                                        np.asarray(rb.traces[name][f], np.float64)).max()))
+  return worst
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_parity_configs_are_well_conditioned(name):
+  """CPU: the oracle against itself with permuted input-feature order (a pure summation-order change)."""
+  cfg = CONFIGS[name]
+  d = cfg["data"][2]
+  perm = np.random.default_rng(0).permutation(d)
+  a, b = _oracle_run(cfg), _oracle_run(cfg, perm)
+  sens = _max_trace_diff(a, b)
+  assert [r.best_index for r in a] == [r.best_index for r in b]
+  assert sens < SENS_TOL, "config %s is ill conditioned: oracle self-sensitivity %.3g" % (name, sens)
+
+
+def _engine_run(cfg, use_graph=True, multi_stream=True):
   from adanet_b200.core import engine as eng
   from adanet_b200.core import search as srch
-  D = x.shape[1]
-  ens_o = orc.EnsemblerSpec(**ens_kw)
-  ens_e = eng.EnsemblerPlanSpec(**ens_kw)
-
-  def o_space(t, frozen):
-    return pu.make_specs(cfgs_fn(t), D, C, t, opt)[0]
-
-  def e_space(t, frozen):
-    return pu.make_specs(cfgs_fn(t), D, C, t, opt)[1]
-
-  o_res, _ = orc.run_adanet(o_space, x, y, B, steps, iters, ens_o, C, head=head, force_grow=force_grow,
-                            replay_indices=replay)
-  s = srch.AdaNetSearch(e_space, ens_e, D, C, B, head=head, use_cuda_graph=use_graph, multi_stream=multi_stream,
-                        force_grow=force_grow, replay_indices=replay)
-  reps = s.run(srch.consecutive_batches(x, y, B), steps, iters)
-  return o_res, reps, s
+  kind, n, d, c, seed = cfg["data"]
+  x, y = _data(kind, n, d, c, seed)
+  space = lambda t, frozen: pu.make_specs(cfg["cfgs"], d, c, t, cfg["opt"])[1]
+  s = srch.AdaNetSearch(space, eng.EnsemblerPlanSpec(**cfg["ens"]), d, c, cfg["B"], head=cfg.get("head", "softmax_xent"),
+                        use_cuda_graph=use_graph, multi_stream=multi_stream, force_grow=cfg.get("force_grow", False),
+                        replay_indices=cfg.get("replay"))
+  reps = s.run(srch.consecutive_batches(x, y, cfg["B"]), cfg["steps"], cfg["iters"])
+  return reps, s
 
 
 def _check(o_res, reps, tol=TOL):
@@ -46,88 +136,58 @@ def _check(o_res, reps, tol=TOL):
         assert got.shape == want.shape
         err = np.abs(got - want).max()
         worst = max(worst, err)
-        assert err < tol, "iteration %d %s/%s: max abs err %.3g" % (o.iteration, name, f, err)
+        assert err < tol, "iteration %d %s/%s: max abs err %.3g (first step err %.3g)" % (
+            o.iteration, name, f, err, abs(got[0] - want[0]))
     assert r.best_index == o.best_index, (r.ema_losses, o.ema_losses)
     assert r.architecture == o.architecture
     np.testing.assert_allclose(r.ema_losses, o.ema_losses, atol=tol)
   return worst
 
 
-ENS = dict(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["simt", "auto"])
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_iteration_parity(built_lib, name, path):
+  from adanet_b200 import _lib
+  cfg = CONFIGS[name]
+  _lib.set_dense_path(_lib.PATH_SIMT if path == "simt" else _lib.PATH_AUTO)
+  try:
+    o = _oracle_run(cfg)
+    r, s = _engine_run(cfg)
+    worst = _check(o, r)
+    print("%s[%s] worst per-step abs err %.3g" % (name, path, worst))
+    assert len(s.frozen) == len(r[-1].architecture)
+    if name == "default_ensembler":
+      # weighted.py:612-613: optimizer None -> no_op, weights stay 1/N; lambda=beta=0 -> reg exactly 0
+      np.testing.assert_allclose(r[-1].mixture_weights, np.full_like(r[-1].mixture_weights, 1.0 / len(r[-1].architecture)))
+      for tr in r[0].traces.values():
+        np.testing.assert_array_equal(tr["ens_loss"], tr["adanet_loss"])
+    if name == "force_grow":
+      assert len(r[-1].architecture) == 3   # a subnetwork is added every iteration (estimator_test.py:3002-3078)
+    if name == "replay":
+      assert [rep.best_index for rep in r] == [1, 2, 1]   # estimator_test.py:3235-3311
+  finally:
+    _lib.set_dense_path(_lib.PATH_AUTO)
 
 
-@pytest.mark.parametrize("use_graph,multi_stream", [(False, False), (True, True)])
-def test_config2_four_candidates_three_iterations(built_lib, use_graph, multi_stream):
-  """BASELINE configs[1]: 784x10 synthetic, 4 candidates (depth 1..2 x width 64/128), 3 iterations."""
-  x, y = orc.make_uniform(8192, 784, 10, seed=2234)
-  cfgs = lambda t: [(1, 64), (2, 64), (1, 128), (2, 128)]
-  o, r, _ = _run_pair(cfgs, x, y, 1024, 40, 3, ("sgd", 0.05), ENS, use_graph=use_graph, multi_stream=multi_stream)
-  worst = _check(o, r)
-  print("config2 worst per-step abs err", worst)
+@pytest.mark.gpu
+def test_eager_launches_match_cuda_graph(built_lib):
+  """Plain stream launches (no graph, single stream) and the captured multi-stream graph agree bit for bit."""
+  cfg = CONFIGS["config2"]
+  a, _ = _engine_run(cfg, use_graph=False, multi_stream=False)
+  b, _ = _engine_run(cfg, use_graph=True, multi_stream=True)
+  for ra, rb in zip(a, b):
+    for name in ra.traces:
+      for f in ("sub_loss", "ens_loss", "adanet_loss", "ema"):
+        np.testing.assert_array_equal(ra.traces[name][f], rb.traces[name][f])
+    assert ra.best_index == rb.best_index
 
 
-def test_tabular_four_candidate_search_100_steps(built_lib):
-  """north_star target: 100-feature 10-class tabular, 4-candidate DNN search, >=100 steps, 1e-5."""
-  x, y = orc.make_tabular(65536, 100, 10, seed=1234)
-  cfgs = lambda t: [(1, 64), (2, 128), (2, 256), (3, 512)]
-  o, r, s = _run_pair(cfgs, x, y, 512, 120, 2, ("sgd", 0.05), ENS)
-  worst = _check(o, r)
-  print("tabular worst per-step abs err", worst)
-  # frozen replay really happened in iteration 1: two members in the final ensemble or previous kept
-  assert len(s.frozen) == len(r[-1].architecture)
-
-
-@pytest.mark.parametrize("opt", [("adam", 0.001), ("rmsprop", 0.001), ("momentum", 0.02, 0.9)])
-def test_other_optimizers(built_lib, opt):
-  x, y = orc.make_tabular(16384, 100, 10, seed=4321)
-  cfgs = lambda t: [(1, 128), (2, 128)]
-  ens = dict(optimizer=opt, adanet_lambda=0.01, adanet_beta=0.001, use_bias=True, mixture_weight_type="vector")
-  o, r, _ = _run_pair(cfgs, x, y, 256, 60, 2, opt, ens)
-  _check(o, r, tol=2e-5 if opt[0] != "momentum" else TOL)
-
-
-def test_default_ensembler_no_mixture_training(built_lib):
-  # weighted.py:612-613: optimizer None -> no_op, weights stay 1/N; lambda=beta=0 -> reg exactly 0
-  x, y = orc.make_tabular(8192, 100, 10, seed=99)
-  cfgs = lambda t: [(1, 64), (2, 64)]
-  o, r, s = _run_pair(cfgs, x, y, 256, 30, 2, ("sgd", 0.05), dict(optimizer=None))
-  _check(o, r)
-  np.testing.assert_allclose(r[-1].mixture_weights, np.full_like(r[-1].mixture_weights, 1.0 / len(r[-1].architecture)))
-  for name, tr in r[0].traces.items():
-    np.testing.assert_array_equal(tr["ens_loss"], tr["adanet_loss"])
-
-
-def test_force_grow_and_replay(built_lib):
-  x, y = orc.make_tabular(8192, 100, 10, seed=5)
-  cfgs = lambda t: [(1, 32), (2, 32)]
-  o, r, s = _run_pair(cfgs, x, y, 256, 10, 3, ("sgd", 0.05), ENS, force_grow=True)
-  _check(o, r)
-  assert len(r[-1].architecture) == 3     # force_grow adds a subnetwork every iteration (estimator_test.py:3002-3078)
-  o, r, s = _run_pair(cfgs, x, y, 256, 10, 3, ("sgd", 0.05), ENS, replay=[1, 2, 1])
-  _check(o, r)
-  assert [rep.best_index for rep in r] == [1, 2, 1]
-
-
-def test_regression_head(built_lib):
-  rng = np.random.default_rng(8)
-  x = rng.standard_normal((4096, 20)).astype(np.float32)
-  y = (x[:, :1] * 0.5 - x[:, 1:2] + 0.1 * rng.standard_normal((4096, 1))).astype(np.float32)
-  cfgs = lambda t: [(1, 32), (2, 32)]
-  o, r, _ = _run_pair(cfgs, x, y, 128, 40, 2, ("sgd", 0.02), ENS, head="mse", C=1)
-  _check(o, r)
-
-
-def test_ragged_last_batch_and_tiny_shapes(built_lib):
-  # edge cases: batch not a multiple of any tile, width 1..3, single candidate
-  x, y = orc.make_tabular(1000, 7, 3, seed=3)
-  cfgs = lambda t: [(1, 3)]
-  o, r, _ = _run_pair(cfgs, x, y, 37, 15, 2, ("sgd", 0.1), ENS, C=3)
-  _check(o, r)
-
-
+@pytest.mark.gpu
 def test_full_size_properties(built_lib):
   """BASELINE-size step (B=32768, H=1024) checked through size-independent properties:
-  determinism (two fresh runs bit-identical) and gradient linearity of the dense backward."""
+  determinism (two fresh runs bit-identical), exact power-of-two linearity of the dense
+  backward, and the ReLU-mask structure of dX."""
   import torch
   from adanet_b200 import _lib
   from adanet_b200.core import engine as eng
@@ -141,7 +201,7 @@ def test_full_size_properties(built_lib):
     reps = s.run(srch.consecutive_batches(x, y, B), 2, 1)
     losses.append(next(iter(reps[0].traces.values()))["sub_loss"].copy())
   np.testing.assert_array_equal(losses[0], losses[1])
-  # linearity: dW(2*dz) == 2*dW(dz) exactly (power-of-two scaling commutes with fp32 rounding)
+  assert np.isfinite(losses[0]).all()
   lib = _lib.load()
   I, O = 1024, 1024
   rng = np.random.default_rng(0)
@@ -161,5 +221,13 @@ def test_full_size_properties(built_lib):
     outs.append((dw, db, dx))
   for a, b in zip(outs[0], outs[1]):
     assert torch.equal(a * 2.0, b)
-  # relu mask property: dx is zero exactly where x is zero
   assert float(outs[0][2][xd == 0].abs().max()) == 0.0
+  # spot-check 64 random dW entries against fp64
+  ii = rng.integers(0, I, 64)
+  oo = rng.integers(0, O, 64)
+  xs = xd[:, torch.as_tensor(ii).cuda()].double()
+  ds = dz[:, torch.as_tensor(oo).cuda()].double()
+  want = (xs * ds).sum(0).cpu().numpy()
+  got = outs[0][0][torch.as_tensor(ii).cuda(), torch.as_tensor(oo).cuda()].cpu().numpy()
+  scale = float((xs.abs() * ds.abs()).sum(0).max())
+  assert np.abs(got - want).max() <= 3e-6 * scale

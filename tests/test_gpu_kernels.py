@@ -61,13 +61,16 @@ def test_dense_fwd(gpu, path, B, I, O, act):
     want = np.maximum(want, 0)
   xd, wd, bd = _dev(x), _dev(w), _dev(b)
   yd = torch.empty((B, O), dtype=torch.float32, device="cuda")
-  _lib.check(gpu.adn_dense_fwd(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), yd.data_ptr(), B, I, O, act, _sp()),
-             "adn_dense_fwd")
+  fws_bytes = _lib.query(_lib.Q_DENSE_FWD_WS, B, I, O)
+  fws = torch.empty((max(fws_bytes, 16),), dtype=torch.uint8, device="cuda")
+  _lib.check(gpu.adn_dense_fwd(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), yd.data_ptr(), B, I, O, act,
+                               fws.data_ptr(), fws_bytes, _sp()), "adn_dense_fwd")
   got = yd.cpu().numpy()
   scale = (np.abs(x).astype(np.float64) @ np.abs(w).astype(np.float64)).max()
   assert np.abs(got - want).max() <= GEMM_RTOL * scale, (np.abs(got - want).max(), scale)
   # no-bias variant
-  _lib.check(gpu.adn_dense_fwd(xd.data_ptr(), wd.data_ptr(), None, yd.data_ptr(), B, I, O, 0, _sp()), "adn_dense_fwd")
+  _lib.check(gpu.adn_dense_fwd(xd.data_ptr(), wd.data_ptr(), None, yd.data_ptr(), B, I, O, 0, fws.data_ptr(), fws_bytes,
+                               _sp()), "adn_dense_fwd")
   want2 = x.astype(np.float64) @ w.astype(np.float64)
   assert np.abs(yd.cpu().numpy() - want2).max() <= GEMM_RTOL * scale
   _set_path("auto")

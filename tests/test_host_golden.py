@@ -80,11 +80,11 @@ def test_cabi_header_symbols_are_exported(built_lib):
 def test_cabi_argument_validation_without_gpu(built_lib):
   """Error behaviour of the boundary: bad arguments fail loudly with a message, before any launch."""
   from adanet_b200 import _lib
-  rc = built_lib.adn_dense_fwd(None, None, None, None, 4, 4, 4, 0, None)
+  rc = built_lib.adn_dense_fwd(None, None, None, None, 4, 4, 4, 0, None, 0, None)
   assert rc == -22 and b"null" in built_lib.adn_last_error()
-  rc = built_lib.adn_dense_fwd(8, 8, None, 8, 0, 4, 4, 0, None)
+  rc = built_lib.adn_dense_fwd(8, 8, None, 8, 0, 4, 4, 0, None, 0, None)
   assert rc == -22
-  rc = built_lib.adn_dense_fwd(8, 8, None, 8, 4, 4, 4, 7, None)
+  rc = built_lib.adn_dense_fwd(8, 8, None, 8, 4, 4, 4, 7, None, 0, None)
   assert rc == -22 and b"act" in built_lib.adn_last_error()
   rc = built_lib.adn_ema_update(None, None, 0.9, None)
   assert rc == -22
