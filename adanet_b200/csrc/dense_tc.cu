@@ -1,26 +1,38 @@
 // tcgen05 dense path: fp32-accurate GEMM on the 5th-gen tensor cores via a
-// 3xTF32 split, TMA-fed, accumulators in TMEM.
+// 3xTF32 split, TMA-fed, accumulators in TMEM, two-level accumulation.
 //
-//   D[M,N] = A[M,K] * B[N,K]^T      (both operands K-major, fp32)
+//   D[M,N] = A[M,K] * B[N,K]^T      (both operands K-major)
 //   a = a_hi + a_lo,  a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi)   (same for b)
 //   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi      (dropped a_lo*b_lo ~ 2^-22 |ab|)
 //
-// Pipeline per GEMM (warp-specialised, one 128x128 output tile per CTA):
+// Accuracy note (measured, profiles/r1_accuracy_probe.txt): the tensor core's
+// fp32 accumulator TRUNCATES on every accumulate (bias -1.1e-8*K relative for
+// same-sign data with one long TMEM chain).  So the K loop is cut into chunks of
+// 128: hi*hi partial sums accumulate in TMEM for one chunk only, then the
+// epilogue warps add the chunk into fp32 REGISTERS with round-to-nearest while
+// the MMA warp fills the other TMEM buffer; the small cross terms get their own
+// TMEM accumulator (their truncation error is 2^-11 smaller).
+//
+// Persistent, warp-specialised CTA (one per SM, 192 threads):
 //   warp 0  TMA producer : 4 tiles/stage (A_hi, A_lo, B_hi, B_lo; 128 rows x 32 fp32,
-//                          SWIZZLE_128B) into a 3-stage smem ring, mbarrier expect_tx
-//   warp 1  MMA issuer   : 12 x tcgen05.mma.kind::tf32 (M128 N128 K8) per stage into a
-//                          128-column fp32 TMEM accumulator; tcgen05.commit frees the stage
-//   warps 2-5 epilogue   : tcgen05.ld (32 lanes x 32 columns) -> bias/ReLU | ReLU-mask |
-//                          split-K partial -> float4 global stores
-// The hi/lo planes are produced by a pre-pass (split / split+transpose kernels below),
-// which also zero-pads K to a multiple of 32 and lays every operand out K-major so only
-// the best-trodden UMMA descriptor form (K-major, SWIZZLE_128B) is used.
+//                          SWIZZLE_128B, one contiguous 16 KiB box each) into a
+//                          3-stage smem ring, mbarrier expect_tx
+//   warp 1  MMA issuer   : 12 x tcgen05.mma.kind::tf32 (M128 N128 K8) per stage;
+//                          tcgen05.commit frees the stage / publishes the chunk
+//   warps 2-5 epilogue   : tcgen05.ld chunk -> register accumulate; at tile end
+//                          bias/ReLU | ReLU-mask | split-K partial, staged through
+//                          smem so every global access is a full 128 B line
+// Operand planes are produced by the split pre-pass below in k-block-major layout
+//   plane[kb][row][32]   (kb = k / 32)
+// so each TMA box is one contiguous 16 KiB read whatever the logical row stride
+// (the transposed operands of dW = X^T dZ have a 128 KiB row stride otherwise).
 //
 // Reference arithmetic being replaced: tf.layers.dense / tf.matmul and their gradients,
 //   adanet/examples/simple_dnn.py:72-86,103-110.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "dense_simt.cuh"
@@ -31,20 +43,25 @@ namespace tc {
 
 static constexpr int BM = 128, BN = 128, BK = 32;
 static constexpr int STAGES = 3;
+static constexpr int CHUNK_KB = 4;                    // k-blocks per TMEM accumulation chunk (K = 128)
 static constexpr int TILE_BYTES = 128 * BK * 4;       // 16 KiB
 static constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi A_lo B_hi B_lo
+static constexpr int EPI_STAGE_FLOATS = 32 * 33;      // per epilogue warp
+static constexpr int EPI_BYTES = 4 * EPI_STAGE_FLOATS * 4;
 static constexpr int BAR_BYTES = 256;
-static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 static constexpr int NUM_THREADS = 192;
-static constexpr int TMEM_COLS = 128;
+static constexpr int TMEM_COLS = 512;                 // H0 [0,128) H1 [128,256) S0 [256,384) S1 [384,512)
+static constexpr int MAX_SPLITS = 64;
 
 enum { EPI_BIAS_ACT = 0, EPI_MASK = 1, EPI_PARTIAL = 2 };
 
 struct GemmParams {
   float* out;
   int M, N, ldc;
+  int tiles_m, tiles_n, splits;
   int total_kb;        // K blocks of 32 over the whole (padded) K
-  int kb_per_split;    // K blocks per blockIdx.z
+  int kb_per_split;
   const float* bias;   // EPI_BIAS_ACT
   int act;
   const float* mask;   // EPI_MASK (nullable)
@@ -61,6 +78,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded spin: a broken pipeline traps (CUDA error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -82,10 +102,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
@@ -135,6 +155,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// work item -> (tile_m, tile_n, split).  n fastest so concurrently resident CTAs share A tiles.
+struct Item {
+  int m0, n0, kb0, nkb, split;
+};
+__device__ __forceinline__ Item decode_item(const GemmParams& g, int item) {
+  Item it;
+  const int tiles = g.tiles_m * g.tiles_n;
+  it.split = item / tiles;
+  const int t = item - it.split * tiles;
+  const int tm = t / g.tiles_n;
+  it.m0 = tm * BM;
+  it.n0 = (t - tm * g.tiles_n) * BN;
+  it.kb0 = it.split * g.kb_per_split;
+  it.nkb = min(g.total_kb, it.kb0 + g.kb_per_split) - it.kb0;
+  return it;
+}
+
 // ---------------------------------------------------------------------------------
 // GEMM kernel
 // ---------------------------------------------------------------------------------
@@ -145,18 +182,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const GemmParams g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;          // [2]       MMA -> epilogue (chunk ready)
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;     // [2]       epilogue -> MMA (chunk drained), count 4
+  uint64_t* s_empty = bars + 2 * STAGES + 4;       // [2]       epilogue -> MMA (small-term acc read), count 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int kb0 = blockIdx.z * g.kb_per_split;
-  const int kb1 = min(g.total_kb, kb0 + g.kb_per_split);
-  const int nkb = max(0, kb1 - kb0);
+  const int n_items = g.tiles_m * g.tiles_n * g.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -170,7 +207,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mbar_init(smem_u32(&full_bar[s]), 1);
         mbar_init(smem_u32(&empty_bar[s]), 1);
       }
-      mbar_init(smem_u32(tmem_full_bar), 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(smem_u32(&acc_full[b]), 1);
+        mbar_init(smem_u32(&acc_empty[b]), 4);
+        mbar_init(smem_u32(&s_empty[b]), 4);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -185,104 +226,153 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ================= TMA producer =================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, STAGE_BYTES);
-        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-        const int kc = (kb0 + kb) * BK;
-        tma_load_2d(&map_a_hi, fb, base + 0 * TILE_BYTES, kc, m0);
-        tma_load_2d(&map_a_lo, fb, base + 1 * TILE_BYTES, kc, m0);
-        tma_load_2d(&map_b_hi, fb, base + 2 * TILE_BYTES, kc, n0);
-        tma_load_2d(&map_b_lo, fb, base + 3 * TILE_BYTES, kc, n0);
+      uint32_t gkb = 0;   // global k-block counter (ring position)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(g, item);
+        for (int kb = 0; kb < it.nkb; ++kb, ++gkb) {
+          const uint32_t s = gkb % STAGES;
+          const uint32_t ph = (gkb / STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+          const int kc = it.kb0 + kb;
+          tma_load_3d(&map_a_hi, fb, base + 0 * TILE_BYTES, 0, it.m0, kc);
+          tma_load_3d(&map_a_lo, fb, base + 1 * TILE_BYTES, 0, it.m0, kc);
+          tma_load_3d(&map_b_hi, fb, base + 2 * TILE_BYTES, 0, it.n0, kc);
+          tma_load_3d(&map_b_lo, fb, base + 3 * TILE_BYTES, 0, it.n0, kc);
+        }
       }
     }
   } else if (warp == 1) {
+    // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+      uint32_t gkb = 0, gchunk = 0, tile_i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
+        const Item it = decode_item(g, item);
+        const uint32_t acc_s = tmem_base + 256 + (tile_i & 1) * 128;
+        mbar_wait(smem_u32(&s_empty[tile_i & 1]), ((tile_i >> 1) & 1) ^ 1);   // small-term accumulator free
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t a_hi = make_desc(base + 0 * TILE_BYTES), a_lo = make_desc(base + 1 * TILE_BYTES);
-        const uint64_t b_hi = make_desc(base + 2 * TILE_BYTES), b_lo = make_desc(base + 3 * TILE_BYTES);
+        for (int kb = 0; kb < it.nkb; ++kb, ++gkb) {
+          const int in_chunk = kb % CHUNK_KB;
+          const uint32_t b = gchunk & 1;
+          if (in_chunk == 0) {
+            mbar_wait(smem_u32(&acc_empty[b]), ((gchunk >> 1) & 1) ^ 1);   // chunk buffer drained
+            tc_fence_after();
+          }
+          const uint32_t s = gkb % STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (gkb / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t acc_h = tmem_base + b * 128;
+          const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t a_hi = make_desc(base + 0 * TILE_BYTES), a_lo = make_desc(base + 1 * TILE_BYTES);
+          const uint64_t b_hi = make_desc(base + 2 * TILE_BYTES), b_lo = make_desc(base + 3 * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {          // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (>>4) address field
-          const uint64_t adv = (uint64_t)(2 * k);
-          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);   // small terms first
-          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
-          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+          for (int k = 0; k < BK / 8; ++k) {        // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (>>4) address field
+            const uint64_t adv = (uint64_t)(2 * k);
+            umma_tf32(acc_s, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(acc_s, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(acc_h, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));      // frees this smem stage when the MMAs retire
+          if (in_chunk == CHUNK_KB - 1 || kb == it.nkb - 1) {
+            umma_commit(smem_u32(&acc_full[b]));     // chunk (and, on the last one, the small terms) complete
+            ++gchunk;
+          }
         }
-        umma_commit(smem_u32(&empty_bar[s]));        // frees this smem stage when the MMAs retire
       }
-      if (nkb > 0) umma_commit(smem_u32(tmem_full_bar));
     }
   } else {
-    // ---- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----
+    // ================= epilogue warps 2..5: TMEM lane quadrant = warp % 4 =================
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int m = m0 + row;
-    if (nkb > 0) {
-      mbar_wait(smem_u32(tmem_full_bar), 0);
-      tc_fence_after();
-    }
-    float* out = g.out;
-    if (EPI == EPI_PARTIAL) out += (size_t)blockIdx.z * g.M * g.N;
-    const bool vec = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
-                     (EPI != EPI_MASK || g.mask == nullptr ||
-                      (((g.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0)));
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (nkb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-      } else {
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    float* stage = epi_stage + quad * EPI_STAGE_FLOATS;
+    uint32_t gchunk = 0, tile_i = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
+      const Item it = decode_item(g, item);
+      float acc[BN];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      const int nchunks = (it.nkb + CHUNK_KB - 1) / CHUNK_KB;
+      for (int c = 0; c < nchunks; ++c, ++gchunk) {
+        const uint32_t b = gchunk & 1;
+        mbar_wait(smem_u32(&acc_full[b]), (gchunk >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_base + b * 128 + q * 32, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);   // fp32 RN adds
+        }
+        if (c == nchunks - 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + q * 32, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&acc_empty[b]));
+          if (c == nchunks - 1) mbar_arrive(smem_u32(&s_empty[tile_i & 1]));
+        }
       }
-      const int nbase = n0 + c0;
-      if (m < g.M && nbase < g.N) {
-        float v[32];
+      // ---- tile output: per-warp smem transpose so each global access is one full 128 B row segment ----
+      float* out = g.out;
+      if (EPI == EPI_PARTIAL) out += (size_t)it.split * g.M * g.N;
+      const int mrow0 = it.m0 + quad * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (EPI == EPI_BIAS_ACT) {
+      for (int q = 0; q < 4; ++q) {
+        const int col = it.n0 + q * 32 + lane;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (g.bias && nbase + j < g.N) v[j] += __ldg(g.bias + nbase + j);
-            if (g.act == ADN_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
-          }
-        }
-        float* dst = out + (size_t)m * g.ldc + nbase;
-        if (vec && nbase + 32 <= g.N) {
-          if (EPI == EPI_MASK && g.mask) {
-            const float4* mk = reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldmask + nbase);
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = acc[q * 32 + j];
+        __syncwarp();
+        float bias_v = 0.f;
+        if (EPI == EPI_BIAS_ACT && g.bias && col < g.N) bias_v = __ldg(g.bias + col);
+        if (col < g.N) {
+          const int rmax = min(32, g.M - mrow0);
+          if (rmax == 32) {
+            // fully unrolled fast path: the 32 mask loads are independent and issue back to back
+            float mk[32];
+            if (EPI == EPI_MASK) {
+              const float* mp = g.mask ? g.mask + (size_t)mrow0 * g.ldmask + col : nullptr;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 t = __ldg(mk + q);
-              if (!(t.x > 0.f)) v[4 * q + 0] = 0.f;
-              if (!(t.y > 0.f)) v[4 * q + 1] = 0.f;
-              if (!(t.z > 0.f)) v[4 * q + 2] = 0.f;
-              if (!(t.w > 0.f)) v[4 * q + 3] = 0.f;
+              for (int r = 0; r < 32; ++r) mk[r] = mp ? __ldg(mp + (size_t)r * g.ldmask) : 1.f;
+            }
+            float* op = out + (size_t)mrow0 * g.ldc + col;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              float v = stage[r * 33 + lane];
+              if (EPI == EPI_BIAS_ACT) {
+                v += bias_v;
+                if (g.act == ADN_ACT_RELU) v = fmaxf(v, 0.f);
+              } else if (EPI == EPI_MASK) {
+                if (!(mk[r] > 0.f)) v = 0.f;
+              }
+              op[(size_t)r * g.ldc] = v;
+            }
+          } else {
+            for (int r = 0; r < rmax; ++r) {
+              float v = stage[r * 33 + lane];
+              const size_t row = (size_t)(mrow0 + r);
+              if (EPI == EPI_BIAS_ACT) {
+                v += bias_v;
+                if (g.act == ADN_ACT_RELU) v = fmaxf(v, 0.f);
+              } else if (EPI == EPI_MASK) {
+                if (g.mask && !(__ldg(g.mask + row * g.ldmask + col) > 0.f)) v = 0.f;
+              }
+              out[row * g.ldc + col] = v;
             }
           }
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (nbase + j < g.N) {
-              float x = v[j];
-              if (EPI == EPI_MASK && g.mask && !(__ldg(g.mask + (size_t)m * g.ldmask + nbase + j) > 0.f)) x = 0.f;
-              dst[j] = x;
-            }
-          }
         }
+        __syncwarp();
       }
     }
   }
@@ -296,7 +386,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------
-// hi/lo split pre-pass (also pads K to a multiple of 32 with zeros)
+// hi/lo split pre-pass into k-block-major planes  plane[kb][row][32]
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   uint32_t h, l;
@@ -306,15 +396,16 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
-// src[rows, cols] (ld = cols) -> hi/lo[rows, ldk]
+// src[rows, cols] row-major (K = cols) -> hi/lo[nkb][rows][32], zero padded in K
 __global__ void __launch_bounds__(256)
 split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int rows, int cols,
-             int ldk) {
-  const int64_t nvec = (int64_t)rows * (ldk / 4);
+             int nkb) {
+  const int vec_per_row = nkb * 8;                       // float4 per padded row
+  const int64_t nvec = (int64_t)rows * vec_per_row;
   const bool vec_src = ((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / (ldk / 4));
-    const int c = (int)(i % (ldk / 4)) * 4;
+    const int r = (int)(i / vec_per_row);
+    const int c = (int)(i % vec_per_row) * 4;
     float v[4];
     if (vec_src && c + 3 < cols) {
       float4 t = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * cols + c));
@@ -326,17 +417,18 @@ split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __res
     float h[4], l[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
-    *reinterpret_cast<float4*>(hi + (size_t)r * ldk + c) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(lo + (size_t)r * ldk + c) = make_float4(l[0], l[1], l[2], l[3]);
+    const size_t dst = ((size_t)(c >> 5) * rows + r) * 32 + (c & 31);
+    *reinterpret_cast<float4*>(hi + dst) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
   }
 }
 
-// src[rows, cols] -> hiT/loT[cols, ldk] with ldk = align_up(rows, 32); pad columns zeroed.
+// src[rows, cols] row-major, K = rows -> hiT/loT[nkb][cols][32] (plane row = source column), zero padded in K
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ src, float* __restrict__ hiT, float* __restrict__ loT, int rows,
-                       int cols, int ldk) {
+                       int cols) {
   __shared__ float tile[32][33];
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;   // blockIdx.x = k-block
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
 #pragma unroll
   for (int i = ty; i < 32; i += 8) {
@@ -346,12 +438,13 @@ split_transpose_kernel(const float* __restrict__ src, float* __restrict__ hiT, f
   __syncthreads();
 #pragma unroll
   for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + tx;     // output row = source column
-    if (c < cols && r < ldk) {
+    const int c = c0 + i;     // plane row
+    if (c < cols) {
       float h, l;
       split_tf32(tile[tx][i], h, l);
-      hiT[(size_t)c * ldk + r] = h;
-      loT[(size_t)c * ldk + r] = l;
+      const size_t dst = ((size_t)blockIdx.x * cols + c) * 32 + tx;
+      hiT[dst] = h;
+      loT[dst] = l;
     }
   }
 }
@@ -385,56 +478,59 @@ int init() {
   return rc;
 }
 
-static inline int64_t pad32(int64_t k) { return align_up(k, 32); }
+static inline int64_t nkb_of(int64_t k) { return ceil_div(k, BK); }
 
 // thresholds: the tensor path pays a split pre-pass; skinny layers stay on CUDA cores
 bool fwd_supported(int64_t batch, int64_t in, int64_t out) { return batch >= 128 && in >= 32 && out >= 64; }
 bool bwd_supported(int64_t batch, int64_t in, int64_t out) { return batch >= 128 && in >= 32 && out >= 64; }
 
-static int make_map(CUtensorMap* map, const float* plane, int64_t rows, int64_t ldk) {
-  if (!g_encode) return fail(ADN_ERR_CUDA, "tc: adn_init() was not called");
-  cuuint64_t gdim[2] = {(cuuint64_t)ldk, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ldk * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(plane), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(ADN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld ldk=%lld", (int)r,
-                                     (long long)rows, (long long)ldk);
-  return ADN_OK;
-}
-
 struct Planes {
   float* hi;
   float* lo;
-  int64_t rows, ldk;
+  int64_t rows, nkb;
 };
 
+static int make_map(CUtensorMap* map, const float* plane, int64_t rows, int64_t nkb) {
+  if (!g_encode) return fail(ADN_ERR_CUDA, "tc: adn_init() was not called");
+  cuuint64_t gdim[3] = {(cuuint64_t)BK, (cuuint64_t)rows, (cuuint64_t)nkb};
+  cuuint64_t gstride[2] = {(cuuint64_t)BK * sizeof(float), (cuuint64_t)rows * BK * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)BK, 128u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(plane), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ADN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld nkb=%lld", (int)r,
+                                     (long long)rows, (long long)nkb);
+  return ADN_OK;
+}
+
 static int do_split(const float* src, int64_t rows, int64_t cols, Planes& p, cudaStream_t st) {
-  const int64_t nvec = rows * (p.ldk / 4);
+  const int64_t nvec = rows * p.nkb * 8;
   int blocks = (int)std::min<int64_t>(ceil_div(nvec, 256), (int64_t)sm_count() * 16);
-  split_kernel<<<blocks, 256, 0, st>>>(src, p.hi, p.lo, (int)rows, (int)cols, (int)p.ldk);
+  split_kernel<<<blocks, 256, 0, st>>>(src, p.hi, p.lo, (int)rows, (int)cols, (int)p.nkb);
   ADN_CHECK_LAUNCH("tc split");
   return ADN_OK;
 }
 
 static int do_split_T(const float* src, int64_t rows, int64_t cols, Planes& p, cudaStream_t st) {
-  dim3 grid((unsigned)(p.ldk / 32), (unsigned)ceil_div(cols, 32));
-  split_transpose_kernel<<<grid, 256, 0, st>>>(src, p.hi, p.lo, (int)rows, (int)cols, (int)p.ldk);
+  dim3 grid((unsigned)p.nkb, (unsigned)ceil_div(cols, 32));
+  split_transpose_kernel<<<grid, 256, 0, st>>>(src, p.hi, p.lo, (int)rows, (int)cols);
   ADN_CHECK_LAUNCH("tc split_transpose");
   return ADN_OK;
 }
 
 template <int EPI>
-static int launch_gemm(const Planes& a, const Planes& b, GemmParams g, int splits, cudaStream_t st, const char* what) {
+static int launch_gemm(const Planes& a, const Planes& b, GemmParams g, cudaStream_t st, const char* what) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, a.hi, a.rows, a.ldk))) return rc;
-  if ((rc = make_map(&ma_lo, a.lo, a.rows, a.ldk))) return rc;
-  if ((rc = make_map(&mb_hi, b.hi, b.rows, b.ldk))) return rc;
-  if ((rc = make_map(&mb_lo, b.lo, b.rows, b.ldk))) return rc;
-  dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), (unsigned)splits);
+  if ((rc = make_map(&ma_hi, a.hi, a.rows, a.nkb))) return rc;
+  if ((rc = make_map(&ma_lo, a.lo, a.rows, a.nkb))) return rc;
+  if ((rc = make_map(&mb_hi, b.hi, b.rows, b.nkb))) return rc;
+  if ((rc = make_map(&mb_lo, b.lo, b.rows, b.nkb))) return rc;
+  g.tiles_m = (int)ceil_div(g.M, BM);
+  g.tiles_n = (int)ceil_div(g.N, BN);
+  const int items = g.tiles_m * g.tiles_n * g.splits;
+  const int grid = std::min(items, sm_count());
   tc_gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
   ADN_CHECK_LAUNCH(what);
   return ADN_OK;
@@ -445,9 +541,9 @@ struct Carver {
   char* p;
   char* end;
   bool ok = true;
-  Planes planes(int64_t rows, int64_t ldk) {
-    Planes pl{nullptr, nullptr, rows, ldk};
-    const int64_t bytes = align_up(rows * ldk * (int64_t)sizeof(float), 256);
+  Planes planes(int64_t rows, int64_t nkb) {
+    Planes pl{nullptr, nullptr, rows, nkb};
+    const int64_t bytes = align_up(rows * nkb * BK * (int64_t)sizeof(float), 256);
     if (p + 2 * bytes > end) { ok = false; return pl; }
     pl.hi = reinterpret_cast<float*>(p);
     pl.lo = reinterpret_cast<float*>(p + bytes);
@@ -463,39 +559,47 @@ struct Carver {
   }
 };
 
-static inline int64_t plane_pair_bytes(int64_t rows, int64_t ldk) {
-  return 2 * align_up(rows * ldk * (int64_t)sizeof(float), 256);
+static inline int64_t plane_pair_bytes(int64_t rows, int64_t nkb) {
+  return 2 * align_up(rows * nkb * BK * (int64_t)sizeof(float), 256);
 }
 
 int64_t dense_fwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
   if (!fwd_supported(batch, in, out)) return 0;
-  return plane_pair_bytes(batch, pad32(in)) + plane_pair_bytes(out, pad32(in)) + 1024;
+  return plane_pair_bytes(batch, nkb_of(in)) + plane_pair_bytes(out, nkb_of(in)) + 1024;
 }
 
-// dW split-K: pick S in [1,16] maximising SM wave efficiency with at least ~1 wave of CTAs
-static int dw_splits(int64_t tiles, int64_t kblocks) {
+// dW split-K: the partial buffer bounds the split count (<= 16M floats, <= 64 splits)
+static int max_dw_splits(int64_t in, int64_t out) {
+  int64_t s = (16LL << 20) / std::max<int64_t>(1, in * out);
+  if (s > MAX_SPLITS) s = MAX_SPLITS;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+// pick S minimising (persistent rounds) x (k-blocks per item) + a per-split reduction cost
+static int dw_splits(int64_t tiles, int64_t kblocks, int max_s) {
   const int sms = sm_count();
   int best = 1;
-  double best_score = -1.0;
-  for (int s = 1; s <= 16 && s <= kblocks; ++s) {
-    const int64_t ctas = tiles * s;
-    const double waves = (double)ctas / sms;
-    const double eff = waves / (double)ceil_div(ctas, sms);
-    const double score = eff * std::min(1.0, waves) - 0.01 * s;   // prefer fewer splits on ties
-    if (score > best_score) { best_score = score; best = s; }
+  double best_t = 1e30;
+  for (int s = 1; s <= max_s && s <= kblocks; ++s) {
+    const int64_t kps = ceil_div(kblocks, s);
+    const int64_t s_eff = ceil_div(kblocks, kps);
+    const int64_t rounds = ceil_div(tiles * s_eff, sms);
+    const double t = (double)rounds * ((double)kps + 6.0) + 0.75 * (double)s_eff;   // 6: tile prologue/epilogue in k-block units
+    if (t < best_t) { best_t = t; best = (int)s_eff; }
   }
   return best;
 }
 
 int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
   if (!bwd_supported(batch, in, out)) return 0;
-  const int64_t kb = pad32(batch);
-  int64_t b = plane_pair_bytes(batch, pad32(out))   // dz       [B, out]   (A of dX)
-              + plane_pair_bytes(in, pad32(out))    // w        [in, out]  (B of dX)
-              + plane_pair_bytes(in, kb)            // x^T      [in, B]    (A of dW)
-              + plane_pair_bytes(out, kb);          // dz^T     [out, B]   (B of dW)
-  b += align_up(16 * in * out * (int64_t)sizeof(float), 256);          // dW split-K partials
-  b += align_up(ceil_div(batch, 512) * out * (int64_t)sizeof(float), 256);  // db partials
+  const int64_t kb_b = nkb_of(batch), kb_o = nkb_of(out);
+  int64_t b = plane_pair_bytes(batch, kb_o)   // dz       [B, out]   (A of dX)
+              + plane_pair_bytes(in, kb_o)    // w        [in, out]  (B of dX)
+              + plane_pair_bytes(in, kb_b)    // x^T      [in, B]    (A of dW)
+              + plane_pair_bytes(out, kb_b);  // dz^T     [out, B]   (B of dW)
+  b += align_up((int64_t)max_dw_splits(in, out) * in * out * (int64_t)sizeof(float), 256);   // dW split-K partials
+  b += align_up(ceil_div(batch, 512) * out * (int64_t)sizeof(float), 256);                   // db partials
   return b + 1024;
 }
 
@@ -506,18 +610,18 @@ int dense_fwd(const float* x, const float* w, const float* b, float* y, int64_t 
                 (long long)dense_fwd_workspace_bytes(batch, in, out));
   Carver c{reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255),
            reinterpret_cast<char*>(ws) + ws_bytes};
-  const int64_t ldk = pad32(in);
-  Planes px = c.planes(batch, ldk);   // A = x        [M=B,   K=in]
-  Planes pw = c.planes(out, ldk);     // B = w^T      [N=out, K=in]
+  const int64_t nkb = nkb_of(in);
+  Planes px = c.planes(batch, nkb);   // A = x        [M=B,   K=in]
+  Planes pw = c.planes(out, nkb);     // B = w^T      [N=out, K=in]
   if (!c.ok) return fail(ADN_ERR_WORKSPACE, "tc dense_fwd: workspace carve failed");
   int rc;
   if ((rc = do_split(x, batch, in, px, st))) return rc;
   if ((rc = do_split_T(w, in, out, pw, st))) return rc;
   GemmParams g{};
   g.out = y; g.M = (int)batch; g.N = (int)out; g.ldc = (int)out;
-  g.total_kb = (int)(ldk / BK); g.kb_per_split = g.total_kb;
+  g.total_kb = (int)nkb; g.kb_per_split = (int)nkb; g.splits = 1;
   g.bias = b; g.act = act;
-  return launch_gemm<EPI_BIAS_ACT>(px, pw, g, 1, st, "tc dense_fwd gemm");
+  return launch_gemm<EPI_BIAS_ACT>(px, pw, g, st, "tc dense_fwd gemm");
 }
 
 int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float* dw, float* db, int64_t batch,
@@ -527,12 +631,13 @@ int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float*
                 (long long)dense_bwd_workspace_bytes(batch, in, out));
   Carver c{reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255),
            reinterpret_cast<char*>(ws) + ws_bytes};
-  const int64_t ldo = pad32(out), ldb = pad32(batch);
-  Planes pdz = c.planes(batch, ldo);
-  Planes pw = c.planes(in, ldo);
-  Planes pxT = c.planes(in, ldb);
-  Planes pdzT = c.planes(out, ldb);
-  float* part = c.floats(16 * in * out);
+  const int64_t kb_o = nkb_of(out), kb_b = nkb_of(batch);
+  const int max_s = max_dw_splits(in, out);
+  Planes pdz = c.planes(batch, kb_o);
+  Planes pw = c.planes(in, kb_o);
+  Planes pxT = c.planes(in, kb_b);
+  Planes pdzT = c.planes(out, kb_b);
+  float* part = c.floats((int64_t)max_s * in * out);
   float* dbpart = c.floats(ceil_div(batch, 512) * out);
   if (!c.ok) return fail(ADN_ERR_WORKSPACE, "tc dense_bwd: workspace carve failed");
   int rc;
@@ -540,15 +645,14 @@ int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float*
   if ((rc = do_split_T(x, batch, in, pxT, st))) return rc;
   if ((rc = do_split_T(dz, batch, out, pdzT, st))) return rc;
   {
-    const int total_kb = (int)(ldb / BK);
-    const int S = dw_splits(ceil_div(in, BM) * ceil_div(out, BN), total_kb);
+    const int S = dw_splits(ceil_div(in, BM) * ceil_div(out, BN), kb_b, max_s);
     GemmParams g{};
     g.M = (int)in; g.N = (int)out; g.ldc = (int)out;
-    g.total_kb = total_kb; g.kb_per_split = (int)ceil_div(total_kb, S);
-    const int S_eff = (int)ceil_div(total_kb, g.kb_per_split);
-    g.out = (S_eff == 1) ? dw : part;
-    if ((rc = launch_gemm<EPI_PARTIAL>(pxT, pdzT, g, S_eff, st, "tc dW gemm"))) return rc;
-    if (S_eff > 1 && (rc = simt::reduce_partials(part, dw, in * out, S_eff, in * out, st))) return rc;
+    g.total_kb = (int)kb_b; g.kb_per_split = (int)ceil_div(kb_b, S);
+    g.splits = (int)ceil_div(kb_b, g.kb_per_split);
+    g.out = (g.splits == 1) ? dw : part;
+    if ((rc = launch_gemm<EPI_PARTIAL>(pxT, pdzT, g, st, "tc dW gemm"))) return rc;
+    if (g.splits > 1 && (rc = simt::reduce_partials(part, dw, in * out, g.splits, in * out, st))) return rc;
   }
   if (db && (rc = simt::colsum(dz, db, batch, out, dbpart, st))) return rc;
   // ---- dX[B,in] = dz[B,out] * (w[in,out])^T, ReLU mask from x ----
@@ -557,9 +661,9 @@ int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float*
     if ((rc = do_split(w, in, out, pw, st))) return rc;
     GemmParams g{};
     g.out = dx; g.M = (int)batch; g.N = (int)in; g.ldc = (int)in;
-    g.total_kb = (int)(ldo / BK); g.kb_per_split = g.total_kb;
+    g.total_kb = (int)kb_o; g.kb_per_split = (int)kb_o; g.splits = 1;
     g.mask = x_relu_mask ? x : nullptr; g.ldmask = (int)in;
-    if ((rc = launch_gemm<EPI_MASK>(pdz, pw, g, 1, st, "tc dX gemm"))) return rc;
+    if ((rc = launch_gemm<EPI_MASK>(pdz, pw, g, st, "tc dX gemm"))) return rc;
   }
   return ADN_OK;
 }

@@ -196,9 +196,14 @@ ensemble_finalize_kernel(const __grid_constant__ HeadParams p, int n_cta) {
   const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : C;
   const int n_w = (p.mixture == ADN_MIX_MATRIX) ? 0 : p.n_members * wdim;
   const int n_red = p.want_grads ? (1 + C + n_w) : 1;
-  for (int j = threadIdx.x; j < n_red; j += blockDim.x) {
+  // one warp per output: lanes stride over the CTA partials, then a fixed-order shuffle tree
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = wid; j < n_red; j += nwarps) {
     float t = 0.f;
-    for (int b = 0; b < n_cta; ++b) t += p.part[(size_t)b * p.n_out + j];
+    for (int b = lane; b < n_cta; b += 32) t += p.part[(size_t)b * p.n_out + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (lane != 0) continue;
     if (j == 0) {
       float denom = (p.head == ADN_HEAD_SOFTMAX_XENT) ? (float)p.batch : (float)p.batch * (float)C;
       s_loss = t / denom;

@@ -256,6 +256,13 @@ def run_ours(args):
   local_losses = plan.last_losses()
   assert np.isfinite(local_losses).all(), "non-finite loss in the timed region"
   rep = s.finish_iteration(secs)   # end-of-iteration all_gather + selection (outside the timed region)
+  if args.profile:   # under ncu: only the in-HBM step loop (a number printed under a profiler is never a bench value)
+    if rank == 0:
+      print(json.dumps({"profile_only": True, "ms_per_step_under_profiler": secs / args.steps * 1e3,
+                        "gpu_launches": int(launches_local)}), flush=True)
+    if world > 1:
+      dist.destroy_process_group()
+    return
 
   # ---------------- e2e: host batches through the public search API ----------------
   e2e_steps = min(args.steps, 20)
@@ -330,6 +337,7 @@ def main():
   ap.add_argument("--steps", type=int, default=30)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--profile", action="store_true", help="step loop only (for ncu captures)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

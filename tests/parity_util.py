@@ -42,6 +42,41 @@ def make_specs(cfgs: Sequence[tuple], in_dim: int, classes: int, iteration: int,
   return o_specs, e_specs
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def oracle_noise(level: float, seed: int):
+  """Temporarily perturbs the oracle's dense forward outputs and weight gradients by
+  `level` relative Gaussian noise: a model of a *different but equally valid* fp32
+  implementation, used to prove a parity configuration is well conditioned."""
+  rng = np.random.default_rng(seed)
+  f0, b0 = orc.mlp_forward, orc.mlp_backward
+
+  def fwd(ws, bs, x):
+    acts = [np.asarray(x, dtype=np.float32)]
+    n = len(ws)
+    for i in range(n):
+      z = acts[-1] @ ws[i] + bs[i]
+      z = z * (1 + np.float32(level) * rng.standard_normal(z.shape).astype(np.float32))
+      if i < n - 1:
+        z = np.maximum(z, np.float32(0))
+      acts.append(z.astype(np.float32))
+    return acts
+
+  def bwd(ws, acts, dlogits):
+    dws, dbs = b0(ws, acts, dlogits)
+    dws = [(d * (1 + np.float32(level) * rng.standard_normal(d.shape).astype(np.float32))).astype(np.float32)
+           for d in dws]
+    return dws, dbs
+
+  orc.mlp_forward, orc.mlp_backward = fwd, bwd
+  try:
+    yield
+  finally:
+    orc.mlp_forward, orc.mlp_backward = f0, b0
+
+
 def rel_err(a, b) -> float:
   a = np.asarray(a, dtype=np.float64)
   b = np.asarray(b, dtype=np.float64)
