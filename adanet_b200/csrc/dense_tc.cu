@@ -46,10 +46,12 @@ static constexpr int STAGES = 3;
 static constexpr int CHUNK_KB = 4;                    // k-blocks per TMEM accumulation chunk (K = 128)
 static constexpr int TILE_BYTES = 128 * BK * 4;       // 16 KiB
 static constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi A_lo B_hi B_lo
-static constexpr int EPI_STAGE_FLOATS = 32 * 33;      // per epilogue warp
-static constexpr int EPI_BYTES = 4 * EPI_STAGE_FLOATS * 4;
+static constexpr int EPI_STAGE_FLOATS = 32 * 33;      // per epilogue warp: output slice, transposed through smem
+static constexpr int EPI_MASK_FLOATS = 32 * 36;       // per epilogue warp: ReLU-mask slice landed by cp.async (16 B rows)
+static constexpr int EPI_BYTES = 4 * (EPI_STAGE_FLOATS + EPI_MASK_FLOATS) * 4;
 static constexpr int BAR_BYTES = 256;
-static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+// dynamic smem is declared __align__(1024) (SWIZZLE_128B atoms need it); no slack is left: 232192 of 232448 B
+static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
 static constexpr int NUM_THREADS = 192;
 static constexpr int TMEM_COLS = 512;                 // H0 [0,128) H1 [128,256) S0 [256,384) S1 [384,512)
 static constexpr int MAX_SPLITS = 64;
@@ -66,6 +68,8 @@ struct GemmParams {
   int act;
   const float* mask;   // EPI_MASK (nullable)
   int ldmask;
+  int chunk_kb;        // k-blocks per TMEM accumulation chunk (tuning knob, default CHUNK_KB)
+  int merge_small;     // 1: cross terms share the chunk accumulator (tuning knob, default 0)
 };
 
 // ---------------------------------------------------------------------------------
@@ -131,13 +135,26 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+// descriptors passed as 32-bit halves: only the low word (address field) differs between operands
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t d_hi, uint32_t idesc,
+                                          uint32_t accum) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(da_lo), "r"(db_lo), "r"(d_hi), "r"(idesc), "r"(accum)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -175,13 +192,14 @@ __device__ __forceinline__ Item decode_item(const GemmParams& g, int item) {
 // ---------------------------------------------------------------------------------
 // GEMM kernel
 // ---------------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, int CHUNK, int MERGE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const GemmParams g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();   // SWIZZLE_128B tiles must sit on 1024 B boundaries
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA
@@ -228,59 +246,75 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      uint32_t gkb = 0;   // global k-block counter (ring position)
+      uint32_t s = 0, ph = 0;   // ring slot / phase, advanced incrementally (no div/mod in the loop)
+      const uint32_t smem0 = smem_u32(smem);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const Item it = decode_item(g, item);
-        for (int kb = 0; kb < it.nkb; ++kb, ++gkb) {
-          const uint32_t s = gkb % STAGES;
-          const uint32_t ph = (gkb / STAGES) & 1;
+        for (int kb = 0; kb < it.nkb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, STAGE_BYTES);
-          const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t base = smem0 + s * STAGE_BYTES;
           const int kc = it.kb0 + kb;
           tma_load_3d(&map_a_hi, fb, base + 0 * TILE_BYTES, 0, it.m0, kc);
           tma_load_3d(&map_a_lo, fb, base + 1 * TILE_BYTES, 0, it.m0, kc);
           tma_load_3d(&map_b_hi, fb, base + 2 * TILE_BYTES, 0, it.n0, kc);
           tma_load_3d(&map_b_lo, fb, base + 3 * TILE_BYTES, 0, it.n0, kc);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // One thread feeds the tensor core: a 128x128x8 TF32 MMA retires every 64 clk, so the issue loop
+    // must stay well under 64 clk per MMA -- ring counters are incremental, descriptors are built from
+    // 32-bit halves (only the 14-bit address field of the low word moves), no div/mod anywhere.
+    // The whole warp runs the loop converged (all lanes wait on the barriers); only the issue itself is
+    // under elect.sync, so every operand is warp-uniform and lives in uniform registers.
+    {
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      uint32_t gkb = 0, gchunk = 0, tile_i = 0;
+      const uint32_t desc_hi = (uint32_t)(make_desc(0) >> 32);
+      const uint32_t desc_lo0 = (uint32_t)make_desc(smem_u32(smem));   // stage 0, tile 0 (A_hi)
+      uint32_t s = 0, ph = 0, gchunk = 0, tile_i = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
         const Item it = decode_item(g, item);
         const uint32_t acc_s = tmem_base + 256 + (tile_i & 1) * 128;
         mbar_wait(smem_u32(&s_empty[tile_i & 1]), ((tile_i >> 1) & 1) ^ 1);   // small-term accumulator free
         tc_fence_after();
-        for (int kb = 0; kb < it.nkb; ++kb, ++gkb) {
-          const int in_chunk = kb % CHUNK_KB;
+        uint32_t s_accum = 0;                      // first small-term MMA of the tile overwrites
+        for (int kb = 0; kb < it.nkb; kb += CHUNK, ++gchunk) {
           const uint32_t b = gchunk & 1;
-          if (in_chunk == 0) {
-            mbar_wait(smem_u32(&acc_empty[b]), ((gchunk >> 1) & 1) ^ 1);   // chunk buffer drained
-            tc_fence_after();
-          }
-          const uint32_t s = gkb % STAGES;
-          mbar_wait(smem_u32(&full_bar[s]), (gkb / STAGES) & 1);
+          mbar_wait(smem_u32(&acc_empty[b]), ((gchunk >> 1) & 1) ^ 1);      // chunk buffer drained
           tc_fence_after();
           const uint32_t acc_h = tmem_base + b * 128;
-          const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t a_hi = make_desc(base + 0 * TILE_BYTES), a_lo = make_desc(base + 1 * TILE_BYTES);
-          const uint64_t b_hi = make_desc(base + 2 * TILE_BYTES), b_lo = make_desc(base + 3 * TILE_BYTES);
+          const int nk = min(CHUNK, it.nkb - kb);
+          uint32_t h_accum = 0;                    // first hi*hi MMA of the chunk overwrites
+          for (int kk = 0; kk < nk; ++kk) {
+            mbar_wait(smem_u32(&full_bar[s]), ph);
+            tc_fence_after();
+            const uint32_t lo = desc_lo0 + s * (STAGE_BYTES >> 4);
+            if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {        // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (>>4) address field
-            const uint64_t adv = (uint64_t)(2 * k);
-            umma_tf32(acc_s, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-            umma_tf32(acc_s, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(acc_h, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0);
-          }
-          umma_commit(smem_u32(&empty_bar[s]));      // frees this smem stage when the MMAs retire
-          if (in_chunk == CHUNK_KB - 1 || kb == it.nkb - 1) {
-            umma_commit(smem_u32(&acc_full[b]));     // chunk (and, on the last one, the small terms) complete
-            ++gchunk;
+              for (int k = 0; k < BK / 8; ++k) {   // UMMA_K = 8 tf32 = 32 B -> +2 in the (>>4) address field
+                const uint32_t a_hi = lo + 0 * (TILE_BYTES >> 4) + 2 * k, a_lo = lo + 1 * (TILE_BYTES >> 4) + 2 * k;
+                const uint32_t b_hi = lo + 2 * (TILE_BYTES >> 4) + 2 * k, b_lo = lo + 3 * (TILE_BYTES >> 4) + 2 * k;
+                if (MERGE) {
+                  umma_tf32(acc_h, a_hi, b_hi, desc_hi, idesc, (k == 0) ? h_accum : 1u);
+                  umma_tf32(acc_h, a_lo, b_hi, desc_hi, idesc, 1u);
+                  umma_tf32(acc_h, a_hi, b_lo, desc_hi, idesc, 1u);
+                } else {
+                  umma_tf32(acc_s, a_lo, b_hi, desc_hi, idesc, (k == 0) ? s_accum : 1u);
+                  umma_tf32(acc_s, a_hi, b_lo, desc_hi, idesc, 1u);
+                  umma_tf32(acc_h, a_hi, b_hi, desc_hi, idesc, (k == 0) ? h_accum : 1u);
+                }
+              }
+              umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs retire
+              if (kk == nk - 1) umma_commit(smem_u32(&acc_full[b]));   // chunk (and small terms) complete
+            }
+            __syncwarp();
+            s_accum = 1u;
+            h_accum = 1u;
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -289,14 +323,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ================= epilogue warps 2..5: TMEM lane quadrant = warp % 4 =================
     const int quad = warp & 3;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    float* stage = epi_stage + quad * EPI_STAGE_FLOATS;
+    float* stage = epi_stage + quad * (EPI_STAGE_FLOATS + EPI_MASK_FLOATS);
+    float* mstage = stage + EPI_STAGE_FLOATS;
     uint32_t gchunk = 0, tile_i = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
       const Item it = decode_item(g, item);
       float acc[BN];
 #pragma unroll
       for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-      const int nchunks = (it.nkb + CHUNK_KB - 1) / CHUNK_KB;
+      const int nchunks = (it.nkb + CHUNK - 1) / CHUNK;
       for (int c = 0; c < nchunks; ++c, ++gchunk) {
         const uint32_t b = gchunk & 1;
         mbar_wait(smem_u32(&acc_full[b]), (gchunk >> 1) & 1);
@@ -308,7 +343,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);   // fp32 RN adds
         }
-        if (c == nchunks - 1) {
+        if (c == nchunks - 1 && !MERGE) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint32_t r[32];
@@ -328,25 +363,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       float* out = g.out;
       if (EPI == EPI_PARTIAL) out += (size_t)it.split * g.M * g.N;
       const int mrow0 = it.m0 + quad * 32;
+      const int rmax = min(32, g.M - mrow0);
+      // ReLU-mask slices land in smem through cp.async (no registers: the 128 accumulators stay live)
+      const bool mask_async = (EPI == EPI_MASK) && g.mask != nullptr && ((g.ldmask & 3) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int col = it.n0 + q * 32 + lane;
+        const int cbase = it.n0 + q * 32;
+        const int col = cbase + lane;
+        if (EPI == EPI_MASK && mask_async) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int id = lane + 32 * i;           // 16-byte chunk id: 8 chunks per 128 B row
+            const int r = id >> 3, c4 = (id & 7) * 4;
+            int bytes = (g.N - (cbase + c4)) * 4;
+            bytes = (r < rmax) ? max(0, min(16, bytes)) : 0;
+            const float* src = bytes > 0 ? g.mask + (size_t)(mrow0 + r) * g.ldmask + cbase + c4 : g.mask;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(mstage + r * 36 + c4)), "l"(src),
+                         "r"(bytes)
+                         : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = acc[q * 32 + j];
+        if (EPI == EPI_MASK && mask_async) asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         float bias_v = 0.f;
         if (EPI == EPI_BIAS_ACT && g.bias && col < g.N) bias_v = __ldg(g.bias + col);
         if (col < g.N) {
-          const int rmax = min(32, g.M - mrow0);
+          float* op = out + (size_t)mrow0 * g.ldc + col;
           if (rmax == 32) {
-            // fully unrolled fast path: the 32 mask loads are independent and issue back to back
-            float mk[32];
-            if (EPI == EPI_MASK) {
-              const float* mp = g.mask ? g.mask + (size_t)mrow0 * g.ldmask + col : nullptr;
-#pragma unroll
-              for (int r = 0; r < 32; ++r) mk[r] = mp ? __ldg(mp + (size_t)r * g.ldmask) : 1.f;
-            }
-            float* op = out + (size_t)mrow0 * g.ldc + col;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
               float v = stage[r * 33 + lane];
@@ -354,21 +401,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 v += bias_v;
                 if (g.act == ADN_ACT_RELU) v = fmaxf(v, 0.f);
               } else if (EPI == EPI_MASK) {
-                if (!(mk[r] > 0.f)) v = 0.f;
+                if (mask_async) {
+                  if (!(mstage[r * 36 + lane] > 0.f)) v = 0.f;
+                } else if (g.mask && !(__ldg(g.mask + (size_t)(mrow0 + r) * g.ldmask + col) > 0.f)) {
+                  v = 0.f;
+                }
               }
               op[(size_t)r * g.ldc] = v;
             }
           } else {
             for (int r = 0; r < rmax; ++r) {
               float v = stage[r * 33 + lane];
-              const size_t row = (size_t)(mrow0 + r);
               if (EPI == EPI_BIAS_ACT) {
                 v += bias_v;
                 if (g.act == ADN_ACT_RELU) v = fmaxf(v, 0.f);
               } else if (EPI == EPI_MASK) {
-                if (g.mask && !(__ldg(g.mask + row * g.ldmask + col) > 0.f)) v = 0.f;
+                if (mask_async) {
+                  if (!(mstage[r * 36 + lane] > 0.f)) v = 0.f;
+                } else if (g.mask && !(__ldg(g.mask + (size_t)(mrow0 + r) * g.ldmask + col) > 0.f)) {
+                  v = 0.f;
+                }
               }
-              out[row * g.ldc + col] = v;
+              op[(size_t)r * g.ldc] = v;
             }
           }
         }
@@ -467,10 +521,15 @@ int init() {
       return;
     }
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
-    cudaError_t e1 = cudaFuncSetAttribute(tc_gemm_kernel<EPI_BIAS_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(tc_gemm_kernel<EPI_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaError_t e3 = cudaFuncSetAttribute(tc_gemm_kernel<EPI_PARTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    bool ok = true;
+#define ADN_TC_ATTR(E, C, MG) \
+  ok = ok && (cudaFuncSetAttribute(tc_gemm_kernel<E, C, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess)
+#define ADN_TC_ATTR3(C, MG) ADN_TC_ATTR(EPI_BIAS_ACT, C, MG); ADN_TC_ATTR(EPI_MASK, C, MG); ADN_TC_ATTR(EPI_PARTIAL, C, MG)
+    ADN_TC_ATTR3(4, 0); ADN_TC_ATTR3(8, 0); ADN_TC_ATTR3(1024, 0);
+    ADN_TC_ATTR3(4, 1); ADN_TC_ATTR3(8, 1); ADN_TC_ATTR3(1024, 1);
+#undef ADN_TC_ATTR3
+#undef ADN_TC_ATTR
+    if (!ok) {
       (void)cudaGetLastError();
       rc = fail(ADN_ERR_CUDA, "tc::init: cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
     }
@@ -527,11 +586,24 @@ static int launch_gemm(const Planes& a, const Planes& b, GemmParams g, cudaStrea
   if ((rc = make_map(&ma_lo, a.lo, a.rows, a.nkb))) return rc;
   if ((rc = make_map(&mb_hi, b.hi, b.rows, b.nkb))) return rc;
   if ((rc = make_map(&mb_lo, b.lo, b.rows, b.nkb))) return rc;
+  // tuning knobs (experiments only; defaults are the shipped configuration)
+  static const int env_chunk = getenv("ADN_TC_CHUNK") ? atoi(getenv("ADN_TC_CHUNK")) : CHUNK_KB;
+  static const int env_merge = getenv("ADN_TC_MERGE") ? atoi(getenv("ADN_TC_MERGE")) : 0;
   g.tiles_m = (int)ceil_div(g.M, BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
   const int items = g.tiles_m * g.tiles_n * g.splits;
   const int grid = std::min(items, sm_count());
-  tc_gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
+#define ADN_TC_LAUNCH(C, MG) tc_gemm_kernel<EPI, C, MG><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g)
+  if (env_merge) {
+    if (env_chunk >= 1024) ADN_TC_LAUNCH(1024, 1);
+    else if (env_chunk >= 8) ADN_TC_LAUNCH(8, 1);
+    else ADN_TC_LAUNCH(4, 1);
+  } else {
+    if (env_chunk >= 1024) ADN_TC_LAUNCH(1024, 0);
+    else if (env_chunk >= 8) ADN_TC_LAUNCH(8, 0);
+    else ADN_TC_LAUNCH(4, 0);
+  }
+#undef ADN_TC_LAUNCH
   ADN_CHECK_LAUNCH(what);
   return ADN_OK;
 }
