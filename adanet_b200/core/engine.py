@@ -371,6 +371,18 @@ class IterationPlan:
       self._graph.replay()
     self.steps_done += 1
 
+  def eval_step(self, x, y) -> List[float]:
+    """Forward-only adanet_loss of every local candidate on one hold-out batch
+    (the Evaluator path, adanet/core/estimator.py:1469-1490)."""
+    self.load_batch(x, y)
+    sp = torch.cuda.current_stream(self.device).cuda_stream
+    for f in self.frozen:
+      f.forward(self.lib, self.x, sp)
+    for c in self.candidates:
+      c.enqueue_eval(self.x, self.labels, self.labels_f, None, sp)
+    torch.cuda.current_stream(self.device).synchronize()
+    return [float(c.out3[2].item()) for c in self.candidates]
+
   # -- read-back ---------------------------------------------------------------
   def ema_losses(self) -> List[float]:
     """EMA adanet loss of each local candidate (candidate.py:125-129), one D2H read."""
@@ -389,3 +401,59 @@ class IterationPlan:
     """[n_candidates, 4] (sub_loss, ens_loss, adanet_loss, ema) of the most recent step."""
     row = (self.steps_done - 1) % self.trace_capacity
     return torch.stack([c.trace[row] for c in self.candidates]).cpu().numpy()
+
+
+class EnsembleEvalPlan:
+  """Forward-only evaluation of a finished ensemble (evaluate / predict and the
+  `previous_ensemble` candidate of the Evaluator): frozen members replayed with
+  adn_dense_fwd, then adn_ensemble_head for logits and loss
+  (adanet/core/estimator.py:1785-1882 rebuilds the same thing as a TF graph)."""
+
+  def __init__(self, members: Sequence[DenseNet], mix_w: np.ndarray, bias: np.ndarray, ens: EnsemblerPlanSpec,
+               head: str, batch: int, logits_dim: int, device: Optional[torch.device] = None):
+    self.lib = _require_cuda()
+    self.device = device or torch.device("cuda", torch.cuda.current_device())
+    self.members, self.batch, self.C, self.head = list(members), batch, logits_dim, _HEAD_KIND[head]
+    for m in self.members:
+      if m.batch != batch:
+        raise ValueError("member %s was built for batch %d, eval plan uses %d" % (m.name, m.batch, batch))
+    f32 = dict(dtype=torch.float32, device=self.device)
+    self.mix = _MIX_KIND[ens.mixture_weight_type]
+    self.mix_w = torch.as_tensor(np.ascontiguousarray(mix_w, dtype=np.float32)).to(self.device).reshape(
+        (len(members),) if self.mix == _lib.MIX_SCALAR else (len(members), logits_dim))
+    self.bias = torch.as_tensor(np.ascontiguousarray(bias, dtype=np.float32)).to(self.device)
+    lam, beta = float(ens.adanet_lambda), float(ens.adanet_beta)
+    self.reg_is_zero = int(lam == 0.0 and beta == 0.0)
+    self.gammas = [float(np.float32(beta) if lam == 0.0 else np.float32(np.float32(lam) * np.float32(m.complexity) + np.float32(beta)))
+                   for m in self.members]
+    self._gammas = _lib.f32_array(self.gammas)
+    self._members = _lib.ptr_array([m.logits.data_ptr() for m in self.members])
+    self.out3 = torch.zeros((3,), **f32)
+    self.ens_logits = torch.empty((batch, logits_dim), **f32)
+    self.ws_bytes = _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, len(self.members))
+    self.workspace = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=self.device)
+    self.x = torch.empty((batch, members[0].dims[0]), **f32)
+    self.labels = torch.zeros((batch,), dtype=torch.int64, device=self.device) if head == "softmax_xent" else None
+    self.labels_f = torch.zeros((batch, logits_dim), **f32) if head != "softmax_xent" else None
+
+  def run(self, x, y=None, forward_members: bool = True):
+    """Returns (loss, reg, adanet_loss) as floats (NaN-free only when labels given) and leaves
+    the ensemble logits in `self.ens_logits`."""
+    sp = torch.cuda.current_stream(self.device).cuda_stream
+    self.x.copy_(torch.as_tensor(x).reshape(self.x.shape), non_blocking=True)
+    if y is not None:
+      if self.labels is not None:
+        self.labels.copy_(torch.as_tensor(y).reshape(self.batch), non_blocking=True)
+      else:
+        self.labels_f.copy_(torch.as_tensor(y).reshape(self.batch, self.C), non_blocking=True)
+    if forward_members:
+      for m in self.members:
+        m.forward(self.lib, self.x, sp)
+    _lib.check(self.lib.adn_ensemble_head(
+        self.head, self.mix, self._members, len(self.members), self.mix_w.data_ptr(), self.bias.data_ptr(),
+        self._gammas, self.reg_is_zero, 1.0, self.labels.data_ptr() if self.labels is not None else None,
+        self.labels_f.data_ptr() if self.labels_f is not None else None, self.out3.data_ptr(), None, None, None,
+        self.ens_logits.data_ptr(), self.batch, self.C, self.workspace.data_ptr(), self.ws_bytes, sp),
+               "adn_ensemble_head")
+    o = self.out3.cpu().numpy()
+    return float(o[0]), float(o[1]), float(o[2])

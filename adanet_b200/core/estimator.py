@@ -1,0 +1,408 @@
+"""adanet.Estimator over the B200 engine.
+
+API mirror of adanet/core/estimator.py (`Estimator` :442-2222): constructor
+arguments and validation (:604-760), `train` (:809-999), `evaluate`, `predict`,
+selection (`_get_best_ensemble_index` :1415-1517) and the per-iteration
+`architecture-{t}.json` files (:1408-1413, :1725-1747).  What the reference
+does by rebuilding a TF graph 3-4 times per iteration and chaining checkpoints
+is a plain Python loop here: per iteration the candidates' builders are called
+once against a symbolic graph (core/lowering.py), lowered to a per-GPU
+`IterationPlan` (core/engine.py) and stepped with CUDA kernels; selection,
+growth and the frozen replay happen in HBM.
+
+Out of scope: TensorBoard summaries, report
+materialisation, TPU, SavedModel export, parameter-server placement.
+"""
+
+from __future__ import annotations
+
+import inspect
+import json
+import logging
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from adanet_b200 import ensemble as ensemble_lib
+from adanet_b200 import graph
+from adanet_b200 import train as train_lib
+from adanet_b200.core import input_utils
+from adanet_b200.core.architecture import _Architecture
+
+
+class RunConfig:
+  """The RunConfig fields the estimator reads (tf.estimator.RunConfig stand-in)."""
+
+  def __init__(self, model_dir=None, tf_random_seed=None, num_worker_replicas=None, global_id_in_cluster=None,
+               is_chief=None, **unused):
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rk = int(os.environ.get("RANK", "0"))
+    self.model_dir = model_dir
+    self.tf_random_seed = tf_random_seed
+    self.num_worker_replicas = num_worker_replicas if num_worker_replicas is not None else ws
+    self.global_id_in_cluster = global_id_in_cluster if global_id_in_cluster is not None else rk
+    self.num_ps_replicas = 0
+    self.is_chief = is_chief if is_chief is not None else (self.global_id_in_cluster == 0)
+
+
+class Estimator(object):
+  """An AdaNet estimator: learns an ensemble of subnetworks over iterations.
+
+  Args are those of adanet/core/estimator.py:604-631.  `head` is one of
+  adanet_b200.heads.*; `subnetwork_generator` an adanet_b200.subnetwork.Generator
+  whose builders use the adanet_b200.graph vocabulary; `ensemblers` defaults to
+  one ComplexityRegularizedEnsembler built from the legacy kwargs
+  (mixture_weight_type, adanet_lambda, adanet_beta, use_bias,
+  warm_start_mixture_weights, mixture_weight_initializer); `ensemble_strategies`
+  defaults to [GrowStrategy()].
+  """
+
+  def __init__(self, head, subnetwork_generator, max_iteration_steps, ensemblers=None, ensemble_strategies=None,
+               evaluator=None, report_materializer=None, metric_fn=None, force_grow=False,
+               replicate_ensemble_in_training=False, adanet_loss_decay=.9, delay_secs_per_worker=5,
+               max_worker_delay_secs=60, worker_wait_secs=5, worker_wait_timeout_secs=7200, model_dir=None,
+               report_dir=None, config=None, debug=False, enable_ensemble_summaries=True,
+               enable_subnetwork_summaries=True, global_step_combiner_fn=None, max_iterations=None,
+               export_subnetwork_logits=False, export_subnetwork_last_layer=True, replay_config=None, **kwargs):
+    if subnetwork_generator is None:
+      raise ValueError("subnetwork_generator can't be None.")
+    if max_iteration_steps is not None and max_iteration_steps <= 0.:
+      raise ValueError("max_iteration_steps must be > 0 or None.")
+    if max_iterations is not None and max_iterations <= 0.:
+      raise ValueError("max_iterations must be > 0 or None.")
+    self._config = config or RunConfig(model_dir=model_dir)
+    is_distributed_training = self._config.num_worker_replicas and self._config.num_worker_replicas > 1
+    self._model_dir = model_dir or getattr(self._config, "model_dir", None)
+    if is_distributed_training and not self._model_dir:
+      raise ValueError("For distributed training, a model_dir must be specified.")
+    self._head = head
+    self._subnetwork_generator = subnetwork_generator
+    self._max_iteration_steps = max_iteration_steps
+    self._evaluator = evaluator
+    self._report_materializer = report_materializer
+    self._force_grow = force_grow
+    self._adanet_loss_decay = adanet_loss_decay
+    self._max_iterations = max_iterations
+    self._replay_config = replay_config
+    self._debug = debug
+    default_ensembler_args = ["mixture_weight_type", "mixture_weight_initializer", "warm_start_mixture_weights",
+                              "adanet_lambda", "adanet_beta", "use_bias"]
+    default_ensembler_kwargs = {k: v for k, v in kwargs.items() if k in default_ensembler_args}
+    if default_ensembler_kwargs:
+      logging.warning("The following arguments have been moved to `adanet.ensemble.ComplexityRegularizedEnsembler` "
+                      "which can be specified in the `ensemblers` argument: %s", sorted(default_ensembler_kwargs.keys()))
+    for key in default_ensembler_kwargs:
+      del kwargs[key]
+    self._placement_strategy = kwargs.pop("experimental_placement_strategy", None)
+    if default_ensembler_kwargs and ensemblers:
+      raise ValueError("When specifying the `ensemblers` argument, the following arguments must not be given: {}".format(
+          default_ensembler_kwargs.keys()))
+    if not ensemblers:
+      if default_ensembler_kwargs.get("warm_start_mixture_weights"):
+        default_ensembler_kwargs["model_dir"] = self._model_dir or "."
+      ensemblers = [ensemble_lib.ComplexityRegularizedEnsembler(**default_ensembler_kwargs)]
+    self._ensemblers = list(ensemblers)
+    self._ensemble_strategies = list(ensemble_strategies or [ensemble_lib.GrowStrategy()])
+    if self._model_dir:
+      os.makedirs(self._model_dir, exist_ok=True)
+    # run state
+    self._search = None
+    self._global_step = 0
+    self._iteration_step = 0
+    self._batch_size = None
+    self._feature_keys = None
+    self._in_dim = None
+    self._member_subnetworks = []     # Subnetwork namedtuple of every frozen member
+    self._member_builders = []
+    self._previous_ensemble = None
+    self._pending = None              # (builders, subnetworks) of the iteration being trained
+    self._eval_plan = None
+    self._last_candidate_name = None
+    self._architecture = None
+
+  # ------------------------------------------------------------------ properties
+  @property
+  def model_dir(self):
+    return self._model_dir
+
+  @property
+  def config(self):
+    return self._config
+
+  def latest_checkpoint(self):
+    if not self._model_dir:
+      return None
+    p = os.path.join(self._model_dir, "ensemble-latest.npz")
+    return p if os.path.exists(p) else None
+
+  # ------------------------------------------------------------------ engine wiring
+  def _ensembler_plan_spec(self):
+    from adanet_b200.core import engine as eng
+    if len(self._ensemblers) != 1:
+      raise NotImplementedError("the B200 engine trains one ensembler per run (got %d)" % len(self._ensemblers))
+    e = self._ensemblers[0]
+    if isinstance(e, ensemble_lib.MeanEnsembler):
+      # mean over the NEW subnetworks only (adanet/ensemble/mean.py:92-101): under GrowStrategy that is the
+      # new subnetwork itself; realised as SCALAR weights (0 for kept members, 1 for the new one), no training
+      raise NotImplementedError("MeanEnsembler is a 'next' row (SURVEY.md 8f.3); use ComplexityRegularizedEnsembler")
+    if not isinstance(e, ensemble_lib.ComplexityRegularizedEnsembler):
+      raise NotImplementedError("custom Ensemblers are not supported by the B200 engine: %r" % (e,))
+    if e.mixture_weight_type == ensemble_lib.MixtureWeightType.MATRIX:
+      raise NotImplementedError("MATRIX mixture weights are a 'next' row (SURVEY.md 8f.3)")
+    if e.warm_start_mixture_weights:
+      raise NotImplementedError("warm_start_mixture_weights is a 'next' row (SURVEY.md 8f.3)")
+    return eng.EnsemblerPlanSpec(optimizer=train_lib.optimizer_from(e.optimizer), mixture_weight_type=e.mixture_weight_type,
+                                 adanet_lambda=e.adanet_lambda, adanet_beta=e.adanet_beta, use_bias=e.use_bias,
+                                 name=e.name)
+
+  def _check_strategies(self):
+    for s in self._ensemble_strategies:
+      if not isinstance(s, ensemble_lib.GrowStrategy):
+        raise NotImplementedError("only GrowStrategy shards one-candidate-per-GPU (SURVEY.md 8e); %s is a 'next' row"
+                                  % type(s).__name__)
+
+  def _generate_builders(self, iteration_number):
+    gen = self._subnetwork_generator
+    kwargs = dict(previous_ensemble=self._previous_ensemble, iteration_number=iteration_number,
+                  previous_ensemble_reports=[], all_reports=[])
+    if "config" in inspect.signature(gen.generate_candidates).parameters:
+      kwargs["config"] = self._config
+    builders = list(gen.generate_candidates(**kwargs))
+    if not builders:
+      raise ValueError("Each iteration must have at least one Builder.")
+    return builders
+
+  def _search_space(self, iteration_number, frozen):
+    """Generator -> Strategy -> Builder.build_subnetwork -> lowering, for iteration t
+    (adanet/core/estimator.py:2107-2117 + iteration.py:628-652)."""
+    from adanet_b200.core import lowering
+    builders = self._generate_builders(iteration_number)
+    names = [b.name for b in builders]
+    for n in names:
+      if names.count(n) > 1:
+        raise ValueError("Two subnetworks have the same name '{}'".format(n))
+    cands = []
+    for strategy in self._ensemble_strategies:
+      cands += list(strategy.generate_ensemble_candidates(builders, list(self._member_builders)))
+    for c in cands:
+      if len(c.subnetwork_builders) != 1:
+        raise NotImplementedError("candidates with several new subnetworks are a 'next' row (SURVEY.md 8e)")
+      if len(c.previous_ensemble_subnetwork_builders) != len(self._member_builders):
+        raise NotImplementedError("pruning the previous ensemble is not implemented by the B200 engine")
+    placeholders = {k: graph.placeholder(w, k) for k, w in self._feature_widths.items()}
+    labels_ph = graph.placeholder(1, "labels")
+    specs, subs = [], []
+    for b in builders:
+      spec, sub = lowering.build_and_lower(b, placeholders, labels_ph, self._head, iteration_step=0,
+                                           previous_ensemble=self._previous_ensemble, in_dim=self._in_dim,
+                                           config=self._config)
+      specs.append(spec)
+      subs.append(sub)
+    self._pending = (builders, subs)
+    return specs
+
+  def _ensure_search(self, features):
+    from adanet_b200.core import search as srch
+    if self._search is not None:
+      return
+    self._check_strategies()
+    self._batch_size = input_utils.batch_size_of(features)
+    widths = input_utils.feature_widths(features)
+    self._feature_keys = sorted(widths)
+    self._feature_widths = widths
+    self._in_dim = sum(widths.values())
+    replay = self._replay_config.best_ensemble_indices if self._replay_config else None
+    self._search = srch.AdaNetSearch(self._search_space, self._ensembler_plan_spec(), self._in_dim,
+                                     self._head.logits_dimension, self._batch_size, head=self._head.loss_kind,
+                                     adanet_loss_decay=self._adanet_loss_decay, force_grow=self._force_grow,
+                                     replay_indices=replay, keep_traces=bool(self._debug))
+
+  # ------------------------------------------------------------------ train
+  def train(self, input_fn, hooks=None, steps=None, max_steps=None, saving_listeners=None):
+    """Trains for `steps` more steps or until `max_steps` global steps
+    (adanet/core/estimator.py:809-999).  An AdaNet iteration ends after
+    `max_iteration_steps` steps (or when the input is exhausted); the best
+    candidate is then selected and frozen, and the next iteration starts."""
+    if steps is not None and max_steps is not None:
+      raise ValueError("Can not provide both steps and max_steps.")
+    if steps is not None and steps <= 0:
+      raise ValueError("Must specify steps > 0, given: {}".format(steps))
+    if max_steps is not None and max_steps <= 0:
+      raise ValueError("Must specify max_steps > 0, given: {}".format(max_steps))
+    limit = None
+    if steps is not None:
+      limit = self._global_step + steps
+    if max_steps is not None:
+      limit = max_steps
+      if self._global_step >= max_steps:
+        logging.info("Skipping training since max_steps has already saved.")
+        return self
+    done_iterations = lambda: self._search.iteration if self._search else 0
+    for features, labels in input_utils.iterate_input_fn(input_fn):
+      if self._max_iterations and done_iterations() >= self._max_iterations:
+        break
+      if limit is not None and self._global_step >= limit:
+        break
+      self._ensure_search(features)
+      bs = input_utils.batch_size_of(features)
+      if bs != self._batch_size:
+        input_utils.warn_ragged(bs, self._batch_size)
+        continue
+      if self._search.plan is None:
+        self._search.build_iteration()
+        self._iteration_step = 0
+      x = input_utils.to_matrix(features, self._feature_keys)
+      self._search.plan.train_step(x, labels)
+      self._global_step += 1
+      self._iteration_step += 1
+      if self._max_iteration_steps is not None and self._iteration_step >= self._max_iteration_steps:
+        self._bookkeeping()
+    else:
+      # input exhausted: the iteration is over (iteration.py:274-284 stops each spec on OutOfRangeError)
+      if self._search is not None and self._search.plan is not None and self._iteration_step > 0 and (
+          limit is None or self._global_step < limit):
+        self._bookkeeping()
+    return self
+
+  def _bookkeeping(self):
+    """_execute_bookkeeping_phase (estimator.py:1247-1283): evaluate candidates, pick the best,
+    write architecture-{t}.json, grow."""
+    s = self._search
+    t = s.iteration
+    builders, subs = self._pending
+    if self._evaluator is not None:
+      ev = self._evaluator
+      prev_metric = None
+      if t > 0:
+        plan_prev = self._ensemble_eval_plan()
+        prev_metric = ev.evaluate(lambda f, l: [plan_prev.run(input_utils.to_matrix(f, self._feature_keys), l)[2]], 1)[0]
+      def local_metric(plan):
+        return ev.evaluate(lambda f, l: plan.eval_step(input_utils.to_matrix(f, self._feature_keys), l),
+                           len(plan.candidates))
+      rep = s.finish_iteration(local_metric_fn=local_metric, previous_metric=prev_metric, objective_fn=ev.objective_fn)
+    else:
+      rep = s.finish_iteration()
+    ens = self._ensemblers[0]
+    if s.last_winner_index is not None:
+      ci = s.last_winner_index
+      self._member_subnetworks.append(subs[ci])
+      self._member_builders.append(builders[ci])
+      cand_name = "{}_grow".format(builders[ci].name)
+    else:
+      cand_name = self._last_candidate_name
+    self._last_candidate_name = cand_name
+    # previous_ensemble handed to the generator / builders of iteration t+1 (weighted.py:90-136)
+    ws = []
+    mw = np.asarray(rep.mixture_weights)
+    for k, (sub, (it, name)) in enumerate(zip(self._member_subnetworks, rep.architecture)):
+      ws.append(ensemble_lib.WeightedSubnetwork(name=name, iteration_number=it, weight=np.array(mw[k]), logits=sub.logits,
+                                                subnetwork=sub))
+    self._previous_ensemble = ensemble_lib.ComplexityRegularized(
+        weighted_subnetworks=ws, bias=np.asarray(rep.bias), logits=("weighted_sum", [w.logits for w in ws]),
+        subnetworks=[w.subnetwork for w in ws],
+        complexity_regularization=ens.complexity_regularization([w.weight for w in ws],
+                                                                [w.subnetwork.complexity for w in ws]))
+    arch = _Architecture(cand_name, ens.name, replay_indices=list(rep.replay_indices))
+    for it, name in rep.architecture:
+      arch.add_subnetwork(it, name)
+    self._architecture = arch
+    self._eval_plan = None
+    self._iteration_step = 0
+    if self._model_dir and self._config.is_chief:
+      with open(os.path.join(self._model_dir, "architecture-{}.json".format(t)), "w") as f:
+        f.write(arch.serialize(t, self._global_step))
+      self._save_ensemble()
+    logging.info("iteration %d: best ensemble '%s' (index %d)", t, rep.candidate_names[rep.best_index], rep.best_index)
+    return rep
+
+  def _save_ensemble(self):
+    """The final ensemble's parameters (replaces the reference's increment.ckpt-{t})."""
+    s = self._search
+    out = {"global_step": self._global_step, "iteration": s.iteration, "mixture_weights": s.mixture_weights,
+           "bias": s.bias}
+    for k, m in enumerate(s.frozen):
+      ws, bs = m.numpy_params()
+      for i, (w, b) in enumerate(zip(ws, bs)):
+        out["m{}_w{}".format(k, i)] = w
+        out["m{}_b{}".format(k, i)] = b
+    np.savez(os.path.join(self._model_dir, "ensemble-latest.npz"), **out)
+
+  # ------------------------------------------------------------------ evaluate / predict
+  def _ensemble_eval_plan(self):
+    from adanet_b200.core import engine as eng
+    s = self._search
+    if s is None or not s.frozen:
+      raise ValueError("no trained ensemble yet: train at least one AdaNet iteration before evaluate/predict")
+    if self._eval_plan is None:
+      self._eval_plan = eng.EnsembleEvalPlan(s.frozen, s.mixture_weights, s.bias, s.ens, s.head, s.batch, s.C, s.device)
+    return self._eval_plan
+
+  def architecture_string(self):
+    """`architecture/adanet/ensembles` text (adanet/core/eval_metrics.py:243-244)."""
+    return "| {} |".format(" | ".join(name for _, name in self._architecture.subnetworks))
+
+  def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):
+    """Mean loss of the best ensemble over `steps` batches (+ accuracy for classification),
+    `global_step`, `iteration` and the architecture string (eval_metrics.py:227-264,347-393)."""
+    plan = self._ensemble_eval_plan()
+    n, loss_sum, correct, total = 0, 0.0, 0, 0
+    for features, labels in input_utils.iterate_input_fn(input_fn):
+      if steps is not None and n >= steps:
+        break
+      if input_utils.batch_size_of(features) != self._batch_size:
+        input_utils.warn_ragged(input_utils.batch_size_of(features), self._batch_size)
+        continue
+      loss, _, _ = plan.run(input_utils.to_matrix(features, self._feature_keys), labels)
+      loss_sum += loss
+      n += 1
+      if self._head.loss_kind == "softmax_xent":
+        import torch
+        pred = plan.ens_logits.argmax(dim=1).cpu()
+        lab = torch.as_tensor(labels).reshape(-1).cpu()
+        correct += int((pred == lab).sum())
+        total += int(lab.numel())
+    if n == 0:
+      raise ValueError("evaluate: input_fn produced no full batches")
+    out = {"loss": loss_sum / n, "average_loss": loss_sum / n, "global_step": self._global_step,
+           "iteration": self._search.iteration, "architecture/adanet/ensembles": self.architecture_string()}
+    if total:
+      out["accuracy"] = correct / total
+    return out
+
+  def predict(self, input_fn, predict_keys=None, hooks=None, checkpoint_path=None, yield_single_examples=True):
+    """Yields per-example predictions of the best ensemble: logits (+ probabilities / class_ids
+    for MultiClassHead, logistic for BinaryClassHead, predictions for RegressionHead)."""
+    import torch
+    plan = self._ensemble_eval_plan()
+    for item in input_utils.iterate_input_fn(input_fn):
+      features = item[0] if isinstance(item, tuple) else item
+      if input_utils.batch_size_of(features) != self._batch_size:
+        input_utils.warn_ragged(input_utils.batch_size_of(features), self._batch_size)
+        continue
+      plan.run(input_utils.to_matrix(features, self._feature_keys), None)
+      logits = plan.ens_logits
+      out = {"logits": logits.cpu().numpy()}
+      if self._head.loss_kind == "softmax_xent":
+        out["probabilities"] = torch.softmax(logits, dim=1).cpu().numpy()
+        out["class_ids"] = logits.argmax(dim=1, keepdim=True).cpu().numpy()
+      elif self._head.loss_kind == "sigmoid_xent":
+        out["logistic"] = torch.sigmoid(logits).cpu().numpy()
+      else:
+        out["predictions"] = out["logits"]
+      if predict_keys:
+        out = {k: v for k, v in out.items() if k in predict_keys}
+      if yield_single_examples:
+        for i in range(self._batch_size):
+          yield {k: v[i] for k, v in out.items()}
+      else:
+        yield out
+
+  def export_saved_model(self, *args, **kwargs):
+    raise NotImplementedError("TF SavedModel export is outside the hot-path scope (SURVEY.md section 2); "
+                              "the trained ensemble is in model_dir/ensemble-latest.npz + architecture-*.json")
+
+  def get_variable_value(self, name):
+    if name == "global_step":
+      return self._global_step
+    raise KeyError(name)

@@ -121,23 +121,38 @@ class AdaNetSearch:
     end.synchronize()
     return start.elapsed_time(end) / 1e3
 
-  def finish_iteration(self, train_seconds: float = 0.0) -> IterationReport:
-    """Selection + growth (bookkeeping phase, estimator.py:1247-1283)."""
+  def finish_iteration(self, train_seconds: float = 0.0, local_metric_fn=None, previous_metric=None,
+                       objective_fn=None) -> IterationReport:
+    """Selection + growth (bookkeeping phase, estimator.py:1247-1283).
+
+    Without an Evaluator the candidates are compared on their EMA adanet losses
+    (estimator.py:1491-1495).  With one, `local_metric_fn(plan)` returns the
+    hold-out metric of each local candidate, `previous_metric` that of the
+    previous ensemble, and `objective_fn` is np.nanargmin / np.nanargmax
+    (estimator.py:1487-1490)."""
     plan, specs, t = self.plan, self._specs, self.iteration
     k = len(specs)
     g = ex.world()
-    new_losses = ex.gather_candidate_losses(plan.ema_losses(), k, device=self.device)
+    local = plan.ema_losses() if local_metric_fn is None else list(local_metric_fn(plan))
+    new_losses = ex.gather_candidate_losses(local, k, device=self.device)
     ens_name = self.ens.name
     names = ["t{}_{}_grow_{}".format(t, s.name, ens_name) for s in specs]
     losses = list(new_losses)
     if t > 0:
       names = ["previous_ensemble"] + names
-      losses = [self.prev_best_ema] + losses
+      losses = [self.prev_best_ema if local_metric_fn is None else previous_metric] + losses
     replay = None
     if self.replay_indices is not None and t < len(self.replay_indices):
       replay = self.replay_indices[t]
-    best = select_best_index(losses, t, self.force_grow, replay)
+    if objective_fn is None or replay is not None or len(losses) == 1 or (t > 0 and self.force_grow and len(losses) == 2):
+      best = select_best_index(losses, t, self.force_grow, replay)
+    elif self.force_grow and t > 0:
+      best = int(objective_fn(np.asarray(losses[1:], dtype=np.float32))) + 1
+    else:
+      best = int(objective_fn(np.asarray(losses, dtype=np.float32)))
+    ema_all = ex.gather_candidate_losses(plan.ema_losses(), k, device=self.device) if local_metric_fn is not None else new_losses
     traces = plan.traces() if self.keep_traces else None
+    self.last_winner_index = None
     if t > 0 and best == 0:
       pass   # previous ensemble kept; nothing grows
     else:
@@ -159,7 +174,8 @@ class AdaNetSearch:
       ex.broadcast_tensors(member.ws + member.bs + [mix_w, bias], src=owner)
       self.frozen = self.frozen + [member]
       self.architecture = self.architecture + [(t, spec.name)]
-      self.prev_best_ema = losses[best]
+      self.prev_best_ema = ema_all[ci]
+      self.last_winner_index = ci
       self.mixture_weights = mix_w.cpu().numpy().copy()
       self.bias = bias.cpu().numpy().copy()
     self.replay_trace = self.replay_trace + [best]
