@@ -22,12 +22,13 @@ MIX_SCALAR, MIX_VECTOR, MIX_MATRIX = 0, 1, 2
 OPT_SGD, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADAM = 0, 1, 2, 3
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 (Q_VERSION, Q_DENSE_BWD_WS, Q_HEAD_WS, Q_DENSE_FWD_PATH, Q_SM_COUNT, Q_LAUNCH_COUNT, Q_DENSE_BWD_PATH,
- Q_DENSE_FWD_WS) = range(8)
+ Q_DENSE_FWD_WS, Q_PLANES_BYTES, Q_DENSE_BWD_P_WS, Q_COLSUM_WS) = range(11)
 
 EXPORTS = (
     "adn_last_error", "adn_init", "adn_query", "adn_set_dense_path", "adn_dense_fwd", "adn_dense_bwd", "adn_head_loss",
     "adn_ensemble_head", "adn_opt_step", "adn_l1_norm", "adn_ema_update", "adn_record_scalars",
-    "adn_counter_add",
+    "adn_counter_add", "adn_planes_split", "adn_planes_merge", "adn_dense_fwd_p", "adn_dense_bwd_p", "adn_colsum",
+    "adn_opt_step_p",
 )
 
 
@@ -65,6 +66,13 @@ def load():
   lib.adn_ema_update.argtypes = [p, p, f32, p]
   lib.adn_record_scalars.argtypes = [POINTER(p), c_int, p, i64, p, i64, p]
   lib.adn_counter_add.argtypes = [p, i64, p]
+  lib.adn_planes_split.argtypes = [p, i64, i64, p, p]
+  lib.adn_planes_merge.argtypes = [p, i64, i64, p, p]
+  lib.adn_dense_fwd_p.argtypes = [p, p, p, p, p, i64, i64, i64, c_int, p]
+  lib.adn_dense_bwd_p.argtypes = [p, p, p, p, p, p, p, i64, i64, i64, c_int, p, i64, p]
+  lib.adn_colsum.argtypes = [p, i64, i64, p, p, i64, p]
+  lib.adn_opt_step_p.argtypes = [c_int, POINTER(p), POINTER(p), POINTER(p), POINTER(p), POINTER(i64), c_int,
+                                 POINTER(f32), p, POINTER(p), POINTER(i64), p]
   for name in EXPORTS:
     if name != "adn_last_error":
       getattr(lib, name).restype = c_int

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "dense_simt.cuh"
 #include "dense_tc.cuh"
+#include "planes.cuh"
 
 namespace adn {
 
@@ -65,6 +66,8 @@ extern "C" int adn_init(void) {
   if (rc) return rc;
   rc = tc::init();
   if (rc) return rc;
+  rc = pl::init();
+  if (rc) return rc;
   (void)sm_count();
   done.store(1);
   return ADN_OK;
@@ -106,6 +109,9 @@ extern "C" int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_
     case ADN_Q_DENSE_FWD_PATH: *out_host = pick_fwd_path(a, b, c); return ADN_OK;
     case ADN_Q_DENSE_BWD_PATH: *out_host = pick_bwd_path(a, b, c); return ADN_OK;
     case ADN_Q_SM_COUNT: *out_host = sm_count(); return ADN_OK;
+    case ADN_Q_PLANES_BYTES: *out_host = pl::planes_bytes(a, b); return ADN_OK;
+    case ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES: *out_host = pl::dense_bwd_workspace_bytes(a, b, c); return ADN_OK;
+    case ADN_Q_COLSUM_WORKSPACE_BYTES: *out_host = ceil_div(a, 512) * b * (int64_t)sizeof(float) + 256; return ADN_OK;
     case ADN_Q_LAUNCH_COUNT: *out_host = g_launches.load(); return ADN_OK;
     default: return fail(ADN_ERR_INVALID, "adn_query: unknown key %d", key);
   }
@@ -143,4 +149,50 @@ extern "C" int adn_dense_bwd(const float* x, const float* w, const float* dz, fl
                          as_stream(stream));
   return simt::dense_bwd(x, w, dz, dx, dw, db, batch, in, out, x_relu_mask, workspace, workspace_bytes,
                          as_stream(stream));
+}
+
+static bool bad_shape(int64_t a, int64_t b, int64_t c) {
+  return a <= 0 || b <= 0 || c <= 0 || a > INT32_MAX || b > INT32_MAX || c > INT32_MAX;
+}
+
+extern "C" int adn_planes_split(const float* src, int64_t rows, int64_t cols, float* planes, void* stream) {
+  if (!src || !planes) return fail(ADN_ERR_INVALID, "adn_planes_split: null pointer");
+  if (bad_shape(rows, cols, 1)) return fail(ADN_ERR_INVALID, "adn_planes_split: bad shape");
+  return pl::split(src, rows, cols, planes, as_stream(stream));
+}
+
+extern "C" int adn_planes_merge(const float* planes, int64_t rows, int64_t cols, float* dst, void* stream) {
+  if (!planes || !dst) return fail(ADN_ERR_INVALID, "adn_planes_merge: null pointer");
+  if (bad_shape(rows, cols, 1)) return fail(ADN_ERR_INVALID, "adn_planes_merge: bad shape");
+  return pl::merge(planes, rows, cols, dst, as_stream(stream));
+}
+
+extern "C" int adn_dense_fwd_p(const float* xp, const float* wp, const float* b, float* yp, float* y, int64_t batch,
+                               int64_t in, int64_t out, int act, void* stream) {
+  if (!xp || !wp) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p: null pointer");
+  if ((yp == nullptr) == (y == nullptr)) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p: exactly one of yp / y");
+  if (bad_shape(batch, in, out)) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p: bad shape");
+  if (act != ADN_ACT_NONE && act != ADN_ACT_RELU) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p: bad act %d", act);
+  return pl::dense_fwd(xp, wp, b, yp, y, batch, in, out, act, as_stream(stream));
+}
+
+extern "C" int adn_dense_bwd_p(const float* xp, const float* wp, const float* dzp, float* dxp, float* dx,
+                               float* dx_colsum, float* dw, int64_t batch, int64_t in, int64_t out, int x_relu_mask,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!xp || !dzp || !workspace) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: null pointer");
+  if ((dxp || dx) && !wp) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: wp required when dx requested");
+  if (dxp && dx) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: at most one of dxp / dx");
+  if (dx_colsum && !(dxp || dx)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: dx_colsum needs dx");
+  if (bad_shape(batch, in, out)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: bad shape");
+  return pl::dense_bwd(xp, wp, dzp, dxp, dx, dx_colsum, dw, batch, in, out, x_relu_mask, workspace, workspace_bytes,
+                       as_stream(stream));
+}
+
+extern "C" int adn_colsum(const float* x, int64_t rows, int64_t cols, float* out, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  if (!x || !out || !workspace) return fail(ADN_ERR_INVALID, "adn_colsum: null pointer");
+  if (bad_shape(rows, cols, 1)) return fail(ADN_ERR_INVALID, "adn_colsum: bad shape");
+  if (workspace_bytes < ceil_div(rows, 512) * cols * (int64_t)sizeof(float))
+    return fail(ADN_ERR_WORKSPACE, "adn_colsum: workspace too small");
+  return simt::colsum(x, out, rows, cols, reinterpret_cast<float*>(workspace), as_stream(stream));
 }

@@ -28,7 +28,27 @@ struct OptParams {
   int kind;
   float h0, h1, h2, h3;
   const int64_t* step_dev;
+  // optional split planes of 2-D parameters, refreshed with the update (planes.cu layout)
+  float* planes[kMaxTensors];     // hi plane base (nullable per tensor)
+  int64_t plane_lo_off[kMaxTensors];
+  int cols[kMaxTensors];
 };
+
+__device__ __forceinline__ void store_planes(const OptParams& o, int t, int64_t j, float v) {
+  float* pl = o.planes[t];
+  if (!pl) return;
+  const int cols = o.cols[t];
+  const int64_t rows = o.size[t] / cols;
+  const int64_t r = j / cols;
+  const int c = (int)(j - r * cols);
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  const float hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  const int64_t dst = ((int64_t)(c >> 5) * rows + r) * 32 + (c & 31);
+  pl[dst] = hi;
+  pl[dst + o.plane_lo_off[t]] = __uint_as_float(l);
+}
 
 __device__ __forceinline__ void apply_one(int kind, float& p, float g, float& s0, float& s1, float h0, float h1,
                                           float h2, float h3, float lr_t) {
@@ -81,6 +101,8 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
         apply_one(o.kind, pv.z, gv.z, a.z, b.z, o.h0, o.h1, o.h2, o.h3, lr_t);
         apply_one(o.kind, pv.w, gv.w, a.w, b.w, o.h0, o.h1, o.h2, o.h3, lr_t);
         *reinterpret_cast<float4*>(p + i) = pv;
+        store_planes(o, t, i, pv.x); store_planes(o, t, i + 1, pv.y);
+        store_planes(o, t, i + 2, pv.z); store_planes(o, t, i + 3, pv.w);
         if (s0) *reinterpret_cast<float4*>(s0 + i) = a;
         if (s1) *reinterpret_cast<float4*>(s1 + i) = b;
       } else {
@@ -88,6 +110,7 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
           float pv = p[j], a = s0 ? s0[j] : 0.f, b = s1 ? s1[j] : 0.f;
           apply_one(o.kind, pv, g[j], a, b, o.h0, o.h1, o.h2, o.h3, lr_t);
           p[j] = pv;
+          store_planes(o, t, j, pv);
           if (s0) s0[j] = a;
           if (s1) s1[j] = b;
         }
@@ -98,6 +121,7 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
       float pv = p[j], a = s0 ? s0[j] : 0.f, b = s1 ? s1[j] : 0.f;
       apply_one(o.kind, pv, g[j], a, b, o.h0, o.h1, o.h2, o.h3, lr_t);
       p[j] = pv;
+      store_planes(o, t, j, pv);
       if (s0) s0[j] = a;
       if (s1) s1[j] = b;
     }
@@ -110,9 +134,19 @@ __global__ void step_increment_kernel(int64_t* step) { *step += 1; }
 
 using namespace adn;
 
+namespace adn { namespace pl { int64_t plane_floats(int64_t rows, int64_t cols); } }
+
 extern "C" int adn_opt_step(int kind, float* const* params_host, const float* const* grads_host,
                             float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
                             int n_tensors, const float* hyper_host, int64_t* step_dev, void* stream) {
+  return adn_opt_step_p(kind, params_host, grads_host, slot0_host, slot1_host, sizes_host, n_tensors, hyper_host,
+                        step_dev, nullptr, nullptr, stream);
+}
+
+extern "C" int adn_opt_step_p(int kind, float* const* params_host, const float* const* grads_host,
+                              float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
+                              int n_tensors, const float* hyper_host, int64_t* step_dev,
+                              float* const* planes_host, const int64_t* cols_host, void* stream) {
   if (kind < ADN_OPT_SGD || kind > ADN_OPT_ADAM) return fail(ADN_ERR_INVALID, "adn_opt_step: bad kind %d", kind);
   if (n_tensors < 1 || n_tensors > kMaxTensors)
     return fail(ADN_ERR_UNSUPPORTED, "adn_opt_step: n_tensors %d not in [1,%d]", n_tensors, kMaxTensors);
@@ -134,6 +168,14 @@ extern "C" int adn_opt_step(int kind, float* const* params_host, const float* co
     if ((need_slots >= 1 && !o.s0[t]) || (need_slots >= 2 && !o.s1[t]))
       return fail(ADN_ERR_INVALID, "adn_opt_step: slot for tensor %d is null", t);
     o.size[t] = sizes_host[t];
+    o.planes[t] = nullptr;
+    if (planes_host && planes_host[t]) {
+      if (!cols_host || cols_host[t] <= 0 || sizes_host[t] % cols_host[t] != 0 || cols_host[t] > INT32_MAX)
+        return fail(ADN_ERR_INVALID, "adn_opt_step_p: tensor %d: cols must divide its size", t);
+      o.planes[t] = planes_host[t];
+      o.cols[t] = (int)cols_host[t];
+      o.plane_lo_off[t] = pl::plane_floats(sizes_host[t] / cols_host[t], cols_host[t]);
+    }
     o.chunk_start[t] = chunks;
     chunks += (int)ceil_div(sizes_host[t], kChunk);
   }

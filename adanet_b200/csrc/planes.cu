@@ -1,0 +1,723 @@
+// Plane-native tcgen05 dense pipeline: fp32-accurate GEMMs (3xTF32) whose operands
+// AND results live in HBM as pre-split TF32 planes, so no conversion pass sits
+// between the layers of a subnetwork.
+//
+// Split planes of a matrix T[rows, cols] (fp32):
+//     hi = rna_tf32(T)          lo = rna_tf32(T - hi)
+//   each stored k-block-major   plane[cols/32][rows][32]   (cols zero padded to 32),
+//   one buffer: hi plane followed by lo plane (adn_query(ADN_Q_PLANES_BYTES)).
+// One layout serves every GEMM of training because tcgen05 takes either operand
+// K-major or MN-major straight from shared memory:
+//     K  = cols of T : box {32, 128 rows, 1 kb}   -> K-major  [128 rows][32 k]      SWIZZLE_128B
+//     K  = rows of T : box {32, 32 rows, 4 kb}    -> MN-major [4][32 k][32 mn]     SWIZZLE_128B_ATOM_32B
+//   both boxes are 16 KiB and contiguous per 16 KiB / 4 KiB run.
+//     fwd  Y = X W       A = Xp  K-major (K=in)    B = Wp  MN-major (N=out, K=in)
+//     dX   = dZ W^T      A = dZp K-major (K=out)   B = Wp  K-major  (N=in,  K=out)
+//     dW   = X^T dZ      A = Xp  MN-major (M=in)   B = dZp MN-major (N=out), K = batch
+//   -> no transposed copies, and the epilogue of one GEMM writes the planes the
+//   next one reads (bias+ReLU for fwd, ReLU mask + column sums for dX).
+//
+// Arithmetic: a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (fp32 accumulate in TMEM).
+// The tensor core truncates its accumulator on every add, so hi*hi partial sums
+// stay in TMEM for 128 K only and are then added in registers with RN
+// (profiles/r1a_accuracy_probe_*.txt); cross terms use their own accumulator.
+//
+// Kernel: persistent, one CTA per SM, 192 threads, warp-specialised
+//   warp 0    TMA producer (3-stage ring, 64 KiB per stage: A_hi A_lo B_hi B_lo)
+//   warp 1    MMA issuer (elected lane; 12 x tcgen05.mma.kind::tf32 M128 N128 K8 per stage)
+//   warps 2-5 epilogue: tcgen05.ld -> registers -> per-warp smem transpose ->
+//             bias/ReLU | mask | partial -> hi/lo split -> coalesced 512 B stores
+//
+// Reference arithmetic replaced: tf.layers.dense and its gradients,
+//   adanet/examples/simple_dnn.py:72-86,103-110.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "dense_simt.cuh"
+#include "planes.cuh"
+
+namespace adn {
+namespace pl {
+
+static constexpr int BM = 128, BN = 128, BK = 32;
+static constexpr int STAGES = 3;
+static constexpr int CHUNK = 4;                       // k-blocks per TMEM accumulation chunk (K = 128)
+static constexpr int TILE_BYTES = 128 * BK * 4;       // 16 KiB
+static constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi A_lo B_hi B_lo
+static constexpr int EPI_STAGE_FLOATS = 32 * 33;      // per epilogue warp: 32x32 slice transposed through smem
+static constexpr int EPI_BYTES = 4 * EPI_STAGE_FLOATS * 4;
+static constexpr int BAR_BYTES = 256;
+static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+static constexpr int NUM_THREADS = 192;
+static constexpr int TMEM_COLS = 512;                 // H0 [0,128) H1 [128,256) S0 [256,384) S1 [384,512)
+static constexpr int MAX_SPLITS = 64;
+
+enum { EPI_BIAS_ACT = 0, EPI_MASK = 1, EPI_PARTIAL = 2 };
+
+struct GemmParams {
+  int M, N;
+  int tiles_m, tiles_n, splits;
+  int total_kb;          // k-blocks of 32 over the whole K
+  int kb_per_split;
+  int a_mn, b_mn;        // operand majorness (0 = K-major box, 1 = MN-major box)
+  // output: dense row-major (ldc) / split-K partial [split][M][N], or planes
+  float* out;            // dense base | hi plane base
+  float* out_lo;         // lo plane base (OUT_PLANES)
+  int ldc;
+  int out_nkb;           // planes: k-blocks of the output tensor (ceil(N/32))
+  const float* bias;     // EPI_BIAS_ACT (nullable)
+  int act;
+  const float* mask_hi;  // EPI_MASK (nullable): hi plane of a [M, N] tensor; out = mask > 0 ? out : 0
+  float* colsum_part;    // EPI_MASK (nullable): [ceil(M/32)][colsum_ld] per-32-row column sums of out
+  int colsum_ld;
+};
+
+// ---------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a broken pipeline traps (CUDA error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((it & 1023u) == 1023u) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), 32-bit elements:
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout type
+//   K-major  tile [128 rows][32 k], SWIZZLE_128B (type 2): SBO = 1024 (8 rows x 128 B), LBO unused (=1);
+//            next K=8 step: +32 B
+//   MN-major tile [4 mn-blocks][32 k][32 mn]: 32-bit operands must use the 32 B-granular 128 B swizzle
+//            SWIZZLE_128B_BASE32B (type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; cute Layout_MN_SW128_32B_Atom:
+//            atom = 32 mn x 4 k rows): LBO = 4096 (next 32-wide mn block), SBO = 512 (next 4 k rows);
+//            next K=8 step: +1024 B
+__device__ __forceinline__ uint32_t desc_hi_word(int mn_major) {
+  return mn_major ? ((uint32_t)(512 >> 4) | (1u << 14) | (1u << 29)) : ((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29));
+}
+__device__ __forceinline__ uint32_t desc_lo_word(uint32_t smem_addr, int mn_major) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((mn_major ? (4096u >> 4) : 1u) << 16);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
+// a_major [15], b_major [16] (0 = K, 1 = MN), n_dim=N>>3 [17,23), m_dim=M>>4 [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t da_hi, uint32_t db_hi,
+                                          uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(da_lo), "r"(db_lo), "r"(da_hi), "r"(db_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  lo = __uint_as_float(l);
+}
+
+// work item -> (tile_m, tile_n, split).  n fastest so concurrently resident CTAs share A tiles.
+struct Item {
+  int m0, n0, kb0, nkb, split;
+};
+__device__ __forceinline__ Item decode_item(const GemmParams& g, int item) {
+  Item it;
+  const int tiles = g.tiles_m * g.tiles_n;
+  it.split = item / tiles;
+  const int t = item - it.split * tiles;
+  const int tm = t / g.tiles_n;
+  it.m0 = tm * BM;
+  it.n0 = (t - tm * g.tiles_n) * BN;
+  it.kb0 = it.split * g.kb_per_split;
+  it.nkb = min(g.total_kb, it.kb0 + g.kb_per_split) - it.kb0;
+  return it;
+}
+
+// ---------------------------------------------------------------------------------
+// GEMM kernel
+// ---------------------------------------------------------------------------------
+template <int EPI, int OUT_PLANES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const GemmParams g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();   // SWIZZLE_128B tiles must sit on 1024 B boundaries
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;          // [2]       MMA -> epilogue (chunk ready)
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;     // [2]       epilogue -> MMA (chunk drained), count 4
+  uint64_t* s_empty = bars + 2 * STAGES + 4;       // [2]       epilogue -> MMA (small-term acc read), count 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int n_items = g.tiles_m * g.tiles_n * g.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi);
+    tma_prefetch_desc(&map_b_lo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(smem_u32(&acc_full[b]), 1);
+        mbar_init(smem_u32(&acc_empty[b]), 4);
+        mbar_init(smem_u32(&s_empty[b]), 4);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      const uint32_t smem0 = smem_u32(smem);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(g, item);
+        for (int kb = 0; kb < it.nkb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t base = smem0 + s * STAGE_BYTES;
+          const int kc = it.kb0 + kb;
+          // K-major box {32, 128 rows, 1 kb} at (0, row0, kc); MN-major box {32, 32 rows, 4 kb} at (0, kc*32, mn0/32)
+          const int a1 = g.a_mn ? kc * BK : it.m0, a2 = g.a_mn ? (it.m0 >> 5) : kc;
+          const int b1 = g.b_mn ? kc * BK : it.n0, b2 = g.b_mn ? (it.n0 >> 5) : kc;
+          tma_load_3d(&map_a_hi, fb, base + 0 * TILE_BYTES, 0, a1, a2);
+          tma_load_3d(&map_a_lo, fb, base + 1 * TILE_BYTES, 0, a1, a2);
+          tma_load_3d(&map_b_hi, fb, base + 2 * TILE_BYTES, 0, b1, b2);
+          tma_load_3d(&map_b_lo, fb, base + 3 * TILE_BYTES, 0, b1, b2);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // The warp runs the loop converged (all lanes wait on the barriers); only the issue is under
+    // elect.sync, so every operand is warp-uniform.  A 128x128x8 TF32 MMA retires every 64 clk: the
+    // issue loop keeps ring counters incremental and builds descriptors from 32-bit halves.
+    {
+      const uint32_t idesc = make_idesc(BM, BN, g.a_mn, g.b_mn);
+      const uint32_t dah = desc_hi_word(g.a_mn), dbh = desc_hi_word(g.b_mn);
+      const uint32_t smem0 = smem_u32(smem);
+      const uint32_t a_lo0 = desc_lo_word(smem0, g.a_mn);
+      const uint32_t b_lo0 = desc_lo_word(smem0 + 2 * TILE_BYTES, g.b_mn);
+      const uint32_t a_step = g.a_mn ? (1024u >> 4) : (32u >> 4);   // address-field advance per K=8 MMA
+      const uint32_t b_step = g.b_mn ? (1024u >> 4) : (32u >> 4);
+      uint32_t s = 0, ph = 0, gchunk = 0, tile_i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
+        const Item it = decode_item(g, item);
+        const uint32_t acc_s = tmem_base + 256 + (tile_i & 1) * 128;
+        mbar_wait(smem_u32(&s_empty[tile_i & 1]), ((tile_i >> 1) & 1) ^ 1);   // small-term accumulator free
+        tc_fence_after();
+        uint32_t s_accum = 0;                      // first small-term MMA of the tile overwrites
+        for (int kb = 0; kb < it.nkb; kb += CHUNK, ++gchunk) {
+          const uint32_t b = gchunk & 1;
+          mbar_wait(smem_u32(&acc_empty[b]), ((gchunk >> 1) & 1) ^ 1);      // chunk buffer drained
+          tc_fence_after();
+          const uint32_t acc_h = tmem_base + b * 128;
+          const int nk = min(CHUNK, it.nkb - kb);
+          uint32_t h_accum = 0;                    // first hi*hi MMA of the chunk overwrites
+          for (int kk = 0; kk < nk; ++kk) {
+            mbar_wait(smem_u32(&full_bar[s]), ph);
+            tc_fence_after();
+            const uint32_t so = s * (STAGE_BYTES >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / 8; ++k) {
+                const uint32_t a_hi = a_lo0 + so + k * a_step, a_lo = a_hi + (TILE_BYTES >> 4);
+                const uint32_t b_hi = b_lo0 + so + k * b_step, b_lo = b_hi + (TILE_BYTES >> 4);
+                umma_tf32(acc_s, a_lo, b_hi, dah, dbh, idesc, (k == 0) ? s_accum : 1u);
+                umma_tf32(acc_s, a_hi, b_lo, dah, dbh, idesc, 1u);
+                umma_tf32(acc_h, a_hi, b_hi, dah, dbh, idesc, (k == 0) ? h_accum : 1u);
+              }
+              umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs retire
+              if (kk == nk - 1) umma_commit(smem_u32(&acc_full[b]));   // chunk (and small terms) complete
+            }
+            __syncwarp();
+            s_accum = 1u;
+            h_accum = 1u;
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5: TMEM lane quadrant = warp % 4 =================
+    const int quad = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    float* stage = epi_stage + quad * EPI_STAGE_FLOATS;
+    uint32_t gchunk = 0, tile_i = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
+      const Item it = decode_item(g, item);
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      const int nchunks = (it.nkb + CHUNK - 1) / CHUNK;
+      for (int c = 0; c < nchunks; ++c, ++gchunk) {
+        const uint32_t b = gchunk & 1;
+        mbar_wait(smem_u32(&acc_full[b]), (gchunk >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_base + b * 128 + q * 32, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);   // fp32 RN adds
+        }
+        if (c == nchunks - 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + q * 32, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&acc_empty[b]));
+          if (c == nchunks - 1) mbar_arrive(smem_u32(&s_empty[tile_i & 1]));
+        }
+      }
+      // ---- tile output.  Each warp owns rows [mrow0, mrow0+32) x 128 columns, processed as four
+      // 32x32 slices: registers (lane = row) -> smem -> (lane = 4-column group of 4 rows) so that
+      // every global access of the warp covers whole 128 B lines (planes: one contiguous 512 B run).
+      const int mrow0 = it.m0 + quad * 32;
+      const int c4 = (lane & 7) * 4;
+      const int rsub = lane >> 3;
+      float* dense = g.out;
+      if (EPI == EPI_PARTIAL) dense += (size_t)it.split * g.M * g.N;
+      const bool dense_vec = !OUT_PLANES && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cbase = it.n0 + q * 32;
+        const int kbo = cbase >> 5;
+        const bool live = OUT_PLANES ? (kbo < g.out_nkb) : (cbase < g.N);   // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = acc[q * 32 + j];
+        __syncwarp();
+        if (live && mrow0 < g.M) {
+          const int col = cbase + c4;
+          float bias_v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (EPI == EPI_BIAS_ACT && g.bias) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (col + k < g.N) bias_v[k] = __ldg(g.bias + col + k);
+          }
+          float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rsub + 4 * i;
+            const int row = mrow0 + r;
+            const bool rv = row < g.M;
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = stage[r * 33 + c4 + k];
+            const size_t poff = ((size_t)kbo * g.M + row) * 32 + c4;   // plane offset of (row, col..col+3)
+            if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                v[k] += bias_v[k];
+                if (g.act == ADN_ACT_RELU) v[k] = fmaxf(v[k], 0.f);
+              }
+            } else if (EPI == EPI_MASK) {
+              if (g.mask_hi && rv) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(g.mask_hi + poff));
+                if (!(m.x > 0.f)) v[0] = 0.f;
+                if (!(m.y > 0.f)) v[1] = 0.f;
+                if (!(m.z > 0.f)) v[2] = 0.f;
+                if (!(m.w > 0.f)) v[3] = 0.f;
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (!rv || col + k >= g.N) v[k] = 0.f;     // K padding of the next GEMM must be exact zeros
+            if (EPI == EPI_MASK) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) cs[k] += v[k];
+            }
+            if (rv) {
+              if (OUT_PLANES) {
+                float h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) split_tf32(v[k], h[k], l[k]);
+                *reinterpret_cast<float4*>(g.out + poff) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(g.out_lo + poff) = make_float4(l[0], l[1], l[2], l[3]);
+              } else {
+                float* op = dense + (size_t)row * g.ldc + col;
+                if (dense_vec && col + 3 < g.N) {
+                  *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (col + k < g.N) op[k] = v[k];
+                }
+              }
+            }
+          }
+          if (EPI == EPI_MASK && g.colsum_part) {
+            // rows of this lane: rsub + 4i; fold the 4 row groups (lanes l, l^8, l^16, l^24) in a fixed order
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+            }
+            if (rsub == 0) {
+              float* cp = g.colsum_part + (size_t)(mrow0 >> 5) * g.colsum_ld + col;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (col + k < g.colsum_ld) cp[k] = cs[k];
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// dense <-> planes conversion (inputs x / labels-side gradients / weights; everything
+// between two GEMMs is written as planes by the producing epilogue instead)
+// ---------------------------------------------------------------------------------
+// src[rows, cols] row-major -> hi/lo[nkb][rows][32], zero padded in cols
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int rows, int cols,
+             int nkb) {
+  const int vec_per_row = nkb * 8;                       // float4 per padded row
+  const int64_t nvec = (int64_t)rows * vec_per_row;
+  const bool vec_src = ((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vec_per_row);
+    const int c = (int)(i % vec_per_row) * 4;
+    float v[4];
+    if (vec_src && c + 3 < cols) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * cols + c));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = (c + q < cols) ? __ldg(src + (size_t)r * cols + c + q) : 0.f;
+    }
+    float h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
+    const size_t dst = ((size_t)(c >> 5) * rows + r) * 32 + (c & 31);
+    *reinterpret_cast<float4*>(hi + dst) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// hi/lo[nkb][rows][32] -> dst[rows, cols] = hi + lo
+__global__ void __launch_bounds__(256)
+merge_kernel(const float* __restrict__ hi, const float* __restrict__ lo, float* __restrict__ dst, int rows, int cols,
+             int nkb) {
+  const int64_t n = (int64_t)rows * nkb * 32;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c32 = (int)(i & 31);
+    const int64_t t = i >> 5;
+    const int r = (int)(t % rows);
+    const int c = (int)(t / rows) * 32 + c32;
+    if (c < cols) dst[(size_t)r * cols + c] = hi[i] + lo[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+
+int init() {
+  static std::once_flag once;
+  static int rc = ADN_OK;
+  std::call_once(once, []() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) {
+      (void)cudaGetLastError();
+      rc = fail(ADN_ERR_CUDA, "pl::init: cuTensorMapEncodeTiled entry point unavailable");
+      return;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    bool ok = true;
+#define ADN_PL_ATTR(E, P) \
+  ok = ok && (cudaFuncSetAttribute(pl_gemm_kernel<E, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess)
+    ADN_PL_ATTR(EPI_BIAS_ACT, 0); ADN_PL_ATTR(EPI_BIAS_ACT, 1);
+    ADN_PL_ATTR(EPI_MASK, 0); ADN_PL_ATTR(EPI_MASK, 1);
+    ADN_PL_ATTR(EPI_PARTIAL, 0);
+#undef ADN_PL_ATTR
+    if (!ok) {
+      (void)cudaGetLastError();
+      rc = fail(ADN_ERR_CUDA, "pl::init: cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
+    }
+  });
+  return rc;
+}
+
+int64_t plane_floats(int64_t rows, int64_t cols) { return align_up(rows * ceil_div(cols, BK) * BK, 64); }
+int64_t planes_bytes(int64_t rows, int64_t cols) { return 2 * plane_floats(rows, cols) * (int64_t)sizeof(float); }
+
+// a plane tensor viewed as a GEMM operand
+struct Operand {
+  const float* hi;
+  const float* lo;
+  int64_t rows, nkb;
+  int mn_major;
+};
+static Operand operand(const float* planes, int64_t rows, int64_t cols, int mn_major) {
+  return Operand{planes, planes + plane_floats(rows, cols), rows, ceil_div(cols, BK), mn_major};
+}
+
+static int make_map(CUtensorMap* map, const float* plane, int64_t rows, int64_t nkb, int mn_major) {
+  if (!g_encode) return fail(ADN_ERR_CUDA, "pl: adn_init() was not called");
+  cuuint64_t gdim[3] = {(cuuint64_t)BK, (cuuint64_t)rows, (cuuint64_t)nkb};
+  cuuint64_t gstride[2] = {(cuuint64_t)BK * sizeof(float), (cuuint64_t)rows * BK * sizeof(float)};
+  cuuint32_t box_k[3] = {(cuuint32_t)BK, 128u, 1u};
+  cuuint32_t box_mn[3] = {(cuuint32_t)BK, 32u, 4u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(plane), gdim, gstride,
+                        mn_major ? box_mn : box_k, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ADN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld nkb=%lld mn=%d", (int)r,
+                                     (long long)rows, (long long)nkb, mn_major);
+  return ADN_OK;
+}
+
+template <int EPI, int OUT_PLANES>
+static int launch_gemm(const Operand& a, const Operand& b, GemmParams g, cudaStream_t st, const char* what) {
+  if ((reinterpret_cast<uintptr_t>(a.hi) | reinterpret_cast<uintptr_t>(a.lo) | reinterpret_cast<uintptr_t>(b.hi) |
+       reinterpret_cast<uintptr_t>(b.lo)) & 127)
+    return fail(ADN_ERR_INVALID, "%s: plane buffers must be 256 B aligned", what);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, a.hi, a.rows, a.nkb, a.mn_major))) return rc;
+  if ((rc = make_map(&ma_lo, a.lo, a.rows, a.nkb, a.mn_major))) return rc;
+  if ((rc = make_map(&mb_hi, b.hi, b.rows, b.nkb, b.mn_major))) return rc;
+  if ((rc = make_map(&mb_lo, b.lo, b.rows, b.nkb, b.mn_major))) return rc;
+  g.a_mn = a.mn_major;
+  g.b_mn = b.mn_major;
+  g.tiles_m = (int)ceil_div(g.M, BM);
+  g.tiles_n = (int)ceil_div(g.N, BN);
+  const int items = g.tiles_m * g.tiles_n * g.splits;
+  const int grid = std::min(items, sm_count());
+  pl_gemm_kernel<EPI, OUT_PLANES><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
+  ADN_CHECK_LAUNCH(what);
+  return ADN_OK;
+}
+
+int split(const float* src, int64_t rows, int64_t cols, float* planes, cudaStream_t st) {
+  const int64_t nkb = ceil_div(cols, BK);
+  const int64_t nvec = rows * nkb * 8;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nvec, 256), (int64_t)sm_count() * 16));
+  split_kernel<<<blocks, 256, 0, st>>>(src, planes, planes + plane_floats(rows, cols), (int)rows, (int)cols, (int)nkb);
+  ADN_CHECK_LAUNCH("planes split");
+  return ADN_OK;
+}
+
+int merge(const float* planes, int64_t rows, int64_t cols, float* dst, cudaStream_t st) {
+  const int64_t nkb = ceil_div(cols, BK);
+  const int64_t n = rows * nkb * 32;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 16));
+  merge_kernel<<<blocks, 256, 0, st>>>(planes, planes + plane_floats(rows, cols), dst, (int)rows, (int)cols, (int)nkb);
+  ADN_CHECK_LAUNCH("planes merge");
+  return ADN_OK;
+}
+
+// dW split-K: the partial buffer bounds the split count (<= 16M floats, <= 64 splits)
+static int max_dw_splits(int64_t in, int64_t out) {
+  int64_t s = (16LL << 20) / std::max<int64_t>(1, in * out);
+  if (s > MAX_SPLITS) s = MAX_SPLITS;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+// pick S minimising (persistent rounds) x (k-blocks per item) + a per-split reduction cost
+static int dw_splits(int64_t tiles, int64_t kblocks, int max_s) {
+  const int sms = sm_count();
+  int best = 1;
+  double best_t = 1e30;
+  for (int s = 1; s <= max_s && s <= kblocks; ++s) {
+    const int64_t kps = ceil_div(kblocks, s);
+    const int64_t s_eff = ceil_div(kblocks, kps);
+    const int64_t rounds = ceil_div(tiles * s_eff, sms);
+    const double t = (double)rounds * ((double)kps + 6.0) + 0.75 * (double)s_eff;
+    if (t < best_t) { best_t = t; best = (int)s_eff; }
+  }
+  return best;
+}
+
+int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
+  int64_t b = align_up((int64_t)max_dw_splits(in, out) * in * out * (int64_t)sizeof(float), 256);   // dW split-K partials
+  b += align_up(ceil_div(batch, 32) * in * (int64_t)sizeof(float), 256);                             // dx column sums per 32 rows
+  b += align_up(ceil_div(ceil_div(batch, 32), 512) * in * (int64_t)sizeof(float), 256);              // their second-level partials
+  return b + 512;
+}
+
+int dense_fwd(const float* xp, const float* wp, const float* bias, float* yp, float* y, int64_t batch, int64_t in,
+              int64_t out, int act, cudaStream_t st) {
+  const Operand a = operand(xp, batch, in, 0);    // A = x  [M=batch, K=in]  K-major
+  const Operand b = operand(wp, in, out, 1);      // B = w  [K=in, N=out]    MN-major
+  GemmParams g{};
+  g.M = (int)batch; g.N = (int)out;
+  g.total_kb = (int)ceil_div(in, BK); g.kb_per_split = g.total_kb; g.splits = 1;
+  g.bias = bias; g.act = act;
+  if (yp) {
+    g.out = yp; g.out_lo = yp + plane_floats(batch, out); g.out_nkb = (int)ceil_div(out, BK);
+    return launch_gemm<EPI_BIAS_ACT, 1>(a, b, g, st, "pl dense_fwd gemm (planes out)");
+  }
+  g.out = y; g.ldc = (int)out;
+  return launch_gemm<EPI_BIAS_ACT, 0>(a, b, g, st, "pl dense_fwd gemm (dense out)");
+}
+
+int dense_bwd(const float* xp, const float* wp, const float* dzp, float* dxp, float* dx, float* dx_colsum, float* dw,
+              int64_t batch, int64_t in, int64_t out, int x_relu_mask, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < dense_bwd_workspace_bytes(batch, in, out))
+    return fail(ADN_ERR_WORKSPACE, "pl dense_bwd: workspace %lld < %lld bytes", (long long)ws_bytes,
+                (long long)dense_bwd_workspace_bytes(batch, in, out));
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const int max_s = max_dw_splits(in, out);
+  float* part = reinterpret_cast<float*>(p);
+  p += align_up((int64_t)max_s * in * out * (int64_t)sizeof(float), 256);
+  float* cspart = reinterpret_cast<float*>(p);
+  p += align_up(ceil_div(batch, 32) * in * (int64_t)sizeof(float), 256);
+  float* cspart2 = reinterpret_cast<float*>(p);
+  const int64_t cs_ld = in;
+  int rc;
+  if (dw) {
+    // ---- dW[in,out] = X^T dZ : A = Xp MN-major (M=in), B = dZp MN-major (N=out), K = batch, split-K ----
+    const Operand a = operand(xp, batch, in, 1);
+    const Operand b = operand(dzp, batch, out, 1);
+    const int64_t kb_b = ceil_div(batch, BK);
+    const int S = dw_splits(ceil_div(in, BM) * ceil_div(out, BN), kb_b, max_s);
+    GemmParams g{};
+    g.M = (int)in; g.N = (int)out; g.ldc = (int)out;
+    g.total_kb = (int)kb_b; g.kb_per_split = (int)ceil_div(kb_b, S);
+    g.splits = (int)ceil_div(kb_b, g.kb_per_split);
+    g.out = (g.splits == 1) ? dw : part;
+    if ((rc = launch_gemm<EPI_PARTIAL, 0>(a, b, g, st, "pl dW gemm"))) return rc;
+    if (g.splits > 1 && (rc = simt::reduce_partials(part, dw, in * out, g.splits, in * out, st))) return rc;
+  }
+  if (dxp || dx) {
+    // ---- dX[batch,in] = dZ W^T : A = dZp K-major (K=out), B = Wp K-major (N=in, K=out); ReLU mask from Xp.hi ----
+    const Operand a = operand(dzp, batch, out, 0);
+    const Operand b = operand(wp, in, out, 0);
+    GemmParams g{};
+    g.M = (int)batch; g.N = (int)in;
+    g.total_kb = (int)ceil_div(out, BK); g.kb_per_split = g.total_kb; g.splits = 1;
+    g.mask_hi = x_relu_mask ? xp : nullptr;
+    g.colsum_part = dx_colsum ? cspart : nullptr;
+    g.colsum_ld = (int)cs_ld;
+    if (dxp) {
+      g.out = dxp; g.out_lo = dxp + plane_floats(batch, in); g.out_nkb = (int)ceil_div(in, BK);
+      if ((rc = launch_gemm<EPI_MASK, 1>(a, b, g, st, "pl dX gemm (planes out)"))) return rc;
+    } else {
+      g.out = dx; g.ldc = (int)in;
+      if ((rc = launch_gemm<EPI_MASK, 0>(a, b, g, st, "pl dX gemm (dense out)"))) return rc;
+    }
+    // column sums of the [ceil(batch/32), in] partial matrix, fixed order
+    if (dx_colsum && (rc = simt::colsum(cspart, dx_colsum, ceil_div(batch, 32), in, cspart2, st))) return rc;
+  }
+  return ADN_OK;
+}
+
+}  // namespace pl
+}  // namespace adn

@@ -70,6 +70,9 @@ extern "C" {
 #define ADN_Q_LAUNCH_COUNT 5              /* kernels launched by this library so far */
 #define ADN_Q_DENSE_BWD_PATH 6            /* a=batch b=in c=out */
 #define ADN_Q_DENSE_FWD_WORKSPACE_BYTES 7 /* a=batch b=in c=out (0 when the SIMT path is taken) */
+#define ADN_Q_PLANES_BYTES 8              /* a=rows b=cols -> bytes of a split-plane tensor */
+#define ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES 9 /* a=batch b=in c=out */
+#define ADN_Q_COLSUM_WORKSPACE_BYTES 10   /* a=rows b=cols */
 
 const char* adn_last_error(void);
 /* One-time, idempotent host-side initialisation (kernel attributes, driver entry
@@ -159,6 +162,44 @@ int adn_ensemble_head(int head, int mixture_type, const float* const* members_ho
 int adn_opt_step(int kind, float* const* params_host, const float* const* grads_host,
                  float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
                  int n_tensors, const float* hyper_host, int64_t* step_dev, void* stream);
+
+/*
+ * ---- plane-native dense pipeline (csrc/planes.cu) ---------------------------------
+ * A *split-plane tensor* of a matrix T[rows, cols] is hi = rna_tf32(T) and
+ * lo = rna_tf32(T - hi), each stored k-block-major [ceil(cols/32)][rows][32] (zero
+ * padded in cols), hi followed by lo in one buffer of adn_query(ADN_Q_PLANES_BYTES)
+ * bytes, 256 B aligned, ZERO-INITIALISED by the caller once (the K padding must stay
+ * zero).  It is the operand format of the tcgen05 3xTF32 GEMM: the same planes are
+ * read K-major or MN-major by TMA, so forward, dX and dW all consume them without a
+ * transposed copy, and each GEMM's epilogue writes the planes its consumer reads.
+ * The per-layer calls below replace the same reference arithmetic as adn_dense_fwd /
+ * adn_dense_bwd (adanet/examples/simple_dnn.py:72-86,103-110) for a whole subnetwork
+ * whose activations never leave the plane format.
+ */
+int adn_planes_split(const float* src, int64_t rows, int64_t cols, float* planes, void* stream);
+int adn_planes_merge(const float* planes, int64_t rows, int64_t cols, float* dst, void* stream);
+/* y = act(x @ w + b): xp planes [batch,in], wp planes [in,out]; result as planes (yp) or
+ * dense fp32 row-major (y) -- exactly one of the two is non-NULL. */
+int adn_dense_fwd_p(const float* xp, const float* wp, const float* b, float* yp, float* y,
+                    int64_t batch, int64_t in, int64_t out, int act, void* stream);
+/* Backward of one dense layer from planes: dzp planes [batch,out].
+ *   dw[in,out] (dense, nullable) = x^T dz
+ *   dx = (dz w^T) * (x_relu_mask ? x > 0 : 1) as planes (dxp) or dense (dx); both may be NULL
+ *   dx_colsum[in] (nullable) = column sums of dx = the bias gradient of the layer below
+ * workspace: adn_query(ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES). */
+int adn_dense_bwd_p(const float* xp, const float* wp, const float* dzp, float* dxp, float* dx,
+                    float* dx_colsum, float* dw, int64_t batch, int64_t in, int64_t out,
+                    int x_relu_mask, void* workspace, int64_t workspace_bytes, void* stream);
+/* out[c] = sum_r x[r,c], fixed order (bias gradient of the logits layer).
+ * workspace: adn_query(ADN_Q_COLSUM_WORKSPACE_BYTES). */
+int adn_colsum(const float* x, int64_t rows, int64_t cols, float* out, void* workspace,
+               int64_t workspace_bytes, void* stream);
+/* adn_opt_step that also refreshes the split planes of 2-D parameters: planes_host[t]
+ * (nullable per tensor) is the plane tensor of parameter t viewed as [size/cols, cols]. */
+int adn_opt_step_p(int kind, float* const* params_host, const float* const* grads_host,
+                   float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
+                   int n_tensors, const float* hyper_host, int64_t* step_dev,
+                   float* const* planes_host, const int64_t* cols_host, void* stream);
 
 /* out[0] = sum_i |x[i]| over n elements (tf.norm(ord=1), weighted.py:573), fixed order. */
 int adn_l1_norm(const float* x, int64_t n, float* out, void* stream);

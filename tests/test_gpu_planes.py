@@ -1,0 +1,184 @@
+"""GPU parity of the plane-native tcgen05 pipeline (csrc/planes.cu) through the C ABI.
+
+Checked against fp64 NumPy restatements of the reference arithmetic
+(tf.layers.dense and its gradients, adanet/examples/simple_dnn.py:72-86,103-110)
+with the forward-error bound of an fp32 GEMM: |err| <= 3e-6 * max(|A| @ |B|)
+(the same bound tests/test_gpu_kernels.py uses for the fp32 ABI).
+"""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 3e-6
+
+
+@pytest.fixture(scope="module")
+def env():
+  import torch
+  import __graft_entry__ as g
+  g.build()
+  from adanet_b200 import _lib
+  lib = _lib.load()
+  _lib.check(lib.adn_init(), "adn_init")
+  return torch, _lib, lib
+
+
+def _planes(torch, _lib, lib, a):
+  """dense numpy [r,c] -> zero-initialised plane tensor on the GPU"""
+  r, c = a.shape
+  nb = _lib.query(_lib.Q_PLANES_BYTES, r, c)
+  pl = torch.zeros((nb // 4,), dtype=torch.float32, device="cuda")
+  src = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+  _lib.check(lib.adn_planes_split(src.data_ptr(), r, c, pl.data_ptr(), torch.cuda.current_stream().cuda_stream), "split")
+  return pl
+
+
+def _merge(torch, _lib, lib, pl, r, c):
+  out = torch.empty((r, c), dtype=torch.float32, device="cuda")
+  _lib.check(lib.adn_planes_merge(pl.data_ptr(), r, c, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "merge")
+  return out.cpu().numpy()
+
+
+def _relerr(got, exact, scale=None):
+  """max |err| relative to `scale` (default: max |exact|)"""
+  if scale is None:
+    scale = np.abs(exact).max() + 1e-30
+  return float(np.abs(got.astype(np.float64) - exact).max() / scale)
+
+
+def _bound(a, b):
+  return float((np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)).max())
+
+
+@pytest.mark.parametrize("r,c", [(1, 1), (37, 100), (128, 32), (300, 130), (4096, 1024)])
+def test_split_merge_roundtrip(env, r, c):
+  torch, _lib, lib = env
+  rng = np.random.default_rng(r * 1000 + c)
+  a = rng.standard_normal((r, c)).astype(np.float32)
+  pl = _planes(torch, _lib, lib, a)
+  back = _merge(torch, _lib, lib, pl, r, c)
+  assert np.abs(back - a).max() <= 2.0 ** -22 * np.abs(a).max()
+  # padding columns of the last k-block are exact zeros, hi is TF32-representable
+  nkb = (c + 31) // 32
+  hi = pl[: nkb * r * 32].cpu().numpy().reshape(nkb, r, 32)
+  if c % 32:
+    assert (hi[-1, :, c % 32:] == 0).all()
+  assert (hi.view(np.uint32) & 0x1FFF == 0).all()
+
+
+SHAPES = [(128, 32, 64), (300, 100, 70), (512, 1024, 256), (1000, 257, 10), (2048, 64, 1024), (129, 33, 129)]
+
+
+@pytest.mark.parametrize("B,I,O", SHAPES)
+@pytest.mark.parametrize("act", [0, 1])
+def test_dense_fwd_planes(env, B, I, O, act):
+  torch, _lib, lib = env
+  rng = np.random.default_rng(B + I + O)
+  x = rng.standard_normal((B, I)).astype(np.float32)
+  w = (rng.standard_normal((I, O)) / np.sqrt(I)).astype(np.float32)
+  b = rng.standard_normal((O,)).astype(np.float32)
+  exact = x.astype(np.float64) @ w.astype(np.float64) + b
+  if act:
+    exact = np.maximum(exact, 0)
+  xp, wp = _planes(torch, _lib, lib, x), _planes(torch, _lib, lib, w)
+  bd = torch.as_tensor(b).cuda()
+  sp = torch.cuda.current_stream().cuda_stream
+  # dense fp32 output
+  y = torch.full((B, O), float("nan"), device="cuda")
+  _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), bd.data_ptr(), None, y.data_ptr(), B, I, O, act, sp), "fwd_p")
+  sc = _bound(x, w) + np.abs(b).max()
+  assert _relerr(y.cpu().numpy(), exact, sc) < TOL
+  # plane output (what the next layer consumes)
+  yp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, O) // 4,), device="cuda")
+  _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), bd.data_ptr(), yp.data_ptr(), None, B, I, O, act, sp), "fwd_p")
+  assert _relerr(_merge(torch, _lib, lib, yp, B, O), exact, sc) < TOL
+  nkb = (O + 31) // 32
+  if O % 32:
+    hi = yp[: nkb * B * 32].cpu().numpy().reshape(nkb, B, 32)
+    assert (hi[-1, :, O % 32:] == 0).all()
+
+
+@pytest.mark.parametrize("B,I,O", SHAPES)
+@pytest.mark.parametrize("mask", [0, 1])
+def test_dense_bwd_planes(env, B, I, O, mask):
+  torch, _lib, lib = env
+  rng = np.random.default_rng(7 * B + I + O)
+  x = rng.standard_normal((B, I)).astype(np.float32)
+  if mask:
+    x = np.maximum(x, 0)          # a ReLU output: the mask is x > 0
+  w = (rng.standard_normal((I, O)) / np.sqrt(O)).astype(np.float32)
+  dz = rng.standard_normal((B, O)).astype(np.float32)
+  dw_exact = x.astype(np.float64).T @ dz.astype(np.float64)
+  dx_exact = dz.astype(np.float64) @ w.astype(np.float64).T
+  if mask:
+    dx_exact = dx_exact * (x > 0)
+  cs_exact = dx_exact.sum(axis=0)
+  xp, wp, dzp = (_planes(torch, _lib, lib, a) for a in (x, w, dz))
+  nb = _lib.query(_lib.Q_DENSE_BWD_P_WS, B, I, O)
+  ws = torch.empty((nb,), dtype=torch.uint8, device="cuda")
+  sp = torch.cuda.current_stream().cuda_stream
+  dw = torch.full((I, O), float("nan"), device="cuda")
+  dxp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, I) // 4,), device="cuda")
+  cs = torch.full((I,), float("nan"), device="cuda")
+  _lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), dxp.data_ptr(), None, cs.data_ptr(),
+                                 dw.data_ptr(), B, I, O, mask, ws.data_ptr(), nb, sp), "bwd_p")
+  s_dw, s_dx = _bound(x.T, dz), _bound(dz, w.T)
+  assert _relerr(dw.cpu().numpy(), dw_exact, s_dw) < TOL
+  assert _relerr(_merge(torch, _lib, lib, dxp, B, I), dx_exact, s_dx) < TOL
+  assert _relerr(cs.cpu().numpy(), cs_exact, np.abs(dx_exact).sum(axis=0).max()) < TOL
+  # dense dx variant, no dw
+  dx = torch.full((B, I), float("nan"), device="cuda")
+  _lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), None, dx.data_ptr(), None, None, B, I, O,
+                                 mask, ws.data_ptr(), nb, sp), "bwd_p")
+  assert _relerr(dx.cpu().numpy(), dx_exact, s_dx) < TOL
+
+
+def test_large_batch_dw_split_k(env):
+  """K = batch = 32768 (BASELINE configs[2] batch): split-K dW and the two-level column sums."""
+  torch, _lib, lib = env
+  B, I, O = 32768, 100, 192
+  rng = np.random.default_rng(3)
+  x = np.maximum(rng.standard_normal((B, I)), 0).astype(np.float32)
+  w = (rng.standard_normal((I, O)) / np.sqrt(O)).astype(np.float32)
+  dz = (rng.standard_normal((B, O)) / B).astype(np.float32)
+  xp, wp, dzp = (_planes(torch, _lib, lib, a) for a in (x, w, dz))
+  nb = _lib.query(_lib.Q_DENSE_BWD_P_WS, B, I, O)
+  ws = torch.empty((nb,), dtype=torch.uint8, device="cuda")
+  dw = torch.empty((I, O), device="cuda")
+  cs = torch.empty((I,), device="cuda")
+  dxp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, I) // 4,), device="cuda")
+  _lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), dxp.data_ptr(), None, cs.data_ptr(),
+                                 dw.data_ptr(), B, I, O, 1, ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream), "bwd_p")
+  assert _relerr(dw.cpu().numpy(), x.astype(np.float64).T @ dz.astype(np.float64), _bound(x.T, dz)) < TOL
+  dx_exact = (dz.astype(np.float64) @ w.astype(np.float64).T) * (x > 0)
+  assert _relerr(cs.cpu().numpy(), dx_exact.sum(axis=0), np.abs(dx_exact).sum(axis=0).max()) < TOL
+
+
+def test_colsum_and_opt_step_planes(env):
+  torch, _lib, lib = env
+  rng = np.random.default_rng(5)
+  sp = torch.cuda.current_stream().cuda_stream
+  a = rng.standard_normal((5000, 10)).astype(np.float32)
+  ad = torch.as_tensor(a).cuda()
+  out = torch.empty((10,), device="cuda")
+  nb = _lib.query(_lib.Q_COLSUM_WS, 5000, 10)
+  ws = torch.empty((nb,), dtype=torch.uint8, device="cuda")
+  _lib.check(lib.adn_colsum(ad.data_ptr(), 5000, 10, out.data_ptr(), ws.data_ptr(), nb, sp), "colsum")
+  assert _relerr(out.cpu().numpy(), a.astype(np.float64).sum(axis=0), np.abs(a).sum(axis=0).max()) < TOL
+  # SGD step that refreshes the planes of a [100, 70] kernel; bias has no planes
+  w = rng.standard_normal((100, 70)).astype(np.float32)
+  g = rng.standard_normal((100, 70)).astype(np.float32)
+  b, gb = rng.standard_normal((70,)).astype(np.float32), rng.standard_normal((70,)).astype(np.float32)
+  wd, gd, bd, gbd = (torch.as_tensor(t).cuda() for t in (w, g, b, gb))
+  wp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, 100, 70) // 4,), device="cuda")
+  _lib.check(lib.adn_opt_step_p(_lib.OPT_SGD, _lib.ptr_array([wd.data_ptr(), bd.data_ptr()]),
+                                _lib.ptr_array([gd.data_ptr(), gbd.data_ptr()]), None, None, _lib.i64_array([7000, 70]), 2,
+                                _lib.f32_array([0.1]), None, _lib.ptr_array([wp.data_ptr(), None]), _lib.i64_array([70, 0]),
+                                sp), "opt_step_p")
+  want = (w - np.float32(0.1) * g).astype(np.float32)
+  assert np.array_equal(wd.cpu().numpy(), want)
+  assert np.array_equal(bd.cpu().numpy(), (b - np.float32(0.1) * gb).astype(np.float32))
+  ref = _planes(torch, _lib, lib, want)
+  assert torch.equal(wp, ref)
