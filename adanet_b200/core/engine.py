@@ -14,6 +14,13 @@ of ``adanet_b200/csrc`` through the C ABI (include/adanet_b200.h):
   candidate head  -> adn_ensemble_head (+ adn_opt_step on the mixture weights)
   EMA / steps     -> adn_ema_update / adn_record_scalars / adn_counter_add
 
+Dense layers run on the plane-native tcgen05 pipeline (csrc/planes.cu): the
+minibatch is split into TF32 hi/lo planes once per step, every hidden
+activation and back-propagated gradient stays in plane format between GEMMs
+(adn_dense_fwd_p / adn_dense_bwd_p), and the optimizer refreshes the weight
+planes (adn_opt_step_p).  With ADN_DENSE_PATH=simt the fp32 CUDA-core ABI
+(adn_dense_fwd / adn_dense_bwd) is used instead, as an on-device cross-check.
+
 Each candidate runs on its own CUDA stream (they are independent within an
 iteration) and, once shapes are fixed, the whole step is captured in a CUDA
 graph so a step is one graph launch.  PyTorch is used for device memory,
@@ -50,6 +57,16 @@ def _require_cuda():
   lib = _lib.load()
   _lib.check(lib.adn_init(), "adn_init")
   return lib
+
+
+def planes_enabled() -> bool:
+  """True unless the fp32 SIMT cross-check path is forced (adn_set_dense_path / ADN_DENSE_PATH=simt)."""
+  return _lib.query(_lib.Q_DENSE_FWD_PATH, 1 << 20, 1024, 1024) == _lib.PATH_TCGEN05
+
+
+def new_planes(rows: int, cols: int, device) -> torch.Tensor:
+  """Zero-initialised split-plane tensor (include/adanet_b200.h: the K padding must stay zero)."""
+  return torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, rows, cols) // 4,), dtype=torch.float32, device=device)
 
 
 @dataclass
@@ -95,9 +112,13 @@ def _opt_hyper(spec: tuple) -> Tuple[int, List[float]]:
 class _Optimizer:
   """Device-resident optimizer state for one group of parameter tensors."""
 
-  def __init__(self, spec: tuple, params: List[torch.Tensor]):
+  def __init__(self, spec: tuple, params: List[torch.Tensor], planes: Optional[List[Optional[torch.Tensor]]] = None):
     self.kind, self.hyper = _opt_hyper(spec)
     self.params = params
+    self.planes = planes
+    if planes is not None:
+      self._planes = _lib.ptr_array([pl.data_ptr() if pl is not None else None for pl in planes])
+      self._cols = _lib.i64_array([p.shape[-1] if pl is not None else 0 for p, pl in zip(params, planes)])
     dev = params[0].device
     n_slots = {_lib.OPT_SGD: 0, _lib.OPT_MOMENTUM: 1, _lib.OPT_RMSPROP: 2, _lib.OPT_ADAM: 2}[self.kind]
     self.slot0 = [torch.zeros_like(p) for p in params] if n_slots >= 1 else None
@@ -114,9 +135,13 @@ class _Optimizer:
 
   def apply(self, lib, grads: List[torch.Tensor], stream_ptr: int):
     g = _lib.ptr_array([t.data_ptr() for t in grads])
-    _lib.check(lib.adn_opt_step(self.kind, self._p, g, self._s0, self._s1, self._sizes, len(self.params),
-                                self._hyper, self.step_dev.data_ptr() if self.step_dev is not None else None,
-                                stream_ptr), "adn_opt_step")
+    step = self.step_dev.data_ptr() if self.step_dev is not None else None
+    if self.planes is not None:
+      _lib.check(lib.adn_opt_step_p(self.kind, self._p, g, self._s0, self._s1, self._sizes, len(self.params),
+                                    self._hyper, step, self._planes, self._cols, stream_ptr), "adn_opt_step_p")
+    else:
+      _lib.check(lib.adn_opt_step(self.kind, self._p, g, self._s0, self._s1, self._sizes, len(self.params),
+                                  self._hyper, step, stream_ptr), "adn_opt_step")
 
 
 class DenseNet:
@@ -139,10 +164,24 @@ class DenseNet:
     for i, w in enumerate(self.ws):
       if tuple(w.shape) != (dims[i], dims[i + 1]):
         raise ValueError("kernel %d of %s has shape %s, want %s" % (i, name, tuple(w.shape), (dims[i], dims[i + 1])))
-    self.acts = [torch.empty((batch, d), dtype=torch.float32, device=device) for d in dims[1:]]
-    fwd_ws = max(_lib.query(_lib.Q_DENSE_FWD_WS, batch, dims[i], dims[i + 1]) for i in range(len(dims) - 1))
-    self.fwd_ws_bytes = fwd_ws
-    self.fwd_ws = torch.empty((max(fwd_ws, 16),), dtype=torch.uint8, device=device)
+    self.planes = planes_enabled()
+    n = len(self.ws)
+    if self.planes:
+      # hidden activations live as split planes; only the logits are dense fp32
+      self.acts = [None] * (n - 1) + [torch.empty((batch, dims[-1]), dtype=torch.float32, device=device)]
+      self.hp = [new_planes(batch, d, device) for d in dims[1:-1]]
+      self.wps = [new_planes(dims[i], dims[i + 1], device) for i in range(n)]
+      sp = torch.cuda.current_stream(device).cuda_stream
+      lib = _lib.load()
+      for w, wp in zip(self.ws, self.wps):
+        _lib.check(lib.adn_planes_split(w.data_ptr(), w.shape[0], w.shape[1], wp.data_ptr(), sp), "adn_planes_split")
+      self.fwd_ws_bytes, self.fwd_ws = 0, None
+    else:
+      self.acts = [torch.empty((batch, d), dtype=torch.float32, device=device) for d in dims[1:]]
+      self.hp, self.wps = None, None
+      fwd_ws = max(_lib.query(_lib.Q_DENSE_FWD_WS, batch, dims[i], dims[i + 1]) for i in range(n))
+      self.fwd_ws_bytes = fwd_ws
+      self.fwd_ws = torch.empty((max(fwd_ws, 16),), dtype=torch.uint8, device=device)
 
   @property
   def logits(self) -> torch.Tensor:
@@ -150,11 +189,31 @@ class DenseNet:
 
   @property
   def last_layer(self) -> torch.Tensor:
-    return self.acts[-2] if len(self.acts) >= 2 else None
+    """Last hidden activation as dense fp32 [batch, d] (merged from its planes on demand)."""
+    if len(self.dims) < 3:
+      return None
+    if not self.planes:
+      return self.acts[-2]
+    out = torch.empty((self.batch, self.dims[-2]), dtype=torch.float32, device=self.device)
+    _lib.check(_lib.load().adn_planes_merge(self.hp[-1].data_ptr(), self.batch, self.dims[-2], out.data_ptr(),
+                                            torch.cuda.current_stream(self.device).cuda_stream), "adn_planes_merge")
+    return out
 
-  def forward(self, lib, x: torch.Tensor, sp: int):
-    h = x
+  def forward(self, lib, x: torch.Tensor, sp: int, xp: Optional[torch.Tensor] = None):
+    """x: dense fp32 minibatch; xp: its split planes (required on the plane path)."""
     n = len(self.ws)
+    if self.planes:
+      hp = xp
+      for i in range(n):
+        last = i == n - 1
+        _lib.check(lib.adn_dense_fwd_p(hp.data_ptr(), self.wps[i].data_ptr(), self.bs[i].data_ptr(),
+                                       None if last else self.hp[i].data_ptr(),
+                                       self.acts[i].data_ptr() if last else None, self.batch, self.dims[i],
+                                       self.dims[i + 1], _lib.ACT_NONE if last else _lib.ACT_RELU, sp),
+                   "adn_dense_fwd_p")
+        hp = None if last else self.hp[i]
+      return
+    h = x
     for i in range(n):
       act = _lib.ACT_RELU if i < n - 1 else _lib.ACT_NONE
       _lib.check(lib.adn_dense_fwd(h.data_ptr(), self.ws[i].data_ptr(), self.bs[i].data_ptr(),
@@ -191,18 +250,28 @@ class CandidatePlan:
     self.dbs = [torch.empty_like(b) for b in self.net.bs]
     self.dlogits = torch.empty((batch, dims[-1]), **f32)
     hid = max(dims[1:-1]) if len(dims) > 2 else 0
-    self.dz = [torch.empty((batch, hid), **f32) for _ in range(2)] if hid else []
-    ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_WS, batch, dims[i], dims[i + 1]) for i in range(len(dims) - 1))
+    self.planes = self.net.planes
+    if self.planes:
+      # back-propagated gradients as split planes: dlogits + two ping-pong buffers for the hidden layers
+      self.dzp_out = new_planes(batch, dims[-1], device)
+      self.dzp = [new_planes(batch, hid, device) for _ in range(2)] if hid else []
+      self.dz = []
+      ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_P_WS, batch, dims[i], dims[i + 1]) for i in range(len(dims) - 1))
+      ws_bytes = max(ws_bytes, _lib.query(_lib.Q_COLSUM_WS, batch, dims[-1]))
+    else:
+      self.dz = [torch.empty((batch, hid), **f32) for _ in range(2)] if hid else []
+      ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_WS, batch, dims[i], dims[i + 1]) for i in range(len(dims) - 1))
     n_members = len(frozen) + 1
     ws_bytes = max(ws_bytes, _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, n_members))
     self.workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
     self.ws_bytes = ws_bytes
     self.sub_loss = torch.zeros((1,), **f32)
-    params, self._grads = [], []
-    for w, b, dw, db in zip(self.net.ws, self.net.bs, self.dws, self.dbs):
+    params, self._grads, planes = [], [], []
+    for i, (w, b, dw, db) in enumerate(zip(self.net.ws, self.net.bs, self.dws, self.dbs)):
       params += [w, b]
       self._grads += [dw, db]
-    self.sub_opt = _Optimizer(spec.optimizer, params)
+      planes += [self.net.wps[i] if self.planes else None, None]
+    self.sub_opt = _Optimizer(spec.optimizer, params, planes if self.planes else None)
     # ensemble state (weighted.py:360-366,419-428,487-516)
     self.mix = _MIX_KIND[ens.mixture_weight_type]
     if self.mix == _lib.MIX_MATRIX:
@@ -235,14 +304,14 @@ class CandidatePlan:
                                       self.out3.data_ptr() + 8, self.ema_state.data_ptr() + 8])
 
   def enqueue_train_step(self, x: torch.Tensor, labels: torch.Tensor, labels_f: Optional[torch.Tensor],
-                         step_dev: torch.Tensor, sp: int):
+                         step_dev: torch.Tensor, sp: int, xp: Optional[torch.Tensor] = None):
     """SURVEY.md section 3.3 steps 1-13 for this candidate (frozen logits already computed)."""
     lib, net, B, C = self.lib, self.net, self.batch, self.C
     lab = labels.data_ptr() if labels is not None else None
     labf = labels_f.data_ptr() if labels_f is not None else None
     wsp = self.workspace.data_ptr()
     # steps 1-2: subnetwork forward
-    net.forward(lib, x, sp)
+    net.forward(lib, x, sp, xp)
     # step 3: subnetwork loss + dlogits
     _lib.check(lib.adn_head_loss(self.head, net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
                                  self.dlogits.data_ptr(), B, C, wsp, self.ws_bytes, sp), "adn_head_loss")
@@ -261,8 +330,24 @@ class CandidatePlan:
                                       self.trace_capacity, sp), "adn_record_scalars")
     # step 4: backward through the subnetwork's own variables only
     n = len(net.ws)
+    if self.planes:
+      # dlogits -> planes; bias gradient of the logits layer; then one call per layer produces dW_i, the
+      # planes of dZ_{i-1} (ReLU mask from the planes of h_{i-1}) and db_{i-1} = colsum(dZ_{i-1})
+      _lib.check(lib.adn_planes_split(self.dlogits.data_ptr(), B, C, self.dzp_out.data_ptr(), sp), "adn_planes_split")
+      _lib.check(lib.adn_colsum(self.dlogits.data_ptr(), B, C, self.dbs[n - 1].data_ptr(), wsp, self.ws_bytes, sp),
+                 "adn_colsum")
+      dzp = self.dzp_out
+      for i in range(n - 1, -1, -1):
+        xin = xp if i == 0 else net.hp[i - 1]
+        dxp = self.dzp[i % 2] if i > 0 else None
+        _lib.check(lib.adn_dense_bwd_p(xin.data_ptr(), net.wps[i].data_ptr(), dzp.data_ptr(),
+                                       dxp.data_ptr() if dxp is not None else None, None,
+                                       self.dbs[i - 1].data_ptr() if i > 0 else None, self.dws[i].data_ptr(), B,
+                                       net.dims[i], net.dims[i + 1], 1 if i > 0 else 0, wsp, self.ws_bytes, sp),
+                   "adn_dense_bwd_p")
+        dzp = dxp
     dz = self.dlogits
-    for i in range(n - 1, -1, -1):
+    for i in range(n - 1, -1, -1) if not self.planes else ():
       xin = x if i == 0 else net.acts[i - 1]
       # dz ping-pong buffers are sized for the widest hidden layer; carve a contiguous [B, d_i] view
       dx = self.dz[i % 2].view(-1)[:B * net.dims[i]].view(B, net.dims[i]) if i > 0 else None
@@ -276,10 +361,11 @@ class CandidatePlan:
       self.ens_opt.apply(lib, self._ens_grads, sp)
     self.sub_opt.apply(lib, self._grads, sp)
 
-  def enqueue_eval(self, x, labels, labels_f, ens_out: Optional[torch.Tensor], sp: int):
+  def enqueue_eval(self, x, labels, labels_f, ens_out: Optional[torch.Tensor], sp: int,
+                   xp: Optional[torch.Tensor] = None):
     """Forward-only: subnetwork logits + ensemble logits/loss (evaluate / predict)."""
     lib, net, B, C = self.lib, self.net, self.batch, self.C
-    net.forward(lib, x, sp)
+    net.forward(lib, x, sp, xp)
     _lib.check(lib.adn_ensemble_head(
         self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
         self._gammas, self.reg_is_zero, self.reg_multiplier,
@@ -308,6 +394,8 @@ class IterationPlan:
                                      adanet_loss_decay, trace_capacity, self.device, i)
                        for i, s in zip(idx, specs)]
     self.x = torch.empty((batch, in_dim), dtype=torch.float32, device=self.device)
+    # split planes of the minibatch, produced once per step and shared by every member and candidate
+    self.xp = new_planes(batch, in_dim, self.device) if planes_enabled() else None
     self.labels = torch.empty((batch,), dtype=torch.int64, device=self.device) if head == "softmax_xent" else None
     self.labels_f = (torch.empty((batch, logits_dim), dtype=torch.float32, device=self.device)
                      if head != "softmax_xent" else None)
@@ -337,19 +425,25 @@ class IterationPlan:
     lib = self.lib
     main = torch.cuda.current_stream(self.device)
     sp = main.cuda_stream
+    self._split_x(sp)
     for f in self.frozen:   # shared by every candidate ensemble on this GPU
-      f.forward(lib, self.x, sp)
+      f.forward(lib, self.x, sp, self.xp)
     if self.multi_stream:
       for c, s in zip(self.candidates, self.streams):
         s.wait_stream(main)
         with torch.cuda.stream(s):
-          c.enqueue_train_step(self.x, self.labels, self.labels_f, self.step_dev, s.cuda_stream)
+          c.enqueue_train_step(self.x, self.labels, self.labels_f, self.step_dev, s.cuda_stream, self.xp)
       for s in self.streams:
         main.wait_stream(s)
     else:
       for c in self.candidates:
-        c.enqueue_train_step(self.x, self.labels, self.labels_f, self.step_dev, sp)
+        c.enqueue_train_step(self.x, self.labels, self.labels_f, self.step_dev, sp, self.xp)
     _lib.check(lib.adn_counter_add(self.step_dev.data_ptr(), 1, sp), "adn_counter_add")
+
+  def _split_x(self, sp: int):
+    if self.xp is not None:
+      _lib.check(self.lib.adn_planes_split(self.x.data_ptr(), self.batch, self.in_dim, self.xp.data_ptr(), sp),
+                 "adn_planes_split")
 
   def train_step(self, x=None, y=None):
     """One training step of every candidate on this GPU on one minibatch."""
@@ -376,10 +470,11 @@ class IterationPlan:
     (the Evaluator path, adanet/core/estimator.py:1469-1490)."""
     self.load_batch(x, y)
     sp = torch.cuda.current_stream(self.device).cuda_stream
+    self._split_x(sp)
     for f in self.frozen:
-      f.forward(self.lib, self.x, sp)
+      f.forward(self.lib, self.x, sp, self.xp)
     for c in self.candidates:
-      c.enqueue_eval(self.x, self.labels, self.labels_f, None, sp)
+      c.enqueue_eval(self.x, self.labels, self.labels_f, None, sp, self.xp)
     torch.cuda.current_stream(self.device).synchronize()
     return [float(c.out3[2].item()) for c in self.candidates]
 
@@ -433,6 +528,7 @@ class EnsembleEvalPlan:
     self.ws_bytes = _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, len(self.members))
     self.workspace = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=self.device)
     self.x = torch.empty((batch, members[0].dims[0]), **f32)
+    self.xp = new_planes(batch, members[0].dims[0], self.device) if planes_enabled() else None
     self.labels = torch.zeros((batch,), dtype=torch.int64, device=self.device) if head == "softmax_xent" else None
     self.labels_f = torch.zeros((batch, logits_dim), **f32) if head != "softmax_xent" else None
 
@@ -447,8 +543,11 @@ class EnsembleEvalPlan:
       else:
         self.labels_f.copy_(torch.as_tensor(y).reshape(self.batch, self.C), non_blocking=True)
     if forward_members:
+      if self.xp is not None:
+        _lib.check(self.lib.adn_planes_split(self.x.data_ptr(), self.batch, self.x.shape[1], self.xp.data_ptr(), sp),
+                   "adn_planes_split")
       for m in self.members:
-        m.forward(self.lib, self.x, sp)
+        m.forward(self.lib, self.x, sp, self.xp)
     _lib.check(self.lib.adn_ensemble_head(
         self.head, self.mix, self._members, len(self.members), self.mix_w.data_ptr(), self.bias.data_ptr(),
         self._gammas, self.reg_is_zero, 1.0, self.labels.data_ptr() if self.labels is not None else None,
