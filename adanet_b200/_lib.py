@@ -28,7 +28,7 @@ EXPORTS = (
     "adn_last_error", "adn_init", "adn_query", "adn_set_dense_path", "adn_dense_fwd", "adn_dense_bwd", "adn_head_loss",
     "adn_ensemble_head", "adn_opt_step", "adn_l1_norm", "adn_ema_update", "adn_record_scalars",
     "adn_counter_add", "adn_planes_split", "adn_planes_merge", "adn_dense_fwd_p", "adn_dense_bwd_p", "adn_colsum",
-    "adn_opt_step_p",
+    "adn_opt_step_p", "adn_head_loss_p",
 )
 
 
@@ -71,6 +71,7 @@ def load():
   lib.adn_dense_fwd_p.argtypes = [p, p, p, p, p, i64, i64, i64, c_int, p]
   lib.adn_dense_bwd_p.argtypes = [p, p, p, p, p, p, p, i64, i64, i64, c_int, p, i64, p]
   lib.adn_colsum.argtypes = [p, i64, i64, p, p, i64, p]
+  lib.adn_head_loss_p.argtypes = [c_int, p, p, p, p, p, p, p, i64, i64, p, i64, p]
   lib.adn_opt_step_p.argtypes = [c_int, POINTER(p), POINTER(p), POINTER(p), POINTER(p), POINTER(i64), c_int,
                                  POINTER(f32), p, POINTER(p), POINTER(i64), p]
   for name in EXPORTS:

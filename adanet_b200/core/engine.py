@@ -312,9 +312,15 @@ class CandidatePlan:
     wsp = self.workspace.data_ptr()
     # steps 1-2: subnetwork forward
     net.forward(lib, x, sp, xp)
-    # step 3: subnetwork loss + dlogits
-    _lib.check(lib.adn_head_loss(self.head, net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
-                                 self.dlogits.data_ptr(), B, C, wsp, self.ws_bytes, sp), "adn_head_loss")
+    # step 3: subnetwork loss + dlogits (plane path: also its split planes and column sums = db of the logits layer)
+    if self.planes:
+      _lib.check(lib.adn_head_loss_p(self.head, net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
+                                     self.dlogits.data_ptr(), self.dzp_out.data_ptr(),
+                                     self.dbs[len(net.ws) - 1].data_ptr(), B, C, wsp, self.ws_bytes, sp),
+                 "adn_head_loss_p")
+    else:
+      _lib.check(lib.adn_head_loss(self.head, net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
+                                   self.dlogits.data_ptr(), B, C, wsp, self.ws_bytes, sp), "adn_head_loss")
     # steps 6-11: ensemble head on pre-update values
     train_ens = self.ens_opt is not None
     _lib.check(lib.adn_ensemble_head(
@@ -331,11 +337,8 @@ class CandidatePlan:
     # step 4: backward through the subnetwork's own variables only
     n = len(net.ws)
     if self.planes:
-      # dlogits -> planes; bias gradient of the logits layer; then one call per layer produces dW_i, the
-      # planes of dZ_{i-1} (ReLU mask from the planes of h_{i-1}) and db_{i-1} = colsum(dZ_{i-1})
-      _lib.check(lib.adn_planes_split(self.dlogits.data_ptr(), B, C, self.dzp_out.data_ptr(), sp), "adn_planes_split")
-      _lib.check(lib.adn_colsum(self.dlogits.data_ptr(), B, C, self.dbs[n - 1].data_ptr(), wsp, self.ws_bytes, sp),
-                 "adn_colsum")
+      # one call per layer produces dW_i, the planes of dZ_{i-1} (ReLU mask = sign bits of h_{i-1}) and
+      # db_{i-1} = colsum(dZ_{i-1}); the planes of dlogits and db of the logits layer came from the head kernel
       dzp = self.dzp_out
       for i in range(n - 1, -1, -1):
         xin = xp if i == 0 else net.hp[i - 1]

@@ -111,7 +111,7 @@ extern "C" int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_
     case ADN_Q_SM_COUNT: *out_host = sm_count(); return ADN_OK;
     case ADN_Q_PLANES_BYTES: *out_host = pl::planes_bytes(a, b); return ADN_OK;
     case ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES: *out_host = pl::dense_bwd_workspace_bytes(a, b, c); return ADN_OK;
-    case ADN_Q_COLSUM_WORKSPACE_BYTES: *out_host = ceil_div(a, 512) * b * (int64_t)sizeof(float) + 256; return ADN_OK;
+    case ADN_Q_COLSUM_WORKSPACE_BYTES: *out_host = 64 * b * (int64_t)sizeof(float) + 256; return ADN_OK;
     case ADN_Q_LAUNCH_COUNT: *out_host = g_launches.load(); return ADN_OK;
     default: return fail(ADN_ERR_INVALID, "adn_query: unknown key %d", key);
   }
@@ -192,7 +192,7 @@ extern "C" int adn_colsum(const float* x, int64_t rows, int64_t cols, float* out
                           int64_t workspace_bytes, void* stream) {
   if (!x || !out || !workspace) return fail(ADN_ERR_INVALID, "adn_colsum: null pointer");
   if (bad_shape(rows, cols, 1)) return fail(ADN_ERR_INVALID, "adn_colsum: bad shape");
-  if (workspace_bytes < ceil_div(rows, 512) * cols * (int64_t)sizeof(float))
+  if (workspace_bytes < 64 * cols * (int64_t)sizeof(float))
     return fail(ADN_ERR_WORKSPACE, "adn_colsum: workspace too small");
   return simt::colsum(x, out, rows, cols, reinterpret_cast<float*>(workspace), as_stream(stream));
 }

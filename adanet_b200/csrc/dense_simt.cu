@@ -34,7 +34,12 @@ colsum_partial_kernel(const float* __restrict__ dz, float* __restrict__ part, in
   }
 }
 
-static const int kColsumRows = 512;
+// rows per first-level slice: at most 64 slices, at least 64 rows each (each thread then adds >= 8 rows)
+static inline int colsum_slice_rows(int64_t rows) {
+  int64_t r = ceil_div(rows, 64);
+  r = ceil_div(r, 8) * 8;
+  return (int)(r < 64 ? 64 : r);
+}
 
 int reduce_partials(const float* part, float* out, int64_t n, int S, int64_t stride, cudaStream_t st) {
   reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(part, out, n, S, stride);
@@ -43,9 +48,10 @@ int reduce_partials(const float* part, float* out, int64_t n, int S, int64_t str
 }
 
 int colsum(const float* dz, float* db, int64_t rows, int64_t N, float* part, cudaStream_t st) {
-  const int S2 = (int)ceil_div(rows, kColsumRows);
+  const int rps = colsum_slice_rows(rows);
+  const int S2 = (int)ceil_div(rows, rps);
   dim3 grid((unsigned)ceil_div(N, 32), (unsigned)S2);
-  colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, part, (int)rows, (int)N, kColsumRows);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, part, (int)rows, (int)N, rps);
   ADN_CHECK_LAUNCH("colsum");
   return reduce_partials(part, db, N, S2, N, st);
 }
@@ -100,7 +106,7 @@ int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
   // dW partials sized for the worst-case split count (64) so every dense path
   // (SIMT or tcgen05) can share the buffer regardless of its own split choice.
   int64_t s = max_splits(batch);
-  int64_t s2 = ceil_div(batch, kColsumRows);
+  int64_t s2 = 64;   // colsum_slice_rows(): at most 64 first-level slices
   return align_up((s * in * out + s2 * out) * (int64_t)sizeof(float), 256);
 }
 

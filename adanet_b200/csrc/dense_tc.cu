@@ -671,7 +671,7 @@ int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
               + plane_pair_bytes(in, kb_b)    // x^T      [in, B]    (A of dW)
               + plane_pair_bytes(out, kb_b);  // dz^T     [out, B]   (B of dW)
   b += align_up((int64_t)max_dw_splits(in, out) * in * out * (int64_t)sizeof(float), 256);   // dW split-K partials
-  b += align_up(ceil_div(batch, 512) * out * (int64_t)sizeof(float), 256);                   // db partials
+  b += align_up(64 * out * (int64_t)sizeof(float), 256);                   // db partials
   return b + 1024;
 }
 
@@ -710,7 +710,7 @@ int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float*
   Planes pxT = c.planes(in, kb_b);
   Planes pdzT = c.planes(out, kb_b);
   float* part = c.floats((int64_t)max_s * in * out);
-  float* dbpart = c.floats(ceil_div(batch, 512) * out);
+  float* dbpart = c.floats(64 * out);
   if (!c.ok) return fail(ADN_ERR_WORKSPACE, "tc dense_bwd: workspace carve failed");
   int rc;
   // ---- dW[in,out] = x^T[in,B] * (dz^T[out,B])^T, split-K over the batch ----

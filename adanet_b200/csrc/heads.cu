@@ -28,6 +28,9 @@ struct HeadParams {
   const int64_t* labels;
   const float* labels_f;
   float* dens;           // [B,dim] or null
+  float* dens_hi;        // split planes of dens (csrc/planes.cu layout [dim/32][B][32]) or null
+  float* dens_lo;
+  int colsum_only;       // want_grads without the mixture-weight pass: only column sums of dens -> dbias
   float* ens_out;        // [B,dim] or null
   float* part;           // workspace: per-CTA partials [n_cta][n_out]
   int64_t batch;
@@ -138,6 +141,23 @@ ensemble_head_kernel(const __grid_constant__ HeadParams p) {
   if (p.dens) {
     for (int i = tid; i < valid; i += kRows) p.dens[base + i] = ens[i];
   }
+  if (p.dens_hi) {
+    // same gradient as TF32 hi/lo planes: the A / B operand of the subnetwork's backward GEMMs
+    const int nkb = (C + 31) >> 5;
+    for (int i = tid; i < kRows * nkb * 32; i += kRows) {
+      const int c32 = i & 31, r = (i >> 5) % kRows, kb = (i >> 5) / kRows;
+      if (r0 + r >= p.batch) continue;
+      const int c = kb * 32 + c32;
+      const float v = (c < C) ? ens[r * C + c] : 0.f;
+      uint32_t h, l;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+      const float hi = __uint_as_float(h);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+      const size_t dst = ((size_t)kb * p.batch + r0 + r) * 32 + c32;
+      p.dens_hi[dst] = hi;
+      p.dens_lo[dst] = __uint_as_float(l);
+    }
+  }
   if (!p.want_grads) return;
 
   // ---- column sums of g -> dbias partial ----
@@ -146,7 +166,7 @@ ensemble_head_kernel(const __grid_constant__ HeadParams p) {
     for (int r = 0; r < kRows; ++r) t += ens[r * C + tid];
     part[1 + tid] = t;
   }
-  if (p.mixture == ADN_MIX_MATRIX) return;
+  if (p.mixture == ADN_MIX_MATRIX || p.colsum_only) return;
 
   // ---- pass 2: dw_k partials = sum_b g (.) member_k  (members re-read, L2-hot) ----
   const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : C;
@@ -194,7 +214,7 @@ ensemble_finalize_kernel(const __grid_constant__ HeadParams p, int n_cta) {
   __shared__ float s_loss, s_reg;
   const int C = p.dim;
   const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : C;
-  const int n_w = (p.mixture == ADN_MIX_MATRIX) ? 0 : p.n_members * wdim;
+  const int n_w = (p.mixture == ADN_MIX_MATRIX || p.colsum_only) ? 0 : p.n_members * wdim;
   const int n_red = p.want_grads ? (1 + C + n_w) : 1;
   // one warp per output: lanes stride over the CTA partials, then a fixed-order shuffle tree
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -313,9 +333,18 @@ int64_t head_workspace_bytes_public(int64_t batch, int64_t dim, int64_t members)
 
 using namespace adn;
 
+namespace adn { namespace pl { int64_t plane_floats(int64_t rows, int64_t cols); } }
+
 extern "C" int adn_head_loss(int head, const float* logits, const int64_t* labels, const float* labels_f,
                              float* loss_out, float* dlogits, int64_t batch, int64_t dim,
                              void* workspace, int64_t workspace_bytes, void* stream) {
+  return adn_head_loss_p(head, logits, labels, labels_f, loss_out, dlogits, nullptr, nullptr, batch, dim, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int adn_head_loss_p(int head, const float* logits, const int64_t* labels, const float* labels_f,
+                               float* loss_out, float* dlogits, float* dlogits_planes, float* dlogits_colsum,
+                               int64_t batch, int64_t dim, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!logits || !loss_out) return fail(ADN_ERR_INVALID, "adn_head_loss: null pointer");
   if (head < 0 || head > 2) return fail(ADN_ERR_INVALID, "adn_head_loss: bad head %d", head);
   // out3 needs 3 floats; the public contract is loss_out[0], so stage through workspace tail.
@@ -327,9 +356,15 @@ extern "C" int adn_head_loss(int head, const float* logits, const int64_t* label
   p.labels = labels;
   p.labels_f = labels_f;
   p.dens = dlogits;
+  if (dlogits_planes) {
+    p.dens_hi = dlogits_planes;
+    p.dens_lo = dlogits_planes + pl::plane_floats(batch, dim);
+  }
   p.batch = batch;
   p.dim = (int)dim;
-  p.want_grads = 0;
+  p.want_grads = dlogits_colsum ? 1 : 0;
+  p.colsum_only = 1;
+  p.dbias = dlogits_colsum;
   p.reg_is_zero = 1;
   const int64_t need = head_workspace_bytes_public(batch, dim, 1);
   if (workspace_bytes < need + 16)

@@ -5,7 +5,9 @@
 // Split planes of a matrix T[rows, cols] (fp32):
 //     hi = rna_tf32(T)          lo = rna_tf32(T - hi)
 //   each stored k-block-major   plane[cols/32][rows][32]   (cols zero padded to 32),
-//   one buffer: hi plane followed by lo plane (adn_query(ADN_Q_PLANES_BYTES)).
+//   plus sign bits  bits[cols/32][rows]  (uint32, bit j = T[row, kb*32+j] > 0): the ReLU mask of
+//   the backward pass costs 1/32 of a plane and one coalesced word per row instead of a 4 B/element read;
+//   one buffer: hi plane, lo plane, sign bits (adn_query(ADN_Q_PLANES_BYTES)).
 // One layout serves every GEMM of training because tcgen05 takes either operand
 // K-major or MN-major straight from shared memory:
 //     K  = cols of T : box {32, 128 rows, 1 kb}   -> K-major  [128 rows][32 k]      SWIZZLE_128B
@@ -22,11 +24,12 @@
 // stay in TMEM for 128 K only and are then added in registers with RN
 // (profiles/r1a_accuracy_probe_*.txt); cross terms use their own accumulator.
 //
-// Kernel: persistent, one CTA per SM, 192 threads, warp-specialised
+// Kernel: persistent, one CTA per SM, 320 threads, warp-specialised
 //   warp 0    TMA producer (3-stage ring, 64 KiB per stage: A_hi A_lo B_hi B_lo)
 //   warp 1    MMA issuer (elected lane; 12 x tcgen05.mma.kind::tf32 M128 N128 K8 per stage)
-//   warps 2-5 epilogue: tcgen05.ld -> registers -> per-warp smem transpose ->
-//             bias/ReLU | mask | partial -> hi/lo split -> coalesced 512 B stores
+//   warps 2-9 epilogue (TMEM lane quadrant = warp % 4, column half = (warp-2)/4, 64 accumulators each):
+//             tcgen05.ld -> registers (bias/ReLU + sign bits | sign-bit mask) -> per-warp smem
+//             transpose -> column sums -> hi/lo split -> coalesced 512 B stores
 //
 // Reference arithmetic replaced: tf.layers.dense and its gradients,
 //   adanet/examples/simple_dnn.py:72-86,103-110.
@@ -47,11 +50,13 @@ static constexpr int STAGES = 3;
 static constexpr int CHUNK = 4;                       // k-blocks per TMEM accumulation chunk (K = 128)
 static constexpr int TILE_BYTES = 128 * BK * 4;       // 16 KiB
 static constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi A_lo B_hi B_lo
+static constexpr int EPI_WARPS = 8;
+static constexpr int EPI_COLS = 64;                   // accumulator columns per epilogue warp
 static constexpr int EPI_STAGE_FLOATS = 32 * 33;      // per epilogue warp: 32x32 slice transposed through smem
-static constexpr int EPI_BYTES = 4 * EPI_STAGE_FLOATS * 4;
+static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
 static constexpr int BAR_BYTES = 256;
 static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-static constexpr int NUM_THREADS = 192;
+static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 static constexpr int TMEM_COLS = 512;                 // H0 [0,128) H1 [128,256) S0 [256,384) S1 [384,512)
 static constexpr int MAX_SPLITS = 64;
 
@@ -70,7 +75,8 @@ struct GemmParams {
   int out_nkb;           // planes: k-blocks of the output tensor (ceil(N/32))
   const float* bias;     // EPI_BIAS_ACT (nullable)
   int act;
-  const float* mask_hi;  // EPI_MASK (nullable): hi plane of a [M, N] tensor; out = mask > 0 ? out : 0
+  uint32_t* out_bits;    // planes + EPI_BIAS_ACT: sign bits of the output
+  const uint32_t* mask_bits;  // EPI_MASK (nullable): sign bits of a [M, N] tensor; out = bit ? out : 0
   float* colsum_part;    // EPI_MASK (nullable): [ceil(M/32)][colsum_ld] per-32-row column sums of out
   int colsum_ld;
 };
@@ -218,8 +224,8 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;          // [2]       MMA -> epilogue (chunk ready)
-  uint64_t* acc_empty = bars + 2 * STAGES + 2;     // [2]       epilogue -> MMA (chunk drained), count 4
-  uint64_t* s_empty = bars + 2 * STAGES + 4;       // [2]       epilogue -> MMA (small-term acc read), count 4
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;     // [2]       epilogue -> MMA (chunk drained), count EPI_WARPS
+  uint64_t* s_empty = bars + 2 * STAGES + 4;       // [2]       epilogue -> MMA (small-term acc read), count EPI_WARPS
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -240,8 +246,8 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(smem_u32(&acc_full[b]), 1);
-        mbar_init(smem_u32(&acc_empty[b]), 4);
-        mbar_init(smem_u32(&s_empty[b]), 4);
+        mbar_init(smem_u32(&acc_empty[b]), EPI_WARPS);
+        mbar_init(smem_u32(&s_empty[b]), EPI_WARPS);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -332,33 +338,47 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else {
-    // ================= epilogue warps 2..5: TMEM lane quadrant = warp % 4 =================
-    const int quad = warp & 3;
+    // ================= epilogue warps 2..9 =================
+    const int quad = warp & 3;                       // TMEM lane quadrant a warp may read = warp % 4
+    const int half = (warp - 2) >> 2;                // which 64 of the tile's 128 columns
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    float* stage = epi_stage + quad * EPI_STAGE_FLOATS;
+    const uint32_t col_base = (uint32_t)(half * EPI_COLS);
+    float* stage = epi_stage + (warp - 2) * EPI_STAGE_FLOATS;
     uint32_t gchunk = 0, tile_i = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
       const Item it = decode_item(g, item);
-      float acc[BN];
+      const int mrow0 = it.m0 + quad * 32;
+      const int ncol0 = it.n0 + (int)col_base;        // first output column of this warp
+      const int my_row = mrow0 + lane;
+      // ReLU mask: one sign-bit word per (row, 32-column block), fetched before the accumulators are awaited
+      uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
+      if (EPI == EPI_MASK && g.mask_bits) {
 #pragma unroll
-      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+        for (int q = 0; q < 2; ++q) {
+          const int kbo = (ncol0 >> 5) + q;
+          mw[q] = (my_row < g.M && kbo < g.out_nkb) ? __ldg(g.mask_bits + (size_t)kbo * g.M + my_row) : 0u;
+        }
+      }
+      float acc[EPI_COLS];
+#pragma unroll
+      for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
       const int nchunks = (it.nkb + CHUNK - 1) / CHUNK;
       for (int c = 0; c < nchunks; ++c, ++gchunk) {
         const uint32_t b = gchunk & 1;
         mbar_wait(smem_u32(&acc_full[b]), (gchunk >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           uint32_t r[32];
-          tmem_ld32(tmem_base + lane_base + b * 128 + q * 32, r);
+          tmem_ld32(tmem_base + lane_base + b * 128 + col_base + q * 32, r);
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);   // fp32 RN adds
         }
         if (c == nchunks - 1) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 2; ++q) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + q * 32, r);
+            tmem_ld32(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + col_base + q * 32, r);
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);
           }
@@ -370,31 +390,42 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (c == nchunks - 1) mbar_arrive(smem_u32(&s_empty[tile_i & 1]));
         }
       }
-      // ---- tile output.  Each warp owns rows [mrow0, mrow0+32) x 128 columns, processed as four
-      // 32x32 slices: registers (lane = row) -> smem -> (lane = 4-column group of 4 rows) so that
-      // every global access of the warp covers whole 128 B lines (planes: one contiguous 512 B run).
-      const int mrow0 = it.m0 + quad * 32;
+      // ---- tile output.  Each warp owns rows [mrow0, mrow0+32) x 64 columns, processed as two 32x32
+      // slices: registers (lane = row; bias/ReLU/mask and sign bits here) -> smem -> (lane = 4-column
+      // group of 4 rows) so that every global access of the warp covers whole 128 B lines (planes: one
+      // contiguous 512 B run per instruction).
       const int c4 = (lane & 7) * 4;
       const int rsub = lane >> 3;
       float* dense = g.out;
       if (EPI == EPI_PARTIAL) dense += (size_t)it.split * g.M * g.N;
       const bool dense_vec = !OUT_PLANES && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int cbase = it.n0 + q * 32;
+      for (int q = 0; q < 2; ++q) {
+        const int cbase = ncol0 + q * 32;
         const int kbo = cbase >> 5;
         const bool live = OUT_PLANES ? (kbo < g.out_nkb) : (cbase < g.N);   // warp-uniform
+        if (EPI == EPI_BIAS_ACT) {
+          uint32_t bits = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = acc[q * 32 + j];
+            if (g.bias && cbase + j < g.N) v += __ldg(g.bias + cbase + j);    // warp-uniform address
+            if (g.act == ADN_ACT_RELU) v = fmaxf(v, 0.f);
+            if (cbase + j >= g.N) v = 0.f;            // K padding of the next GEMM must be exact zeros
+            bits |= (v > 0.f) ? (1u << j) : 0u;
+            acc[q * 32 + j] = v;
+          }
+          if (OUT_PLANES && live && my_row < g.M) g.out_bits[(size_t)kbo * g.M + my_row] = bits;
+        } else if (EPI == EPI_MASK) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (!((mw[q] >> j) & 1u) || cbase + j >= g.N) acc[q * 32 + j] = 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = acc[q * 32 + j];
         __syncwarp();
         if (live && mrow0 < g.M) {
           const int col = cbase + c4;
-          float bias_v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (EPI == EPI_BIAS_ACT && g.bias) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (col + k < g.N) bias_v[k] = __ldg(g.bias + col + k);
-          }
           float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -403,32 +434,14 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const bool rv = row < g.M;
             float v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = stage[r * 33 + c4 + k];
-            const size_t poff = ((size_t)kbo * g.M + row) * 32 + c4;   // plane offset of (row, col..col+3)
-            if (EPI == EPI_BIAS_ACT) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                v[k] += bias_v[k];
-                if (g.act == ADN_ACT_RELU) v[k] = fmaxf(v[k], 0.f);
-              }
-            } else if (EPI == EPI_MASK) {
-              if (g.mask_hi && rv) {
-                const float4 m = __ldg(reinterpret_cast<const float4*>(g.mask_hi + poff));
-                if (!(m.x > 0.f)) v[0] = 0.f;
-                if (!(m.y > 0.f)) v[1] = 0.f;
-                if (!(m.z > 0.f)) v[2] = 0.f;
-                if (!(m.w > 0.f)) v[3] = 0.f;
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (!rv || col + k >= g.N) v[k] = 0.f;     // K padding of the next GEMM must be exact zeros
+            for (int k = 0; k < 4; ++k) v[k] = rv ? stage[r * 33 + c4 + k] : 0.f;
             if (EPI == EPI_MASK) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) cs[k] += v[k];
             }
             if (rv) {
               if (OUT_PLANES) {
+                const size_t poff = ((size_t)kbo * g.M + row) * 32 + c4;   // plane offset of (row, col..col+3)
                 float h[4], l[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) split_tf32(v[k], h[k], l[k]);
@@ -478,30 +491,45 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 // dense <-> planes conversion (inputs x / labels-side gradients / weights; everything
 // between two GEMMs is written as planes by the producing epilogue instead)
 // ---------------------------------------------------------------------------------
-// src[rows, cols] row-major -> hi/lo[nkb][rows][32], zero padded in cols
+// src[rows, cols] row-major -> hi/lo[nkb][rows][32] (zero padded in cols) + sign bits[nkb][rows]
 __global__ void __launch_bounds__(256)
-split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int rows, int cols,
-             int nkb) {
-  const int vec_per_row = nkb * 8;                       // float4 per padded row
+split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, uint32_t* __restrict__ bits,
+             int rows, int cols, int nkb) {
+  const int vec_per_row = nkb * 8;                       // float4 per padded row; 8 consecutive threads = one k-block
   const int64_t nvec = (int64_t)rows * vec_per_row;
+  const int64_t nvec_pad = (nvec + 31) & ~(int64_t)31;   // whole warps run the loop (shuffles below)
   const bool vec_src = ((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / vec_per_row);
-    const int c = (int)(i % vec_per_row) * 4;
-    float v[4];
-    if (vec_src && c + 3 < cols) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * cols + c));
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_pad; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = i < nvec;
+    const int r = live ? (int)(i / vec_per_row) : 0;
+    const int c = live ? (int)(i % vec_per_row) * 4 : 0;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      if (vec_src && c + 3 < cols) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * cols + c));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = (c + q < cols) ? __ldg(src + (size_t)r * cols + c + q) : 0.f;
+        for (int q = 0; q < 4; ++q) v[q] = (c + q < cols) ? __ldg(src + (size_t)r * cols + c + q) : 0.f;
+      }
     }
     float h[4], l[4];
+    uint32_t nib = 0u;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
-    const size_t dst = ((size_t)(c >> 5) * rows + r) * 32 + (c & 31);
-    *reinterpret_cast<float4*>(hi + dst) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
+    for (int q = 0; q < 4; ++q) {
+      split_tf32(v[q], h[q], l[q]);
+      nib |= (v[q] > 0.f) ? (1u << q) : 0u;
+    }
+    uint32_t w = nib << (4 * (threadIdx.x & 7));
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    if (live) {
+      const size_t dst = ((size_t)(c >> 5) * rows + r) * 32 + (c & 31);
+      *reinterpret_cast<float4*>(hi + dst) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
+      if ((threadIdx.x & 7) == 0) bits[(size_t)(c >> 5) * rows + r] = w;
+    }
   }
 }
 
@@ -553,7 +581,16 @@ int init() {
 }
 
 int64_t plane_floats(int64_t rows, int64_t cols) { return align_up(rows * ceil_div(cols, BK) * BK, 64); }
-int64_t planes_bytes(int64_t rows, int64_t cols) { return 2 * plane_floats(rows, cols) * (int64_t)sizeof(float); }
+int64_t bits_words(int64_t rows, int64_t cols) { return align_up(rows * ceil_div(cols, BK), 64); }
+int64_t planes_bytes(int64_t rows, int64_t cols) {
+  return (2 * plane_floats(rows, cols) + bits_words(rows, cols)) * (int64_t)sizeof(float);
+}
+static inline uint32_t* bits_of(float* planes, int64_t rows, int64_t cols) {
+  return reinterpret_cast<uint32_t*>(planes + 2 * plane_floats(rows, cols));
+}
+static inline const uint32_t* bits_of(const float* planes, int64_t rows, int64_t cols) {
+  return reinterpret_cast<const uint32_t*>(planes + 2 * plane_floats(rows, cols));
+}
 
 // a plane tensor viewed as a GEMM operand
 struct Operand {
@@ -608,7 +645,8 @@ int split(const float* src, int64_t rows, int64_t cols, float* planes, cudaStrea
   const int64_t nkb = ceil_div(cols, BK);
   const int64_t nvec = rows * nkb * 8;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nvec, 256), (int64_t)sm_count() * 16));
-  split_kernel<<<blocks, 256, 0, st>>>(src, planes, planes + plane_floats(rows, cols), (int)rows, (int)cols, (int)nkb);
+  split_kernel<<<blocks, 256, 0, st>>>(src, planes, planes + plane_floats(rows, cols), bits_of(planes, rows, cols),
+                                       (int)rows, (int)cols, (int)nkb);
   ADN_CHECK_LAUNCH("planes split");
   return ADN_OK;
 }
@@ -648,7 +686,7 @@ static int dw_splits(int64_t tiles, int64_t kblocks, int max_s) {
 int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
   int64_t b = align_up((int64_t)max_dw_splits(in, out) * in * out * (int64_t)sizeof(float), 256);   // dW split-K partials
   b += align_up(ceil_div(batch, 32) * in * (int64_t)sizeof(float), 256);                             // dx column sums per 32 rows
-  b += align_up(ceil_div(ceil_div(batch, 32), 512) * in * (int64_t)sizeof(float), 256);              // their second-level partials
+  b += align_up(64 * in * (int64_t)sizeof(float), 256);                                              // their second-level partials
   return b + 512;
 }
 
@@ -662,6 +700,7 @@ int dense_fwd(const float* xp, const float* wp, const float* bias, float* yp, fl
   g.bias = bias; g.act = act;
   if (yp) {
     g.out = yp; g.out_lo = yp + plane_floats(batch, out); g.out_nkb = (int)ceil_div(out, BK);
+    g.out_bits = bits_of(yp, batch, out);
     return launch_gemm<EPI_BIAS_ACT, 1>(a, b, g, st, "pl dense_fwd gemm (planes out)");
   }
   g.out = y; g.ldc = (int)out;
@@ -703,11 +742,12 @@ int dense_bwd(const float* xp, const float* wp, const float* dzp, float* dxp, fl
     GemmParams g{};
     g.M = (int)batch; g.N = (int)in;
     g.total_kb = (int)ceil_div(out, BK); g.kb_per_split = g.total_kb; g.splits = 1;
-    g.mask_hi = x_relu_mask ? xp : nullptr;
+    g.mask_bits = x_relu_mask ? bits_of(xp, batch, in) : nullptr;
+    g.out_nkb = (int)ceil_div(in, BK);
     g.colsum_part = dx_colsum ? cspart : nullptr;
     g.colsum_ld = (int)cs_ld;
     if (dxp) {
-      g.out = dxp; g.out_lo = dxp + plane_floats(batch, in); g.out_nkb = (int)ceil_div(in, BK);
+      g.out = dxp; g.out_lo = dxp + plane_floats(batch, in);
       if ((rc = launch_gemm<EPI_MASK, 1>(a, b, g, st, "pl dX gemm (planes out)"))) return rc;
     } else {
       g.out = dx; g.ldc = (int)in;

@@ -8,6 +8,7 @@ namespace pl {
 int init();
 // floats in ONE plane (hi or lo) of a [rows, cols] tensor; a plane tensor is hi followed by lo
 int64_t plane_floats(int64_t rows, int64_t cols);
+int64_t bits_words(int64_t rows, int64_t cols);   // uint32 words of the sign-bit block that follows the two planes
 int64_t planes_bytes(int64_t rows, int64_t cols);
 int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out);
 

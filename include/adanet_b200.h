@@ -190,6 +190,11 @@ int adn_dense_fwd_p(const float* xp, const float* wp, const float* b, float* yp,
 int adn_dense_bwd_p(const float* xp, const float* wp, const float* dzp, float* dxp, float* dx,
                     float* dx_colsum, float* dw, int64_t batch, int64_t in, int64_t out,
                     int x_relu_mask, void* workspace, int64_t workspace_bytes, void* stream);
+/* adn_head_loss that also emits, in the same pass, dlogits as split planes (nullable) and its
+ * column sums = the bias gradient of the logits layer (nullable): what the backward GEMMs consume. */
+int adn_head_loss_p(int head, const float* logits, const int64_t* labels, const float* labels_f,
+                    float* loss_out, float* dlogits, float* dlogits_planes, float* dlogits_colsum,
+                    int64_t batch, int64_t dim, void* workspace, int64_t workspace_bytes, void* stream);
 /* out[c] = sum_r x[r,c], fixed order (bias gradient of the logits layer).
  * workspace: adn_query(ADN_Q_COLSUM_WORKSPACE_BYTES). */
 int adn_colsum(const float* x, int64_t rows, int64_t cols, float* out, void* workspace,

@@ -66,6 +66,13 @@ def test_split_merge_roundtrip(env, r, c):
   if c % 32:
     assert (hi[-1, :, c % 32:] == 0).all()
   assert (hi.view(np.uint32) & 0x1FFF == 0).all()
+  # sign bits [nkb][rows]: bit j of word (kb, row) <=> a[row, kb*32+j] > 0
+  n2 = 2 * (-(-(nkb * r * 32) // 64) * 64)
+  bits = pl[n2: n2 + nkb * r].cpu().numpy().view(np.uint32).reshape(nkb, r)
+  pad = np.zeros((r, nkb * 32), dtype=bool)
+  pad[:, :c] = a > 0
+  want_bits = (pad.reshape(r, nkb, 32) * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32).T
+  assert np.array_equal(bits, want_bits)
 
 
 SHAPES = [(128, 32, 64), (300, 100, 70), (512, 1024, 256), (1000, 257, 10), (2048, 64, 1024), (129, 33, 129)]
@@ -95,9 +102,14 @@ def test_dense_fwd_planes(env, B, I, O, act):
   _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), bd.data_ptr(), yp.data_ptr(), None, B, I, O, act, sp), "fwd_p")
   assert _relerr(_merge(torch, _lib, lib, yp, B, O), exact, sc) < TOL
   nkb = (O + 31) // 32
+  hi = yp[: nkb * B * 32].cpu().numpy().reshape(nkb, B, 32)
   if O % 32:
-    hi = yp[: nkb * B * 32].cpu().numpy().reshape(nkb, B, 32)
     assert (hi[-1, :, O % 32:] == 0).all()
+  # sign bits written by the epilogue agree with the stored values
+  n2 = 2 * (-(-(nkb * B * 32) // 64) * 64)
+  bits = yp[n2: n2 + nkb * B].cpu().numpy().view(np.uint32).reshape(nkb, B)
+  want_bits = ((hi > 0) * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32)
+  assert np.array_equal(bits, want_bits)
 
 
 @pytest.mark.parametrize("B,I,O", SHAPES)
@@ -181,4 +193,5 @@ def test_colsum_and_opt_step_planes(env):
   assert np.array_equal(wd.cpu().numpy(), want)
   assert np.array_equal(bd.cpu().numpy(), (b - np.float32(0.1) * gb).astype(np.float32))
   ref = _planes(torch, _lib, lib, want)
-  assert torch.equal(wp, ref)
+  n2 = 2 * (-(-(100 * 3 * 32) // 64) * 64)      # hi + lo planes of a [100, 70] tensor (3 k-blocks); sign bits follow
+  assert torch.equal(wp[:n2], ref[:n2])
