@@ -64,8 +64,6 @@ extern "C" int adn_init(void) {
   if (done.load()) return ADN_OK;
   int rc = heads_init();
   if (rc) return rc;
-  rc = tc::init();
-  if (rc) return rc;
   rc = pl::init();
   if (rc) return rc;
   (void)sm_count();

@@ -34,6 +34,7 @@ WIDTHS = (64, 128, 192, 256, 384, 512, 768, 1024)
 IN_DIM, CLASSES, BATCH = 100, 10, 32768
 DATA_ROWS = 1_000_000
 METRIC = "candidate-train examples/sec per AdaNet iteration"
+REF_SAMPLE_ROWS = 4096   # rows per step of the --impl reference arm (bounded sample)
 
 
 def workload_name(gpus):
@@ -57,7 +58,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits", "-lms", "100"],
+                                    "--format=csv,noheader,nounits", "-lms", "50"],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
@@ -117,7 +118,8 @@ def run_reference(args):
   from tests import parity_util as pu
   from oracle import adanet_oracle as orc
   cores = os.cpu_count() or 1
-  x, y = orc.make_tabular(BATCH * 4, IN_DIM, CLASSES, seed=1234)
+  rows = REF_SAMPLE_ROWS   # a bounded sample of the B=32768 minibatch per step, so K steps finish in minutes
+  x, y = orc.make_tabular(rows * 4, IN_DIM, CLASSES, seed=1234)
   o_specs, _ = pu.make_specs(oracle_specs(), IN_DIM, CLASSES, 0, ("sgd", 0.05))
   ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
   cands = orc.build_candidates(0, o_specs, [], ens, CLASSES, 0.9)
@@ -125,8 +127,8 @@ def run_reference(args):
 
   def step():
     nonlocal it
-    off = (it % 4) * BATCH
-    orc.train_step(cands, [], ens, x[off:off + BATCH], y[off:off + BATCH])
+    off = (it % 4) * rows
+    orc.train_step(cands, [], ens, x[off:off + rows], y[off:off + rows])
     it += 1
 
   for _ in range(args.warmup):
@@ -135,68 +137,74 @@ def run_reference(args):
   for _ in range(args.steps):
     step()
   dt = time.perf_counter() - t0
-  val = BATCH * args.steps / dt
+  val = rows * args.steps / dt
   line = {
       "impl": "reference", "metric": METRIC, "value": val, "unit": "examples/s", "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
       "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
       "config": {"workload": workload_name(args.gpus), "candidates": len(WIDTHS), "batch": BATCH},
       "cpu_baseline": {"value": val, "unit": "examples/s", "cores": cores, "kind": "port",
-                       "sample": "%d full steps of the same 8-candidate B=%d workload (NumPy/OpenBLAS fp32 oracle; "
-                                 "the TF1 reference itself is not installable: TensorFlow 2.1 absent)" % (args.steps, BATCH)},
+                       "sample": "%d steps, each a %d-row sample of the B=%d minibatch of the same 8-candidate "
+                                 "workload (NumPy/OpenBLAS fp32 oracle on all host cores; the TF1 reference itself "
+                                 "is not installable: TensorFlow 2.1 absent)" % (args.steps, rows, BATCH)},
       "e2e": {"value": val, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
   print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(seconds_budget=20.0):
+def cpu_baseline_sample(seconds_budget=15.0):
+  """The oracle (CPU port of the reference's path) on all host cores, on the same bounded sample
+  per step as the --impl reference arm."""
   from tests import parity_util as pu
   from oracle import adanet_oracle as orc
   cores = os.cpu_count() or 1
-  x, y = orc.make_tabular(BATCH * 2, IN_DIM, CLASSES, seed=1234)
+  rows = REF_SAMPLE_ROWS
+  x, y = orc.make_tabular(rows * 4, IN_DIM, CLASSES, seed=1234)
   o_specs, _ = pu.make_specs(oracle_specs(), IN_DIM, CLASSES, 0, ("sgd", 0.05))
   ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
   cands = orc.build_candidates(0, o_specs, [], ens, CLASSES, 0.9)
-  orc.train_step(cands, [], ens, x[:BATCH], y[:BATCH])   # warm-up
+  for i in range(2):   # warm-up
+    orc.train_step(cands, [], ens, x[i * rows:(i + 1) * rows], y[i * rows:(i + 1) * rows])
   n, t0 = 0, time.perf_counter()
   while True:
-    off = (n % 2) * BATCH
-    orc.train_step(cands, [], ens, x[off:off + BATCH], y[off:off + BATCH])
+    off = (n % 4) * rows
+    orc.train_step(cands, [], ens, x[off:off + rows], y[off:off + rows])
     n += 1
     dt = time.perf_counter() - t0
-    if dt > seconds_budget or n >= 30:
+    if dt > seconds_budget or n >= 200:
       break
-  return {"value": BATCH * n / dt, "unit": "examples/s", "cores": cores, "kind": "port",
-          "sample": "%d full steps (%.1f s) of the same 8-candidate B=%d workload on the NumPy/OpenBLAS fp32 oracle"
-                    % (n, dt, BATCH)}
+  return {"value": rows * n / dt, "unit": "examples/s", "cores": cores, "kind": "port",
+          "sample": "%d steps (%.1f s), each a %d-row sample of the B=%d minibatch of the same 8-candidate workload, "
+                    "NumPy/OpenBLAS fp32 oracle" % (n, dt, rows, BATCH)}
 
 
 def measure_dominant_kernel(lib, torch, reps=20):
-  """CUDA-event timing of the dominant kernel of the step -- the H=1024 hidden-layer
-  dense forward [32768,1024]x[1024,1024] -- on the stream it is launched on."""
+  """CUDA-event timing of the dominant kernel of the step -- the H=1024 hidden-layer dense forward
+  [32768,1024]x[1024,1024] + bias + ReLU, planes in / planes out, exactly as the engine launches it
+  (adn_dense_fwd_p) -- on the stream it is launched on, L2 flushed between launches."""
   from adanet_b200 import _lib
+  from adanet_b200.core import engine as eng
   B, I, O = BATCH, 1024, 1024
+  sp = torch.cuda.current_stream()
   x = torch.randn((B, I), device="cuda")
   w = torch.randn((I, O), device="cuda") * 0.03
   b = torch.zeros((O,), device="cuda")
-  y = torch.empty((B, O), device="cuda")
-  ws_bytes = _lib.query(_lib.Q_DENSE_FWD_WS, B, I, O)
-  ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device="cuda")
-  st = torch.cuda.current_stream()
+  xp, wp, yp = eng.new_planes(B, I, "cuda"), eng.new_planes(I, O, "cuda"), eng.new_planes(B, O, "cuda")
+  _lib.check(lib.adn_planes_split(x.data_ptr(), B, I, xp.data_ptr(), sp.cuda_stream), "split")
+  _lib.check(lib.adn_planes_split(w.data_ptr(), I, O, wp.data_ptr(), sp.cuda_stream), "split")
   flush = torch.empty((256 * 1024 * 1024 // 4,), device="cuda")   # 256 MB > 126 MB L2
   times = []
   for i in range(reps + 3):
     flush.fill_(float(i))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    _lib.check(lib.adn_dense_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, I, O, 1, ws.data_ptr(),
-                                 ws_bytes, st.cuda_stream), "adn_dense_fwd")
-    e1.record(st)
+    e0.record(sp)
+    _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), b.data_ptr(), yp.data_ptr(), None, B, I, O, 1,
+                                   sp.cuda_stream), "adn_dense_fwd_p")
+    e1.record(sp)
     e1.synchronize()
     if i >= 3:
       times.append(e0.elapsed_time(e1) * 1e-3)
-  path = _lib.query(_lib.Q_DENSE_FWD_PATH, B, I, O)
-  return float(np.mean(times)), 2.0 * B * I * O, {1: "simt_fp32", 2: "tcgen05_3xtf32"}.get(path, str(path))
+  return float(np.mean(times)), 2.0 * B * I * O, "tcgen05_3xtf32_planes"
 
 
 def run_ours(args):
@@ -302,7 +310,7 @@ def run_ours(args):
   kt, kflops, kpath = measure_dominant_kernel(lib, torch)
   achieved = kflops / kt / 1e12
   roofline = {
-      "bound": "tensor", "kernel": "adn_dense_fwd [32768,1024]x[1024,1024] bias+relu (%s)" % kpath,
+      "bound": "tensor", "kernel": "adn_dense_fwd_p [32768,1024]x[1024,1024] bias+relu, planes in/out (%s)" % kpath,
       "achieved": achieved, "peak": bf16_burst, "unit": "TFLOP/s", "frac": achieved / bf16_burst,
       "peak_source": "MEASURED_PEAKS.json bf16 burst (%s); algorithmic fp32 FLOPs 2*B*in*out; the tcgen05 path "
                      "issues 3 TF32 MMAs per product (3xTF32 split for 1e-5 fp32 parity), TF32 dense peak = bf16/2"
@@ -334,7 +342,7 @@ def run_ours(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=30)
+  ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--profile", action="store_true", help="step loop only (for ncu captures)")
