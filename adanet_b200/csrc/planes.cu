@@ -52,7 +52,7 @@ static constexpr int TILE_BYTES = 128 * BK * 4;       // 16 KiB
 static constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi A_lo B_hi B_lo
 static constexpr int EPI_WARPS = 8;
 static constexpr int EPI_COLS = 64;                   // accumulator columns per epilogue warp
-static constexpr int EPI_STAGE_FLOATS = 32 * 33;      // per epilogue warp: 32x32 slice transposed through smem
+static constexpr int EPI_STAGE_FLOATS = 32 * 32;      // per epilogue warp: 32x32 slice transposed through smem (swizzled)
 static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
 static constexpr int BAR_BYTES = 256;
 static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
@@ -170,6 +170,18 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -206,6 +218,121 @@ __device__ __forceinline__ Item decode_item(const GemmParams& g, int item) {
   it.kb0 = it.split * g.kb_per_split;
   it.nkb = min(g.total_kb, it.kb0 + g.kb_per_split) - it.kb0;
   return it;
+}
+
+// One 32-row x 32-column slice of a tile: lane = row holds its 32 accumulators a[0..31] (columns
+// cbase..cbase+31).  Applies bias/ReLU (+ sign bits) or the sign-bit ReLU mask in the register layout,
+// transposes through `stage` (16 B chunks XOR-swizzled by row: conflict-free both ways) and writes with
+// lane = 4-column group of 4 rows, so every global access covers whole 128 B lines (planes: one contiguous
+// 512 B run per instruction).  Shared by the 1-CTA and the CTA-pair kernels.
+template <int EPI, int OUT_PLANES>
+__device__ __forceinline__ void emit_slice(const GemmParams& g, float* a, uint32_t mwq, float* stage, int lane,
+                                           int mrow0, int cbase, int rows_ok, float* dense, bool dense_vec) {
+  const int cc = lane & 7;                 // 16 B chunk (4 columns) this lane owns after the transpose
+  const int c4 = cc * 4;
+  const int rsub = lane >> 3;
+  const int my_row = mrow0 + lane;
+  const int kbo = cbase >> 5;
+  const bool live = (OUT_PLANES ? (kbo < g.out_nkb) : (cbase < g.N)) && rows_ok > 0;   // warp-uniform
+  // valid columns of this slice as a bit mask (warp-uniform); all ones for interior tiles
+  const uint32_t cmask = (cbase + 32 <= g.N) ? 0xffffffffu : ((cbase < g.N) ? ((1u << (g.N - cbase)) - 1u) : 0u);
+  if (EPI == EPI_BIAS_ACT) {
+    if (g.bias) {
+      if (cmask == 0xffffffffu && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + cbase) + jj);   // warp-uniform address
+          a[4 * jj + 0] += bv.x; a[4 * jj + 1] += bv.y;
+          a[4 * jj + 2] += bv.z; a[4 * jj + 3] += bv.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if ((cmask >> j) & 1u) a[j] += __ldg(g.bias + cbase + j);
+      }
+    }
+    if (g.act == ADN_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
+    }
+    if (OUT_PLANES) {
+      uint32_t bits = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bits |= (a[j] > 0.f) ? (1u << j) : 0u;
+      bits &= cmask;
+      if (live && my_row < g.M) g.out_bits[(size_t)kbo * g.M + my_row] = bits;
+    }
+    if (cmask != 0xffffffffu) {       // K padding of the next GEMM must be exact zeros
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (!((cmask >> j) & 1u)) a[j] = 0.f;
+    }
+  } else if (EPI == EPI_MASK) {
+    const uint32_t keep = mwq & cmask;
+    if (keep != 0xffffffffu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (!((keep >> j) & 1u)) a[j] = 0.f;
+    }
+  }
+  {
+    float4* srow = reinterpret_cast<float4*>(stage + lane * 32);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+      srow[jj ^ (lane & 7)] = make_float4(a[4 * jj], a[4 * jj + 1], a[4 * jj + 2],
+                                          a[4 * jj + 3]);
+  }
+  __syncwarp();
+  if (live) {
+    const int col = cbase + c4;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    float* hp = OUT_PLANES ? g.out + ((size_t)kbo * g.M + mrow0 + rsub) * 32 + c4 : nullptr;
+    float* lp = OUT_PLANES ? g.out_lo + ((size_t)kbo * g.M + mrow0 + rsub) * 32 + c4 : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rsub + 4 * i;
+      const bool rv = r < rows_ok;
+      float4 t = reinterpret_cast<const float4*>(stage + r * 32)[cc ^ (r & 7)];
+      float v[4] = {t.x, t.y, t.z, t.w};
+      if (EPI == EPI_MASK) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cs[k] += rv ? v[k] : 0.f;
+      }
+      if (rv) {
+        if (OUT_PLANES) {
+          float h[4], l[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) split_tf32(v[k], h[k], l[k]);
+          *reinterpret_cast<float4*>(hp + i * 128) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(lp + i * 128) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+          float* op = dense + (size_t)(mrow0 + r) * g.ldc + col;
+          if (dense_vec && col + 3 < g.N) {
+            *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (col + k < g.N) op[k] = v[k];
+          }
+        }
+      }
+    }
+    if (EPI == EPI_MASK && g.colsum_part) {
+      // rows of this lane: rsub + 4i; fold the 4 row groups (lanes l, l^8, l^16, l^24) in a fixed order
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+      }
+      if (rsub == 0) {
+        float* cp = g.colsum_part + (size_t)(mrow0 >> 5) * g.colsum_ld + col;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (col + k < g.colsum_ld) cp[k] = cs[k];
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------
@@ -367,20 +494,26 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t b = gchunk & 1;
         mbar_wait(smem_u32(&acc_full[b]), (gchunk >> 1) & 1);
         tc_fence_after();
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(tmem_base + lane_base + b * 128 + col_base, r0);
+          tmem_ld32_nowait(tmem_base + lane_base + b * 128 + col_base + 32, r1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_base + b * 128 + col_base + q * 32, r);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);   // fp32 RN adds
+          for (int j = 0; j < 32; ++j) {          // fp32 RN adds
+            acc[j] += __uint_as_float(r0[j]);
+            acc[32 + j] += __uint_as_float(r1[j]);
+          }
         }
         if (c == nchunks - 1) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + col_base, r0);
+          tmem_ld32_nowait(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + col_base + 32, r1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + col_base + q * 32, r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[q * 32 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) {
+            acc[j] += __uint_as_float(r0[j]);
+            acc[32 + j] += __uint_as_float(r1[j]);
           }
         }
         tc_fence_before();
@@ -391,91 +524,17 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
       // ---- tile output.  Each warp owns rows [mrow0, mrow0+32) x 64 columns, processed as two 32x32
-      // slices: registers (lane = row; bias/ReLU/mask and sign bits here) -> smem -> (lane = 4-column
-      // group of 4 rows) so that every global access of the warp covers whole 128 B lines (planes: one
-      // contiguous 512 B run per instruction).
-      const int c4 = (lane & 7) * 4;
-      const int rsub = lane >> 3;
+      // slices: registers (lane = row; bias/ReLU/mask and sign bits here) -> smem (16 B chunks XOR-swizzled
+      // by row, so both the row-wise float4 writes and the transposed float4 reads are conflict-free) ->
+      // (lane = 4-column group of 4 rows) so that every global access of the warp covers whole 128 B
+      // lines (planes: one contiguous 512 B run per instruction).
       float* dense = g.out;
       if (EPI == EPI_PARTIAL) dense += (size_t)it.split * g.M * g.N;
       const bool dense_vec = !OUT_PLANES && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+      const int rows_ok = min(32, g.M - mrow0);          // warp-uniform; <= 0: nothing to write
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int cbase = ncol0 + q * 32;
-        const int kbo = cbase >> 5;
-        const bool live = OUT_PLANES ? (kbo < g.out_nkb) : (cbase < g.N);   // warp-uniform
-        if (EPI == EPI_BIAS_ACT) {
-          uint32_t bits = 0u;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = acc[q * 32 + j];
-            if (g.bias && cbase + j < g.N) v += __ldg(g.bias + cbase + j);    // warp-uniform address
-            if (g.act == ADN_ACT_RELU) v = fmaxf(v, 0.f);
-            if (cbase + j >= g.N) v = 0.f;            // K padding of the next GEMM must be exact zeros
-            bits |= (v > 0.f) ? (1u << j) : 0u;
-            acc[q * 32 + j] = v;
-          }
-          if (OUT_PLANES && live && my_row < g.M) g.out_bits[(size_t)kbo * g.M + my_row] = bits;
-        } else if (EPI == EPI_MASK) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (!((mw[q] >> j) & 1u) || cbase + j >= g.N) acc[q * 32 + j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = acc[q * 32 + j];
-        __syncwarp();
-        if (live && mrow0 < g.M) {
-          const int col = cbase + c4;
-          float cs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rsub + 4 * i;
-            const int row = mrow0 + r;
-            const bool rv = row < g.M;
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = rv ? stage[r * 33 + c4 + k] : 0.f;
-            if (EPI == EPI_MASK) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) cs[k] += v[k];
-            }
-            if (rv) {
-              if (OUT_PLANES) {
-                const size_t poff = ((size_t)kbo * g.M + row) * 32 + c4;   // plane offset of (row, col..col+3)
-                float h[4], l[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) split_tf32(v[k], h[k], l[k]);
-                *reinterpret_cast<float4*>(g.out + poff) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(g.out_lo + poff) = make_float4(l[0], l[1], l[2], l[3]);
-              } else {
-                float* op = dense + (size_t)row * g.ldc + col;
-                if (dense_vec && col + 3 < g.N) {
-                  *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (col + k < g.N) op[k] = v[k];
-                }
-              }
-            }
-          }
-          if (EPI == EPI_MASK && g.colsum_part) {
-            // rows of this lane: rsub + 4i; fold the 4 row groups (lanes l, l^8, l^16, l^24) in a fixed order
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
-              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
-            }
-            if (rsub == 0) {
-              float* cp = g.colsum_part + (size_t)(mrow0 >> 5) * g.colsum_ld + col;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (col + k < g.colsum_ld) cp[k] = cs[k];
-            }
-          }
-        }
-        __syncwarp();
-      }
+      for (int q = 0; q < 2; ++q)
+        emit_slice<EPI, OUT_PLANES>(g, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
     }
   }
   tc_fence_before();
@@ -483,6 +542,345 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// CTA-pair GEMM kernel (tcgen05 cta_group::2): one 256 x 256 tile per pair of SMs.
+//
+// Per SM and k-block the pair tile moves (128 A rows + 128 B rows) x 32 x 8 B = 64 KiB for 1536 clk of
+// tensor work -- half the operand traffic per flop of the 128x128 single-CTA tile, which is what that
+// kernel is bound by (TMA latency cover and shared-memory traffic) on the big layers.
+//   CTA rank r of the pair owns A rows / D rows [m0 + 128 r, +128) and supplies B rows
+//   [n0 + r n_inst/2, + n_inst/2); the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256,
+//   N = n_inst <= 256, trimmed to the live columns in steps of 64) for both SMs.
+//   TMEM per SM (512 columns): H [0,256) = hi*hi partial sums of ONE 128-K chunk, S [256,512) = cross
+//   terms of the whole tile.  H is single-buffered: the next chunk starts with its 8 cross-term MMAs
+//   (1024 clk of tensor work) while the epilogue warps of both CTAs drain H into registers.
+//   Barriers: TMA of both CTAs -> leader's full[s] (tx bytes of both); commit multicast -> both CTAs'
+//   empty[s] / acc_full; epilogue warps of both CTAs -> leader's acc_empty / s_empty (remote arrive).
+// Arithmetic (MMA order per accumulator, RN register adds) is identical to pl_gemm_kernel.
+// ---------------------------------------------------------------------------------
+static constexpr int BM2 = 256, BN2 = 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier whose arrivals come from other CTAs of the cluster
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((it & 1023u) == 1023u) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t da_hi, uint32_t db_hi,
+                                              uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(da_lo), "r"(db_lo), "r"(da_hi), "r"(db_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+struct Item2 {
+  int m0, n0, kb0, nkb, split, n_inst;
+};
+__device__ __forceinline__ Item2 decode_item2(const GemmParams& g, int item) {
+  Item2 it;
+  const int tiles = g.tiles_m * g.tiles_n;       // 256 x 256 tiles
+  it.split = item / tiles;
+  const int t = item - it.split * tiles;
+  const int tm = t / g.tiles_n;
+  it.m0 = tm * BM2;
+  it.n0 = (t - tm * g.tiles_n) * BN2;
+  it.kb0 = it.split * g.kb_per_split;
+  it.nkb = min(g.total_kb, it.kb0 + g.kb_per_split) - it.kb0;
+  it.n_inst = min(BN2, ((g.N - it.n0 + 63) >> 6) << 6);   // live columns, in steps of 64 (32 per CTA half)
+  return it;
+}
+
+template <int EPI, int OUT_PLANES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+pl_gemm2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const GemmParams g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]  leader's: TMA of both CTAs -> MMA
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]  each CTA's: MMA commit (multicast) -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;          // [1]       each CTA's: MMA commit (multicast) -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 1;     // [1]       leader's: epilogue warps of both CTAs -> MMA (H drained)
+  uint64_t* s_empty = bars + 2 * STAGES + 2;       // [1]       leader's: epilogue warps of both CTAs -> MMA (S drained)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 3);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int n_items = g.tiles_m * g.tiles_n * g.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi);
+    tma_prefetch_desc(&map_b_lo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(acc_full), 1);
+      mbar_init(smem_u32(acc_empty), 2 * EPI_WARPS);
+      mbar_init(smem_u32(s_empty), 2 * EPI_WARPS);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs: own A rows, own half of B) =================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      const uint32_t smem0 = smem_u32(smem);
+      for (int item = pair; item < n_items; item += npairs) {
+        const Item2 it = decode_item2(g, item);
+        const int a_row = it.m0 + (int)rank * 128;
+        const int b_row = it.n0 + (int)rank * (it.n_inst >> 1);
+        for (int kb = 0; kb < it.nkb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2 * STAGE_BYTES);   // bytes of both CTAs
+          const uint32_t fb = mapa_rank(smem_u32(&full_bar[s]), 0);                 // leader's barrier
+          const uint32_t base = smem0 + s * STAGE_BYTES;
+          const int kc = it.kb0 + kb;
+          const int a1 = g.a_mn ? kc * BK : a_row, a2 = g.a_mn ? (a_row >> 5) : kc;
+          const int b1 = g.b_mn ? kc * BK : b_row, b2 = g.b_mn ? (b_row >> 5) : kc;
+          tma_load_3d_2sm(&map_a_hi, fb, base + 0 * TILE_BYTES, 0, a1, a2);
+          tma_load_3d_2sm(&map_a_lo, fb, base + 1 * TILE_BYTES, 0, a1, a2);
+          tma_load_3d_2sm(&map_b_hi, fb, base + 2 * TILE_BYTES, 0, b1, b2);
+          tma_load_3d_2sm(&map_b_lo, fb, base + 3 * TILE_BYTES, 0, b1, b2);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0) {
+      const uint32_t dah = desc_hi_word(g.a_mn), dbh = desc_hi_word(g.b_mn);
+      const uint32_t smem0 = smem_u32(smem);
+      const uint32_t a_lo0 = desc_lo_word(smem0, g.a_mn);
+      const uint32_t b_lo0 = desc_lo_word(smem0 + 2 * TILE_BYTES, g.b_mn);
+      const uint32_t a_step = g.a_mn ? (1024u >> 4) : (32u >> 4);
+      const uint32_t b_step = g.b_mn ? (1024u >> 4) : (32u >> 4);
+      const uint32_t acc_h = tmem_base, acc_s = tmem_base + 256;
+      uint32_t s = 0, ph = 0, gchunk = 0, tile_i = 0;
+      for (int item = pair; item < n_items; item += npairs, ++tile_i) {
+        const Item2 it = decode_item2(g, item);
+        const uint32_t idesc = make_idesc(BM2, it.n_inst, g.a_mn, g.b_mn);
+        mbar_wait_cluster(smem_u32(s_empty), (tile_i & 1) ^ 1);     // cross-term accumulator drained by both CTAs
+        tc_fence_after();
+        uint32_t s_accum = 0;
+        for (int kb = 0; kb < it.nkb; kb += CHUNK, ++gchunk) {
+          const int nk = min(CHUNK, it.nkb - kb);
+          uint32_t h_accum = 0;
+          for (int kk = 0; kk < nk; ++kk) {
+            mbar_wait(smem_u32(&full_bar[s]), ph);
+            tc_fence_after();
+            const uint32_t so = s * (STAGE_BYTES >> 4);
+            if (kk == 0) {
+              // new chunk: cross terms first, so the tensor pipe stays busy while H is being drained
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                  const uint32_t a_hi = a_lo0 + so + k * a_step, a_lo = a_hi + (TILE_BYTES >> 4);
+                  const uint32_t b_hi = b_lo0 + so + k * b_step, b_lo = b_hi + (TILE_BYTES >> 4);
+                  umma_tf32_2sm(acc_s, a_lo, b_hi, dah, dbh, idesc, (k == 0) ? s_accum : 1u);
+                  umma_tf32_2sm(acc_s, a_hi, b_lo, dah, dbh, idesc, 1u);
+                }
+              }
+              __syncwarp();
+              mbar_wait_cluster(smem_u32(acc_empty), (gchunk & 1) ^ 1);   // H drained by both CTAs
+              tc_fence_after();
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                  const uint32_t a_hi = a_lo0 + so + k * a_step;
+                  const uint32_t b_hi = b_lo0 + so + k * b_step;
+                  umma_tf32_2sm(acc_h, a_hi, b_hi, dah, dbh, idesc, (k == 0) ? 0u : 1u);
+                }
+                umma_commit_2sm(smem_u32(&empty_bar[s]));
+                if (nk == 1) umma_commit_2sm(smem_u32(acc_full));
+              }
+            } else {
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                  const uint32_t a_hi = a_lo0 + so + k * a_step, a_lo = a_hi + (TILE_BYTES >> 4);
+                  const uint32_t b_hi = b_lo0 + so + k * b_step, b_lo = b_hi + (TILE_BYTES >> 4);
+                  umma_tf32_2sm(acc_s, a_lo, b_hi, dah, dbh, idesc, 1u);
+                  umma_tf32_2sm(acc_s, a_hi, b_lo, dah, dbh, idesc, 1u);
+                  umma_tf32_2sm(acc_h, a_hi, b_hi, dah, dbh, idesc, 1u);
+                }
+                umma_commit_2sm(smem_u32(&empty_bar[s]));
+                if (kk == nk - 1) umma_commit_2sm(smem_u32(acc_full));
+              }
+            }
+            __syncwarp();
+            s_accum = 1u;
+            (void)h_accum;
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..9 (both CTAs; 32 rows x 128 columns each) =================
+    const int quad = warp & 3;
+    const int cgrp = (warp - 2) >> 2;                // which 128 of the tile's 256 columns
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t col_base = (uint32_t)(cgrp * 128);
+    float* stage = epi_stage + (warp - 2) * EPI_STAGE_FLOATS;
+    const uint32_t acc_empty_leader = mapa_rank(smem_u32(acc_empty), 0);
+    const uint32_t s_empty_leader = mapa_rank(smem_u32(s_empty), 0);
+    uint32_t gchunk = 0;
+    for (int item = pair; item < n_items; item += npairs) {
+      const Item2 it = decode_item2(g, item);
+      const int mrow0 = it.m0 + (int)rank * 128 + quad * 32;
+      const int ncol0 = it.n0 + (int)col_base;
+      const int my_row = mrow0 + lane;
+      const bool cols_live = ncol0 < g.N;            // warp-uniform: does this warp own any live column?
+      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (EPI == EPI_MASK && g.mask_bits) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int kbo = (ncol0 >> 5) + q;
+          mw[q] = (my_row < g.M && kbo < g.out_nkb) ? __ldg(g.mask_bits + (size_t)kbo * g.M + my_row) : 0u;
+        }
+      }
+      float acc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      const int nchunks = (it.nkb + CHUNK - 1) / CHUNK;
+      for (int c = 0; c < nchunks; ++c, ++gchunk) {
+        mbar_wait(smem_u32(acc_full), gchunk & 1);
+        tc_fence_after();
+        if (cols_live) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16_nowait(tmem_base + lane_base + col_base + t * 32, r0);
+            tmem_ld16_nowait(tmem_base + lane_base + col_base + t * 32 + 16, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {           // fp32 RN adds
+              acc[t * 32 + j] += __uint_as_float(r0[j]);
+              acc[t * 32 + 16 + j] += __uint_as_float(r1[j]);
+            }
+          }
+          if (c == nchunks - 1) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              uint32_t r0[16], r1[16];
+              tmem_ld16_nowait(tmem_base + lane_base + 256 + col_base + t * 32, r0);
+              tmem_ld16_nowait(tmem_base + lane_base + 256 + col_base + t * 32 + 16, r1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                acc[t * 32 + j] += __uint_as_float(r0[j]);
+                acc[t * 32 + 16 + j] += __uint_as_float(r1[j]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(acc_empty_leader);
+          if (c == nchunks - 1) mbar_arrive_cluster(s_empty_leader);
+        }
+      }
+      if (cols_live) {
+        float* dense = g.out;
+        if (EPI == EPI_PARTIAL) dense += (size_t)it.split * g.M * g.N;
+        const bool dense_vec = !OUT_PLANES && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+        const int rows_ok = min(32, g.M - mrow0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          emit_slice<EPI, OUT_PLANES>(g, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // neither CTA frees TMEM / exits while the peer may still use its smem or barriers
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
 }
@@ -572,6 +970,12 @@ int init() {
     ADN_PL_ATTR(EPI_MASK, 0); ADN_PL_ATTR(EPI_MASK, 1);
     ADN_PL_ATTR(EPI_PARTIAL, 0);
 #undef ADN_PL_ATTR
+#define ADN_PL_ATTR2(E, P) \
+  ok = ok && (cudaFuncSetAttribute(pl_gemm2_kernel<E, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess)
+    ADN_PL_ATTR2(EPI_BIAS_ACT, 0); ADN_PL_ATTR2(EPI_BIAS_ACT, 1);
+    ADN_PL_ATTR2(EPI_MASK, 0); ADN_PL_ATTR2(EPI_MASK, 1);
+    ADN_PL_ATTR2(EPI_PARTIAL, 0);
+#undef ADN_PL_ATTR2
     if (!ok) {
       (void)cudaGetLastError();
       rc = fail(ADN_ERR_CUDA, "pl::init: cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
@@ -619,6 +1023,16 @@ static int make_map(CUtensorMap* map, const float* plane, int64_t rows, int64_t 
   return ADN_OK;
 }
 
+// Measured on B200 (profiles/r1d_pair_vs_single.txt): under the ~1 kW power cap both kernels sit at the same
+// ~0.85-0.9 of the clock-limited TF32 rate on the big layers, and the pair kernel loses on small problems, so it
+// is only taken for large ones.  ADN_PL_PAIR=0/1 forces the choice (tests exercise both).
+static bool use_pair(int M, int N) {
+  static const int env = getenv("ADN_PL_PAIR") ? atoi(getenv("ADN_PL_PAIR")) : -1;
+  if (env == 0) return false;
+  if (env == 1) return true;
+  return M >= 2048 && N >= 512;
+}
+
 template <int EPI, int OUT_PLANES>
 static int launch_gemm(const Operand& a, const Operand& b, GemmParams g, cudaStream_t st, const char* what) {
   if ((reinterpret_cast<uintptr_t>(a.hi) | reinterpret_cast<uintptr_t>(a.lo) | reinterpret_cast<uintptr_t>(b.hi) |
@@ -632,11 +1046,20 @@ static int launch_gemm(const Operand& a, const Operand& b, GemmParams g, cudaStr
   if ((rc = make_map(&mb_lo, b.lo, b.rows, b.nkb, b.mn_major))) return rc;
   g.a_mn = a.mn_major;
   g.b_mn = b.mn_major;
-  g.tiles_m = (int)ceil_div(g.M, BM);
-  g.tiles_n = (int)ceil_div(g.N, BN);
-  const int items = g.tiles_m * g.tiles_n * g.splits;
-  const int grid = std::min(items, sm_count());
-  pl_gemm_kernel<EPI, OUT_PLANES><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
+  if (use_pair(g.M, g.N)) {
+    // CTA-pair kernel: 256 x 256 tiles, one per pair of SMs
+    g.tiles_m = (int)ceil_div(g.M, BM2);
+    g.tiles_n = (int)ceil_div(g.N, BN2);
+    const int items = g.tiles_m * g.tiles_n * g.splits;
+    const int grid = 2 * std::min(items, sm_count() / 2);
+    pl_gemm2_kernel<EPI, OUT_PLANES><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
+  } else {
+    g.tiles_m = (int)ceil_div(g.M, BM);
+    g.tiles_n = (int)ceil_div(g.N, BN);
+    const int items = g.tiles_m * g.tiles_n * g.splits;
+    const int grid = std::min(items, sm_count());
+    pl_gemm_kernel<EPI, OUT_PLANES><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
+  }
   ADN_CHECK_LAUNCH(what);
   return ADN_OK;
 }
@@ -669,8 +1092,8 @@ static int max_dw_splits(int64_t in, int64_t out) {
 }
 
 // pick S minimising (persistent rounds) x (k-blocks per item) + a per-split reduction cost
-static int dw_splits(int64_t tiles, int64_t kblocks, int max_s) {
-  const int sms = sm_count();
+static int dw_splits(int64_t tiles, int64_t kblocks, int max_s, int workers) {
+  const int sms = workers;
   int best = 1;
   double best_t = 1e30;
   for (int s = 1; s <= max_s && s <= kblocks; ++s) {
@@ -726,7 +1149,9 @@ int dense_bwd(const float* xp, const float* wp, const float* dzp, float* dxp, fl
     const Operand a = operand(xp, batch, in, 1);
     const Operand b = operand(dzp, batch, out, 1);
     const int64_t kb_b = ceil_div(batch, BK);
-    const int S = dw_splits(ceil_div(in, BM) * ceil_div(out, BN), kb_b, max_s);
+    const bool pair = use_pair((int)in, (int)out);
+    const int S = pair ? dw_splits(ceil_div(in, BM2) * ceil_div(out, BN2), kb_b, max_s, sm_count() / 2)
+                       : dw_splits(ceil_div(in, BM) * ceil_div(out, BN), kb_b, max_s, sm_count());
     GemmParams g{};
     g.M = (int)in; g.N = (int)out; g.ldc = (int)out;
     g.total_kb = (int)kb_b; g.kb_per_split = (int)ceil_div(kb_b, S);
