@@ -195,3 +195,46 @@ def test_colsum_and_opt_step_planes(env):
   ref = _planes(torch, _lib, lib, want)
   n2 = 2 * (-(-(100 * 3 * 32) // 64) * 64)      # hi + lo planes of a [100, 70] tensor (3 k-blocks); sign bits follow
   assert torch.equal(wp[:n2], ref[:n2])
+
+
+def test_pair_kernel_forced_matches_single():
+  """The CTA-pair (cta_group::2) kernel and the single-CTA kernel run the same MMA / accumulate order per
+  output element: forcing either through ADN_PL_PAIR must give bit-identical results (subprocesses: the
+  knob is read once per process)."""
+  import os
+  import subprocess
+  import sys
+  code = r"""
+import numpy as np, torch, sys, hashlib
+sys.path.insert(0, %r)
+import __graft_entry__ as g; g.build()
+from adanet_b200 import _lib
+lib = _lib.load(); _lib.check(lib.adn_init(), "init")
+sp = torch.cuda.current_stream().cuda_stream
+rng = np.random.default_rng(11)
+B, I, O = 1000, 300, 330
+def planes(a):
+  r, c = a.shape
+  pl = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, r, c) // 4,), device="cuda")
+  src = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+  _lib.check(lib.adn_planes_split(src.data_ptr(), r, c, pl.data_ptr(), sp), "split"); return pl
+x = np.maximum(rng.standard_normal((B, I)), 0).astype(np.float32); w = rng.standard_normal((I, O)).astype(np.float32) / 17
+dz = rng.standard_normal((B, O)).astype(np.float32); b = rng.standard_normal((O,)).astype(np.float32)
+xp, wp, dzp = planes(x), planes(w), planes(dz); bd = torch.as_tensor(b).cuda()
+yp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, O) // 4,), device="cuda")
+_lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), bd.data_ptr(), yp.data_ptr(), None, B, I, O, 1, sp), "fwd")
+nb = _lib.query(_lib.Q_DENSE_BWD_P_WS, B, I, O); ws = torch.empty((nb,), dtype=torch.uint8, device="cuda")
+dw = torch.empty((I, O), device="cuda"); cs = torch.empty((I,), device="cuda")
+dxp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, I) // 4,), device="cuda")
+_lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), dxp.data_ptr(), None, cs.data_ptr(), dw.data_ptr(), B, I, O, 1, ws.data_ptr(), nb, sp), "bwd")
+h = hashlib.sha256()
+for t in (yp, dw, cs, dxp): h.update(t.cpu().numpy().tobytes())
+print("HASH", h.hexdigest())
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = []
+  for pair in ("0", "1"):
+    env = dict(os.environ, ADN_PL_PAIR=pair)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][0])
+  assert out[0] == out[1]
