@@ -195,12 +195,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// hi = rna_tf32(v), lo = rna_tf32(v - hi).  cvt.rna.tf32.f32 is emulated in SASS (add, NaN/Inf test, select,
+// mask: 4 instructions); on the bit pattern it is "add half a TF32 ulp to the magnitude, clear the low 13
+// bits", done here in two integer ops (Inf stays Inf, NaN stays NaN, finite values are bit-identical).
+__device__ __forceinline__ float rna_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-  lo = __uint_as_float(l);
+  hi = rna_tf32(v);
+  lo = rna_tf32(v - hi);
 }
 
 // work item -> (tile_m, tile_n, split).  n fastest so concurrently resident CTAs share A tiles.
