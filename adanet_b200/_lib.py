@@ -28,8 +28,22 @@ EXPORTS = (
     "adn_last_error", "adn_init", "adn_query", "adn_set_dense_path", "adn_dense_fwd", "adn_dense_bwd", "adn_head_loss",
     "adn_ensemble_head", "adn_opt_step", "adn_l1_norm", "adn_ema_update", "adn_record_scalars",
     "adn_counter_add", "adn_planes_split", "adn_planes_merge", "adn_dense_fwd_p", "adn_dense_bwd_p", "adn_colsum",
-    "adn_opt_step_p", "adn_head_loss_p",
+    "adn_opt_step_p", "adn_head_loss_p", "adn_dense_fwd_p_group", "adn_dense_bwd_p_group",
 )
+
+
+class FwdOp(ctypes.Structure):
+  """adn_fwd_op (include/adanet_b200.h)"""
+  _fields_ = [("xp", c_void_p), ("wp", c_void_p), ("bias", c_void_p), ("yp", c_void_p), ("y", c_void_p),
+              ("in_", c_int64), ("out", c_int64), ("act", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class BwdOp(ctypes.Structure):
+  """adn_bwd_op (include/adanet_b200.h)"""
+  _fields_ = [("xp", c_void_p), ("wp", c_void_p), ("dzp", c_void_p), ("dxp", c_void_p), ("dx", c_void_p),
+              ("dx_colsum", c_void_p), ("dw", c_void_p), ("in_", c_int64), ("out", c_int64),
+              ("x_relu_mask", ctypes.c_int32), ("reserved", ctypes.c_int32), ("workspace", c_void_p),
+              ("workspace_bytes", c_int64)]
 
 
 class AdnError(RuntimeError):
@@ -72,6 +86,8 @@ def load():
   lib.adn_dense_bwd_p.argtypes = [p, p, p, p, p, p, p, i64, i64, i64, c_int, p, i64, p]
   lib.adn_colsum.argtypes = [p, i64, i64, p, p, i64, p]
   lib.adn_head_loss_p.argtypes = [c_int, p, p, p, p, p, p, p, i64, i64, p, i64, p]
+  lib.adn_dense_fwd_p_group.argtypes = [POINTER(FwdOp), c_int, i64, p]
+  lib.adn_dense_bwd_p_group.argtypes = [POINTER(BwdOp), c_int, i64, p]
   lib.adn_opt_step_p.argtypes = [c_int, POINTER(p), POINTER(p), POINTER(p), POINTER(p), POINTER(i64), c_int,
                                  POINTER(f32), p, POINTER(p), POINTER(i64), p]
   for name in EXPORTS:

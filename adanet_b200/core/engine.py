@@ -199,6 +199,14 @@ class DenseNet:
                                             torch.cuda.current_stream(self.device).cuda_stream), "adn_planes_merge")
     return out
 
+  def fwd_op(self, i: int, xp: torch.Tensor) -> "_lib.FwdOp":
+    """Layer i as an adn_fwd_op (plane path): hidden layers write planes, the logits layer dense fp32."""
+    last = i == len(self.ws) - 1
+    src = xp if i == 0 else self.hp[i - 1]
+    return _lib.FwdOp(src.data_ptr(), self.wps[i].data_ptr(), self.bs[i].data_ptr(),
+                      None if last else self.hp[i].data_ptr(), self.acts[i].data_ptr() if last else None,
+                      self.dims[i], self.dims[i + 1], _lib.ACT_NONE if last else _lib.ACT_RELU, 0)
+
   def forward(self, lib, x: torch.Tensor, sp: int, xp: Optional[torch.Tensor] = None):
     """x: dense fp32 minibatch; xp: its split planes (required on the plane path)."""
     n = len(self.ws)
@@ -262,6 +270,11 @@ class CandidatePlan:
       self.dz = [torch.empty((batch, hid), **f32) for _ in range(2)] if hid else []
       ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_WS, batch, dims[i], dims[i + 1]) for i in range(len(dims) - 1))
     n_members = len(frozen) + 1
+    if self.planes:
+      self.bwd_ws_bytes = ws_bytes
+      self.bwd_ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
+      self.head_ws_bytes = _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, n_members)
+      self.head_ws = torch.empty((self.head_ws_bytes,), dtype=torch.uint8, device=device)
     ws_bytes = max(ws_bytes, _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, n_members))
     self.workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
     self.ws_bytes = ws_bytes
@@ -364,6 +377,53 @@ class CandidatePlan:
       self.ens_opt.apply(lib, self._ens_grads, sp)
     self.sub_opt.apply(lib, self._grads, sp)
 
+  # ---- plane path, wave-synchronous schedule (IterationPlan._enqueue_waves) ----
+  def enqueue_sub_loss(self, labels, labels_f, sp: int):
+    """step 3 after the forward waves: subnetwork loss, dlogits (dense + planes) and db of the logits layer."""
+    lab = labels.data_ptr() if labels is not None else None
+    labf = labels_f.data_ptr() if labels_f is not None else None
+    _lib.check(self.lib.adn_head_loss_p(self.head, self.net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
+                                        self.dlogits.data_ptr(), self.dzp_out.data_ptr(),
+                                        self.dbs[len(self.net.ws) - 1].data_ptr(), self.batch, self.C,
+                                        self.workspace.data_ptr(), self.ws_bytes, sp), "adn_head_loss_p")
+
+  def enqueue_ensemble(self, labels, labels_f, step_dev, sp: int):
+    """steps 6-12: ensemble head on pre-update values, EMA, trace (own small workspace: runs beside the
+    backward waves)."""
+    lib, B, C = self.lib, self.batch, self.C
+    lab = labels.data_ptr() if labels is not None else None
+    labf = labels_f.data_ptr() if labels_f is not None else None
+    train_ens = self.ens_opt is not None
+    _lib.check(lib.adn_ensemble_head(
+        self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
+        self._gammas, self.reg_is_zero, self.reg_multiplier, lab, labf, self.out3.data_ptr(),
+        self.d_mix_w.data_ptr() if train_ens else None,
+        self.d_bias.data_ptr() if (train_ens and self.ens.use_bias) else None,
+        None, None, B, C, self.head_ws.data_ptr(), self.head_ws_bytes, sp), "adn_ensemble_head")
+    _lib.check(lib.adn_ema_update(self.ema_state.data_ptr(), self.out3.data_ptr() + 8, self.decay, sp),
+               "adn_ema_update")
+    _lib.check(lib.adn_record_scalars(self._trace_src, 4, self.trace.data_ptr(), 4, step_dev.data_ptr(),
+                                      self.trace_capacity, sp), "adn_record_scalars")
+    if train_ens:
+      self.ens_opt.apply(lib, self._ens_grads, sp)
+
+  def bwd_op(self, k: int, xp: torch.Tensor) -> "_lib.BwdOp":
+    """k-th backward wave = layer n-1-k: dW_i, planes of dZ_{i-1} (ReLU mask = sign bits of h_{i-1}) and
+    db_{i-1} = colsum(dZ_{i-1})."""
+    net, n = self.net, len(self.net.ws)
+    i = n - 1 - k
+    xin = xp if i == 0 else net.hp[i - 1]
+    dzp = self.dzp_out if k == 0 else self.dzp[(i + 1) % 2]
+    dxp = self.dzp[i % 2] if i > 0 else None
+    ws = self.bwd_ws            # waves are serialised on the main stream
+    return _lib.BwdOp(xin.data_ptr(), net.wps[i].data_ptr(), dzp.data_ptr(),
+                      dxp.data_ptr() if dxp is not None else None, None,
+                      self.dbs[i - 1].data_ptr() if i > 0 else None, self.dws[i].data_ptr(), net.dims[i],
+                      net.dims[i + 1], 1 if i > 0 else 0, 0, ws.data_ptr(), self.bwd_ws_bytes)
+
+  def enqueue_sub_update(self, sp: int):
+    self.sub_opt.apply(self.lib, self._grads, sp)
+
   def enqueue_eval(self, x, labels, labels_f, ens_out: Optional[torch.Tensor], sp: int,
                    xp: Optional[torch.Tensor] = None):
     """Forward-only: subnetwork logits + ensemble logits/loss (evaluate / predict)."""
@@ -424,7 +484,46 @@ class IterationPlan:
       self.labels_f.copy_(y.reshape(self.batch, self.C), non_blocking=True)
 
   # -- one step --------------------------------------------------------------
+  def _enqueue_waves(self):
+    """Plane path: layer waves across ALL subnetworks of the GPU (frozen members and candidates) as grouped
+    launches on the main stream; the per-candidate small kernels (losses, ensemble heads, EMA, optimizer)
+    run on the candidates' side streams beside them."""
+    lib = self.lib
+    main = torch.cuda.current_stream(self.device)
+    sp = main.cuda_stream
+    self._split_x(sp)
+    nets = list(self.frozen) + [c.net for c in self.candidates]
+    for w in range(max(len(n.ws) for n in nets)):
+      ops = [n.fwd_op(w, self.xp) for n in nets if w < len(n.ws)]
+      arr = (_lib.FwdOp * len(ops))(*ops)
+      _lib.check(lib.adn_dense_fwd_p_group(arr, len(ops), self.batch, sp), "adn_dense_fwd_p_group")
+    side = self.streams if self.multi_stream else [main] * len(self.candidates)
+    for c, s in zip(self.candidates, side):
+      if s is not main:
+        s.wait_stream(main)
+      with torch.cuda.stream(s):
+        c.enqueue_sub_loss(self.labels, self.labels_f, s.cuda_stream)
+        if s is not main:
+          ev = torch.cuda.Event()
+          ev.record(s)
+          main.wait_event(ev)          # the backward waves need every candidate's dlogits planes
+        c.enqueue_ensemble(self.labels, self.labels_f, self.step_dev, s.cuda_stream)
+    for k in range(max(len(c.net.ws) for c in self.candidates)):
+      ops = [c.bwd_op(k, self.xp) for c in self.candidates if k < len(c.net.ws)]
+      arr = (_lib.BwdOp * len(ops))(*ops)
+      _lib.check(lib.adn_dense_bwd_p_group(arr, len(ops), self.batch, sp), "adn_dense_bwd_p_group")
+    for c, s in zip(self.candidates, side):
+      if s is not main:
+        s.wait_stream(main)
+      with torch.cuda.stream(s):
+        c.enqueue_sub_update(s.cuda_stream)
+    for s in self.streams if self.multi_stream else []:
+      main.wait_stream(s)
+    _lib.check(lib.adn_counter_add(self.step_dev.data_ptr(), 1, sp), "adn_counter_add")
+
   def _enqueue(self):
+    if self.xp is not None and self.candidates:
+      return self._enqueue_waves()
     lib = self.lib
     main = torch.cuda.current_stream(self.device)
     sp = main.cuda_stream

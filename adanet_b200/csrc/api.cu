@@ -194,3 +194,36 @@ extern "C" int adn_colsum(const float* x, int64_t rows, int64_t cols, float* out
     return fail(ADN_ERR_WORKSPACE, "adn_colsum: workspace too small");
   return simt::colsum(x, out, rows, cols, reinterpret_cast<float*>(workspace), as_stream(stream));
 }
+
+extern "C" int adn_dense_fwd_p_group(const adn_fwd_op* ops, int n, int64_t batch, void* stream) {
+  if (n < 0 || (n > 0 && !ops)) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p_group: bad ops");
+  if (n > 256) return fail(ADN_ERR_UNSUPPORTED, "adn_dense_fwd_p_group: n %d > 256", n);
+  pl::FwdOp o[256];
+  for (int i = 0; i < n; ++i) {
+    if (!ops[i].xp || !ops[i].wp) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p_group: op %d: null pointer", i);
+    if ((ops[i].yp == nullptr) == (ops[i].y == nullptr))
+      return fail(ADN_ERR_INVALID, "adn_dense_fwd_p_group: op %d: exactly one of yp / y", i);
+    if (bad_shape(batch, ops[i].in, ops[i].out)) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p_group: op %d: bad shape", i);
+    if (ops[i].act != ADN_ACT_NONE && ops[i].act != ADN_ACT_RELU)
+      return fail(ADN_ERR_INVALID, "adn_dense_fwd_p_group: op %d: bad act %d", i, ops[i].act);
+    o[i] = pl::FwdOp{ops[i].xp, ops[i].wp, ops[i].bias, ops[i].yp, ops[i].y, ops[i].in, ops[i].out, ops[i].act};
+  }
+  return pl::dense_fwd_group(o, n, batch, as_stream(stream));
+}
+
+extern "C" int adn_dense_bwd_p_group(const adn_bwd_op* ops, int n, int64_t batch, void* stream) {
+  if (n < 0 || (n > 0 && !ops)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: bad ops");
+  if (n > 256) return fail(ADN_ERR_UNSUPPORTED, "adn_dense_bwd_p_group: n %d > 256", n);
+  pl::BwdOp o[256];
+  for (int i = 0; i < n; ++i) {
+    const adn_bwd_op& p = ops[i];
+    if (!p.xp || !p.dzp || !p.workspace) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: null pointer", i);
+    if ((p.dxp || p.dx) && !p.wp) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: wp required for dx", i);
+    if (p.dxp && p.dx) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: at most one of dxp / dx", i);
+    if (p.dx_colsum && !(p.dxp || p.dx)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: dx_colsum needs dx", i);
+    if (bad_shape(batch, p.in, p.out)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: bad shape", i);
+    o[i] = pl::BwdOp{p.xp, p.wp, p.dzp, p.dxp, p.dx, p.dx_colsum, p.dw, p.in, p.out, p.x_relu_mask, p.workspace,
+                     p.workspace_bytes};
+  }
+  return pl::dense_bwd_group(o, n, batch, as_stream(stream));
+}

@@ -1,4 +1,6 @@
 // Launchers for the CUDA-core fp32 dense path.  See dense_simt.cuh.
+#include <algorithm>
+
 #include "dense_simt.cuh"
 
 namespace adn {
@@ -54,6 +56,82 @@ int colsum(const float* dz, float* db, int64_t rows, int64_t N, float* part, cud
   colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, part, (int)rows, (int)N, rps);
   ADN_CHECK_LAUNCH("colsum");
   return reduce_partials(part, db, N, S2, N, st);
+}
+
+// ---- grouped variants: one launch for the same reduction of several subnetworks (blockIdx.z = job) ----
+static constexpr int kMaxJobs = 16;
+struct ReduceJobs { ReduceJob j[kMaxJobs]; };
+struct ColsumJobs { ColsumJob j[kMaxJobs]; int rps[kMaxJobs]; };
+
+static __global__ void reduce_partials_group_kernel(const __grid_constant__ ReduceJobs jobs) {
+  const ReduceJob& jb = jobs.j[blockIdx.z];
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= jb.n) return;
+  float acc = 0.f;
+  for (int s = 0; s < jb.S; ++s) acc += jb.part[(size_t)s * jb.stride + i];
+  jb.out[i] = acc;
+}
+
+static __global__ void __launch_bounds__(256)
+colsum_partial_group_kernel(const __grid_constant__ ColsumJobs jobs) {
+  __shared__ float sm[8][33];
+  const ColsumJob& jb = jobs.j[blockIdx.z];
+  const int rows_per_slice = jobs.rps[blockIdx.z];
+  const int N = (int)jb.cols, rows = (int)jb.rows;
+  const int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
+  const int n = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_slice;
+  if (r0 >= rows || blockIdx.x * 32 >= N) return;       // uniform per block
+  const int r1 = min(rows, r0 + rows_per_slice);
+  float acc = 0.f;
+  if (n < N)
+    for (int r = r0 + ry; r < r1; r += 8) acc += jb.x[(size_t)r * N + n];
+  sm[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    jb.part[(size_t)blockIdx.y * N + n] = t;
+  }
+}
+
+int reduce_partials_group(const ReduceJob* jobs, int n, cudaStream_t st) {
+  for (int i0 = 0; i0 < n; i0 += kMaxJobs) {
+    const int m = std::min(kMaxJobs, n - i0);
+    ReduceJobs rj{};
+    int64_t max_n = 0;
+    for (int i = 0; i < m; ++i) { rj.j[i] = jobs[i0 + i]; max_n = std::max(max_n, jobs[i0 + i].n); }
+    dim3 grid((unsigned)ceil_div(max_n, 256), 1, (unsigned)m);
+    reduce_partials_group_kernel<<<grid, 256, 0, st>>>(rj);
+    ADN_CHECK_LAUNCH("reduce_partials_group");
+  }
+  return ADN_OK;
+}
+
+int colsum_group(const ColsumJob* jobs, int n, cudaStream_t st) {
+  for (int i0 = 0; i0 < n; i0 += kMaxJobs) {
+    const int m = std::min(kMaxJobs, n - i0);
+    ColsumJobs cj{};
+    ReduceJobs rj{};
+    int64_t max_cols = 0;
+    int max_s2 = 0;
+    for (int i = 0; i < m; ++i) {
+      cj.j[i] = jobs[i0 + i];
+      cj.rps[i] = colsum_slice_rows(jobs[i0 + i].rows);
+      const int s2 = (int)ceil_div(jobs[i0 + i].rows, cj.rps[i]);
+      max_s2 = std::max(max_s2, s2);
+      max_cols = std::max(max_cols, jobs[i0 + i].cols);
+      rj.j[i] = ReduceJob{jobs[i0 + i].part, jobs[i0 + i].out, jobs[i0 + i].cols, s2, jobs[i0 + i].cols};
+    }
+    dim3 grid((unsigned)ceil_div(max_cols, 32), (unsigned)max_s2, (unsigned)m);
+    colsum_partial_group_kernel<<<grid, 256, 0, st>>>(cj);
+    ADN_CHECK_LAUNCH("colsum_group");
+    dim3 grid2((unsigned)ceil_div(max_cols, 256), 1, (unsigned)m);
+    reduce_partials_group_kernel<<<grid2, 256, 0, st>>>(rj);
+    ADN_CHECK_LAUNCH("colsum_group reduce");
+  }
+  return ADN_OK;
 }
 
 // Tile configs: BIG for wide N, SKINNY for N <= 32 (logits layers).

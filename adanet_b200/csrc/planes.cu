@@ -36,8 +36,11 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "dense_simt.cuh"
 #include "planes.cuh"
@@ -68,6 +71,7 @@ struct GemmParams {
   int total_kb;          // k-blocks of 32 over the whole K
   int kb_per_split;
   int a_mn, b_mn;        // operand majorness (0 = K-major box, 1 = MN-major box)
+  int out_planes;        // 1: result written as split planes (out / out_lo / out_bits), 0: dense fp32
   // output: dense row-major (ldc) / split-K partial [split][M][N], or planes
   float* out;            // dense base | hi plane base
   float* out_lo;         // lo plane base (OUT_PLANES)
@@ -226,9 +230,9 @@ __device__ __forceinline__ Item decode_item(const GemmParams& g, int item) {
 // transposes through `stage` (16 B chunks XOR-swizzled by row: conflict-free both ways) and writes with
 // lane = 4-column group of 4 rows, so every global access covers whole 128 B lines (planes: one contiguous
 // 512 B run per instruction).  Shared by the 1-CTA and the CTA-pair kernels.
-template <int EPI, int OUT_PLANES>
-__device__ __forceinline__ void emit_slice(const GemmParams& g, float* a, uint32_t mwq, float* stage, int lane,
-                                           int mrow0, int cbase, int rows_ok, float* dense, bool dense_vec) {
+template <int EPI>
+__device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_PLANES, float* a, uint32_t mwq, float* stage,
+                                           int lane, int mrow0, int cbase, int rows_ok, float* dense, bool dense_vec) {
   const int cc = lane & 7;                 // 16 B chunk (4 columns) this lane owns after the transpose
   const int c4 = cc * 4;
   const int rsub = lane >> 3;
@@ -337,13 +341,36 @@ __device__ __forceinline__ void emit_slice(const GemmParams& g, float* a, uint32
 }
 
 // ---------------------------------------------------------------------------------
-// GEMM kernel
+// GEMM kernel (grouped): one persistent launch runs the tiles of up to MAX_GROUP independent GEMMs of
+// the same epilogue kind -- the same layer of every candidate subnetwork of an AdaNet iteration -- so the
+// launch, prologue and pipeline fill/drain are paid once per layer wave instead of once per candidate,
+// and the short-K tiles of narrow candidates hide behind the long-K tiles of wide ones.
+// Work items are numbered problem after problem; CTA c takes items c, c + grid, ... (every CTA gets the
+// same share of every problem).  A group of one is the plain single-GEMM call.
 // ---------------------------------------------------------------------------------
-template <int EPI, int OUT_PLANES>
+static constexpr int MAX_GROUP = 8;
+
+struct alignas(64) Problem {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  GemmParams g;
+  int item0;             // first work item of this problem
+  int pad_[3];
+};
+struct alignas(64) Group {
+  Problem p[MAX_GROUP];
+  int n;                 // problems
+  int total_items;
+};
+
+// advance `cur` to the problem that owns `item` (items are visited in increasing order)
+__device__ __forceinline__ int find_problem(const Group& grp, int cur, int item) {
+  while (cur + 1 < grp.n && item >= grp.p[cur + 1].item0) ++cur;
+  return cur;
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const GemmParams g) {
+pl_gemm_kernel(const __grid_constant__ Group grp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();   // SWIZZLE_128B tiles must sit on 1024 B boundaries
@@ -358,13 +385,13 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int n_items = g.tiles_m * g.tiles_n * g.splits;
+  const int n_items = grp.total_items;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a_hi);
-    tma_prefetch_desc(&map_a_lo);
-    tma_prefetch_desc(&map_b_hi);
-    tma_prefetch_desc(&map_b_lo);
+  if (warp == 0 && lane < grp.n) {       // every problem's descriptors: each CTA visits every problem
+    tma_prefetch_desc(&grp.p[lane].a_hi);
+    tma_prefetch_desc(&grp.p[lane].a_lo);
+    tma_prefetch_desc(&grp.p[lane].b_hi);
+    tma_prefetch_desc(&grp.p[lane].b_lo);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -394,9 +421,13 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      int cur = 0;
       const uint32_t smem0 = smem_u32(smem);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const Item it = decode_item(g, item);
+        cur = find_problem(grp, cur, item);
+        const Problem& pr = grp.p[cur];
+        const GemmParams& g = pr.g;
+        const Item it = decode_item(g, item - pr.item0);
         for (int kb = 0; kb < it.nkb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full_bar[s]);
@@ -406,10 +437,10 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           // K-major box {32, 128 rows, 1 kb} at (0, row0, kc); MN-major box {32, 32 rows, 4 kb} at (0, kc*32, mn0/32)
           const int a1 = g.a_mn ? kc * BK : it.m0, a2 = g.a_mn ? (it.m0 >> 5) : kc;
           const int b1 = g.b_mn ? kc * BK : it.n0, b2 = g.b_mn ? (it.n0 >> 5) : kc;
-          tma_load_3d(&map_a_hi, fb, base + 0 * TILE_BYTES, 0, a1, a2);
-          tma_load_3d(&map_a_lo, fb, base + 1 * TILE_BYTES, 0, a1, a2);
-          tma_load_3d(&map_b_hi, fb, base + 2 * TILE_BYTES, 0, b1, b2);
-          tma_load_3d(&map_b_lo, fb, base + 3 * TILE_BYTES, 0, b1, b2);
+          tma_load_3d(&pr.a_hi, fb, base + 0 * TILE_BYTES, 0, a1, a2);
+          tma_load_3d(&pr.a_lo, fb, base + 1 * TILE_BYTES, 0, a1, a2);
+          tma_load_3d(&pr.b_hi, fb, base + 2 * TILE_BYTES, 0, b1, b2);
+          tma_load_3d(&pr.b_lo, fb, base + 3 * TILE_BYTES, 0, b1, b2);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -420,16 +451,19 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // elect.sync, so every operand is warp-uniform.  A 128x128x8 TF32 MMA retires every 64 clk: the
     // issue loop keeps ring counters incremental and builds descriptors from 32-bit halves.
     {
-      const uint32_t idesc = make_idesc(BM, BN, g.a_mn, g.b_mn);
-      const uint32_t dah = desc_hi_word(g.a_mn), dbh = desc_hi_word(g.b_mn);
       const uint32_t smem0 = smem_u32(smem);
-      const uint32_t a_lo0 = desc_lo_word(smem0, g.a_mn);
-      const uint32_t b_lo0 = desc_lo_word(smem0 + 2 * TILE_BYTES, g.b_mn);
-      const uint32_t a_step = g.a_mn ? (1024u >> 4) : (32u >> 4);   // address-field advance per K=8 MMA
-      const uint32_t b_step = g.b_mn ? (1024u >> 4) : (32u >> 4);
       uint32_t s = 0, ph = 0, gchunk = 0, tile_i = 0;
+      int cur = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
-        const Item it = decode_item(g, item);
+        cur = find_problem(grp, cur, item);
+        const GemmParams& g = grp.p[cur].g;
+        const Item it = decode_item(g, item - grp.p[cur].item0);
+        const uint32_t idesc = make_idesc(BM, BN, g.a_mn, g.b_mn);
+        const uint32_t dah = desc_hi_word(g.a_mn), dbh = desc_hi_word(g.b_mn);
+        const uint32_t a_lo0 = desc_lo_word(smem0, g.a_mn);
+        const uint32_t b_lo0 = desc_lo_word(smem0 + 2 * TILE_BYTES, g.b_mn);
+        const uint32_t a_step = g.a_mn ? (1024u >> 4) : (32u >> 4);   // address-field advance per K=8 MMA
+        const uint32_t b_step = g.b_mn ? (1024u >> 4) : (32u >> 4);
         const uint32_t acc_s = tmem_base + 256 + (tile_i & 1) * 128;
         mbar_wait(smem_u32(&s_empty[tile_i & 1]), ((tile_i >> 1) & 1) ^ 1);   // small-term accumulator free
         tc_fence_after();
@@ -473,8 +507,11 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const uint32_t col_base = (uint32_t)(half * EPI_COLS);
     float* stage = epi_stage + (warp - 2) * EPI_STAGE_FLOATS;
     uint32_t gchunk = 0, tile_i = 0;
+    int cur = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
-      const Item it = decode_item(g, item);
+      cur = find_problem(grp, cur, item);
+      const GemmParams& g = grp.p[cur].g;
+      const Item it = decode_item(g, item - grp.p[cur].item0);
       const int mrow0 = it.m0 + quad * 32;
       const int ncol0 = it.n0 + (int)col_base;        // first output column of this warp
       const int my_row = mrow0 + lane;
@@ -531,11 +568,12 @@ pl_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       // lines (planes: one contiguous 512 B run per instruction).
       float* dense = g.out;
       if (EPI == EPI_PARTIAL) dense += (size_t)it.split * g.M * g.N;
-      const bool dense_vec = !OUT_PLANES && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+      const bool out_planes = g.out_planes != 0;
+      const bool dense_vec = !out_planes && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
       const int rows_ok = min(32, g.M - mrow0);          // warp-uniform; <= 0: nothing to write
 #pragma unroll
       for (int q = 0; q < 2; ++q)
-        emit_slice<EPI, OUT_PLANES>(g, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
+        emit_slice<EPI>(g, out_planes, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
     }
   }
   tc_fence_before();
@@ -872,7 +910,7 @@ pl_gemm2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int rows_ok = min(32, g.M - mrow0);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          emit_slice<EPI, OUT_PLANES>(g, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
+          emit_slice<EPI>(g, OUT_PLANES != 0, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
       }
     }
   }
@@ -965,11 +1003,9 @@ int init() {
     }
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
     bool ok = true;
-#define ADN_PL_ATTR(E, P) \
-  ok = ok && (cudaFuncSetAttribute(pl_gemm_kernel<E, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess)
-    ADN_PL_ATTR(EPI_BIAS_ACT, 0); ADN_PL_ATTR(EPI_BIAS_ACT, 1);
-    ADN_PL_ATTR(EPI_MASK, 0); ADN_PL_ATTR(EPI_MASK, 1);
-    ADN_PL_ATTR(EPI_PARTIAL, 0);
+#define ADN_PL_ATTR(E) \
+  ok = ok && (cudaFuncSetAttribute(pl_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess)
+    ADN_PL_ATTR(EPI_BIAS_ACT); ADN_PL_ATTR(EPI_MASK); ADN_PL_ATTR(EPI_PARTIAL);
 #undef ADN_PL_ATTR
 #define ADN_PL_ATTR2(E, P) \
   ok = ok && (cudaFuncSetAttribute(pl_gemm2_kernel<E, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess)
@@ -1024,44 +1060,85 @@ static int make_map(CUtensorMap* map, const float* plane, int64_t rows, int64_t 
   return ADN_OK;
 }
 
-// Measured on B200 (profiles/r1d_pair_vs_single.txt): under the ~1 kW power cap both kernels sit at the same
-// ~0.85-0.9 of the clock-limited TF32 rate on the big layers, and the pair kernel loses on small problems, so it
-// is only taken for large ones.  ADN_PL_PAIR=0/1 forces the choice (tests exercise both).
-static bool use_pair(int M, int N) {
-  static const int env = getenv("ADN_PL_PAIR") ? atoi(getenv("ADN_PL_PAIR")) : -1;
-  if (env == 0) return false;
-  if (env == 1) return true;
-  return M >= 2048 && N >= 512;
+// Measured on B200 (profiles/r1d_pair_vs_single.txt): under the ~1 kW power cap the CTA-pair kernel and the
+// single-CTA kernel sit at the same ~0.85-0.9 of the clock-limited TF32 rate on the big layers and the pair
+// kernel loses on small problems, so the grouped single-CTA kernel is the default; ADN_PL_PAIR=1 routes every
+// GEMM through the pair kernel instead (tests check both are bit-identical).
+static bool use_pair() {
+  static const int env = getenv("ADN_PL_PAIR") ? atoi(getenv("ADN_PL_PAIR")) : 0;
+  return env == 1;
 }
 
-template <int EPI, int OUT_PLANES>
-static int launch_gemm(const Operand& a, const Operand& b, GemmParams g, cudaStream_t st, const char* what) {
-  if ((reinterpret_cast<uintptr_t>(a.hi) | reinterpret_cast<uintptr_t>(a.lo) | reinterpret_cast<uintptr_t>(b.hi) |
-       reinterpret_cast<uintptr_t>(b.lo)) & 127)
+// one GEMM of a group: operands + epilogue description (tiles / item numbering are filled at launch)
+struct GemmDesc {
+  Operand a, b;
+  GemmParams g;
+};
+
+static int encode_maps(const GemmDesc& d, CUtensorMap* a_hi, CUtensorMap* a_lo, CUtensorMap* b_hi, CUtensorMap* b_lo,
+                       const char* what) {
+  if ((reinterpret_cast<uintptr_t>(d.a.hi) | reinterpret_cast<uintptr_t>(d.a.lo) | reinterpret_cast<uintptr_t>(d.b.hi) |
+       reinterpret_cast<uintptr_t>(d.b.lo)) & 127)
     return fail(ADN_ERR_INVALID, "%s: plane buffers must be 256 B aligned", what);
+  int rc;
+  if ((rc = make_map(a_hi, d.a.hi, d.a.rows, d.a.nkb, d.a.mn_major))) return rc;
+  if ((rc = make_map(a_lo, d.a.lo, d.a.rows, d.a.nkb, d.a.mn_major))) return rc;
+  if ((rc = make_map(b_hi, d.b.hi, d.b.rows, d.b.nkb, d.b.mn_major))) return rc;
+  if ((rc = make_map(b_lo, d.b.lo, d.b.rows, d.b.nkb, d.b.mn_major))) return rc;
+  return ADN_OK;
+}
+
+template <int EPI>
+static int launch_pair(const GemmDesc& d, cudaStream_t st, const char* what) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map(&ma_hi, a.hi, a.rows, a.nkb, a.mn_major))) return rc;
-  if ((rc = make_map(&ma_lo, a.lo, a.rows, a.nkb, a.mn_major))) return rc;
-  if ((rc = make_map(&mb_hi, b.hi, b.rows, b.nkb, b.mn_major))) return rc;
-  if ((rc = make_map(&mb_lo, b.lo, b.rows, b.nkb, b.mn_major))) return rc;
-  g.a_mn = a.mn_major;
-  g.b_mn = b.mn_major;
-  if (use_pair(g.M, g.N)) {
-    // CTA-pair kernel: 256 x 256 tiles, one per pair of SMs
-    g.tiles_m = (int)ceil_div(g.M, BM2);
-    g.tiles_n = (int)ceil_div(g.N, BN2);
-    const int items = g.tiles_m * g.tiles_n * g.splits;
-    const int grid = 2 * std::min(items, sm_count() / 2);
-    pl_gemm2_kernel<EPI, OUT_PLANES><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
-  } else {
-    g.tiles_m = (int)ceil_div(g.M, BM);
-    g.tiles_n = (int)ceil_div(g.N, BN);
-    const int items = g.tiles_m * g.tiles_n * g.splits;
-    const int grid = std::min(items, sm_count());
-    pl_gemm_kernel<EPI, OUT_PLANES><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
-  }
+  if ((rc = encode_maps(d, &ma_hi, &ma_lo, &mb_hi, &mb_lo, what))) return rc;
+  GemmParams g = d.g;
+  g.a_mn = d.a.mn_major;
+  g.b_mn = d.b.mn_major;
+  g.tiles_m = (int)ceil_div(g.M, BM2);
+  g.tiles_n = (int)ceil_div(g.N, BN2);
+  const int items = g.tiles_m * g.tiles_n * g.splits;
+  const int grid = 2 * std::min(items, sm_count() / 2);
+  if (g.out_planes) pl_gemm2_kernel<EPI, 1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
+  else pl_gemm2_kernel<EPI, 0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
   ADN_CHECK_LAUNCH(what);
+  return ADN_OK;
+}
+
+// n independent GEMMs of the same epilogue kind -> ceil(n / MAX_GROUP) persistent launches
+template <int EPI>
+static int launch_group(const GemmDesc* d, int n, cudaStream_t st, const char* what) {
+  if (use_pair()) {
+    for (int i = 0; i < n; ++i) {
+      int rc = launch_pair<EPI>(d[i], st, what);
+      if (rc) return rc;
+    }
+    return ADN_OK;
+  }
+  for (int i0 = 0; i0 < n; i0 += MAX_GROUP) {
+    const int m = std::min(MAX_GROUP, n - i0);
+    Group grp;
+    memset(&grp, 0, sizeof(grp));
+    int items = 0;
+    for (int i = 0; i < m; ++i) {
+      Problem& pr = grp.p[i];
+      int rc = encode_maps(d[i0 + i], &pr.a_hi, &pr.a_lo, &pr.b_hi, &pr.b_lo, what);
+      if (rc) return rc;
+      pr.g = d[i0 + i].g;
+      pr.g.a_mn = d[i0 + i].a.mn_major;
+      pr.g.b_mn = d[i0 + i].b.mn_major;
+      pr.g.tiles_m = (int)ceil_div(pr.g.M, BM);
+      pr.g.tiles_n = (int)ceil_div(pr.g.N, BN);
+      pr.item0 = items;
+      items += pr.g.tiles_m * pr.g.tiles_n * pr.g.splits;
+    }
+    grp.n = m;
+    grp.total_items = items;
+    const int grid = std::min(items, sm_count());
+    pl_gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(grp);
+    ADN_CHECK_LAUNCH(what);
+  }
   return ADN_OK;
 }
 
@@ -1092,21 +1169,6 @@ static int max_dw_splits(int64_t in, int64_t out) {
   return (int)s;
 }
 
-// pick S minimising (persistent rounds) x (k-blocks per item) + a per-split reduction cost
-static int dw_splits(int64_t tiles, int64_t kblocks, int max_s, int workers) {
-  const int sms = workers;
-  int best = 1;
-  double best_t = 1e30;
-  for (int s = 1; s <= max_s && s <= kblocks; ++s) {
-    const int64_t kps = ceil_div(kblocks, s);
-    const int64_t s_eff = ceil_div(kblocks, kps);
-    const int64_t rounds = ceil_div(tiles * s_eff, sms);
-    const double t = (double)rounds * ((double)kps + 6.0) + 0.75 * (double)s_eff;
-    if (t < best_t) { best_t = t; best = (int)s_eff; }
-  }
-  return best;
-}
-
 int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
   int64_t b = align_up((int64_t)max_dw_splits(in, out) * in * out * (int64_t)sizeof(float), 256);   // dW split-K partials
   b += align_up(ceil_div(batch, 32) * in * (int64_t)sizeof(float), 256);                             // dx column sums per 32 rows
@@ -1114,75 +1176,143 @@ int64_t dense_bwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
   return b + 512;
 }
 
+int dense_fwd_group(const FwdOp* ops, int n, int64_t batch, cudaStream_t st) {
+  if (n <= 0) return ADN_OK;
+  std::vector<GemmDesc> d((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const FwdOp& o = ops[i];
+    GemmDesc& e = d[(size_t)i];
+    e.a = operand(o.xp, batch, o.in, 0);       // A = x  [M=batch, K=in]  K-major
+    e.b = operand(o.wp, o.in, o.out, 1);       // B = w  [K=in, N=out]    MN-major
+    GemmParams g{};
+    g.M = (int)batch; g.N = (int)o.out;
+    g.total_kb = (int)ceil_div(o.in, BK); g.kb_per_split = g.total_kb; g.splits = 1;
+    g.bias = o.bias; g.act = o.act;
+    if (o.yp) {
+      g.out_planes = 1;
+      g.out = o.yp; g.out_lo = o.yp + plane_floats(batch, o.out); g.out_nkb = (int)ceil_div(o.out, BK);
+      g.out_bits = bits_of(o.yp, batch, o.out);
+    } else {
+      g.out = o.y; g.ldc = (int)o.out;
+    }
+    e.g = g;
+  }
+  return launch_group<EPI_BIAS_ACT>(d.data(), n, st, "pl dense_fwd gemm");
+}
+
+int dense_bwd_group(const BwdOp* ops, int n, int64_t batch, cudaStream_t st) {
+  if (n <= 0) return ADN_OK;
+  const int workers = use_pair() ? sm_count() / 2 : sm_count();
+  const int tm = use_pair() ? BM2 : BM, tn = use_pair() ? BN2 : BN;
+  struct Carve { float* part; float* cspart; float* cspart2; int splits; };
+  std::vector<Carve> cv((size_t)n);
+  std::vector<GemmDesc> dwd, dxd;
+  // Split-K over the batch for the dW GEMMs of the group.  Items of one launch are dealt round-robin to the
+  // CTAs, so they should all cost the same: every problem uses the same k-blocks-per-item `kps`, chosen to
+  // minimise (rounds of the whole group) x (kps + per-item overhead) + reduction cost, subject to each
+  // problem's partial-buffer bound.
+  const int64_t kb_b = ceil_div(batch, BK);
+  int64_t best_kps = kb_b;
+  {
+    double best_t = 1e30;
+    for (int s0 = 1; s0 <= MAX_SPLITS && s0 <= kb_b; ++s0) {
+      const int64_t kps = ceil_div(kb_b, s0);
+      int64_t items = 0, max_s_used = 1;
+      for (int i = 0; i < n; ++i) {
+        if (!ops[i].dw) continue;
+        int64_t k_i = std::max<int64_t>(kps, ceil_div(kb_b, max_dw_splits(ops[i].in, ops[i].out)));
+        const int64_t s_i = ceil_div(kb_b, k_i);
+        items += ceil_div(ops[i].in, tm) * ceil_div(ops[i].out, tn) * s_i;
+        max_s_used = std::max(max_s_used, s_i);
+      }
+      if (items == 0) break;
+      const double t = (double)ceil_div(items, workers) * ((double)kps + 6.0) + 0.75 * (double)max_s_used;
+      if (t < best_t) { best_t = t; best_kps = kps; }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    const BwdOp& o = ops[i];
+    if (!o.ws || o.ws_bytes < dense_bwd_workspace_bytes(batch, o.in, o.out))
+      return fail(ADN_ERR_WORKSPACE, "pl dense_bwd: op %d workspace %lld < %lld bytes", i, (long long)o.ws_bytes,
+                  (long long)dense_bwd_workspace_bytes(batch, o.in, o.out));
+    char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(o.ws) + 255) & ~(uintptr_t)255);
+    const int max_s = max_dw_splits(o.in, o.out);
+    Carve& c = cv[(size_t)i];
+    c.part = reinterpret_cast<float*>(p);
+    p += align_up((int64_t)max_s * o.in * o.out * (int64_t)sizeof(float), 256);
+    c.cspart = reinterpret_cast<float*>(p);
+    p += align_up(ceil_div(batch, 32) * o.in * (int64_t)sizeof(float), 256);
+    c.cspart2 = reinterpret_cast<float*>(p);
+    c.splits = 1;
+    if (o.dw) {
+      // ---- dW[in,out] = X^T dZ : A = Xp MN-major (M=in), B = dZp MN-major (N=out), K = batch, split-K ----
+      GemmDesc e;
+      e.a = operand(o.xp, batch, o.in, 1);
+      e.b = operand(o.dzp, batch, o.out, 1);
+      GemmParams g{};
+      g.M = (int)o.in; g.N = (int)o.out; g.ldc = (int)o.out;
+      g.total_kb = (int)kb_b; g.kb_per_split = (int)std::max<int64_t>(best_kps, ceil_div(kb_b, max_s));
+      g.splits = (int)ceil_div(kb_b, g.kb_per_split);
+      g.out = (g.splits == 1) ? o.dw : c.part;
+      c.splits = g.splits;
+      e.g = g;
+      dwd.push_back(e);
+    }
+    if (o.dxp || o.dx) {
+      // ---- dX[batch,in] = dZ W^T : A = dZp K-major (K=out), B = Wp K-major (N=in, K=out); ReLU mask = sign bits of X ----
+      GemmDesc e;
+      e.a = operand(o.dzp, batch, o.out, 0);
+      e.b = operand(o.wp, o.in, o.out, 0);
+      GemmParams g{};
+      g.M = (int)batch; g.N = (int)o.in;
+      g.total_kb = (int)ceil_div(o.out, BK); g.kb_per_split = g.total_kb; g.splits = 1;
+      g.mask_bits = o.x_relu_mask ? bits_of(o.xp, batch, o.in) : nullptr;
+      g.out_nkb = (int)ceil_div(o.in, BK);
+      g.colsum_part = o.dx_colsum ? c.cspart : nullptr;
+      g.colsum_ld = (int)o.in;
+      if (o.dxp) {
+        g.out_planes = 1;
+        g.out = o.dxp; g.out_lo = o.dxp + plane_floats(batch, o.in);
+      } else {
+        g.out = o.dx; g.ldc = (int)o.in;
+      }
+      e.g = g;
+      dxd.push_back(e);
+    }
+  }
+  int rc;
+  if (!dwd.empty()) {
+    if ((rc = launch_group<EPI_PARTIAL>(dwd.data(), (int)dwd.size(), st, "pl dW gemm"))) return rc;
+    std::vector<simt::ReduceJob> jobs;
+    for (int i = 0; i < n; ++i)
+      if (ops[i].dw && cv[(size_t)i].splits > 1)
+        jobs.push_back(simt::ReduceJob{cv[(size_t)i].part, ops[i].dw, ops[i].in * ops[i].out, cv[(size_t)i].splits,
+                                       ops[i].in * ops[i].out});
+    if ((rc = simt::reduce_partials_group(jobs.data(), (int)jobs.size(), st))) return rc;
+  }
+  if (!dxd.empty()) {
+    if ((rc = launch_group<EPI_MASK>(dxd.data(), (int)dxd.size(), st, "pl dX gemm"))) return rc;
+    // column sums of each [ceil(batch/32), in] partial matrix, fixed order
+    std::vector<simt::ColsumJob> jobs;
+    for (int i = 0; i < n; ++i)
+      if (ops[i].dx_colsum && (ops[i].dxp || ops[i].dx))
+        jobs.push_back(simt::ColsumJob{cv[(size_t)i].cspart, ops[i].dx_colsum, ceil_div(batch, 32), ops[i].in,
+                                       cv[(size_t)i].cspart2});
+    if ((rc = simt::colsum_group(jobs.data(), (int)jobs.size(), st))) return rc;
+  }
+  return ADN_OK;
+}
+
 int dense_fwd(const float* xp, const float* wp, const float* bias, float* yp, float* y, int64_t batch, int64_t in,
               int64_t out, int act, cudaStream_t st) {
-  const Operand a = operand(xp, batch, in, 0);    // A = x  [M=batch, K=in]  K-major
-  const Operand b = operand(wp, in, out, 1);      // B = w  [K=in, N=out]    MN-major
-  GemmParams g{};
-  g.M = (int)batch; g.N = (int)out;
-  g.total_kb = (int)ceil_div(in, BK); g.kb_per_split = g.total_kb; g.splits = 1;
-  g.bias = bias; g.act = act;
-  if (yp) {
-    g.out = yp; g.out_lo = yp + plane_floats(batch, out); g.out_nkb = (int)ceil_div(out, BK);
-    g.out_bits = bits_of(yp, batch, out);
-    return launch_gemm<EPI_BIAS_ACT, 1>(a, b, g, st, "pl dense_fwd gemm (planes out)");
-  }
-  g.out = y; g.ldc = (int)out;
-  return launch_gemm<EPI_BIAS_ACT, 0>(a, b, g, st, "pl dense_fwd gemm (dense out)");
+  const FwdOp op{xp, wp, bias, yp, y, in, out, act};
+  return dense_fwd_group(&op, 1, batch, st);
 }
 
 int dense_bwd(const float* xp, const float* wp, const float* dzp, float* dxp, float* dx, float* dx_colsum, float* dw,
               int64_t batch, int64_t in, int64_t out, int x_relu_mask, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  if (!ws || ws_bytes < dense_bwd_workspace_bytes(batch, in, out))
-    return fail(ADN_ERR_WORKSPACE, "pl dense_bwd: workspace %lld < %lld bytes", (long long)ws_bytes,
-                (long long)dense_bwd_workspace_bytes(batch, in, out));
-  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  const int max_s = max_dw_splits(in, out);
-  float* part = reinterpret_cast<float*>(p);
-  p += align_up((int64_t)max_s * in * out * (int64_t)sizeof(float), 256);
-  float* cspart = reinterpret_cast<float*>(p);
-  p += align_up(ceil_div(batch, 32) * in * (int64_t)sizeof(float), 256);
-  float* cspart2 = reinterpret_cast<float*>(p);
-  const int64_t cs_ld = in;
-  int rc;
-  if (dw) {
-    // ---- dW[in,out] = X^T dZ : A = Xp MN-major (M=in), B = dZp MN-major (N=out), K = batch, split-K ----
-    const Operand a = operand(xp, batch, in, 1);
-    const Operand b = operand(dzp, batch, out, 1);
-    const int64_t kb_b = ceil_div(batch, BK);
-    const bool pair = use_pair((int)in, (int)out);
-    const int S = pair ? dw_splits(ceil_div(in, BM2) * ceil_div(out, BN2), kb_b, max_s, sm_count() / 2)
-                       : dw_splits(ceil_div(in, BM) * ceil_div(out, BN), kb_b, max_s, sm_count());
-    GemmParams g{};
-    g.M = (int)in; g.N = (int)out; g.ldc = (int)out;
-    g.total_kb = (int)kb_b; g.kb_per_split = (int)ceil_div(kb_b, S);
-    g.splits = (int)ceil_div(kb_b, g.kb_per_split);
-    g.out = (g.splits == 1) ? dw : part;
-    if ((rc = launch_gemm<EPI_PARTIAL, 0>(a, b, g, st, "pl dW gemm"))) return rc;
-    if (g.splits > 1 && (rc = simt::reduce_partials(part, dw, in * out, g.splits, in * out, st))) return rc;
-  }
-  if (dxp || dx) {
-    // ---- dX[batch,in] = dZ W^T : A = dZp K-major (K=out), B = Wp K-major (N=in, K=out); ReLU mask from Xp.hi ----
-    const Operand a = operand(dzp, batch, out, 0);
-    const Operand b = operand(wp, in, out, 0);
-    GemmParams g{};
-    g.M = (int)batch; g.N = (int)in;
-    g.total_kb = (int)ceil_div(out, BK); g.kb_per_split = g.total_kb; g.splits = 1;
-    g.mask_bits = x_relu_mask ? bits_of(xp, batch, in) : nullptr;
-    g.out_nkb = (int)ceil_div(in, BK);
-    g.colsum_part = dx_colsum ? cspart : nullptr;
-    g.colsum_ld = (int)cs_ld;
-    if (dxp) {
-      g.out = dxp; g.out_lo = dxp + plane_floats(batch, in);
-      if ((rc = launch_gemm<EPI_MASK, 1>(a, b, g, st, "pl dX gemm (planes out)"))) return rc;
-    } else {
-      g.out = dx; g.ldc = (int)in;
-      if ((rc = launch_gemm<EPI_MASK, 0>(a, b, g, st, "pl dX gemm (dense out)"))) return rc;
-    }
-    // column sums of the [ceil(batch/32), in] partial matrix, fixed order
-    if (dx_colsum && (rc = simt::colsum(cspart, dx_colsum, ceil_div(batch, 32), in, cspart2, st))) return rc;
-  }
-  return ADN_OK;
+  const BwdOp op{xp, wp, dzp, dxp, dx, dx_colsum, dw, in, out, x_relu_mask, ws, ws_bytes};
+  return dense_bwd_group(&op, 1, batch, st);
 }
 
 }  // namespace pl

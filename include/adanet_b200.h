@@ -190,6 +190,39 @@ int adn_dense_fwd_p(const float* xp, const float* wp, const float* b, float* yp,
 int adn_dense_bwd_p(const float* xp, const float* wp, const float* dzp, float* dxp, float* dx,
                     float* dx_colsum, float* dw, int64_t batch, int64_t in, int64_t out,
                     int x_relu_mask, void* workspace, int64_t workspace_bytes, void* stream);
+/*
+ * Grouped forms: the same layer wave of several subnetworks (all candidates of an AdaNet iteration consume
+ * the same minibatch, adanet/core/iteration.py:185-192) in ONE persistent launch per GEMM kind, so launch,
+ * prologue and pipeline fill/drain are paid once per wave and narrow candidates hide behind wide ones.
+ * Per-op semantics are exactly adn_dense_fwd_p / adn_dense_bwd_p; ops must not alias each other's outputs.
+ */
+typedef struct adn_fwd_op {
+  const float* xp;     /* planes [batch, in]  */
+  const float* wp;     /* planes [in, out]    */
+  const float* bias;   /* [out] or NULL       */
+  float* yp;           /* planes [batch, out] -- exactly one of yp / y */
+  float* y;            /* dense  [batch, out] */
+  int64_t in, out;
+  int32_t act;         /* ADN_ACT_* */
+  int32_t reserved;
+} adn_fwd_op;
+typedef struct adn_bwd_op {
+  const float* xp;     /* planes [batch, in]  */
+  const float* wp;     /* planes [in, out]; required when dx is requested */
+  const float* dzp;    /* planes [batch, out] */
+  float* dxp;          /* planes [batch, in] or NULL */
+  float* dx;           /* dense  [batch, in] or NULL (at most one of dxp / dx) */
+  float* dx_colsum;    /* [in] or NULL */
+  float* dw;           /* dense [in, out] or NULL */
+  int64_t in, out;
+  int32_t x_relu_mask;
+  int32_t reserved;
+  void* workspace;     /* adn_query(ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES, batch, in, out); one per op */
+  int64_t workspace_bytes;
+} adn_bwd_op;
+int adn_dense_fwd_p_group(const adn_fwd_op* ops_host, int n, int64_t batch, void* stream);
+int adn_dense_bwd_p_group(const adn_bwd_op* ops_host, int n, int64_t batch, void* stream);
+
 /* adn_head_loss that also emits, in the same pass, dlogits as split planes (nullable) and its
  * column sums = the bias gradient of the logits layer (nullable): what the backward GEMMs consume. */
 int adn_head_loss_p(int head, const float* logits, const int64_t* labels, const float* labels_f,
