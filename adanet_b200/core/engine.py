@@ -171,10 +171,7 @@ class DenseNet:
       self.acts = [None] * (n - 1) + [torch.empty((batch, dims[-1]), dtype=torch.float32, device=device)]
       self.hp = [new_planes(batch, d, device) for d in dims[1:-1]]
       self.wps = [new_planes(dims[i], dims[i + 1], device) for i in range(n)]
-      sp = torch.cuda.current_stream(device).cuda_stream
-      lib = _lib.load()
-      for w, wp in zip(self.ws, self.wps):
-        _lib.check(lib.adn_planes_split(w.data_ptr(), w.shape[0], w.shape[1], wp.data_ptr(), sp), "adn_planes_split")
+      self.refresh_planes()
       self.fwd_ws_bytes, self.fwd_ws = 0, None
     else:
       self.acts = [torch.empty((batch, d), dtype=torch.float32, device=device) for d in dims[1:]]
@@ -182,6 +179,16 @@ class DenseNet:
       fwd_ws = max(_lib.query(_lib.Q_DENSE_FWD_WS, batch, dims[i], dims[i + 1]) for i in range(n))
       self.fwd_ws_bytes = fwd_ws
       self.fwd_ws = torch.empty((max(fwd_ws, 16),), dtype=torch.uint8, device=device)
+
+  def refresh_planes(self):
+    """Re-splits every kernel into its planes (after the dense weights were written from outside the engine,
+    e.g. the end-of-iteration broadcast of the winner)."""
+    if not self.planes:
+      return
+    sp = torch.cuda.current_stream(self.device).cuda_stream
+    lib = _lib.load()
+    for w, wp in zip(self.ws, self.wps):
+      _lib.check(lib.adn_planes_split(w.data_ptr(), w.shape[0], w.shape[1], wp.data_ptr(), sp), "adn_planes_split")
 
   @property
   def logits(self) -> torch.Tensor:

@@ -172,6 +172,8 @@ class AdaNetSearch:
         mix_w = torch.empty(wshape, dtype=torch.float32, device=self.device)
         bias = torch.empty((self.C,), dtype=torch.float32, device=self.device)
       ex.broadcast_tensors(member.ws + member.bs + [mix_w, bias], src=owner)
+      if ex.rank() != owner:
+        member.refresh_planes()   # its planes were split from the (pre-broadcast) initial weights
       self.frozen = self.frozen + [member]
       self.architecture = self.architecture + [(t, spec.name)]
       self.prev_best_ema = ema_all[ci]

@@ -1,0 +1,190 @@
+"""GPU lifecycle tests of the reference-shaped public API (Estimator / AutoEnsembleEstimator / Evaluator /
+replay.Config) against the CPU oracle: train -> select -> grow -> evaluate -> predict, as
+adanet/core/estimator_test.py::test_lifecycle does with XOR data (:417-1120), here with per-step parity
+instead of 3-decimal goldens because initial weights are injected identically on both sides."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+B, D, C = 256, 20, 4
+SEED = 7
+
+
+@pytest.fixture(scope="module")
+def env():
+  import torch
+  import __graft_entry__ as g
+  g.build()
+  import adanet_b200 as adanet
+  from oracle import adanet_oracle as orc
+  return torch, adanet, orc
+
+
+def _data(orc, n=B * 64, seed=4321):
+  return orc.make_tabular(n, D, C, seed=seed)
+
+
+def _input_fn(x, y, key="x"):
+  def fn():
+    for i in range(0, x.shape[0] - B + 1, B):
+      yield {key: x[i:i + B]}, y[i:i + B]
+  return fn
+
+
+def _glorot(shape, seed):
+  # graph.glorot_uniform_initializer(seed): a fresh NumPy generator per dense layer
+  limit = np.sqrt(6.0 / (shape[0] + shape[-1]))
+  return np.random.default_rng(seed).uniform(-limit, limit, size=shape).astype(np.float32)
+
+
+def _oracle_simple_dnn_space(orc, layer_size, lr):
+  """examples/simple_dnn.Generator restated for the oracle: depth of the most recent member, and one deeper."""
+  def space(t, frozen):
+    depth = 0 if not frozen else len(frozen[-1].ws) - 1
+    specs = []
+    for nl in (depth, depth + 1):
+      dims = [D] + [layer_size] * nl + [C]
+      ws = [_glorot((dims[i], dims[i + 1]), SEED) for i in range(len(dims) - 1)]
+      bs = [np.zeros((d,), np.float32) for d in dims[1:]]
+      name = "linear" if nl == 0 else "{}_layer_dnn".format(nl)
+      specs.append(orc.SubnetworkSpec(name, dims, float(np.sqrt(np.float32(nl))), ("sgd", lr), ws=ws, bs=bs))
+    return specs
+  return space
+
+
+def _oracle_eval(orc, frozen, mix_w, bias, x, y):
+  logits = [orc.mlp_forward(m.ws, m.bs, x)[-1] for m in frozen]
+  ens = orc.ensemble_logits("scalar", list(mix_w), bias, logits, [None] * len(logits))
+  return float(orc.softmax_xent_mean(ens, y)[0]), ens
+
+
+def test_estimator_simple_dnn_lifecycle_matches_oracle(env, tmp_path):
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  from adanet_b200.examples import simple_dnn
+  x, y = _data(orc)
+  steps, iters, lr = 12, 3, 0.05
+  gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)], optimizer=train.GradientDescentOptimizer(lr),
+                             layer_size=16, seed=SEED)
+  est = adanet.Estimator(
+      head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
+      ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(0.01),
+                                                                 adanet_lambda=0.01, adanet_beta=0.001)],
+      max_iterations=iters, model_dir=str(tmp_path), debug=True)
+  est.train(_input_fn(x, y), max_steps=steps * iters)
+  ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+  results, frozen = orc.run_adanet(_oracle_simple_dnn_space(orc, 16, lr), x, y, B, steps, iters, ens, C)
+  reports = est._search.reports
+  assert len(reports) == iters
+  for rep, res in zip(reports, results):
+    assert rep.best_index == res.best_index
+    assert rep.architecture == res.architecture
+    np.testing.assert_allclose(rep.ema_losses, res.ema_losses, atol=1e-5, rtol=0)
+    for name, tr in res.traces.items():       # per-step losses of every candidate
+      got = rep.traces[name]                  # both sides use the reference's spec names (iteration.py:633,691-693)
+      np.testing.assert_allclose(got["sub_loss"], tr["sub_loss"], atol=1e-5, rtol=0)
+      np.testing.assert_allclose(got["adanet_loss"], tr["adanet_loss"], atol=1e-5, rtol=0)
+  # architecture files (adanet/core/estimator.py:1408-1413) and the eval metric string
+  for t in range(iters):
+    arch = json.load(open(os.path.join(str(tmp_path), "architecture-{}.json".format(t))))
+    assert [s["builder_name"] for s in arch["subnetworks"]] == [n for _, n in results[t].architecture]
+  assert est.architecture_string() == "| " + " | ".join(n for _, n in results[-1].architecture) + " |"
+  # evaluate / predict of the final ensemble on a hold-out batch
+  xe, ye = _data(orc, n=B * 2, seed=99)
+  ev = est.evaluate(_input_fn(xe, ye), steps=2)
+  want = np.mean([_oracle_eval(orc, frozen, results[-1].mixture_weights, results[-1].bias, xe[i:i + B], ye[i:i + B])[0]
+                  for i in (0, B)])
+  assert abs(ev["loss"] - want) < 1e-5 and ev["iteration"] == iters and ev["global_step"] == steps * iters
+  preds = list(est.predict(_input_fn(xe[:B], ye[:B])))
+  assert len(preds) == B
+  _, ens_logits = _oracle_eval(orc, frozen, results[-1].mixture_weights, results[-1].bias, xe[:B], ye[:B])
+  np.testing.assert_allclose(np.stack([p["logits"] for p in preds]), ens_logits, atol=2e-5)
+  assert all(int(p["class_ids"][0]) == int(np.argmax(p["logits"])) for p in preds)
+  acc = np.mean([int(p["class_ids"][0]) == int(t) for p, t in zip(preds, ye[:B])])
+  want_acc = [np.mean(np.argmax(_oracle_eval(orc, frozen, results[-1].mixture_weights, results[-1].bias, xe[i:i + B],
+                                             ye[i:i + B])[1], axis=1) == ye[i:i + B]) for i in (0, B)]
+  assert abs(acc - want_acc[0]) < 1e-9 and abs(ev["accuracy"] - np.mean(want_acc)) < 1e-9
+  # training past max_iterations is a no-op, like the reference's max_iterations stop (estimator.py:958-962)
+  est.train(_input_fn(x, y), steps=5)
+  assert est._search.iteration == iters
+
+
+def test_force_grow_and_replay(env, tmp_path):
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  from adanet_b200.examples import simple_dnn
+  x, y = _data(orc)
+
+  def make(**kw):
+    gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
+                               optimizer=train.GradientDescentOptimizer(0.0), layer_size=8, seed=SEED)
+    return adanet.Estimator(head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=3,
+                            max_iterations=3, **kw)
+  # frozen (lr=0) candidates never beat the previous ensemble once its EMA is established ...
+  est = make()
+  est.train(_input_fn(x, y), max_steps=9)
+  n_plain = len(est._search.frozen)
+  # ... unless force_grow drops index 0 from the comparison (adanet/core/estimator.py:1503-1510)
+  est = make(force_grow=True)
+  est.train(_input_fn(x, y), max_steps=9)
+  assert len(est._search.frozen) == 3 and n_plain <= 3
+  trace = list(est._search.replay_trace)
+  # replay.Config reproduces the recorded choices without looking at losses (estimator.py:1434-1438)
+  est2 = make(replay_config=adanet.replay.Config(best_ensemble_indices=trace))
+  est2.train(_input_fn(x, y), max_steps=9)
+  assert est2._search.replay_trace == trace and est2._search.architecture == est._search.architecture
+
+
+def test_evaluator_selection(env):
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  from adanet_b200.examples import simple_dnn
+  x, y = _data(orc)
+  xh, yh = _data(orc, n=B * 2, seed=5)
+  gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)], optimizer=train.GradientDescentOptimizer(0.05),
+                             layer_size=16, seed=SEED)
+  ev = adanet.Evaluator(input_fn=_input_fn(xh, yh), steps=2)
+  est = adanet.Estimator(head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=10,
+                         evaluator=ev, max_iterations=2)
+  est.train(_input_fn(x, y), max_steps=20)
+  reps = est._search.reports
+  assert len(reps) == 2 and all(np.isfinite(r.ema_losses).all() for r in reps)
+  # iteration 0: the winner minimises the hold-out adanet loss, which (lambda=beta=0) is the hold-out loss itself
+  ens = orc.EnsemblerSpec()
+  results, _ = orc.run_adanet(_oracle_simple_dnn_space(orc, 16, 0.05), x, y, B, 10, 1, ens, C)
+  # recompute the oracle's hold-out losses of the two iteration-0 candidates
+  space = _oracle_simple_dnn_space(orc, 16, 0.05)
+  cands = orc.build_candidates(0, space(0, []), [], ens, C, 0.9)
+  for s in range(10):
+    orc.train_step(cands, [], ens, x[s * B:(s + 1) * B], y[s * B:(s + 1) * B])
+  hold = []
+  for c in cands:
+    l = [float(orc.softmax_xent_mean(orc.mlp_forward(c.ws, c.bs, xh[i:i + B])[-1] * c.weights[0], yh[i:i + B])[0])
+         for i in (0, B)]
+    hold.append(np.mean(l))
+  np.testing.assert_allclose(reps[0].ema_losses, hold, atol=1e-5)
+  assert reps[0].best_index == int(np.argmin(hold))
+
+
+def test_autoensemble_linear_plus_dnn(env):
+  """BASELINE configs[0] plumbing: AutoEnsembleEstimator over {linear, DNN} (adanet/autoensemble/estimator.py:177-220)."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  x, y = _data(orc)
+  cols = [graph.numeric_column("x", D)]
+  pool = {"linear": adanet.estimators.LinearEstimator(cols, train.GradientDescentOptimizer(0.05)),
+          "dnn": adanet.estimators.DNNEstimator(cols, [32, 16], train.GradientDescentOptimizer(0.05))}
+  est = adanet.AutoEnsembleEstimator(head=adanet.heads.MultiClassHead(C), candidate_pool=pool, max_iteration_steps=15,
+                                     max_iterations=1, debug=True)
+  est.train(_input_fn(x, y), max_steps=15)
+  rep = est._search.reports[0]
+  assert [n.split("_grow_")[0] for n in rep.candidate_names] == ["t0_dnn", "t0_linear"]   # dict pools sorted by name
+  for name, tr in rep.traces.items():
+    assert tr["sub_loss"][-1] < tr["sub_loss"][0]        # both subestimators train
+  ev = est.evaluate(_input_fn(x[:B * 2], y[:B * 2]), steps=2)
+  assert np.isfinite(ev["loss"]) and ev["loss"] < np.log(C)
