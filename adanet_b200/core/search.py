@@ -72,7 +72,7 @@ class AdaNetSearch:
                head: str = "softmax_xent", adanet_loss_decay: float = 0.9, force_grow: bool = False,
                replay_indices: Optional[Sequence[int]] = None, device: Optional[torch.device] = None,
                use_cuda_graph: bool = True, multi_stream: bool = True, keep_traces: bool = True,
-               trace_capacity: int = 4096):
+               trace_capacity: int = 4096, placement: str = "balanced"):
     self.search_space, self.ens = search_space, ensembler
     self.in_dim, self.C, self.batch, self.head = in_dim, logits_dim, batch_size, head
     self.decay, self.force_grow = adanet_loss_decay, force_grow
@@ -80,6 +80,9 @@ class AdaNetSearch:
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.use_cuda_graph, self.multi_stream = use_cuda_graph, multi_stream
     self.keep_traces, self.trace_capacity = keep_traces, trace_capacity
+    if placement not in ("balanced", "round_robin"):
+      raise ValueError("placement must be 'balanced' or 'round_robin'")
+    self.placement = placement
     self.frozen: List[eng.DenseNet] = []
     self.iteration = 0
     self.prev_best_ema: Optional[float] = None
@@ -101,7 +104,11 @@ class AdaNetSearch:
       raise ValueError("Each iteration must have at least one Builder.")      # iteration.py:564-565
     self._specs = specs
     g, r = ex.world(), ex.rank()
-    mine = ex.owned_indices(len(specs), r, g)
+    # candidate -> rank: cost-balanced by training FLOPs per example (sum d_i d_{i+1}), or the reference-like i % G
+    costs = [sum(a * b for a, b in zip(s.dims[:-1], s.dims[1:])) for s in specs]
+    self._owners = (ex.balanced_owners(costs, g) if self.placement == "balanced"
+                    else ex.round_robin_owners(len(specs), g))
+    mine = ex.owned_indices(len(specs), r, g, self._owners)
     self.plan = eng.IterationPlan(self.iteration, [specs[i] for i in mine], self.frozen, self.ens, self.batch,
                                   self.in_dim, self.C, self.head, self.decay, self.trace_capacity, self.device,
                                   candidate_indices=mine, use_cuda_graph=self.use_cuda_graph,
@@ -134,7 +141,7 @@ class AdaNetSearch:
     k = len(specs)
     g = ex.world()
     local = plan.ema_losses() if local_metric_fn is None else list(local_metric_fn(plan))
-    new_losses = ex.gather_candidate_losses(local, k, device=self.device)
+    new_losses = ex.gather_candidate_losses(local, k, device=self.device, owners=self._owners)
     ens_name = self.ens.name
     names = ["t{}_{}_grow_{}".format(t, s.name, ens_name) for s in specs]
     losses = list(new_losses)
@@ -150,14 +157,15 @@ class AdaNetSearch:
       best = int(objective_fn(np.asarray(losses[1:], dtype=np.float32))) + 1
     else:
       best = int(objective_fn(np.asarray(losses, dtype=np.float32)))
-    ema_all = ex.gather_candidate_losses(plan.ema_losses(), k, device=self.device) if local_metric_fn is not None else new_losses
+    ema_all = (ex.gather_candidate_losses(plan.ema_losses(), k, device=self.device, owners=self._owners)
+               if local_metric_fn is not None else new_losses)
     traces = plan.traces() if self.keep_traces else None
     self.last_winner_index = None
     if t > 0 and best == 0:
       pass   # previous ensemble kept; nothing grows
     else:
       ci = best - (1 if t > 0 else 0)
-      owner = ex.owner_of(ci, g)
+      owner = self._owners[ci]
       spec = specs[ci]
       # materialise the winner's subnetwork on every rank for frozen replay
       if ex.rank() == owner:

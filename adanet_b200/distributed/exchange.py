@@ -36,27 +36,53 @@ def owner_of(candidate_index: int, world_size: int) -> int:
   return candidate_index % world_size
 
 
-def owned_indices(num_candidates: int, rank_: int, world_size: int) -> List[int]:
-  return [i for i in range(num_candidates) if owner_of(i, world_size) == rank_]
+def round_robin_owners(num_candidates: int, world_size: int) -> List[int]:
+  return [owner_of(i, world_size) for i in range(num_candidates)]
 
 
-def gather_candidate_losses(local_losses: Sequence[float], num_candidates: int, device=None, group=None) -> List[float]:
+def balanced_owners(costs: Sequence[float], world_size: int) -> List[int]:
+  """Cost-balanced colocated placement (longest-processing-time first): the heaviest candidate goes to the
+  least-loaded rank (ties: lowest rank).  Candidates differ by >100x in FLOPs across a width sweep, so
+  `i % G` leaves most GPUs waiting for the rank that drew the widest ones; every rank computes this same
+  mapping from the candidate specs, no communication."""
+  order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+  load = [0.0] * world_size
+  owners = [0] * len(costs)
+  for i in order:
+    r = min(range(world_size), key=lambda q: (load[q], q))
+    owners[i] = r
+    load[r] += float(costs[i])
+  return owners
+
+
+def owned_indices(num_candidates: int, rank_: int, world_size: int, owners: Optional[Sequence[int]] = None) -> List[int]:
+  owners = owners if owners is not None else round_robin_owners(num_candidates, world_size)
+  return [i for i in range(num_candidates) if owners[i] == rank_]
+
+
+def gather_candidate_losses(local_losses: Sequence[float], num_candidates: int, device=None, group=None,
+                            owners: Optional[Sequence[int]] = None) -> List[float]:
   """all_gather of the per-candidate EMA losses, returned in candidate order.
 
-  local_losses[j] belongs to candidate owned_indices(...)[j].  Every rank pads
-  to ceil(K/G) slots with NaN, gathers, and un-interleaves.
+  local_losses[j] belongs to the j-th candidate this rank owns (increasing candidate index).  Every rank
+  pads to the largest per-rank count with NaN, gathers, and un-interleaves with the shared owner map.
   """
   g, r = world(), rank()
   if g == 1:
     return [float(v) for v in local_losses]
-  slots = (num_candidates + g - 1) // g
+  owners = list(owners) if owners is not None else round_robin_owners(num_candidates, g)
+  slots = max(1, max(owners.count(q) for q in range(g)))
   mine = torch.full((slots,), float("nan"), dtype=torch.float32, device=device)
   for j, v in enumerate(local_losses):
     mine[j] = float(v)
   parts = [torch.empty_like(mine) for _ in range(g)]
   dist.all_gather(parts, mine, group=group)   # ncclAllGather on GPU, gloo on CPU
   out = torch.stack(parts).cpu()
-  return [float(out[owner_of(i, g), i // g]) for i in range(num_candidates)]
+  pos, seen = [], [0] * g
+  for i in range(num_candidates):
+    pos.append(seen[owners[i]])
+    seen[owners[i]] += 1
+  return [float(out[owners[i], pos[i]]) for i in range(num_candidates)]
 
 
 def broadcast_tensors(tensors: Sequence[torch.Tensor], src: int, group=None) -> None:

@@ -7,9 +7,9 @@ A "step" is one training step of EVERY candidate of the iteration on one
 minibatch (subnetwork fwd+bwd+update, candidate-ensemble head, EMA).  Workload
 (config.workload): BASELINE configs[2] -- 8-candidate DNN search 100->H->H->10,
 H in {64..1024}, 1M x 100 synthetic tabular data, B = 32768; it fits one GPU,
-so N=1 trains all 8 candidates on one B200 and N>1 shards candidate i -> GPU
-i % N (strong scaling: total work fixed, no data-path collective; the only
-exchange is the end-of-iteration loss all_gather, outside the step).
+so N=1 trains all 8 candidates on one B200 and N>1 shards whole candidates across
+the GPUs, cost-balanced (strong scaling: total work fixed, no data-path collective;
+the only exchange is the end-of-iteration loss all_gather, outside the step).
 
 Prints ONE JSON line on rank 0.  `value` = B*K / device time (CUDA events, max
 over ranks) with the dataset resident in HBM; `e2e` = same metric through
@@ -39,7 +39,7 @@ REF_SAMPLE_ROWS = 4096   # rows per step of the --impl reference arm (bounded sa
 
 def workload_name(gpus):
   return ("configs[2]: 8-candidate DNN search 100->H->H->10, H in %s, 1Mx100 tabular synthetic, B=%d, "
-          "candidate i -> GPU i %% %d" % (list(WIDTHS), BATCH, gpus))
+          "candidates placed on %d GPU(s) cost-balanced (LPT over train FLOPs)" % (list(WIDTHS), BATCH, gpus))
 
 
 def train_flops_per_example():

@@ -66,6 +66,50 @@ def test_exchange_world2_gloo(k):
   assert t0 == t1 == 11.0
 
 
+def _worker_balanced(rank, world, port, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from adanet_b200.distributed import exchange as ex
+    costs = [64 * 64, 128 * 128, 192 * 192, 256 * 256, 384 * 384, 512 * 512, 768 * 768, 1024 * 1024]
+    owners = ex.balanced_owners(costs, world)
+    mine = ex.owned_indices(len(costs), rank, world, owners)
+    losses = ex.gather_candidate_losses([float(10 + i) for i in mine], len(costs), owners=owners)
+    q.put((rank, owners, mine, losses))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_balanced_placement_world2_gloo():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker_balanced, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  out = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+  for p in procs:
+    p.join(60)
+    assert p.exitcode == 0
+  (_, o0, m0, l0), (_, o1, m1, l1) = out
+  assert o0 == o1 and sorted(m0 + m1) == list(range(8)) and o0[7] == 0      # the widest candidate goes first, to rank 0
+  costs = [64 * 64, 128 * 128, 192 * 192, 256 * 256, 384 * 384, 512 * 512, 768 * 768, 1024 * 1024]
+  load = [sum(costs[i] for i in m) for m in (m0, m1)]
+  assert abs(load[0] - load[1]) <= max(costs) * 0.1                          # i % 2 would be off by 0.6 M of 2.2 M
+  assert l0 == l1 == [float(10 + i) for i in range(8)]                      # un-interleaved back to candidate order
+
+
+def test_balanced_owners_properties():
+  from adanet_b200.distributed import exchange as ex
+  assert ex.balanced_owners([5, 5, 5, 5], 2) == [0, 1, 0, 1]
+  assert ex.balanced_owners([1, 1, 1], 8) == [0, 1, 2]
+  assert ex.balanced_owners([], 4) == []
+  o = ex.balanced_owners([3, 1, 2, 10], 2)
+  assert o[3] == 0 and o[0] == 1 and sorted(set(o)) == [0, 1]
+  assert ex.round_robin_owners(5, 2) == [0, 1, 0, 1, 0]
+
+
 def test_single_process_passthrough():
   from adanet_b200.distributed import exchange as ex
   assert ex.world() == 1 and ex.rank() == 0
