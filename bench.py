@@ -308,6 +308,12 @@ def run_ours(args):
   # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N=1 only for cpu) ----------------
   hbm, bf16_burst, bf16_sust, which = load_peaks()
   kt, kflops, kpath = measure_dominant_kernel(lib, torch)
+  traffic = None   # dram bytes per launch of that kernel from the committed ncu --set full capture
+  try:
+    with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
+      traffic = int(json.load(f)["traffic_bytes"])
+  except Exception:
+    pass
   achieved = kflops / kt / 1e12
   roofline = {
       "bound": "tensor", "kernel": "adn_dense_fwd_p [32768,1024]x[1024,1024] bias+relu, planes in/out (%s)" % kpath,
@@ -316,7 +322,8 @@ def run_ours(args):
                      "issues 3 TF32 MMAs per product (3xTF32 split for 1e-5 fp32 parity), TF32 dense peak = bf16/2"
                      % which,
       "issued_frac_of_tf32_peak": (3.0 * achieved / (bf16_burst / 2.0)) if kpath.startswith("tcgen05") else None,
-      "traffic": None, "launch_seconds": kt,
+      "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write; algorithmic 553.6 MB of split planes)",
+      "launch_seconds": kt,
   }
   cpu = cpu_baseline_sample() if world == 1 else None
   line = {
