@@ -60,7 +60,7 @@ static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
 static constexpr int BAR_BYTES = 256;
 static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
 static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
-static constexpr int TMEM_COLS = 512;                 // H0 [0,128) H1 [128,256) S0 [256,384) S1 [384,512)
+static constexpr int TMEM_COLS = 512;                 // two chunk buffers of [H: 128 | S: 128] columns (pair kernel: H 256 | S 256)
 static constexpr int MAX_SPLITS = 64;
 
 enum { EPI_BIAS_ACT = 0, EPI_MASK = 1, EPI_PARTIAL = 2 };
@@ -380,8 +380,7 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;          // [2]       MMA -> epilogue (chunk ready)
   uint64_t* acc_empty = bars + 2 * STAGES + 2;     // [2]       epilogue -> MMA (chunk drained), count EPI_WARPS
-  uint64_t* s_empty = bars + 2 * STAGES + 4;       // [2]       epilogue -> MMA (small-term acc read), count EPI_WARPS
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -402,7 +401,6 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
       for (int b = 0; b < 2; ++b) {
         mbar_init(smem_u32(&acc_full[b]), 1);
         mbar_init(smem_u32(&acc_empty[b]), EPI_WARPS);
-        mbar_init(smem_u32(&s_empty[b]), EPI_WARPS);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -458,23 +456,24 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
         cur = find_problem(grp, cur, item);
         const GemmParams& g = grp.p[cur].g;
         const Item it = decode_item(g, item - grp.p[cur].item0);
-        const uint32_t idesc = make_idesc(BM, BN, g.a_mn, g.b_mn);
+        // B_hi and B_lo tiles are adjacent in the stage, so ONE N=256 MMA computes a_hi x [b_hi | b_lo] (hi*hi into
+        // columns [0,128), hi*lo into [128,256) of the chunk buffer) and a second N=128 MMA adds a_lo x b_hi to the
+        // cross-term half: 20 KiB of operand reads per K=8 step instead of 24 (the 128x128 single-CTA tile is
+        // bound by shared-memory traffic, not by MMA issue), same 192 clk of tensor work.
+        const uint32_t idesc256 = make_idesc(BM, 2 * BN, g.a_mn, g.b_mn);
+        const uint32_t idesc128 = make_idesc(BM, BN, g.a_mn, g.b_mn);
         const uint32_t dah = desc_hi_word(g.a_mn), dbh = desc_hi_word(g.b_mn);
         const uint32_t a_lo0 = desc_lo_word(smem0, g.a_mn);
         const uint32_t b_lo0 = desc_lo_word(smem0 + 2 * TILE_BYTES, g.b_mn);
         const uint32_t a_step = g.a_mn ? (1024u >> 4) : (32u >> 4);   // address-field advance per K=8 MMA
         const uint32_t b_step = g.b_mn ? (1024u >> 4) : (32u >> 4);
-        const uint32_t acc_s = tmem_base + 256 + (tile_i & 1) * 128;
-        mbar_wait(smem_u32(&s_empty[tile_i & 1]), ((tile_i >> 1) & 1) ^ 1);   // small-term accumulator free
-        tc_fence_after();
-        uint32_t s_accum = 0;                      // first small-term MMA of the tile overwrites
         for (int kb = 0; kb < it.nkb; kb += CHUNK, ++gchunk) {
           const uint32_t b = gchunk & 1;
           mbar_wait(smem_u32(&acc_empty[b]), ((gchunk >> 1) & 1) ^ 1);      // chunk buffer drained
           tc_fence_after();
-          const uint32_t acc_h = tmem_base + b * 128;
+          const uint32_t acc = tmem_base + b * 256;     // [H: 128 cols | S: 128 cols]
           const int nk = min(CHUNK, it.nkb - kb);
-          uint32_t h_accum = 0;                    // first hi*hi MMA of the chunk overwrites
+          uint32_t accum = 0;                      // first MMA of the chunk overwrites both halves
           for (int kk = 0; kk < nk; ++kk) {
             mbar_wait(smem_u32(&full_bar[s]), ph);
             tc_fence_after();
@@ -483,17 +482,15 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
 #pragma unroll
               for (int k = 0; k < BK / 8; ++k) {
                 const uint32_t a_hi = a_lo0 + so + k * a_step, a_lo = a_hi + (TILE_BYTES >> 4);
-                const uint32_t b_hi = b_lo0 + so + k * b_step, b_lo = b_hi + (TILE_BYTES >> 4);
-                umma_tf32(acc_s, a_lo, b_hi, dah, dbh, idesc, (k == 0) ? s_accum : 1u);
-                umma_tf32(acc_s, a_hi, b_lo, dah, dbh, idesc, 1u);
-                umma_tf32(acc_h, a_hi, b_hi, dah, dbh, idesc, (k == 0) ? h_accum : 1u);
+                const uint32_t b_hi = b_lo0 + so + k * b_step;
+                umma_tf32(acc, a_hi, b_hi, dah, dbh, idesc256, (k == 0) ? accum : 1u);       // hi*hi | hi*lo
+                umma_tf32(acc + 128, a_lo, b_hi, dah, dbh, idesc128, 1u);                    // + lo*hi
               }
               umma_commit(smem_u32(&empty_bar[s]));  // frees this smem stage when the MMAs retire
-              if (kk == nk - 1) umma_commit(smem_u32(&acc_full[b]));   // chunk (and small terms) complete
+              if (kk == nk - 1) umma_commit(smem_u32(&acc_full[b]));   // chunk complete
             }
             __syncwarp();
-            s_accum = 1u;
-            h_accum = 1u;
+            accum = 1u;
             if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -534,32 +531,26 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
         tc_fence_after();
         {
           uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(tmem_base + lane_base + b * 128 + col_base, r0);
-          tmem_ld32_nowait(tmem_base + lane_base + b * 128 + col_base + 32, r1);
+          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + col_base, r0);
+          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + col_base + 32, r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {          // fp32 RN adds
+          for (int j = 0; j < 32; ++j) {          // fp32 RN adds: hi*hi partial sums of this 128-K chunk
             acc[j] += __uint_as_float(r0[j]);
             acc[32 + j] += __uint_as_float(r1[j]);
           }
-        }
-        if (c == nchunks - 1) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + col_base, r0);
-          tmem_ld32_nowait(tmem_base + lane_base + 256 + (tile_i & 1) * 128 + col_base + 32, r1);
+          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + 128 + col_base, r0);
+          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + 128 + col_base + 32, r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 32; ++j) {          // cross terms of the chunk
             acc[j] += __uint_as_float(r0[j]);
             acc[32 + j] += __uint_as_float(r1[j]);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(&acc_empty[b]));
-          if (c == nchunks - 1) mbar_arrive(smem_u32(&s_empty[tile_i & 1]));
-        }
+        if (lane == 0) mbar_arrive(smem_u32(&acc_empty[b]));
       }
       // ---- tile output.  Each warp owns rows [mrow0, mrow0+32) x 64 columns, processed as two 32x32
       // slices: registers (lane = row; bias/ReLU/mask and sign bits here) -> smem (16 B chunks XOR-swizzled

@@ -197,15 +197,16 @@ def test_colsum_and_opt_step_planes(env):
   assert torch.equal(wp[:n2], ref[:n2])
 
 
-def test_pair_kernel_forced_matches_single():
-  """The CTA-pair (cta_group::2) kernel and the single-CTA kernel run the same MMA / accumulate order per
-  output element: forcing either through ADN_PL_PAIR must give bit-identical results (subprocesses: the
-  knob is read once per process)."""
+def test_pair_kernel_forced_matches_single(tmp_path):
+  """The CTA-pair (cta_group::2) kernel against the single-CTA kernel on the same planes, both forced through
+  ADN_PL_PAIR (subprocesses: the knob is read once per process).  They issue the same products into the same
+  kind of two-level accumulation; only the point where the cross-term accumulator is folded in differs (per
+  128-K chunk vs once per tile), so results agree to fp32 rounding of the sums, far inside the GEMM bound."""
   import os
   import subprocess
   import sys
   code = r"""
-import numpy as np, torch, sys, hashlib
+import numpy as np, torch, sys
 sys.path.insert(0, %r)
 import __graft_entry__ as g; g.build()
 from adanet_b200 import _lib
@@ -218,6 +219,9 @@ def planes(a):
   pl = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, r, c) // 4,), device="cuda")
   src = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
   _lib.check(lib.adn_planes_split(src.data_ptr(), r, c, pl.data_ptr(), sp), "split"); return pl
+def merged(pl, r, c):
+  out = torch.empty((r, c), device="cuda")
+  _lib.check(lib.adn_planes_merge(pl.data_ptr(), r, c, out.data_ptr(), sp), "merge"); return out.cpu().numpy()
 x = np.maximum(rng.standard_normal((B, I)), 0).astype(np.float32); w = rng.standard_normal((I, O)).astype(np.float32) / 17
 dz = rng.standard_normal((B, O)).astype(np.float32); b = rng.standard_normal((O,)).astype(np.float32)
 xp, wp, dzp = planes(x), planes(w), planes(dz); bd = torch.as_tensor(b).cuda()
@@ -227,14 +231,15 @@ nb = _lib.query(_lib.Q_DENSE_BWD_P_WS, B, I, O); ws = torch.empty((nb,), dtype=t
 dw = torch.empty((I, O), device="cuda"); cs = torch.empty((I,), device="cuda")
 dxp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, I) // 4,), device="cuda")
 _lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), dxp.data_ptr(), None, cs.data_ptr(), dw.data_ptr(), B, I, O, 1, ws.data_ptr(), nb, sp), "bwd")
-h = hashlib.sha256()
-for t in (yp, dw, cs, dxp): h.update(t.cpu().numpy().tobytes())
-print("HASH", h.hexdigest())
+np.savez(sys.argv[1], y=merged(yp, B, O), dw=dw.cpu().numpy(), cs=cs.cpu().numpy(), dx=merged(dxp, B, I))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   out = []
   for pair in ("0", "1"):
     env = dict(os.environ, ADN_PL_PAIR=pair)
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    path = str(tmp_path / ("pair%s.npz" % pair))
+    r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
-    out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][0])
-  assert out[0] == out[1]
+    out.append(np.load(path))
+  for k in ("y", "dw", "cs", "dx"):
+    a, b = out[0][k].astype(np.float64), out[1][k].astype(np.float64)
+    assert np.abs(a - b).max() <= 4e-7 * max(np.abs(a).max(), 1e-30), k
