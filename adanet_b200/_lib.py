@@ -29,6 +29,7 @@ EXPORTS = (
     "adn_ensemble_head", "adn_opt_step", "adn_l1_norm", "adn_ema_update", "adn_record_scalars",
     "adn_counter_add", "adn_planes_split", "adn_planes_merge", "adn_dense_fwd_p", "adn_dense_bwd_p", "adn_colsum",
     "adn_opt_step_p", "adn_head_loss_p", "adn_dense_fwd_p_group", "adn_dense_bwd_p_group",
+    "adn_l1_grad_add",
 )
 
 
@@ -86,6 +87,7 @@ def load():
   lib.adn_dense_bwd_p.argtypes = [p, p, p, p, p, p, p, i64, i64, i64, c_int, p, i64, p]
   lib.adn_colsum.argtypes = [p, i64, i64, p, p, i64, p]
   lib.adn_head_loss_p.argtypes = [c_int, p, p, p, p, p, p, p, i64, i64, p, i64, p]
+  lib.adn_l1_grad_add.argtypes = [p, p, i64, f32, p]
   lib.adn_dense_fwd_p_group.argtypes = [POINTER(FwdOp), c_int, i64, p]
   lib.adn_dense_bwd_p_group.argtypes = [POINTER(BwdOp), c_int, i64, p]
   lib.adn_opt_step_p.argtypes = [c_int, POINTER(p), POINTER(p), POINTER(p), POINTER(p), POINTER(i64), c_int,

@@ -194,6 +194,15 @@ class DenseNet:
   def logits(self) -> torch.Tensor:
     return self.acts[-1]
 
+  def last_layer_planes(self, xp: torch.Tensor) -> torch.Tensor:
+    """Split planes of the last layer (MATRIX mixture weights multiply it, weighted.py:449): the last hidden
+    activation, or the input itself for a linear model (simple_dnn.py:70-78)."""
+    return self.hp[-1] if len(self.dims) > 2 else xp
+
+  @property
+  def last_layer_dim(self) -> int:
+    return self.dims[-2]
+
   @property
   def last_layer(self) -> torch.Tensor:
     """Last hidden activation as dense fp32 [batch, d] (merged from its planes on demand)."""
@@ -294,12 +303,27 @@ class CandidatePlan:
     self.sub_opt = _Optimizer(spec.optimizer, params, planes if self.planes else None)
     # ensemble state (weighted.py:360-366,419-428,487-516)
     self.mix = _MIX_KIND[ens.mixture_weight_type]
+    self.member_nets = list(frozen) + [self.net]
     if self.mix == _lib.MIX_MATRIX:
-      raise NotImplementedError("MATRIX mixture weights are not wired into the iteration plan yet")
-    wshape = (n_members,) if self.mix == _lib.MIX_SCALAR else (n_members, logits_dim)
-    self.mix_w = torch.full(wshape, 1.0 / n_members, **f32)
+      # W_k [D_k, C] (zeros, weighted.py:424-428) applied to each member's last layer by the plane GEMM; the
+      # head kernel then sees pre-multiplied members and the L1 norms (include/adanet_b200.h)
+      if not self.planes:
+        raise NotImplementedError("MATRIX mixture weights run on the plane path only (ADN_DENSE_PATH=simt is a cross-check)")
+      self.mw = [torch.zeros((m.last_layer_dim, logits_dim), **f32) for m in self.member_nets]
+      self.mwp = [new_planes(m.last_layer_dim, logits_dim, device) for m in self.member_nets]
+      self.d_mw = [torch.zeros_like(w) for w in self.mw]
+      self.mw_logits = [torch.empty((batch, logits_dim), **f32) for _ in self.member_nets]
+      self.mw_l1 = torch.zeros((n_members,), **f32)
+      self.dens = torch.empty((batch, logits_dim), **f32)
+      self.densp = new_planes(batch, logits_dim, device)
+      self.mw_ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_P_WS, batch, m.last_layer_dim, logits_dim) for m in self.member_nets)
+      self.mw_ws = torch.empty((self.mw_ws_bytes,), dtype=torch.uint8, device=device)
+      self.mix_w = self.mw_l1
+    else:
+      wshape = (n_members,) if self.mix == _lib.MIX_SCALAR else (n_members, logits_dim)
+      self.mix_w = torch.full(wshape, 1.0 / n_members, **f32)
     self.bias = torch.zeros((logits_dim,), **f32)
-    self.d_mix_w = torch.zeros(wshape, **f32)
+    self.d_mix_w = torch.zeros_like(self.mix_w)
     self.d_bias = torch.zeros((logits_dim,), **f32)
     self.complexities = [f.complexity for f in frozen] + [spec.complexity]
     lam, beta = float(ens.adanet_lambda), float(ens.adanet_beta)
@@ -311,14 +335,22 @@ class CandidatePlan:
     self.out3 = torch.zeros((3,), **f32)
     self.ens_opt = None
     if ens.optimizer is not None:
-      ens_params = [self.mix_w] + ([self.bias] if ens.use_bias else [])
-      self._ens_grads = [self.d_mix_w] + ([self.d_bias] if ens.use_bias else [])
-      self.ens_opt = _Optimizer(ens.optimizer, ens_params)
+      if self.mix == _lib.MIX_MATRIX:
+        ens_params = list(self.mw) + ([self.bias] if ens.use_bias else [])
+        self._ens_grads = list(self.d_mw) + ([self.d_bias] if ens.use_bias else [])
+        self.ens_opt = _Optimizer(ens.optimizer, ens_params, list(self.mwp) + ([None] if ens.use_bias else []))
+      else:
+        ens_params = [self.mix_w] + ([self.bias] if ens.use_bias else [])
+        self._ens_grads = [self.d_mix_w] + ([self.d_bias] if ens.use_bias else [])
+        self.ens_opt = _Optimizer(ens.optimizer, ens_params)
     self.ema_state = torch.zeros((3,), **f32)   # {biased, n, value}; candidate.py:101-129
     self.decay = float(decay)
     self.trace = torch.zeros((trace_capacity, 4), **f32)
     self.trace_capacity = trace_capacity
-    self._members = _lib.ptr_array([f.logits.data_ptr() for f in self.frozen] + [self.net.logits.data_ptr()])
+    if self.mix == _lib.MIX_MATRIX:
+      self._members = _lib.ptr_array([t.data_ptr() for t in self.mw_logits])
+    else:
+      self._members = _lib.ptr_array([f.logits.data_ptr() for f in self.frozen] + [self.net.logits.data_ptr()])
     self._gammas = _lib.f32_array(self.gammas)
     self._trace_src = _lib.ptr_array([self.sub_loss.data_ptr(), self.out3.data_ptr(),
                                       self.out3.data_ptr() + 8, self.ema_state.data_ptr() + 8])
@@ -384,6 +416,10 @@ class CandidatePlan:
       self.ens_opt.apply(lib, self._ens_grads, sp)
     self.sub_opt.apply(lib, self._grads, sp)
 
+  def mixture_weight_tensors(self) -> List[torch.Tensor]:
+    """The trained mixture weights as tensors: [w] (SCALAR [N] / VECTOR [N,C]) or the N matrices (MATRIX)."""
+    return list(self.mw) if self.mix == _lib.MIX_MATRIX else [self.mix_w]
+
   # ---- plane path, wave-synchronous schedule (IterationPlan._enqueue_waves) ----
   def enqueue_sub_loss(self, labels, labels_f, sp: int):
     """step 3 after the forward waves: subnetwork loss, dlogits (dense + planes) and db of the logits layer."""
@@ -394,19 +430,43 @@ class CandidatePlan:
                                         self.dbs[len(self.net.ws) - 1].data_ptr(), self.batch, self.C,
                                         self.workspace.data_ptr(), self.ws_bytes, sp), "adn_head_loss_p")
 
-  def enqueue_ensemble(self, labels, labels_f, step_dev, sp: int):
+  def _matrix_forward(self, xp, sp: int):
+    """weighted.py:449: weighted_k = last_layer_k @ W_k for every member, and ||W_k||_1 for the regulariser."""
+    lib, B, C = self.lib, self.batch, self.C
+    for k, m in enumerate(self.member_nets):
+      _lib.check(lib.adn_dense_fwd_p(m.last_layer_planes(xp).data_ptr(), self.mwp[k].data_ptr(), None, None,
+                                     self.mw_logits[k].data_ptr(), B, m.last_layer_dim, C, _lib.ACT_NONE, sp),
+                 "adn_dense_fwd_p")
+      _lib.check(lib.adn_l1_norm(self.mw[k].data_ptr(), self.mw[k].numel(), self.mw_l1.data_ptr() + 4 * k, sp),
+                 "adn_l1_norm")
+
+  def enqueue_ensemble(self, labels, labels_f, step_dev, sp: int, xp: Optional[torch.Tensor] = None):
     """steps 6-12: ensemble head on pre-update values, EMA, trace (own small workspace: runs beside the
     backward waves)."""
     lib, B, C = self.lib, self.batch, self.C
     lab = labels.data_ptr() if labels is not None else None
     labf = labels_f.data_ptr() if labels_f is not None else None
     train_ens = self.ens_opt is not None
+    matrix = self.mix == _lib.MIX_MATRIX
+    if matrix:
+      self._matrix_forward(xp, sp)
     _lib.check(lib.adn_ensemble_head(
         self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
         self._gammas, self.reg_is_zero, self.reg_multiplier, lab, labf, self.out3.data_ptr(),
-        self.d_mix_w.data_ptr() if train_ens else None,
+        self.d_mix_w.data_ptr() if (train_ens and not matrix) else None,
         self.d_bias.data_ptr() if (train_ens and self.ens.use_bias) else None,
-        None, None, B, C, self.head_ws.data_ptr(), self.head_ws_bytes, sp), "adn_ensemble_head")
+        self.dens.data_ptr() if (train_ens and matrix) else None, None, B, C, self.head_ws.data_ptr(),
+        self.head_ws_bytes, sp), "adn_ensemble_head")
+    if train_ens and matrix:
+      # dW_k = last_layer_k^T @ dLoss/d(ens)  + reg_multiplier * gamma_k * sign(W_k)   (weighted.py:606-617)
+      _lib.check(lib.adn_planes_split(self.dens.data_ptr(), B, C, self.densp.data_ptr(), sp), "adn_planes_split")
+      for k, m in enumerate(self.member_nets):
+        _lib.check(lib.adn_dense_bwd_p(m.last_layer_planes(xp).data_ptr(), None, self.densp.data_ptr(), None, None, None,
+                                       self.d_mw[k].data_ptr(), B, m.last_layer_dim, C, 0, self.mw_ws.data_ptr(),
+                                       self.mw_ws_bytes, sp), "adn_dense_bwd_p")
+        if not self.reg_is_zero:
+          _lib.check(lib.adn_l1_grad_add(self.d_mw[k].data_ptr(), self.mw[k].data_ptr(), self.mw[k].numel(),
+                                         self.reg_multiplier * self.gammas[k], sp), "adn_l1_grad_add")
     _lib.check(lib.adn_ema_update(self.ema_state.data_ptr(), self.out3.data_ptr() + 8, self.decay, sp),
                "adn_ema_update")
     _lib.check(lib.adn_record_scalars(self._trace_src, 4, self.trace.data_ptr(), 4, step_dev.data_ptr(),
@@ -436,6 +496,8 @@ class CandidatePlan:
     """Forward-only: subnetwork logits + ensemble logits/loss (evaluate / predict)."""
     lib, net, B, C = self.lib, self.net, self.batch, self.C
     net.forward(lib, x, sp, xp)
+    if self.mix == _lib.MIX_MATRIX:
+      self._matrix_forward(xp, sp)
     _lib.check(lib.adn_ensemble_head(
         self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
         self._gammas, self.reg_is_zero, self.reg_multiplier,
@@ -514,7 +576,7 @@ class IterationPlan:
           ev = torch.cuda.Event()
           ev.record(s)
           main.wait_event(ev)          # the backward waves need every candidate's dlogits planes
-        c.enqueue_ensemble(self.labels, self.labels_f, self.step_dev, s.cuda_stream)
+        c.enqueue_ensemble(self.labels, self.labels_f, self.step_dev, s.cuda_stream, self.xp)
     for k in range(max(len(c.net.ws) for c in self.candidates)):
       ops = [c.bwd_op(k, self.xp) for c in self.candidates if k < len(c.net.ws)]
       arr = (_lib.BwdOp * len(ops))(*ops)
@@ -623,15 +685,29 @@ class EnsembleEvalPlan:
         raise ValueError("member %s was built for batch %d, eval plan uses %d" % (m.name, m.batch, batch))
     f32 = dict(dtype=torch.float32, device=self.device)
     self.mix = _MIX_KIND[ens.mixture_weight_type]
-    self.mix_w = torch.as_tensor(np.ascontiguousarray(mix_w, dtype=np.float32)).to(self.device).reshape(
-        (len(members),) if self.mix == _lib.MIX_SCALAR else (len(members), logits_dim))
+    if self.mix == _lib.MIX_MATRIX:
+      # mix_w: list of [D_k, C] matrices; members are pre-multiplied by the plane GEMM, w = their L1 norms
+      if not planes_enabled():
+        raise NotImplementedError("MATRIX mixture weights run on the plane path only")
+      self.mw = [torch.as_tensor(np.ascontiguousarray(w, dtype=np.float32)).to(self.device) for w in mix_w]
+      self.mwp = [new_planes(w.shape[0], w.shape[1], self.device) for w in self.mw]
+      sp0 = torch.cuda.current_stream(self.device).cuda_stream
+      for w, wp in zip(self.mw, self.mwp):
+        _lib.check(self.lib.adn_planes_split(w.data_ptr(), w.shape[0], w.shape[1], wp.data_ptr(), sp0), "adn_planes_split")
+      self.mw_logits = [torch.empty((batch, logits_dim), **f32) for _ in self.mw]
+      self.mix_w = torch.as_tensor(np.array([np.abs(np.asarray(w, dtype=np.float32)).sum(dtype=np.float32)
+                                             for w in mix_w], dtype=np.float32)).to(self.device)
+    else:
+      self.mix_w = torch.as_tensor(np.ascontiguousarray(mix_w, dtype=np.float32)).to(self.device).reshape(
+          (len(members),) if self.mix == _lib.MIX_SCALAR else (len(members), logits_dim))
     self.bias = torch.as_tensor(np.ascontiguousarray(bias, dtype=np.float32)).to(self.device)
     lam, beta = float(ens.adanet_lambda), float(ens.adanet_beta)
     self.reg_is_zero = int(lam == 0.0 and beta == 0.0)
     self.gammas = [float(np.float32(beta) if lam == 0.0 else np.float32(np.float32(lam) * np.float32(m.complexity) + np.float32(beta)))
                    for m in self.members]
     self._gammas = _lib.f32_array(self.gammas)
-    self._members = _lib.ptr_array([m.logits.data_ptr() for m in self.members])
+    self._members = _lib.ptr_array([t.data_ptr() for t in self.mw_logits] if self.mix == _lib.MIX_MATRIX
+                                   else [m.logits.data_ptr() for m in self.members])
     self.out3 = torch.zeros((3,), **f32)
     self.ens_logits = torch.empty((batch, logits_dim), **f32)
     self.ws_bytes = _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, len(self.members))
@@ -657,6 +733,11 @@ class EnsembleEvalPlan:
                    "adn_planes_split")
       for m in self.members:
         m.forward(self.lib, self.x, sp, self.xp)
+      if self.mix == _lib.MIX_MATRIX:
+        for k, m in enumerate(self.members):
+          _lib.check(self.lib.adn_dense_fwd_p(m.last_layer_planes(self.xp).data_ptr(), self.mwp[k].data_ptr(), None, None,
+                                              self.mw_logits[k].data_ptr(), self.batch, m.last_layer_dim, self.C,
+                                              _lib.ACT_NONE, sp), "adn_dense_fwd_p")
     _lib.check(self.lib.adn_ensemble_head(
         self.head, self.mix, self._members, len(self.members), self.mix_w.data_ptr(), self.bias.data_ptr(),
         self._gammas, self.reg_is_zero, 1.0, self.labels.data_ptr() if self.labels is not None else None,

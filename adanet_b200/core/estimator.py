@@ -148,8 +148,6 @@ class Estimator(object):
       raise NotImplementedError("MeanEnsembler is a 'next' row (SURVEY.md 8f.3); use ComplexityRegularizedEnsembler")
     if not isinstance(e, ensemble_lib.ComplexityRegularizedEnsembler):
       raise NotImplementedError("custom Ensemblers are not supported by the B200 engine: %r" % (e,))
-    if e.mixture_weight_type == ensemble_lib.MixtureWeightType.MATRIX:
-      raise NotImplementedError("MATRIX mixture weights are a 'next' row (SURVEY.md 8f.3)")
     if e.warm_start_mixture_weights:
       raise NotImplementedError("warm_start_mixture_weights is a 'next' row (SURVEY.md 8f.3)")
     return eng.EnsemblerPlanSpec(optimizer=train_lib.optimizer_from(e.optimizer), mixture_weight_type=e.mixture_weight_type,
@@ -294,7 +292,7 @@ class Estimator(object):
     self._last_candidate_name = cand_name
     # previous_ensemble handed to the generator / builders of iteration t+1 (weighted.py:90-136)
     ws = []
-    mw = np.asarray(rep.mixture_weights)
+    mw = rep.mixture_weights if isinstance(rep.mixture_weights, list) else np.asarray(rep.mixture_weights)
     for k, (sub, (it, name)) in enumerate(zip(self._member_subnetworks, rep.architecture)):
       ws.append(ensemble_lib.WeightedSubnetwork(name=name, iteration_number=it, weight=np.array(mw[k]), logits=sub.logits,
                                                 subnetwork=sub))
@@ -319,8 +317,12 @@ class Estimator(object):
   def _save_ensemble(self):
     """The final ensemble's parameters (replaces the reference's increment.ckpt-{t})."""
     s = self._search
-    out = {"global_step": self._global_step, "iteration": s.iteration, "mixture_weights": s.mixture_weights,
-           "bias": s.bias}
+    out = {"global_step": self._global_step, "iteration": s.iteration, "bias": s.bias}
+    if isinstance(s.mixture_weights, list):
+      for k, w in enumerate(s.mixture_weights):
+        out["mixture_weight_{}".format(k)] = w
+    else:
+      out["mixture_weights"] = s.mixture_weights
     for k, m in enumerate(s.frozen):
       ws, bs = m.numpy_params()
       for i, (w, b) in enumerate(zip(ws, bs)):

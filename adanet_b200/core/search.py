@@ -168,25 +168,31 @@ class AdaNetSearch:
       owner = self._owners[ci]
       spec = specs[ci]
       # materialise the winner's subnetwork on every rank for frozen replay
+      matrix = self.ens.mixture_weight_type == "matrix"
       if ex.rank() == owner:
         cand = next(c for c in plan.candidates if c.index == ci)
         member = cand.net
-        mix_w, bias = cand.mix_w, cand.bias
+        mix_ws, bias = cand.mixture_weight_tensors(), cand.bias
       else:
         member = eng.DenseNet(spec.name, spec.dims, spec.ws, spec.bs, spec.complexity, self.batch, self.device,
                               t, spec.shared)
         n_members = len(self.frozen) + 1
-        wshape = (n_members,) if self.ens.mixture_weight_type == "scalar" else (n_members, self.C)
-        mix_w = torch.empty(wshape, dtype=torch.float32, device=self.device)
+        if matrix:
+          mix_ws = [torch.empty((m.last_layer_dim, self.C), dtype=torch.float32, device=self.device)
+                    for m in list(self.frozen) + [member]]
+        else:
+          wshape = (n_members,) if self.ens.mixture_weight_type == "scalar" else (n_members, self.C)
+          mix_ws = [torch.empty(wshape, dtype=torch.float32, device=self.device)]
         bias = torch.empty((self.C,), dtype=torch.float32, device=self.device)
-      ex.broadcast_tensors(member.ws + member.bs + [mix_w, bias], src=owner)
+      ex.broadcast_tensors(member.ws + member.bs + mix_ws + [bias], src=owner)
       if ex.rank() != owner:
         member.refresh_planes()   # its planes were split from the (pre-broadcast) initial weights
       self.frozen = self.frozen + [member]
       self.architecture = self.architecture + [(t, spec.name)]
       self.prev_best_ema = ema_all[ci]
       self.last_winner_index = ci
-      self.mixture_weights = mix_w.cpu().numpy().copy()
+      # SCALAR [N] / VECTOR [N,C] array, or the list of N [D_k,C] matrices (MATRIX)
+      self.mixture_weights = ([w.cpu().numpy().copy() for w in mix_ws] if matrix else mix_ws[0].cpu().numpy().copy())
       self.bias = bias.cpu().numpy().copy()
     self.replay_trace = self.replay_trace + [best]
     rep = IterationReport(t, names, [float(v) for v in losses], best, list(self.architecture),

@@ -242,6 +242,11 @@ int adn_opt_step_p(int kind, float* const* params_host, const float* const* grad
 /* out[0] = sum_i |x[i]| over n elements (tf.norm(ord=1), weighted.py:573), fixed order. */
 int adn_l1_norm(const float* x, int64_t n, float* out, void* stream);
 
+/* dw[i] += coef * sign(w[i]): the complexity-regulariser term of a MATRIX mixture weight's gradient,
+ * coef = reg_multiplier * gamma_k (adanet/ensemble/weighted.py:563-617; SCALAR / VECTOR weights get it
+ * inside adn_ensemble_head). */
+int adn_l1_grad_add(float* dw, const float* w, int64_t n, float coef, void* stream);
+
 /*
  * Zero-debiased EMA of the AdaNet loss (adanet/core/candidate.py:117-129 ->
  * assign_moving_average(zero_debias=True)).  state: device float[3] =

@@ -60,6 +60,11 @@ CONFIGS = {
                      opt=("momentum", 0.005, 0.9),
                      ens=dict(optimizer=("momentum", 0.005, 0.9), adanet_lambda=0.01, adanet_beta=0.001,
                               use_bias=True, mixture_weight_type="vector")),
+    # MATRIX mixture weights (weighted.py:424-453): W_k [D_k, C] from zeros on every member's last layer, with bias
+    "matrix": dict(data=("tabular", 8192, 100, 10, 77), cfgs=[(1, 64), (2, 96)], B=256, steps=30, iters=2,
+                   opt=("sgd", 0.02),
+                   ens=dict(optimizer=("sgd", 0.02), adanet_lambda=0.01, adanet_beta=0.001, use_bias=True,
+                            mixture_weight_type="matrix")),
     "default_ensembler": dict(data=("tabular", 8192, 100, 10, 99), cfgs=[(1, 64), (2, 64)], B=256, steps=30, iters=2,
                               opt=("sgd", 0.01), ens=dict(optimizer=None)),
     "force_grow": dict(data=("tabular", 8192, 100, 10, 5), cfgs=[(1, 32), (2, 32)], B=256, steps=10, iters=3,
@@ -161,6 +166,8 @@ def _check(o_res, reps, tol=TOL):
 def test_iteration_parity(built_lib, name, path):
   from adanet_b200 import _lib
   cfg = CONFIGS[name]
+  if name == "matrix" and path == "simt":
+    pytest.skip("MATRIX mixture weights run on the plane path only")
   _lib.set_dense_path(_lib.PATH_SIMT if path == "simt" else _lib.PATH_AUTO)
   try:
     o = _oracle_run(cfg)
