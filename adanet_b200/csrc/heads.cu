@@ -32,7 +32,8 @@ struct HeadParams {
   float* dens_lo;
   int colsum_only;       // want_grads without the mixture-weight pass: only column sums of dens -> dbias
   float* ens_out;        // [B,dim] or null
-  float* part;           // workspace: per-CTA partials [n_cta][n_out]
+  float* part;           // workspace: per-CTA partials, output-major [n_out][n_cta] (coalesced for the finalize)
+  int n_cta;
   int64_t batch;
   int dim;
   int n_out;             // 1 + dim + N*wdim
@@ -49,69 +50,94 @@ __device__ __forceinline__ float weight_of(const HeadParams& p, int k, int c) {
   return p.mixture == ADN_MIX_SCALAR ? __ldg(p.w + k) : __ldg(p.w + (size_t)k * p.dim + c);
 }
 
-// smem layout (floats): ens[kRows*dim] | tile[kRows*dim] | red[kRows]
+// Block-wide sum of one value per thread in a FIXED order (shuffle tree inside each warp, then warp 0..W-1 in
+// sequence): run-to-run deterministic.  `wred` holds kRows/32 floats; the result is returned on thread 0 only.
+__device__ __forceinline__ float block_sum(float v, float* wred, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((tid & 31) == 0) wred[tid >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (tid == 0) {
+#pragma unroll
+    for (int w = 0; w < kRows / 32; ++w) t += wred[w];
+  }
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+               "r"(bytes)
+               : "memory");
+}
+
+// One CTA = kRows examples, one thread per example.  The CTA's contiguous [kRows*dim] slab of EVERY member is
+// brought into shared memory with one burst of 16-byte cp.async copies (all members in flight at once: the
+// kernel is a pure HBM stream, SURVEY.md 8d: N*C*4 + 8 bytes per example), then each thread works on its row:
+// weighted sum, head loss and gradient, and the mixture-weight gradient from the SAME smem copy (no second
+// read).  All reductions are shuffle trees in a fixed order (no serial loops over rows, no atomics).
+// smem layout (floats): mem[n_members][kRows*dim] | ens[kRows*dim] | wred[kRows/32 * max(dim, n_members)]
+template <int CT>   // CT > 0: logits dimension known at compile time (loops unroll, row offsets fold); 0: runtime
 __global__ void __launch_bounds__(kRows)
 ensemble_head_kernel(const __grid_constant__ HeadParams p) {
   extern __shared__ __align__(16) float smem[];
-  const int C = p.dim;
-  float* ens = smem;
-  float* tile = smem + kRows * C;
-  float* red = tile + kRows * C;
-  const int tid = threadIdx.x;
+  const int C = CT > 0 ? CT : p.dim, N = p.n_members;
+  float* mem = smem;
+  float* ens = smem + (size_t)N * kRows * C;
+  float* wred = ens + kRows * C;        // [kRows/32][max(C, N)] warp partials
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * kRows;
   const int rows = (int)min((int64_t)kRows, p.batch - r0);
-  const int valid = rows * C;           // flat elements of this CTA's tile
+  const int valid = rows * C;           // flat elements of this CTA's slab
   const size_t base = (size_t)r0 * C;
   const int nvec = (kRows * C) / 4;     // kRows*C is a multiple of 4
 
-  // ---- pass 1: ens = bias + sum_k w_k (.) member_k   (flat, coalesced) ----
-  for (int i = tid; i < kRows * C; i += kRows) ens[i] = p.bias ? __ldg(p.bias + (i % C)) : 0.f;
-  // each thread only ever touches flat elements {4*(tid + j*kRows) .. +3}: no sync needed
-  __syncthreads();
-  for (int k = 0; k < p.n_members; ++k) {
+  // ---- stream every member's slab into smem (zero-filled past `valid`) ----
+  for (int k = 0; k < N; ++k) {
     const float* m = p.members[k] + base;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
-    for (int v = tid; v < nvec; v += kRows) {
-      const int i = v * 4;
-      if (i >= valid) break;
-      float x[4];
-      if (vec_ok && i + 3 < valid) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(m + i));
-        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) x[q] = (i + q < valid) ? __ldg(m + i + q) : 0.f;
+    float* dst = mem + (size_t)k * kRows * C;
+    if ((reinterpret_cast<uintptr_t>(m) & 15) == 0) {
+      for (int v = tid; v < nvec; v += kRows) {
+        const int i = v * 4;
+        const int bytes = max(0, min(16, (valid - i) * 4));
+        cp_async16(dst + i, bytes > 0 ? m + i : m, bytes);
       }
-      int c = i % C;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        ens[i + q] += weight_of(p, k, c) * x[q];
-        c = (c + 1 == C) ? 0 : c + 1;
-      }
+    } else {
+      for (int i = tid; i < kRows * C; i += kRows) dst[i] = (i < valid) ? __ldg(m + i) : 0.f;
     }
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  if (p.ens_out) {
-    for (int i = tid; i < valid; i += kRows) p.ens_out[base + i] = ens[i];
-  }
 
-  // ---- per-row head: loss_r, g[r,:] = dLoss/d ens (overwrites ens in place) ----
+  // ---- per-row: ens = bias + sum_k w_k (.) member_k (sequential over members like tf.add, weighted.py:558-561),
+  //      loss_r, g[r,:] = dLoss/d ens (kept in the thread's smem row) ----
+  float* e = ens + tid * C;
   float loss_r = 0.f;
   if (tid < rows) {
-    float* e = ens + tid * C;
+    for (int c = 0; c < C; ++c) {
+      float v = p.bias ? __ldg(p.bias + c) : 0.f;
+      for (int k = 0; k < N; ++k) v += weight_of(p, k, c) * mem[(size_t)k * kRows * C + tid * C + c];
+      e[c] = v;
+    }
+    if (p.ens_out) {
+      for (int c = 0; c < C; ++c) p.ens_out[base + (size_t)tid * C + c] = e[c];
+    }
     if (p.head == ADN_HEAD_SOFTMAX_XENT) {
       const int y = (int)p.labels[r0 + tid];
       float mx = e[0];
       for (int c = 1; c < C; ++c) mx = fmaxf(mx, e[c]);
+      const float zy = e[y] - mx;
       float s = 0.f;
-      for (int c = 0; c < C; ++c) s += expf(e[c] - mx);
-      const float logs = logf(s);
-      loss_r = -((e[y] - mx) - logs);
-      const float inv = 1.f / s, invb = 1.f / (float)p.batch;
-      for (int c = 0; c < C; ++c) {
-        float pr = expf(e[c] - mx) * inv;
-        e[c] = (pr - (c == y ? 1.f : 0.f)) * invb;
+      for (int c = 0; c < C; ++c) {          // one expf per class: the exponentials are kept in the row
+        const float ex = expf(e[c] - mx);
+        e[c] = ex;
+        s += ex;
       }
+      const float logs = logf(s);
+      loss_r = -(zy - logs);
+      const float inv = 1.f / s, invb = 1.f / (float)p.batch;
+      for (int c = 0; c < C; ++c) e[c] = (e[c] * inv - (c == y ? 1.f : 0.f)) * invb;
     } else if (p.head == ADN_HEAD_MSE) {
       const float invn = 1.f / ((float)p.batch * (float)C);
       for (int c = 0; c < C; ++c) {
@@ -128,15 +154,13 @@ ensemble_head_kernel(const __grid_constant__ HeadParams p) {
       }
     }
   } else {
-    for (int c = 0; c < C; ++c) ens[tid * C + c] = 0.f;
+    for (int c = 0; c < C; ++c) e[c] = 0.f;
   }
-  red[tid] = loss_r;
-  __syncthreads();
-  float* part = p.part + (size_t)blockIdx.x * p.n_out;
-  if (tid == 0) {
-    float t = 0.f;
-    for (int r = 0; r < kRows; ++r) t += red[r];   // fixed order
-    part[0] = t;
+  float* part = p.part + blockIdx.x;                   // output j of this CTA lives at part[j * n_cta]
+  const size_t ps = (size_t)p.n_cta;
+  {
+    const float t = block_sum(loss_r, wred, tid);     // (contains the barrier that publishes every row's g)
+    if (tid == 0) part[0] = t;
   }
   if (p.dens) {
     for (int i = tid; i < valid; i += kRows) p.dens[base + i] = ens[i];
@@ -149,68 +173,96 @@ ensemble_head_kernel(const __grid_constant__ HeadParams p) {
       if (r0 + r >= p.batch) continue;
       const int c = kb * 32 + c32;
       const float v = (c < C) ? ens[r * C + c] : 0.f;
-      uint32_t h, l;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-      const float hi = __uint_as_float(h);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+      const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+      const float lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
       const size_t dst = ((size_t)kb * p.batch + r0 + r) * 32 + c32;
       p.dens_hi[dst] = hi;
-      p.dens_lo[dst] = __uint_as_float(l);
+      p.dens_lo[dst] = lo;
     }
   }
   if (!p.want_grads) return;
 
-  // ---- column sums of g -> dbias partial ----
+  // ---- column sums of g -> dbias partial: warp trees per column, then the warps in sequence ----
+  const int wr = (C > N) ? C : N;          // row stride of the warp-partial scratch
+  // thread (w, c) adds column c over the 32 rows of row-group w straight from the smem rows (fixed order)
+  for (int j = tid; j < (kRows / 32) * C; j += kRows) {
+    const int w = j / C, c = j - w * C;
+    const float* col = ens + (size_t)(w * 32) * C + c;
+    float v = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) v += col[r * C];
+    wred[w * wr + c] = v;
+  }
+  __syncthreads();
   if (tid < C) {
     float t = 0.f;
-    for (int r = 0; r < kRows; ++r) t += ens[r * C + tid];
-    part[1 + tid] = t;
+#pragma unroll
+    for (int w = 0; w < kRows / 32; ++w) t += wred[w * wr + tid];
+    part[(1 + tid) * ps] = t;
   }
   if (p.mixture == ADN_MIX_MATRIX || p.colsum_only) return;
 
-  // ---- pass 2: dw_k partials = sum_b g (.) member_k  (members re-read, L2-hot) ----
-  const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : C;
-  for (int k = 0; k < p.n_members; ++k) {
-    const float* m = p.members[k] + base;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
-    __syncthreads();   // previous column reduce finished reading tile
-    for (int v = tid; v < nvec; v += kRows) {
-      const int i = v * 4;
-      float x[4] = {0.f, 0.f, 0.f, 0.f};
-      if (i < valid) {
-        if (vec_ok && i + 3 < valid) {
-          float4 t = __ldg(reinterpret_cast<const float4*>(m + i));
-          x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
-        } else {
+  // ---- dw_k partials = sum_b g (.) member_k from the smem copy of the members ----
+  if (p.mixture == ADN_MIX_SCALAR) {
+    __syncthreads();                       // dbias readers done with wred
+    for (int k = 0; k < N; ++k) {
+      const float* mrow = mem + (size_t)k * kRows * C + tid * C;
+      float d = 0.f;
+      for (int c = 0; c < C; ++c) d += e[c] * mrow[c];       // row dot product, then the block tree
 #pragma unroll
-          for (int q = 0; q < 4; ++q) x[q] = (i + q < valid) ? __ldg(m + i + q) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tile[i + q] = ens[i + q] * x[q];
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+      if (lane == 0) wred[warp * wr + k] = d;
     }
     __syncthreads();
-    if (tid < C) {
+    if (tid < N) {
       float t = 0.f;
-      for (int r = 0; r < kRows; ++r) t += tile[r * C + tid];
-      red[tid] = t;
+#pragma unroll
+      for (int w = 0; w < kRows / 32; ++w) t += wred[w * wr + tid];
+      part[(1 + C + tid) * ps] = t;
     }
-    if (wdim == 1) {
-      __syncthreads();
-      if (tid == 0) {
-        float t = 0.f;
-        for (int c = 0; c < C; ++c) t += red[c];
-        part[1 + C + k] = t;
+  } else {
+    for (int k = 0; k < N; ++k) {
+      const float* mrow = mem + (size_t)k * kRows * C + tid * C;
+      __syncthreads();                     // previous readers done with wred
+      for (int c = 0; c < C; ++c) {
+        float v = e[c] * mrow[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) wred[warp * wr + c] = v;
       }
-    } else if (tid < C) {
-      part[1 + C + k * C + tid] = red[tid];
+      __syncthreads();
+      if (tid < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRows / 32; ++w) t += wred[w * wr + tid];
+        part[(1 + C + k * C + tid) * ps] = t;
+      }
     }
   }
 }
 
 // Fixed-order reduction of the per-CTA partials + regulariser + adanet loss.
+// First level for many CTAs: block j sums the n_cta partials of output j (coalesced, fixed order) into out[j].
 __global__ void __launch_bounds__(256)
-ensemble_finalize_kernel(const __grid_constant__ HeadParams p, int n_cta) {
+head_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int n_cta) {
+  __shared__ float wsum[8];
+  const float* src = part + (size_t)blockIdx.x * n_cta;
+  float t = 0.f;
+  for (int b = threadIdx.x; b < n_cta; b += 256) t += src[b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += wsum[w];
+    out[blockIdx.x] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ensemble_finalize_kernel(const __grid_constant__ HeadParams p, const float* __restrict__ part, int n_cta) {
   __shared__ float s_loss, s_reg;
   const int C = p.dim;
   const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : C;
@@ -220,7 +272,7 @@ ensemble_finalize_kernel(const __grid_constant__ HeadParams p, int n_cta) {
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int j = wid; j < n_red; j += nwarps) {
     float t = 0.f;
-    for (int b = lane; b < n_cta; b += 32) t += p.part[(size_t)b * p.n_out + j];
+    for (int b = lane; b < n_cta; b += 32) t += part[(size_t)j * n_cta + b];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
     if (lane != 0) continue;
@@ -294,7 +346,12 @@ __global__ void __launch_bounds__(1024) l1_norm_kernel(const float* x, int64_t n
 static int64_t head_workspace_bytes(int64_t batch, int64_t dim, int64_t members) {
   int64_t n_cta = ceil_div(batch, kRows);
   int64_t n_out = 1 + dim + members * dim;
-  return align_up(n_cta * n_out * (int64_t)sizeof(float), 256);
+  return align_up((n_cta + 1) * n_out * (int64_t)sizeof(float), 256);   // + one row for the two-level finalize
+}
+
+static size_t head_smem_bytes(int dim, int members) {
+  const int wr = dim > members ? dim : members;
+  return ((size_t)(members + 1) * kRows * dim + (size_t)(kRows / 32) * wr) * sizeof(float);
 }
 
 static int run_head(HeadParams& p, void* ws, int64_t ws_bytes, cudaStream_t st) {
@@ -311,17 +368,40 @@ static int run_head(HeadParams& p, void* ws, int64_t ws_bytes, cudaStream_t st) 
                 (long long)head_workspace_bytes(p.batch, p.dim, p.n_members));
   p.part = reinterpret_cast<float*>(ws);
   const int n_cta = (int)ceil_div(p.batch, kRows);
-  const size_t smem = (size_t)(2 * kRows * p.dim + kRows) * sizeof(float);
-  ensemble_head_kernel<<<n_cta, kRows, smem, st>>>(p);
+  p.n_cta = n_cta;
+  const size_t smem = head_smem_bytes(p.dim, p.n_members);
+  if (smem > 227 * 1024)
+    return fail(ADN_ERR_UNSUPPORTED, "head: n_members*dim = %d*%d does not fit shared memory", p.n_members, p.dim);
+  switch (p.dim) {
+    case 1: ensemble_head_kernel<1><<<n_cta, kRows, smem, st>>>(p); break;
+    case 2: ensemble_head_kernel<2><<<n_cta, kRows, smem, st>>>(p); break;
+    case 3: ensemble_head_kernel<3><<<n_cta, kRows, smem, st>>>(p); break;
+    case 4: ensemble_head_kernel<4><<<n_cta, kRows, smem, st>>>(p); break;
+    case 10: ensemble_head_kernel<10><<<n_cta, kRows, smem, st>>>(p); break;
+    case 16: ensemble_head_kernel<16><<<n_cta, kRows, smem, st>>>(p); break;
+    default: ensemble_head_kernel<0><<<n_cta, kRows, smem, st>>>(p); break;
+  }
   ADN_CHECK_LAUNCH("ensemble_head");
-  ensemble_finalize_kernel<<<1, 256, 0, st>>>(p, n_cta);
+  if (n_cta > 512) {
+    // many CTAs (large batches): one block per output sums its partials first, the finalize then sees one row
+    const int n_red = p.want_grads ? (1 + p.dim + ((p.mixture == ADN_MIX_MATRIX || p.colsum_only) ? 0 : p.n_members * wdim)) : 1;
+    float* red = p.part + (size_t)n_cta * p.n_out;
+    head_partials_kernel<<<n_red, 256, 0, st>>>(p.part, red, n_cta);
+    ADN_CHECK_LAUNCH("head_partials");
+    ensemble_finalize_kernel<<<1, 256, 0, st>>>(p, red, 1);
+  } else {
+    ensemble_finalize_kernel<<<1, 256, 0, st>>>(p, p.part, n_cta);
+  }
   ADN_CHECK_LAUNCH("ensemble_finalize");
   return ADN_OK;
 }
 
 int heads_init() {
-  ADN_CUDA(cudaFuncSetAttribute(ensemble_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((2 * kRows * kMaxDim + kRows) * sizeof(float))));
+#define ADN_HEAD_ATTR(CT) \
+  ADN_CUDA(cudaFuncSetAttribute(ensemble_head_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+  ADN_HEAD_ATTR(0); ADN_HEAD_ATTR(1); ADN_HEAD_ATTR(2); ADN_HEAD_ATTR(3); ADN_HEAD_ATTR(4); ADN_HEAD_ATTR(10);
+  ADN_HEAD_ATTR(16);
+#undef ADN_HEAD_ATTR
   return ADN_OK;
 }
 

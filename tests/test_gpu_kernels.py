@@ -151,6 +151,7 @@ def test_head_loss(gpu, head, B, C):
 @pytest.mark.parametrize("B,C,N,use_bias,lam,beta,mult", [
     (256, 10, 1, False, 0.0, 0.0, 2.0), (1000, 10, 2, False, 0.01, 0.001, 2.0), (4096, 10, 5, True, 0.1, 0.01, 2.0),
     (333, 3, 3, True, 0.05, 0.0, 1.0), (128, 16, 4, False, 0.0, 0.5, 2.0),
+    (70001, 10, 3, True, 0.01, 0.001, 2.0),     # > 512 CTAs: two-level finalize, ragged last CTA
 ])
 def test_ensemble_head(gpu, mix, B, C, N, use_bias, lam, beta, mult):
   import torch
