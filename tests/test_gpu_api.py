@@ -177,8 +177,8 @@ def test_autoensemble_linear_plus_dnn(env):
   from adanet_b200 import graph, train
   x, y = _data(orc)
   cols = [graph.numeric_column("x", D)]
-  pool = {"linear": adanet.estimators.LinearEstimator(cols, train.GradientDescentOptimizer(0.05)),
-          "dnn": adanet.estimators.DNNEstimator(cols, [32, 16], train.GradientDescentOptimizer(0.05))}
+  pool = {"linear": adanet.estimators.LinearEstimator(cols, train.GradientDescentOptimizer(0.05), seed=11),
+          "dnn": adanet.estimators.DNNEstimator(cols, [32, 16], train.GradientDescentOptimizer(0.05), seed=12)}
   est = adanet.AutoEnsembleEstimator(head=adanet.heads.MultiClassHead(C), candidate_pool=pool, max_iteration_steps=15,
                                      max_iterations=1, debug=True)
   est.train(_input_fn(x, y), max_steps=15)
