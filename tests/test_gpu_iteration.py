@@ -60,6 +60,9 @@ CONFIGS = {
                      opt=("momentum", 0.005, 0.9),
                      ens=dict(optimizer=("momentum", 0.005, 0.9), adanet_lambda=0.01, adanet_beta=0.001,
                               use_bias=True, mixture_weight_type="vector")),
+    # BASELINE configs[4] shape in small: depth 1..8 in one iteration (mixed-depth layer waves, deep dZ ping-pong)
+    "deep": dict(data=("tabular", 8192, 100, 10, 31), cfgs=[(1, 32), (8, 32), (4, 48), (6, 24), (2, 40)], B=256, steps=25,
+                 iters=2, opt=("sgd", 0.01), ens=ENS),
     # MATRIX mixture weights (weighted.py:424-453): W_k [D_k, C] from zeros on every member's last layer, with bias
     "matrix": dict(data=("tabular", 8192, 100, 10, 77), cfgs=[(1, 64), (2, 96)], B=256, steps=30, iters=2,
                    opt=("sgd", 0.02),
