@@ -59,7 +59,13 @@ static constexpr int EPI_STAGE_FLOATS = 32 * 32;      // per epilogue warp: 32x3
 static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
 static constexpr int BAR_BYTES = 256;
 static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // CTA-pair kernel: 8 epilogue warps x 128 columns
+// single-CTA kernel: 16 epilogue warps x 32 columns (TMEM lane quadrant = warp % 4, column group = (warp-2)/4):
+// the short-K layer waves are bound by epilogue latency per warp, so thread-level parallelism is what helps;
+// each warp stages 32x16 floats (2 KB) at a time to stay inside the 32 KB left beside the 3-stage ring.
+static constexpr int EPI_WARPS1 = 16;
+static constexpr int NUM_THREADS1 = 64 + 32 * EPI_WARPS1;
+static constexpr int EPI_STAGE_FLOATS1 = 32 * 16;
 static constexpr int TMEM_COLS = 512;                 // two chunk buffers of [H: 128 | S: 128] columns (pair kernel: H 256 | S 256)
 static constexpr int MAX_SPLITS = 64;
 
@@ -72,6 +78,7 @@ struct GemmParams {
   int kb_per_split;
   int a_mn, b_mn;        // operand majorness (0 = K-major box, 1 = MN-major box)
   int out_planes;        // 1: result written as split planes (out / out_lo / out_bits), 0: dense fp32
+  int m_fastest;         // work-item order: 1 = row blocks fastest (write locality), 0 = column blocks fastest (A reuse in L2)
   // output: dense row-major (ldc) / split-K partial [split][M][N], or planes
   float* out;            // dense base | hi plane base
   float* out_lo;         // lo plane base (OUT_PLANES)
@@ -217,9 +224,15 @@ __device__ __forceinline__ Item decode_item(const GemmParams& g, int item) {
   const int tiles = g.tiles_m * g.tiles_n;
   it.split = item / tiles;
   const int t = item - it.split * tiles;
-  const int tm = t / g.tiles_n;
-  it.m0 = tm * BM;
-  it.n0 = (t - tm * g.tiles_n) * BN;
+  if (g.m_fastest) {            // consecutive items = consecutive row blocks of the same column block
+    const int tn = t / g.tiles_m;
+    it.n0 = tn * BN;
+    it.m0 = (t - tn * g.tiles_m) * BM;
+  } else {
+    const int tm = t / g.tiles_n;
+    it.m0 = tm * BM;
+    it.n0 = (t - tm * g.tiles_n) * BN;
+  }
   it.kb0 = it.split * g.kb_per_split;
   it.nkb = min(g.total_kb, it.kb0 + g.kb_per_split) - it.kb0;
   return it;
@@ -230,12 +243,13 @@ __device__ __forceinline__ Item decode_item(const GemmParams& g, int item) {
 // transposes through `stage` (16 B chunks XOR-swizzled by row: conflict-free both ways) and writes with
 // lane = 4-column group of 4 rows, so every global access covers whole 128 B lines (planes: one contiguous
 // 512 B run per instruction).  Shared by the 1-CTA and the CTA-pair kernels.
-template <int EPI>
+template <int EPI, int SW>     // SW = staged columns per pass: 32 (4 KB per warp) or 16 (2 KB per warp, two passes)
 __device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_PLANES, float* a, uint32_t mwq, float* stage,
                                            int lane, int mrow0, int cbase, int rows_ok, float* dense, bool dense_vec) {
-  const int cc = lane & 7;                 // 16 B chunk (4 columns) this lane owns after the transpose
-  const int c4 = cc * 4;
-  const int rsub = lane >> 3;
+  constexpr int CH = SW / 4;               // 16 B chunks per staged row
+  constexpr int RPI = 32 / CH;             // rows covered by one transposed instruction (4 or 8)
+  const int cc = lane % CH;                // 16 B chunk (4 columns) this lane owns after the transpose
+  const int rsub = lane / CH;
   const int my_row = mrow0 + lane;
   const int kbo = cbase >> 5;
   const bool live = (OUT_PLANES ? (kbo < g.out_nkb) : (cbase < g.N)) && rows_ok > 0;   // warp-uniform
@@ -280,64 +294,73 @@ __device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_P
         if (!((keep >> j) & 1u)) a[j] = 0.f;
     }
   }
-  {
-    float4* srow = reinterpret_cast<float4*>(stage + lane * 32);
+  // chunk swizzle by row: both the row-wise float4 writes and the transposed float4 reads are bank-conflict free
+#define ADN_SWZ(r) (SW == 32 ? ((r) & 7) : (((r) >> 1) & 3))
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj)
-      srow[jj ^ (lane & 7)] = make_float4(a[4 * jj], a[4 * jj + 1], a[4 * jj + 2],
-                                          a[4 * jj + 3]);
-  }
-  __syncwarp();
-  if (live) {
-    const int col = cbase + c4;
-    float cs[4] = {0.f, 0.f, 0.f, 0.f};
-    float* hp = OUT_PLANES ? g.out + ((size_t)kbo * g.M + mrow0 + rsub) * 32 + c4 : nullptr;
-    float* lp = OUT_PLANES ? g.out_lo + ((size_t)kbo * g.M + mrow0 + rsub) * 32 + c4 : nullptr;
+  for (int h = 0; h < 32 / SW; ++h) {
+    {
+      float4* srow = reinterpret_cast<float4*>(stage + lane * SW);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rsub + 4 * i;
-      const bool rv = r < rows_ok;
-      float4 t = reinterpret_cast<const float4*>(stage + r * 32)[cc ^ (r & 7)];
-      float v[4] = {t.x, t.y, t.z, t.w};
-      if (EPI == EPI_MASK) {
+      for (int jj = 0; jj < CH; ++jj)
+        srow[jj ^ ADN_SWZ(lane)] = make_float4(a[h * SW + 4 * jj], a[h * SW + 4 * jj + 1], a[h * SW + 4 * jj + 2],
+                                               a[h * SW + 4 * jj + 3]);
+    }
+    __syncwarp();
+    if (live) {
+      const int c4 = h * SW + cc * 4;       // column offset inside the 32-column slice
+      const int col = cbase + c4;
+      if (SW == 16) { cs[0] = cs[1] = cs[2] = cs[3] = 0.f; }
+      float* hp = OUT_PLANES ? g.out + ((size_t)kbo * g.M + mrow0 + rsub) * 32 + c4 : nullptr;
+      float* lp = OUT_PLANES ? g.out_lo + ((size_t)kbo * g.M + mrow0 + rsub) * 32 + c4 : nullptr;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cs[k] += rv ? v[k] : 0.f;
-      }
-      if (rv) {
-        if (OUT_PLANES) {
-          float h[4], l[4];
+      for (int i = 0; i < 32 / RPI; ++i) {
+        const int r = rsub + RPI * i;
+        const bool rv = (rows_ok == 32) || (r < rows_ok);
+        float4 t = reinterpret_cast<const float4*>(stage + r * SW)[cc ^ ADN_SWZ(r)];
+        float v[4] = {t.x, t.y, t.z, t.w};
+        if (EPI == EPI_MASK) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) split_tf32(v[k], h[k], l[k]);
-          *reinterpret_cast<float4*>(hp + i * 128) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(lp + i * 128) = make_float4(l[0], l[1], l[2], l[3]);
-        } else {
-          float* op = dense + (size_t)(mrow0 + r) * g.ldc + col;
-          if (dense_vec && col + 3 < g.N) {
-            *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+          for (int k = 0; k < 4; ++k) cs[k] += rv ? v[k] : 0.f;
+        }
+        if (rv) {
+          if (OUT_PLANES) {
+            float hh[4], ll[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_tf32(v[k], hh[k], ll[k]);
+            *reinterpret_cast<float4*>(hp + i * RPI * 32) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(lp + i * RPI * 32) = make_float4(ll[0], ll[1], ll[2], ll[3]);
           } else {
+            float* op = dense + (size_t)(mrow0 + r) * g.ldc + col;
+            if (dense_vec && col + 3 < g.N) {
+              *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (col + k < g.N) op[k] = v[k];
+              for (int k = 0; k < 4; ++k)
+                if (col + k < g.N) op[k] = v[k];
+            }
           }
         }
       }
-    }
-    if (EPI == EPI_MASK && g.colsum_part) {
-      // rows of this lane: rsub + 4i; fold the 4 row groups (lanes l, l^8, l^16, l^24) in a fixed order
+      if (EPI == EPI_MASK && g.colsum_part) {
+        // rows of this lane: rsub + RPI*i; fold the lanes that own the same columns in a fixed order
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
-        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
-      }
-      if (rsub == 0) {
-        float* cp = g.colsum_part + (size_t)(mrow0 >> 5) * g.colsum_ld + col;
+        for (int k = 0; k < 4; ++k) {
+          if (SW == 16) cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 4);
+          cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+          cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+        }
+        if (rsub == 0) {
+          float* cp = g.colsum_part + (size_t)(mrow0 >> 5) * g.colsum_ld + col;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (col + k < g.colsum_ld) cp[k] = cs[k];
+          for (int k = 0; k < 4; ++k)
+            if (col + k < g.colsum_ld) cp[k] = cs[k];
+        }
       }
     }
+    __syncwarp();
   }
-  __syncwarp();
+#undef ADN_SWZ
 }
 
 // ---------------------------------------------------------------------------------
@@ -369,7 +392,7 @@ __device__ __forceinline__ int find_problem(const Group& grp, int cur, int item)
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS1, 1)
 pl_gemm_kernel(const __grid_constant__ Group grp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -400,7 +423,7 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(smem_u32(&acc_full[b]), 1);
-        mbar_init(smem_u32(&acc_empty[b]), EPI_WARPS);
+        mbar_init(smem_u32(&acc_empty[b]), EPI_WARPS1);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -497,15 +520,15 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
       }
     }
   } else {
-    // ================= epilogue warps 2..9 =================
+    // ================= epilogue warps 2..17 =================
     const int quad = warp & 3;                       // TMEM lane quadrant a warp may read = warp % 4
-    const int half = (warp - 2) >> 2;                // which 64 of the tile's 128 columns
+    const int cgrp = (warp - 2) >> 2;                // which 32 of the tile's 128 columns
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const uint32_t col_base = (uint32_t)(half * EPI_COLS);
-    float* stage = epi_stage + (warp - 2) * EPI_STAGE_FLOATS;
-    uint32_t gchunk = 0, tile_i = 0;
+    const uint32_t col_base = (uint32_t)(cgrp * 32);
+    float* stage = epi_stage + (warp - 2) * EPI_STAGE_FLOATS1;
+    uint32_t gchunk = 0;
     int cur = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       cur = find_problem(grp, cur, item);
       const GemmParams& g = grp.p[cur].g;
       const Item it = decode_item(g, item - grp.p[cur].item0);
@@ -513,17 +536,14 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
       const int ncol0 = it.n0 + (int)col_base;        // first output column of this warp
       const int my_row = mrow0 + lane;
       // ReLU mask: one sign-bit word per (row, 32-column block), fetched before the accumulators are awaited
-      uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
+      uint32_t mw = 0xffffffffu;
       if (EPI == EPI_MASK && g.mask_bits) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int kbo = (ncol0 >> 5) + q;
-          mw[q] = (my_row < g.M && kbo < g.out_nkb) ? __ldg(g.mask_bits + (size_t)kbo * g.M + my_row) : 0u;
-        }
+        const int kbo = ncol0 >> 5;
+        mw = (my_row < g.M && kbo < g.out_nkb) ? __ldg(g.mask_bits + (size_t)kbo * g.M + my_row) : 0u;
       }
-      float acc[EPI_COLS];
+      float acc[32];
 #pragma unroll
-      for (int j = 0; j < EPI_COLS; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
       const int nchunks = (it.nkb + CHUNK - 1) / CHUNK;
       for (int c = 0; c < nchunks; ++c, ++gchunk) {
         const uint32_t b = gchunk & 1;
@@ -531,40 +551,25 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
         tc_fence_after();
         {
           uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + col_base, r0);
-          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + col_base + 32, r1);
+          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + col_base, r0);          // hi*hi partial sums of this chunk
+          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + 128 + col_base, r1);    // cross terms of this chunk
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {          // fp32 RN adds: hi*hi partial sums of this 128-K chunk
-            acc[j] += __uint_as_float(r0[j]);
-            acc[32 + j] += __uint_as_float(r1[j]);
-          }
-          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + 128 + col_base, r0);
-          tmem_ld32_nowait(tmem_base + lane_base + b * 256 + 128 + col_base + 32, r1);
-          tmem_ld_wait();
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r0[j]);   // fp32 RN adds
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {          // cross terms of the chunk
-            acc[j] += __uint_as_float(r0[j]);
-            acc[32 + j] += __uint_as_float(r1[j]);
-          }
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r1[j]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&acc_empty[b]));
       }
-      // ---- tile output.  Each warp owns rows [mrow0, mrow0+32) x 64 columns, processed as two 32x32
-      // slices: registers (lane = row; bias/ReLU/mask and sign bits here) -> smem (16 B chunks XOR-swizzled
-      // by row, so both the row-wise float4 writes and the transposed float4 reads are conflict-free) ->
-      // (lane = 4-column group of 4 rows) so that every global access of the warp covers whole 128 B
-      // lines (planes: one contiguous 512 B run per instruction).
+      // ---- tile output: this warp's 32 rows x 32 columns (one plane row segment of 128 B per row) ----
       float* dense = g.out;
       if (EPI == EPI_PARTIAL) dense += (size_t)it.split * g.M * g.N;
       const bool out_planes = g.out_planes != 0;
       const bool dense_vec = !out_planes && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
       const int rows_ok = min(32, g.M - mrow0);          // warp-uniform; <= 0: nothing to write
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        emit_slice<EPI>(g, out_planes, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
+      emit_slice<EPI, 16>(g, out_planes, acc, mw, stage, lane, mrow0, ncol0, rows_ok, dense, dense_vec);
     }
   }
   tc_fence_before();
@@ -901,7 +906,7 @@ pl_gemm2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int rows_ok = min(32, g.M - mrow0);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          emit_slice<EPI>(g, OUT_PLANES != 0, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
+          emit_slice<EPI, 32>(g, OUT_PLANES != 0, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
       }
     }
   }
@@ -1097,6 +1102,15 @@ static int launch_pair(const GemmDesc& d, cudaStream_t st, const char* what) {
   return ADN_OK;
 }
 
+// Work-item order of one problem.  Column blocks fastest lets the CTAs that run together share the A tile through
+// L2 (A is the big operand of the long-K layers); row blocks fastest makes them write adjacent 16 KB runs of the
+// same output k-block slab.  ADN_PL_MFAST: -1 heuristic (default), 0 / 1 force.
+static int item_order_m_fastest(const GemmParams& g) {
+  static const int env = getenv("ADN_PL_MFAST") ? atoi(getenv("ADN_PL_MFAST")) : -1;
+  if (env >= 0) return env;
+  return 0;
+}
+
 // n independent GEMMs of the same epilogue kind -> ceil(n / MAX_GROUP) persistent launches
 template <int EPI>
 static int launch_group(const GemmDesc* d, int n, cudaStream_t st, const char* what) {
@@ -1121,13 +1135,14 @@ static int launch_group(const GemmDesc* d, int n, cudaStream_t st, const char* w
       pr.g.b_mn = d[i0 + i].b.mn_major;
       pr.g.tiles_m = (int)ceil_div(pr.g.M, BM);
       pr.g.tiles_n = (int)ceil_div(pr.g.N, BN);
+      pr.g.m_fastest = item_order_m_fastest(pr.g);
       pr.item0 = items;
       items += pr.g.tiles_m * pr.g.tiles_n * pr.g.splits;
     }
     grp.n = m;
     grp.total_items = items;
     const int grid = std::min(items, sm_count());
-    pl_gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(grp);
+    pl_gemm_kernel<EPI><<<grid, NUM_THREADS1, SMEM_BYTES, st>>>(grp);
     ADN_CHECK_LAUNCH(what);
   }
   return ADN_OK;
