@@ -97,6 +97,7 @@ class EnsemblerPlanSpec:
   use_bias: bool = False
   name: str = "complexity_regularized"
   legacy_train_op: bool = False
+  warm_start_mixture_weights: bool = False   # weighted.py:270-285,487-516
 
 
 def _opt_hyper(spec: tuple) -> Tuple[int, List[float]]:
@@ -260,7 +261,7 @@ class CandidatePlan:
 
   def __init__(self, lib, spec: SubnetworkPlanSpec, frozen: Sequence[DenseNet], ens: EnsemblerPlanSpec,
                iteration: int, batch: int, logits_dim: int, head: str, decay: float, trace_capacity: int,
-               device: torch.device, index: int):
+               device: torch.device, index: int, prev_mixture_weights=None, prev_bias=None):
     self.lib, self.spec, self.ens, self.index = lib, spec, ens, index
     self.batch, self.C, self.head = batch, logits_dim, _HEAD_KIND[head]
     self.name = "t{}_{}_grow_{}".format(iteration, spec.name, ens.name)   # iteration.py:633,691-693
@@ -323,6 +324,21 @@ class CandidatePlan:
       wshape = (n_members,) if self.mix == _lib.MIX_SCALAR else (n_members, logits_dim)
       self.mix_w = torch.full(wshape, 1.0 / n_members, **f32)
     self.bias = torch.zeros((logits_dim,), **f32)
+    if ens.warm_start_mixture_weights and prev_mixture_weights is not None and len(frozen) > 0:
+      # kept members and the bias start from the previous ensemble's trained values (weighted.py:270-285,487-516);
+      # the new member keeps the default initialiser for the grown member count
+      nf = len(frozen)
+      if self.mix == _lib.MIX_MATRIX:
+        sp0 = torch.cuda.current_stream(device).cuda_stream
+        for k in range(nf):
+          self.mw[k].copy_(torch.as_tensor(np.ascontiguousarray(prev_mixture_weights[k], dtype=np.float32)))
+          _lib.check(lib.adn_planes_split(self.mw[k].data_ptr(), self.mw[k].shape[0], self.mw[k].shape[1],
+                                          self.mwp[k].data_ptr(), sp0), "adn_planes_split")
+      else:
+        prev = torch.as_tensor(np.ascontiguousarray(prev_mixture_weights, dtype=np.float32)).to(device)
+        self.mix_w[:nf] = prev.reshape((nf,) + tuple(self.mix_w.shape[1:]))
+      if prev_bias is not None:
+        self.bias.copy_(torch.as_tensor(np.ascontiguousarray(prev_bias, dtype=np.float32)).reshape(logits_dim))
     self.d_mix_w = torch.zeros_like(self.mix_w)
     self.d_bias = torch.zeros((logits_dim,), **f32)
     self.complexities = [f.complexity for f in frozen] + [spec.complexity]
@@ -513,7 +529,7 @@ class IterationPlan:
                ens: EnsemblerPlanSpec, batch: int, in_dim: int, logits_dim: int, head: str = "softmax_xent",
                adanet_loss_decay: float = 0.9, trace_capacity: int = 4096, device: Optional[torch.device] = None,
                candidate_indices: Optional[Sequence[int]] = None, use_cuda_graph: bool = True,
-               multi_stream: bool = True):
+               multi_stream: bool = True, prev_mixture_weights=None, prev_bias=None):
     self.lib = _require_cuda()
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.iteration, self.batch, self.in_dim, self.C, self.head = iteration, batch, in_dim, logits_dim, head
@@ -523,7 +539,8 @@ class IterationPlan:
         raise ValueError("frozen member %s was built for batch %d, plan uses %d" % (f.name, f.batch, batch))
     idx = list(candidate_indices) if candidate_indices is not None else list(range(len(specs)))
     self.candidates = [CandidatePlan(self.lib, s, self.frozen, ens, iteration, batch, logits_dim, head,
-                                     adanet_loss_decay, trace_capacity, self.device, i)
+                                     adanet_loss_decay, trace_capacity, self.device, i,
+                                     prev_mixture_weights=prev_mixture_weights, prev_bias=prev_bias)
                        for i, s in zip(idx, specs)]
     self.x = torch.empty((batch, in_dim), dtype=torch.float32, device=self.device)
     # split planes of the minibatch, produced once per step and shared by every member and candidate

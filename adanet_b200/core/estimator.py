@@ -46,6 +46,13 @@ class RunConfig:
     self.is_chief = is_chief if is_chief is not None else (self.global_id_in_cluster == 0)
 
 
+class _RestoredBuilder:
+  """Stands in for the builder of a member restored from a checkpoint (strategies only count / name them)."""
+
+  def __init__(self, name):
+    self.name = name
+
+
 class Estimator(object):
   """An AdaNet estimator: learns an ensemble of subnetworks over iterations.
 
@@ -148,11 +155,9 @@ class Estimator(object):
       raise NotImplementedError("MeanEnsembler is a 'next' row (SURVEY.md 8f.3); use ComplexityRegularizedEnsembler")
     if not isinstance(e, ensemble_lib.ComplexityRegularizedEnsembler):
       raise NotImplementedError("custom Ensemblers are not supported by the B200 engine: %r" % (e,))
-    if e.warm_start_mixture_weights:
-      raise NotImplementedError("warm_start_mixture_weights is a 'next' row (SURVEY.md 8f.3)")
     return eng.EnsemblerPlanSpec(optimizer=train_lib.optimizer_from(e.optimizer), mixture_weight_type=e.mixture_weight_type,
                                  adanet_lambda=e.adanet_lambda, adanet_beta=e.adanet_beta, use_bias=e.use_bias,
-                                 name=e.name)
+                                 name=e.name, warm_start_mixture_weights=bool(e.warm_start_mixture_weights))
 
   def _check_strategies(self):
     for s in self._ensemble_strategies:
@@ -216,6 +221,68 @@ class Estimator(object):
                                      adanet_loss_decay=self._adanet_loss_decay, force_grow=self._force_grow,
                                      replay_indices=replay, keep_traces=bool(self._debug))
 
+  def _maybe_restore(self):
+    """Continues from `model_dir/ensemble-latest.{npz,json}` (written at every iteration boundary): frozen
+    members, mixture weights, selection state and step counters -- what the reference restores from
+    `increment.ckpt-{t}` + `architecture-{t}.json` when an Estimator is re-created on the same model_dir
+    (adanet/core/estimator.py:951-984)."""
+    from adanet_b200 import subnetwork as subnetwork_lib
+    from adanet_b200.core import engine as eng
+    path = self.latest_checkpoint()
+    meta_path = os.path.join(self._model_dir, "ensemble-latest.json") if self._model_dir else None
+    if not path or not meta_path or not os.path.exists(meta_path) or self._search.iteration > 0:
+      return False
+    with open(meta_path) as f:
+      meta = json.load(f)
+    if int(meta["batch_size"]) != int(self._batch_size) or {k: int(v) for k, v in meta["feature_widths"].items()} != \
+        {k: int(v) for k, v in self._feature_widths.items()}:
+      raise ValueError("model_dir %s holds a checkpoint for batch size %s / features %s, input_fn yields %s / %s" % (
+          self._model_dir, meta["batch_size"], meta["feature_widths"], self._batch_size, self._feature_widths))
+    data = np.load(path)
+    s = self._search
+    members = []
+    for k, m in enumerate(meta["members"]):
+      n_layers = len(m["dims"]) - 1
+      ws = [data["m{}_w{}".format(k, i)] for i in range(n_layers)]
+      bs = [data["m{}_b{}".format(k, i)] for i in range(n_layers)]
+      members.append(eng.DenseNet(m["name"], m["dims"], ws, bs, m["complexity"], s.batch, s.device, m["iteration"],
+                                  m["shared"]))
+    s.frozen = members
+    s.iteration = int(meta["iteration"])
+    s.architecture = [(int(t), n) for t, n in meta["architecture"]]
+    s.replay_trace = list(meta["replay_trace"])
+    s.prev_best_ema = meta["prev_best_ema"]
+    if "mixture_weights" in data:
+      s.mixture_weights = data["mixture_weights"]
+    else:
+      s.mixture_weights = [data["mixture_weight_{}".format(k)] for k in range(len(members))]
+    s.bias = data["bias"]
+    self._global_step = int(meta["global_step"])
+    self._last_candidate_name = meta["last_candidate_name"]
+    # previous_ensemble for the generator: symbolic subnetworks carrying complexity + shared (what builders read)
+    ens = self._ensemblers[0]
+    self._member_subnetworks, self._member_builders, ws_list = [], [], []
+    mw = s.mixture_weights
+    for k, m in enumerate(meta["members"]):
+      lg = graph.placeholder(s.C, "restored_logits_{}".format(k))
+      sub = subnetwork_lib.Subnetwork(last_layer=graph.placeholder(m["dims"][-2], "restored_last_layer_{}".format(k)),
+                                      logits=lg, complexity=m["complexity"], shared=m["shared"])
+      self._member_subnetworks.append(sub)
+      self._member_builders.append(_RestoredBuilder(m["name"]))
+      ws_list.append(ensemble_lib.WeightedSubnetwork(name=m["name"], iteration_number=m["iteration"],
+                                                     weight=np.array(mw[k]), logits=lg, subnetwork=sub))
+    self._previous_ensemble = ensemble_lib.ComplexityRegularized(
+        weighted_subnetworks=ws_list, bias=np.asarray(s.bias), logits=("weighted_sum", [w.logits for w in ws_list]),
+        subnetworks=[w.subnetwork for w in ws_list],
+        complexity_regularization=ens.complexity_regularization([w.weight for w in ws_list],
+                                                                [w.subnetwork.complexity for w in ws_list]))
+    arch = _Architecture(self._last_candidate_name, ens.name, replay_indices=list(s.replay_trace))
+    for t, n in s.architecture:
+      arch.add_subnetwork(t, n)
+    self._architecture = arch
+    logging.info("restored iteration %d (global step %d) from %s", s.iteration, self._global_step, path)
+    return True
+
   # ------------------------------------------------------------------ train
   def train(self, input_fn, hooks=None, steps=None, max_steps=None, saving_listeners=None):
     """Trains for `steps` more steps or until `max_steps` global steps
@@ -242,7 +309,13 @@ class Estimator(object):
         break
       if limit is not None and self._global_step >= limit:
         break
-      self._ensure_search(features)
+      if self._search is None:
+        self._ensure_search(features)
+        if self._maybe_restore() and steps is not None:
+          limit = self._global_step + steps        # `steps` counts from the restored global step
+        if (self._max_iterations and done_iterations() >= self._max_iterations) or (
+            limit is not None and self._global_step >= limit):
+          break
       bs = input_utils.batch_size_of(features)
       if bs != self._batch_size:
         input_utils.warn_ragged(bs, self._batch_size)
@@ -329,6 +402,21 @@ class Estimator(object):
         out["m{}_w{}".format(k, i)] = w
         out["m{}_b{}".format(k, i)] = b
     np.savez(os.path.join(self._model_dir, "ensemble-latest.npz"), **out)
+    # everything else a fresh process needs to continue from this iteration boundary (the reference keeps it in
+    # the TF checkpoint + architecture-{t}.json, adanet/core/estimator.py:1357-1413)
+    meta = {
+        "global_step": int(self._global_step), "iteration": int(s.iteration),
+        "batch_size": int(self._batch_size), "feature_widths": self._feature_widths,
+        "architecture": [[int(t), n] for t, n in s.architecture], "replay_trace": [int(v) for v in s.replay_trace],
+        "prev_best_ema": None if s.prev_best_ema is None else float(s.prev_best_ema),
+        "last_candidate_name": self._last_candidate_name,
+        "members": [{"name": m.name, "iteration": int(m.iteration), "complexity": float(m.complexity),
+                     "dims": [int(d) for d in m.dims], "shared": m.shared} for m in s.frozen],
+    }
+    tmp = os.path.join(self._model_dir, "ensemble-latest.json.tmp")
+    with open(tmp, "w") as f:
+      json.dump(meta, f)
+    os.replace(tmp, os.path.join(self._model_dir, "ensemble-latest.json"))
 
   # ------------------------------------------------------------------ evaluate / predict
   def _ensemble_eval_plan(self):

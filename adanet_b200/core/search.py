@@ -112,7 +112,8 @@ class AdaNetSearch:
     self.plan = eng.IterationPlan(self.iteration, [specs[i] for i in mine], self.frozen, self.ens, self.batch,
                                   self.in_dim, self.C, self.head, self.decay, self.trace_capacity, self.device,
                                   candidate_indices=mine, use_cuda_graph=self.use_cuda_graph,
-                                  multi_stream=self.multi_stream)
+                                  multi_stream=self.multi_stream, prev_mixture_weights=self.mixture_weights,
+                                  prev_bias=self.bias)
     return self.plan
 
   def train_iteration(self, batches: Iterator, steps: int) -> float:

@@ -24,12 +24,12 @@
 // stay in TMEM for 128 K only and are then added in registers with RN
 // (profiles/r1a_accuracy_probe_*.txt); cross terms use their own accumulator.
 //
-// Kernel: persistent, one CTA per SM, 320 threads, warp-specialised
+// Kernel: persistent, one CTA per SM, 576 threads, warp-specialised, grouped (up to 8 GEMMs per launch)
 //   warp 0    TMA producer (3-stage ring, 64 KiB per stage: A_hi A_lo B_hi B_lo)
-//   warp 1    MMA issuer (elected lane; 12 x tcgen05.mma.kind::tf32 M128 N128 K8 per stage)
-//   warps 2-9 epilogue (TMEM lane quadrant = warp % 4, column half = (warp-2)/4, 64 accumulators each):
-//             tcgen05.ld -> registers (bias/ReLU + sign bits | sign-bit mask) -> per-warp smem
-//             transpose -> column sums -> hi/lo split -> coalesced 512 B stores
+//   warp 1    MMA issuer (elected lane; per K=8 step one N=256 MMA a_hi x [b_hi|b_lo] + one N=128 MMA a_lo x b_hi)
+//   warps 2-17 epilogue (TMEM lane quadrant = warp % 4, column group = (warp-2)/4, 32 accumulators each):
+//             tcgen05.ld -> registers (bias/ReLU + sign bits | sign-bit mask) -> per-warp swizzled smem
+//             transpose -> column sums -> hi/lo split -> stores that cover whole 32 B sectors of 8 rows
 //
 // Reference arithmetic replaced: tf.layers.dense and its gradients,
 //   adanet/examples/simple_dnn.py:72-86,103-110.
@@ -54,7 +54,6 @@ static constexpr int CHUNK = 4;                       // k-blocks per TMEM accum
 static constexpr int TILE_BYTES = 128 * BK * 4;       // 16 KiB
 static constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi A_lo B_hi B_lo
 static constexpr int EPI_WARPS = 8;
-static constexpr int EPI_COLS = 64;                   // accumulator columns per epilogue warp
 static constexpr int EPI_STAGE_FLOATS = 32 * 32;      // per epilogue warp: 32x32 slice transposed through smem (swizzled)
 static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
 static constexpr int BAR_BYTES = 256;
@@ -192,18 +191,6 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // hi = rna_tf32(v), lo = rna_tf32(v - hi).  cvt.rna.tf32.f32 is emulated in SASS (add, NaN/Inf test, select,
@@ -473,9 +460,9 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
     // issue loop keeps ring counters incremental and builds descriptors from 32-bit halves.
     {
       const uint32_t smem0 = smem_u32(smem);
-      uint32_t s = 0, ph = 0, gchunk = 0, tile_i = 0;
+      uint32_t s = 0, ph = 0, gchunk = 0;
       int cur = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tile_i) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         cur = find_problem(grp, cur, item);
         const GemmParams& g = grp.p[cur].g;
         const Item it = decode_item(g, item - grp.p[cur].item0);

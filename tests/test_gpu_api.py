@@ -188,3 +188,49 @@ def test_autoensemble_linear_plus_dnn(env):
     assert tr["sub_loss"][-1] < tr["sub_loss"][0]        # both subestimators train
   ev = est.evaluate(_input_fn(x[:B * 2], y[:B * 2]), steps=2)
   assert np.isfinite(ev["loss"]) and ev["loss"] < np.log(C)
+
+
+def test_resume_from_model_dir_matches_uninterrupted_run(env, tmp_path):
+  """A new Estimator on the same model_dir continues from the last iteration boundary (the reference restores
+  increment.ckpt-{t} + architecture-{t}.json, adanet/core/estimator.py:951-984): 2 iterations + restart + 1
+  iteration equals 3 uninterrupted iterations bit for bit (same batches, deterministic kernels)."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  from adanet_b200.examples import simple_dnn
+  x, y = _data(orc)
+  steps = 8
+
+  def make(model_dir):
+    gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
+                               optimizer=train.GradientDescentOptimizer(0.05), layer_size=16, seed=SEED)
+    return adanet.Estimator(
+        head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
+        ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(0.01),
+                                                                   adanet_lambda=0.01, use_bias=True)],
+        max_iterations=3, model_dir=model_dir)
+
+  def input_from(start):       # the reference re-creates input_fn on restart; feed the same batches the long run saw
+    def fn():
+      for i in range(start * B, x.shape[0] - B + 1, B):
+        yield {"x": x[i:i + B]}, y[i:i + B]
+    return fn
+
+  full = make(str(tmp_path / "full"))
+  full.train(input_from(0), max_steps=3 * steps)
+  a = make(str(tmp_path / "resumed"))
+  a.train(input_from(0), max_steps=2 * steps)
+  assert a._search.iteration == 2 and os.path.exists(os.path.join(str(tmp_path / "resumed"), "ensemble-latest.json"))
+  b = make(str(tmp_path / "resumed"))          # fresh process state, same model_dir
+  b.train(input_from(2 * steps), max_steps=3 * steps)
+  assert b._search.iteration == 3 and b._global_step == 3 * steps
+  assert b._search.architecture == full._search.architecture and b._search.replay_trace == full._search.replay_trace
+  np.testing.assert_array_equal(b._search.mixture_weights, full._search.mixture_weights)
+  np.testing.assert_array_equal(b._search.bias, full._search.bias)
+  xe, ye = _data(orc, n=B * 2, seed=99)
+  assert b.evaluate(_input_fn(xe, ye), steps=2)["loss"] == full.evaluate(_input_fn(xe, ye), steps=2)["loss"]
+  assert b.architecture_string() == full.architecture_string()
+  # `steps` counts from the restored global step
+  c = make(str(tmp_path / "resumed"))
+  c._max_iterations = 4
+  c.train(input_from(3 * steps), steps=3)
+  assert c._global_step == 3 * steps + 3

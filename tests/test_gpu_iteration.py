@@ -68,6 +68,15 @@ CONFIGS = {
                    opt=("sgd", 0.02),
                    ens=dict(optimizer=("sgd", 0.02), adanet_lambda=0.01, adanet_beta=0.001, use_bias=True,
                             mixture_weight_type="matrix")),
+    # warm_start_mixture_weights (weighted.py:270-285,487-516): kept members + bias start from the previous ensemble's
+    "warm_start": dict(data=("tabular", 8192, 100, 10, 12), cfgs=[(1, 48), (2, 48)], B=256, steps=25, iters=3,
+                       opt=("sgd", 0.02),
+                       ens=dict(optimizer=("sgd", 0.05), adanet_lambda=0.01, adanet_beta=0.001, use_bias=True,
+                                mixture_weight_type="vector", warm_start_mixture_weights=True)),
+    "warm_start_matrix": dict(data=("tabular", 8192, 100, 10, 13), cfgs=[(1, 48), (2, 48)], B=256, steps=25, iters=2,
+                              opt=("sgd", 0.02),
+                              ens=dict(optimizer=("sgd", 0.02), adanet_lambda=0.01, adanet_beta=0.001, use_bias=True,
+                                       mixture_weight_type="matrix", warm_start_mixture_weights=True)),
     "default_ensembler": dict(data=("tabular", 8192, 100, 10, 99), cfgs=[(1, 64), (2, 64)], B=256, steps=30, iters=2,
                               opt=("sgd", 0.01), ens=dict(optimizer=None)),
     "force_grow": dict(data=("tabular", 8192, 100, 10, 5), cfgs=[(1, 32), (2, 32)], B=256, steps=10, iters=3,
@@ -169,7 +178,7 @@ def _check(o_res, reps, tol=TOL):
 def test_iteration_parity(built_lib, name, path):
   from adanet_b200 import _lib
   cfg = CONFIGS[name]
-  if name == "matrix" and path == "simt":
+  if name in ("matrix", "warm_start_matrix") and path == "simt":
     pytest.skip("MATRIX mixture weights run on the plane path only")
   _lib.set_dense_path(_lib.PATH_SIMT if path == "simt" else _lib.PATH_AUTO)
   try:
