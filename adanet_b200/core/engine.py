@@ -555,6 +555,7 @@ class IterationPlan:
     self.multi_stream = multi_stream and len(self.candidates) > 1
     self.streams = [torch.cuda.Stream(device=self.device) for _ in self.candidates] if self.multi_stream else []
     self._graph = None
+    self._stage = None
     self.launches_per_step = None
 
   # -- staging -------------------------------------------------------------
@@ -568,6 +569,34 @@ class IterationPlan:
       self.labels.copy_(y.reshape(self.batch), non_blocking=True)
     else:
       self.labels_f.copy_(y.reshape(self.batch, self.C), non_blocking=True)
+
+  def stage_batch(self, x, y):
+    """Starts copying the NEXT minibatch into a second set of device buffers on a copy stream, so the
+    host->device transfer of step i+1 runs under the kernels of step i; `train_step()` without arguments then
+    consumes it (device-to-device move into the graph's fixed input buffers).  Pinned host sources copy
+    asynchronously; the staging buffers are only rewritten after the previous staged batch has been consumed."""
+    if self._stage is None:
+      self._stage = dict(
+          x=torch.empty_like(self.x), y=torch.empty_like(self.labels if self.labels is not None else self.labels_f),
+          stream=torch.cuda.Stream(device=self.device), ready=torch.cuda.Event(), consumed=None)
+    st = self._stage
+    with torch.cuda.stream(st["stream"]):
+      if st["consumed"] is not None:
+        st["stream"].wait_event(st["consumed"])
+      st["x"].copy_(torch.as_tensor(x).reshape(self.batch, self.in_dim), non_blocking=True)
+      st["y"].copy_(torch.as_tensor(y).reshape(st["y"].shape), non_blocking=True)
+      st["ready"].record(st["stream"])
+    st["pending"] = True
+
+  def _consume_staged(self):
+    st = self._stage
+    main = torch.cuda.current_stream(self.device)
+    main.wait_event(st["ready"])
+    self.x.copy_(st["x"], non_blocking=True)
+    (self.labels if self.labels is not None else self.labels_f).copy_(st["y"], non_blocking=True)
+    st["consumed"] = torch.cuda.Event()
+    st["consumed"].record(main)
+    st["pending"] = False
 
   # -- one step --------------------------------------------------------------
   def _enqueue_waves(self):
@@ -634,9 +663,12 @@ class IterationPlan:
                  "adn_planes_split")
 
   def train_step(self, x=None, y=None):
-    """One training step of every candidate on this GPU on one minibatch."""
+    """One training step of every candidate on this GPU on one minibatch: the one passed in, or the one
+    started earlier with `stage_batch`."""
     if x is not None:
       self.load_batch(x, y)
+    elif self._stage is not None and self._stage.get("pending"):
+      self._consume_staged()
     if not self.use_cuda_graph:
       before = _lib.launch_count()
       self._enqueue()

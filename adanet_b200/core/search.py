@@ -116,15 +116,23 @@ class AdaNetSearch:
                                   prev_bias=self.bias)
     return self.plan
 
-  def train_iteration(self, batches: Iterator, steps: int) -> float:
-    """Runs `steps` training steps; returns device seconds (CUDA events) of the phase."""
+  def train_iteration(self, batches: Iterator, steps: int, on_step=None) -> float:
+    """Runs `steps` training steps; returns device seconds (CUDA events) of the phase.
+
+    The transfer of batch i+1 is started (copy stream) right after step i is enqueued, so host batches stream
+    in under the kernels; `on_step(plan)` -- e.g. reading the step's losses back -- runs after that."""
     plan = self.plan or self.build_iteration()
     start = torch.cuda.Event(enable_timing=True)
     end = torch.cuda.Event(enable_timing=True)
     start.record()
-    for _ in range(steps):
-      x, y = next(batches)
-      plan.train_step(x, y)
+    if steps > 0:
+      plan.stage_batch(*next(batches))
+    for i in range(steps):
+      plan.train_step()
+      if i + 1 < steps:
+        plan.stage_batch(*next(batches))
+      if on_step is not None:
+        on_step(plan)
     end.record()
     end.synchronize()
     return start.elapsed_time(end) / 1e3
