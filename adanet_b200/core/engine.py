@@ -134,6 +134,24 @@ class _Optimizer:
     self._sizes = _lib.i64_array([p.numel() for p in params])
     self._hyper = _lib.f32_array(self.hyper)
 
+  def state(self) -> Dict[str, np.ndarray]:
+    out = {}
+    for name, slots in (("s0", self.slot0), ("s1", self.slot1)):
+      if slots:
+        for i, t in enumerate(slots):
+          out["%s_%d" % (name, i)] = t.cpu().numpy()
+    if self.step_dev is not None:
+      out["step"] = self.step_dev.cpu().numpy()
+    return out
+
+  def load_state(self, st: Dict[str, np.ndarray]):
+    for name, slots in (("s0", self.slot0), ("s1", self.slot1)):
+      if slots:
+        for i, t in enumerate(slots):
+          t.copy_(torch.as_tensor(st["%s_%d" % (name, i)]))
+    if self.step_dev is not None:
+      self.step_dev.copy_(torch.as_tensor(st["step"]))
+
   def apply(self, lib, grads: List[torch.Tensor], stream_ptr: int):
     g = _lib.ptr_array([t.data_ptr() for t in grads])
     step = self.step_dev.data_ptr() if self.step_dev is not None else None
@@ -432,6 +450,42 @@ class CandidatePlan:
       self.ens_opt.apply(lib, self._ens_grads, sp)
     self.sub_opt.apply(lib, self._grads, sp)
 
+  def state_dict(self) -> Dict[str, np.ndarray]:
+    """Everything that changes while the candidate trains (the reference persists the same through the TF
+    checkpoint: variables, optimizer slots, EMA, per-spec step counters; iteration.py:40-118,172-183)."""
+    out = {}
+    for i, (w, b) in enumerate(zip(self.net.ws, self.net.bs)):
+      out["w%d" % i], out["b%d" % i] = w.cpu().numpy(), b.cpu().numpy()
+    for k, v in self.sub_opt.state().items():
+      out["sub_opt_" + k] = v
+    for i, t in enumerate(self.mixture_weight_tensors()):
+      out["mix%d" % i] = t.cpu().numpy()
+    out["bias"] = self.bias.cpu().numpy()
+    if self.ens_opt is not None:
+      for k, v in self.ens_opt.state().items():
+        out["ens_opt_" + k] = v
+    out["ema_state"] = self.ema_state.cpu().numpy()
+    out["trace"] = self.trace.cpu().numpy()
+    return out
+
+  def load_state_dict(self, st: Dict[str, np.ndarray]):
+    for i, (w, b) in enumerate(zip(self.net.ws, self.net.bs)):
+      w.copy_(torch.as_tensor(st["w%d" % i]))
+      b.copy_(torch.as_tensor(st["b%d" % i]))
+    self.net.refresh_planes()
+    self.sub_opt.load_state({k[len("sub_opt_"):]: v for k, v in st.items() if k.startswith("sub_opt_")})
+    for i, t in enumerate(self.mixture_weight_tensors()):
+      t.copy_(torch.as_tensor(st["mix%d" % i]))
+    if self.mix == _lib.MIX_MATRIX:
+      sp = torch.cuda.current_stream(self.net.device).cuda_stream
+      for w, wp in zip(self.mw, self.mwp):
+        _lib.check(self.lib.adn_planes_split(w.data_ptr(), w.shape[0], w.shape[1], wp.data_ptr(), sp), "adn_planes_split")
+    self.bias.copy_(torch.as_tensor(st["bias"]))
+    if self.ens_opt is not None:
+      self.ens_opt.load_state({k[len("ens_opt_"):]: v for k, v in st.items() if k.startswith("ens_opt_")})
+    self.ema_state.copy_(torch.as_tensor(st["ema_state"]))
+    self.trace.copy_(torch.as_tensor(st["trace"]))
+
   def mixture_weight_tensors(self) -> List[torch.Tensor]:
     """The trained mixture weights as tensors: [w] (SCALAR [N] / VECTOR [N,C]) or the N matrices (MATRIX)."""
     return list(self.mw) if self.mix == _lib.MIX_MATRIX else [self.mix_w]
@@ -697,6 +751,24 @@ class IterationPlan:
       c.enqueue_eval(self.x, self.labels, self.labels_f, None, sp, self.xp)
     torch.cuda.current_stream(self.device).synchronize()
     return [float(c.out3[2].item()) for c in self.candidates]
+
+  # -- in-flight checkpoint -------------------------------------------------------
+  def state_dict(self) -> Dict[str, np.ndarray]:
+    """State of the iteration in flight on this GPU (one flat dict, keys prefixed by candidate index)."""
+    torch.cuda.current_stream(self.device).synchronize()
+    out = {"steps_done": np.asarray(self.steps_done, dtype=np.int64), "step_dev": self.step_dev.cpu().numpy()}
+    for c in self.candidates:
+      for k, v in c.state_dict().items():
+        out["c%d_%s" % (c.index, k)] = v
+    return out
+
+  def load_state_dict(self, st: Dict[str, np.ndarray]):
+    self.steps_done = int(st["steps_done"])
+    self.step_dev.copy_(torch.as_tensor(st["step_dev"]))
+    for c in self.candidates:
+      pre = "c%d_" % c.index
+      c.load_state_dict({k[len(pre):]: v for k, v in st.items() if k.startswith(pre)})
+    torch.cuda.current_stream(self.device).synchronize()
 
   # -- read-back ---------------------------------------------------------------
   def ema_losses(self) -> List[float]:

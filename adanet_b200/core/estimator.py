@@ -35,7 +35,7 @@ class RunConfig:
   """The RunConfig fields the estimator reads (tf.estimator.RunConfig stand-in)."""
 
   def __init__(self, model_dir=None, tf_random_seed=None, num_worker_replicas=None, global_id_in_cluster=None,
-               is_chief=None, **unused):
+               is_chief=None, save_checkpoints_steps=None, **unused):
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rk = int(os.environ.get("RANK", "0"))
     self.model_dir = model_dir
@@ -43,6 +43,7 @@ class RunConfig:
     self.num_worker_replicas = num_worker_replicas if num_worker_replicas is not None else ws
     self.global_id_in_cluster = global_id_in_cluster if global_id_in_cluster is not None else rk
     self.num_ps_replicas = 0
+    self.save_checkpoints_steps = save_checkpoints_steps   # in-flight iteration state every N global steps
     self.is_chief = is_chief if is_chief is not None else (self.global_id_in_cluster == 0)
 
 
@@ -221,6 +222,36 @@ class Estimator(object):
                                      adanet_loss_decay=self._adanet_loss_decay, force_grow=self._force_grow,
                                      replay_indices=replay, keep_traces=bool(self._debug))
 
+  def _inflight_path(self):
+    return os.path.join(self._model_dir, "iteration-inflight-rank{}.npz".format(self._config.global_id_in_cluster))
+
+  def _save_inflight(self):
+    """Mid-iteration checkpoint (every `RunConfig.save_checkpoints_steps` global steps): the candidates' weights,
+    optimizer slots, mixture weights, EMA and step counters of THIS rank's shard, so a killed run resumes
+    inside the iteration (the reference persists the same through the TF checkpoint,
+    adanet/core/iteration.py:40-118,172-183).  Candidate builders are re-generated deterministically on resume."""
+    st = self._search.plan.state_dict()
+    st["meta_iteration"] = np.asarray(self._search.iteration, dtype=np.int64)
+    st["meta_global_step"] = np.asarray(self._global_step, dtype=np.int64)
+    st["meta_iteration_step"] = np.asarray(self._iteration_step, dtype=np.int64)
+    tmp = self._inflight_path() + ".tmp.npz"
+    np.savez(tmp, **st)
+    os.replace(tmp, self._inflight_path())
+
+  def _maybe_restore_inflight(self):
+    """Called right after an iteration's plan was built: loads the in-flight state if it belongs to it."""
+    if not self._model_dir or not os.path.exists(self._inflight_path()) or self._iteration_step != 0:
+      return False
+    st = dict(np.load(self._inflight_path()))
+    if int(st["meta_iteration"]) != self._search.iteration or int(st["meta_global_step"]) < self._global_step:
+      return False
+    self._search.plan.load_state_dict(st)
+    self._global_step = int(st["meta_global_step"])
+    self._iteration_step = int(st["meta_iteration_step"])
+    logging.info("resumed iteration %d at iteration step %d (global step %d)", self._search.iteration,
+                 self._iteration_step, self._global_step)
+    return True
+
   def _maybe_restore(self):
     """Continues from `model_dir/ensemble-latest.{npz,json}` (written at every iteration boundary): frozen
     members, mixture weights, selection state and step counters -- what the reference restores from
@@ -323,12 +354,18 @@ class Estimator(object):
       if self._search.plan is None:
         self._search.build_iteration()
         self._iteration_step = 0
+        if self._maybe_restore_inflight() and steps is not None:
+          limit = self._global_step + steps
       x = input_utils.to_matrix(features, self._feature_keys)
       self._search.plan.train_step(x, labels)
       self._global_step += 1
       self._iteration_step += 1
       if self._max_iteration_steps is not None and self._iteration_step >= self._max_iteration_steps:
         self._bookkeeping()
+      else:
+        every = getattr(self._config, "save_checkpoints_steps", None)
+        if every and self._model_dir and self._global_step % int(every) == 0:
+          self._save_inflight()
     else:
       # input exhausted: the iteration is over (iteration.py:274-284 stops each spec on OutOfRangeError)
       if self._search is not None and self._search.plan is not None and self._iteration_step > 0 and (

@@ -235,3 +235,64 @@ def test_resume_from_model_dir_matches_uninterrupted_run(env, tmp_path):
   c._max_iterations = 4
   c.train(input_from(3 * steps), steps=3)
   assert c._global_step == 3 * steps + 3
+
+
+def test_resume_inside_an_iteration(env, tmp_path):
+  """RunConfig.save_checkpoints_steps persists the in-flight iteration (weights, optimizer slots, mixture
+  weights, EMA, step counters; adanet/core/iteration.py:40-118,172-183): a run killed inside iteration 1
+  resumes from the last in-flight checkpoint and ends bit-identical to the uninterrupted run."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  from adanet_b200.examples import simple_dnn
+  x, y = _data(orc)
+  steps = 8
+
+  def make(model_dir):
+    gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
+                               optimizer=train.MomentumOptimizer(0.02, 0.9), layer_size=16, seed=SEED)
+    return adanet.Estimator(
+        head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
+        ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.AdamOptimizer(0.01),
+                                                                   adanet_lambda=0.01, use_bias=True)],
+        max_iterations=2, model_dir=model_dir, config=adanet.RunConfig(model_dir=model_dir, save_checkpoints_steps=3),
+        debug=True)
+
+  def input_from(start):
+    def fn():
+      for i in range(start * B, x.shape[0] - B + 1, B):
+        yield {"x": x[i:i + B]}, y[i:i + B]
+    return fn
+
+  full = make(str(tmp_path / "full"))
+  full.train(input_from(0), max_steps=2 * steps)
+  a = make(str(tmp_path / "killed"))
+  a.train(input_from(0), max_steps=11)             # dies inside iteration 1; last in-flight save at global step 9
+  b = make(str(tmp_path / "killed"))
+  b.train(input_from(9), max_steps=2 * steps)      # boundary restore (iteration 1, step 8) + in-flight restore (step 9)
+  assert b._global_step == 2 * steps and b._search.iteration == 2
+  ra, rb = full._search.reports[-1], b._search.reports[-1]
+  assert rb.best_index == ra.best_index and rb.architecture == ra.architecture
+  np.testing.assert_array_equal(rb.ema_losses, ra.ema_losses)
+  np.testing.assert_array_equal(rb.mixture_weights, ra.mixture_weights)
+  for name in ra.traces:
+    np.testing.assert_array_equal(rb.traces[name]["adanet_loss"], ra.traces[name]["adanet_loss"])
+
+
+def test_nan_candidate_loses_selection(env):
+  """A diverged candidate (NaN adanet loss) never wins: np.nanargmin over the EMA losses
+  (adanet/core/estimator.py:1491-1495; estimator_test.py's _NanLossBuilder cases)."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  x, y = _data(orc)
+  cols = [graph.numeric_column("x", D)]
+
+  pool = {"sane": adanet.estimators.DNNEstimator(cols, [16], train.GradientDescentOptimizer(0.05), seed=3),
+          "wild": adanet.estimators.DNNEstimator(cols, [16], train.GradientDescentOptimizer(1e30), seed=4)}
+  est = adanet.AutoEnsembleEstimator(head=adanet.heads.MultiClassHead(C), candidate_pool=pool, max_iteration_steps=6,
+                                     max_iterations=1, debug=True)
+  est.train(_input_fn(x, y), max_steps=6)
+  rep = est._search.reports[0]
+  sane, wild = rep.ema_losses          # dict pools are sorted by name
+  assert not np.isfinite(wild) and np.isfinite(sane)
+  assert rep.best_index == 0 and rep.architecture == [(0, "sane")]
+  assert np.isfinite(est.evaluate(_input_fn(x[:B], y[:B]), steps=1)["loss"])
