@@ -269,6 +269,192 @@ class DenseNet:
     return [w.cpu().numpy() for w in self.ws], [b.cpu().numpy() for b in self.bs]
 
 
+class EnsembleHead:
+  """One candidate ensemble: mixture weights (+bias) over a list of member subnetworks, its fused head kernel,
+  the zero-debiased EMA of its adanet loss and its loss trace.
+
+  `member_nets` = kept previous members first, then the candidate's new subnetworks
+  (adanet/ensemble/weighted.py:253-300).  The head only reads the members' logits / last layers, so any number
+  of heads can share the subnetworks of an iteration (GrowStrategy: one head per new subnetwork; SoloStrategy:
+  the new subnetwork alone; AllStrategy: every new subnetwork; adanet/ensemble/strategy.py:79-117).
+  """
+
+  def __init__(self, lib, name: str, member_nets: Sequence[DenseNet], n_prev: int, ens: EnsemblerPlanSpec, batch: int,
+               logits_dim: int, head: str, decay: float, trace_capacity: int, device: torch.device,
+               prev_mixture_weights=None, prev_bias=None, sub_loss: Optional[torch.Tensor] = None):
+    self.lib, self.name, self.ens = lib, name, ens
+    self.batch, self.C, self.head = batch, logits_dim, _HEAD_KIND[head]
+    self.member_nets = list(member_nets)
+    self.n_prev = n_prev
+    n_members = len(self.member_nets)
+    f32 = dict(dtype=torch.float32, device=device)
+    self.device = device
+    self.planes = planes_enabled()
+    self.kind = getattr(ens, "kind", "complexity_regularized")
+    self.mix = _MIX_KIND[ens.mixture_weight_type]
+    if self.mix == _lib.MIX_MATRIX:
+      # W_k [D_k, C] (zeros, weighted.py:424-428) applied to each member's last layer by the plane GEMM; the
+      # head kernel then sees pre-multiplied members and the L1 norms (include/adanet_b200.h)
+      if not self.planes:
+        raise NotImplementedError("MATRIX mixture weights run on the plane path only (ADN_DENSE_PATH=simt is a cross-check)")
+      self.mw = [torch.zeros((m.last_layer_dim, logits_dim), **f32) for m in self.member_nets]
+      self.mwp = [new_planes(m.last_layer_dim, logits_dim, device) for m in self.member_nets]
+      self.d_mw = [torch.zeros_like(w) for w in self.mw]
+      self.mw_logits = [torch.empty((batch, logits_dim), **f32) for _ in self.member_nets]
+      self.mw_l1 = torch.zeros((n_members,), **f32)
+      self.dens = torch.empty((batch, logits_dim), **f32)
+      self.densp = new_planes(batch, logits_dim, device)
+      self.mw_ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_P_WS, batch, m.last_layer_dim, logits_dim) for m in self.member_nets)
+      self.mw_ws = torch.empty((self.mw_ws_bytes,), dtype=torch.uint8, device=device)
+      self.mix_w = self.mw_l1
+    else:
+      wshape = (n_members,) if self.mix == _lib.MIX_SCALAR else (n_members, logits_dim)
+      self.mix_w = torch.full(wshape, 1.0 / n_members, **f32)
+    self.bias = torch.zeros((logits_dim,), **f32)
+    if self.kind == "mean":
+      # MeanEnsembler (adanet/ensemble/mean.py:92-135): the mean of the NEW subnetworks' logits, previous members
+      # ignored, nothing trained, no complexity penalty
+      n_new = n_members - n_prev
+      self.mix_w.zero_()
+      self.mix_w[n_prev:] = 1.0 / n_new
+    elif ens.warm_start_mixture_weights and prev_mixture_weights is not None and n_prev > 0:
+      # kept members and the bias start from the previous ensemble's trained values (weighted.py:270-285,487-516);
+      # new members keep the default initialiser for the grown member count
+      if self.mix == _lib.MIX_MATRIX:
+        sp0 = torch.cuda.current_stream(device).cuda_stream
+        for k in range(n_prev):
+          self.mw[k].copy_(torch.as_tensor(np.ascontiguousarray(prev_mixture_weights[k], dtype=np.float32)))
+          _lib.check(lib.adn_planes_split(self.mw[k].data_ptr(), self.mw[k].shape[0], self.mw[k].shape[1],
+                                          self.mwp[k].data_ptr(), sp0), "adn_planes_split")
+      else:
+        prev = torch.as_tensor(np.ascontiguousarray(prev_mixture_weights, dtype=np.float32)).to(device)
+        self.mix_w[:n_prev] = prev.reshape((n_prev,) + tuple(self.mix_w.shape[1:]))
+      if prev_bias is not None:
+        self.bias.copy_(torch.as_tensor(np.ascontiguousarray(prev_bias, dtype=np.float32)).reshape(logits_dim))
+    self.d_mix_w = torch.zeros_like(self.mix_w)
+    self.d_bias = torch.zeros((logits_dim,), **f32)
+    self.complexities = [m.complexity for m in self.member_nets]
+    lam, beta = float(ens.adanet_lambda), float(ens.adanet_beta)
+    if self.kind == "mean":
+      lam = beta = 0.0
+    self.reg_is_zero = int(lam == 0.0 and beta == 0.0)
+    # weighted.py:351-358 (_compute_adanet_gamma), evaluated in fp32 like the graph does
+    self.gammas = [float(np.float32(beta) if lam == 0.0 else np.float32(np.float32(lam) * np.float32(c) + np.float32(beta)))
+                   for c in self.complexities]
+    self.reg_multiplier = 1.0 if ens.legacy_train_op else 2.0   # SURVEY.md section 3.3 step 11
+    self.out3 = torch.zeros((3,), **f32)
+    self.ens_opt = None
+    if ens.optimizer is not None and self.kind != "mean":
+      if self.mix == _lib.MIX_MATRIX:
+        ens_params = list(self.mw) + ([self.bias] if ens.use_bias else [])
+        self._ens_grads = list(self.d_mw) + ([self.d_bias] if ens.use_bias else [])
+        self.ens_opt = _Optimizer(ens.optimizer, ens_params, list(self.mwp) + ([None] if ens.use_bias else []))
+      else:
+        ens_params = [self.mix_w] + ([self.bias] if ens.use_bias else [])
+        self._ens_grads = [self.d_mix_w] + ([self.d_bias] if ens.use_bias else [])
+        self.ens_opt = _Optimizer(ens.optimizer, ens_params)
+    self.ema_state = torch.zeros((3,), **f32)   # {biased, n, value}; candidate.py:101-129
+    self.decay = float(decay)
+    self.trace = torch.zeros((trace_capacity, 4), **f32)
+    self.trace_capacity = trace_capacity
+    self.head_ws_bytes = _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, n_members)
+    self.head_ws = torch.empty((self.head_ws_bytes,), dtype=torch.uint8, device=device)
+    if self.mix == _lib.MIX_MATRIX:
+      self._members = _lib.ptr_array([t.data_ptr() for t in self.mw_logits])
+    else:
+      self._members = _lib.ptr_array([m.logits.data_ptr() for m in self.member_nets])
+    self._gammas = _lib.f32_array(self.gammas)
+    # trace row = (sub_loss of the candidate's subnetwork | NaN for a head that owns none, ens_loss, adanet_loss, ema)
+    self._nan = torch.full((1,), float("nan"), **f32)
+    src0 = sub_loss if sub_loss is not None else self._nan
+    self._trace_src = _lib.ptr_array([src0.data_ptr(), self.out3.data_ptr(), self.out3.data_ptr() + 8,
+                                      self.ema_state.data_ptr() + 8])
+
+  def matrix_forward(self, xp, sp: int):
+    """weighted.py:449: weighted_k = last_layer_k @ W_k for every member, and ||W_k||_1 for the regulariser."""
+    lib, B, C = self.lib, self.batch, self.C
+    for k, m in enumerate(self.member_nets):
+      _lib.check(lib.adn_dense_fwd_p(m.last_layer_planes(xp).data_ptr(), self.mwp[k].data_ptr(), None, None,
+                                     self.mw_logits[k].data_ptr(), B, m.last_layer_dim, C, _lib.ACT_NONE, sp),
+                 "adn_dense_fwd_p")
+      _lib.check(lib.adn_l1_norm(self.mw[k].data_ptr(), self.mw[k].numel(), self.mw_l1.data_ptr() + 4 * k, sp),
+                 "adn_l1_norm")
+
+  def enqueue(self, labels, labels_f, step_dev, sp: int, xp: Optional[torch.Tensor] = None):
+    """steps 6-13 on pre-update values: ensemble logits, loss, penalty, mixture-weight gradient and update, EMA,
+    trace.  Uses only its own scratch, so it can run beside the backward waves."""
+    lib, B, C = self.lib, self.batch, self.C
+    lab = labels.data_ptr() if labels is not None else None
+    labf = labels_f.data_ptr() if labels_f is not None else None
+    train_ens = self.ens_opt is not None
+    matrix = self.mix == _lib.MIX_MATRIX
+    if matrix:
+      self.matrix_forward(xp, sp)
+    _lib.check(lib.adn_ensemble_head(
+        self.head, self.mix, self._members, len(self.member_nets), self.mix_w.data_ptr(), self.bias.data_ptr(),
+        self._gammas, self.reg_is_zero, self.reg_multiplier, lab, labf, self.out3.data_ptr(),
+        self.d_mix_w.data_ptr() if (train_ens and not matrix) else None,
+        self.d_bias.data_ptr() if (train_ens and self.ens.use_bias) else None,
+        self.dens.data_ptr() if (train_ens and matrix) else None, None, B, C, self.head_ws.data_ptr(),
+        self.head_ws_bytes, sp), "adn_ensemble_head")
+    if train_ens and matrix:
+      # dW_k = last_layer_k^T @ dLoss/d(ens)  + reg_multiplier * gamma_k * sign(W_k)   (weighted.py:606-617)
+      _lib.check(lib.adn_planes_split(self.dens.data_ptr(), B, C, self.densp.data_ptr(), sp), "adn_planes_split")
+      for k, m in enumerate(self.member_nets):
+        _lib.check(lib.adn_dense_bwd_p(m.last_layer_planes(xp).data_ptr(), None, self.densp.data_ptr(), None, None, None,
+                                       self.d_mw[k].data_ptr(), B, m.last_layer_dim, C, 0, self.mw_ws.data_ptr(),
+                                       self.mw_ws_bytes, sp), "adn_dense_bwd_p")
+        if not self.reg_is_zero:
+          _lib.check(lib.adn_l1_grad_add(self.d_mw[k].data_ptr(), self.mw[k].data_ptr(), self.mw[k].numel(),
+                                         self.reg_multiplier * self.gammas[k], sp), "adn_l1_grad_add")
+    _lib.check(lib.adn_ema_update(self.ema_state.data_ptr(), self.out3.data_ptr() + 8, self.decay, sp),
+               "adn_ema_update")
+    _lib.check(lib.adn_record_scalars(self._trace_src, 4, self.trace.data_ptr(), 4, step_dev.data_ptr(),
+                                      self.trace_capacity, sp), "adn_record_scalars")
+    if train_ens:
+      self.ens_opt.apply(lib, self._ens_grads, sp)
+
+  def enqueue_eval(self, labels, labels_f, ens_out: Optional[torch.Tensor], sp: int, xp: Optional[torch.Tensor] = None):
+    """Forward-only ensemble logits / loss over the members' current logits (Evaluator, evaluate, predict)."""
+    if self.mix == _lib.MIX_MATRIX:
+      self.matrix_forward(xp, sp)
+    _lib.check(self.lib.adn_ensemble_head(
+        self.head, self.mix, self._members, len(self.member_nets), self.mix_w.data_ptr(), self.bias.data_ptr(),
+        self._gammas, self.reg_is_zero, self.reg_multiplier,
+        labels.data_ptr() if labels is not None else None, labels_f.data_ptr() if labels_f is not None else None,
+        self.out3.data_ptr(), None, None, None, ens_out.data_ptr() if ens_out is not None else None, self.batch,
+        self.C, self.head_ws.data_ptr(), self.head_ws_bytes, sp), "adn_ensemble_head")
+
+  def mixture_weight_tensors(self) -> List[torch.Tensor]:
+    """The trained mixture weights as tensors: [w] (SCALAR [N] / VECTOR [N,C]) or the N matrices (MATRIX)."""
+    return list(self.mw) if self.mix == _lib.MIX_MATRIX else [self.mix_w]
+
+  def state_dict(self) -> Dict[str, np.ndarray]:
+    out = {}
+    for i, t in enumerate(self.mixture_weight_tensors()):
+      out["mix%d" % i] = t.cpu().numpy()
+    out["bias"] = self.bias.cpu().numpy()
+    if self.ens_opt is not None:
+      for k, v in self.ens_opt.state().items():
+        out["ens_opt_" + k] = v
+    out["ema_state"] = self.ema_state.cpu().numpy()
+    out["trace"] = self.trace.cpu().numpy()
+    return out
+
+  def load_state_dict(self, st: Dict[str, np.ndarray]):
+    for i, t in enumerate(self.mixture_weight_tensors()):
+      t.copy_(torch.as_tensor(st["mix%d" % i]))
+    if self.mix == _lib.MIX_MATRIX:
+      sp = torch.cuda.current_stream(self.device).cuda_stream
+      for w, wp in zip(self.mw, self.mwp):
+        _lib.check(self.lib.adn_planes_split(w.data_ptr(), w.shape[0], w.shape[1], wp.data_ptr(), sp), "adn_planes_split")
+    self.bias.copy_(torch.as_tensor(st["bias"]))
+    if self.ens_opt is not None:
+      self.ens_opt.load_state({k[len("ens_opt_"):]: v for k, v in st.items() if k.startswith("ens_opt_")})
+    self.ema_state.copy_(torch.as_tensor(st["ema_state"]))
+    self.trace.copy_(torch.as_tensor(st["trace"]))
+
+
 class CandidatePlan:
   """One `*_grow` candidate: its new subnetwork + its ensemble head + EMA.
 
@@ -304,13 +490,10 @@ class CandidatePlan:
     else:
       self.dz = [torch.empty((batch, hid), **f32) for _ in range(2)] if hid else []
       ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_WS, batch, dims[i], dims[i + 1]) for i in range(len(dims) - 1))
-    n_members = len(frozen) + 1
     if self.planes:
       self.bwd_ws_bytes = ws_bytes
       self.bwd_ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
-      self.head_ws_bytes = _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, n_members)
-      self.head_ws = torch.empty((self.head_ws_bytes,), dtype=torch.uint8, device=device)
-    ws_bytes = max(ws_bytes, _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, n_members))
+    ws_bytes = max(ws_bytes, _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, 1))   # the subnetwork's own head loss
     self.workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
     self.ws_bytes = ws_bytes
     self.sub_loss = torch.zeros((1,), **f32)
@@ -320,74 +503,21 @@ class CandidatePlan:
       self._grads += [dw, db]
       planes += [self.net.wps[i] if self.planes else None, None]
     self.sub_opt = _Optimizer(spec.optimizer, params, planes if self.planes else None)
-    # ensemble state (weighted.py:360-366,419-428,487-516)
-    self.mix = _MIX_KIND[ens.mixture_weight_type]
-    self.member_nets = list(frozen) + [self.net]
-    if self.mix == _lib.MIX_MATRIX:
-      # W_k [D_k, C] (zeros, weighted.py:424-428) applied to each member's last layer by the plane GEMM; the
-      # head kernel then sees pre-multiplied members and the L1 norms (include/adanet_b200.h)
-      if not self.planes:
-        raise NotImplementedError("MATRIX mixture weights run on the plane path only (ADN_DENSE_PATH=simt is a cross-check)")
-      self.mw = [torch.zeros((m.last_layer_dim, logits_dim), **f32) for m in self.member_nets]
-      self.mwp = [new_planes(m.last_layer_dim, logits_dim, device) for m in self.member_nets]
-      self.d_mw = [torch.zeros_like(w) for w in self.mw]
-      self.mw_logits = [torch.empty((batch, logits_dim), **f32) for _ in self.member_nets]
-      self.mw_l1 = torch.zeros((n_members,), **f32)
-      self.dens = torch.empty((batch, logits_dim), **f32)
-      self.densp = new_planes(batch, logits_dim, device)
-      self.mw_ws_bytes = max(_lib.query(_lib.Q_DENSE_BWD_P_WS, batch, m.last_layer_dim, logits_dim) for m in self.member_nets)
-      self.mw_ws = torch.empty((self.mw_ws_bytes,), dtype=torch.uint8, device=device)
-      self.mix_w = self.mw_l1
-    else:
-      wshape = (n_members,) if self.mix == _lib.MIX_SCALAR else (n_members, logits_dim)
-      self.mix_w = torch.full(wshape, 1.0 / n_members, **f32)
-    self.bias = torch.zeros((logits_dim,), **f32)
-    if ens.warm_start_mixture_weights and prev_mixture_weights is not None and len(frozen) > 0:
-      # kept members and the bias start from the previous ensemble's trained values (weighted.py:270-285,487-516);
-      # the new member keeps the default initialiser for the grown member count
-      nf = len(frozen)
-      if self.mix == _lib.MIX_MATRIX:
-        sp0 = torch.cuda.current_stream(device).cuda_stream
-        for k in range(nf):
-          self.mw[k].copy_(torch.as_tensor(np.ascontiguousarray(prev_mixture_weights[k], dtype=np.float32)))
-          _lib.check(lib.adn_planes_split(self.mw[k].data_ptr(), self.mw[k].shape[0], self.mw[k].shape[1],
-                                          self.mwp[k].data_ptr(), sp0), "adn_planes_split")
-      else:
-        prev = torch.as_tensor(np.ascontiguousarray(prev_mixture_weights, dtype=np.float32)).to(device)
-        self.mix_w[:nf] = prev.reshape((nf,) + tuple(self.mix_w.shape[1:]))
-      if prev_bias is not None:
-        self.bias.copy_(torch.as_tensor(np.ascontiguousarray(prev_bias, dtype=np.float32)).reshape(logits_dim))
-    self.d_mix_w = torch.zeros_like(self.mix_w)
-    self.d_bias = torch.zeros((logits_dim,), **f32)
-    self.complexities = [f.complexity for f in frozen] + [spec.complexity]
-    lam, beta = float(ens.adanet_lambda), float(ens.adanet_beta)
-    self.reg_is_zero = int(lam == 0.0 and beta == 0.0)
-    # weighted.py:351-358 (_compute_adanet_gamma), evaluated in fp32 like the graph does
-    self.gammas = [float(np.float32(beta) if lam == 0.0 else np.float32(np.float32(lam) * np.float32(c) + np.float32(beta)))
-                   for c in self.complexities]
-    self.reg_multiplier = 1.0 if ens.legacy_train_op else 2.0
-    self.out3 = torch.zeros((3,), **f32)
-    self.ens_opt = None
-    if ens.optimizer is not None:
-      if self.mix == _lib.MIX_MATRIX:
-        ens_params = list(self.mw) + ([self.bias] if ens.use_bias else [])
-        self._ens_grads = list(self.d_mw) + ([self.d_bias] if ens.use_bias else [])
-        self.ens_opt = _Optimizer(ens.optimizer, ens_params, list(self.mwp) + ([None] if ens.use_bias else []))
-      else:
-        ens_params = [self.mix_w] + ([self.bias] if ens.use_bias else [])
-        self._ens_grads = [self.d_mix_w] + ([self.d_bias] if ens.use_bias else [])
-        self.ens_opt = _Optimizer(ens.optimizer, ens_params)
-    self.ema_state = torch.zeros((3,), **f32)   # {biased, n, value}; candidate.py:101-129
-    self.decay = float(decay)
-    self.trace = torch.zeros((trace_capacity, 4), **f32)
-    self.trace_capacity = trace_capacity
-    if self.mix == _lib.MIX_MATRIX:
-      self._members = _lib.ptr_array([t.data_ptr() for t in self.mw_logits])
-    else:
-      self._members = _lib.ptr_array([f.logits.data_ptr() for f in self.frozen] + [self.net.logits.data_ptr()])
-    self._gammas = _lib.f32_array(self.gammas)
-    self._trace_src = _lib.ptr_array([self.sub_loss.data_ptr(), self.out3.data_ptr(),
-                                      self.out3.data_ptr() + 8, self.ema_state.data_ptr() + 8])
+    # the candidate's ensemble: kept previous members + this new subnetwork
+    self.ehead = EnsembleHead(lib, self.name, list(frozen) + [self.net], len(frozen), ens, batch, logits_dim, head, decay,
+                              trace_capacity, device, prev_mixture_weights=prev_mixture_weights, prev_bias=prev_bias,
+                              sub_loss=self.sub_loss)
+    self.has_head = True      # False when no strategy asked for this subnetwork's `_grow` ensemble
+
+  # the head's state under the names the search / tests use
+  mix = property(lambda self: self.ehead.mix)
+  mix_w = property(lambda self: self.ehead.mix_w)
+  bias = property(lambda self: self.ehead.bias)
+  out3 = property(lambda self: self.ehead.out3)
+  ema_state = property(lambda self: self.ehead.ema_state)
+  trace = property(lambda self: self.ehead.trace)
+  trace_capacity = property(lambda self: self.ehead.trace_capacity)
+  ens_opt = property(lambda self: self.ehead.ens_opt)
 
   def enqueue_train_step(self, x: torch.Tensor, labels: torch.Tensor, labels_f: Optional[torch.Tensor],
                          step_dev: torch.Tensor, sp: int, xp: Optional[torch.Tensor] = None):
@@ -407,19 +537,9 @@ class CandidatePlan:
     else:
       _lib.check(lib.adn_head_loss(self.head, net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
                                    self.dlogits.data_ptr(), B, C, wsp, self.ws_bytes, sp), "adn_head_loss")
-    # steps 6-11: ensemble head on pre-update values
-    train_ens = self.ens_opt is not None
-    _lib.check(lib.adn_ensemble_head(
-        self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
-        self._gammas, self.reg_is_zero, self.reg_multiplier, lab, labf, self.out3.data_ptr(),
-        self.d_mix_w.data_ptr() if train_ens else None,
-        self.d_bias.data_ptr() if (train_ens and self.ens.use_bias) else None,
-        None, None, B, C, wsp, self.ws_bytes, sp), "adn_ensemble_head")
-    # step 12: EMA of adanet_loss
-    _lib.check(lib.adn_ema_update(self.ema_state.data_ptr(), self.out3.data_ptr() + 8, self.decay, sp),
-               "adn_ema_update")
-    _lib.check(lib.adn_record_scalars(self._trace_src, 4, self.trace.data_ptr(), 4, step_dev.data_ptr(),
-                                      self.trace_capacity, sp), "adn_record_scalars")
+    # steps 6-13: ensemble head on pre-update values, EMA, trace, mixture-weight update
+    if self.has_head:
+      self.ehead.enqueue(labels, labels_f, step_dev, sp, xp)
     # step 4: backward through the subnetwork's own variables only
     n = len(net.ws)
     if self.planes:
@@ -445,9 +565,7 @@ class CandidatePlan:
                                    self.dbs[i].data_ptr(), B, net.dims[i], net.dims[i + 1], 1 if i > 0 else 0,
                                    wsp, self.ws_bytes, sp), "adn_dense_bwd")
       dz = dx
-    # step 11 (apply) then steps 4-5 (apply)
-    if train_ens:
-      self.ens_opt.apply(lib, self._ens_grads, sp)
+    # steps 4-5 (apply)
     self.sub_opt.apply(lib, self._grads, sp)
 
   def state_dict(self) -> Dict[str, np.ndarray]:
@@ -458,14 +576,7 @@ class CandidatePlan:
       out["w%d" % i], out["b%d" % i] = w.cpu().numpy(), b.cpu().numpy()
     for k, v in self.sub_opt.state().items():
       out["sub_opt_" + k] = v
-    for i, t in enumerate(self.mixture_weight_tensors()):
-      out["mix%d" % i] = t.cpu().numpy()
-    out["bias"] = self.bias.cpu().numpy()
-    if self.ens_opt is not None:
-      for k, v in self.ens_opt.state().items():
-        out["ens_opt_" + k] = v
-    out["ema_state"] = self.ema_state.cpu().numpy()
-    out["trace"] = self.trace.cpu().numpy()
+    out.update(self.ehead.state_dict())
     return out
 
   def load_state_dict(self, st: Dict[str, np.ndarray]):
@@ -474,21 +585,10 @@ class CandidatePlan:
       b.copy_(torch.as_tensor(st["b%d" % i]))
     self.net.refresh_planes()
     self.sub_opt.load_state({k[len("sub_opt_"):]: v for k, v in st.items() if k.startswith("sub_opt_")})
-    for i, t in enumerate(self.mixture_weight_tensors()):
-      t.copy_(torch.as_tensor(st["mix%d" % i]))
-    if self.mix == _lib.MIX_MATRIX:
-      sp = torch.cuda.current_stream(self.net.device).cuda_stream
-      for w, wp in zip(self.mw, self.mwp):
-        _lib.check(self.lib.adn_planes_split(w.data_ptr(), w.shape[0], w.shape[1], wp.data_ptr(), sp), "adn_planes_split")
-    self.bias.copy_(torch.as_tensor(st["bias"]))
-    if self.ens_opt is not None:
-      self.ens_opt.load_state({k[len("ens_opt_"):]: v for k, v in st.items() if k.startswith("ens_opt_")})
-    self.ema_state.copy_(torch.as_tensor(st["ema_state"]))
-    self.trace.copy_(torch.as_tensor(st["trace"]))
+    self.ehead.load_state_dict(st)
 
   def mixture_weight_tensors(self) -> List[torch.Tensor]:
-    """The trained mixture weights as tensors: [w] (SCALAR [N] / VECTOR [N,C]) or the N matrices (MATRIX)."""
-    return list(self.mw) if self.mix == _lib.MIX_MATRIX else [self.mix_w]
+    return self.ehead.mixture_weight_tensors()
 
   # ---- plane path, wave-synchronous schedule (IterationPlan._enqueue_waves) ----
   def enqueue_sub_loss(self, labels, labels_f, sp: int):
@@ -500,49 +600,9 @@ class CandidatePlan:
                                         self.dbs[len(self.net.ws) - 1].data_ptr(), self.batch, self.C,
                                         self.workspace.data_ptr(), self.ws_bytes, sp), "adn_head_loss_p")
 
-  def _matrix_forward(self, xp, sp: int):
-    """weighted.py:449: weighted_k = last_layer_k @ W_k for every member, and ||W_k||_1 for the regulariser."""
-    lib, B, C = self.lib, self.batch, self.C
-    for k, m in enumerate(self.member_nets):
-      _lib.check(lib.adn_dense_fwd_p(m.last_layer_planes(xp).data_ptr(), self.mwp[k].data_ptr(), None, None,
-                                     self.mw_logits[k].data_ptr(), B, m.last_layer_dim, C, _lib.ACT_NONE, sp),
-                 "adn_dense_fwd_p")
-      _lib.check(lib.adn_l1_norm(self.mw[k].data_ptr(), self.mw[k].numel(), self.mw_l1.data_ptr() + 4 * k, sp),
-                 "adn_l1_norm")
-
   def enqueue_ensemble(self, labels, labels_f, step_dev, sp: int, xp: Optional[torch.Tensor] = None):
-    """steps 6-12: ensemble head on pre-update values, EMA, trace (own small workspace: runs beside the
-    backward waves)."""
-    lib, B, C = self.lib, self.batch, self.C
-    lab = labels.data_ptr() if labels is not None else None
-    labf = labels_f.data_ptr() if labels_f is not None else None
-    train_ens = self.ens_opt is not None
-    matrix = self.mix == _lib.MIX_MATRIX
-    if matrix:
-      self._matrix_forward(xp, sp)
-    _lib.check(lib.adn_ensemble_head(
-        self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
-        self._gammas, self.reg_is_zero, self.reg_multiplier, lab, labf, self.out3.data_ptr(),
-        self.d_mix_w.data_ptr() if (train_ens and not matrix) else None,
-        self.d_bias.data_ptr() if (train_ens and self.ens.use_bias) else None,
-        self.dens.data_ptr() if (train_ens and matrix) else None, None, B, C, self.head_ws.data_ptr(),
-        self.head_ws_bytes, sp), "adn_ensemble_head")
-    if train_ens and matrix:
-      # dW_k = last_layer_k^T @ dLoss/d(ens)  + reg_multiplier * gamma_k * sign(W_k)   (weighted.py:606-617)
-      _lib.check(lib.adn_planes_split(self.dens.data_ptr(), B, C, self.densp.data_ptr(), sp), "adn_planes_split")
-      for k, m in enumerate(self.member_nets):
-        _lib.check(lib.adn_dense_bwd_p(m.last_layer_planes(xp).data_ptr(), None, self.densp.data_ptr(), None, None, None,
-                                       self.d_mw[k].data_ptr(), B, m.last_layer_dim, C, 0, self.mw_ws.data_ptr(),
-                                       self.mw_ws_bytes, sp), "adn_dense_bwd_p")
-        if not self.reg_is_zero:
-          _lib.check(lib.adn_l1_grad_add(self.d_mw[k].data_ptr(), self.mw[k].data_ptr(), self.mw[k].numel(),
-                                         self.reg_multiplier * self.gammas[k], sp), "adn_l1_grad_add")
-    _lib.check(lib.adn_ema_update(self.ema_state.data_ptr(), self.out3.data_ptr() + 8, self.decay, sp),
-               "adn_ema_update")
-    _lib.check(lib.adn_record_scalars(self._trace_src, 4, self.trace.data_ptr(), 4, step_dev.data_ptr(),
-                                      self.trace_capacity, sp), "adn_record_scalars")
-    if train_ens:
-      self.ens_opt.apply(lib, self._ens_grads, sp)
+    if self.has_head:
+      self.ehead.enqueue(labels, labels_f, step_dev, sp, xp)
 
   def bwd_op(self, k: int, xp: torch.Tensor) -> "_lib.BwdOp":
     """k-th backward wave = layer n-1-k: dW_i, planes of dZ_{i-1} (ReLU mask = sign bits of h_{i-1}) and
@@ -564,16 +624,8 @@ class CandidatePlan:
   def enqueue_eval(self, x, labels, labels_f, ens_out: Optional[torch.Tensor], sp: int,
                    xp: Optional[torch.Tensor] = None):
     """Forward-only: subnetwork logits + ensemble logits/loss (evaluate / predict)."""
-    lib, net, B, C = self.lib, self.net, self.batch, self.C
-    net.forward(lib, x, sp, xp)
-    if self.mix == _lib.MIX_MATRIX:
-      self._matrix_forward(xp, sp)
-    _lib.check(lib.adn_ensemble_head(
-        self.head, self.mix, self._members, len(self.frozen) + 1, self.mix_w.data_ptr(), self.bias.data_ptr(),
-        self._gammas, self.reg_is_zero, self.reg_multiplier,
-        labels.data_ptr() if labels is not None else None, labels_f.data_ptr() if labels_f is not None else None,
-        self.out3.data_ptr(), None, None, None, ens_out.data_ptr() if ens_out is not None else None, B, C,
-        self.workspace.data_ptr(), self.ws_bytes, sp), "adn_ensemble_head")
+    self.net.forward(self.lib, x, sp, xp)
+    self.ehead.enqueue_eval(labels, labels_f, ens_out, sp, xp)
 
 
 class IterationPlan:
