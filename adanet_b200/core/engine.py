@@ -89,7 +89,8 @@ class SubnetworkPlanSpec:
 
 @dataclass
 class EnsemblerPlanSpec:
-  """ComplexityRegularizedEnsembler arguments (adanet/ensemble/weighted.py:228-251)."""
+  """ComplexityRegularizedEnsembler arguments (adanet/ensemble/weighted.py:228-251); kind="mean" is the
+  MeanEnsembler (adanet/ensemble/mean.py:92-135)."""
   optimizer: Optional[tuple] = None
   mixture_weight_type: str = "scalar"
   adanet_lambda: float = 0.0
@@ -98,6 +99,7 @@ class EnsemblerPlanSpec:
   name: str = "complexity_regularized"
   legacy_train_op: bool = False
   warm_start_mixture_weights: bool = False   # weighted.py:270-285,487-516
+  kind: str = "complexity_regularized"
 
 
 def _opt_hyper(spec: tuple) -> Tuple[int, List[float]]:
@@ -635,7 +637,11 @@ class IterationPlan:
                ens: EnsemblerPlanSpec, batch: int, in_dim: int, logits_dim: int, head: str = "softmax_xent",
                adanet_loss_decay: float = 0.9, trace_capacity: int = 4096, device: Optional[torch.device] = None,
                candidate_indices: Optional[Sequence[int]] = None, use_cuda_graph: bool = True,
-               multi_stream: bool = True, prev_mixture_weights=None, prev_bias=None):
+               multi_stream: bool = True, prev_mixture_weights=None, prev_bias=None,
+               ensemble_candidates: Optional[Sequence[tuple]] = None):
+    """`ensemble_candidates`: the candidate ensembles whose members all live on this GPU, as
+    (global_index, name, [global subnetwork indices], keep_previous); None = one `*_grow` ensemble per local
+    subnetwork (GrowStrategy).  Several ensembles may share a subnetwork (adanet/ensemble/strategy.py:79-117)."""
     self.lib = _require_cuda()
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.iteration, self.batch, self.in_dim, self.C, self.head = iteration, batch, in_dim, logits_dim, head
@@ -648,6 +654,30 @@ class IterationPlan:
                                      adanet_loss_decay, trace_capacity, self.device, i,
                                      prev_mixture_weights=prev_mixture_weights, prev_bias=prev_bias)
                        for i, s in zip(idx, specs)]
+    # candidate ensembles: (global index, head, side-stream slot).  A `*_grow` ensemble over one local subnetwork
+    # is that CandidatePlan's own head; anything else (solo, all, ...) gets a head of its own over shared nets.
+    by_index = {c.index: k for k, c in enumerate(self.candidates)}
+    self.heads: List[tuple] = []
+    if ensemble_candidates is None:
+      self.heads = [(c.index, c.ehead, k) for k, c in enumerate(self.candidates)]
+    else:
+      for c in self.candidates:
+        c.has_head = False
+      for gidx, name, builders, keep_prev in ensemble_candidates:
+        local = [by_index[b] for b in builders]        # KeyError = a member lives on another rank (caller's bug)
+        full_name = "t{}_{}_{}".format(iteration, name, ens.name)            # iteration.py:691-693
+        own = self.candidates[local[0]]
+        if len(local) == 1 and keep_prev and name == "{}_grow".format(own.spec.name):
+          own.has_head = True
+          self.heads.append((gidx, own.ehead, local[0]))
+          continue
+        members = (list(self.frozen) if keep_prev else []) + [self.candidates[k].net for k in local]
+        h = EnsembleHead(self.lib, full_name, members, len(self.frozen) if keep_prev else 0, ens, batch, logits_dim,
+                         head, adanet_loss_decay, trace_capacity, self.device,
+                         prev_mixture_weights=prev_mixture_weights if keep_prev else None,
+                         prev_bias=prev_bias if keep_prev else None,
+                         sub_loss=own.sub_loss if len(local) == 1 else None)
+        self.heads.append((gidx, h, local[0]))
     self.x = torch.empty((batch, in_dim), dtype=torch.float32, device=self.device)
     # split planes of the minibatch, produced once per step and shared by every member and candidate
     self.xp = new_planes(batch, in_dim, self.device) if planes_enabled() else None
@@ -729,6 +759,12 @@ class IterationPlan:
           ev.record(s)
           main.wait_event(ev)          # the backward waves need every candidate's dlogits planes
         c.enqueue_ensemble(self.labels, self.labels_f, self.step_dev, s.cuda_stream, self.xp)
+    for _, h, slot in self.heads:        # ensembles that are not a CandidatePlan's own `_grow` head
+      if any(h is c.ehead for c in self.candidates):
+        continue
+      s = side[slot]
+      with torch.cuda.stream(s):
+        h.enqueue(self.labels, self.labels_f, self.step_dev, s.cuda_stream, self.xp)
     for k in range(max(len(c.net.ws) for c in self.candidates)):
       ops = [c.bwd_op(k, self.xp) for c in self.candidates if k < len(c.net.ws)]
       arr = (_lib.BwdOp * len(ops))(*ops)
@@ -761,6 +797,8 @@ class IterationPlan:
     else:
       for c in self.candidates:
         c.enqueue_train_step(self.x, self.labels, self.labels_f, self.step_dev, sp, self.xp)
+    if any(not any(h is c.ehead for c in self.candidates) for _, h, _ in self.heads):
+      raise NotImplementedError("ensembles that share subnetworks run on the plane path only")
     _lib.check(lib.adn_counter_add(self.step_dev.data_ptr(), 1, sp), "adn_counter_add")
 
   def _split_x(self, sp: int):
@@ -800,9 +838,11 @@ class IterationPlan:
     for f in self.frozen:
       f.forward(self.lib, self.x, sp, self.xp)
     for c in self.candidates:
-      c.enqueue_eval(self.x, self.labels, self.labels_f, None, sp, self.xp)
+      c.net.forward(self.lib, self.x, sp, self.xp)
+    for _, h, _ in self.heads:
+      h.enqueue_eval(self.labels, self.labels_f, None, sp, self.xp)
     torch.cuda.current_stream(self.device).synchronize()
-    return [float(c.out3[2].item()) for c in self.candidates]
+    return [float(h.out3[2].item()) for _, h, _ in self.heads]
 
   # -- in-flight checkpoint -------------------------------------------------------
   def state_dict(self) -> Dict[str, np.ndarray]:
@@ -812,6 +852,10 @@ class IterationPlan:
     for c in self.candidates:
       for k, v in c.state_dict().items():
         out["c%d_%s" % (c.index, k)] = v
+    for gidx, h, _ in self.heads:
+      if not any(h is c.ehead for c in self.candidates):
+        for k, v in h.state_dict().items():
+          out["h%d_%s" % (gidx, k)] = v
     return out
 
   def load_state_dict(self, st: Dict[str, np.ndarray]):
@@ -820,26 +864,30 @@ class IterationPlan:
     for c in self.candidates:
       pre = "c%d_" % c.index
       c.load_state_dict({k[len(pre):]: v for k, v in st.items() if k.startswith(pre)})
+    for gidx, h, _ in self.heads:
+      if not any(h is c.ehead for c in self.candidates):
+        pre = "h%d_" % gidx
+        h.load_state_dict({k[len(pre):]: v for k, v in st.items() if k.startswith(pre)})
     torch.cuda.current_stream(self.device).synchronize()
 
   # -- read-back ---------------------------------------------------------------
   def ema_losses(self) -> List[float]:
     """EMA adanet loss of each local candidate (candidate.py:125-129), one D2H read."""
     torch.cuda.current_stream(self.device).synchronize()
-    return [float(c.ema_state[2].item()) for c in self.candidates]
+    return [float(h.ema_state[2].item()) for _, h, _ in self.heads]
 
   def traces(self) -> Dict[str, Dict[str, np.ndarray]]:
     n = min(self.steps_done, self.trace_capacity)
     out = {}
-    for c in self.candidates:
-      t = c.trace[:n].cpu().numpy()
-      out[c.name] = {f: t[:, i].copy() for i, f in enumerate(TRACE_FIELDS)}
+    for _, h, _ in self.heads:
+      t = h.trace[:n].cpu().numpy()
+      out[h.name] = {f: t[:, i].copy() for i, f in enumerate(TRACE_FIELDS)}
     return out
 
   def last_losses(self) -> np.ndarray:
     """[n_candidates, 4] (sub_loss, ens_loss, adanet_loss, ema) of the most recent step."""
     row = (self.steps_done - 1) % self.trace_capacity
-    return torch.stack([c.trace[row] for c in self.candidates]).cpu().numpy()
+    return torch.stack([h.trace[row] for _, h, _ in self.heads]).cpu().numpy()
 
 
 class EnsembleEvalPlan:

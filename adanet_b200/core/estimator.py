@@ -151,9 +151,9 @@ class Estimator(object):
       raise NotImplementedError("the B200 engine trains one ensembler per run (got %d)" % len(self._ensemblers))
     e = self._ensemblers[0]
     if isinstance(e, ensemble_lib.MeanEnsembler):
-      # mean over the NEW subnetworks only (adanet/ensemble/mean.py:92-101): under GrowStrategy that is the
-      # new subnetwork itself; realised as SCALAR weights (0 for kept members, 1 for the new one), no training
-      raise NotImplementedError("MeanEnsembler is a 'next' row (SURVEY.md 8f.3); use ComplexityRegularizedEnsembler")
+      # mean over the candidate's NEW subnetworks only (adanet/ensemble/mean.py:92-101; previous members are
+      # ignored, nothing is trained): SCALAR weights 0 for kept members, 1/n_new for the new ones
+      return eng.EnsemblerPlanSpec(optimizer=None, mixture_weight_type="scalar", name=e.name, kind="mean")
     if not isinstance(e, ensemble_lib.ComplexityRegularizedEnsembler):
       raise NotImplementedError("custom Ensemblers are not supported by the B200 engine: %r" % (e,))
     return eng.EnsemblerPlanSpec(optimizer=train_lib.optimizer_from(e.optimizer), mixture_weight_type=e.mixture_weight_type,
@@ -162,9 +162,8 @@ class Estimator(object):
 
   def _check_strategies(self):
     for s in self._ensemble_strategies:
-      if not isinstance(s, ensemble_lib.GrowStrategy):
-        raise NotImplementedError("only GrowStrategy shards one-candidate-per-GPU (SURVEY.md 8e); %s is a 'next' row"
-                                  % type(s).__name__)
+      if not isinstance(s, ensemble_lib.Strategy):
+        raise ValueError("ensemble_strategies must be adanet.ensemble.Strategy instances, got %r" % (s,))
 
   def _generate_builders(self, iteration_number):
     gen = self._subnetwork_generator
@@ -186,14 +185,18 @@ class Estimator(object):
     for n in names:
       if names.count(n) > 1:
         raise ValueError("Two subnetworks have the same name '{}'".format(n))
+    from adanet_b200.core import search as srch
     cands = []
     for strategy in self._ensemble_strategies:
       cands += list(strategy.generate_ensemble_candidates(builders, list(self._member_builders)))
-    for c in cands:
-      if len(c.subnetwork_builders) != 1:
-        raise NotImplementedError("candidates with several new subnetworks are a 'next' row (SURVEY.md 8e)")
-      if len(c.previous_ensemble_subnetwork_builders) != len(self._member_builders):
-        raise NotImplementedError("pruning the previous ensemble is not implemented by the B200 engine")
+    ecands = []
+    for c in cands:     # strategy.py:26-76: (name, new builders, previous builders kept | None)
+      prev = c.previous_ensemble_subnetwork_builders
+      if prev and len(prev) != len(self._member_builders):
+        raise NotImplementedError("pruning only part of the previous ensemble is not implemented by the B200 engine")
+      ecands.append(srch.EnsembleCandidate(c.name, [builders.index(b) for b in c.subnetwork_builders],
+                                           bool(prev) or not self._member_builders))
+    self._pending_ecands = ecands
     placeholders = {k: graph.placeholder(w, k) for k, w in self._feature_widths.items()}
     labels_ph = graph.placeholder(1, "labels")
     specs, subs = [], []
@@ -220,7 +223,8 @@ class Estimator(object):
     self._search = srch.AdaNetSearch(self._search_space, self._ensembler_plan_spec(), self._in_dim,
                                      self._head.logits_dimension, self._batch_size, head=self._head.loss_kind,
                                      adanet_loss_decay=self._adanet_loss_decay, force_grow=self._force_grow,
-                                     replay_indices=replay, keep_traces=bool(self._debug))
+                                     replay_indices=replay, keep_traces=bool(self._debug),
+                                     candidates_fn=lambda specs, n_frozen: self._pending_ecands)
 
   def _inflight_path(self):
     return os.path.join(self._model_dir, "iteration-inflight-rank{}.npz".format(self._config.global_id_in_cluster))
@@ -392,11 +396,13 @@ class Estimator(object):
     else:
       rep = s.finish_iteration()
     ens = self._ensemblers[0]
-    if s.last_winner_index is not None:
-      ci = s.last_winner_index
-      self._member_subnetworks.append(subs[ci])
-      self._member_builders.append(builders[ci])
-      cand_name = "{}_grow".format(builders[ci].name)
+    if s.last_winner_builders is not None:
+      if not s.last_winner_keeps_previous:      # e.g. SoloStrategy: the previous ensemble's subnetworks are dropped
+        self._member_subnetworks, self._member_builders = [], []
+      for ci in s.last_winner_builders:
+        self._member_subnetworks.append(subs[ci])
+        self._member_builders.append(builders[ci])
+      cand_name = s.last_winner_name
     else:
       cand_name = self._last_candidate_name
     self._last_candidate_name = cand_name
@@ -406,11 +412,18 @@ class Estimator(object):
     for k, (sub, (it, name)) in enumerate(zip(self._member_subnetworks, rep.architecture)):
       ws.append(ensemble_lib.WeightedSubnetwork(name=name, iteration_number=it, weight=np.array(mw[k]), logits=sub.logits,
                                                 subnetwork=sub))
-    self._previous_ensemble = ensemble_lib.ComplexityRegularized(
-        weighted_subnetworks=ws, bias=np.asarray(rep.bias), logits=("weighted_sum", [w.logits for w in ws]),
-        subnetworks=[w.subnetwork for w in ws],
-        complexity_regularization=ens.complexity_regularization([w.weight for w in ws],
-                                                                [w.subnetwork.complexity for w in ws]))
+    if isinstance(ens, ensemble_lib.MeanEnsembler):
+      # mean.py:92-135: a MeanEnsemble carries the candidate's new subnetworks only
+      n_new = len(s.last_winner_builders) if s.last_winner_builders is not None else len(self._previous_ensemble.subnetworks)
+      new_subs = self._member_subnetworks[-n_new:]
+      self._previous_ensemble = ensemble_lib.MeanEnsemble(logits=("mean", [sb.logits for sb in new_subs]),
+                                                          subnetworks=new_subs, predictions=None)
+    else:
+      self._previous_ensemble = ensemble_lib.ComplexityRegularized(
+          weighted_subnetworks=ws, bias=np.asarray(rep.bias), logits=("weighted_sum", [w.logits for w in ws]),
+          subnetworks=[w.subnetwork for w in ws],
+          complexity_regularization=ens.complexity_regularization([w.weight for w in ws],
+                                                                  [w.subnetwork.complexity for w in ws]))
     arch = _Architecture(cand_name, ens.name, replay_indices=list(rep.replay_indices))
     for it, name in rep.architecture:
       arch.add_subnetwork(it, name)

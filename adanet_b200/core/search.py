@@ -64,6 +64,31 @@ class IterationReport:
   traces: Optional[Dict[str, Dict[str, np.ndarray]]] = None
 
 
+@dataclass
+class EnsembleCandidate:
+  """One candidate ensemble of an iteration (adanet/ensemble/strategy.py:26-76 `Candidate`): the strategy's
+  candidate name, the new subnetworks it contains (indices into the iteration's builders) and whether the
+  previous ensemble's subnetworks are kept."""
+  name: str
+  builders: List[int]
+  keep_previous: bool = True
+
+
+def strategy_candidates(strategies: Sequence[str], builder_names: Sequence[str]) -> List[EnsembleCandidate]:
+  """Grow / Solo / All (adanet/ensemble/strategy.py:79-117), in the order the strategies are listed."""
+  out: List[EnsembleCandidate] = []
+  for st in strategies:
+    if st == "grow":
+      out += [EnsembleCandidate("{}_grow".format(n), [i], True) for i, n in enumerate(builder_names)]
+    elif st == "solo":
+      out += [EnsembleCandidate("{}_solo".format(n), [i], False) for i, n in enumerate(builder_names)]
+    elif st == "all":
+      out.append(EnsembleCandidate("all", list(range(len(builder_names))), True))
+    else:
+      raise ValueError("unknown ensemble strategy %r" % (st,))
+  return out
+
+
 class AdaNetSearch:
   """Runs AdaNet iterations on this process's GPU (rank r of G owns candidates i % G == r)."""
 
@@ -72,7 +97,8 @@ class AdaNetSearch:
                head: str = "softmax_xent", adanet_loss_decay: float = 0.9, force_grow: bool = False,
                replay_indices: Optional[Sequence[int]] = None, device: Optional[torch.device] = None,
                use_cuda_graph: bool = True, multi_stream: bool = True, keep_traces: bool = True,
-               trace_capacity: int = 4096, placement: str = "balanced"):
+               trace_capacity: int = 4096, placement: str = "balanced", strategies: Sequence[str] = ("grow",),
+               candidates_fn: Optional[Callable] = None):
     self.search_space, self.ens = search_space, ensembler
     self.in_dim, self.C, self.batch, self.head = in_dim, logits_dim, batch_size, head
     self.decay, self.force_grow = adanet_loss_decay, force_grow
@@ -83,6 +109,9 @@ class AdaNetSearch:
     if placement not in ("balanced", "round_robin"):
       raise ValueError("placement must be 'balanced' or 'round_robin'")
     self.placement = placement
+    # candidate ensembles of an iteration: candidates_fn(specs, n_frozen) -> [EnsembleCandidate], or the named strategies
+    self.strategies = tuple(strategies)
+    self.candidates_fn = candidates_fn
     self.frozen: List[eng.DenseNet] = []
     self.iteration = 0
     self.prev_best_ema: Optional[float] = None
@@ -104,16 +133,29 @@ class AdaNetSearch:
       raise ValueError("Each iteration must have at least one Builder.")      # iteration.py:564-565
     self._specs = specs
     g, r = ex.world(), ex.rank()
-    # candidate -> rank: cost-balanced by training FLOPs per example (sum d_i d_{i+1}), or the reference-like i % G
+    # candidate ensembles (strategy candidates x this ensembler)
+    ecs = (self.candidates_fn(specs, len(self.frozen)) if self.candidates_fn is not None
+           else strategy_candidates(self.strategies, names))
+    if not ecs:
+      raise ValueError("the ensemble strategies produced no candidate")
+    self._ecands = ecs
+    # subnetwork -> rank.  Subnetworks read by the same candidate ensemble (e.g. AllStrategy) must share a GPU --
+    # splitting them would need the member logits gathered every step -- so the units of placement
+    # are the connected components of "shares an ensemble"; a component's cost is its training FLOPs per example
+    # (sum d_i d_{i+1}).  "balanced" = longest-processing-time first, "round_robin" = the reference-like i % G.
     costs = [sum(a * b for a, b in zip(s.dims[:-1], s.dims[1:])) for s in specs]
-    self._owners = (ex.balanced_owners(costs, g) if self.placement == "balanced"
-                    else ex.round_robin_owners(len(specs), g))
+    self._owners = ex.component_owners(costs, [c.builders for c in ecs], g, self.placement)
     mine = ex.owned_indices(len(specs), r, g, self._owners)
+    self._ec_owners = [self._owners[c.builders[0]] for c in ecs]
+    default_grow = (len(ecs) == len(specs) and all(
+        c.keep_previous and c.builders == [i] and c.name == "{}_grow".format(specs[i].name) for i, c in enumerate(ecs)))
+    local = None if default_grow else [(j, c.name, list(c.builders), c.keep_previous)
+                                       for j, c in enumerate(ecs) if self._ec_owners[j] == r]
     self.plan = eng.IterationPlan(self.iteration, [specs[i] for i in mine], self.frozen, self.ens, self.batch,
                                   self.in_dim, self.C, self.head, self.decay, self.trace_capacity, self.device,
                                   candidate_indices=mine, use_cuda_graph=self.use_cuda_graph,
                                   multi_stream=self.multi_stream, prev_mixture_weights=self.mixture_weights,
-                                  prev_bias=self.bias)
+                                  prev_bias=self.bias, ensemble_candidates=local)
     return self.plan
 
   def train_iteration(self, batches: Iterator, steps: int, on_step=None) -> float:
@@ -147,12 +189,13 @@ class AdaNetSearch:
     previous ensemble, and `objective_fn` is np.nanargmin / np.nanargmax
     (estimator.py:1487-1490)."""
     plan, specs, t = self.plan, self._specs, self.iteration
-    k = len(specs)
+    ecs, ec_owners = self._ecands, self._ec_owners
+    k = len(ecs)
     g = ex.world()
     local = plan.ema_losses() if local_metric_fn is None else list(local_metric_fn(plan))
-    new_losses = ex.gather_candidate_losses(local, k, device=self.device, owners=self._owners)
+    new_losses = ex.gather_candidate_losses(local, k, device=self.device, owners=ec_owners)
     ens_name = self.ens.name
-    names = ["t{}_{}_grow_{}".format(t, s.name, ens_name) for s in specs]
+    names = ["t{}_{}_{}".format(t, c.name, ens_name) for c in ecs]
     losses = list(new_losses)
     if t > 0:
       names = ["previous_ensemble"] + names
@@ -166,40 +209,45 @@ class AdaNetSearch:
       best = int(objective_fn(np.asarray(losses[1:], dtype=np.float32))) + 1
     else:
       best = int(objective_fn(np.asarray(losses, dtype=np.float32)))
-    ema_all = (ex.gather_candidate_losses(plan.ema_losses(), k, device=self.device, owners=self._owners)
+    ema_all = (ex.gather_candidate_losses(plan.ema_losses(), k, device=self.device, owners=ec_owners)
                if local_metric_fn is not None else new_losses)
     traces = plan.traces() if self.keep_traces else None
     self.last_winner_index = None
+    self.last_winner_builders, self.last_winner_keeps_previous = None, True
     if t > 0 and best == 0:
       pass   # previous ensemble kept; nothing grows
     else:
       ci = best - (1 if t > 0 else 0)
-      owner = self._owners[ci]
-      spec = specs[ci]
-      # materialise the winner's subnetwork on every rank for frozen replay
+      ec = ecs[ci]
+      owner = ec_owners[ci]
       matrix = self.ens.mixture_weight_type == "matrix"
+      kept = list(self.frozen) if ec.keep_previous else []
+      # materialise the winner's new subnetworks on every rank for frozen replay
       if ex.rank() == owner:
-        cand = next(c for c in plan.candidates if c.index == ci)
-        member = cand.net
-        mix_ws, bias = cand.mixture_weight_tensors(), cand.bias
+        head = next(h for gidx, h, _ in plan.heads if gidx == ci)
+        new_members = [next(c for c in plan.candidates if c.index == b).net for b in ec.builders]
+        mix_ws, bias = head.mixture_weight_tensors(), head.bias
       else:
-        member = eng.DenseNet(spec.name, spec.dims, spec.ws, spec.bs, spec.complexity, self.batch, self.device,
-                              t, spec.shared)
-        n_members = len(self.frozen) + 1
+        new_members = [eng.DenseNet(specs[b].name, specs[b].dims, specs[b].ws, specs[b].bs, specs[b].complexity,
+                                    self.batch, self.device, t, specs[b].shared) for b in ec.builders]
+        n_members = len(kept) + len(new_members)
         if matrix:
           mix_ws = [torch.empty((m.last_layer_dim, self.C), dtype=torch.float32, device=self.device)
-                    for m in list(self.frozen) + [member]]
+                    for m in kept + new_members]
         else:
           wshape = (n_members,) if self.ens.mixture_weight_type == "scalar" else (n_members, self.C)
           mix_ws = [torch.empty(wshape, dtype=torch.float32, device=self.device)]
         bias = torch.empty((self.C,), dtype=torch.float32, device=self.device)
-      ex.broadcast_tensors(member.ws + member.bs + mix_ws + [bias], src=owner)
+      ex.broadcast_tensors([t_ for m in new_members for t_ in (m.ws + m.bs)] + mix_ws + [bias], src=owner)
       if ex.rank() != owner:
-        member.refresh_planes()   # its planes were split from the (pre-broadcast) initial weights
-      self.frozen = self.frozen + [member]
-      self.architecture = self.architecture + [(t, spec.name)]
+        for m in new_members:
+          m.refresh_planes()   # their planes were split from the (pre-broadcast) initial weights
+      self.frozen = kept + new_members
+      self.architecture = (self.architecture if ec.keep_previous else []) + [(t, specs[b].name) for b in ec.builders]
       self.prev_best_ema = ema_all[ci]
-      self.last_winner_index = ci
+      self.last_winner_index = ec.builders[-1]
+      self.last_winner_builders, self.last_winner_keeps_previous = list(ec.builders), ec.keep_previous
+      self.last_winner_name = ec.name
       # SCALAR [N] / VECTOR [N,C] array, or the list of N [D_k,C] matrices (MATRIX)
       self.mixture_weights = ([w.cpu().numpy().copy() for w in mix_ws] if matrix else mix_ws[0].cpu().numpy().copy())
       self.bias = bias.cpu().numpy().copy()

@@ -55,6 +55,33 @@ def balanced_owners(costs: Sequence[float], world_size: int) -> List[int]:
   return owners
 
 
+def component_owners(costs: Sequence[float], groups: Sequence[Sequence[int]], world_size: int,
+                     placement: str = "balanced") -> List[int]:
+  """Owner rank of every subnetwork when `groups[j]` lists the subnetworks candidate ensemble j reads.
+
+  Subnetworks read by one ensemble must share a GPU, so the connected components of the "shares an ensemble"
+  relation are placed as units (cost = sum of member costs): LPT for "balanced", component-index % G for
+  "round_robin".  With one subnetwork per ensemble (GrowStrategy) this is exactly balanced_owners / i % G."""
+  n = len(costs)
+  comp = list(range(n))
+
+  def find(i):
+    while comp[i] != i:
+      comp[i] = comp[comp[i]]
+      i = comp[i]
+    return i
+
+  for grp in groups:
+    for b in grp[1:]:
+      ra, rb = find(grp[0]), find(b)
+      comp[max(ra, rb)] = min(ra, rb)
+  roots = sorted({find(i) for i in range(n)})
+  comp_cost = [sum(float(costs[i]) for i in range(n) if find(i) == q) for q in roots]
+  comp_owner = balanced_owners(comp_cost, world_size) if placement == "balanced" else \
+      round_robin_owners(len(roots), world_size)
+  return [comp_owner[roots.index(find(i))] for i in range(n)]
+
+
 def owned_indices(num_candidates: int, rank_: int, world_size: int, owners: Optional[Sequence[int]] = None) -> List[int]:
   owners = owners if owners is not None else round_robin_owners(num_candidates, world_size)
   return [i for i in range(num_candidates) if owners[i] == rank_]

@@ -116,3 +116,16 @@ def test_single_process_passthrough():
   assert ex.gather_candidate_losses([0.3, 0.1], 2) == [pytest.approx(0.3), pytest.approx(0.1)]
   ex.broadcast_tensors([torch.zeros(3)], src=0)
   assert ex.max_over_ranks(2.5) == 2.5
+
+
+def test_component_owners_keeps_shared_ensembles_on_one_rank():
+  from adanet_b200.distributed import exchange as ex
+  costs = [4, 1, 2, 8]
+  # GrowStrategy: one subnetwork per ensemble -> same as balanced / round robin
+  assert ex.component_owners(costs, [[0], [1], [2], [3]], 2) == ex.balanced_owners(costs, 2)
+  assert ex.component_owners(costs, [[0], [1], [2], [3]], 2, "round_robin") == [0, 1, 0, 1]
+  # AllStrategy ties everything to one rank; a partial tie moves as a unit
+  assert ex.component_owners(costs, [[0], [1], [2], [3], [0, 1, 2, 3]], 4) == [0, 0, 0, 0]
+  o = ex.component_owners(costs, [[0, 2], [1], [3]], 2)
+  assert o[0] == o[2] and o[3] != o[0]
+  assert ex.component_owners([], [], 3) == []

@@ -296,3 +296,55 @@ def test_nan_candidate_loses_selection(env):
   assert not np.isfinite(wild) and np.isfinite(sane)
   assert rep.best_index == 0 and rep.architecture == [(0, "sane")]
   assert np.isfinite(est.evaluate(_input_fn(x[:B], y[:B]), steps=1)["loss"])
+
+
+def test_estimator_with_all_solo_grow_strategies_and_mean_ensembler(env):
+  """ensemble_strategies=[AllStrategy, SoloStrategy, GrowStrategy] and MeanEnsembler through the public API
+  (adanet/ensemble/strategy.py:79-117, mean.py:92-135) against the oracle's generalised runner."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  from adanet_b200.examples import simple_dnn
+  x, y = _data(orc)
+  steps, iters, lr = 10, 3, 0.05
+  strat = [adanet.ensemble.AllStrategy(), adanet.ensemble.SoloStrategy(), adanet.ensemble.GrowStrategy()]
+
+  def make(ensembler):
+    gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)], optimizer=train.GradientDescentOptimizer(lr),
+                               layer_size=16, seed=SEED)
+    return adanet.Estimator(head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
+                            ensemblers=[ensembler], ensemble_strategies=strat, max_iterations=iters, debug=True)
+
+  est = make(adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(0.01),
+                                                            adanet_lambda=0.01, adanet_beta=0.001))
+  est.train(_input_fn(x, y), max_steps=steps * iters)
+  ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+  want, frozen = orc.run_adanet_strategies(_oracle_simple_dnn_space(orc, 16, lr), x, y, B, steps, iters, ens, C,
+                                           strategies=("all", "solo", "grow"))
+  for rep, res in zip(est._search.reports, want):
+    assert rep.candidate_names == res.candidate_names
+    assert rep.best_index == res.best_index and rep.architecture == res.architecture
+    np.testing.assert_allclose(rep.ema_losses, res.ema_losses, atol=1e-5, rtol=0)
+  assert est.architecture_string() == "| " + " | ".join(n for _, n in want[-1].architecture) + " |"
+  # MeanEnsembler: named "mean", nothing trained, selection by the mean-of-new-subnetworks loss.  A MeanEnsemble
+  # has no weighted_subnetworks (simple_dnn.Generator reads them), so the search space is two fixed builders.
+  fixed = [simple_dnn._SimpleDNNBuilder([graph.numeric_column("x", D)], train.GradientDescentOptimizer(lr), 16, nl, False,
+                                        0., SEED) for nl in (1, 2)]
+  est = adanet.Estimator(head=adanet.heads.MultiClassHead(C), subnetwork_generator=adanet.subnetwork.SimpleGenerator(fixed),
+                         max_iteration_steps=steps, ensemblers=[adanet.ensemble.MeanEnsembler()], ensemble_strategies=strat,
+                         max_iterations=2, debug=True)
+  est.train(_input_fn(x, y), max_steps=steps * 2)
+
+  def fixed_space(t, frozen):
+    specs = []
+    for nl in (1, 2):
+      dims = [D] + [16] * nl + [C]
+      ws = [_glorot((dims[i], dims[i + 1]), SEED) for i in range(len(dims) - 1)]
+      specs.append(orc.SubnetworkSpec("{}_layer_dnn".format(nl), dims, float(np.sqrt(np.float32(nl))), ("sgd", lr), ws=ws,
+                                      bs=[np.zeros((d_,), np.float32) for d_ in dims[1:]]))
+    return specs
+
+  want, _ = orc.run_adanet_strategies(fixed_space, x, y, B, steps, 2, orc.EnsemblerSpec(name="mean"), C,
+                                      strategies=("all", "solo", "grow"), mean_ensembler=True)
+  for rep, res in zip(est._search.reports, want):
+    assert rep.candidate_names == res.candidate_names and rep.best_index == res.best_index
+    np.testing.assert_allclose(rep.ema_losses, res.ema_losses, atol=1e-5, rtol=0)

@@ -261,3 +261,42 @@ def test_full_size_properties(built_lib):
   got = outs[0][0][torch.as_tensor(ii).cuda(), torch.as_tensor(oo).cuda()].cpu().numpy()
   scale = float((xs.abs() * ds.abs()).sum(0).max())
   assert np.abs(got - want).max() <= 3e-6 * scale
+
+
+STRATEGY_CASES = {
+    # adanet/ensemble/strategy.py:79-117: several candidate ensembles share the iteration's subnetworks
+    "all_solo_grow": dict(strategies=("all", "solo", "grow"), ens=dict(optimizer=("sgd", 0.01), adanet_lambda=0.01,
+                                                                       adanet_beta=0.001, use_bias=True)),
+    "solo_only": dict(strategies=("solo",), ens=ENS),
+    "all_matrix": dict(strategies=("all",), ens=dict(optimizer=("sgd", 0.02), adanet_lambda=0.01, use_bias=True,
+                                                     mixture_weight_type="matrix")),
+    # adanet/ensemble/mean.py:92-135: mean of the new subnetworks' logits, nothing trained
+    "mean_grow": dict(strategies=("grow",), mean=True, ens=dict(optimizer=None)),
+    "mean_all": dict(strategies=("all",), mean=True, ens=dict(optimizer=None)),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(STRATEGY_CASES))
+def test_strategy_parity(built_lib, name):
+  from adanet_b200.core import engine as eng
+  from adanet_b200.core import search as srch
+  case = STRATEGY_CASES[name]
+  d, c, B, steps, iters = 100, 10, 256, 20, 3
+  x, y = orc.make_tabular(8192, d, c, seed=21)
+  cfgs = [(1, 48), (2, 32), (3, 24)]
+  o_ens = orc.EnsemblerSpec(**case["ens"])
+  o, _ = orc.run_adanet_strategies(lambda t, frozen: pu.make_specs(cfgs, d, c, t, ("sgd", 0.02))[0], x, y, B, steps, iters,
+                                   o_ens, c, strategies=case["strategies"], mean_ensembler=case.get("mean", False))
+  e_ens = eng.EnsemblerPlanSpec(kind="mean" if case.get("mean") else "complexity_regularized", **case["ens"])
+  s = srch.AdaNetSearch(lambda t, frozen: pu.make_specs(cfgs, d, c, t, ("sgd", 0.02))[1], e_ens, d, c, B,
+                        strategies=case["strategies"])
+  reps = s.run(srch.consecutive_batches(x, y, B), steps, iters)
+  for ro, r in zip(o, reps):
+    assert r.candidate_names == ro.candidate_names
+    for cname, tr in ro.traces.items():
+      for f in ("sub_loss", "ens_loss", "adanet_loss", "ema"):
+        np.testing.assert_allclose(r.traces[cname][f], np.asarray(tr[f], dtype=np.float64), atol=TOL, rtol=0, equal_nan=True)
+    assert r.best_index == ro.best_index and r.architecture == ro.architecture
+    np.testing.assert_allclose(r.ema_losses, ro.ema_losses, atol=TOL)
+  assert [m.name for m in s.frozen] == [n for _, n in o[-1].architecture]

@@ -1,0 +1,110 @@
+"""Two-GPU parity: candidates sharded over ranks, NCCL only at the iteration boundary.
+
+Every rank trains the subnetworks / candidate ensembles it owns; at the end of an iteration the EMA losses are
+all-gathered and the winner's weights broadcast (distributed/exchange.py).  The result -- per-step losses of every
+candidate, selected index, architecture, mixture weights -- must equal the single-process oracle's, whatever the
+placement.  Needs 2 GPUs on the box (`gpurun --gpus 2`); skipped otherwise.
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from tests import parity_util as pu
+from tests.parity_util import orc
+
+TOL = 1e-5
+
+CASES = {
+    # four subnetworks of very different cost -> LPT placement puts the widest alone on one rank
+    "grow_balanced": dict(cfgs=[(1, 48), (2, 32), (3, 24), (2, 96)], strategies=("grow",), placement="balanced"),
+    "grow_round_robin": dict(cfgs=[(1, 48), (2, 32), (3, 24)], strategies=("grow",), placement="round_robin"),
+    # Solo + Grow heads over the same subnetwork stay with it
+    "solo_grow": dict(cfgs=[(1, 48), (2, 32), (3, 24)], strategies=("solo", "grow"), placement="balanced"),
+    # AllStrategy reads every subnetwork: one component, one rank; the other rank owns nothing this iteration
+    "all_solo_grow": dict(cfgs=[(1, 48), (2, 32)], strategies=("all", "solo", "grow"), placement="balanced"),
+    # a single candidate on two GPUs: rank 1 idles and still takes part in the exchange
+    "one_candidate": dict(cfgs=[(2, 32)], strategies=("grow",), placement="balanced"),
+}
+D, C, B, STEPS, ITERS = 100, 10, 256, 12, 3
+ENS = dict(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001, use_bias=True)
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, q):
+  import torch
+  import torch.distributed as dist
+  os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  try:
+    from adanet_b200.core import engine as eng
+    from adanet_b200.core import search as srch
+    x, y = orc.make_tabular(8192, D, C, seed=21)
+    s = srch.AdaNetSearch(lambda t, frozen: pu.make_specs(case["cfgs"], D, C, t, ("sgd", 0.02))[1],
+                          eng.EnsemblerPlanSpec(**ENS), D, C, B, strategies=case["strategies"],
+                          placement=case["placement"])
+    reps = s.run(srch.consecutive_batches(x, y, B), STEPS, ITERS)
+    out = []
+    for r in reps:
+      mw = r.mixture_weights
+      out.append(dict(names=list(r.candidate_names), ema=[float(v) for v in r.ema_losses], best=int(r.best_index),
+                      arch=list(r.architecture), mw=np.asarray(mw), bias=np.asarray(r.bias),
+                      traces={k: {f: np.asarray(v[f]) for f in ("sub_loss", "adanet_loss", "ema")}
+                              for k, v in (r.traces or {}).items()}))
+    frozen = [[w.cpu().numpy() for w in m.ws] for m in s.frozen]
+    q.put((rank, out, frozen))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_two_gpu_search_matches_oracle(built_lib, name):
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  import torch.multiprocessing as mp
+  case = CASES[name]
+  x, y = orc.make_tabular(8192, D, C, seed=21)
+  want, o_frozen = orc.run_adanet_strategies(lambda t, frozen: pu.make_specs(case["cfgs"], D, C, t, ("sgd", 0.02))[0], x, y,
+                                             B, STEPS, ITERS, orc.EnsemblerSpec(**ENS), C, strategies=case["strategies"])
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  got = {}
+  for _ in procs:
+    rank, out, frozen = q.get(timeout=240)
+    got[rank] = (out, frozen)
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  seen = set()
+  for rank in (0, 1):
+    out, frozen = got[rank]
+    for t, (r, ro) in enumerate(zip(out, want)):
+      # every rank reaches the same decision from the gathered losses
+      assert r["names"] == ro.candidate_names and r["best"] == ro.best_index and r["arch"] == ro.architecture
+      np.testing.assert_allclose(r["ema"], ro.ema_losses, atol=TOL)
+      np.testing.assert_allclose(r["mw"], np.asarray(ro.mixture_weights), atol=TOL)
+      np.testing.assert_allclose(r["bias"], np.asarray(ro.bias), atol=TOL)
+      for cname, tr in r["traces"].items():          # the candidates this rank trained, step by step
+        seen.add((t, cname))
+        for f in ("sub_loss", "adanet_loss", "ema"):
+          np.testing.assert_allclose(tr[f], np.asarray(ro.traces[cname][f], dtype=np.float64), atol=TOL, equal_nan=True)
+    # the frozen members (winner weights broadcast from their owner) agree on both ranks and with the oracle
+    assert len(frozen) == len(o_frozen)
+    for ws, m in zip(frozen, o_frozen):
+      for w, wo in zip(ws, m.ws):
+        np.testing.assert_allclose(w, wo, atol=2e-5)
+  assert seen == {(t, cname) for t, ro in enumerate(want) for cname in ro.traces}   # every candidate trained somewhere
