@@ -19,17 +19,17 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libadanet_b200.so")
 ACT_NONE, ACT_RELU = 0, 1
 HEAD_SOFTMAX_XENT, HEAD_MSE, HEAD_SIGMOID_XENT = 0, 1, 2
 MIX_SCALAR, MIX_VECTOR, MIX_MATRIX = 0, 1, 2
-OPT_SGD, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADAM = 0, 1, 2, 3
+OPT_SGD, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADAM, OPT_MOMENTUM_COSINE = 0, 1, 2, 3, 4
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 (Q_VERSION, Q_DENSE_BWD_WS, Q_HEAD_WS, Q_DENSE_FWD_PATH, Q_SM_COUNT, Q_LAUNCH_COUNT, Q_DENSE_BWD_PATH,
- Q_DENSE_FWD_WS, Q_PLANES_BYTES, Q_DENSE_BWD_P_WS, Q_COLSUM_WS) = range(11)
+ Q_DENSE_FWD_WS, Q_PLANES_BYTES, Q_DENSE_BWD_P_WS, Q_COLSUM_WS, Q_CONV_STEM_BWD_WS) = range(12)
 
 EXPORTS = (
     "adn_last_error", "adn_init", "adn_query", "adn_set_dense_path", "adn_dense_fwd", "adn_dense_bwd", "adn_head_loss",
     "adn_ensemble_head", "adn_opt_step", "adn_l1_norm", "adn_ema_update", "adn_record_scalars",
     "adn_counter_add", "adn_planes_split", "adn_planes_merge", "adn_dense_fwd_p", "adn_dense_bwd_p", "adn_colsum",
     "adn_opt_step_p", "adn_head_loss_p", "adn_dense_fwd_p_group", "adn_dense_bwd_p_group",
-    "adn_l1_grad_add",
+    "adn_l1_grad_add", "adn_conv_stem_fwd", "adn_conv_stem_bwd",
 )
 
 
@@ -88,6 +88,8 @@ def load():
   lib.adn_colsum.argtypes = [p, i64, i64, p, p, i64, p]
   lib.adn_head_loss_p.argtypes = [c_int, p, p, p, p, p, p, p, i64, i64, p, i64, p]
   lib.adn_l1_grad_add.argtypes = [p, p, i64, f32, p]
+  lib.adn_conv_stem_fwd.argtypes = [p, p, p, p, p, i64, c_int, c_int, c_int, c_int, p]
+  lib.adn_conv_stem_bwd.argtypes = [p, p, p, p, p, i64, c_int, c_int, c_int, c_int, p, i64, p]
   lib.adn_dense_fwd_p_group.argtypes = [POINTER(FwdOp), c_int, i64, p]
   lib.adn_dense_bwd_p_group.argtypes = [POINTER(BwdOp), c_int, i64, p]
   lib.adn_opt_step_p.argtypes = [c_int, POINTER(p), POINTER(p), POINTER(p), POINTER(p), POINTER(i64), c_int,

@@ -41,8 +41,11 @@ from adanet_b200 import _lib
 
 _HEAD_KIND = {"softmax_xent": _lib.HEAD_SOFTMAX_XENT, "mse": _lib.HEAD_MSE, "sigmoid_xent": _lib.HEAD_SIGMOID_XENT}
 _MIX_KIND = {"scalar": _lib.MIX_SCALAR, "vector": _lib.MIX_VECTOR, "matrix": _lib.MIX_MATRIX}
-_OPT_KIND = {"sgd": _lib.OPT_SGD, "momentum": _lib.OPT_MOMENTUM, "rmsprop": _lib.OPT_RMSPROP, "adam": _lib.OPT_ADAM}
-_OPT_DEFAULTS = {"sgd": (), "momentum": (), "rmsprop": (0.9, 0.0, 1e-10), "adam": (0.9, 0.999, 1e-8)}
+_OPT_KIND = {"sgd": _lib.OPT_SGD, "momentum": _lib.OPT_MOMENTUM, "rmsprop": _lib.OPT_RMSPROP, "adam": _lib.OPT_ADAM,
+             "momentum_cosine": _lib.OPT_MOMENTUM_COSINE}
+# ("momentum_cosine", lr, momentum, decay_steps[, alpha]): Momentum under tf.train.cosine_decay of the iteration step
+_OPT_DEFAULTS = {"sgd": (), "momentum": (), "rmsprop": (0.9, 0.0, 1e-10), "adam": (0.9, 0.999, 1e-8),
+                 "momentum_cosine": (0.0,)}
 TRACE_FIELDS = ("sub_loss", "ens_loss", "adanet_loss", "ema")
 
 
@@ -77,6 +80,10 @@ class SubnetworkPlanSpec:
   [d0, H, ..., H, logits_dim]; `optimizer` is ("sgd", lr) | ("momentum", lr, m)
   | ("rmsprop", lr[, rho, mu, eps]) | ("adam", lr[, b1, b2, eps]) with TF1
   semantics; `ws`/`bs` are the initial kernels W[in,out] / biases (NumPy fp32).
+
+  A SimpleCNN subnetwork (customizing_adanet.ipynb SimpleCNNBuilder) is the same dense stack behind a conv stem:
+  `ws[0]` is then the 4-D HWIO kernel [3,3,Cin,F] and `bs[0]` its bias, `image_shape` = (H, W, Cin) of the NHWC
+  minibatch, and `dims[0]` = (H/2)(W/2)F, the flattened pooled feature map the first dense layer consumes.
   """
   name: str
   dims: Sequence[int]
@@ -85,6 +92,7 @@ class SubnetworkPlanSpec:
   ws: List[np.ndarray]
   bs: List[np.ndarray]
   shared: Optional[dict] = None
+  image_shape: Optional[Tuple[int, int, int]] = None
 
 
 @dataclass
@@ -106,7 +114,7 @@ def _opt_hyper(spec: tuple) -> Tuple[int, List[float]]:
   kind = spec[0]
   vals = list(spec[1:])
   defaults = _OPT_DEFAULTS[kind]
-  n_fixed = {"sgd": 1, "momentum": 2, "rmsprop": 1, "adam": 1}[kind]
+  n_fixed = {"sgd": 1, "momentum": 2, "rmsprop": 1, "adam": 1, "momentum_cosine": 3}[kind]
   extra = vals[n_fixed:]
   vals = vals[:n_fixed] + list(extra) + list(defaults[len(extra):])
   return _OPT_KIND[kind], [float(v) for v in vals]
@@ -123,13 +131,15 @@ class _Optimizer:
       self._planes = _lib.ptr_array([pl.data_ptr() if pl is not None else None for pl in planes])
       self._cols = _lib.i64_array([p.shape[-1] if pl is not None else 0 for p, pl in zip(params, planes)])
     dev = params[0].device
-    n_slots = {_lib.OPT_SGD: 0, _lib.OPT_MOMENTUM: 1, _lib.OPT_RMSPROP: 2, _lib.OPT_ADAM: 2}[self.kind]
+    n_slots = {_lib.OPT_SGD: 0, _lib.OPT_MOMENTUM: 1, _lib.OPT_RMSPROP: 2, _lib.OPT_ADAM: 2,
+               _lib.OPT_MOMENTUM_COSINE: 1}[self.kind]
     self.slot0 = [torch.zeros_like(p) for p in params] if n_slots >= 1 else None
     self.slot1 = [torch.zeros_like(p) for p in params] if n_slots >= 2 else None
     if self.kind == _lib.OPT_RMSPROP:
       for s in self.slot0:
         s.fill_(1.0)   # TF RMSProp: ms initialised to ones
-    self.step_dev = torch.zeros((), dtype=torch.int64, device=dev) if self.kind == _lib.OPT_ADAM else None
+    self.step_dev = (torch.zeros((), dtype=torch.int64, device=dev)
+                     if self.kind in (_lib.OPT_ADAM, _lib.OPT_MOMENTUM_COSINE) else None)
     self._p = _lib.ptr_array([p.data_ptr() for p in params])
     self._s0 = _lib.ptr_array([s.data_ptr() for s in self.slot0]) if self.slot0 else None
     self._s1 = _lib.ptr_array([s.data_ptr() for s in self.slot1]) if self.slot1 else None
@@ -174,11 +184,31 @@ class DenseNet:
   """
 
   def __init__(self, name: str, dims: Sequence[int], ws, bs, complexity: float, batch: int,
-               device: torch.device, iteration: int = 0, shared: Optional[dict] = None):
+               device: torch.device, iteration: int = 0, shared: Optional[dict] = None,
+               image_shape: Optional[Sequence[int]] = None):
     self.name, self.dims, self.complexity, self.iteration = name, list(dims), float(complexity), iteration
     self.shared = shared or {}
     self.batch = batch
     self.device = device
+    # conv stem (SimpleCNN): a 4-D HWIO first kernel; conv3x3+ReLU+maxpool+flatten into the planes of dims[0]
+    self.stem = None
+    self.image_shape = tuple(int(v) for v in image_shape) if image_shape is not None else None
+    if len(ws) and np.ndim(ws[0]) == 4:
+      if self.image_shape is None:
+        raise ValueError("subnetwork %s has a conv stem but no image_shape" % name)
+      h, w, cin = self.image_shape
+      k = np.ascontiguousarray(ws[0], dtype=np.float32)
+      if k.shape[:3] != (3, 3, cin) or dims[0] != (h // 2) * (w // 2) * k.shape[3]:
+        raise ValueError("conv stem of %s: kernel %s / image %s do not give dims[0]=%d" % (name, k.shape, self.image_shape, dims[0]))
+      if not planes_enabled():
+        raise NotImplementedError("conv-stem subnetworks run on the plane path only")
+      self.stem = dict(h=h, w=w, cin=cin, f=int(k.shape[3]))
+      self.stem_k = torch.as_tensor(k).to(device)
+      self.stem_b = torch.as_tensor(np.ascontiguousarray(bs[0], dtype=np.float32)).to(device)
+      self.stem_out = new_planes(batch, dims[0], device)
+      self.stem_arg = torch.zeros((batch * dims[0] // 16,), dtype=torch.int32, device=device)
+      ws, bs = ws[1:], bs[1:]
+    self.in_dim = int(np.prod(self.image_shape)) if self.stem else self.dims[0]
     assert len(ws) == len(dims) - 1
     self.ws = [torch.as_tensor(np.ascontiguousarray(w, dtype=np.float32)).to(device) for w in ws]
     self.bs = [torch.as_tensor(np.ascontiguousarray(b, dtype=np.float32)).to(device) for b in bs]
@@ -218,7 +248,18 @@ class DenseNet:
   def last_layer_planes(self, xp: torch.Tensor) -> torch.Tensor:
     """Split planes of the last layer (MATRIX mixture weights multiply it, weighted.py:449): the last hidden
     activation, or the input itself for a linear model (simple_dnn.py:70-78)."""
-    return self.hp[-1] if len(self.dims) > 2 else xp
+    return self.hp[-1] if len(self.dims) > 2 else (self.stem_out if self.stem else xp)
+
+  def all_params(self) -> List[torch.Tensor]:
+    """Every trainable tensor (what the end-of-iteration broadcast of the winner moves)."""
+    return ([self.stem_k, self.stem_b] if self.stem else []) + self.ws + self.bs
+
+  def stem_forward(self, lib, x: torch.Tensor, sp: int):
+    """images [batch, H*W*Cin] (NHWC) -> planes of the flattened pooled features + the pool arg-max."""
+    st = self.stem
+    _lib.check(lib.adn_conv_stem_fwd(x.data_ptr(), self.stem_k.data_ptr(), self.stem_b.data_ptr(), self.stem_out.data_ptr(),
+                                     self.stem_arg.data_ptr(), self.batch, st["h"], st["w"], st["cin"], st["f"], sp),
+               "adn_conv_stem_fwd")
 
   @property
   def last_layer_dim(self) -> int:
@@ -239,7 +280,7 @@ class DenseNet:
   def fwd_op(self, i: int, xp: torch.Tensor) -> "_lib.FwdOp":
     """Layer i as an adn_fwd_op (plane path): hidden layers write planes, the logits layer dense fp32."""
     last = i == len(self.ws) - 1
-    src = xp if i == 0 else self.hp[i - 1]
+    src = (self.stem_out if self.stem else xp) if i == 0 else self.hp[i - 1]
     return _lib.FwdOp(src.data_ptr(), self.wps[i].data_ptr(), self.bs[i].data_ptr(),
                       None if last else self.hp[i].data_ptr(), self.acts[i].data_ptr() if last else None,
                       self.dims[i], self.dims[i + 1], _lib.ACT_NONE if last else _lib.ACT_RELU, 0)
@@ -249,6 +290,9 @@ class DenseNet:
     n = len(self.ws)
     if self.planes:
       hp = xp
+      if self.stem:
+        self.stem_forward(lib, x, sp)
+        hp = self.stem_out
       for i in range(n):
         last = i == n - 1
         _lib.check(lib.adn_dense_fwd_p(hp.data_ptr(), self.wps[i].data_ptr(), self.bs[i].data_ptr(),
@@ -268,7 +312,11 @@ class DenseNet:
       h = self.acts[i]
 
   def numpy_params(self):
-    return [w.cpu().numpy() for w in self.ws], [b.cpu().numpy() for b in self.bs]
+    """(kernels, biases) in layer order; a conv stem's HWIO kernel / bias come first."""
+    ws, bs = [w.cpu().numpy() for w in self.ws], [b.cpu().numpy() for b in self.bs]
+    if self.stem:
+      ws, bs = [self.stem_k.cpu().numpy()] + ws, [self.stem_b.cpu().numpy()] + bs
+    return ws, bs
 
 
 class EnsembleHead:
@@ -472,7 +520,7 @@ class CandidatePlan:
     self.batch, self.C, self.head = batch, logits_dim, _HEAD_KIND[head]
     self.name = "t{}_{}_grow_{}".format(iteration, spec.name, ens.name)   # iteration.py:633,691-693
     self.net = DenseNet(spec.name, spec.dims, spec.ws, spec.bs, spec.complexity, batch, device, iteration,
-                        spec.shared)
+                        spec.shared, spec.image_shape)
     self.frozen = list(frozen)
     dims = self.net.dims
     f32 = dict(dtype=torch.float32, device=device)
@@ -500,6 +548,16 @@ class CandidatePlan:
     self.ws_bytes = ws_bytes
     self.sub_loss = torch.zeros((1,), **f32)
     params, self._grads, planes = [], [], []
+    if self.net.stem:
+      # conv stem: dense gradient of the pooled features (first dense layer's dX), kernel / bias gradients
+      st = self.net.stem
+      self.dpool = torch.empty((batch, dims[0]), **f32)
+      self.d_stem_k, self.d_stem_b = torch.empty_like(self.net.stem_k), torch.empty_like(self.net.stem_b)
+      self.stem_ws_bytes = _lib.query(_lib.Q_CONV_STEM_BWD_WS, batch, st["cin"], st["f"])
+      self.stem_ws = torch.empty((self.stem_ws_bytes,), dtype=torch.uint8, device=device)
+      params += [self.net.stem_k, self.net.stem_b]
+      self._grads += [self.d_stem_k, self.d_stem_b]
+      planes += [None, None]
     for i, (w, b, dw, db) in enumerate(zip(self.net.ws, self.net.bs, self.dws, self.dbs)):
       params += [w, b]
       self._grads += [dw, db]
@@ -525,6 +583,8 @@ class CandidatePlan:
                          step_dev: torch.Tensor, sp: int, xp: Optional[torch.Tensor] = None):
     """SURVEY.md section 3.3 steps 1-13 for this candidate (frozen logits already computed)."""
     lib, net, B, C = self.lib, self.net, self.batch, self.C
+    if net.stem:
+      raise NotImplementedError("conv-stem subnetworks train on the wave schedule (IterationPlan._enqueue_waves)")
     lab = labels.data_ptr() if labels is not None else None
     labf = labels_f.data_ptr() if labels_f is not None else None
     wsp = self.workspace.data_ptr()
@@ -576,6 +636,8 @@ class CandidatePlan:
     out = {}
     for i, (w, b) in enumerate(zip(self.net.ws, self.net.bs)):
       out["w%d" % i], out["b%d" % i] = w.cpu().numpy(), b.cpu().numpy()
+    if self.net.stem:
+      out["stem_k"], out["stem_b"] = self.net.stem_k.cpu().numpy(), self.net.stem_b.cpu().numpy()
     for k, v in self.sub_opt.state().items():
       out["sub_opt_" + k] = v
     out.update(self.ehead.state_dict())
@@ -585,6 +647,9 @@ class CandidatePlan:
     for i, (w, b) in enumerate(zip(self.net.ws, self.net.bs)):
       w.copy_(torch.as_tensor(st["w%d" % i]))
       b.copy_(torch.as_tensor(st["b%d" % i]))
+    if self.net.stem:
+      self.net.stem_k.copy_(torch.as_tensor(st["stem_k"]))
+      self.net.stem_b.copy_(torch.as_tensor(st["stem_b"]))
     self.net.refresh_planes()
     self.sub_opt.load_state({k[len("sub_opt_"):]: v for k, v in st.items() if k.startswith("sub_opt_")})
     self.ehead.load_state_dict(st)
@@ -611,14 +676,25 @@ class CandidatePlan:
     db_{i-1} = colsum(dZ_{i-1})."""
     net, n = self.net, len(self.net.ws)
     i = n - 1 - k
-    xin = xp if i == 0 else net.hp[i - 1]
+    xin = (net.stem_out if net.stem else xp) if i == 0 else net.hp[i - 1]
     dzp = self.dzp_out if k == 0 else self.dzp[(i + 1) % 2]
     dxp = self.dzp[i % 2] if i > 0 else None
     ws = self.bwd_ws            # waves are serialised on the main stream
+    # below a conv stem the first dense layer also produces dX: dense fp32, masked by the sign bits of the pooled
+    # features (= ReLU and max-pool routing mask), which is what adn_conv_stem_bwd consumes
+    dx = self.dpool if (i == 0 and net.stem) else None
     return _lib.BwdOp(xin.data_ptr(), net.wps[i].data_ptr(), dzp.data_ptr(),
-                      dxp.data_ptr() if dxp is not None else None, None,
+                      dxp.data_ptr() if dxp is not None else None, dx.data_ptr() if dx is not None else None,
                       self.dbs[i - 1].data_ptr() if i > 0 else None, self.dws[i].data_ptr(), net.dims[i],
-                      net.dims[i + 1], 1 if i > 0 else 0, 0, ws.data_ptr(), self.bwd_ws_bytes)
+                      net.dims[i + 1], 1 if (i > 0 or dx is not None) else 0, 0, ws.data_ptr(), self.bwd_ws_bytes)
+
+  def enqueue_stem_bwd(self, x: torch.Tensor, sp: int):
+    """Kernel / bias gradients of the conv stem from the pooled-feature gradient the last backward wave left."""
+    st = self.net.stem
+    _lib.check(self.lib.adn_conv_stem_bwd(x.data_ptr(), self.net.stem_arg.data_ptr(), self.dpool.data_ptr(),
+                                          self.d_stem_k.data_ptr(), self.d_stem_b.data_ptr(), self.batch, st["h"], st["w"],
+                                          st["cin"], st["f"], self.stem_ws.data_ptr(), self.stem_ws_bytes, sp),
+               "adn_conv_stem_bwd")
 
   def enqueue_sub_update(self, sp: int):
     self.sub_opt.apply(self.lib, self._grads, sp)
@@ -654,6 +730,9 @@ class IterationPlan:
                                      adanet_loss_decay, trace_capacity, self.device, i,
                                      prev_mixture_weights=prev_mixture_weights, prev_bias=prev_bias)
                        for i, s in zip(idx, specs)]
+    for n in list(self.frozen) + [c.net for c in self.candidates]:
+      if n.in_dim != in_dim:
+        raise ValueError("subnetwork %s consumes %d input values per example, the plan feeds %d" % (n.name, n.in_dim, in_dim))
     # candidate ensembles: (global index, head, side-stream slot).  A `*_grow` ensemble over one local subnetwork
     # is that CandidatePlan's own head; anything else (solo, all, ...) gets a head of its own over shared nets.
     by_index = {c.index: k for k, c in enumerate(self.candidates)}
@@ -744,6 +823,9 @@ class IterationPlan:
     sp = main.cuda_stream
     self._split_x(sp)
     nets = list(self.frozen) + [c.net for c in self.candidates]
+    for n in nets:
+      if n.stem:
+        n.stem_forward(lib, self.x, sp)
     for w in range(max(len(n.ws) for n in nets)):
       ops = [n.fwd_op(w, self.xp) for n in nets if w < len(n.ws)]
       arr = (_lib.FwdOp * len(ops))(*ops)
@@ -773,6 +855,8 @@ class IterationPlan:
       if s is not main:
         s.wait_stream(main)
       with torch.cuda.stream(s):
+        if c.net.stem:
+          c.enqueue_stem_bwd(self.x, s.cuda_stream)
         c.enqueue_sub_update(s.cuda_stream)
     for s in self.streams if self.multi_stream else []:
       main.wait_stream(s)
@@ -802,7 +886,8 @@ class IterationPlan:
     _lib.check(lib.adn_counter_add(self.step_dev.data_ptr(), 1, sp), "adn_counter_add")
 
   def _split_x(self, sp: int):
-    if self.xp is not None:
+    # the minibatch's own planes feed first dense layers (and MATRIX weights of linear members); conv stems read x
+    if self.xp is not None and any(not n.stem for n in list(self.frozen) + [c.net for c in self.candidates]):
       _lib.check(self.lib.adn_planes_split(self.x.data_ptr(), self.batch, self.in_dim, self.xp.data_ptr(), sp),
                  "adn_planes_split")
 
@@ -933,8 +1018,8 @@ class EnsembleEvalPlan:
     self.ens_logits = torch.empty((batch, logits_dim), **f32)
     self.ws_bytes = _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, len(self.members))
     self.workspace = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=self.device)
-    self.x = torch.empty((batch, members[0].dims[0]), **f32)
-    self.xp = new_planes(batch, members[0].dims[0], self.device) if planes_enabled() else None
+    self.x = torch.empty((batch, members[0].in_dim), **f32)
+    self.xp = new_planes(batch, members[0].in_dim, self.device) if planes_enabled() else None
     self.labels = torch.zeros((batch,), dtype=torch.int64, device=self.device) if head == "softmax_xent" else None
     self.labels_f = torch.zeros((batch, logits_dim), **f32) if head != "softmax_xent" else None
 
@@ -949,7 +1034,7 @@ class EnsembleEvalPlan:
       else:
         self.labels_f.copy_(torch.as_tensor(y).reshape(self.batch, self.C), non_blocking=True)
     if forward_members:
-      if self.xp is not None:
+      if self.xp is not None and any(not m.stem for m in self.members):
         _lib.check(self.lib.adn_planes_split(self.x.data_ptr(), self.batch, self.x.shape[1], self.xp.data_ptr(), sp),
                    "adn_planes_split")
       for m in self.members:

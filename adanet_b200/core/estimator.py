@@ -197,7 +197,9 @@ class Estimator(object):
       ecands.append(srch.EnsembleCandidate(c.name, [builders.index(b) for b in c.subnetwork_builders],
                                            bool(prev) or not self._member_builders))
     self._pending_ecands = ecands
-    placeholders = {k: graph.placeholder(w, k) for k, w in self._feature_widths.items()}
+    # image features keep their [batch, H, W, C] shape for the builder; everything else is [batch, width]
+    placeholders = {k: graph.placeholder(self._feature_shapes[k] if len(self._feature_shapes.get(k, ())) == 3 else w, k)
+                    for k, w in self._feature_widths.items()}
     labels_ph = graph.placeholder(1, "labels")
     specs, subs = [], []
     for b in builders:
@@ -207,7 +209,39 @@ class Estimator(object):
       specs.append(spec)
       subs.append(sub)
     self._pending = (builders, subs)
+    self._apply_legacy_mixture_weights_train_op(builders, subs, labels_ph)
     return specs
+
+  def _apply_legacy_mixture_weights_train_op(self, builders, subs, labels_ph):
+    """adanet/core/ensemble_builder.py:523-537: a candidate whose first builder still defines the deprecated
+    `build_mixture_weights_train_op` trains its mixture weights with THAT op (given loss=adanet_loss, so the
+    regulariser is counted once), not with `Ensembler.build_train_op`.  The engine runs one mixture-weight
+    optimizer per iteration, so all builders of an iteration must agree."""
+    import dataclasses
+    from adanet_b200 import train
+    from adanet_b200.core import lowering
+    base = self._ensembler_plan_spec()
+    fns = [getattr(b, "build_mixture_weights_train_op", None) for b in builders]
+    if self._search is None:
+      return
+    if not any(callable(f) for f in fns) or base.kind == "mean":
+      self._search.ens = base
+      return
+    if not all(callable(f) for f in fns):
+      raise NotImplementedError("builders with and without the deprecated build_mixture_weights_train_op in one "
+                                "iteration are not implemented by the B200 engine")
+    logging.warning("The `build_mixture_weights_train_op` method is deprecated. Please use the `Ensembler#build_train_op` instead.")
+    specs = set()
+    for b, f, sub in zip(builders, fns, subs):
+      op = f(loss=self._head.create_loss(sub.logits), var_list=[], logits=sub.logits, labels=labels_ph, iteration_step=0,
+             summary=lowering._NullSummary())
+      op = op.train_op if hasattr(op, "train_op") and not isinstance(op, train.TrainOp) else op
+      if not isinstance(op, train.TrainOp):
+        raise ValueError("build_mixture_weights_train_op of %s must return optimizer.minimize(...) or tf.no_op(), got %r" % (b.name, op))
+      specs.add(None if op.kind == "no_op" else tuple(op.spec))
+    if len(specs) != 1:
+      raise NotImplementedError("builders whose build_mixture_weights_train_op differ within one iteration are not implemented")
+    self._search.ens = dataclasses.replace(base, optimizer=specs.pop(), legacy_train_op=True)
 
   def _ensure_search(self, features):
     from adanet_b200.core import search as srch
@@ -218,6 +252,7 @@ class Estimator(object):
     widths = input_utils.feature_widths(features)
     self._feature_keys = sorted(widths)
     self._feature_widths = widths
+    self._feature_shapes = input_utils.feature_shapes(features)
     self._in_dim = sum(widths.values())
     replay = self._replay_config.best_ensemble_indices if self._replay_config else None
     self._search = srch.AdaNetSearch(self._search_space, self._ensembler_plan_spec(), self._in_dim,
@@ -277,11 +312,11 @@ class Estimator(object):
     s = self._search
     members = []
     for k, m in enumerate(meta["members"]):
-      n_layers = len(m["dims"]) - 1
+      n_layers = len(m["dims"]) - 1 + (1 if m.get("image_shape") else 0)     # a conv stem's kernel / bias come first
       ws = [data["m{}_w{}".format(k, i)] for i in range(n_layers)]
       bs = [data["m{}_b{}".format(k, i)] for i in range(n_layers)]
       members.append(eng.DenseNet(m["name"], m["dims"], ws, bs, m["complexity"], s.batch, s.device, m["iteration"],
-                                  m["shared"]))
+                                  m["shared"], m.get("image_shape")))
     s.frozen = members
     s.iteration = int(meta["iteration"])
     s.architecture = [(int(t), n) for t, n in meta["architecture"]]
@@ -461,7 +496,8 @@ class Estimator(object):
         "prev_best_ema": None if s.prev_best_ema is None else float(s.prev_best_ema),
         "last_candidate_name": self._last_candidate_name,
         "members": [{"name": m.name, "iteration": int(m.iteration), "complexity": float(m.complexity),
-                     "dims": [int(d) for d in m.dims], "shared": m.shared} for m in s.frozen],
+                     "dims": [int(d) for d in m.dims], "shared": m.shared,
+                     "image_shape": list(m.image_shape) if m.stem else None} for m in s.frozen],
     }
     tmp = os.path.join(self._model_dir, "ensemble-latest.json.tmp")
     with open(tmp, "w") as f:

@@ -31,9 +31,17 @@ def batch_size_of(features) -> int:
 
 
 def feature_widths(features):
+  """Values per example of each feature ([B, d] -> d; NHWC images [B, H, W, C] -> H*W*C)."""
   if isinstance(features, dict):
-    return {k: (int(v.shape[1]) if len(v.shape) > 1 else 1) for k, v in features.items()}
-  return {"x": int(features.shape[1]) if len(features.shape) > 1 else 1}
+    return {k: (int(np.prod(v.shape[1:])) if len(v.shape) > 1 else 1) for k, v in features.items()}
+  return {"x": int(np.prod(features.shape[1:])) if len(features.shape) > 1 else 1}
+
+
+def feature_shapes(features):
+  """Per-example shape of each feature, kept for image features so builders see [batch, H, W, C] tensors."""
+  if not isinstance(features, dict):
+    features = {"x": features}
+  return {k: tuple(int(d) for d in v.shape[1:]) or (1,) for k, v in features.items()}
 
 
 def to_matrix(features, keys):

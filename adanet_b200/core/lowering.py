@@ -64,13 +64,37 @@ def _trace_dense_chain(logits: graph.Tensor) -> Tuple[List[graph.Tensor], graph.
         raise NotImplementedError("relu must directly follow a linear dense layer")
       inner.attrs["activation"] = "relu"
       t = inner
-    elif t.op in ("input_layer", "placeholder"):
+    elif t.op in ("input_layer", "placeholder", "flatten"):
       break
     else:
       raise NotImplementedError(
-          "the B200 engine runs dense subnetworks (input_layer -> [dense+relu]* -> dense); op %r is not supported" % t.op)
+          "the B200 engine runs dense subnetworks (input_layer -> [dense+relu]* -> dense), optionally behind a "
+          "conv3x3+relu -> maxpool2 -> flatten stem; op %r is not supported" % t.op)
   chain.reverse()
   return chain, t
+
+
+def _trace_conv_stem(flat: graph.Tensor):
+  """flatten <- max_pool2d(2,2) <- [relu <-] conv2d(3x3, same) <- NHWC images: the SimpleCNN stem
+  (customizing_adanet.ipynb SimpleCNNBuilder.build_subnetwork).  Returns (conv op, image placeholder)."""
+  pool = flat.inputs[0]
+  if pool.op != "max_pool2d":
+    raise NotImplementedError("flatten must follow max_pooling2d in a conv-stem subnetwork (got op %r)" % pool.op)
+  conv = pool.inputs[0]
+  if conv.op == "relu":
+    inner = conv.inputs[0]
+    if inner.op != "conv2d" or inner.attrs.get("activation") is not None:
+      raise NotImplementedError("relu must directly follow a linear conv2d layer")
+    inner.attrs["activation"] = "relu"
+    conv = inner
+  if conv.op != "conv2d":
+    raise NotImplementedError("max_pooling2d must follow conv2d (+relu) in a conv-stem subnetwork (got op %r)" % conv.op)
+  if conv.attrs.get("activation") != "relu":
+    raise NotImplementedError("the conv stem's activation must be relu")
+  images = conv.inputs[0]
+  if images.op != "placeholder" or len(images.shape) != 4:
+    raise NotImplementedError("the conv stem must read the NHWC image feature directly")
+  return conv, images
 
 
 def lower_subnetwork(builder, sub: subnetwork_lib.Subnetwork, variables: List[graph.Variable], train_op,
@@ -85,9 +109,16 @@ def lower_subnetwork(builder, sub: subnetwork_lib.Subnetwork, variables: List[gr
   for d in chain[:-1]:
     if d.attrs.get("activation") != "relu":
       raise NotImplementedError("hidden layers must use relu")
-  if inp.shape[-1] != in_dim:
+  stem, image_shape = None, None
+  if inp.op == "flatten":
+    stem, images = _trace_conv_stem(inp)
+    image_shape = tuple(int(v) for v in images.shape[1:])
+    if int(np.prod(image_shape)) != in_dim:
+      raise ValueError("subnetwork %s consumes images of shape %s, the input_fn provides %d values per example" % (
+          builder.name, image_shape, in_dim))
+  elif inp.shape[-1] != in_dim or len(inp.shape) != 2:
     raise ValueError("subnetwork %s consumes %s input features, the input_fn provides %d" % (builder.name, inp.shape[-1], in_dim))
-  dims = [in_dim] + [d.shape[-1] for d in chain]
+  dims = [int(inp.shape[-1])] + [d.shape[-1] for d in chain]
   if dims[-1] != logits_dim:
     raise ValueError("subnetwork %s produces logits of dimension %d, head expects %d" % (builder.name, dims[-1], logits_dim))
   # last_layer must be the tensor feeding the logits layer (or the logits themselves)
@@ -95,9 +126,12 @@ def lower_subnetwork(builder, sub: subnetwork_lib.Subnetwork, variables: List[gr
   if ll is not chain[-1].inputs[0] and ll is not sub.logits:
     if not (isinstance(ll, graph.Tensor) and ll.op == "relu" and ll.inputs[0] is chain[-1].inputs[0]):
       raise NotImplementedError("last_layer must be the input of the logits layer (or the logits)")
-  ws = [np.array(d.attrs["kernel"].value, dtype=np.float32) for d in chain]
+  layers = ([stem] if stem is not None else []) + chain     # a conv stem's HWIO kernel / bias lead the lists
+  ws = [np.array(d.attrs["kernel"].value, dtype=np.float32) for d in layers]
   bs = [np.array(d.attrs["bias"].value, dtype=np.float32) if d.attrs["bias"] is not None
-        else np.zeros((d.shape[-1],), dtype=np.float32) for d in chain]
+        else np.zeros((d.shape[-1],), dtype=np.float32) for d in layers]
+  if stem is not None and stem.attrs["bias"] is None:
+    raise NotImplementedError("a conv stem without bias is not implemented")
   # train op: TrainOp from optimizer.minimize, or a TrainOpSpec wrapping one
   op = train_op.train_op if isinstance(train_op, subnetwork_lib.TrainOpSpec) else train_op
   if not isinstance(op, train.TrainOp):
@@ -106,11 +140,11 @@ def lower_subnetwork(builder, sub: subnetwork_lib.Subnetwork, variables: List[gr
     opt_spec = ("sgd", 0.0)     # a frozen subnetwork (e.g. estimator_test.py _FrozenLinearBuilder)
   else:
     opt_spec = op.spec
-    chain_vars = {id(d.attrs["kernel"]) for d in chain} | {id(d.attrs["bias"]) for d in chain if d.attrs["bias"] is not None}
+    chain_vars = {id(d.attrs["kernel"]) for d in layers} | {id(d.attrs["bias"]) for d in layers if d.attrs["bias"] is not None}
     if op.var_list is not None and {id(v) for v in op.var_list} != chain_vars:
       raise NotImplementedError("training a strict subset of a subnetwork's variables is not implemented")
   complexity = float(np.asarray(sub.complexity, dtype=np.float32))
-  return eng.SubnetworkPlanSpec(builder.name, dims, complexity, opt_spec, ws, bs, shared=sub.shared)
+  return eng.SubnetworkPlanSpec(builder.name, dims, complexity, opt_spec, ws, bs, shared=sub.shared, image_shape=image_shape)
 
 
 def build_and_lower(builder, feature_placeholders: Dict[str, graph.Tensor], labels_placeholder, head,

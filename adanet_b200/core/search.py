@@ -143,7 +143,9 @@ class AdaNetSearch:
     # splitting them would need the member logits gathered every step -- so the units of placement
     # are the connected components of "shares an ensemble"; a component's cost is its training FLOPs per example
     # (sum d_i d_{i+1}).  "balanced" = longest-processing-time first, "round_robin" = the reference-like i % G.
-    costs = [sum(a * b for a, b in zip(s.dims[:-1], s.dims[1:])) for s in specs]
+    costs = [sum(a * b for a, b in zip(s.dims[:-1], s.dims[1:])) +
+             (s.image_shape[0] * s.image_shape[1] * int(np.prod(np.shape(s.ws[0])[:3])) * np.shape(s.ws[0])[3]
+              if s.image_shape is not None else 0) for s in specs]
     self._owners = ex.component_owners(costs, [c.builders for c in ecs], g, self.placement)
     mine = ex.owned_indices(len(specs), r, g, self._owners)
     self._ec_owners = [self._owners[c.builders[0]] for c in ecs]
@@ -229,7 +231,8 @@ class AdaNetSearch:
         mix_ws, bias = head.mixture_weight_tensors(), head.bias
       else:
         new_members = [eng.DenseNet(specs[b].name, specs[b].dims, specs[b].ws, specs[b].bs, specs[b].complexity,
-                                    self.batch, self.device, t, specs[b].shared) for b in ec.builders]
+                                    self.batch, self.device, t, specs[b].shared, specs[b].image_shape)
+                       for b in ec.builders]
         n_members = len(kept) + len(new_members)
         if matrix:
           mix_ws = [torch.empty((m.last_layer_dim, self.C), dtype=torch.float32, device=self.device)
@@ -238,7 +241,7 @@ class AdaNetSearch:
           wshape = (n_members,) if self.ens.mixture_weight_type == "scalar" else (n_members, self.C)
           mix_ws = [torch.empty(wshape, dtype=torch.float32, device=self.device)]
         bias = torch.empty((self.C,), dtype=torch.float32, device=self.device)
-      ex.broadcast_tensors([t_ for m in new_members for t_ in (m.ws + m.bs)] + mix_ws + [bias], src=owner)
+      ex.broadcast_tensors([t_ for m in new_members for t_ in m.all_params()] + mix_ws + [bias], src=owner)
       if ex.rank() != owner:
         for m in new_members:
           m.refresh_planes()   # their planes were split from the (pre-broadcast) initial weights

@@ -9,6 +9,7 @@
 #include "planes.cuh"
 
 namespace adn {
+namespace conv { int64_t bwd_workspace_bytes(int64_t batch, int cin, int f); }
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
@@ -110,6 +111,7 @@ extern "C" int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_
     case ADN_Q_PLANES_BYTES: *out_host = pl::planes_bytes(a, b); return ADN_OK;
     case ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES: *out_host = pl::dense_bwd_workspace_bytes(a, b, c); return ADN_OK;
     case ADN_Q_COLSUM_WORKSPACE_BYTES: *out_host = 64 * b * (int64_t)sizeof(float) + 256; return ADN_OK;
+    case ADN_Q_CONV_STEM_BWD_WORKSPACE_BYTES: *out_host = conv::bwd_workspace_bytes(a, (int)b, (int)c); return ADN_OK;
     case ADN_Q_LAUNCH_COUNT: *out_host = g_launches.load(); return ADN_OK;
     default: return fail(ADN_ERR_INVALID, "adn_query: unknown key %d", key);
   }

@@ -1,0 +1,331 @@
+// K6: the SimpleCNN stem -- Conv2D(F, 3x3, "same") + bias + ReLU -> MaxPool2D(2, 2) -> Flatten -- fused into one
+// forward kernel that writes the pooled features straight into the split-plane format the tcgen05 dense
+// pipeline consumes (planes.cu), and one backward kernel for the kernel / bias gradients.
+//
+// Replaces the Keras layers of SimpleCNNBuilder.build_subnetwork in
+//   adanet/examples/tutorials/customizing_adanet.ipynb (the `simple_cnn` subnetwork of BASELINE config 4):
+//   x = Conv2D(filters=16, kernel_size=3, padding="same", activation="relu")(images)
+//   x = MaxPool2D(pool_size=2, strides=2)(x);  x = Flatten()(x)            [TF/Keras, NHWC, HWIO kernel]
+//
+// Why SIMT fp32 and not tcgen05: the contraction is K = 9*Cin = 27 by N = F = 16 -- per example 0.44 MFMA against
+// 12 KB of image read and ~37 KB of planes written, i.e. the kernel sits between the FP32-FMA rate and HBM, and
+// an implicit-GEMM tile (K padded to 32, N=16) would leave the tensor pipe >90 % idle while adding an im2col
+// stage.  Exact fp32 FMAs also keep the conv bit-comparable with the fp32 cross-check.
+//
+// Forward: one CTA per image (grid-stride), 256 threads, image staged zero-padded in shared memory with cp.async
+// (double buffered: the next image lands while this one is computed); a thread owns one pooled pixel and 16
+// filters at a time: 4 conv positions x 16 filters = 64 accumulators fed from a 4x4xCin register patch and
+// float4 broadcast reads of the kernel.  Epilogue: bias, ReLU, 2x2 max, hi/lo TF32 split, sign bits, and a
+// 2-bit argmax per element for the backward.
+// Backward: dK[ky,kx,c,f] = sum_{b,p} patch(b, argmax(b,p,f))[ky,kx,c] * g[b,p,f], db[f] = sum g, where g is the
+// gradient w.r.t. the pooled features already masked by (pooled > 0) (the dX epilogue of the first dense layer
+// applies the sign bits written here).  One thread per (channel, filter) pair holding the nine taps, images looped
+// per CTA, per-CTA partials reduced in fixed order by a second kernel (deterministic).
+#include "common.cuh"
+
+namespace adn {
+namespace pl {
+int64_t plane_floats(int64_t rows, int64_t cols);
+}
+
+namespace conv {
+
+static constexpr int FWD_THREADS = 256;
+static constexpr int FC = 16;   // filters per accumulator chunk
+
+__device__ __forceinline__ float rna_tf32(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// image [H][W][CIN] (global) -> zero-padded [(H+2)][(W+2)][CIN] (shared); borders are zeroed once by the caller
+template <int CIN>
+__device__ __forceinline__ void stage_image(float* s_img, const float* img, int H, int W, int tid, int nthreads) {
+  const int row = W * CIN;
+  const int prow = (W + 2) * CIN;
+  for (int i = tid; i < H * row; i += nthreads) {
+    const int y = i / row;
+    const int r = i - y * row;
+    cp_async4(s_img + (y + 1) * prow + CIN + r, img + i);
+  }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(FWD_THREADS)
+conv_stem_fwd_kernel(const float* __restrict__ images, const float* __restrict__ kernel, const float* __restrict__ bias,
+                     float* __restrict__ hi, float* __restrict__ lo, uint16_t* __restrict__ bits16,
+                     uint32_t* __restrict__ argmax, int64_t B, int H, int W, int F) {
+  extern __shared__ __align__(16) float smem[];
+  const int K = 9 * CIN;
+  const int pimg = (H + 2) * (W + 2) * CIN;
+  float* s_w = smem;                       // [K][F]
+  float* s_b = s_w + K * F;                // [F]
+  float* s_img0 = s_b + F;                 // two padded images
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * F; i += FWD_THREADS) s_w[i] = kernel[i];
+  for (int i = tid; i < F; i += FWD_THREADS) s_b[i] = bias[i];
+  for (int i = tid; i < 2 * pimg; i += FWD_THREADS) s_img0[i] = 0.f;
+  __syncthreads();
+  const int PH = H / 2, PW = W / 2, P = PH * PW;
+  const int64_t img_elems = (int64_t)H * W * CIN;
+  const int64_t words_per_row = (int64_t)P * F / 16;
+  const int prow = (W + 2) * CIN;
+  int64_t b = blockIdx.x;
+  int buf = 0;
+  if (b < B) stage_image<CIN>(s_img0, images + b * img_elems, H, W, tid, FWD_THREADS);
+  cp_async_commit();
+  for (; b < B; b += gridDim.x, buf ^= 1) {
+    const int64_t nb = b + gridDim.x;
+    if (nb < B) stage_image<CIN>(s_img0 + (buf ^ 1) * pimg, images + nb * img_elems, H, W, tid, FWD_THREADS);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* s_img = s_img0 + buf * pimg;
+    for (int p = tid; p < P; p += FWD_THREADS) {
+      const int py = p / PW, px = p - py * PW;
+      // 4x4xCIN input patch around the 2x2 conv positions (padded coordinates start at (2py, 2px))
+      float patch[4][4][CIN];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) patch[i][j][c] = s_img[(2 * py + i) * prow + (2 * px + j) * CIN + c];
+      for (int f0 = 0; f0 < F; f0 += FC) {
+        float acc[4][FC];
+#pragma unroll
+        for (int j = 0; j < FC; ++j) {
+          const float bv = s_b[f0 + j];
+          acc[0][j] = bv; acc[1][j] = bv; acc[2][j] = bv; acc[3][j] = bv;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+              float w[FC];
+              const float4* wp = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CIN + c) * F + f0);
+#pragma unroll
+              for (int q = 0; q < FC / 4; ++q) {
+                const float4 t = wp[q];
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+              }
+#pragma unroll
+              for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                  const float v = patch[dy + ky][dx + kx][c];
+#pragma unroll
+                  for (int j = 0; j < FC; ++j) acc[dy * 2 + dx][j] = fmaf(v, w[j], acc[dy * 2 + dx][j]);
+                }
+            }
+        // bias is in; ReLU + 2x2 max (first maximum in scan order wins, as TF's MaxPoolGrad routes it)
+        float out_hi[FC], out_lo[FC];
+        uint32_t sign = 0u, arg = 0u;
+#pragma unroll
+        for (int j = 0; j < FC; ++j) {
+          float m = acc[0][j];
+          uint32_t a = 0u;
+          if (acc[1][j] > m) { m = acc[1][j]; a = 1u; }
+          if (acc[2][j] > m) { m = acc[2][j]; a = 2u; }
+          if (acc[3][j] > m) { m = acc[3][j]; a = 3u; }
+          m = fmaxf(m, 0.f);
+          sign |= (m > 0.f) ? (1u << j) : 0u;
+          arg |= a << (2 * j);
+          const float h = rna_tf32(m);
+          out_hi[j] = h;
+          out_lo[j] = rna_tf32(m - h);
+        }
+        const int64_t col0 = (int64_t)p * F + f0;       // multiple of 16
+        const int64_t kb = col0 >> 5;
+        const int off = (int)(col0 & 31);
+        const int64_t dst = (kb * B + b) * 32 + off;
+#pragma unroll
+        for (int q = 0; q < FC / 4; ++q) {
+          *reinterpret_cast<float4*>(hi + dst + 4 * q) =
+              make_float4(out_hi[4 * q], out_hi[4 * q + 1], out_hi[4 * q + 2], out_hi[4 * q + 3]);
+          *reinterpret_cast<float4*>(lo + dst + 4 * q) =
+              make_float4(out_lo[4 * q], out_lo[4 * q + 1], out_lo[4 * q + 2], out_lo[4 * q + 3]);
+        }
+        bits16[(kb * B + b) * 2 + (off >> 4)] = (uint16_t)sign;   // low half = columns 0..15 of the k-block
+        argmax[b * words_per_row + (col0 >> 4)] = arg;
+      }
+    }
+    __syncthreads();   // everyone is done with s_img[buf] before the next iteration's prefetch overwrites it
+  }
+}
+
+// A thread owns one (channel c, filter f) pair and all nine taps: the gradient value and the arg-max word are read
+// once per nine FMAs (the gather address depends on f through the arg-max, so taps are the only reuse there is).
+// G groups of CIN*F threads split the pooled pixels of an image; their accumulators are summed in fixed order
+// through shared memory once per CTA.
+template <int CIN>
+__global__ void __launch_bounds__(1024)
+conv_stem_bwd_kernel(const float* __restrict__ images, const uint32_t* __restrict__ argmax,
+                     const float* __restrict__ dpooled, float* __restrict__ partials, int64_t B, int H, int W, int F,
+                     int G) {
+  extern __shared__ __align__(16) float smem[];
+  const int K = 9 * CIN;
+  const int PH = H / 2, PW = W / 2, P = PH * PW;
+  const int pimg = (H + 2) * (W + 2) * CIN;
+  const int prow = (W + 2) * CIN;
+  float* s_img = smem;                                            // padded image
+  float* s_g = s_img + ((pimg + 3) & ~3);                         // [P*F]
+  uint32_t* s_arg = reinterpret_cast<uint32_t*>(s_g + P * F);     // [P*F/16]
+  float* s_red = reinterpret_cast<float*>(s_arg + P * F / 16);    // [G][K*F + F]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < pimg; i += nt) s_img[i] = 0.f;
+  const int f = tid % F;
+  const int c = (tid / F) % CIN;
+  const int grp = tid / (F * CIN);
+  const int wsel = f >> 4, sh = 2 * (f & 15);
+  const int fw = F / 16;
+  float acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = 0.f;
+  float accb = 0.f;
+  const int64_t img_elems = (int64_t)H * W * CIN;
+  const int64_t cols = (int64_t)P * F;
+  __syncthreads();
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    stage_image<CIN>(s_img, images + b * img_elems, H, W, tid, nt);
+    for (int i = tid; i < (int)(cols / 4); i += nt) cp_async16(s_g + 4 * i, dpooled + b * cols + 4 * i);
+    for (int i = tid; i < (int)(cols / 16); i += nt) cp_async4(s_arg + i, argmax + b * (cols / 16) + i);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    int py = grp / PW, px = grp - py * PW;
+    for (int p = grp; p < P; p += G) {
+      const float g = s_g[p * F + f];
+      const uint32_t pos = (s_arg[p * fw + wsel] >> sh) & 3u;
+      // padded coordinates of tap (0, 0) at the arg-max conv position (2py + dy, 2px + dx)
+      const float* src = s_img + (2 * py + (int)(pos >> 1)) * prow + (2 * px + (int)(pos & 1u)) * CIN + c;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(src[ky * prow + kx * CIN], g, acc[ky * 3 + kx]);
+      accb += g;
+      px += G;
+      while (px >= PW) { px -= PW; ++py; }
+    }
+    __syncthreads();
+  }
+  // group-major partial sums -> fixed-order sum over groups -> this CTA's partial
+  const int n_out = K * F + F;
+  float* red = s_red + grp * n_out;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) red[(q * CIN + c) * F + f] = acc[q];     // k = (ky*3+kx)*CIN + c
+  if (c == 0) red[K * F + f] = accb;
+  __syncthreads();
+  float* mine = partials + (size_t)blockIdx.x * n_out;
+  for (int i = tid; i < n_out; i += nt) {
+    float s = 0.f;
+    for (int q = 0; q < G; ++q) s += s_red[q * n_out + i];
+    mine[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+conv_stem_reduce_kernel(const float* __restrict__ partials, int n_part, int n_out, int kf, float* __restrict__ dkernel,
+                        float* __restrict__ dbias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  float s = 0.f;
+  for (int q = 0; q < n_part; ++q) s += partials[(size_t)q * n_out + i];   // fixed order
+  if (i < kf) dkernel[i] = s;
+  else dbias[i - kf] = s;
+}
+
+static int bwd_ctas(int64_t batch) {
+  const int64_t cap = (int64_t)sm_count() * 4;
+  return (int)(batch < cap ? batch : cap);
+}
+
+static int check_shape(const char* who, int64_t batch, int h, int w, int cin, int f) {
+  if (batch < 1 || h < 2 || w < 2 || (h & 1) || (w & 1))
+    return fail(ADN_ERR_INVALID, "%s: batch %lld, image %dx%d (height and width must be even and >= 2)", who,
+                (long long)batch, h, w);
+  if (cin != 1 && cin != 3) return fail(ADN_ERR_UNSUPPORTED, "%s: channels %d not in {1, 3}", who, cin);
+  if (f < 16 || f > 64 || f % 16) return fail(ADN_ERR_UNSUPPORTED, "%s: filters %d not in {16, 32, 48, 64}", who, f);
+  if ((int64_t)(h + 2) * (w + 2) * cin > 24 * 1024)
+    return fail(ADN_ERR_UNSUPPORTED, "%s: image %dx%dx%d does not fit the shared-memory staging", who, h, w, cin);
+  return ADN_OK;
+}
+
+int64_t bwd_workspace_bytes(int64_t batch, int cin, int f) {
+  return (int64_t)bwd_ctas(batch) * (9 * cin * f + f) * (int64_t)sizeof(float);
+}
+
+}  // namespace conv
+}  // namespace adn
+
+using namespace adn;
+
+extern "C" int adn_conv_stem_fwd(const float* images, const float* kernel, const float* bias, float* out_planes,
+                                 uint32_t* argmax, int64_t batch, int height, int width, int channels, int filters,
+                                 void* stream) {
+  if (!images || !kernel || !bias || !out_planes || !argmax) return fail(ADN_ERR_INVALID, "adn_conv_stem_fwd: null pointer");
+  if (int rc = conv::check_shape("adn_conv_stem_fwd", batch, height, width, channels, filters)) return rc;
+  const int64_t cols = (int64_t)(height / 2) * (width / 2) * filters;
+  const int64_t pf = pl::plane_floats(batch, cols);
+  float* hi = out_planes;
+  float* lo = out_planes + pf;
+  uint16_t* bits16 = reinterpret_cast<uint16_t*>(out_planes + 2 * pf);
+  const int pimg = (height + 2) * (width + 2) * channels;
+  const size_t smem = (size_t)(9 * channels * filters + filters + 2 * pimg) * sizeof(float);
+  const int64_t cap = (int64_t)sm_count() * 2;
+  const int grid = (int)(batch < cap ? batch : cap);
+  auto launch = [&](auto kern) -> int {
+    ADN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, conv::FWD_THREADS, smem, as_stream(stream)>>>(images, kernel, bias, hi, lo, bits16, argmax, batch, height,
+                                                             width, filters);
+    ADN_CHECK_LAUNCH("conv_stem_fwd");
+    return ADN_OK;
+  };
+  return channels == 3 ? launch(conv::conv_stem_fwd_kernel<3>) : launch(conv::conv_stem_fwd_kernel<1>);
+}
+
+extern "C" int adn_conv_stem_bwd(const float* images, const uint32_t* argmax, const float* dpooled, float* dkernel,
+                                 float* dbias, int64_t batch, int height, int width, int channels, int filters,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!images || !argmax || !dpooled || !dkernel || !dbias) return fail(ADN_ERR_INVALID, "adn_conv_stem_bwd: null pointer");
+  if (int rc = conv::check_shape("adn_conv_stem_bwd", batch, height, width, channels, filters)) return rc;
+  const int64_t need = conv::bwd_workspace_bytes(batch, channels, filters);
+  if (!workspace || workspace_bytes < need)
+    return fail(ADN_ERR_WORKSPACE, "adn_conv_stem_bwd: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+  const int kf = 9 * channels * filters;
+  // G thread groups of channels*filters threads share the pooled pixels of an image (even, so threads % 32 == 0)
+  int groups = (384 / (channels * filters)) & ~1;
+  groups = groups < 2 ? 2 : (groups > 16 ? 16 : groups);
+  const int threads = groups * channels * filters;
+  const int grid = conv::bwd_ctas(batch);
+  const int pimg = (height + 2) * (width + 2) * channels;
+  const int64_t cols = (int64_t)(height / 2) * (width / 2) * filters;
+  const size_t smem = ((size_t)((pimg + 3) & ~3) + cols + cols / 16 + (size_t)groups * (kf + filters)) * sizeof(float);
+  if (smem > 200 * 1024) return fail(ADN_ERR_UNSUPPORTED, "adn_conv_stem_bwd: %zu bytes of staging do not fit", smem);
+  float* partials = static_cast<float*>(workspace);
+  auto launch = [&](auto kern) -> int {
+    ADN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, as_stream(stream)>>>(images, argmax, dpooled, partials, batch, height, width, filters,
+                                                     groups);
+    ADN_CHECK_LAUNCH("conv_stem_bwd");
+    return ADN_OK;
+  };
+  if (int rc = channels == 3 ? launch(conv::conv_stem_bwd_kernel<3>) : launch(conv::conv_stem_bwd_kernel<1>)) return rc;
+  const int n_out = kf + filters;
+  conv::conv_stem_reduce_kernel<<<(n_out + 255) / 256, 256, 0, as_stream(stream)>>>(partials, grid, n_out, kf, dkernel,
+                                                                                   dbias);
+  ADN_CHECK_LAUNCH("conv_stem_reduce");
+  return ADN_OK;
+}

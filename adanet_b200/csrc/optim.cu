@@ -10,6 +10,8 @@
 //   RMSProp          ms = rho*ms + (1-rho) g^2 ; mom = mu*mom + lr*g/sqrt(ms+eps) ; v -= mom   (ms init 1)
 //   Adam             lr_t = lr*sqrt(1-b2^t)/(1-b1^t) ; m += (1-b1)(g-m) ; v += (1-b2)(g^2-v) ;
 //                    var -= lr_t*m/(sqrt(v)+eps)
+//   Momentum+cosine  Momentum with lr_t = tf.train.cosine_decay(lr, step, decay_steps, alpha) read from the
+//                    device step counter (customizing_adanet.ipynb SimpleCNNBuilder.build_subnetwork_train_op)
 #include "common.cuh"
 
 namespace adn {
@@ -60,6 +62,10 @@ __device__ __forceinline__ void apply_one(int kind, float& p, float g, float& s0
       s0 = h1 * s0 + g;
       p -= h0 * s0;
       break;
+    case ADN_OPT_MOMENTUM_COSINE:
+      s0 = h1 * s0 + g;
+      p -= lr_t * s0;
+      break;
     case ADN_OPT_RMSPROP:
       s0 = h1 * s0 + (1.f - h1) * g * g;
       s1 = h2 * s1 + h0 * g / sqrtf(s0 + h3);
@@ -87,6 +93,11 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
   if (o.kind == ADN_OPT_ADAM) {
     const float tt = (float)(*o.step_dev + 1);
     lr_t = o.h0 * sqrtf(1.f - powf(o.h2, tt)) / (1.f - powf(o.h1, tt));
+  } else if (o.kind == ADN_OPT_MOMENTUM_COSINE) {
+    // tf.train.cosine_decay [TF]: step clipped to decay_steps, fp32 arithmetic
+    const float st = fminf((float)(*o.step_dev), o.h2);
+    const float cosine = 0.5f * (1.f + cosf(3.14159265358979323846f * (st / o.h2)));
+    lr_t = o.h0 * ((1.f - o.h3) * cosine + o.h3);
   }
   const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)s0 | (uintptr_t)s1) & 15) == 0;
   if (vec) {
@@ -147,15 +158,18 @@ extern "C" int adn_opt_step_p(int kind, float* const* params_host, const float* 
                               float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
                               int n_tensors, const float* hyper_host, int64_t* step_dev,
                               float* const* planes_host, const int64_t* cols_host, void* stream) {
-  if (kind < ADN_OPT_SGD || kind > ADN_OPT_ADAM) return fail(ADN_ERR_INVALID, "adn_opt_step: bad kind %d", kind);
+  if (kind < ADN_OPT_SGD || kind > ADN_OPT_MOMENTUM_COSINE) return fail(ADN_ERR_INVALID, "adn_opt_step: bad kind %d", kind);
   if (n_tensors < 1 || n_tensors > kMaxTensors)
     return fail(ADN_ERR_UNSUPPORTED, "adn_opt_step: n_tensors %d not in [1,%d]", n_tensors, kMaxTensors);
   if (!params_host || !grads_host || !sizes_host || !hyper_host)
     return fail(ADN_ERR_INVALID, "adn_opt_step: null pointer");
-  const int need_slots = kind == ADN_OPT_SGD ? 0 : (kind == ADN_OPT_MOMENTUM ? 1 : 2);
+  const int need_slots = kind == ADN_OPT_SGD ? 0 : ((kind == ADN_OPT_MOMENTUM || kind == ADN_OPT_MOMENTUM_COSINE) ? 1 : 2);
   if (need_slots >= 1 && !slot0_host) return fail(ADN_ERR_INVALID, "adn_opt_step: slot0 required");
   if (need_slots >= 2 && !slot1_host) return fail(ADN_ERR_INVALID, "adn_opt_step: slot1 required");
-  if (kind == ADN_OPT_ADAM && !step_dev) return fail(ADN_ERR_INVALID, "adn_opt_step: Adam needs step_dev");
+  if ((kind == ADN_OPT_ADAM || kind == ADN_OPT_MOMENTUM_COSINE) && !step_dev)
+    return fail(ADN_ERR_INVALID, "adn_opt_step: Adam / cosine-decay Momentum need step_dev");
+  if (kind == ADN_OPT_MOMENTUM_COSINE && !(hyper_host[2] > 0.f))
+    return fail(ADN_ERR_INVALID, "adn_opt_step: cosine decay needs decay_steps > 0");
   OptParams o{};
   int chunks = 0;
   for (int t = 0; t < n_tensors; ++t) {
@@ -185,7 +199,7 @@ extern "C" int adn_opt_step_p(int kind, float* const* params_host, const float* 
   o.h0 = hyper_host[0];
   o.h1 = kind >= ADN_OPT_MOMENTUM ? hyper_host[1] : 0.f;
   o.h2 = kind >= ADN_OPT_RMSPROP ? hyper_host[2] : 0.f;
-  o.h3 = kind >= ADN_OPT_RMSPROP ? hyper_host[3] : 0.f;
+  o.h3 = kind >= ADN_OPT_RMSPROP ? hyper_host[3] : 0.f;   // MOMENTUM_COSINE (4): {lr, momentum, decay_steps, alpha}
   o.step_dev = step_dev;
   opt_step_kernel<<<chunks, 256, 0, as_stream(stream)>>>(o);
   ADN_CHECK_LAUNCH("opt_step");

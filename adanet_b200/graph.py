@@ -99,6 +99,26 @@ def glorot_uniform_initializer(seed: Optional[int] = None):
   return init
 
 
+def he_normal_initializer(seed: Optional[int] = None):
+  """tf.keras.initializers.he_normal [TF]: VarianceScaling(scale=2, mode="fan_in", truncated normal), i.e.
+  N(0, sqrt(2/fan_in)/0.8796...) truncated at two standard deviations; fan_in = prod(shape[:-1])
+  (9*Cin for a 3x3 conv kernel, `in` for a dense kernel).  NumPy's generator, not TF's stream."""
+  state = {"rng": np.random.default_rng(seed)}
+
+  def init(shape):
+    fan_in = int(np.prod(shape[:-1]))
+    std = math.sqrt(2.0 / max(1, fan_in)) / 0.87962566103423978
+    rng = state["rng"]
+    out = rng.standard_normal(shape)
+    bad = np.abs(out) > 2.0
+    while bad.any():                       # resample the tails (truncated normal)
+      out[bad] = rng.standard_normal(int(bad.sum()))
+      bad = np.abs(out) > 2.0
+    return (out * std).astype(np.float32)
+
+  return init
+
+
 def zeros_initializer():
   return lambda shape: np.zeros(shape, dtype=np.float32)
 
@@ -137,8 +157,10 @@ def numeric_column(key: str, shape=(1,)) -> NumericColumn:
   return NumericColumn(key, shape)
 
 
-def placeholder(width: int, name: str) -> Tensor:
-  return Tensor((None, width), "placeholder", (), {"key": name}, name)
+def placeholder(width, name: str) -> Tensor:
+  """A fed tensor [batch, width], or [batch, *shape] when `width` is a shape tuple (NHWC images)."""
+  shape = (None, int(width)) if np.ndim(width) == 0 else (None,) + tuple(int(v) for v in width)
+  return Tensor(shape, "placeholder", (), {"key": name}, name)
 
 
 def input_layer(features, feature_columns: Iterable[NumericColumn]) -> Tensor:
@@ -184,6 +206,84 @@ def dense(inputs: Tensor, units: int, activation=None, use_bias: bool = True, ke
     g.add(bias)
   return Tensor((None, units), "dense", (inputs,),
                 {"kernel": kernel, "bias": bias, "activation": "relu" if activation is not None else None}, base)
+
+
+def conv2d(inputs: Tensor, filters: int, kernel_size=3, strides=1, padding: str = "valid", activation=None,
+           use_bias: bool = True, kernel_initializer=None, bias_initializer=None, name: Optional[str] = None) -> Tensor:
+  """tf.keras.layers.Conv2D / tf.layers.conv2d [TF] on NHWC images: kernel [kh, kw, Cin, filters] (HWIO).
+  The engine runs the SimpleCNN stem -- 3x3, stride 1, padding "same", ReLU -- and nothing else (csrc/conv_stem.cu)."""
+  ks = (kernel_size, kernel_size) if np.ndim(kernel_size) == 0 else tuple(kernel_size)
+  st = (strides, strides) if np.ndim(strides) == 0 else tuple(strides)
+  if len(inputs.shape) != 4:
+    raise ValueError("conv2d expects NHWC images [batch, H, W, C], got shape %s" % (inputs.shape,))
+  if ks != (3, 3) or st != (1, 1) or str(padding).lower() != "same":
+    raise NotImplementedError("the B200 engine implements conv2d with kernel_size=3, strides=1, padding='same' "
+                              "(got kernel_size=%s strides=%s padding=%r)" % (ks, st, padding))
+  if activation not in (None, relu, "relu"):
+    raise NotImplementedError("conv2d supports activation None or relu (got %r)" % (activation,))
+  g = get_default_graph()
+  _, h, w, cin = inputs.shape
+  base = g.unique_name(name or "conv2d")
+  kernel = Variable(base + "/kernel", (kernel_initializer or glorot_uniform_initializer())((3, 3, cin, filters)))
+  g.add(kernel)
+  bias = None
+  if use_bias:
+    bias = Variable(base + "/bias", (bias_initializer or zeros_initializer())((filters,)))
+    g.add(bias)
+  return Tensor((None, h, w, filters), "conv2d", (inputs,),
+                {"kernel": kernel, "bias": bias, "activation": "relu" if activation is not None else None}, base)
+
+
+def max_pooling2d(inputs: Tensor, pool_size=2, strides=2, padding: str = "valid") -> Tensor:
+  """tf.keras.layers.MaxPool2D [TF]; the engine fuses the 2x2 / stride 2 pool into the conv stem."""
+  ps = (pool_size, pool_size) if np.ndim(pool_size) == 0 else tuple(pool_size)
+  st = (strides, strides) if np.ndim(strides) == 0 else tuple(strides)
+  if len(inputs.shape) != 4:
+    raise ValueError("max_pooling2d expects [batch, H, W, C], got shape %s" % (inputs.shape,))
+  if ps != (2, 2) or st != (2, 2):
+    raise NotImplementedError("the B200 engine implements max pooling with pool_size=2, strides=2")
+  _, h, w, c = inputs.shape
+  if h % 2 or w % 2:
+    raise NotImplementedError("max_pooling2d needs even height and width (got %dx%d)" % (h, w))
+  return Tensor((None, h // 2, w // 2, c), "max_pool2d", (inputs,))
+
+
+def flatten(inputs: Tensor) -> Tensor:
+  """tf.keras.layers.Flatten [TF]: [batch, ...] -> [batch, prod(...)] in row-major (h, w, c) order."""
+  return Tensor((None, int(np.prod(inputs.shape[1:]))), "flatten", (inputs,))
+
+
+class layers:
+  """Keras-style spellings of the ops above, so a builder written against `tf.keras.layers`
+  (customizing_adanet.ipynb SimpleCNNBuilder) keeps its shape: `layers.Conv2D(...)(images)`."""
+
+  class Conv2D:
+    def __init__(self, filters, kernel_size, strides=1, padding="valid", activation=None, use_bias=True,
+                 kernel_initializer=None, bias_initializer=None, name=None):
+      self._kw = dict(filters=filters, kernel_size=kernel_size, strides=strides, padding=padding, activation=activation,
+                      use_bias=use_bias, kernel_initializer=kernel_initializer, bias_initializer=bias_initializer, name=name)
+
+    def __call__(self, inputs):
+      return conv2d(inputs, **self._kw)
+
+  class MaxPool2D:
+    def __init__(self, pool_size=2, strides=None, padding="valid"):
+      self._kw = dict(pool_size=pool_size, strides=pool_size if strides is None else strides, padding=padding)
+
+    def __call__(self, inputs):
+      return max_pooling2d(inputs, **self._kw)
+
+  class Flatten:
+    def __call__(self, inputs):
+      return flatten(inputs)
+
+  class Dense:
+    def __init__(self, units, activation=None, use_bias=True, kernel_initializer=None, bias_initializer=None, name=None):
+      self._kw = dict(units=units, activation=activation, use_bias=use_bias, kernel_initializer=kernel_initializer,
+                      bias_initializer=bias_initializer, name=name)
+
+    def __call__(self, inputs):
+      return dense(inputs, **self._kw)
 
 
 def dropout(inputs: Tensor, rate: float = 0.0, seed=None, training: bool = False) -> Tensor:

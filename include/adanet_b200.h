@@ -55,6 +55,10 @@ extern "C" {
 #define ADN_OPT_MOMENTUM 1
 #define ADN_OPT_RMSPROP 2
 #define ADN_OPT_ADAM 3
+/* Momentum whose learning rate follows tf.train.cosine_decay(lr, step, decay_steps, alpha) of the per-optimizer
+ * step counter (SimpleCNNBuilder.build_subnetwork_train_op, customizing_adanet.ipynb): hyper = {lr, momentum,
+ * decay_steps, alpha}; lr_t = lr * ((1-alpha) * 0.5 * (1 + cos(pi * min(step, decay_steps) / decay_steps)) + alpha) */
+#define ADN_OPT_MOMENTUM_COSINE 4
 
 /* compute paths for the dense kernels (adn_set_dense_path / adn_query) */
 #define ADN_PATH_AUTO 0    /* tcgen05 3xTF32 where shapes allow, SIMT fp32 otherwise */
@@ -73,6 +77,7 @@ extern "C" {
 #define ADN_Q_PLANES_BYTES 8              /* a=rows b=cols -> bytes of a split-plane tensor */
 #define ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES 9 /* a=batch b=in c=out */
 #define ADN_Q_COLSUM_WORKSPACE_BYTES 10   /* a=rows b=cols */
+#define ADN_Q_CONV_STEM_BWD_WORKSPACE_BYTES 11 /* a=batch b=channels c=filters */
 
 const char* adn_last_error(void);
 /* One-time, idempotent host-side initialisation (kernel attributes, driver entry
@@ -246,6 +251,28 @@ int adn_l1_norm(const float* x, int64_t n, float* out, void* stream);
  * coef = reg_multiplier * gamma_k (adanet/ensemble/weighted.py:563-617; SCALAR / VECTOR weights get it
  * inside adn_ensemble_head). */
 int adn_l1_grad_add(float* dw, const float* w, int64_t n, float coef, void* stream);
+
+/*
+ * SimpleCNN stem (adanet/examples/tutorials/customizing_adanet.ipynb, SimpleCNNBuilder.build_subnetwork):
+ *   Conv2D(filters, kernel_size=3, padding="same", activation="relu") -> MaxPool2D(2, 2) -> Flatten   [Keras, NHWC]
+ * images [batch, height, width, channels] fp32, kernel [3, 3, channels, filters] (HWIO), bias [filters].
+ * Forward writes the flattened pooled features [batch, (height/2)*(width/2)*filters] (h, w, c order) as a
+ * split-plane tensor (adn_query(ADN_Q_PLANES_BYTES, batch, cols), zero-initialised) -- the input format of
+ * adn_dense_fwd_p, sign bits = ReLU/pool mask -- plus a 2-bit argmax per element (16 per word,
+ * [batch, cols/16] uint32) that routes the gradient like TF's MaxPoolGrad (first maximum in scan order).
+ * Backward takes the gradient w.r.t. the pooled features as dense fp32 [batch, cols] already multiplied by
+ * (pooled > 0) -- adn_dense_bwd_p(..., dx=dense, x_relu_mask=1) of the first dense layer produces exactly
+ * that -- and returns dkernel [3,3,channels,filters] and dbias [filters] (fixed-order reduction).  No gradient
+ * w.r.t. the images is formed (the stem is the first layer).
+ * height, width even; channels in {1, 3}; filters in {16, 32, 48, 64}.
+ * workspace: adn_query(ADN_Q_CONV_STEM_BWD_WORKSPACE_BYTES, batch, channels, filters).
+ */
+int adn_conv_stem_fwd(const float* images, const float* kernel, const float* bias, float* out_planes,
+                      uint32_t* argmax, int64_t batch, int height, int width, int channels, int filters,
+                      void* stream);
+int adn_conv_stem_bwd(const float* images, const uint32_t* argmax, const float* dpooled, float* dkernel,
+                      float* dbias, int64_t batch, int height, int width, int channels, int filters,
+                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Zero-debiased EMA of the AdaNet loss (adanet/core/candidate.py:117-129 ->

@@ -42,6 +42,27 @@ def make_specs(cfgs: Sequence[tuple], in_dim: int, classes: int, iteration: int,
   return o_specs, e_specs
 
 
+def make_cnn_specs(seeds: Sequence[int], image_shape, filters: int, hidden: int, classes: int, iteration: int,
+                   optimizer: tuple):
+  """SimpleCNN subnetworks (customizing_adanet.ipynb SimpleCNNBuilder: conv3x3(F)+ReLU -> maxpool2 -> flatten ->
+  dense(hidden)+ReLU -> dense(classes), complexity 1) differing by seed, with he_normal-scaled injected weights.
+  -> (oracle SubnetworkSpec list, engine SubnetworkPlanSpec list)."""
+  from adanet_b200.core import engine as eng
+  h, w, cin = image_shape
+  dims = [(h // 2) * (w // 2) * filters, hidden, classes]
+  o_specs, e_specs = [], []
+  for sd in seeds:
+    rng = np.random.default_rng(7000 + 100 * iteration + sd)
+    he = lambda shape, fan_in: (rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+    ws = [he((3, 3, cin, filters), 9 * cin), he((dims[0], hidden), dims[0]), he((hidden, classes), hidden)]
+    bs = [np.zeros((filters,), np.float32), np.zeros((hidden,), np.float32), np.zeros((classes,), np.float32)]
+    name = "simple_cnn_s{}".format(sd)
+    o_specs.append(orc.SubnetworkSpec(name, dims, 1.0, optimizer, ws=ws, bs=bs))
+    e_specs.append(eng.SubnetworkPlanSpec(name, dims, 1.0, optimizer, [w_.copy() for w_ in ws], [b.copy() for b in bs],
+                                          image_shape=tuple(image_shape)))
+  return o_specs, e_specs
+
+
 import contextlib
 
 

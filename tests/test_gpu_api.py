@@ -57,6 +57,33 @@ def _oracle_simple_dnn_space(orc, layer_size, lr):
   return space
 
 
+def _modern(gen):
+  """The same generator with builders that do NOT define the deprecated `build_mixture_weights_train_op`
+  (examples/simple_dnn keeps it, like the reference's simple_dnn.py:112-122, and it then takes precedence over
+  `Ensembler.build_train_op`: adanet/core/ensemble_builder.py:523-537)."""
+  import adanet_b200 as adanet
+
+  class _Builder(adanet.subnetwork.Builder):
+    def __init__(self, inner):
+      self._inner = inner
+
+    name = property(lambda self: self._inner.name)
+
+    def build_subnetwork(self, features, logits_dimension, training, iteration_step, summary, previous_ensemble=None):
+      return self._inner.build_subnetwork(features, logits_dimension, training, iteration_step, summary, previous_ensemble)
+
+    def build_subnetwork_train_op(self, subnetwork, loss, var_list, labels, iteration_step, summary, previous_ensemble):
+      return self._inner.build_subnetwork_train_op(subnetwork, loss, var_list, labels, iteration_step, summary,
+                                                   previous_ensemble)
+
+  class _Gen(adanet.subnetwork.Generator):
+    def generate_candidates(self, previous_ensemble, iteration_number, previous_ensemble_reports, all_reports):
+      return [_Builder(b) for b in gen.generate_candidates(previous_ensemble, iteration_number, previous_ensemble_reports,
+                                                           all_reports)]
+
+  return _Gen()
+
+
 def _oracle_eval(orc, frozen, mix_w, bias, x, y):
   logits = [orc.mlp_forward(m.ws, m.bs, x)[-1] for m in frozen]
   ens = orc.ensemble_logits("scalar", list(mix_w), bias, logits, [None] * len(logits))
@@ -69,8 +96,8 @@ def test_estimator_simple_dnn_lifecycle_matches_oracle(env, tmp_path):
   from adanet_b200.examples import simple_dnn
   x, y = _data(orc)
   steps, iters, lr = 12, 3, 0.05
-  gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)], optimizer=train.GradientDescentOptimizer(lr),
-                             layer_size=16, seed=SEED)
+  gen = _modern(simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
+                                     optimizer=train.GradientDescentOptimizer(lr), layer_size=16, seed=SEED))
   est = adanet.Estimator(
       head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
       ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(0.01),
@@ -202,8 +229,8 @@ def test_resume_from_model_dir_matches_uninterrupted_run(env, tmp_path):
   steps = 8
 
   def make(model_dir):
-    gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
-                               optimizer=train.GradientDescentOptimizer(0.05), layer_size=16, seed=SEED)
+    gen = _modern(simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
+                                       optimizer=train.GradientDescentOptimizer(0.05), layer_size=16, seed=SEED))
     return adanet.Estimator(
         head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
         ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(0.01),
@@ -248,8 +275,8 @@ def test_resume_inside_an_iteration(env, tmp_path):
   steps = 8
 
   def make(model_dir):
-    gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
-                               optimizer=train.MomentumOptimizer(0.02, 0.9), layer_size=16, seed=SEED)
+    gen = _modern(simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
+                                       optimizer=train.MomentumOptimizer(0.02, 0.9), layer_size=16, seed=SEED))
     return adanet.Estimator(
         head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
         ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.AdamOptimizer(0.01),
@@ -309,8 +336,8 @@ def test_estimator_with_all_solo_grow_strategies_and_mean_ensembler(env):
   strat = [adanet.ensemble.AllStrategy(), adanet.ensemble.SoloStrategy(), adanet.ensemble.GrowStrategy()]
 
   def make(ensembler):
-    gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)], optimizer=train.GradientDescentOptimizer(lr),
-                               layer_size=16, seed=SEED)
+    gen = _modern(simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
+                                       optimizer=train.GradientDescentOptimizer(lr), layer_size=16, seed=SEED))
     return adanet.Estimator(head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
                             ensemblers=[ensembler], ensemble_strategies=strat, max_iterations=iters, debug=True)
 
@@ -348,3 +375,37 @@ def test_estimator_with_all_solo_grow_strategies_and_mean_ensembler(env):
   for rep, res in zip(est._search.reports, want):
     assert rep.candidate_names == res.candidate_names and rep.best_index == res.best_index
     np.testing.assert_allclose(rep.ema_losses, res.ema_losses, atol=1e-5, rtol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("learn", [False, True])
+def test_deprecated_mixture_weights_train_op_takes_precedence(env, learn):
+  """adanet/core/ensemble_builder.py:523-537: examples/simple_dnn builders still define
+  `build_mixture_weights_train_op` (simple_dnn.py:112-122), so the mixture weights follow IT -- a no_op unless
+  learn_mixture_weights, else the builder's optimizer on adanet_loss (regulariser counted once) -- and the
+  Ensembler's own optimizer is ignored."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  from adanet_b200.examples import simple_dnn
+  x, y = _data(orc)
+  steps, iters, lr = 10, 2, 0.05
+  gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)], optimizer=train.GradientDescentOptimizer(lr),
+                             layer_size=16, learn_mixture_weights=learn, seed=SEED)
+  est = adanet.Estimator(
+      head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
+      ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.AdamOptimizer(0.5), adanet_lambda=0.01,
+                                                                 adanet_beta=0.001)],
+      max_iterations=iters, debug=True)
+  est.train(_input_fn(x, y), max_steps=steps * iters)
+  ens = orc.EnsemblerSpec(optimizer=("sgd", lr) if learn else None, adanet_lambda=0.01, adanet_beta=0.001, legacy_train_op=True)
+  want, _ = orc.run_adanet(_oracle_simple_dnn_space(orc, 16, lr), x, y, B, steps, iters, ens, C)
+  for rep, res in zip(est._search.reports, want):
+    assert rep.best_index == res.best_index and rep.architecture == res.architecture
+    np.testing.assert_allclose(rep.ema_losses, res.ema_losses, atol=1e-5, rtol=0)
+    for name, tr in res.traces.items():
+      np.testing.assert_allclose(rep.traces[name]["adanet_loss"], tr["adanet_loss"], atol=1e-5, rtol=0)
+  mw = np.asarray(est._search.reports[-1].mixture_weights)
+  if not learn:
+    np.testing.assert_array_equal(mw, np.full_like(mw, 1.0 / len(mw)))    # never trained (weighted.py:424-437 init)
+  else:
+    assert np.abs(mw - 1.0 / len(mw)).max() > 1e-4

@@ -300,3 +300,48 @@ def test_strategy_parity(built_lib, name):
     assert r.best_index == ro.best_index and r.architecture == ro.architecture
     np.testing.assert_allclose(r.ema_losses, ro.ema_losses, atol=TOL)
   assert [m.name for m in s.frozen] == [n for _, n in o[-1].architecture]
+
+
+# BASELINE config 4: simple_cnn subnetworks on CIFAR-shaped synthetic images (customizing_adanet.ipynb: SimpleCNNBuilder,
+# Momentum(0.9) under cosine decay of the iteration step, mixture weights not trained, adanet_loss_decay=.99)
+CNN_CASES = {
+    "cifar_shaped": dict(image=(32, 32, 3), filters=16, hidden=64, seeds=(0, 1, 2, 3), n=1024, B=64, steps=12, iters=2,
+                         opt=lambda steps: ("momentum_cosine", 0.003, 0.9, steps)),
+    "mnist_shaped_sgd": dict(image=(28, 28, 1), filters=16, hidden=32, seeds=(0, 1), n=600, B=50, steps=10, iters=3,
+                             opt=lambda steps: ("sgd", 0.02)),
+    "wide_stem": dict(image=(12, 12, 3), filters=32, hidden=24, seeds=(5,), n=512, B=128, steps=8, iters=2,
+                      opt=lambda steps: ("momentum", 0.02, 0.9)),
+}
+
+
+def _cnn_data(case, classes=10):
+  h, w, c = case["image"]
+  # X ~ U[0,1) NHWC, labels randint(0, 10); centred like the tutorial's `images / 127.5 - 1`
+  # preprocessing so that the short parity runs train smoothly (no loss spikes amplifying rounding differences)
+  rng = np.random.default_rng(3234)
+  return (rng.uniform(0, 1, (case["n"], h, w, c)) * 2 - 1).astype(np.float32), rng.integers(0, classes, case["n"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CNN_CASES))
+def test_simple_cnn_parity(built_lib, name):
+  from adanet_b200.core import engine as eng
+  from adanet_b200.core import search as srch
+  case = CNN_CASES[name]
+  C = 10
+  x, y = _cnn_data(case, C)
+  opt = case["opt"](case["steps"])
+  mk = lambda t, which: pu.make_cnn_specs(case["seeds"], case["image"], case["filters"], case["hidden"], C, t, opt)[which]
+  o, o_frozen = orc.run_adanet(lambda t, frozen: mk(t, 0), x, y, case["B"], case["steps"], case["iters"], orc.EnsemblerSpec(),
+                               C, adanet_loss_decay=0.99)
+  s = srch.AdaNetSearch(lambda t, frozen: mk(t, 1), eng.EnsemblerPlanSpec(), int(np.prod(case["image"])), C, case["B"],
+                        adanet_loss_decay=0.99)
+  reps = s.run(srch.consecutive_batches(x, y, case["B"]), case["steps"], case["iters"])
+  worst = _check(o, reps)
+  print("%s worst per-step abs err %.3g" % (name, worst))
+  # the trained stem and dense weights of the selected members
+  for m, mo in zip(s.frozen, o_frozen):
+    ws, bs = m.numpy_params()
+    assert ws[0].ndim == 4
+    for a, b in zip(ws + bs, list(mo.ws) + list(mo.bs)):
+      np.testing.assert_allclose(a, b, atol=5e-5)

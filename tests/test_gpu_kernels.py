@@ -198,7 +198,8 @@ def test_ensemble_head(gpu, mix, B, C, N, use_bias, lam, beta, mult):
     np.testing.assert_allclose(db.cpu().numpy(), want_db, atol=5e-6)
 
 
-@pytest.mark.parametrize("spec", [("sgd", 0.05), ("momentum", 0.05, 0.9), ("rmsprop", 0.01), ("adam", 0.001)])
+@pytest.mark.parametrize("spec", [("sgd", 0.05), ("momentum", 0.05, 0.9), ("rmsprop", 0.01), ("adam", 0.001),
+                                  ("momentum_cosine", 0.05, 0.9, 4), ("momentum_cosine", 0.05, 0.9, 50, 0.1)])
 def test_opt_step(gpu, spec):
   import torch
   from adanet_b200.core import engine as eng
@@ -250,3 +251,70 @@ def test_record_and_counter(gpu):
     _lib.check(gpu.adn_counter_add(step.data_ptr(), 1, _sp()), "counter")
   assert int(step.item()) == 6
   np.testing.assert_allclose(trace.cpu().numpy()[:, 0], [4, 5, 2, 3])
+
+
+@pytest.mark.parametrize("B,H,W,CIN,F", [(64, 32, 32, 3, 16), (5, 8, 8, 3, 16), (33, 28, 28, 1, 16), (16, 10, 10, 3, 32),
+                                         (700, 32, 32, 3, 16), (3, 6, 4, 1, 48)])
+def test_conv_stem_fwd_bwd(gpu, B, H, W, CIN, F):
+  """SimpleCNN stem (customizing_adanet.ipynb SimpleCNNBuilder): conv3x3 same + ReLU + maxpool 2x2 + flatten,
+  forward into split planes and the kernel / bias gradients, vs the oracle."""
+  import torch
+  from adanet_b200 import _lib
+  rng = np.random.default_rng(B * 7 + H + F)
+  x = rng.uniform(0, 1, (B, H, W, CIN)).astype(np.float32)
+  k = (rng.standard_normal((3, 3, CIN, F)) * np.sqrt(2.0 / (9 * CIN))).astype(np.float32)   # he_normal scale
+  bias = (rng.standard_normal(F) * 0.1).astype(np.float32)
+  want = orc.conv_stem_forward(k, bias, x)
+  cols = (H // 2) * (W // 2) * F
+  xd, kd, bd = _dev(x), _dev(k), _dev(bias)
+  planes = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, cols) // 4,), dtype=torch.float32, device="cuda")
+  arg = torch.zeros((B * cols // 16,), dtype=torch.int32, device="cuda")
+  _lib.check(gpu.adn_conv_stem_fwd(xd.data_ptr(), kd.data_ptr(), bd.data_ptr(), planes.data_ptr(), arg.data_ptr(), B, H, W,
+                                   CIN, F, _sp()), "adn_conv_stem_fwd")
+  got = torch.empty((B, cols), dtype=torch.float32, device="cuda")
+  _lib.check(gpu.adn_planes_merge(planes.data_ptr(), B, cols, got.data_ptr(), _sp()), "adn_planes_merge")
+  got = got.cpu().numpy()
+  np.testing.assert_allclose(got, np.asarray(want), rtol=0, atol=2e-6 * max(1.0, float(np.abs(want).max())))
+  # sign bits = (pooled > 0): [cols/32][B] words after the two planes
+  nkb = (cols + 31) // 32
+  plane_floats = ((B * nkb * 32 + 63) // 64) * 64
+  words = planes.view(torch.int32)[2 * plane_floats:2 * plane_floats + nkb * B].cpu().numpy().view(np.uint32).reshape(nkb, B)
+  padded = np.zeros((B, nkb * 32), dtype=bool)
+  padded[:, :cols] = got > 0
+  want_words = (padded.reshape(B, nkb, 32) * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32).T
+  np.testing.assert_array_equal(words, want_words)
+  # arg-max agrees with the oracle wherever the maximum is unique and active
+  a = arg.cpu().numpy().view(np.uint32).reshape(B, cols // 16)
+  pos = ((a[:, :, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3).reshape(B, cols)
+  o_arg = want.cache[1].reshape(B, cols)
+  active = np.asarray(want) > 1e-4
+  assert (pos[active] == o_arg[active]).mean() > 0.999
+  # backward: dpooled already masked by (pooled > 0), as the first dense layer's dX epilogue delivers it
+  g = (rng.standard_normal((B, cols)).astype(np.float32) / B) * (got > 0)
+  dk_want, db_want = orc.conv_stem_backward(want, g)
+  ws_bytes = _lib.query(_lib.Q_CONV_STEM_BWD_WS, B, CIN, F)
+  ws = torch.empty((ws_bytes,), dtype=torch.uint8, device="cuda")
+  dk = torch.empty((3, 3, CIN, F), dtype=torch.float32, device="cuda")
+  db = torch.empty((F,), dtype=torch.float32, device="cuda")
+  gd = _dev(g)
+  for _ in range(2):     # twice: no state carried between calls
+    _lib.check(gpu.adn_conv_stem_bwd(xd.data_ptr(), arg.data_ptr(), gd.data_ptr(), dk.data_ptr(), db.data_ptr(), B, H, W,
+                                     CIN, F, ws.data_ptr(), ws_bytes, _sp()), "adn_conv_stem_bwd")
+  tol = 2e-5 * max(1e-3, float(np.abs(dk_want).max()))
+  np.testing.assert_allclose(dk.cpu().numpy(), dk_want, rtol=0, atol=tol)
+  np.testing.assert_allclose(db.cpu().numpy(), db_want, rtol=0, atol=2e-5 * max(1e-3, float(np.abs(db_want).max())))
+
+
+def test_conv_stem_rejects_bad_shapes(gpu):
+  import torch
+  from adanet_b200 import _lib
+  t = torch.zeros((1 << 16,), dtype=torch.float32, device="cuda")
+  p = t.data_ptr()
+  for (h, w, c, f) in [(7, 8, 3, 16), (8, 8, 2, 16), (8, 8, 3, 24), (8, 8, 3, 128), (0, 8, 3, 16)]:
+    assert gpu.adn_conv_stem_fwd(p, p, p, p, p, 2, h, w, c, f, _sp()) != 0
+    assert b"adn_conv_stem_fwd" in gpu.adn_last_error()
+  assert gpu.adn_conv_stem_bwd(p, p, p, p, p, 2, 8, 8, 3, 16, p, 16, _sp()) == _lib_err_workspace()
+
+
+def _lib_err_workspace():
+  return -12
