@@ -505,6 +505,17 @@ class Estimator(object):
     os.replace(tmp, os.path.join(self._model_dir, "ensemble-latest.json"))
 
   # ------------------------------------------------------------------ evaluate / predict
+  def _restore_for_inference(self, input_fn):
+    """evaluate / predict on a fresh Estimator whose model_dir holds a trained ensemble: shapes come from the
+    first batch of `input_fn`, the ensemble from the latest checkpoint (the reference rebuilds the graph from
+    architecture-{t}.json and restores increment.ckpt-{t}, adanet/core/estimator.py:1785-1882)."""
+    if self._search is not None or not self._model_dir or not self.latest_checkpoint():
+      return
+    for item in input_utils.iterate_input_fn(input_fn):
+      self._ensure_search(item[0] if isinstance(item, tuple) else item)
+      self._maybe_restore()
+      return
+
   def _ensemble_eval_plan(self):
     from adanet_b200.core import engine as eng
     s = self._search
@@ -521,6 +532,7 @@ class Estimator(object):
   def evaluate(self, input_fn, steps=None, hooks=None, checkpoint_path=None, name=None):
     """Mean loss of the best ensemble over `steps` batches (+ accuracy for classification),
     `global_step`, `iteration` and the architecture string (eval_metrics.py:227-264,347-393)."""
+    self._restore_for_inference(input_fn)
     plan = self._ensemble_eval_plan()
     n, loss_sum, correct, total = 0, 0.0, 0, 0
     for features, labels in input_utils.iterate_input_fn(input_fn):
@@ -550,6 +562,7 @@ class Estimator(object):
     """Yields per-example predictions of the best ensemble: logits (+ probabilities / class_ids
     for MultiClassHead, logistic for BinaryClassHead, predictions for RegressionHead)."""
     import torch
+    self._restore_for_inference(input_fn)
     plan = self._ensemble_eval_plan()
     for item in input_utils.iterate_input_fn(input_fn):
       features = item[0] if isinstance(item, tuple) else item

@@ -409,3 +409,63 @@ def test_deprecated_mixture_weights_train_op_takes_precedence(env, learn):
     np.testing.assert_array_equal(mw, np.full_like(mw, 1.0 / len(mw)))    # never trained (weighted.py:424-437 init)
   else:
     assert np.abs(mw - 1.0 / len(mw)).max() > 1e-4
+
+
+@pytest.mark.gpu
+def test_estimator_simple_cnn_matches_oracle_and_resumes(env, tmp_path):
+  """BASELINE config 4 through the public API: examples/simple_cnn (the tutorial's SimpleCNNBuilder /
+  SimpleCNNGenerator, customizing_adanet.ipynb) on NHWC image features; per-step losses and the selection against
+  the oracle, then evaluate / predict and a restart from model_dir (conv stem weights restored)."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph
+  from adanet_b200.examples import simple_cnn
+  H = W = 16
+  CIN, K, steps, iters, lr, seed = 3, 2, 8, 2, 0.004, 5
+  rng = np.random.default_rng(3234)
+  x = (rng.uniform(0, 1, (B * 24, H, W, CIN)) * 2 - 1).astype(np.float32)
+  y = rng.integers(0, C, x.shape[0])
+
+  def make(model_dir):
+    return adanet.Estimator(head=adanet.heads.MultiClassHead(C),
+                            subnetwork_generator=simple_cnn.SimpleCNNGenerator(lr, steps, seed=seed, num_candidates=K),
+                            max_iteration_steps=steps, adanet_loss_decay=.99, max_iterations=iters, model_dir=model_dir,
+                            debug=True)
+
+  est = make(str(tmp_path))
+  est.train(_input_fn(x, y, key="images"), max_steps=steps * iters)
+
+  def space(t, frozen):
+    specs = []
+    P = (H // 2) * (W // 2) * 16
+    for j in range(K):
+      init = graph.he_normal_initializer(seed=seed + t * K + j)     # one generator per builder, layers in build order
+      ws = [init((3, 3, CIN, 16)), init((P, 64)), init((64, C))]
+      bs = [np.zeros((16,), np.float32), np.zeros((64,), np.float32), np.zeros((C,), np.float32)]
+      specs.append(orc.SubnetworkSpec("simple_cnn_{}".format(j), [P, 64, C], 1.0, ("momentum_cosine", lr, 0.9, steps), ws=ws,
+                                      bs=bs))
+    return specs
+
+  # mixture weights: the builder's deprecated no-op train op (ensemble_builder.py:523-537) -> never trained
+  want, frozen = orc.run_adanet(space, x, y, B, steps, iters, orc.EnsemblerSpec(), C, adanet_loss_decay=0.99)
+  for rep, res in zip(est._search.reports, want):
+    assert rep.candidate_names == res.candidate_names
+    assert rep.best_index == res.best_index and rep.architecture == res.architecture
+    np.testing.assert_allclose(rep.ema_losses, res.ema_losses, atol=1e-5, rtol=0)
+    for name, tr in res.traces.items():
+      for f in ("sub_loss", "adanet_loss"):
+        np.testing.assert_allclose(rep.traces[name][f], tr[f], atol=1e-5, rtol=0)
+  # evaluate / predict on held-out images
+  xe = (np.random.default_rng(99).uniform(0, 1, (B * 2, H, W, CIN)) * 2 - 1).astype(np.float32)
+  ye = np.random.default_rng(98).integers(0, C, B * 2)
+  ev = est.evaluate(_input_fn(xe, ye, key="images"), steps=2)
+  want_loss = np.mean([_oracle_eval(orc, frozen, want[-1].mixture_weights, want[-1].bias, xe[i:i + B], ye[i:i + B])[0]
+                       for i in (0, B)])
+  assert abs(ev["loss"] - want_loss) < 1e-5
+  preds = list(est.predict(_input_fn(xe[:B], ye[:B], key="images")))
+  _, ens_logits = _oracle_eval(orc, frozen, want[-1].mixture_weights, want[-1].bias, xe[:B], ye[:B])
+  np.testing.assert_allclose(np.stack([p["logits"] for p in preds]), ens_logits, atol=2e-5)
+  # a new Estimator on the same model_dir restores the ensemble, conv stems included
+  est2 = make(str(tmp_path))
+  ev2 = est2.evaluate(_input_fn(xe, ye, key="images"), steps=2)
+  assert ev2["loss"] == ev["loss"] and ev2["iteration"] == iters
+  assert est2.architecture_string() == est.architecture_string()
