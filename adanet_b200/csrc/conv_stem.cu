@@ -14,8 +14,8 @@
 //
 // Forward: one CTA per image (grid-stride), 256 threads, image staged zero-padded in shared memory with cp.async
 // (double buffered: the next image lands while this one is computed); a thread owns one pooled pixel and 16
-// filters at a time: 4 conv positions x 16 filters = 64 accumulators fed from a 4x4xCin register patch and
-// float4 broadcast reads of the kernel.  Epilogue: bias, ReLU, 2x2 max, hi/lo TF32 split, sign bits, and a
+// filters at a time: 4 conv positions x 16 filters = 64 accumulators fed from the 4x4xCin patch in shared memory
+// and float4 broadcast reads of the kernel (<= 128 registers: two CTAs per SM hide each other's latencies).  Epilogue: bias, ReLU, 2x2 max, hi/lo TF32 split, sign bits, and a
 // 2-bit argmax per element for the backward.
 // Backward: dK[ky,kx,c,f] = sum_{b,p} patch(b, argmax(b,p,f))[ky,kx,c] * g[b,p,f], db[f] = sum g, where g is the
 // gradient w.r.t. the pooled features already masked by (pooled > 0) (the dX epilogue of the first dense layer
@@ -53,15 +53,16 @@ template <int CIN>
 __device__ __forceinline__ void stage_image(float* s_img, const float* img, int H, int W, int tid, int nthreads) {
   const int row = W * CIN;
   const int prow = (W + 2) * CIN;
-  for (int i = tid; i < H * row; i += nthreads) {
-    const int y = i / row;
-    const int r = i - y * row;
-    cp_async4(s_img + (y + 1) * prow + CIN + r, img + i);
+  const int lane = tid & 31, nwarps = nthreads >> 5;
+  for (int y = tid >> 5; y < H; y += nwarps) {          // a warp per image row: no per-element division
+    const float* src = img + y * row;
+    float* dst = s_img + (y + 1) * prow + CIN;
+    for (int r = lane; r < row; r += 32) cp_async4(dst + r, src + r);
   }
 }
 
 template <int CIN>
-__global__ void __launch_bounds__(FWD_THREADS)
+__global__ void __launch_bounds__(FWD_THREADS, 2)
 conv_stem_fwd_kernel(const float* __restrict__ images, const float* __restrict__ kernel, const float* __restrict__ bias,
                      float* __restrict__ hi, float* __restrict__ lo, uint16_t* __restrict__ bits16,
                      uint32_t* __restrict__ argmax, int64_t B, int H, int W, int F) {
@@ -93,14 +94,8 @@ conv_stem_fwd_kernel(const float* __restrict__ images, const float* __restrict__
     const float* s_img = s_img0 + buf * pimg;
     for (int p = tid; p < P; p += FWD_THREADS) {
       const int py = p / PW, px = p - py * PW;
-      // 4x4xCIN input patch around the 2x2 conv positions (padded coordinates start at (2py, 2px))
-      float patch[4][4][CIN];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int c = 0; c < CIN; ++c) patch[i][j][c] = s_img[(2 * py + i) * prow + (2 * px + j) * CIN + c];
+      // the 4x4xCIN input patch of this pooled pixel starts at padded coordinates (2py, 2px)
+      const float* patch = s_img + (2 * py) * prow + (2 * px) * CIN;
       for (int f0 = 0; f0 < F; f0 += FC) {
         float acc[4][FC];
 #pragma unroll
@@ -125,7 +120,7 @@ conv_stem_fwd_kernel(const float* __restrict__ images, const float* __restrict__
               for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
-                  const float v = patch[dy + ky][dx + kx][c];
+                  const float v = patch[(dy + ky) * prow + (dx + kx) * CIN + c];
 #pragma unroll
                   for (int j = 0; j < FC; ++j) acc[dy * 2 + dx][j] = fmaf(v, w[j], acc[dy * 2 + dx][j]);
                 }
@@ -170,11 +165,10 @@ conv_stem_fwd_kernel(const float* __restrict__ images, const float* __restrict__
 // once per nine FMAs (the gather address depends on f through the arg-max, so taps are the only reuse there is).
 // G groups of CIN*F threads split the pooled pixels of an image; their accumulators are summed in fixed order
 // through shared memory once per CTA.
-template <int CIN>
+template <int CIN, int F>
 __global__ void __launch_bounds__(1024)
 conv_stem_bwd_kernel(const float* __restrict__ images, const uint32_t* __restrict__ argmax,
-                     const float* __restrict__ dpooled, float* __restrict__ partials, int64_t B, int H, int W, int F,
-                     int G) {
+                     const float* __restrict__ dpooled, float* __restrict__ partials, int64_t B, int H, int W, int G) {
   extern __shared__ __align__(16) float smem[];
   const int K = 9 * CIN;
   const int PH = H / 2, PW = W / 2, P = PH * PW;
@@ -190,7 +184,7 @@ conv_stem_bwd_kernel(const float* __restrict__ images, const uint32_t* __restric
   const int c = (tid / F) % CIN;
   const int grp = tid / (F * CIN);
   const int wsel = f >> 4, sh = 2 * (f & 15);
-  const int fw = F / 16;
+  constexpr int fw = F / 16;
   float acc[9];
 #pragma unroll
   for (int q = 0; q < 9; ++q) acc[q] = 0.f;
@@ -205,19 +199,29 @@ conv_stem_bwd_kernel(const float* __restrict__ images, const uint32_t* __restric
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    int py = grp / PW, px = grp - py * PW;
-    for (int p = grp; p < P; p += G) {
-      const float g = s_g[p * F + f];
-      const uint32_t pos = (s_arg[p * fw + wsel] >> sh) & 3u;
-      // padded coordinates of tap (0, 0) at the arg-max conv position (2py + dy, 2px + dx)
-      const float* src = s_img + (2 * py + (int)(pos >> 1)) * prow + (2 * px + (int)(pos & 1u)) * CIN + c;
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(src[ky * prow + kx * CIN], g, acc[ky * 3 + kx]);
-      accb += g;
-      px += G;
-      while (px >= PW) { px -= PW; ++py; }
+    // groups stride the pooled pixels of a row; tap addresses are three row pointers + compile-time offsets
+    for (int py = 0; py < PH; ++py) {
+      const float* grow = s_g + (py * PW) * F + f;
+      const uint32_t* arow = s_arg + (py * PW) * fw + wsel;
+      const float* irow = s_img + (2 * py) * prow + c;
+      for (int px = grp; px < PW; px += G) {
+        const float g = grow[px * F];
+        const uint32_t pos = (arow[px * fw] >> sh) & 3u;
+        // padded coordinates of tap (0, 0) at the arg-max conv position (2py + dy, 2px + dx)
+        const float* r0 = irow + (pos >> 1) * prow + (2 * px + (pos & 1u)) * CIN;
+        const float* r1 = r0 + prow;
+        const float* r2 = r1 + prow;
+        acc[0] = fmaf(r0[0], g, acc[0]);
+        acc[1] = fmaf(r0[CIN], g, acc[1]);
+        acc[2] = fmaf(r0[2 * CIN], g, acc[2]);
+        acc[3] = fmaf(r1[0], g, acc[3]);
+        acc[4] = fmaf(r1[CIN], g, acc[4]);
+        acc[5] = fmaf(r1[2 * CIN], g, acc[5]);
+        acc[6] = fmaf(r2[0], g, acc[6]);
+        acc[7] = fmaf(r2[CIN], g, acc[7]);
+        acc[8] = fmaf(r2[2 * CIN], g, acc[8]);
+        accb += g;
+      }
     }
     __syncthreads();
   }
@@ -317,12 +321,22 @@ extern "C" int adn_conv_stem_bwd(const float* images, const uint32_t* argmax, co
   float* partials = static_cast<float*>(workspace);
   auto launch = [&](auto kern) -> int {
     ADN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, as_stream(stream)>>>(images, argmax, dpooled, partials, batch, height, width, filters,
-                                                     groups);
+    kern<<<grid, threads, smem, as_stream(stream)>>>(images, argmax, dpooled, partials, batch, height, width, groups);
     ADN_CHECK_LAUNCH("conv_stem_bwd");
     return ADN_OK;
   };
-  if (int rc = channels == 3 ? launch(conv::conv_stem_bwd_kernel<3>) : launch(conv::conv_stem_bwd_kernel<1>)) return rc;
+  int rc = ADN_OK;
+  switch (filters / 16 * 4 + channels) {      // filters in {16,32,48,64} x channels in {1,3}
+    case 1 * 4 + 1: rc = launch(conv::conv_stem_bwd_kernel<1, 16>); break;
+    case 1 * 4 + 3: rc = launch(conv::conv_stem_bwd_kernel<3, 16>); break;
+    case 2 * 4 + 1: rc = launch(conv::conv_stem_bwd_kernel<1, 32>); break;
+    case 2 * 4 + 3: rc = launch(conv::conv_stem_bwd_kernel<3, 32>); break;
+    case 3 * 4 + 1: rc = launch(conv::conv_stem_bwd_kernel<1, 48>); break;
+    case 3 * 4 + 3: rc = launch(conv::conv_stem_bwd_kernel<3, 48>); break;
+    case 4 * 4 + 1: rc = launch(conv::conv_stem_bwd_kernel<1, 64>); break;
+    default: rc = launch(conv::conv_stem_bwd_kernel<3, 64>); break;
+  }
+  if (rc) return rc;
   const int n_out = kf + filters;
   conv::conv_stem_reduce_kernel<<<(n_out + 255) / 256, 256, 0, as_stream(stream)>>>(partials, grid, n_out, kf, dkernel,
                                                                                    dbias);

@@ -200,3 +200,54 @@ def test_run_adanet_small_end_to_end():
   # loss decreases within the first iteration
   tr = res[0].traces[res[0].candidate_names[0]]["sub_loss"]
   assert tr[-1] < tr[0]
+
+
+def test_conv_stem_matches_torch_fp64():
+  """The SimpleCNN stem of the oracle (conv3x3 same + ReLU + maxpool 2x2 + flatten, and its kernel / bias
+  gradients) is PARITY UNPINNED by the reference's tests (the notebook holds no known-answer values); it is pinned
+  here against torch's conv2d / max_pool2d autograd in fp64, an independent implementation of the same Keras
+  layers (customizing_adanet.ipynb SimpleCNNBuilder.build_subnetwork)."""
+  import torch
+  rng = np.random.default_rng(0)
+  for (B, H, W, CIN, F) in [(4, 8, 8, 3, 16), (3, 6, 10, 1, 32)]:
+    x = rng.standard_normal((B, H, W, CIN)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, CIN, F)) * 0.3).astype(np.float32)
+    b = (rng.standard_normal(F) * 0.1).astype(np.float32)
+    w1 = (rng.standard_normal(((H // 2) * (W // 2) * F, 10)) * 0.1).astype(np.float32)
+    b1 = np.zeros(10, np.float32)
+    y = rng.integers(0, 10, B)
+    acts = orc.mlp_forward([k, w1], [b, b1], x)
+    loss, dl = orc.softmax_xent_mean(acts[-1], y)
+    dws, dbs = orc.mlp_backward([k, w1], acts, dl)
+    xt = torch.tensor(x).permute(0, 3, 1, 2).double()
+    kt = torch.tensor(k).permute(3, 2, 0, 1).double().requires_grad_()
+    bt = torch.tensor(b).double().requires_grad_()
+    w1t = torch.tensor(w1).double().requires_grad_()
+    p = torch.nn.functional.max_pool2d(torch.nn.functional.conv2d(xt, kt, bt, padding=1).relu(), 2, 2)
+    p = p.permute(0, 2, 3, 1).reshape(B, -1)                      # Keras Flatten of NHWC
+    l = torch.nn.functional.cross_entropy(p @ w1t, torch.tensor(y))
+    l.backward()
+    assert abs(float(loss) - float(l.detach())) < 1e-6
+    np.testing.assert_allclose(np.asarray(acts[1]), p.detach().numpy(), atol=2e-6)
+    np.testing.assert_allclose(dws[0], kt.grad.permute(2, 3, 1, 0).numpy(), atol=1e-6)
+    np.testing.assert_allclose(dbs[0], bt.grad.numpy(), atol=1e-6)
+    np.testing.assert_allclose(dws[1], w1t.grad.numpy(), atol=1e-6)
+    # flat [B, H*W*Cin] square images are accepted too (what the engine is fed)
+    if H == W:
+      np.testing.assert_array_equal(np.asarray(orc.mlp_forward([k, w1], [b, b1], x.reshape(B, -1))[-1]), np.asarray(acts[-1]))
+
+
+def test_cosine_decay_momentum_schedule():
+  """tf.train.cosine_decay [TF] at the iteration step before the update: lr, ..., 0 at decay_steps and after."""
+  o = orc.make_optimizer(("momentum_cosine", 0.05, 0.9, 10))
+  p = [np.ones(3, np.float32)]
+  lrs = []
+  for _ in range(12):
+    o.apply(p, [np.ones(3, np.float32)])
+    lrs.append(float(o.lr))
+  want = [0.05 * 0.5 * (1 + np.cos(np.pi * min(t, 10) / 10)) for t in range(12)]
+  np.testing.assert_allclose(lrs, want, atol=1e-8)
+  assert lrs[0] == np.float32(0.05) and lrs[10] == 0.0 and lrs[11] == 0.0
+  o = orc.make_optimizer(("momentum_cosine", 0.05, 0.9, 4, 0.1))
+  o.apply(p, [np.ones(3, np.float32)]); o.apply(p, [np.ones(3, np.float32)])
+  assert abs(float(o.lr) - 0.05 * (0.9 * 0.5 * (1 + np.cos(np.pi / 4)) + 0.1)) < 1e-8
