@@ -18,8 +18,9 @@ from adanet_b200 import subnetwork as subnetwork_lib
 
 class AutoEnsembleSubestimator(collections.namedtuple("AutoEnsembleSubestimator",
                                                       ["estimator", "train_input_fn", "prediction_only"])):
-  """A sub-estimator with optional bagging input (common.py:63-93).  Per-candidate
-  `train_input_fn` (bagging) is a 'next' row."""
+  """A sub-estimator with optional bagging input (common.py:63-93): with `train_input_fn` the subnetwork trains on
+  minibatches of that input_fn (same `(features, labels)` batch conventions and batch size as the Estimator's
+  `input_fn`), one step before each main step, and the ensembles read its forward on the shared minibatch."""
 
   def __new__(cls, estimator, train_input_fn=None, prediction_only=False):
     return super(AutoEnsembleSubestimator, cls).__new__(cls, estimator, train_input_fn, prediction_only)
@@ -53,8 +54,8 @@ class _BuilderFromSubestimator(subnetwork_lib.Builder):
   def build_subnetwork(self, features, labels, logits_dimension, training, iteration_step, summary,
                        previous_ensemble=None, config=None):
     sub = self._subestimator
-    if sub.train_input_fn is not None:
-      raise NotImplementedError("bagging (per-candidate train_input_fn) is a 'next' row (SURVEY.md 8f.4)")
+    # bagging (common.py:151-180): the engine is told to train this subnetwork on its own input_fn
+    self.bagging_train_input_fn = sub.train_input_fn if (training and not sub.prediction_only) else None
     logits = sub.estimator.build_logits(features, logits_dimension)
     if self._logits_fn is not None:
       logits = self._logits_fn(logits)

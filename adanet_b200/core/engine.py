@@ -93,6 +93,9 @@ class SubnetworkPlanSpec:
   bs: List[np.ndarray]
   shared: Optional[dict] = None
   image_shape: Optional[Tuple[int, int, int]] = None
+  # bagging (adanet/autoensemble/common.py:151-180): the subnetwork trains on minibatches of its OWN input_fn
+  # (before the step's main pass, :43-56) and only its forward on the shared minibatch feeds the ensembles
+  own_input: bool = False
 
 
 @dataclass
@@ -547,6 +550,15 @@ class CandidatePlan:
     self.workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
     self.ws_bytes = ws_bytes
     self.sub_loss = torch.zeros((1,), **f32)
+    self.bagged = bool(getattr(spec, "own_input", False))
+    if self.bagged:
+      if not self.planes:
+        raise NotImplementedError("bagged subnetworks (own train_input_fn) run on the plane path only")
+      self.x_own = torch.empty((batch, self.net.in_dim), **f32)
+      self.xp_own = None if self.net.stem else new_planes(batch, self.net.in_dim, device)
+      self.labels_own = (torch.empty((batch,), dtype=torch.int64, device=device) if head == "softmax_xent"
+                         else torch.empty((batch, logits_dim), **f32))
+      self.own_loss = torch.zeros((1,), **f32)    # loss on the bagged minibatch (not reported by the reference)
     params, self._grads, planes = [], [], []
     if self.net.stem:
       # conv stem: dense gradient of the pooled features (first dense layer's dX), kernel / bias gradients
@@ -658,11 +670,17 @@ class CandidatePlan:
     return self.ehead.mixture_weight_tensors()
 
   # ---- plane path, wave-synchronous schedule (IterationPlan._enqueue_waves) ----
-  def enqueue_sub_loss(self, labels, labels_f, sp: int):
+  def load_own_batch(self, x, y):
+    """The bagged subnetwork's own minibatch for the next step (its `train_input_fn`, common.py:151-160)."""
+    self.x_own.copy_(torch.as_tensor(x).reshape(self.x_own.shape), non_blocking=True)
+    self.labels_own.copy_(torch.as_tensor(y).reshape(self.labels_own.shape), non_blocking=True)
+
+  def enqueue_sub_loss(self, labels, labels_f, sp: int, loss_out: Optional[torch.Tensor] = None):
     """step 3 after the forward waves: subnetwork loss, dlogits (dense + planes) and db of the logits layer."""
     lab = labels.data_ptr() if labels is not None else None
     labf = labels_f.data_ptr() if labels_f is not None else None
-    _lib.check(self.lib.adn_head_loss_p(self.head, self.net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
+    loss_out = loss_out if loss_out is not None else self.sub_loss
+    _lib.check(self.lib.adn_head_loss_p(self.head, self.net.logits.data_ptr(), lab, labf, loss_out.data_ptr(),
                                         self.dlogits.data_ptr(), self.dzp_out.data_ptr(),
                                         self.dbs[len(self.net.ws) - 1].data_ptr(), self.batch, self.C,
                                         self.workspace.data_ptr(), self.ws_bytes, sp), "adn_head_loss_p")
@@ -821,6 +839,32 @@ class IterationPlan:
     lib = self.lib
     main = torch.cuda.current_stream(self.device)
     sp = main.cuda_stream
+    # bagging pre-pass (adanet/autoensemble/common.py:43-56,151-180): a bagged subnetwork takes one training step
+    # on a minibatch of its own input_fn BEFORE the main pass, which then only reads its (updated) forward
+    bag = [c for c in self.candidates if c.bagged]
+    if bag:
+      for c in bag:
+        if c.xp_own is not None:
+          _lib.check(lib.adn_planes_split(c.x_own.data_ptr(), self.batch, c.net.in_dim, c.xp_own.data_ptr(), sp),
+                     "adn_planes_split")
+        else:
+          c.net.stem_forward(lib, c.x_own, sp)
+      for w in range(max(len(c.net.ws) for c in bag)):
+        ops = [c.net.fwd_op(w, c.xp_own) for c in bag if w < len(c.net.ws)]
+        _lib.check(lib.adn_dense_fwd_p_group((_lib.FwdOp * len(ops))(*ops), len(ops), self.batch, sp),
+                   "adn_dense_fwd_p_group")
+      for c in bag:
+        lab_i = c.labels_own if self.labels is not None else None
+        lab_f = c.labels_own if self.labels is None else None
+        c.enqueue_sub_loss(lab_i, lab_f, sp, loss_out=c.own_loss)
+      for k in range(max(len(c.net.ws) for c in bag)):
+        ops = [c.bwd_op(k, c.xp_own) for c in bag if k < len(c.net.ws)]
+        _lib.check(lib.adn_dense_bwd_p_group((_lib.BwdOp * len(ops))(*ops), len(ops), self.batch, sp),
+                   "adn_dense_bwd_p_group")
+      for c in bag:
+        if c.net.stem:
+          c.enqueue_stem_bwd(c.x_own, sp)
+        c.enqueue_sub_update(sp)
     self._split_x(sp)
     nets = list(self.frozen) + [c.net for c in self.candidates]
     for n in nets:
@@ -847,11 +891,14 @@ class IterationPlan:
       s = side[slot]
       with torch.cuda.stream(s):
         h.enqueue(self.labels, self.labels_f, self.step_dev, s.cuda_stream, self.xp)
-    for k in range(max(len(c.net.ws) for c in self.candidates)):
-      ops = [c.bwd_op(k, self.xp) for c in self.candidates if k < len(c.net.ws)]
+    trained = [c for c in self.candidates if not c.bagged]      # bagged subnetworks already took their step
+    for k in range(max([len(c.net.ws) for c in trained] or [0])):
+      ops = [c.bwd_op(k, self.xp) for c in trained if k < len(c.net.ws)]
       arr = (_lib.BwdOp * len(ops))(*ops)
       _lib.check(lib.adn_dense_bwd_p_group(arr, len(ops), self.batch, sp), "adn_dense_bwd_p_group")
     for c, s in zip(self.candidates, side):
+      if c.bagged:
+        continue
       if s is not main:
         s.wait_stream(main)
       with torch.cuda.stream(s):
@@ -891,9 +938,15 @@ class IterationPlan:
       _lib.check(self.lib.adn_planes_split(self.x.data_ptr(), self.batch, self.in_dim, self.xp.data_ptr(), sp),
                  "adn_planes_split")
 
-  def train_step(self, x=None, y=None):
+  def train_step(self, x=None, y=None, own_batches: Optional[Dict[int, tuple]] = None):
     """One training step of every candidate on this GPU on one minibatch: the one passed in, or the one
-    started earlier with `stage_batch`."""
+    started earlier with `stage_batch`.  `own_batches[candidate_index] = (x, y)` feeds the bagged subnetworks
+    (those whose spec has `own_input`); each must get a fresh minibatch every step."""
+    for c in self.candidates:
+      if c.bagged:
+        if own_batches is None or c.index not in own_batches:
+          raise ValueError("bagged subnetwork %s needs its own minibatch (own_batches[%d])" % (c.spec.name, c.index))
+        c.load_own_batch(*own_batches[c.index])
     if x is not None:
       self.load_batch(x, y)
     elif self._stage is not None and self._stage.get("pending"):

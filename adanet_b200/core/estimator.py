@@ -209,8 +209,28 @@ class Estimator(object):
       specs.append(spec)
       subs.append(sub)
     self._pending = (builders, subs)
+    # bagged candidates: a fresh iterator over their own train_input_fn for this iteration (the reference builds a
+    # new one-shot iterator with every iteration graph, autoensemble/common.py:151-160)
+    self._bagging_iters = {i: iter(input_utils.iterate_input_fn(b.bagging_train_input_fn))
+                           for i, (b, sp) in enumerate(zip(builders, specs)) if sp.own_input}
     self._apply_legacy_mixture_weights_train_op(builders, subs, labels_ph)
     return specs
+
+  def _next_bagging_batches(self):
+    """One minibatch per bagged candidate for the coming step; None when any of them ran out of data (the
+    reference's OutOfRangeError ends training, autoensemble/common.py:75-78)."""
+    out = {}
+    for i, it in getattr(self, "_bagging_iters", {}).items():
+      try:
+        f, l = next(it)
+      except StopIteration:
+        logging.info("bagging input of candidate %d is exhausted: training stops", i)
+        return None
+      if input_utils.batch_size_of(f) != self._batch_size:
+        raise ValueError("bagging train_input_fn of candidate %d yields batches of %d examples, the Estimator's input_fn %d"
+                         % (i, input_utils.batch_size_of(f), self._batch_size))
+      out[i] = (input_utils.to_matrix(f, self._feature_keys), l)
+    return out
 
   def _apply_legacy_mixture_weights_train_op(self, builders, subs, labels_ph):
     """adanet/core/ensemble_builder.py:523-537: a candidate whose first builder still defines the deprecated
@@ -287,6 +307,9 @@ class Estimator(object):
     self._search.plan.load_state_dict(st)
     self._global_step = int(st["meta_global_step"])
     self._iteration_step = int(st["meta_iteration_step"])
+    for it in getattr(self, "_bagging_iters", {}).values():      # bagging inputs restart with the iteration: skip what it consumed
+      for _ in range(self._iteration_step):
+        next(it, None)
     logging.info("resumed iteration %d at iteration step %d (global step %d)", self._search.iteration,
                  self._iteration_step, self._global_step)
     return True
@@ -396,7 +419,10 @@ class Estimator(object):
         if self._maybe_restore_inflight() and steps is not None:
           limit = self._global_step + steps
       x = input_utils.to_matrix(features, self._feature_keys)
-      self._search.plan.train_step(x, labels)
+      own = self._next_bagging_batches()
+      if own is None:
+        break
+      self._search.plan.train_step(x, labels, own_batches=own or None)
       self._global_step += 1
       self._iteration_step += 1
       if self._max_iteration_steps is not None and self._iteration_step >= self._max_iteration_steps:

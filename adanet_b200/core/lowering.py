@@ -162,4 +162,6 @@ def build_and_lower(builder, feature_placeholders: Dict[str, graph.Tensor], labe
                                                  labels=labels_placeholder, iteration_step=iteration_step,
                                                  summary=summary, previous_ensemble=previous_ensemble)
   spec = lower_subnetwork(builder, sub, variables, train_op, in_dim, head.logits_dimension)
+  # bagging: a builder from an AutoEnsembleSubestimator with its own train_input_fn (autoensemble/common.py:151-180)
+  spec.own_input = getattr(builder, "bagging_train_input_fn", None) is not None
   return spec, sub

@@ -469,3 +469,43 @@ def test_estimator_simple_cnn_matches_oracle_and_resumes(env, tmp_path):
   ev2 = est2.evaluate(_input_fn(xe, ye, key="images"), steps=2)
   assert ev2["loss"] == ev["loss"] and ev2["iteration"] == iters
   assert est2.architecture_string() == est.architecture_string()
+
+
+@pytest.mark.gpu
+def test_autoensemble_bagging_matches_oracle(env):
+  """AutoEnsembleSubestimator(estimator, train_input_fn) (adanet/autoensemble/common.py:63-93,151-180): the bagged
+  DNN trains on its own input_fn, one step before each main step; the linear model on the shared minibatches."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  x, y = _data(orc)
+  xb, yb = orc.make_tabular(B * 5, D, C, seed=777)        # the bag: 5 minibatches of its own
+  cols = [graph.numeric_column("x", D)]
+  steps, lr = 5, 0.05          # exactly the bag's length: a bagging dataset that runs out ends training (common.py:75-78)
+  dims = [D, 32, 16, C]
+  dnn = adanet.estimators.DNNEstimator(cols, [32, 16], train.GradientDescentOptimizer(lr), seed=12)
+  pool = {"linear": adanet.estimators.LinearEstimator(cols, train.GradientDescentOptimizer(lr), seed=11),
+          "dnn": adanet.AutoEnsembleSubestimator(dnn, train_input_fn=_input_fn(xb, yb))}
+  est = adanet.AutoEnsembleEstimator(head=adanet.heads.MultiClassHead(C), candidate_pool=pool, max_iteration_steps=steps,
+                                     max_iterations=2, debug=True)
+  est.train(_input_fn(x, y), max_steps=steps * 2)
+
+  def space(t, frozen):       # dict pools are sorted by name: dnn, linear (common.py:236-243); complexity 0 (:186)
+    ws = [_glorot((dims[i], dims[i + 1]), 12 + i) for i in range(3)]
+    return [orc.SubnetworkSpec("dnn", dims, 0.0, ("sgd", lr), ws=ws, bs=[np.zeros((d_,), np.float32) for d_ in dims[1:]],
+                               own_data=(xb, yb)),
+            orc.SubnetworkSpec("linear", [D, C], 0.0, ("sgd", lr), ws=[_glorot((D, C), 11)], bs=[np.zeros((C,), np.float32)])]
+
+  want, _ = orc.run_adanet(space, x, y, B, steps, 2, orc.EnsemblerSpec(), C)
+  assert len(est._search.reports) == 2
+  for rep, res in zip(est._search.reports, want):
+    assert rep.candidate_names == res.candidate_names and rep.best_index == res.best_index
+    np.testing.assert_allclose(rep.ema_losses, res.ema_losses, atol=1e-5, rtol=0)
+    for name, tr in res.traces.items():
+      for f in ("sub_loss", "adanet_loss"):
+        np.testing.assert_allclose(rep.traces[name][f], tr[f], atol=1e-5, rtol=0)
+  # a bag shorter than the iteration stops training when it runs out
+  pool["dnn"] = adanet.AutoEnsembleSubestimator(dnn, train_input_fn=_input_fn(xb[:B * 3], yb[:B * 3]))
+  est = adanet.AutoEnsembleEstimator(head=adanet.heads.MultiClassHead(C), candidate_pool=pool, max_iteration_steps=steps,
+                                     max_iterations=1)
+  est.train(_input_fn(x, y), max_steps=steps)
+  assert est._global_step == 3

@@ -345,3 +345,48 @@ def test_simple_cnn_parity(built_lib, name):
     assert ws[0].ndim == 4
     for a, b in zip(ws + bs, list(mo.ws) + list(mo.bs)):
       np.testing.assert_allclose(a, b, atol=5e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opt", [("sgd", 0.05), ("adam", 0.003)])
+def test_bagged_subnetworks_parity(built_lib, opt):
+  """Bagging (adanet/autoensemble/common.py:63-93,151-180): candidates 0 and 2 train on minibatches of their own
+  input (one step BEFORE the main pass, :43-56), candidate 1 on the shared minibatch; every ensemble head reads the
+  forwards on the shared minibatch."""
+  from adanet_b200.core import engine as eng
+  from adanet_b200.core import search as srch
+  d, c, B, steps, iters = 100, 10, 256, 15, 3
+  x, y = orc.make_tabular(8192, d, c, seed=51)
+  bags = {0: orc.make_tabular(B * 4, d, c, seed=52), 2: orc.make_tabular(B * 6, d, c, seed=53)}
+  cfgs = [(1, 48), (2, 32), (2, 64)]
+  ens = dict(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+
+  def o_space(t, frozen):
+    specs = pu.make_specs(cfgs, d, c, t, opt)[0]
+    for i, data in bags.items():
+      specs[i].own_data = data
+    return specs
+
+  def e_space(t, frozen):
+    specs = pu.make_specs(cfgs, d, c, t, opt)[1]
+    for i in bags:
+      specs[i].own_input = True
+    return specs
+
+  want, _ = orc.run_adanet(o_space, x, y, B, steps, iters, orc.EnsemblerSpec(**ens), c)
+  s = srch.AdaNetSearch(e_space, eng.EnsemblerPlanSpec(**ens), d, c, B)
+  batches = srch.consecutive_batches(x, y, B)
+  for t in range(iters):
+    plan = s.build_iteration()
+    if t == 0:
+      with pytest.raises(ValueError):      # a bagged subnetwork without its minibatch is an error, not a silent reuse
+        plan.train_step(*next(srch.consecutive_batches(x, y, B)))
+    for step in range(steps):
+      own = {}
+      for i, (xo, yo) in bags.items():
+        o = (step % (xo.shape[0] // B)) * B
+        own[i] = (xo[o:o + B], yo[o:o + B])
+      plan.train_step(*next(batches), own_batches=own)
+    s.finish_iteration()
+  worst = _check(want, s.reports)
+  print("bagging %s worst per-step abs err %.3g" % (opt[0], worst))

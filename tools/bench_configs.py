@@ -66,6 +66,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--rows", type=int, default=0)
   ap.add_argument("--oracle-steps", type=int, default=0)
+  ap.add_argument("--placement", default="balanced", choices=["balanced", "round_robin"])
   a = ap.parse_args()
   import torch
   import torch.distributed as dist
@@ -89,7 +90,7 @@ def main():
       torch.randn((rows, in_dim), device="cuda", generator=g)
   y = torch.randint(0, C, (rows,), device="cuda", generator=g)
   s = srch.AdaNetSearch(lambda t, frozen: mk(t, 1), eng.EnsemblerPlanSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01),
-                        in_dim, C, B, keep_traces=False)
+                        in_dim, C, B, keep_traces=False, placement=a.placement)
   plan = s.build_iteration()
   batches = srch.consecutive_batches(x, y, B)
   for _ in range(a.warmup):
@@ -108,6 +109,11 @@ def main():
     dist.barrier()
   secs = ex.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device=torch.device("cuda", local))
   launches = plan.launches_per_step
+  # end of the iteration: all_gather of the candidates' EMA losses, selection, broadcast of the winner
+  t0 = time.perf_counter()
+  rep = s.finish_iteration()
+  torch.cuda.synchronize()
+  finish_ms = ex.max_over_ranks((time.perf_counter() - t0) * 1e3, device=torch.device("cuda", local))
   if rank == 0:
     specs = mk(0, 1)
     flops = train_flops(specs)
@@ -115,6 +121,7 @@ def main():
            "batch": B, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3,
            "value": B * a.steps / secs, "unit": "examples/s", "train_flops_per_example": flops,
            "useful_tflops": flops * B * a.steps / secs / 1e12, "launches_per_step_rank0": launches,
+           "placement": a.placement, "finish_iteration_ms": finish_ms, "selected": rep.candidate_names[rep.best_index],
            "data": "synthetic, %d rows x %d resident in HBM (> L2)" % (rows, in_dim)}
     if a.oracle_steps:
       # the NumPy oracle on the host cores: same candidates, same batch size, bounded number of steps
