@@ -21,6 +21,8 @@
 // gradient w.r.t. the pooled features already masked by (pooled > 0) (the dX epilogue of the first dense layer
 // applies the sign bits written here).  One thread per (channel, filter) pair holding the nine taps, images looped
 // per CTA, per-CTA partials reduced in fixed order by a second kernel (deterministic).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace adn {
@@ -28,7 +30,29 @@ namespace pl {
 int64_t plane_floats(int64_t rows, int64_t cols);
 }
 
+namespace convtc {
+bool bwd_supported(int h, int w, int cin, int f);
+int bwd(const float* images, const uint32_t* argmax, const float* dpooled, float* partials, int* n_partials, int64_t batch,
+        int h, int w, int cin, int f, cudaStream_t st);
+bool supported(int h, int w, int cin, int f);
+int fwd(const float* images, const float* kernel, const float* bias, float* out_planes, uint32_t* argmax, int64_t batch,
+        int h, int w, int cin, int f, cudaStream_t st);
+}
+
 namespace conv {
+
+// ADN_CONV_PATH=simt forces the exact-fp32 SIMT forward (cross-check); default: tcgen05 implicit GEMM where supported
+static bool use_tc() {      // read per call (host side, cheap): tests switch it at run time
+  const char* e = getenv("ADN_CONV_PATH");
+  return !(e && (e[0] == 's' || e[0] == 'S'));
+}
+
+// The tcgen05 backward (conv_stem_tc.cu) is correct but, with its serial build -> MMA -> drain per warpgroup, slower
+// than the SIMT gather (204 vs 136 us at B=4096, profiles/r1h_conv_tc_*.txt): opt-in with ADN_CONV_BWD_PATH=tcgen05.
+static bool use_tc_bwd() {
+  const char* e = getenv("ADN_CONV_BWD_PATH");
+  return e && (e[0] == 't' || e[0] == 'T');
+}
 
 static constexpr int FWD_THREADS = 256;
 static constexpr int FC = 16;   // filters per accumulator chunk
@@ -174,12 +198,13 @@ conv_stem_bwd_kernel(const float* __restrict__ images, const uint32_t* __restric
   const int PH = H / 2, PW = W / 2, P = PH * PW;
   const int pimg = (H + 2) * (W + 2) * CIN;
   const int prow = (W + 2) * CIN;
-  float* s_img = smem;                                            // padded image
-  float* s_g = s_img + ((pimg + 3) & ~3);                         // [P*F]
-  uint32_t* s_arg = reinterpret_cast<uint32_t*>(s_g + P * F);     // [P*F/16]
-  float* s_red = reinterpret_cast<float*>(s_arg + P * F / 16);    // [G][K*F + F]
+  // two staging sets {padded image, g [P*F], arg-max words [P*F/16]}: the next image is fetched under this one
+  const int pimg4 = (pimg + 3) & ~3;
+  const int set_floats = pimg4 + P * F + ((P * F / 16 + 3) & ~3);     // 16-byte aligned sets
+  float* s_set0 = smem;
+  float* s_red = smem + 2 * set_floats;                           // [G][K*F + F]
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < pimg; i += nt) s_img[i] = 0.f;
+  for (int i = tid; i < pimg; i += nt) { s_set0[i] = 0.f; s_set0[set_floats + i] = 0.f; }
   const int f = tid % F;
   const int c = (tid / F) % CIN;
   const int grp = tid / (F * CIN);
@@ -191,14 +216,26 @@ conv_stem_bwd_kernel(const float* __restrict__ images, const uint32_t* __restric
   float accb = 0.f;
   const int64_t img_elems = (int64_t)H * W * CIN;
   const int64_t cols = (int64_t)P * F;
+  auto stage = [&](float* set, int64_t bb) {
+    stage_image<CIN>(set, images + bb * img_elems, H, W, tid, nt);
+    float* sg = set + pimg4;
+    uint32_t* sa = reinterpret_cast<uint32_t*>(sg + P * F);
+    for (int i = tid; i < (int)(cols / 4); i += nt) cp_async16(sg + 4 * i, dpooled + bb * cols + 4 * i);
+    for (int i = tid; i < (int)(cols / 16); i += nt) cp_async4(sa + i, argmax + bb * (cols / 16) + i);
+  };
   __syncthreads();
-  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-    stage_image<CIN>(s_img, images + b * img_elems, H, W, tid, nt);
-    for (int i = tid; i < (int)(cols / 4); i += nt) cp_async16(s_g + 4 * i, dpooled + b * cols + 4 * i);
-    for (int i = tid; i < (int)(cols / 16); i += nt) cp_async4(s_arg + i, argmax + b * (cols / 16) + i);
+  int buf = 0;
+  if ((int64_t)blockIdx.x < B) stage(s_set0, blockIdx.x);
+  cp_async_commit();
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
+    const int64_t nb = b + gridDim.x;
+    if (nb < B) stage(s_set0 + (buf ^ 1) * set_floats, nb);
     cp_async_commit();
-    cp_async_wait<0>();
+    cp_async_wait<1>();
     __syncthreads();
+    const float* s_img = s_set0 + buf * set_floats;
+    const float* s_g = s_img + pimg4;
+    const uint32_t* s_arg = reinterpret_cast<const uint32_t*>(s_g + P * F);
     // groups stride the pooled pixels of a row; tap addresses are three row pointers + compile-time offsets
     for (int py = 0; py < PH; ++py) {
       const float* grow = s_g + (py * PW) * F + f;
@@ -281,6 +318,8 @@ extern "C" int adn_conv_stem_fwd(const float* images, const float* kernel, const
                                  void* stream) {
   if (!images || !kernel || !bias || !out_planes || !argmax) return fail(ADN_ERR_INVALID, "adn_conv_stem_fwd: null pointer");
   if (int rc = conv::check_shape("adn_conv_stem_fwd", batch, height, width, channels, filters)) return rc;
+  if (conv::use_tc() && convtc::supported(height, width, channels, filters))
+    return convtc::fwd(images, kernel, bias, out_planes, argmax, batch, height, width, channels, filters, as_stream(stream));
   const int64_t cols = (int64_t)(height / 2) * (width / 2) * filters;
   const int64_t pf = pl::plane_floats(batch, cols);
   float* hi = out_planes;
@@ -309,6 +348,17 @@ extern "C" int adn_conv_stem_bwd(const float* images, const uint32_t* argmax, co
   if (!workspace || workspace_bytes < need)
     return fail(ADN_ERR_WORKSPACE, "adn_conv_stem_bwd: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
   const int kf = 9 * channels * filters;
+  if (conv::use_tc_bwd() && convtc::bwd_supported(height, width, channels, filters)) {
+    int n_part = 0;
+    if (int rc = convtc::bwd(images, argmax, dpooled, static_cast<float*>(workspace), &n_part, batch, height, width, channels,
+                             filters, as_stream(stream)))
+      return rc;
+    const int n_out = kf + filters;
+    conv::conv_stem_reduce_kernel<<<(n_out + 255) / 256, 256, 0, as_stream(stream)>>>(static_cast<float*>(workspace), n_part,
+                                                                                     n_out, kf, dkernel, dbias);
+    ADN_CHECK_LAUNCH("conv_stem_reduce");
+    return ADN_OK;
+  }
   // G thread groups of channels*filters threads share the pooled pixels of an image (even, so threads % 32 == 0)
   int groups = (384 / (channels * filters)) & ~1;
   groups = groups < 2 ? 2 : (groups > 16 ? 16 : groups);
@@ -316,7 +366,7 @@ extern "C" int adn_conv_stem_bwd(const float* images, const uint32_t* argmax, co
   const int grid = conv::bwd_ctas(batch);
   const int pimg = (height + 2) * (width + 2) * channels;
   const int64_t cols = (int64_t)(height / 2) * (width / 2) * filters;
-  const size_t smem = ((size_t)((pimg + 3) & ~3) + cols + cols / 16 + (size_t)groups * (kf + filters)) * sizeof(float);
+  const size_t smem = (2 * ((size_t)((pimg + 3) & ~3) + cols + ((cols / 16 + 3) & ~(int64_t)3)) + (size_t)groups * (kf + filters)) * sizeof(float);
   if (smem > 200 * 1024) return fail(ADN_ERR_UNSUPPORTED, "adn_conv_stem_bwd: %zu bytes of staging do not fit", smem);
   float* partials = static_cast<float*>(workspace);
   auto launch = [&](auto kern) -> int {

@@ -253,13 +253,17 @@ def test_record_and_counter(gpu):
   np.testing.assert_allclose(trace.cpu().numpy()[:, 0], [4, 5, 2, 3])
 
 
+@pytest.mark.parametrize("conv_path", ["tcgen05", "simt"])
 @pytest.mark.parametrize("B,H,W,CIN,F", [(64, 32, 32, 3, 16), (5, 8, 8, 3, 16), (33, 28, 28, 1, 16), (16, 10, 10, 3, 32),
-                                         (700, 32, 32, 3, 16), (3, 6, 4, 1, 48)])
-def test_conv_stem_fwd_bwd(gpu, B, H, W, CIN, F):
+                                         (700, 32, 32, 3, 16), (3, 6, 4, 1, 48), (40, 28, 28, 1, 32), (9, 36, 20, 3, 16)])
+def test_conv_stem_fwd_bwd(gpu, monkeypatch, conv_path, B, H, W, CIN, F):
   """SimpleCNN stem (customizing_adanet.ipynb SimpleCNNBuilder): conv3x3 same + ReLU + maxpool 2x2 + flatten,
-  forward into split planes and the kernel / bias gradients, vs the oracle."""
+  forward into split planes and the kernel / bias gradients, vs the oracle; the forward on both of its paths
+  (tcgen05 implicit GEMM over pooled pixels, 3xTF32; exact-fp32 SIMT, which also serves shapes the former skips)."""
   import torch
   from adanet_b200 import _lib
+  monkeypatch.setenv("ADN_CONV_PATH", conv_path)
+  monkeypatch.setenv("ADN_CONV_BWD_PATH", conv_path)      # the backward's tcgen05 variant is opt-in
   rng = np.random.default_rng(B * 7 + H + F)
   x = rng.uniform(0, 1, (B, H, W, CIN)).astype(np.float32)
   k = (rng.standard_normal((3, 3, CIN, F)) * np.sqrt(2.0 / (9 * CIN))).astype(np.float32)   # he_normal scale
