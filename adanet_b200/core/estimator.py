@@ -47,6 +47,33 @@ class RunConfig:
     self.is_chief = is_chief if is_chief is not None else (self.global_id_in_cluster == 0)
 
 
+class _Lookahead:
+  """Iterator with a one-item peek (the item is handed out by the next `__next__`)."""
+
+  _EMPTY = object()
+
+  def __init__(self, iterable):
+    self._it = iter(iterable)
+    self._head = self._EMPTY
+
+  def __iter__(self):
+    return self
+
+  def __next__(self):
+    if self._head is not self._EMPTY:
+      item, self._head = self._head, self._EMPTY
+      return item
+    return next(self._it)
+
+  def peek(self):
+    if self._head is self._EMPTY:
+      try:
+        self._head = next(self._it)
+      except StopIteration:
+        return None
+    return self._head
+
+
 class _RestoredBuilder:
   """Stands in for the builder of a member restored from a checkpoint (strategies only count / name them)."""
 
@@ -397,7 +424,10 @@ class Estimator(object):
         logging.info("Skipping training since max_steps has already saved.")
         return self
     done_iterations = lambda: self._search.iteration if self._search else 0
-    for features, labels in input_utils.iterate_input_fn(input_fn):
+    batches = _Lookahead(input_utils.iterate_input_fn(input_fn))
+    staged = None        # (item, plan) whose host->device copy was started while the previous step ran
+    for item in batches:
+      features, labels = item
       if self._max_iterations and done_iterations() >= self._max_iterations:
         break
       if limit is not None and self._global_step >= limit:
@@ -422,10 +452,23 @@ class Estimator(object):
       own = self._next_bagging_batches()
       if own is None:
         break
-      self._search.plan.train_step(x, labels, own_batches=own or None)
+      plan = self._search.plan
+      if staged is not None and staged[0] is item and staged[1] is plan:
+        plan.train_step(own_batches=own or None)          # the minibatch is already on the device
+      else:
+        plan.train_step(x, labels, own_batches=own or None)
+      staged = None
       self._global_step += 1
       self._iteration_step += 1
-      if self._max_iteration_steps is not None and self._iteration_step >= self._max_iteration_steps:
+      ends_iteration = self._max_iteration_steps is not None and self._iteration_step >= self._max_iteration_steps
+      if not ends_iteration and (limit is None or self._global_step < limit):
+        # the step above only ENQUEUED work: start the next minibatch's host->device copy on the copy stream now, so
+        # it runs under this step's kernels (pageable NumPy input blocks the host for the copy, not the GPU)
+        nxt = batches.peek()
+        if nxt is not None and input_utils.batch_size_of(nxt[0]) == self._batch_size:
+          plan.stage_batch(input_utils.to_matrix(nxt[0], self._feature_keys), nxt[1])
+          staged = (nxt, plan)
+      if ends_iteration:
         self._bookkeeping()
       else:
         every = getattr(self._config, "save_checkpoints_steps", None)
