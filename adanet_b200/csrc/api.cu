@@ -9,7 +9,8 @@
 #include "planes.cuh"
 
 namespace adn {
-namespace conv { int64_t bwd_workspace_bytes(int64_t batch, int cin, int f); }
+namespace conv { int64_t bwd_workspace_bytes(int64_t batch, int cin, int f); int init(); }
+namespace convtc { int init(); }
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
@@ -66,6 +67,10 @@ extern "C" int adn_init(void) {
   int rc = heads_init();
   if (rc) return rc;
   rc = pl::init();
+  if (rc) return rc;
+  rc = conv::init();
+  if (rc) return rc;
+  rc = convtc::init();
   if (rc) return rc;
   (void)sm_count();
   done.store(1);

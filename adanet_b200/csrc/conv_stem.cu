@@ -295,6 +295,22 @@ conv_stem_reduce_kernel(const float* __restrict__ partials, int n_part, int n_ou
   }
 }
 
+static constexpr size_t kMaxSmem = 200 * 1024;
+
+// Dynamic shared-memory limits are raised ONCE here (adn_init): cudaFuncSetAttribute inside a stream capture can
+// invalidate the capture (first use of a larger size while the engine records its CUDA graph).
+int init() {
+#define ADN_CONV_ATTR(K) ADN_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem))
+  ADN_CONV_ATTR(conv_stem_fwd_kernel<1>);
+  ADN_CONV_ATTR(conv_stem_fwd_kernel<3>);
+  ADN_CONV_ATTR((conv_stem_bwd_kernel<1, 16>)); ADN_CONV_ATTR((conv_stem_bwd_kernel<3, 16>));
+  ADN_CONV_ATTR((conv_stem_bwd_kernel<1, 32>)); ADN_CONV_ATTR((conv_stem_bwd_kernel<3, 32>));
+  ADN_CONV_ATTR((conv_stem_bwd_kernel<1, 48>)); ADN_CONV_ATTR((conv_stem_bwd_kernel<3, 48>));
+  ADN_CONV_ATTR((conv_stem_bwd_kernel<1, 64>)); ADN_CONV_ATTR((conv_stem_bwd_kernel<3, 64>));
+#undef ADN_CONV_ATTR
+  return ADN_OK;
+}
+
 static int bwd_ctas(int64_t batch) {
   const int64_t cap = (int64_t)sm_count() * 4;
   return (int)(batch < cap ? batch : cap);
@@ -336,8 +352,8 @@ extern "C" int adn_conv_stem_fwd(const float* images, const float* kernel, const
   const size_t smem = (size_t)(9 * channels * filters + filters + 2 * pimg) * sizeof(float);
   const int64_t cap = (int64_t)sm_count() * 2;
   const int grid = (int)(batch < cap ? batch : cap);
+  if (smem > conv::kMaxSmem) return fail(ADN_ERR_UNSUPPORTED, "adn_conv_stem_fwd: %zu bytes of staging do not fit", smem);
   auto launch = [&](auto kern) -> int {
-    ADN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, conv::FWD_THREADS, smem, as_stream(stream)>>>(images, kernel, bias, hi, lo, bits16, argmax, batch, height,
                                                              width, filters);
     ADN_CHECK_LAUNCH("conv_stem_fwd");
@@ -374,10 +390,9 @@ extern "C" int adn_conv_stem_bwd(const float* images, const uint32_t* argmax, co
   const int pimg = (height + 2) * (width + 2) * channels;
   const int64_t cols = (int64_t)(height / 2) * (width / 2) * filters;
   const size_t smem = (2 * ((size_t)((pimg + 3) & ~3) + cols + ((cols / 16 + 3) & ~(int64_t)3)) + (size_t)groups * (kf + filters)) * sizeof(float);
-  if (smem > 200 * 1024) return fail(ADN_ERR_UNSUPPORTED, "adn_conv_stem_bwd: %zu bytes of staging do not fit", smem);
+  if (smem > conv::kMaxSmem) return fail(ADN_ERR_UNSUPPORTED, "adn_conv_stem_bwd: %zu bytes of staging do not fit", smem);
   float* partials = static_cast<float*>(workspace);
   auto launch = [&](auto kern) -> int {
-    ADN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, as_stream(stream)>>>(images, argmax, dpooled, partials, batch, height, width, groups);
     ADN_CHECK_LAUNCH("conv_stem_bwd");
     return ADN_OK;

@@ -615,12 +615,10 @@ int bwd(const float* images, const uint32_t* argmax, const float* dpooled, float
   if (cin == 3) {
     const size_t smem = bwd_smem_bytes<3, 16>(h, w);
     auto kern = conv_stem_tc_bwd_kernel<3, 16>;
-    ADN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, THREADS, smem, st>>>(images, argmax, dpooled, partials, batch, h, w);
   } else {
     const size_t smem = bwd_smem_bytes<1, 16>(h, w);
     auto kern = conv_stem_tc_bwd_kernel<1, 16>;
-    ADN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, THREADS, smem, st>>>(images, argmax, dpooled, partials, batch, h, w);
   }
   ADN_CHECK_LAUNCH("conv_stem_tc_bwd");
@@ -639,11 +637,20 @@ static int launch(const float* images, const float* kernel, const float* bias, f
                   uint32_t* argmax, int64_t batch, int h, int w, cudaStream_t st) {
   const size_t smem = smem_bytes<CIN, F>(h, w);
   auto kern = conv_stem_tc_fwd_kernel<CIN, F>;
-  ADN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t cap = sm_count();
   const int grid = (int)(batch < cap ? batch : cap);
   kern<<<grid, FWD_THREADS, smem, st>>>(images, kernel, bias, hi, lo, bits16, argmax, batch, h, w);
   ADN_CHECK_LAUNCH("conv_stem_tc_fwd");
+  return ADN_OK;
+}
+
+// raised once from adn_init (never inside a stream capture, see conv::init)
+int init() {
+#define ADN_CONVTC_ATTR(K) ADN_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+  ADN_CONVTC_ATTR((conv_stem_tc_fwd_kernel<1, 16>)); ADN_CONVTC_ATTR((conv_stem_tc_fwd_kernel<3, 16>));
+  ADN_CONVTC_ATTR((conv_stem_tc_fwd_kernel<1, 32>)); ADN_CONVTC_ATTR((conv_stem_tc_fwd_kernel<3, 32>));
+  ADN_CONVTC_ATTR((conv_stem_tc_bwd_kernel<1, 16>)); ADN_CONVTC_ATTR((conv_stem_tc_bwd_kernel<3, 16>));
+#undef ADN_CONVTC_ATTR
   return ADN_OK;
 }
 

@@ -264,19 +264,31 @@ def test_resume_from_model_dir_matches_uninterrupted_run(env, tmp_path):
   assert c._global_step == 3 * steps + 3
 
 
-def test_resume_inside_an_iteration(env, tmp_path):
+@pytest.mark.parametrize("family", ["dnn", "cnn"])
+def test_resume_inside_an_iteration(env, tmp_path, family):
   """RunConfig.save_checkpoints_steps persists the in-flight iteration (weights, optimizer slots, mixture
   weights, EMA, step counters; adanet/core/iteration.py:40-118,172-183): a run killed inside iteration 1
-  resumes from the last in-flight checkpoint and ends bit-identical to the uninterrupted run."""
+  resumes from the last in-flight checkpoint and ends bit-identical to the uninterrupted run.  The `cnn` family
+  adds the conv stem's weights and the cosine-decay step counter of its Momentum optimizer to that state."""
   torch, adanet, orc = env
   from adanet_b200 import graph, train
-  from adanet_b200.examples import simple_dnn
-  x, y = _data(orc)
+  from adanet_b200.examples import simple_cnn, simple_dnn
   steps = 8
+  if family == "dnn":
+    x, y = _data(orc)
+    key = "x"
+  else:
+    rng = np.random.default_rng(3234)
+    x = (rng.uniform(0, 1, (B * 24, 12, 12, 3)) * 2 - 1).astype(np.float32)
+    y = rng.integers(0, C, x.shape[0])
+    key = "images"
 
   def make(model_dir):
-    gen = _modern(simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
-                                       optimizer=train.MomentumOptimizer(0.02, 0.9), layer_size=16, seed=SEED))
+    if family == "dnn":
+      gen = _modern(simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)],
+                                         optimizer=train.MomentumOptimizer(0.02, 0.9), layer_size=16, seed=SEED))
+    else:
+      gen = _modern(simple_cnn.SimpleCNNGenerator(0.004, steps, seed=3, num_candidates=2))
     return adanet.Estimator(
         head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=steps,
         ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.AdamOptimizer(0.01),
@@ -287,7 +299,7 @@ def test_resume_inside_an_iteration(env, tmp_path):
   def input_from(start):
     def fn():
       for i in range(start * B, x.shape[0] - B + 1, B):
-        yield {"x": x[i:i + B]}, y[i:i + B]
+        yield {key: x[i:i + B]}, y[i:i + B]
     return fn
 
   full = make(str(tmp_path / "full"))
