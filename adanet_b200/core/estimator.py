@@ -47,6 +47,13 @@ class RunConfig:
     self.is_chief = is_chief if is_chief is not None else (self.global_id_in_cluster == 0)
 
 
+class _RunValues:
+  """tf.estimator.SessionRunValues stand-in: `.results` holds what the step produced."""
+
+  def __init__(self, results):
+    self.results = results
+
+
 class _Lookahead:
   """Iterator with a one-item peek (the item is handed out by the next `__next__`)."""
 
@@ -408,7 +415,24 @@ class Estimator(object):
     """Trains for `steps` more steps or until `max_steps` global steps
     (adanet/core/estimator.py:809-999).  An AdaNet iteration ends after
     `max_iteration_steps` steps (or when the input is exhausted); the best
-    candidate is then selected and frozen, and the next iteration starts."""
+    candidate is then selected and frozen, and the next iteration starts.
+
+    `hooks`: objects with the SessionRunHook method `after_run(run_context, run_values)`; after every step it is
+    called with `run_values.results = {"global_step": int, "losses": float32[n_candidates, 4]}` (sub_loss, ens_loss,
+    adanet_loss, ema of this rank's candidate ensembles, read back from the device -- which synchronises on the
+    step, so pass hooks only when per-step values are wanted; `begin()` / `end(session)` are called if present."""
+    hooks = list(hooks or [])
+    for h in hooks:
+      if hasattr(h, "begin"):
+        h.begin()
+    try:
+      return self._train(input_fn, hooks, steps, max_steps)
+    finally:
+      for h in hooks:
+        if hasattr(h, "end"):
+          h.end(None)
+
+  def _train(self, input_fn, hooks, steps, max_steps):
     if steps is not None and max_steps is not None:
       raise ValueError("Can not provide both steps and max_steps.")
     if steps is not None and steps <= 0:
@@ -468,6 +492,10 @@ class Estimator(object):
         if nxt is not None and input_utils.batch_size_of(nxt[0]) == self._batch_size:
           plan.stage_batch(input_utils.to_matrix(nxt[0], self._feature_keys), nxt[1])
           staged = (nxt, plan)
+      if hooks:      # after the next copy was started: reading the losses back waits for the step to finish
+        values = _RunValues({"global_step": self._global_step, "losses": plan.last_losses()})
+        for h in hooks:
+          h.after_run(None, values)
       if ends_iteration:
         self._bookkeeping()
       else:

@@ -13,8 +13,8 @@ the only exchange is the end-of-iteration loss all_gather, outside the step).
 
 Prints ONE JSON line on rank 0.  `value` = B*K / device time (CUDA events, max
 over ranks) with the dataset resident in HBM; `e2e` = same metric through
-AdaNetSearch.train_iteration with HOST (pinned) batches, H2D of every batch and
-a D2H read of every step's losses inside the timed region.
+the public adanet_b200.Estimator.train call with HOST (pinned) batches, H2D of every
+batch and a D2H read of every step's losses (an `after_run` hook) inside the timed region.
 """
 
 import argparse
@@ -310,36 +310,98 @@ def run_ours(args):
       dist.destroy_process_group()
     return
 
-  # ---------------- e2e: host batches through the public search API ----------------
+  # ---------------- e2e: host batches through the PUBLIC API (adanet.Estimator.train) ----------------
   e2e_steps = min(args.steps, 100)
   n_host = BATCH * 4
   x_host = torch.as_tensor(x_np[:n_host]).pin_memory()
   y_host = torch.as_tensor(y_np[:n_host]).pin_memory()
-  s2 = srch.AdaNetSearch(space, ens, IN_DIM, CLASSES, BATCH, device=dev, keep_traces=False)
-  plan2 = s2.build_iteration()
-  hb = srch.consecutive_batches(x_host, y_host, BATCH)
-  for _ in range(max(3, args.warmup)):
-    plan2.train_step(*next(hb))
-    plan2.last_losses()
-  torch.cuda.synchronize()
-  if world > 1:
-    dist.barrier()
-  host_losses = None
+  warm = max(3, args.warmup)
 
-  def read_losses(plan):
-    nonlocal host_losses
-    host_losses = plan.last_losses()    # D2H read of this step's losses (synchronises on the step)
+  def host_batches(n):
+    def fn():
+      for i in range(n):
+        o = (i % 4) * BATCH
+        yield {"x": x_host[o:o + BATCH]}, y_host[o:o + BATCH]
+    return fn
 
-  # the public search API with HOST batches: every step's batch goes host->device (pinned, on the copy stream,
-  # under the previous step's kernels) and every step's losses come back device->host
-  e2e_secs = s2.train_iteration(hb, e2e_steps, on_step=read_losses)
-  torch.cuda.synchronize()
+  e2e_api, e2e_note, e2e_secs, d2h = "adanet_b200.Estimator.train", None, None, 0
+  try:
+    import adanet_b200 as adanet
+    from adanet_b200 import graph, train
+
+    class _WidthBuilder(adanet.subnetwork.Builder):
+      """100 -> H -> H -> 10 with the same injected weights as the device-resident run."""
+
+      def __init__(self, spec):
+        self._spec = spec
+
+      name = property(lambda self: self._spec.name)
+
+      def build_subnetwork(self, features, logits_dimension, training, iteration_step, summary, previous_ensemble=None):
+        h = graph.input_layer(features, [graph.numeric_column("x", IN_DIM)])
+        n = len(self._spec.ws)
+        for i, (w, b) in enumerate(zip(self._spec.ws, self._spec.bs)):
+          h = graph.dense(h, w.shape[1], activation=graph.relu if i < n - 1 else None,
+                          kernel_initializer=graph.constant_initializer(w), bias_initializer=graph.constant_initializer(b))
+          if i == n - 2:
+            last = h
+        return adanet.Subnetwork(last_layer=last, logits=h, complexity=self._spec.complexity)
+
+      def build_subnetwork_train_op(self, subnetwork, loss, var_list, labels, iteration_step, summary, previous_ensemble):
+        return train.GradientDescentOptimizer(0.05).minimize(loss=loss, var_list=var_list)
+
+    class _Losses:
+      last = None
+
+      def after_run(self, run_context, run_values):      # D2H read of every step's losses
+        self.last = run_values.results["losses"]
+
+    est = adanet.Estimator(
+        head=adanet.heads.MultiClassHead(CLASSES),
+        subnetwork_generator=adanet.subnetwork.SimpleGenerator([_WidthBuilder(sp) for sp in space(0, [])]),
+        max_iteration_steps=10 ** 9, max_iterations=1,
+        ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(0.01),
+                                                                   adanet_lambda=0.01, adanet_beta=0.001)])
+    hook = _Losses()
+    est.train(host_batches(warm), steps=warm, hooks=[hook])          # builds the plan, captures the graph
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    # every step: host->device copy of its (pinned) minibatch, started under the previous step's kernels, and a
+    # device->host read of its losses through the hook
+    est.train(host_batches(e2e_steps), steps=e2e_steps, hooks=[hook])
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_secs = e0.elapsed_time(e1) * 1e-3
+    d2h = int(hook.last.nbytes)
+  except Exception as exc:      # measured below through the engine-level search API instead; the reason is reported
+    e2e_api, e2e_note = "adanet_b200.core.search.AdaNetSearch.train_iteration", "Estimator path failed: %r" % (exc,)
+    s2 = srch.AdaNetSearch(space, ens, IN_DIM, CLASSES, BATCH, device=dev, keep_traces=False)
+    plan2 = s2.build_iteration()
+    hb = srch.consecutive_batches(x_host, y_host, BATCH)
+    for _ in range(warm):
+      plan2.train_step(*next(hb))
+      plan2.last_losses()
+    torch.cuda.synchronize()
+    host_losses = None
+
+    def read_losses(plan):
+      nonlocal host_losses
+      host_losses = plan.last_losses()
+
+    e2e_secs = s2.train_iteration(hb, e2e_steps, on_step=read_losses)
+    torch.cuda.synchronize()
+    d2h = int(host_losses.nbytes)
   if world > 1:
     dist.barrier()
   e2e_secs = ex.max_over_ranks(e2e_secs, device=dev)
   e2e = {"value": BATCH * e2e_steps / e2e_secs, "unit": "examples/s",
-         "h2d_bytes_per_step": BATCH * IN_DIM * 4 + BATCH * 8,
-         "d2h_bytes_per_step": int(host_losses.nbytes), "steps": e2e_steps}
+         "h2d_bytes_per_step": BATCH * IN_DIM * 4 + BATCH * 8, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+         "api": e2e_api}
+  if e2e_note:
+    e2e["note"] = e2e_note
 
   if rank != 0:
     if world > 1:
