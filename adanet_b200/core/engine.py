@@ -788,6 +788,7 @@ class IterationPlan:
     self.multi_stream = multi_stream and len(self.candidates) > 1
     self.streams = [torch.cuda.Stream(device=self.device) for _ in self.candidates] if self.multi_stream else []
     self._graph = None
+    self._warmed = False      # set by the first (eager) step
     self._stage = None
     self.launches_per_step = None
 
@@ -951,17 +952,28 @@ class IterationPlan:
       self.load_batch(x, y)
     elif self._stage is not None and self._stage.get("pending"):
       self._consume_staged()
-    if not self.use_cuda_graph:
+    if not self.use_cuda_graph or not self._warmed:
+      # the plan's FIRST step always runs eagerly: every kernel variant of the step is launched (and lazily loaded by
+      # the driver) once outside any stream capture -- a first launch inside the capture can invalidate it
       before = _lib.launch_count()
       self._enqueue()
       self.launches_per_step = _lib.launch_count() - before
+      self._warmed = True
     else:
       if self._graph is None:
+        import gc
         before = _lib.launch_count()
         g = torch.cuda.CUDAGraph()
-        # graph capture records the launches without running them: no state changes
-        with torch.cuda.graph(g):
-          self._enqueue()
+        # graph capture records the launches without running them: no state changes.  The collector stays off while
+        # the stream is capturing (destroying another plan's graph / events in the middle of it is not capture-safe).
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+          with torch.cuda.graph(g):
+            self._enqueue()
+        finally:
+          if gc_was_on:
+            gc.enable()
         self.launches_per_step = _lib.launch_count() - before
         self._graph = g
       self._graph.replay()
