@@ -21,15 +21,18 @@ HEAD_SOFTMAX_XENT, HEAD_MSE, HEAD_SIGMOID_XENT = 0, 1, 2
 MIX_SCALAR, MIX_VECTOR, MIX_MATRIX = 0, 1, 2
 OPT_SGD, OPT_MOMENTUM, OPT_RMSPROP, OPT_ADAM, OPT_MOMENTUM_COSINE = 0, 1, 2, 3, 4
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+PLANES_TF32, PLANES_F16 = 0, 1
 (Q_VERSION, Q_DENSE_BWD_WS, Q_HEAD_WS, Q_DENSE_FWD_PATH, Q_SM_COUNT, Q_LAUNCH_COUNT, Q_DENSE_BWD_PATH,
- Q_DENSE_FWD_WS, Q_PLANES_BYTES, Q_DENSE_BWD_P_WS, Q_COLSUM_WS, Q_CONV_STEM_BWD_WS) = range(12)
+ Q_DENSE_FWD_WS, Q_PLANES_BYTES, Q_DENSE_BWD_P_WS, Q_COLSUM_WS, Q_CONV_STEM_BWD_WS, Q_PLANE_FORMAT,
+ Q_TMA_MAP_CACHE_HITS, Q_TMA_MAP_CACHE_MISSES) = range(15)
 
 EXPORTS = (
     "adn_last_error", "adn_init", "adn_query", "adn_set_dense_path", "adn_dense_fwd", "adn_dense_bwd", "adn_head_loss",
     "adn_ensemble_head", "adn_opt_step", "adn_l1_norm", "adn_ema_update", "adn_record_scalars",
     "adn_counter_add", "adn_planes_split", "adn_planes_merge", "adn_dense_fwd_p", "adn_dense_bwd_p", "adn_colsum",
     "adn_opt_step_p", "adn_head_loss_p", "adn_dense_fwd_p_group", "adn_dense_bwd_p_group",
-    "adn_l1_grad_add", "adn_conv_stem_fwd", "adn_conv_stem_bwd",
+    "adn_l1_grad_add", "adn_conv_stem_fwd", "adn_conv_stem_bwd", "adn_set_plane_format", "adn_plane_overflow",
+    "adn_planes_split_scaled",
 )
 
 
@@ -43,7 +46,7 @@ class BwdOp(ctypes.Structure):
   """adn_bwd_op (include/adanet_b200.h)"""
   _fields_ = [("xp", c_void_p), ("wp", c_void_p), ("dzp", c_void_p), ("dxp", c_void_p), ("dx", c_void_p),
               ("dx_colsum", c_void_p), ("dw", c_void_p), ("in_", c_int64), ("out", c_int64),
-              ("x_relu_mask", ctypes.c_int32), ("reserved", ctypes.c_int32), ("workspace", c_void_p),
+              ("x_relu_mask", ctypes.c_int32), ("dz_log2_scale", ctypes.c_int32), ("workspace", c_void_p),
               ("workspace_bytes", c_int64)]
 
 
@@ -82,11 +85,14 @@ def load():
   lib.adn_record_scalars.argtypes = [POINTER(p), c_int, p, i64, p, i64, p]
   lib.adn_counter_add.argtypes = [p, i64, p]
   lib.adn_planes_split.argtypes = [p, i64, i64, p, p]
+  lib.adn_planes_split_scaled.argtypes = [p, i64, i64, p, c_int, p]
   lib.adn_planes_merge.argtypes = [p, i64, i64, p, p]
+  lib.adn_set_plane_format.argtypes = [c_int]
+  lib.adn_plane_overflow.argtypes = [POINTER(c_int), c_int, p]
   lib.adn_dense_fwd_p.argtypes = [p, p, p, p, p, i64, i64, i64, c_int, p]
-  lib.adn_dense_bwd_p.argtypes = [p, p, p, p, p, p, p, i64, i64, i64, c_int, p, i64, p]
+  lib.adn_dense_bwd_p.argtypes = [p, p, p, p, p, p, p, i64, i64, i64, c_int, c_int, p, i64, p]
   lib.adn_colsum.argtypes = [p, i64, i64, p, p, i64, p]
-  lib.adn_head_loss_p.argtypes = [c_int, p, p, p, p, p, p, p, i64, i64, p, i64, p]
+  lib.adn_head_loss_p.argtypes = [c_int, p, p, p, p, p, p, p, c_int, i64, i64, p, i64, p]
   lib.adn_l1_grad_add.argtypes = [p, p, i64, f32, p]
   lib.adn_conv_stem_fwd.argtypes = [p, p, p, p, p, i64, c_int, c_int, c_int, c_int, p]
   lib.adn_conv_stem_bwd.argtypes = [p, p, p, p, p, i64, c_int, c_int, c_int, c_int, p, i64, p]
@@ -119,6 +125,22 @@ def launch_count() -> int:
 
 def set_dense_path(path: int):
   check(load().adn_set_dense_path(path), "adn_set_dense_path")
+
+
+def plane_format() -> int:
+  """Current split-plane format of the *_p entry points (PLANES_F16 unless ADN_PLANES=tf32 / set_plane_format)."""
+  return query(Q_PLANE_FORMAT)
+
+
+def set_plane_format(fmt: int):
+  check(load().adn_set_plane_format(fmt), "adn_set_plane_format")
+
+
+def plane_overflow(stream_ptr: int = 0, reset: bool = True) -> bool:
+  """Reads (and by default clears) the sticky "a finite value did not fit fp16 planes" flag; synchronises the stream."""
+  out = c_int(0)
+  check(load().adn_plane_overflow(ctypes.byref(out), 1 if reset else 0, stream_ptr), "adn_plane_overflow")
+  return bool(out.value)
 
 
 def ptr_array(ptrs):

@@ -47,6 +47,15 @@ _OPT_KIND = {"sgd": _lib.OPT_SGD, "momentum": _lib.OPT_MOMENTUM, "rmsprop": _lib
 _OPT_DEFAULTS = {"sgd": (), "momentum": (), "rmsprop": (0.9, 0.0, 1e-10), "adam": (0.9, 0.999, 1e-8),
                  "momentum_cosine": (0.0,)}
 TRACE_FIELDS = ("sub_loss", "ens_loss", "adanet_loss", "ema")
+EVAL_METRICS = ("adanet_loss", "loss", "average_loss", "accuracy")
+
+
+def accuracy_of(logits: torch.Tensor, labels: torch.Tensor) -> float:
+  """Fraction of examples whose predicted class equals the label: arg-max for [B, C>1] logits against int labels,
+  logit > 0 for a single-logit (sigmoid) head against {0,1} labels.  Evaluation bookkeeping, not on the step path."""
+  if logits.shape[1] > 1:
+    return float((logits.argmax(dim=1) == labels.reshape(-1)).float().mean().item())
+  return float(((logits.reshape(-1) > 0) == (labels.reshape(-1) > 0.5)).float().mean().item())
 
 
 def _stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> int:
@@ -68,8 +77,15 @@ def planes_enabled() -> bool:
 
 
 def new_planes(rows: int, cols: int, device) -> torch.Tensor:
-  """Zero-initialised split-plane tensor (include/adanet_b200.h: the K padding must stay zero)."""
+  """Zero-initialised split-plane tensor in the CURRENT plane format (include/adanet_b200.h: the K padding must
+  stay zero)."""
   return torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, rows, cols) // 4,), dtype=torch.float32, device=device)
+
+
+def grad_log2_scale(batch: int) -> int:
+  """Power-of-two scale of every gradient plane tensor (csrc/plane_fmt.cuh): mean-reduced losses give dlogits of
+  O(1/batch), below fp16's normal range; 2^ceil(log2 batch) brings them back to O(1).  TF32 planes need none."""
+  return int(math.ceil(math.log2(max(batch, 1)))) if _lib.plane_format() == _lib.PLANES_F16 else 0
 
 
 @dataclass
@@ -96,6 +112,9 @@ class SubnetworkPlanSpec:
   # bagging (adanet/autoensemble/common.py:151-180): the subnetwork trains on minibatches of its OWN input_fn
   # (before the step's main pass, :43-56) and only its forward on the shared minibatch feeds the ensembles
   own_input: bool = False
+  # Subnetwork.last_layer is the logits tensor itself (autoensemble/common.py:115-118) rather than the activation
+  # feeding the logits layer; only MATRIX mixture weights read it
+  last_layer_is_logits: bool = False
 
 
 @dataclass
@@ -111,6 +130,9 @@ class EnsemblerPlanSpec:
   legacy_train_op: bool = False
   warm_start_mixture_weights: bool = False   # weighted.py:270-285,487-516
   kind: str = "complexity_regularized"
+  # custom `mixture_weight_initializer` (weighted.py:360-366,419-428): fn(num_members, last_layer_dim, logits_dim) ->
+  # the initial weight of ONE member (shape [] / [C] / [D_k, C]); None = the reference defaults (1/N, zeros for MATRIX)
+  initial_weight_fn: Optional[object] = None
 
 
 def _opt_hyper(spec: tuple) -> Tuple[int, List[float]]:
@@ -212,6 +234,7 @@ class DenseNet:
       self.stem_arg = torch.zeros((batch * dims[0] // 16,), dtype=torch.int32, device=device)
       ws, bs = ws[1:], bs[1:]
     self.in_dim = int(np.prod(self.image_shape)) if self.stem else self.dims[0]
+    self.fmt = _lib.plane_format()
     assert len(ws) == len(dims) - 1
     self.ws = [torch.as_tensor(np.ascontiguousarray(w, dtype=np.float32)).to(device) for w in ws]
     self.bs = [torch.as_tensor(np.ascontiguousarray(b, dtype=np.float32)).to(device) for b in bs]
@@ -233,6 +256,19 @@ class DenseNet:
       fwd_ws = max(_lib.query(_lib.Q_DENSE_FWD_WS, batch, dims[i], dims[i + 1]) for i in range(n))
       self.fwd_ws_bytes = fwd_ws
       self.fwd_ws = torch.empty((max(fwd_ws, 16),), dtype=torch.uint8, device=device)
+
+  def ensure_format(self):
+    """Re-creates the plane buffers when the process-wide plane format changed since this net was built (the
+    fp16 -> TF32 fallback after an overflow, core/search.py)."""
+    if not self.planes or self.fmt == _lib.plane_format():
+      return
+    self.fmt = _lib.plane_format()
+    n = len(self.ws)
+    self.hp = [new_planes(self.batch, d, self.device) for d in self.dims[1:-1]]
+    self.wps = [new_planes(self.dims[i], self.dims[i + 1], self.device) for i in range(n)]
+    if self.stem:
+      self.stem_out = new_planes(self.batch, self.dims[0], self.device)
+    self.refresh_planes()
 
   def refresh_planes(self):
     """Re-splits every kernel into its planes (after the dense weights were written from outside the engine,
@@ -343,6 +379,7 @@ class EnsembleHead:
     f32 = dict(dtype=torch.float32, device=device)
     self.device = device
     self.planes = planes_enabled()
+    self.dz_log2 = grad_log2_scale(batch)
     self.kind = getattr(ens, "kind", "complexity_regularized")
     self.mix = _MIX_KIND[ens.mixture_weight_type]
     if self.mix == _lib.MIX_MATRIX:
@@ -363,6 +400,16 @@ class EnsembleHead:
     else:
       wshape = (n_members,) if self.mix == _lib.MIX_SCALAR else (n_members, logits_dim)
       self.mix_w = torch.full(wshape, 1.0 / n_members, **f32)
+    if getattr(ens, "initial_weight_fn", None) is not None and self.kind != "mean":
+      sp0 = torch.cuda.current_stream(device).cuda_stream
+      for k, m in enumerate(self.member_nets):
+        w0 = np.asarray(ens.initial_weight_fn(n_members, m.last_layer_dim, logits_dim), dtype=np.float32)
+        if self.mix == _lib.MIX_MATRIX:
+          self.mw[k].copy_(torch.as_tensor(np.ascontiguousarray(w0.reshape(self.mw[k].shape))))
+          _lib.check(lib.adn_planes_split(self.mw[k].data_ptr(), self.mw[k].shape[0], self.mw[k].shape[1],
+                                          self.mwp[k].data_ptr(), sp0), "adn_planes_split")
+        else:
+          self.mix_w[k] = torch.as_tensor(np.ascontiguousarray(w0.reshape(tuple(self.mix_w.shape[1:])))).to(device)
     self.bias = torch.zeros((logits_dim,), **f32)
     if self.kind == "mean":
       # MeanEnsembler (adanet/ensemble/mean.py:92-135): the mean of the NEW subnetworks' logits, previous members
@@ -452,11 +499,12 @@ class EnsembleHead:
         self.head_ws_bytes, sp), "adn_ensemble_head")
     if train_ens and matrix:
       # dW_k = last_layer_k^T @ dLoss/d(ens)  + reg_multiplier * gamma_k * sign(W_k)   (weighted.py:606-617)
-      _lib.check(lib.adn_planes_split(self.dens.data_ptr(), B, C, self.densp.data_ptr(), sp), "adn_planes_split")
+      _lib.check(lib.adn_planes_split_scaled(self.dens.data_ptr(), B, C, self.densp.data_ptr(), self.dz_log2, sp),
+                 "adn_planes_split_scaled")
       for k, m in enumerate(self.member_nets):
         _lib.check(lib.adn_dense_bwd_p(m.last_layer_planes(xp).data_ptr(), None, self.densp.data_ptr(), None, None, None,
-                                       self.d_mw[k].data_ptr(), B, m.last_layer_dim, C, 0, self.mw_ws.data_ptr(),
-                                       self.mw_ws_bytes, sp), "adn_dense_bwd_p")
+                                       self.d_mw[k].data_ptr(), B, m.last_layer_dim, C, 0, self.dz_log2,
+                                       self.mw_ws.data_ptr(), self.mw_ws_bytes, sp), "adn_dense_bwd_p")
         if not self.reg_is_zero:
           _lib.check(lib.adn_l1_grad_add(self.d_mw[k].data_ptr(), self.mw[k].data_ptr(), self.mw[k].numel(),
                                          self.reg_multiplier * self.gammas[k], sp), "adn_l1_grad_add")
@@ -522,6 +570,11 @@ class CandidatePlan:
     self.lib, self.spec, self.ens, self.index = lib, spec, ens, index
     self.batch, self.C, self.head = batch, logits_dim, _HEAD_KIND[head]
     self.name = "t{}_{}_grow_{}".format(iteration, spec.name, ens.name)   # iteration.py:633,691-693
+    if ens.mixture_weight_type == "matrix" and getattr(spec, "last_layer_is_logits", False):
+      # the reference would train W_k [C, C] on the logits (weighted.py:424-453 with common.py:115-118); the engine's
+      # MATRIX path multiplies the penultimate activation, which would be a different model: refuse instead
+      raise NotImplementedError("MATRIX mixture weights over a subnetwork whose last_layer is its logits (%s) are not "
+                                "implemented by the B200 engine; pass last_layer_fn or use SCALAR / VECTOR" % spec.name)
     self.net = DenseNet(spec.name, spec.dims, spec.ws, spec.bs, spec.complexity, batch, device, iteration,
                         spec.shared, spec.image_shape)
     self.frozen = list(frozen)
@@ -533,6 +586,7 @@ class CandidatePlan:
     self.dlogits = torch.empty((batch, dims[-1]), **f32)
     hid = max(dims[1:-1]) if len(dims) > 2 else 0
     self.planes = self.net.planes
+    self.dz_log2 = grad_log2_scale(batch)
     if self.planes:
       # back-propagated gradients as split planes: dlogits + two ping-pong buffers for the hidden layers
       self.dzp_out = new_planes(batch, dims[-1], device)
@@ -606,7 +660,7 @@ class CandidatePlan:
     if self.planes:
       _lib.check(lib.adn_head_loss_p(self.head, net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
                                      self.dlogits.data_ptr(), self.dzp_out.data_ptr(),
-                                     self.dbs[len(net.ws) - 1].data_ptr(), B, C, wsp, self.ws_bytes, sp),
+                                     self.dbs[len(net.ws) - 1].data_ptr(), self.dz_log2, B, C, wsp, self.ws_bytes, sp),
                  "adn_head_loss_p")
     else:
       _lib.check(lib.adn_head_loss(self.head, net.logits.data_ptr(), lab, labf, self.sub_loss.data_ptr(),
@@ -626,7 +680,8 @@ class CandidatePlan:
         _lib.check(lib.adn_dense_bwd_p(xin.data_ptr(), net.wps[i].data_ptr(), dzp.data_ptr(),
                                        dxp.data_ptr() if dxp is not None else None, None,
                                        self.dbs[i - 1].data_ptr() if i > 0 else None, self.dws[i].data_ptr(), B,
-                                       net.dims[i], net.dims[i + 1], 1 if i > 0 else 0, wsp, self.ws_bytes, sp),
+                                       net.dims[i], net.dims[i + 1], 1 if i > 0 else 0, self.dz_log2, wsp,
+                                       self.ws_bytes, sp),
                    "adn_dense_bwd_p")
         dzp = dxp
     dz = self.dlogits
@@ -682,7 +737,7 @@ class CandidatePlan:
     loss_out = loss_out if loss_out is not None else self.sub_loss
     _lib.check(self.lib.adn_head_loss_p(self.head, self.net.logits.data_ptr(), lab, labf, loss_out.data_ptr(),
                                         self.dlogits.data_ptr(), self.dzp_out.data_ptr(),
-                                        self.dbs[len(self.net.ws) - 1].data_ptr(), self.batch, self.C,
+                                        self.dbs[len(self.net.ws) - 1].data_ptr(), self.dz_log2, self.batch, self.C,
                                         self.workspace.data_ptr(), self.ws_bytes, sp), "adn_head_loss_p")
 
   def enqueue_ensemble(self, labels, labels_f, step_dev, sp: int, xp: Optional[torch.Tensor] = None):
@@ -704,7 +759,8 @@ class CandidatePlan:
     return _lib.BwdOp(xin.data_ptr(), net.wps[i].data_ptr(), dzp.data_ptr(),
                       dxp.data_ptr() if dxp is not None else None, dx.data_ptr() if dx is not None else None,
                       self.dbs[i - 1].data_ptr() if i > 0 else None, self.dws[i].data_ptr(), net.dims[i],
-                      net.dims[i + 1], 1 if (i > 0 or dx is not None) else 0, 0, ws.data_ptr(), self.bwd_ws_bytes)
+                      net.dims[i + 1], 1 if (i > 0 or dx is not None) else 0, self.dz_log2, ws.data_ptr(),
+                      self.bwd_ws_bytes)
 
   def enqueue_stem_bwd(self, x: torch.Tensor, sp: int):
     """Kernel / bias gradients of the conv stem from the pooled-feature gradient the last backward wave left."""
@@ -740,7 +796,9 @@ class IterationPlan:
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.iteration, self.batch, self.in_dim, self.C, self.head = iteration, batch, in_dim, logits_dim, head
     self.frozen = list(frozen)
+    self.fmt = _lib.plane_format()
     for f in self.frozen:
+      f.ensure_format()
       if f.batch != batch:
         raise ValueError("frozen member %s was built for batch %d, plan uses %d" % (f.name, f.batch, batch))
     idx = list(candidate_indices) if candidate_indices is not None else list(range(len(specs)))
@@ -979,9 +1037,14 @@ class IterationPlan:
       self._graph.replay()
     self.steps_done += 1
 
-  def eval_step(self, x, y) -> List[float]:
-    """Forward-only adanet_loss of every local candidate on one hold-out batch
-    (the Evaluator path, adanet/core/estimator.py:1469-1490)."""
+  def eval_step(self, x, y, metric: str = "adanet_loss") -> List[float]:
+    """Forward-only metric of every local candidate ensemble on one hold-out batch (the Evaluator path,
+    adanet/core/estimator.py:1469-1490): "adanet_loss" (default), "loss" / "average_loss" (the head's mean loss) or
+    "accuracy" (classification heads; arg-max of the ensemble logits, sigmoid heads at 0)."""
+    if metric not in EVAL_METRICS:
+      raise NotImplementedError("Evaluator metric %r is not computed by the B200 engine (supported: %s)" % (metric, ", ".join(EVAL_METRICS)))
+    if metric == "accuracy" and self.head == "mse":
+      raise ValueError("accuracy is not an evaluation metric of a regression head")
     self.load_batch(x, y)
     sp = torch.cuda.current_stream(self.device).cuda_stream
     self._split_x(sp)
@@ -989,10 +1052,16 @@ class IterationPlan:
       f.forward(self.lib, self.x, sp, self.xp)
     for c in self.candidates:
       c.net.forward(self.lib, self.x, sp, self.xp)
+    out = []
+    ens_out = torch.empty((self.batch, self.C), dtype=torch.float32, device=self.device) if metric == "accuracy" else None
     for _, h, _ in self.heads:
-      h.enqueue_eval(self.labels, self.labels_f, None, sp, self.xp)
+      h.enqueue_eval(self.labels, self.labels_f, ens_out, sp, self.xp)
+      if metric == "accuracy":
+        out.append(accuracy_of(ens_out, self.labels if self.labels is not None else self.labels_f))
     torch.cuda.current_stream(self.device).synchronize()
-    return [float(h.out3[2].item()) for _, h, _ in self.heads]
+    if metric == "accuracy":
+      return out
+    return [float(h.out3[2 if metric == "adanet_loss" else 0].item()) for _, h, _ in self.heads]
 
   # -- in-flight checkpoint -------------------------------------------------------
   def state_dict(self) -> Dict[str, np.ndarray]:
@@ -1019,6 +1088,13 @@ class IterationPlan:
         pre = "h%d_" % gidx
         h.load_state_dict({k[len(pre):]: v for k, v in st.items() if k.startswith(pre)})
     torch.cuda.current_stream(self.device).synchronize()
+
+  def plane_overflow(self) -> bool:
+    """True when a finite value did not fit the fp16 planes since the flag was last read (csrc/plane_fmt.cuh); the
+    caller re-runs the iteration on TF32 planes (AdaNetSearch.run / Estimator.train)."""
+    if self.fmt != _lib.PLANES_F16 or self.xp is None:
+      return False
+    return _lib.plane_overflow(torch.cuda.current_stream(self.device).cuda_stream)
 
   # -- read-back ---------------------------------------------------------------
   def ema_losses(self) -> List[float]:
@@ -1052,6 +1128,7 @@ class EnsembleEvalPlan:
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.members, self.batch, self.C, self.head = list(members), batch, logits_dim, _HEAD_KIND[head]
     for m in self.members:
+      m.ensure_format()
       if m.batch != batch:
         raise ValueError("member %s was built for batch %d, eval plan uses %d" % (m.name, m.batch, batch))
     f32 = dict(dtype=torch.float32, device=self.device)
@@ -1117,3 +1194,14 @@ class EnsembleEvalPlan:
                "adn_ensemble_head")
     o = self.out3.cpu().numpy()
     return float(o[0]), float(o[1]), float(o[2])
+
+  def metric(self, x, y, metric: str = "adanet_loss") -> float:
+    """One Evaluator metric of the finished ensemble on a batch (see IterationPlan.eval_step)."""
+    if metric not in EVAL_METRICS:
+      raise NotImplementedError("Evaluator metric %r is not computed by the B200 engine (supported: %s)" % (metric, ", ".join(EVAL_METRICS)))
+    loss, _, adanet = self.run(x, y)
+    if metric == "accuracy":
+      if self.head == _lib.HEAD_MSE:
+        raise ValueError("accuracy is not an evaluation metric of a regression head")
+      return accuracy_of(self.ens_logits, self.labels if self.labels is not None else self.labels_f)
+    return adanet if metric == "adanet_loss" else loss

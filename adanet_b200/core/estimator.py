@@ -192,7 +192,9 @@ class Estimator(object):
       raise NotImplementedError("custom Ensemblers are not supported by the B200 engine: %r" % (e,))
     return eng.EnsemblerPlanSpec(optimizer=train_lib.optimizer_from(e.optimizer), mixture_weight_type=e.mixture_weight_type,
                                  adanet_lambda=e.adanet_lambda, adanet_beta=e.adanet_beta, use_bias=e.use_bias,
-                                 name=e.name, warm_start_mixture_weights=bool(e.warm_start_mixture_weights))
+                                 name=e.name, warm_start_mixture_weights=bool(e.warm_start_mixture_weights),
+                                 initial_weight_fn=(e.initial_mixture_weight
+                                                    if getattr(e, "_mixture_weight_initializer", None) is not None else None))
 
   def _check_strategies(self):
     for s in self._ensemble_strategies:
@@ -514,16 +516,23 @@ class Estimator(object):
     write architecture-{t}.json, grow."""
     s = self._search
     t = s.iteration
+    if s.restart_on_tf32_if_overflowed():
+      # the iteration is trained again (TF32 planes) on the input that follows; its steps do not count
+      self._global_step -= self._iteration_step
+      self._iteration_step = 0
+      return None
     builders, subs = self._pending
     if self._evaluator is not None:
       ev = self._evaluator
       prev_metric = None
       if t > 0:
         plan_prev = self._ensemble_eval_plan()
-        prev_metric = ev.evaluate(lambda f, l: [plan_prev.run(input_utils.to_matrix(f, self._feature_keys), l)[2]], 1)[0]
+        prev_metric = ev.evaluate(lambda f, l: [plan_prev.metric(input_utils.to_matrix(f, self._feature_keys), l,
+                                                                 ev.metric_name)], 1)[0]
       def local_metric(plan):
-        return ev.evaluate(lambda f, l: plan.eval_step(input_utils.to_matrix(f, self._feature_keys), l),
-                           len(plan.candidates))
+        # the metric the Evaluator names, of every candidate ensemble (estimator.py:1483-1490)
+        return ev.evaluate(lambda f, l: plan.eval_step(input_utils.to_matrix(f, self._feature_keys), l, ev.metric_name),
+                           len(plan.heads))
       rep = s.finish_iteration(local_metric_fn=local_metric, previous_metric=prev_metric, objective_fn=ev.objective_fn)
     else:
       rep = s.finish_iteration()

@@ -144,7 +144,11 @@ def lower_subnetwork(builder, sub: subnetwork_lib.Subnetwork, variables: List[gr
     if op.var_list is not None and {id(v) for v in op.var_list} != chain_vars:
       raise NotImplementedError("training a strict subset of a subnetwork's variables is not implemented")
   complexity = float(np.asarray(sub.complexity, dtype=np.float32))
-  return eng.SubnetworkPlanSpec(builder.name, dims, complexity, opt_spec, ws, bs, shared=sub.shared, image_shape=image_shape)
+  spec = eng.SubnetworkPlanSpec(builder.name, dims, complexity, opt_spec, ws, bs, shared=sub.shared, image_shape=image_shape)
+  # which tensor MATRIX mixture weights multiply (weighted.py:449): the logits themselves for sub-estimator builders
+  # (autoensemble/common.py:115-118), the penultimate activation for simple_dnn-style builders
+  spec.last_layer_is_logits = ll is sub.logits and len(chain) >= 1 and ll is not chain[-1].inputs[0]
+  return spec
 
 
 def build_and_lower(builder, feature_placeholders: Dict[str, graph.Tensor], labels_placeholder, head,

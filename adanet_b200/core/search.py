@@ -181,6 +181,26 @@ class AdaNetSearch:
     end.synchronize()
     return start.elapsed_time(end) / 1e3
 
+  def restart_on_tf32_if_overflowed(self) -> bool:
+    """fp16 planes hold |v| < 65520 only (csrc/plane_fmt.cuh).  When any rank met a finite value beyond that during
+    the iteration just trained, its results are discarded: the process switches to TF32 planes for good, the plan is
+    dropped and the caller trains the iteration again (its candidates are re-created from the same deterministic
+    specs).  Returns True in that case.  One all_reduce of a flag per iteration, outside the step."""
+    from adanet_b200 import _lib
+    plan = self.plan
+    if plan is None or plan.fmt != _lib.PLANES_F16:
+      return False
+    flag = ex.max_over_ranks(1.0 if plan.plane_overflow() else 0.0, device=self.device) > 0.0
+    if not flag:
+      return False
+    import logging
+    logging.getLogger("adanet_b200").warning(
+        "iteration %d: a value did not fit the fp16 split planes; re-running the iteration on TF32 planes", self.iteration)
+    _lib.set_plane_format(_lib.PLANES_TF32)
+    self.plan = None
+    self.tf32_fallbacks = getattr(self, "tf32_fallbacks", 0) + 1
+    return True
+
   def finish_iteration(self, train_seconds: float = 0.0, local_metric_fn=None, previous_metric=None,
                        objective_fn=None) -> IterationReport:
     """Selection + growth (bookkeeping phase, estimator.py:1247-1283).
@@ -265,8 +285,11 @@ class AdaNetSearch:
 
   def run(self, batches: Iterator, steps_per_iteration: int, iterations: int) -> List[IterationReport]:
     for _ in range(iterations):
-      self.build_iteration()
-      secs = self.train_iteration(batches, steps_per_iteration)
+      while True:
+        self.build_iteration()
+        secs = self.train_iteration(batches, steps_per_iteration)
+        if not self.restart_on_tf32_if_overflowed():
+          break
       self.finish_iteration(secs)
     return self.reports
 

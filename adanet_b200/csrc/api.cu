@@ -1,4 +1,4 @@
-// C-ABI glue: error state, queries, dense path dispatch (SIMT fp32 vs tcgen05 3xTF32).
+// C-ABI glue: error state, queries, dense path dispatch (SIMT fp32 vs tcgen05 split planes).
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -113,7 +113,10 @@ extern "C" int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_
     case ADN_Q_DENSE_FWD_PATH: *out_host = pick_fwd_path(a, b, c); return ADN_OK;
     case ADN_Q_DENSE_BWD_PATH: *out_host = pick_bwd_path(a, b, c); return ADN_OK;
     case ADN_Q_SM_COUNT: *out_host = sm_count(); return ADN_OK;
-    case ADN_Q_PLANES_BYTES: *out_host = pl::planes_bytes(a, b); return ADN_OK;
+    case ADN_Q_PLANES_BYTES: *out_host = pl::planes_bytes(pl::format(), a, b); return ADN_OK;
+    case ADN_Q_PLANE_FORMAT: *out_host = pl::format(); return ADN_OK;
+    case ADN_Q_TMA_MAP_CACHE_HITS: *out_host = pl::map_cache_hits(); return ADN_OK;
+    case ADN_Q_TMA_MAP_CACHE_MISSES: *out_host = pl::map_cache_misses(); return ADN_OK;
     case ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES: *out_host = pl::dense_bwd_workspace_bytes(a, b, c); return ADN_OK;
     case ADN_Q_COLSUM_WORKSPACE_BYTES: *out_host = 64 * b * (int64_t)sizeof(float) + 256; return ADN_OK;
     case ADN_Q_CONV_STEM_BWD_WORKSPACE_BYTES: *out_host = conv::bwd_workspace_bytes(a, (int)b, (int)c); return ADN_OK;
@@ -160,37 +163,51 @@ static bool bad_shape(int64_t a, int64_t b, int64_t c) {
   return a <= 0 || b <= 0 || c <= 0 || a > INT32_MAX || b > INT32_MAX || c > INT32_MAX;
 }
 
-extern "C" int adn_planes_split(const float* src, int64_t rows, int64_t cols, float* planes, void* stream) {
+extern "C" int adn_set_plane_format(int fmt) { return pl::set_format(fmt); }
+
+extern "C" int adn_plane_overflow(int* flag_host, int reset, void* stream) {
+  if (!flag_host) return fail(ADN_ERR_INVALID, "adn_plane_overflow: null pointer");
+  return pl::read_overflow(flag_host, reset, as_stream(stream));
+}
+
+extern "C" int adn_planes_split_scaled(const float* src, int64_t rows, int64_t cols, void* planes, int log2_scale,
+                                       void* stream) {
   if (!src || !planes) return fail(ADN_ERR_INVALID, "adn_planes_split: null pointer");
   if (bad_shape(rows, cols, 1)) return fail(ADN_ERR_INVALID, "adn_planes_split: bad shape");
-  return pl::split(src, rows, cols, planes, as_stream(stream));
+  if (log2_scale < -60 || log2_scale > 60) return fail(ADN_ERR_INVALID, "adn_planes_split: bad log2_scale %d", log2_scale);
+  return pl::split(pl::format(), src, rows, cols, planes, log2_scale, as_stream(stream));
 }
 
-extern "C" int adn_planes_merge(const float* planes, int64_t rows, int64_t cols, float* dst, void* stream) {
+extern "C" int adn_planes_split(const float* src, int64_t rows, int64_t cols, void* planes, void* stream) {
+  return adn_planes_split_scaled(src, rows, cols, planes, 0, stream);
+}
+
+extern "C" int adn_planes_merge(const void* planes, int64_t rows, int64_t cols, float* dst, void* stream) {
   if (!planes || !dst) return fail(ADN_ERR_INVALID, "adn_planes_merge: null pointer");
   if (bad_shape(rows, cols, 1)) return fail(ADN_ERR_INVALID, "adn_planes_merge: bad shape");
-  return pl::merge(planes, rows, cols, dst, as_stream(stream));
+  return pl::merge(pl::format(), planes, rows, cols, dst, as_stream(stream));
 }
 
-extern "C" int adn_dense_fwd_p(const float* xp, const float* wp, const float* b, float* yp, float* y, int64_t batch,
+extern "C" int adn_dense_fwd_p(const void* xp, const void* wp, const float* b, void* yp, float* y, int64_t batch,
                                int64_t in, int64_t out, int act, void* stream) {
   if (!xp || !wp) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p: null pointer");
   if ((yp == nullptr) == (y == nullptr)) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p: exactly one of yp / y");
   if (bad_shape(batch, in, out)) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p: bad shape");
   if (act != ADN_ACT_NONE && act != ADN_ACT_RELU) return fail(ADN_ERR_INVALID, "adn_dense_fwd_p: bad act %d", act);
-  return pl::dense_fwd(xp, wp, b, yp, y, batch, in, out, act, as_stream(stream));
+  return pl::dense_fwd(pl::format(), xp, wp, b, yp, y, batch, in, out, act, as_stream(stream));
 }
 
-extern "C" int adn_dense_bwd_p(const float* xp, const float* wp, const float* dzp, float* dxp, float* dx,
+extern "C" int adn_dense_bwd_p(const void* xp, const void* wp, const void* dzp, void* dxp, float* dx,
                                float* dx_colsum, float* dw, int64_t batch, int64_t in, int64_t out, int x_relu_mask,
-                               void* workspace, int64_t workspace_bytes, void* stream) {
+                               int dz_log2_scale, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!xp || !dzp || !workspace) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: null pointer");
   if ((dxp || dx) && !wp) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: wp required when dx requested");
   if (dxp && dx) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: at most one of dxp / dx");
   if (dx_colsum && !(dxp || dx)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: dx_colsum needs dx");
   if (bad_shape(batch, in, out)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: bad shape");
-  return pl::dense_bwd(xp, wp, dzp, dxp, dx, dx_colsum, dw, batch, in, out, x_relu_mask, workspace, workspace_bytes,
-                       as_stream(stream));
+  if (dz_log2_scale < -60 || dz_log2_scale > 60) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p: bad dz_log2_scale");
+  return pl::dense_bwd(pl::format(), xp, wp, dzp, dxp, dx, dx_colsum, dw, batch, in, out, x_relu_mask, dz_log2_scale,
+                       workspace, workspace_bytes, as_stream(stream));
 }
 
 extern "C" int adn_colsum(const float* x, int64_t rows, int64_t cols, float* out, void* workspace,
@@ -215,7 +232,7 @@ extern "C" int adn_dense_fwd_p_group(const adn_fwd_op* ops, int n, int64_t batch
       return fail(ADN_ERR_INVALID, "adn_dense_fwd_p_group: op %d: bad act %d", i, ops[i].act);
     o[i] = pl::FwdOp{ops[i].xp, ops[i].wp, ops[i].bias, ops[i].yp, ops[i].y, ops[i].in, ops[i].out, ops[i].act};
   }
-  return pl::dense_fwd_group(o, n, batch, as_stream(stream));
+  return pl::dense_fwd_group(pl::format(), o, n, batch, as_stream(stream));
 }
 
 extern "C" int adn_dense_bwd_p_group(const adn_bwd_op* ops, int n, int64_t batch, void* stream) {
@@ -229,8 +246,10 @@ extern "C" int adn_dense_bwd_p_group(const adn_bwd_op* ops, int n, int64_t batch
     if (p.dxp && p.dx) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: at most one of dxp / dx", i);
     if (p.dx_colsum && !(p.dxp || p.dx)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: dx_colsum needs dx", i);
     if (bad_shape(batch, p.in, p.out)) return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: bad shape", i);
-    o[i] = pl::BwdOp{p.xp, p.wp, p.dzp, p.dxp, p.dx, p.dx_colsum, p.dw, p.in, p.out, p.x_relu_mask, p.workspace,
-                     p.workspace_bytes};
+    if (p.dz_log2_scale < -60 || p.dz_log2_scale > 60)
+      return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: bad dz_log2_scale", i);
+    o[i] = pl::BwdOp{p.xp, p.wp, p.dzp, p.dxp, p.dx, p.dx_colsum, p.dw, p.in, p.out, p.x_relu_mask, p.dz_log2_scale,
+                     p.workspace, p.workspace_bytes};
   }
-  return pl::dense_bwd_group(o, n, batch, as_stream(stream));
+  return pl::dense_bwd_group(pl::format(), o, n, batch, as_stream(stream));
 }

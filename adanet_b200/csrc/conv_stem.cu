@@ -24,18 +24,16 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "plane_fmt.cuh"
 
 namespace adn {
-namespace pl {
-int64_t plane_floats(int64_t rows, int64_t cols);
-}
 
 namespace convtc {
 bool bwd_supported(int h, int w, int cin, int f);
 int bwd(const float* images, const uint32_t* argmax, const float* dpooled, float* partials, int* n_partials, int64_t batch,
         int h, int w, int cin, int f, cudaStream_t st);
 bool supported(int h, int w, int cin, int f);
-int fwd(const float* images, const float* kernel, const float* bias, float* out_planes, uint32_t* argmax, int64_t batch,
+int fwd(const float* images, const float* kernel, const float* bias, void* out_planes, uint32_t* argmax, int64_t batch,
         int h, int w, int cin, int f, cudaStream_t st);
 }
 
@@ -88,7 +86,7 @@ __device__ __forceinline__ void stage_image(float* s_img, const float* img, int 
 template <int CIN>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 conv_stem_fwd_kernel(const float* __restrict__ images, const float* __restrict__ kernel, const float* __restrict__ bias,
-                     float* __restrict__ hi, float* __restrict__ lo, uint16_t* __restrict__ bits16,
+                     const pl::PlaneView pv, unsigned int* ovf,
                      uint32_t* __restrict__ argmax, int64_t B, int H, int W, int F) {
   extern __shared__ __align__(16) float smem[];
   const int K = 9 * CIN;
@@ -150,7 +148,7 @@ conv_stem_fwd_kernel(const float* __restrict__ images, const float* __restrict__
                 }
             }
         // bias is in; ReLU + 2x2 max (first maximum in scan order wins, as TF's MaxPoolGrad routes it)
-        float out_hi[FC], out_lo[FC];
+        float outv[FC];
         uint32_t sign = 0u, arg = 0u;
 #pragma unroll
         for (int j = 0; j < FC; ++j) {
@@ -162,22 +160,18 @@ conv_stem_fwd_kernel(const float* __restrict__ images, const float* __restrict__
           m = fmaxf(m, 0.f);
           sign |= (m > 0.f) ? (1u << j) : 0u;
           arg |= a << (2 * j);
-          const float h = rna_tf32(m);
-          out_hi[j] = h;
-          out_lo[j] = rna_tf32(m - h);
+          outv[j] = m;
         }
         const int64_t col0 = (int64_t)p * F + f0;       // multiple of 16
-        const int64_t kb = col0 >> 5;
-        const int off = (int)(col0 & 31);
-        const int64_t dst = (kb * B + b) * 32 + off;
 #pragma unroll
-        for (int q = 0; q < FC / 4; ++q) {
-          *reinterpret_cast<float4*>(hi + dst + 4 * q) =
-              make_float4(out_hi[4 * q], out_hi[4 * q + 1], out_hi[4 * q + 2], out_hi[4 * q + 3]);
-          *reinterpret_cast<float4*>(lo + dst + 4 * q) =
-              make_float4(out_lo[4 * q], out_lo[4 * q + 1], out_lo[4 * q + 2], out_lo[4 * q + 3]);
+        for (int q = 0; q < FC / 8; ++q) {
+          float m8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) m8[e] = outv[8 * q + e];
+          pl::plane_store8(pv, b, col0 + 8 * q, m8, ovf);
         }
-        bits16[(kb * B + b) * 2 + (off >> 4)] = (uint16_t)sign;   // low half = columns 0..15 of the k-block
+        // sign bits: one uint32 per (32-column block, row); this thread owns one 16-bit half of it
+        reinterpret_cast<uint16_t*>(pv.bits)[((col0 >> 5) * B + b) * 2 + ((col0 >> 4) & 1)] = (uint16_t)sign;
         argmax[b * words_per_row + (col0 >> 4)] = arg;
       }
     }
@@ -336,7 +330,7 @@ int64_t bwd_workspace_bytes(int64_t batch, int cin, int f) {
 
 using namespace adn;
 
-extern "C" int adn_conv_stem_fwd(const float* images, const float* kernel, const float* bias, float* out_planes,
+extern "C" int adn_conv_stem_fwd(const float* images, const float* kernel, const float* bias, void* out_planes,
                                  uint32_t* argmax, int64_t batch, int height, int width, int channels, int filters,
                                  void* stream) {
   if (!images || !kernel || !bias || !out_planes || !argmax) return fail(ADN_ERR_INVALID, "adn_conv_stem_fwd: null pointer");
@@ -344,18 +338,15 @@ extern "C" int adn_conv_stem_fwd(const float* images, const float* kernel, const
   if (conv::use_tc() && convtc::supported(height, width, channels, filters))
     return convtc::fwd(images, kernel, bias, out_planes, argmax, batch, height, width, channels, filters, as_stream(stream));
   const int64_t cols = (int64_t)(height / 2) * (width / 2) * filters;
-  const int64_t pf = pl::plane_floats(batch, cols);
-  float* hi = out_planes;
-  float* lo = out_planes + pf;
-  uint16_t* bits16 = reinterpret_cast<uint16_t*>(out_planes + 2 * pf);
+  const pl::PlaneView pv = pl::plane_view(pl::format(), out_planes, batch, cols);
   const int pimg = (height + 2) * (width + 2) * channels;
   const size_t smem = (size_t)(9 * channels * filters + filters + 2 * pimg) * sizeof(float);
   const int64_t cap = (int64_t)sm_count() * 2;
   const int grid = (int)(batch < cap ? batch : cap);
   if (smem > conv::kMaxSmem) return fail(ADN_ERR_UNSUPPORTED, "adn_conv_stem_fwd: %zu bytes of staging do not fit", smem);
   auto launch = [&](auto kern) -> int {
-    kern<<<grid, conv::FWD_THREADS, smem, as_stream(stream)>>>(images, kernel, bias, hi, lo, bits16, argmax, batch, height,
-                                                             width, filters);
+    kern<<<grid, conv::FWD_THREADS, smem, as_stream(stream)>>>(images, kernel, bias, pv, pl::overflow_flag(), argmax, batch,
+                                                             height, width, filters);
     ADN_CHECK_LAUNCH("conv_stem_fwd");
     return ADN_OK;
   };

@@ -20,11 +20,9 @@
 // the MMAs and commits to the warpgroup's mbarrier, then all 128 threads read their accumulator row with
 // tcgen05.ld (warp w reads TMEM lanes 32(w%4)..) and run the epilogue.  W' (hi / lo, K-major) is built once per CTA.
 #include "common.cuh"
+#include "plane_fmt.cuh"
 
 namespace adn {
-namespace pl {
-int64_t plane_floats(int64_t rows, int64_t cols);
-}
 namespace convtc {
 
 static constexpr int THREADS = 256;
@@ -154,7 +152,7 @@ __host__ __device__ constexpr int fwd_image_buffers(int f) { return f == 16 ? 4 
 template <int CIN, int F>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_stem_tc_fwd_kernel(const float* __restrict__ images, const float* __restrict__ kernel, const float* __restrict__ bias,
-                        float* __restrict__ hi, float* __restrict__ lo, uint16_t* __restrict__ bits16,
+                        const pl::PlaneView pv, unsigned int* ovf,
                         uint32_t* __restrict__ argmax, int64_t B, int H, int W) {
   constexpr int K = 16 * CIN;              // 4x4xCIN patch
   constexpr int KB = (K + 31) / 32;        // k-blocks of 32 floats (128 B swizzle atoms)
@@ -308,9 +306,6 @@ conv_stem_tc_fwd_kernel(const float* __restrict__ images, const float* __restric
         for (int f0 = 0; f0 < F; f0 += 16) {
           uint32_t sign = 0u, arg = 0u;
           const int64_t col0 = (int64_t)p * F + f0;
-          const int64_t kb = col0 >> 5;
-          const int off = (int)(col0 & 31);
-          const int64_t dst = (kb * B + b) * 32 + off;
 #pragma unroll
           for (int f8 = 0; f8 < 16; f8 += 8) {
             float a0[8], a1[8], a2[8], a3[8];
@@ -323,7 +318,7 @@ conv_stem_tc_fwd_kernel(const float* __restrict__ images, const float* __restric
               tc_fence_before();
               mbar_arrive(acc_free0 + 8 * accsel);
             }
-            float out_hi[8], out_lo[8];
+            float outv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float bv = s_b[f0 + f8 + j];
@@ -336,22 +331,12 @@ conv_stem_tc_fwd_kernel(const float* __restrict__ images, const float* __restric
               m = fmaxf(m, 0.f);
               sign |= (m > 0.f) ? (1u << (f8 + j)) : 0u;
               arg |= a << (2 * (f8 + j));
-              const float h = rna_tf32(m);
-              out_hi[j] = h;
-              out_lo[j] = rna_tf32(m - h);
+              outv[j] = m;
             }
-            if (valid) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                *reinterpret_cast<float4*>(hi + dst + f8 + 4 * q) =
-                    make_float4(out_hi[4 * q], out_hi[4 * q + 1], out_hi[4 * q + 2], out_hi[4 * q + 3]);
-                *reinterpret_cast<float4*>(lo + dst + f8 + 4 * q) =
-                    make_float4(out_lo[4 * q], out_lo[4 * q + 1], out_lo[4 * q + 2], out_lo[4 * q + 3]);
-              }
-            }
+            if (valid) pl::plane_store8(pv, b, col0 + f8, outv, ovf);
           }
           if (valid) {
-            bits16[(kb * B + b) * 2 + (off >> 4)] = (uint16_t)sign;
+            reinterpret_cast<uint16_t*>(pv.bits)[((col0 >> 5) * B + b) * 2 + ((col0 >> 4) & 1)] = (uint16_t)sign;
             argmax[b * words_per_row + (col0 >> 4)] = arg;
           }
         }
@@ -633,13 +618,13 @@ static size_t smem_bytes(int h, int w) {
 }
 
 template <int CIN, int F>
-static int launch(const float* images, const float* kernel, const float* bias, float* hi, float* lo, uint16_t* bits16,
+static int launch(const float* images, const float* kernel, const float* bias, const pl::PlaneView pv,
                   uint32_t* argmax, int64_t batch, int h, int w, cudaStream_t st) {
   const size_t smem = smem_bytes<CIN, F>(h, w);
   auto kern = conv_stem_tc_fwd_kernel<CIN, F>;
   const int64_t cap = sm_count();
   const int grid = (int)(batch < cap ? batch : cap);
-  kern<<<grid, FWD_THREADS, smem, st>>>(images, kernel, bias, hi, lo, bits16, argmax, batch, h, w);
+  kern<<<grid, FWD_THREADS, smem, st>>>(images, kernel, bias, pv, pl::overflow_flag(), argmax, batch, h, w);
   ADN_CHECK_LAUNCH("conv_stem_tc_fwd");
   return ADN_OK;
 }
@@ -662,17 +647,14 @@ bool supported(int h, int w, int cin, int f) {
   return smem <= 227 * 1024;
 }
 
-int fwd(const float* images, const float* kernel, const float* bias, float* out_planes, uint32_t* argmax, int64_t batch,
+int fwd(const float* images, const float* kernel, const float* bias, void* out_planes, uint32_t* argmax, int64_t batch,
         int h, int w, int cin, int f, cudaStream_t st) {
   const int64_t cols = (int64_t)(h / 2) * (w / 2) * f;
-  const int64_t pf = pl::plane_floats(batch, cols);
-  float* hi = out_planes;
-  float* lo = out_planes + pf;
-  uint16_t* bits16 = reinterpret_cast<uint16_t*>(out_planes + 2 * pf);
-  if (cin == 3) return f == 16 ? launch<3, 16>(images, kernel, bias, hi, lo, bits16, argmax, batch, h, w, st)
-                               : launch<3, 32>(images, kernel, bias, hi, lo, bits16, argmax, batch, h, w, st);
-  return f == 16 ? launch<1, 16>(images, kernel, bias, hi, lo, bits16, argmax, batch, h, w, st)
-                 : launch<1, 32>(images, kernel, bias, hi, lo, bits16, argmax, batch, h, w, st);
+  const pl::PlaneView pv = pl::plane_view(pl::format(), out_planes, batch, cols);
+  if (cin == 3) return f == 16 ? launch<3, 16>(images, kernel, bias, pv, argmax, batch, h, w, st)
+                               : launch<3, 32>(images, kernel, bias, pv, argmax, batch, h, w, st);
+  return f == 16 ? launch<1, 16>(images, kernel, bias, pv, argmax, batch, h, w, st)
+                 : launch<1, 32>(images, kernel, bias, pv, argmax, batch, h, w, st);
 }
 
 }  // namespace convtc

@@ -69,7 +69,7 @@ static __global__ void reduce_partials_group_kernel(const __grid_constant__ Redu
   if (i >= jb.n) return;
   float acc = 0.f;
   for (int s = 0; s < jb.S; ++s) acc += jb.part[(size_t)s * jb.stride + i];
-  jb.out[i] = acc;
+  jb.out[i] = acc * jb.scale;     // scale is a power of two (gradient planes carry 2^k): exact
 }
 
 static __global__ void __launch_bounds__(256)
@@ -122,7 +122,7 @@ int colsum_group(const ColsumJob* jobs, int n, cudaStream_t st) {
       const int s2 = (int)ceil_div(jobs[i0 + i].rows, cj.rps[i]);
       max_s2 = std::max(max_s2, s2);
       max_cols = std::max(max_cols, jobs[i0 + i].cols);
-      rj.j[i] = ReduceJob{jobs[i0 + i].part, jobs[i0 + i].out, jobs[i0 + i].cols, s2, jobs[i0 + i].cols};
+      rj.j[i] = ReduceJob{jobs[i0 + i].part, jobs[i0 + i].out, jobs[i0 + i].cols, s2, jobs[i0 + i].cols, jobs[i0 + i].scale};
     }
     dim3 grid((unsigned)ceil_div(max_cols, 32), (unsigned)max_s2, (unsigned)m);
     colsum_partial_group_kernel<<<grid, 256, 0, st>>>(cj);

@@ -144,10 +144,10 @@ sgemm_kernel(GemmArgs g) {
 // out[i] = sum_{s<S} part[s*stride + i]   (fixed order -> deterministic)
 int reduce_partials(const float* part, float* out, int64_t n, int S, int64_t stride, cudaStream_t st);
 // grouped: out[i] = sum_s part[s*stride + i] for several (part, out) pairs in one launch
-struct ReduceJob { const float* part; float* out; int64_t n; int S; int64_t stride; };
+struct ReduceJob { const float* part; float* out; int64_t n; int S; int64_t stride; float scale = 1.0f; };   // out = scale * sum
 int reduce_partials_group(const ReduceJob* jobs, int n, cudaStream_t st);
 // grouped column sums: out[c] = sum_r x[r, c]; part = 64 * cols floats of scratch per job
-struct ColsumJob { const float* x; float* out; int64_t rows, cols; float* part; };
+struct ColsumJob { const float* x; float* out; int64_t rows, cols; float* part; float scale = 1.0f; };
 int colsum_group(const ColsumJob* jobs, int n, cudaStream_t st);
 // db[n] = sum_rows dz[row*N + n] via fixed-order partials in `part` (ceil(rows/512)*N floats)
 int colsum(const float* dz, float* db, int64_t rows, int64_t N, float* part, cudaStream_t st);

@@ -1,5 +1,6 @@
 // fp32-in / fp32-out entry points of the tcgen05 dense path (adn_dense_fwd / adn_dense_bwd with
-// ADN_PATH_TCGEN05 or AUTO): the operands are split into TF32 hi/lo planes in the caller's
+// ADN_PATH_TCGEN05 or AUTO): the operands are split into TF32 hi/lo planes (always TF32 here: the caller's
+// gradient magnitudes are unknown, so no fp16 scale can be chosen for it) in the caller's
 // workspace and the plane-native GEMM of planes.cu does the rest.  A subnetwork that keeps its
 // activations in plane format (adn_dense_fwd_p / adn_dense_bwd_p, what core/engine.py runs) never
 // pays these conversion passes; this file exists so that the row-major fp32 ABI stays a drop-in.
@@ -19,7 +20,7 @@ int init() { return pl::init(); }
 bool fwd_supported(int64_t batch, int64_t in, int64_t out) { return batch >= 128 && in >= 32 && out >= 64; }
 bool bwd_supported(int64_t batch, int64_t in, int64_t out) { return batch >= 128 && in >= 32 && out >= 64; }
 
-static inline int64_t pbytes(int64_t rows, int64_t cols) { return align_up(pl::planes_bytes(rows, cols), 256); }
+static inline int64_t pbytes(int64_t rows, int64_t cols) { return align_up(pl::planes_bytes(pl::FMT_TF32, rows, cols), 256); }
 
 int64_t dense_fwd_workspace_bytes(int64_t batch, int64_t in, int64_t out) {
   if (!fwd_supported(batch, in, out)) return 0;
@@ -56,13 +57,13 @@ int dense_fwd(const float* x, const float* w, const float* b, float* y, int64_t 
     return fail(ADN_ERR_WORKSPACE, "tc dense_fwd: workspace %lld < %lld bytes", (long long)ws_bytes,
                 (long long)dense_fwd_workspace_bytes(batch, in, out));
   Carver c = carver(ws, ws_bytes);
-  float* xp = reinterpret_cast<float*>(c.take(pl::planes_bytes(batch, in)));
-  float* wp = reinterpret_cast<float*>(c.take(pl::planes_bytes(in, out)));
+  void* xp = c.take(pl::planes_bytes(pl::FMT_TF32, batch, in));
+  void* wp = c.take(pl::planes_bytes(pl::FMT_TF32, in, out));
   if (!c.ok) return fail(ADN_ERR_WORKSPACE, "tc dense_fwd: workspace carve failed");
   int rc;
-  if ((rc = pl::split(x, batch, in, xp, st))) return rc;
-  if ((rc = pl::split(w, in, out, wp, st))) return rc;
-  return pl::dense_fwd(xp, wp, b, nullptr, y, batch, in, out, act, st);
+  if ((rc = pl::split(pl::FMT_TF32, x, batch, in, xp, 0, st))) return rc;
+  if ((rc = pl::split(pl::FMT_TF32, w, in, out, wp, 0, st))) return rc;
+  return pl::dense_fwd(pl::FMT_TF32, xp, wp, b, nullptr, y, batch, in, out, act, st);
 }
 
 int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float* dw, float* db, int64_t batch,
@@ -71,19 +72,19 @@ int dense_bwd(const float* x, const float* w, const float* dz, float* dx, float*
     return fail(ADN_ERR_WORKSPACE, "tc dense_bwd: workspace %lld < %lld bytes", (long long)ws_bytes,
                 (long long)dense_bwd_workspace_bytes(batch, in, out));
   Carver c = carver(ws, ws_bytes);
-  float* xp = reinterpret_cast<float*>(c.take(pl::planes_bytes(batch, in)));
-  float* wp = reinterpret_cast<float*>(c.take(pl::planes_bytes(in, out)));
-  float* dzp = reinterpret_cast<float*>(c.take(pl::planes_bytes(batch, out)));
+  void* xp = c.take(pl::planes_bytes(pl::FMT_TF32, batch, in));
+  void* wp = c.take(pl::planes_bytes(pl::FMT_TF32, in, out));
+  void* dzp = c.take(pl::planes_bytes(pl::FMT_TF32, batch, out));
   const int64_t inner = pl::dense_bwd_workspace_bytes(batch, in, out);
   void* inner_ws = c.take(inner);
   float* dbpart = reinterpret_cast<float*>(c.take(64 * out * (int64_t)sizeof(float)));
   if (!c.ok) return fail(ADN_ERR_WORKSPACE, "tc dense_bwd: workspace carve failed");
   int rc;
-  if ((rc = pl::split(x, batch, in, xp, st))) return rc;     // also yields the sign bits used as the ReLU mask
-  if ((rc = pl::split(dz, batch, out, dzp, st))) return rc;
-  if (dx && (rc = pl::split(w, in, out, wp, st))) return rc;
+  if ((rc = pl::split(pl::FMT_TF32, x, batch, in, xp, 0, st))) return rc;     // also yields the sign bits used as the ReLU mask
+  if ((rc = pl::split(pl::FMT_TF32, dz, batch, out, dzp, 0, st))) return rc;
+  if (dx && (rc = pl::split(pl::FMT_TF32, w, in, out, wp, 0, st))) return rc;
   if (db && (rc = simt::colsum(dz, db, batch, out, dbpart, st))) return rc;
-  return pl::dense_bwd(xp, wp, dzp, nullptr, dx, nullptr, dw, batch, in, out, x_relu_mask, inner_ws, inner, st);
+  return pl::dense_bwd(pl::FMT_TF32, xp, wp, dzp, nullptr, dx, nullptr, dw, batch, in, out, x_relu_mask, 0, inner_ws, inner, st);
 }
 
 }  // namespace tc

@@ -11,6 +11,7 @@
 //   mixture-weight gradient  adanet/ensemble/weighted.py:606-617
 //   EMA                      adanet/core/candidate.py:117-129
 #include "common.cuh"
+#include "plane_fmt.cuh"
 
 namespace adn {
 
@@ -28,8 +29,10 @@ struct HeadParams {
   const int64_t* labels;
   const float* labels_f;
   float* dens;           // [B,dim] or null
-  float* dens_hi;        // split planes of dens (csrc/planes.cu layout [dim/32][B][32]) or null
-  float* dens_lo;
+  pl::PlaneView densp;   // split planes of dens * dens_scale (csrc/plane_fmt.cuh) or hi == null
+  float dens_scale;      // power of two
+  int dens_nkb;          // k-blocks of the plane tensor
+  unsigned int* ovf;
   int colsum_only;       // want_grads without the mixture-weight pass: only column sums of dens -> dbias
   float* ens_out;        // [B,dim] or null
   float* part;           // workspace: per-CTA partials, output-major [n_out][n_cta] (coalesced for the finalize)
@@ -165,20 +168,19 @@ ensemble_head_kernel(const __grid_constant__ HeadParams p) {
   if (p.dens) {
     for (int i = tid; i < valid; i += kRows) p.dens[base + i] = ens[i];
   }
-  if (p.dens_hi) {
-    // same gradient as TF32 hi/lo planes: the A / B operand of the subnetwork's backward GEMMs
-    const int nkb = (C + 31) >> 5;
-    for (int i = tid; i < kRows * nkb * 32; i += kRows) {
-      const int c32 = i & 31, r = (i >> 5) % kRows, kb = (i >> 5) / kRows;
+  if (p.densp.hi) {
+    // same gradient (times the power-of-two plane scale) as hi/lo planes: the A / B operand of the subnetwork's
+    // backward GEMMs; padding columns of the last k-block are rewritten as zeros
+    const int bk = pl::fmt_bk(p.densp.fmt);
+    const int pc = p.dens_nkb * bk;
+    for (int i = tid; i < kRows * pc; i += kRows) {
+      const int cb = i % bk, r = (i / bk) % kRows, kb = (i / bk) / kRows;
       if (r0 + r >= p.batch) continue;
-      const int c = kb * 32 + c32;
-      const float v = (c < C) ? ens[r * C + c] : 0.f;
-      const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-      const float lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
-      const size_t dst = ((size_t)kb * p.batch + r0 + r) * 32 + c32;
-      p.dens_hi[dst] = hi;
-      p.dens_lo[dst] = lo;
+      const int c = kb * bk + cb;
+      const float v = (c < C) ? ens[r * C + c] * p.dens_scale : 0.f;
+      pl::plane_store(p.densp, r0 + r, c, v, p.ovf);
     }
+    // sign bits are not consumed for gradient tensors
   }
   if (!p.want_grads) return;
 
@@ -413,18 +415,18 @@ int64_t head_workspace_bytes_public(int64_t batch, int64_t dim, int64_t members)
 
 using namespace adn;
 
-namespace adn { namespace pl { int64_t plane_floats(int64_t rows, int64_t cols); } }
 
 extern "C" int adn_head_loss(int head, const float* logits, const int64_t* labels, const float* labels_f,
                              float* loss_out, float* dlogits, int64_t batch, int64_t dim,
                              void* workspace, int64_t workspace_bytes, void* stream) {
-  return adn_head_loss_p(head, logits, labels, labels_f, loss_out, dlogits, nullptr, nullptr, batch, dim, workspace,
+  return adn_head_loss_p(head, logits, labels, labels_f, loss_out, dlogits, nullptr, nullptr, 0, batch, dim, workspace,
                          workspace_bytes, stream);
 }
 
 extern "C" int adn_head_loss_p(int head, const float* logits, const int64_t* labels, const float* labels_f,
-                               float* loss_out, float* dlogits, float* dlogits_planes, float* dlogits_colsum,
-                               int64_t batch, int64_t dim, void* workspace, int64_t workspace_bytes, void* stream) {
+                               float* loss_out, float* dlogits, void* dlogits_planes, float* dlogits_colsum,
+                               int dz_log2_scale, int64_t batch, int64_t dim, void* workspace, int64_t workspace_bytes,
+                               void* stream) {
   if (!logits || !loss_out) return fail(ADN_ERR_INVALID, "adn_head_loss: null pointer");
   if (head < 0 || head > 2) return fail(ADN_ERR_INVALID, "adn_head_loss: bad head %d", head);
   // out3 needs 3 floats; the public contract is loss_out[0], so stage through workspace tail.
@@ -436,9 +438,13 @@ extern "C" int adn_head_loss_p(int head, const float* logits, const int64_t* lab
   p.labels = labels;
   p.labels_f = labels_f;
   p.dens = dlogits;
+  if (dz_log2_scale < -60 || dz_log2_scale > 60) return fail(ADN_ERR_INVALID, "adn_head_loss_p: bad dz_log2_scale");
   if (dlogits_planes) {
-    p.dens_hi = dlogits_planes;
-    p.dens_lo = dlogits_planes + pl::plane_floats(batch, dim);
+    const int fmt = pl::format();
+    p.densp = pl::plane_view(fmt, dlogits_planes, batch, dim);
+    p.dens_scale = ldexpf(1.0f, dz_log2_scale);
+    p.dens_nkb = (int)ceil_div(dim, pl::fmt_bk(fmt));
+    p.ovf = pl::overflow_flag();
   }
   p.batch = batch;
   p.dim = (int)dim;

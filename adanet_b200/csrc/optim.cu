@@ -13,6 +13,7 @@
 //   Momentum+cosine  Momentum with lr_t = tf.train.cosine_decay(lr, step, decay_steps, alpha) read from the
 //                    device step counter (customizing_adanet.ipynb SimpleCNNBuilder.build_subnetwork_train_op)
 #include "common.cuh"
+#include "plane_fmt.cuh"
 
 namespace adn {
 
@@ -30,26 +31,21 @@ struct OptParams {
   int kind;
   float h0, h1, h2, h3;
   const int64_t* step_dev;
-  // optional split planes of 2-D parameters, refreshed with the update (planes.cu layout)
-  float* planes[kMaxTensors];     // hi plane base (nullable per tensor)
-  int64_t plane_lo_off[kMaxTensors];
+  // optional split planes of 2-D parameters, refreshed with the update (plane_fmt.cuh layout)
+  void* plane_hi[kMaxTensors];    // hi plane base (nullable per tensor)
+  void* plane_lo[kMaxTensors];
   int cols[kMaxTensors];
+  int fmt;
+  unsigned int* ovf;
 };
 
 __device__ __forceinline__ void store_planes(const OptParams& o, int t, int64_t j, float v) {
-  float* pl = o.planes[t];
-  if (!pl) return;
+  if (!o.plane_hi[t]) return;
   const int cols = o.cols[t];
   const int64_t rows = o.size[t] / cols;
   const int64_t r = j / cols;
   const int c = (int)(j - r * cols);
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  const float hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-  const int64_t dst = ((int64_t)(c >> 5) * rows + r) * 32 + (c & 31);
-  pl[dst] = hi;
-  pl[dst + o.plane_lo_off[t]] = __uint_as_float(l);
+  pl::plane_store(pl::PlaneView{o.plane_hi[t], o.plane_lo[t], nullptr, rows, o.fmt}, r, c, v, o.ovf);
 }
 
 __device__ __forceinline__ void apply_one(int kind, float& p, float g, float& s0, float& s1, float h0, float h1,
@@ -145,7 +141,6 @@ __global__ void step_increment_kernel(int64_t* step) { *step += 1; }
 
 using namespace adn;
 
-namespace adn { namespace pl { int64_t plane_floats(int64_t rows, int64_t cols); } }
 
 extern "C" int adn_opt_step(int kind, float* const* params_host, const float* const* grads_host,
                             float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
@@ -157,7 +152,7 @@ extern "C" int adn_opt_step(int kind, float* const* params_host, const float* co
 extern "C" int adn_opt_step_p(int kind, float* const* params_host, const float* const* grads_host,
                               float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
                               int n_tensors, const float* hyper_host, int64_t* step_dev,
-                              float* const* planes_host, const int64_t* cols_host, void* stream) {
+                              void* const* planes_host, const int64_t* cols_host, void* stream) {
   if (kind < ADN_OPT_SGD || kind > ADN_OPT_MOMENTUM_COSINE) return fail(ADN_ERR_INVALID, "adn_opt_step: bad kind %d", kind);
   if (n_tensors < 1 || n_tensors > kMaxTensors)
     return fail(ADN_ERR_UNSUPPORTED, "adn_opt_step: n_tensors %d not in [1,%d]", n_tensors, kMaxTensors);
@@ -182,13 +177,14 @@ extern "C" int adn_opt_step_p(int kind, float* const* params_host, const float* 
     if ((need_slots >= 1 && !o.s0[t]) || (need_slots >= 2 && !o.s1[t]))
       return fail(ADN_ERR_INVALID, "adn_opt_step: slot for tensor %d is null", t);
     o.size[t] = sizes_host[t];
-    o.planes[t] = nullptr;
+    o.plane_hi[t] = nullptr;
     if (planes_host && planes_host[t]) {
       if (!cols_host || cols_host[t] <= 0 || sizes_host[t] % cols_host[t] != 0 || cols_host[t] > INT32_MAX)
         return fail(ADN_ERR_INVALID, "adn_opt_step_p: tensor %d: cols must divide its size", t);
-      o.planes[t] = planes_host[t];
+      const pl::PlaneView v = pl::plane_view(pl::format(), planes_host[t], sizes_host[t] / cols_host[t], cols_host[t]);
+      o.plane_hi[t] = v.hi;
+      o.plane_lo[t] = v.lo;
       o.cols[t] = (int)cols_host[t];
-      o.plane_lo_off[t] = pl::plane_floats(sizes_host[t] / cols_host[t], cols_host[t]);
     }
     o.chunk_start[t] = chunks;
     chunks += (int)ceil_div(sizes_host[t], kChunk);
@@ -201,6 +197,8 @@ extern "C" int adn_opt_step_p(int kind, float* const* params_host, const float* 
   o.h2 = kind >= ADN_OPT_RMSPROP ? hyper_host[2] : 0.f;
   o.h3 = kind >= ADN_OPT_RMSPROP ? hyper_host[3] : 0.f;   // MOMENTUM_COSINE (4): {lr, momentum, decay_steps, alpha}
   o.step_dev = step_dev;
+  o.fmt = pl::format();
+  o.ovf = pl::overflow_flag();
   opt_step_kernel<<<chunks, 256, 0, as_stream(stream)>>>(o);
   ADN_CHECK_LAUNCH("opt_step");
   if (step_dev) {

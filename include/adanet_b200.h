@@ -17,7 +17,9 @@
  *   - returns 0 on success, negative errno-style code otherwise, and
  *     adn_last_error() returns a thread-local human-readable message;
  *   - re-entrant across streams; the only process-global state is a cache of
- *     TMA descriptors / kernel attributes keyed by shape and pointer.
+ *     TMA descriptors keyed by (plane pointer, rows, k-blocks, majorness, format)
+ *     (csrc/planes.cu make_map), kernel attributes, and the two process-wide
+ *     settings adn_set_dense_path / adn_set_plane_format.
  *   - reductions (loss means, bias/weight gradients) use a fixed summation
  *     order: results are run-to-run deterministic.
  */
@@ -65,6 +67,10 @@ extern "C" {
 #define ADN_PATH_SIMT 1    /* CUDA-core fp32 FMA everywhere                         */
 #define ADN_PATH_TCGEN05 2 /* force tensor path; unsupported shapes return an error  */
 
+/* split-plane formats of the tcgen05 dense pipeline (adn_set_plane_format; csrc/plane_fmt.cuh) */
+#define ADN_PLANES_TF32 0 /* hi/lo TF32, 4 B per value, kind::tf32 MMAs, fp32 exponent range           */
+#define ADN_PLANES_F16 1  /* hi/lo' fp16 (lo' carries 2^11), 2 B per value, kind::f16 MMAs (default)   */
+
 /* adn_query keys */
 #define ADN_Q_VERSION 0
 #define ADN_Q_DENSE_BWD_WORKSPACE_BYTES 1 /* a=batch b=in c=out */
@@ -78,6 +84,9 @@ extern "C" {
 #define ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES 9 /* a=batch b=in c=out */
 #define ADN_Q_COLSUM_WORKSPACE_BYTES 10   /* a=rows b=cols */
 #define ADN_Q_CONV_STEM_BWD_WORKSPACE_BYTES 11 /* a=batch b=channels c=filters */
+#define ADN_Q_PLANE_FORMAT 12             /* current ADN_PLANES_* */
+#define ADN_Q_TMA_MAP_CACHE_HITS 13       /* TMA descriptor cache statistics */
+#define ADN_Q_TMA_MAP_CACHE_MISSES 14
 
 const char* adn_last_error(void);
 /* One-time, idempotent host-side initialisation (kernel attributes, driver entry
@@ -86,6 +95,14 @@ const char* adn_last_error(void);
 int adn_init(void);
 int adn_query(int key, int64_t a, int64_t b, int64_t c, int64_t* out_host);
 int adn_set_dense_path(int path);
+/* Process-wide format of every split-plane tensor the *_p entry points read and write (default ADN_PLANES_F16, or
+ * the ADN_PLANES=tf32|f16 environment variable).  Plane buffers written under one format must not be read under
+ * the other; ADN_Q_PLANES_BYTES follows the current format. */
+int adn_set_plane_format(int fmt);
+/* fp16 planes cannot hold a finite |value| >= 65520.  Every kernel that writes planes raises a sticky device flag
+ * when it meets one; this call copies the flag to *flag_host (synchronising `stream`) and optionally clears it.
+ * The caller is expected to re-run the affected work under ADN_PLANES_TF32 (core/search.py does, per iteration). */
+int adn_plane_overflow(int* flag_host, int reset, void* stream);
 
 /*
  * y[batch,out] = act(x[batch,in] @ w[in,out] + b[out])      (b may be NULL)
@@ -169,32 +186,40 @@ int adn_opt_step(int kind, float* const* params_host, const float* const* grads_
                  int n_tensors, const float* hyper_host, int64_t* step_dev, void* stream);
 
 /*
- * ---- plane-native dense pipeline (csrc/planes.cu) ---------------------------------
- * A *split-plane tensor* of a matrix T[rows, cols] is hi = rna_tf32(T) and
- * lo = rna_tf32(T - hi), each stored k-block-major [ceil(cols/32)][rows][32] (zero
- * padded in cols), hi followed by lo in one buffer of adn_query(ADN_Q_PLANES_BYTES)
- * bytes, 256 B aligned, ZERO-INITIALISED by the caller once (the K padding must stay
- * zero).  It is the operand format of the tcgen05 3xTF32 GEMM: the same planes are
- * read K-major or MN-major by TMA, so forward, dX and dW all consume them without a
- * transposed copy, and each GEMM's epilogue writes the planes its consumer reads.
+ * ---- plane-native dense pipeline (csrc/planes.cu, csrc/plane_fmt.cuh) ---------------
+ * A *split-plane tensor* of a matrix T[rows, cols] is a pair of 11-significant-bit
+ * planes, ADN_PLANES_F16: hi = fp16(T), lo' = fp16((T - hi) * 2^11), k-block = 64
+ * columns; ADN_PLANES_TF32: hi = rna_tf32(T), lo = rna_tf32(T - hi), k-block = 32
+ * columns; each stored k-block-major [ceil(cols/BK)][rows][BK] (zero padded in cols),
+ * hi followed by lo followed by sign bits [ceil(cols/32)][rows] in one buffer of
+ * adn_query(ADN_Q_PLANES_BYTES) bytes, 256 B aligned, ZERO-INITIALISED by the caller
+ * once (the K padding must stay zero).  It is the operand format of the tcgen05 GEMM
+ * (3 MMAs per product: hi*hi, hi*lo, lo*hi): the same planes are read K-major or
+ * MN-major by TMA, so forward, dX and dW all consume them without a transposed copy,
+ * and each GEMM's epilogue writes the planes its consumer reads.
+ * Gradient planes carry dz * 2^dz_log2_scale (fp16 has 5 exponent bits; the scale is
+ * a power of two chosen by the caller, 0 for TF32 planes): dxp keeps the scale, every
+ * fp32 output (dw, dx, dx_colsum) is returned un-scaled.
  * The per-layer calls below replace the same reference arithmetic as adn_dense_fwd /
  * adn_dense_bwd (adanet/examples/simple_dnn.py:72-86,103-110) for a whole subnetwork
  * whose activations never leave the plane format.
  */
-int adn_planes_split(const float* src, int64_t rows, int64_t cols, float* planes, void* stream);
-int adn_planes_merge(const float* planes, int64_t rows, int64_t cols, float* dst, void* stream);
+int adn_planes_split(const float* src, int64_t rows, int64_t cols, void* planes, void* stream);
+/* planes of src * 2^log2_scale (gradient tensors) */
+int adn_planes_split_scaled(const float* src, int64_t rows, int64_t cols, void* planes, int log2_scale, void* stream);
+int adn_planes_merge(const void* planes, int64_t rows, int64_t cols, float* dst, void* stream);
 /* y = act(x @ w + b): xp planes [batch,in], wp planes [in,out]; result as planes (yp) or
  * dense fp32 row-major (y) -- exactly one of the two is non-NULL. */
-int adn_dense_fwd_p(const float* xp, const float* wp, const float* b, float* yp, float* y,
+int adn_dense_fwd_p(const void* xp, const void* wp, const float* b, void* yp, float* y,
                     int64_t batch, int64_t in, int64_t out, int act, void* stream);
-/* Backward of one dense layer from planes: dzp planes [batch,out].
+/* Backward of one dense layer from planes: dzp planes [batch,out] holding dz * 2^dz_log2_scale.
  *   dw[in,out] (dense, nullable) = x^T dz
  *   dx = (dz w^T) * (x_relu_mask ? x > 0 : 1) as planes (dxp) or dense (dx); both may be NULL
  *   dx_colsum[in] (nullable) = column sums of dx = the bias gradient of the layer below
  * workspace: adn_query(ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES). */
-int adn_dense_bwd_p(const float* xp, const float* wp, const float* dzp, float* dxp, float* dx,
+int adn_dense_bwd_p(const void* xp, const void* wp, const void* dzp, void* dxp, float* dx,
                     float* dx_colsum, float* dw, int64_t batch, int64_t in, int64_t out,
-                    int x_relu_mask, void* workspace, int64_t workspace_bytes, void* stream);
+                    int x_relu_mask, int dz_log2_scale, void* workspace, int64_t workspace_bytes, void* stream);
 /*
  * Grouped forms: the same layer wave of several subnetworks (all candidates of an AdaNet iteration consume
  * the same minibatch, adanet/core/iteration.py:185-192) in ONE persistent launch per GEMM kind, so launch,
@@ -202,37 +227,39 @@ int adn_dense_bwd_p(const float* xp, const float* wp, const float* dzp, float* d
  * Per-op semantics are exactly adn_dense_fwd_p / adn_dense_bwd_p; ops must not alias each other's outputs.
  */
 typedef struct adn_fwd_op {
-  const float* xp;     /* planes [batch, in]  */
-  const float* wp;     /* planes [in, out]    */
+  const void* xp;      /* planes [batch, in]  */
+  const void* wp;      /* planes [in, out]    */
   const float* bias;   /* [out] or NULL       */
-  float* yp;           /* planes [batch, out] -- exactly one of yp / y */
+  void* yp;            /* planes [batch, out] -- exactly one of yp / y */
   float* y;            /* dense  [batch, out] */
   int64_t in, out;
   int32_t act;         /* ADN_ACT_* */
   int32_t reserved;
 } adn_fwd_op;
 typedef struct adn_bwd_op {
-  const float* xp;     /* planes [batch, in]  */
-  const float* wp;     /* planes [in, out]; required when dx is requested */
-  const float* dzp;    /* planes [batch, out] */
-  float* dxp;          /* planes [batch, in] or NULL */
+  const void* xp;      /* planes [batch, in]  */
+  const void* wp;      /* planes [in, out]; required when dx is requested */
+  const void* dzp;     /* planes [batch, out] of dz * 2^dz_log2_scale */
+  void* dxp;           /* planes [batch, in] or NULL (same scale as dzp) */
   float* dx;           /* dense  [batch, in] or NULL (at most one of dxp / dx) */
   float* dx_colsum;    /* [in] or NULL */
   float* dw;           /* dense [in, out] or NULL */
   int64_t in, out;
   int32_t x_relu_mask;
-  int32_t reserved;
+  int32_t dz_log2_scale;
   void* workspace;     /* adn_query(ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES, batch, in, out); one per op */
   int64_t workspace_bytes;
 } adn_bwd_op;
 int adn_dense_fwd_p_group(const adn_fwd_op* ops_host, int n, int64_t batch, void* stream);
 int adn_dense_bwd_p_group(const adn_bwd_op* ops_host, int n, int64_t batch, void* stream);
 
-/* adn_head_loss that also emits, in the same pass, dlogits as split planes (nullable) and its
- * column sums = the bias gradient of the logits layer (nullable): what the backward GEMMs consume. */
+/* adn_head_loss that also emits, in the same pass, dlogits * 2^dz_log2_scale as split planes (nullable) and the
+ * (un-scaled) column sums of dlogits = the bias gradient of the logits layer (nullable): what the backward
+ * GEMMs consume. */
 int adn_head_loss_p(int head, const float* logits, const int64_t* labels, const float* labels_f,
-                    float* loss_out, float* dlogits, float* dlogits_planes, float* dlogits_colsum,
-                    int64_t batch, int64_t dim, void* workspace, int64_t workspace_bytes, void* stream);
+                    float* loss_out, float* dlogits, void* dlogits_planes, float* dlogits_colsum,
+                    int dz_log2_scale, int64_t batch, int64_t dim, void* workspace, int64_t workspace_bytes,
+                    void* stream);
 /* out[c] = sum_r x[r,c], fixed order (bias gradient of the logits layer).
  * workspace: adn_query(ADN_Q_COLSUM_WORKSPACE_BYTES). */
 int adn_colsum(const float* x, int64_t rows, int64_t cols, float* out, void* workspace,
@@ -242,7 +269,7 @@ int adn_colsum(const float* x, int64_t rows, int64_t cols, float* out, void* wor
 int adn_opt_step_p(int kind, float* const* params_host, const float* const* grads_host,
                    float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
                    int n_tensors, const float* hyper_host, int64_t* step_dev,
-                   float* const* planes_host, const int64_t* cols_host, void* stream);
+                   void* const* planes_host, const int64_t* cols_host, void* stream);
 
 /* out[0] = sum_i |x[i]| over n elements (tf.norm(ord=1), weighted.py:573), fixed order. */
 int adn_l1_norm(const float* x, int64_t n, float* out, void* stream);
@@ -267,7 +294,7 @@ int adn_l1_grad_add(float* dw, const float* w, int64_t n, float coef, void* stre
  * height, width even; channels in {1, 3}; filters in {16, 32, 48, 64}.
  * workspace: adn_query(ADN_Q_CONV_STEM_BWD_WORKSPACE_BYTES, batch, channels, filters).
  */
-int adn_conv_stem_fwd(const float* images, const float* kernel, const float* bias, float* out_planes,
+int adn_conv_stem_fwd(const float* images, const float* kernel, const float* bias, void* out_planes,
                       uint32_t* argmax, int64_t batch, int height, int width, int channels, int filters,
                       void* stream);
 int adn_conv_stem_bwd(const float* images, const uint32_t* argmax, const float* dpooled, float* dkernel,

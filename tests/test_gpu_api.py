@@ -218,6 +218,50 @@ def test_autoensemble_linear_plus_dnn(env):
   assert np.isfinite(ev["loss"]) and ev["loss"] < max(tr["sub_loss"][0] for tr in rep.traces.values())
 
 
+def test_autoensemble_baseline_config0_matches_oracle(env):
+  """BASELINE configs[0] at its real size, end to end through the public API against the oracle:
+  AutoEnsembleEstimator over {linear 100->10, DNN 100->1000->500->100->10}, 10-class synthetic tabular data,
+  2 candidates, 1 iteration, B=1024, 50 steps (adanet/autoensemble/common.py:96-198,
+  estimator.py:177-220: logits and train op of each sub-estimator, complexity 0, default ensembler)."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  d, c, b, steps, lr = 100, 10, 1024, 50, 0.05
+  x, y = orc.make_tabular(b * steps, d, c, seed=1234)
+  cols = [graph.numeric_column("x", d)]
+  hidden = [1000, 500, 100]
+  pool = {"linear": adanet.estimators.LinearEstimator(cols, train.GradientDescentOptimizer(lr), seed=11),
+          "dnn": adanet.estimators.DNNEstimator(cols, hidden, train.GradientDescentOptimizer(lr), seed=12)}
+  est = adanet.AutoEnsembleEstimator(head=adanet.heads.MultiClassHead(c), candidate_pool=pool, max_iteration_steps=steps,
+                                     max_iterations=1, debug=True)
+
+  def input_fn():
+    for i in range(0, x.shape[0] - b + 1, b):
+      yield {"x": x[i:i + b]}, y[i:i + b]
+
+  est.train(input_fn, max_steps=steps)
+  dims = [d] + hidden + [c]
+
+  def space(t, frozen):       # dict pools are sorted by name: dnn, linear (common.py:236-243); complexity 0 (:186)
+    ws = [_glorot((dims[i], dims[i + 1]), 12 + i) for i in range(len(dims) - 1)]
+    return [orc.SubnetworkSpec("dnn", dims, 0.0, ("sgd", lr), ws=ws, bs=[np.zeros((d_,), np.float32) for d_ in dims[1:]]),
+            orc.SubnetworkSpec("linear", [d, c], 0.0, ("sgd", lr), ws=[_glorot((d, c), 11)], bs=[np.zeros((c,), np.float32)])]
+
+  want, _ = orc.run_adanet(space, x, y, b, steps, 1, orc.EnsemblerSpec(), c)
+  rep, res = est._search.reports[0], want[0]
+  assert rep.candidate_names == res.candidate_names and rep.best_index == res.best_index
+  assert rep.steps == steps
+  np.testing.assert_allclose(rep.ema_losses, res.ema_losses, atol=1e-5, rtol=0)
+  worst = 0.0
+  for name, tr in res.traces.items():
+    for f in ("sub_loss", "ens_loss", "adanet_loss", "ema"):
+      err = float(np.abs(rep.traces[name][f].astype(np.float64) - np.asarray(tr[f], np.float64)).max())
+      worst = max(worst, err)
+      assert err < 1e-5, (name, f, err)
+  print("configs[0] AutoEnsemble linear + DNN[1000,500,100]: worst per-step abs err %.3g" % worst)
+  ev = est.evaluate(input_fn, steps=2)
+  assert np.isfinite(ev["loss"]) and ev["architecture/adanet/ensembles"] in ("| dnn |", "| linear |")
+
+
 def test_resume_from_model_dir_matches_uninterrupted_run(env, tmp_path):
   """A new Estimator on the same model_dir continues from the last iteration boundary (the reference restores
   increment.ckpt-{t} + architecture-{t}.json, adanet/core/estimator.py:951-984): 2 iterations + restart + 1

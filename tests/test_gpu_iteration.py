@@ -27,6 +27,8 @@ ENS = dict(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
 def _data(kind, n, d, c, seed):
   if kind == "tabular":
     return orc.make_tabular(n, d, c, seed=seed)
+  if kind == "uniform":               # BASELINE configs[1] exactly as SURVEY.md 8d specifies it: X ~ U[0,1), uncentred
+    return orc.make_uniform(n, d, c, seed=seed)
   if kind == "uniform_centered":      # BASELINE configs[1] shape, centred so that training is well conditioned
     x, y = orc.make_uniform(n, d, c, seed=seed)
     return (x - np.float32(0.5)).astype(np.float32), y
@@ -85,6 +87,10 @@ CONFIGS = {
                    opt=("sgd", 0.01), ens=ENS, replay=[1, 2, 1]),
     "regression": dict(data=("regression", 4096, 20, 1, 8), cfgs=[(1, 32), (2, 32)], B=128, steps=40, iters=2,
                        opt=("sgd", 0.02), ens=ENS, head="mse"),
+    # BASELINE configs[2] -- the workload bench.py is quoted on: the exact 8 candidates 100->H->H->10 with the bench's
+    # optimizers, at B=4096 (B=32768: test_bench_workload_parity_full_batch)
+    "bench_shape": dict(data=("tabular", 4096 * 8, 100, 10, 1234), cfgs=[(2, h) for h in (64, 128, 192, 256, 384, 512, 768, 1024)],
+                        B=4096, steps=20, iters=1, opt=("sgd", 0.05), ens=ENS),
     # edge cases: batch not a multiple of any tile, widths 3, single candidate, 3 classes
     "ragged": dict(data=("tabular", 1000, 7, 3, 3), cfgs=[(1, 3)], B=37, steps=15, iters=2, opt=("sgd", 0.05),
                    ens=ENS),
@@ -198,6 +204,57 @@ def test_iteration_parity(built_lib, name, path):
       assert [rep.best_index for rep in r] == [1, 2, 1]   # estimator_test.py:3235-3311
   finally:
     _lib.set_dense_path(_lib.PATH_AUTO)
+
+
+@pytest.mark.gpu
+def test_bench_workload_parity_full_batch(built_lib):
+  """bench.py's configuration itself (BASELINE configs[2]: 8 candidates 100->H->H->10, H in 64..1024, B=32768, SGD .05 /
+  mixture SGD .01, lambda .01, beta .001) against the oracle: per-step losses of every candidate within 1e-5 and
+  the same winner.  5 steps (the oracle needs ~3 s per step at this size)."""
+  cfg = dict(data=("tabular", 32768 * 5, 100, 10, 1234), cfgs=[(2, h) for h in (64, 128, 192, 256, 384, 512, 768, 1024)],
+             B=32768, steps=5, iters=1, opt=("sgd", 0.05), ens=ENS)
+  o = _oracle_run(cfg)
+  r, _ = _engine_run(cfg)
+  worst = _check(o, r)
+  print("bench workload B=32768 worst per-step abs err %.3g" % worst)
+
+
+@pytest.mark.gpu
+def test_config5_sweep_at_real_widths(built_lib):
+  """BASELINE configs[4] at its real size for one iteration: 32 candidates, depth 1..8 x width {128,256,512,1024},
+  B=4096 (241 MFLOP per example summed over the candidates), 3 steps against the oracle."""
+  cfgs = [(l, h) for l in range(1, 9) for h in (128, 256, 512, 1024)]
+  cfg = dict(data=("tabular", 4096 * 3, 100, 10, 1234), cfgs=cfgs, B=4096, steps=3, iters=1, opt=("sgd", 0.01), ens=ENS)
+  o = _oracle_run(cfg)
+  r, _ = _engine_run(cfg)
+  worst = _check(o, r)
+  print("configs[4] 32-candidate sweep worst per-step abs err %.3g" % worst)
+
+
+# BASELINE configs[1] on the data SURVEY.md 8d specifies, X ~ U[0,1) UNCENTRED: every feature has mean 0.5, so the
+# first-layer pre-activations share a large common component and SGD at lr 0.05 amplifies rounding differences --
+# the oracle run against itself with a permuted feature order (a pure change of summation order) already differs by
+# ~2e-4 after 40 steps (module docstring).  1e-5 is therefore not a property of ANY fp32 implementation there; what
+# is checked is the first steps at 1e-5 (before amplification), the whole trace at a bound a few times the
+# oracle's own sensitivity, and identical selection.
+UNCENTRED_TOL = 2e-3
+
+
+@pytest.mark.gpu
+def test_config2_uncentred_data(built_lib):
+  cfg = dict(CONFIGS["config2"], data=("uniform", 8192, 784, 10, 2234))
+  o = _oracle_run(cfg)
+  perm = np.random.default_rng(0).permutation(784)
+  sens = _max_trace_diff(o, _oracle_run(cfg, perm))
+  r, _ = _engine_run(cfg)
+  worst = _check(o, r, tol=UNCENTRED_TOL)
+  early = 0.0
+  for name, tr in o[0].traces.items():
+    for f in ("sub_loss", "adanet_loss"):
+      early = max(early, float(np.abs(r[0].traces[name][f][:3].astype(np.float64) - np.asarray(tr[f][:3], np.float64)).max()))
+  print("config2 uncentred: worst %.3g (oracle self-sensitivity %.3g), first 3 steps %.3g" % (worst, sens, early))
+  assert early < TOL
+  assert worst < max(10 * sens, 1e-4)
 
 
 @pytest.mark.gpu

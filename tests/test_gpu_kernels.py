@@ -279,10 +279,13 @@ def test_conv_stem_fwd_bwd(gpu, monkeypatch, conv_path, B, H, W, CIN, F):
   _lib.check(gpu.adn_planes_merge(planes.data_ptr(), B, cols, got.data_ptr(), _sp()), "adn_planes_merge")
   got = got.cpu().numpy()
   np.testing.assert_allclose(got, np.asarray(want), rtol=0, atol=2e-6 * max(1.0, float(np.abs(want).max())))
-  # sign bits = (pooled > 0): [cols/32][B] words after the two planes
-  nkb = (cols + 31) // 32
-  plane_floats = ((B * nkb * 32 + 63) // 64) * 64
-  words = planes.view(torch.int32)[2 * plane_floats:2 * plane_floats + nkb * B].cpu().numpy().view(np.uint32).reshape(nkb, B)
+  # sign bits = (pooled > 0): [ceil(cols/32) padded to whole k-blocks][B] words after the two planes
+  f16 = _lib.plane_format() == _lib.PLANES_F16
+  bk, esz = (64, 2) if f16 else (32, 4)
+  nkbf = (cols + bk - 1) // bk
+  plane_words = ((B * nkbf * bk + 127) // 128) * 128 * esz // 4
+  nkb = nkbf * (bk // 32)
+  words = planes.view(torch.int32)[2 * plane_words:2 * plane_words + nkb * B].cpu().numpy().view(np.uint32).reshape(nkb, B)
   padded = np.zeros((B, nkb * 32), dtype=bool)
   padded[:, :cols] = got > 0
   want_words = (padded.reshape(B, nkb, 32) * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32).T

@@ -1,4 +1,5 @@
-"""GPU parity of the plane-native tcgen05 pipeline (csrc/planes.cu) through the C ABI.
+"""GPU parity of the plane-native tcgen05 pipeline (csrc/planes.cu) through the C ABI, in BOTH plane formats
+(fp16 hi/lo' planes with kind::f16 MMAs -- the default -- and the TF32 fallback, csrc/plane_fmt.cuh).
 
 Checked against fp64 NumPy restatements of the reference arithmetic
 (tf.layers.dense and its gradients, adanet/examples/simple_dnn.py:72-86,103-110)
@@ -14,24 +15,47 @@ pytestmark = pytest.mark.gpu
 TOL = 3e-6
 
 
-@pytest.fixture(scope="module")
-def env():
+@pytest.fixture(scope="module", params=["f16", "tf32"])
+def env(request):
   import torch
   import __graft_entry__ as g
   g.build()
   from adanet_b200 import _lib
   lib = _lib.load()
   _lib.check(lib.adn_init(), "adn_init")
-  return torch, _lib, lib
+  before = _lib.plane_format()
+  _lib.set_plane_format(_lib.PLANES_F16 if request.param == "f16" else _lib.PLANES_TF32)
+  _lib.plane_overflow()      # clear the sticky flag
+  yield torch, _lib, lib
+  _lib.set_plane_format(before)
 
 
-def _planes(torch, _lib, lib, a):
-  """dense numpy [r,c] -> zero-initialised plane tensor on the GPU"""
+def _layout(_lib, pl, r, c):
+  """(hi plane as float64 [nkb, r, BK], sign-bit words [nb32, r]) of a plane tensor in the current format"""
+  f16 = _lib.plane_format() == _lib.PLANES_F16
+  bk = 64 if f16 else 32
+  nkb = (c + bk - 1) // bk
+  elems = -(-(nkb * r * bk) // 128) * 128
+  raw = pl.cpu().numpy()
+  if f16:
+    hi = raw.view(np.float16)[: nkb * r * bk].reshape(nkb, r, bk)
+    off_words = 2 * elems * 2 // 4
+  else:
+    hi = raw[: nkb * r * bk].reshape(nkb, r, bk)
+    off_words = 2 * elems
+  nb32 = nkb * (bk // 32)
+  bits = raw[off_words: off_words + nb32 * r].view(np.uint32).reshape(nb32, r)
+  return hi, bits, bk
+
+
+def _planes(torch, _lib, lib, a, log2_scale=0):
+  """dense numpy [r,c] (times 2^log2_scale) -> zero-initialised plane tensor on the GPU"""
   r, c = a.shape
   nb = _lib.query(_lib.Q_PLANES_BYTES, r, c)
   pl = torch.zeros((nb // 4,), dtype=torch.float32, device="cuda")
   src = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
-  _lib.check(lib.adn_planes_split(src.data_ptr(), r, c, pl.data_ptr(), torch.cuda.current_stream().cuda_stream), "split")
+  _lib.check(lib.adn_planes_split_scaled(src.data_ptr(), r, c, pl.data_ptr(), log2_scale,
+                                         torch.cuda.current_stream().cuda_stream), "split")
   return pl
 
 
@@ -60,18 +84,17 @@ def test_split_merge_roundtrip(env, r, c):
   pl = _planes(torch, _lib, lib, a)
   back = _merge(torch, _lib, lib, pl, r, c)
   assert np.abs(back - a).max() <= 2.0 ** -22 * np.abs(a).max()
-  # padding columns of the last k-block are exact zeros, hi is TF32-representable
-  nkb = (c + 31) // 32
-  hi = pl[: nkb * r * 32].cpu().numpy().reshape(nkb, r, 32)
-  if c % 32:
-    assert (hi[-1, :, c % 32:] == 0).all()
-  assert (hi.view(np.uint32) & 0x1FFF == 0).all()
-  # sign bits [nkb][rows]: bit j of word (kb, row) <=> a[row, kb*32+j] > 0
-  n2 = 2 * (-(-(nkb * r * 32) // 64) * 64)
-  bits = pl[n2: n2 + nkb * r].cpu().numpy().view(np.uint32).reshape(nkb, r)
-  pad = np.zeros((r, nkb * 32), dtype=bool)
+  # padding columns of the last k-block are exact zeros, hi carries 11 significant bits
+  hi, bits, bk = _layout(_lib, pl, r, c)
+  if c % bk:
+    assert (hi[-1, :, c % bk:] == 0).all()
+  if hi.dtype == np.float32:
+    assert (hi.view(np.uint32) & 0x1FFF == 0).all()
+  # sign bits [cols/32][rows]: bit j of word (q, row) <=> a[row, q*32+j] > 0
+  nb32 = bits.shape[0]
+  pad = np.zeros((r, nb32 * 32), dtype=bool)
   pad[:, :c] = a > 0
-  want_bits = (pad.reshape(r, nkb, 32) * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32).T
+  want_bits = (pad.reshape(r, nb32, 32) * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32).T
   assert np.array_equal(bits, want_bits)
 
 
@@ -101,14 +124,12 @@ def test_dense_fwd_planes(env, B, I, O, act):
   yp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, O) // 4,), device="cuda")
   _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), bd.data_ptr(), yp.data_ptr(), None, B, I, O, act, sp), "fwd_p")
   assert _relerr(_merge(torch, _lib, lib, yp, B, O), exact, sc) < TOL
-  nkb = (O + 31) // 32
-  hi = yp[: nkb * B * 32].cpu().numpy().reshape(nkb, B, 32)
-  if O % 32:
-    assert (hi[-1, :, O % 32:] == 0).all()
+  hi, bits, bk = _layout(_lib, yp, B, O)
+  if O % bk:
+    assert (hi[-1, :, O % bk:] == 0).all()
   # sign bits written by the epilogue agree with the stored values
-  n2 = 2 * (-(-(nkb * B * 32) // 64) * 64)
-  bits = yp[n2: n2 + nkb * B].cpu().numpy().view(np.uint32).reshape(nkb, B)
-  want_bits = ((hi > 0) * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32)
+  pos = (hi > 0).transpose(1, 0, 2).reshape(B, -1, 32)               # [B, nb32, 32]
+  want_bits = (pos * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32).T
   assert np.array_equal(bits, want_bits)
 
 
@@ -135,7 +156,7 @@ def test_dense_bwd_planes(env, B, I, O, mask):
   dxp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, I) // 4,), device="cuda")
   cs = torch.full((I,), float("nan"), device="cuda")
   _lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), dxp.data_ptr(), None, cs.data_ptr(),
-                                 dw.data_ptr(), B, I, O, mask, ws.data_ptr(), nb, sp), "bwd_p")
+                                 dw.data_ptr(), B, I, O, mask, 0, ws.data_ptr(), nb, sp), "bwd_p")
   s_dw, s_dx = _bound(x.T, dz), _bound(dz, w.T)
   assert _relerr(dw.cpu().numpy(), dw_exact, s_dw) < TOL
   assert _relerr(_merge(torch, _lib, lib, dxp, B, I), dx_exact, s_dx) < TOL
@@ -143,7 +164,7 @@ def test_dense_bwd_planes(env, B, I, O, mask):
   # dense dx variant, no dw
   dx = torch.full((B, I), float("nan"), device="cuda")
   _lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), None, dx.data_ptr(), None, None, B, I, O,
-                                 mask, ws.data_ptr(), nb, sp), "bwd_p")
+                                 mask, 0, ws.data_ptr(), nb, sp), "bwd_p")
   assert _relerr(dx.cpu().numpy(), dx_exact, s_dx) < TOL
 
 
@@ -155,17 +176,24 @@ def test_large_batch_dw_split_k(env):
   x = np.maximum(rng.standard_normal((B, I)), 0).astype(np.float32)
   w = (rng.standard_normal((I, O)) / np.sqrt(O)).astype(np.float32)
   dz = (rng.standard_normal((B, O)) / B).astype(np.float32)
-  xp, wp, dzp = (_planes(torch, _lib, lib, a) for a in (x, w, dz))
+  # the gradient (O(1/B): below fp16's normal range) travels as dz * 2^15; dW / db come back un-scaled, dX planes
+  # keep the scale
+  LOG2 = 15
+  xp, wp = (_planes(torch, _lib, lib, a) for a in (x, w))
+  dzp = _planes(torch, _lib, lib, dz, LOG2)
   nb = _lib.query(_lib.Q_DENSE_BWD_P_WS, B, I, O)
   ws = torch.empty((nb,), dtype=torch.uint8, device="cuda")
   dw = torch.empty((I, O), device="cuda")
   cs = torch.empty((I,), device="cuda")
   dxp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, I) // 4,), device="cuda")
   _lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), dxp.data_ptr(), None, cs.data_ptr(),
-                                 dw.data_ptr(), B, I, O, 1, ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream), "bwd_p")
+                                 dw.data_ptr(), B, I, O, 1, LOG2, ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream),
+             "bwd_p")
   assert _relerr(dw.cpu().numpy(), x.astype(np.float64).T @ dz.astype(np.float64), _bound(x.T, dz)) < TOL
   dx_exact = (dz.astype(np.float64) @ w.astype(np.float64).T) * (x > 0)
   assert _relerr(cs.cpu().numpy(), dx_exact.sum(axis=0), np.abs(dx_exact).sum(axis=0).max()) < TOL
+  assert _relerr(_merge(torch, _lib, lib, dxp, B, I) / 2.0 ** LOG2, dx_exact, _bound(dz, w.T)) < TOL
+  assert not _lib.plane_overflow()
 
 
 def test_colsum_and_opt_step_planes(env):
@@ -193,53 +221,49 @@ def test_colsum_and_opt_step_planes(env):
   assert np.array_equal(wd.cpu().numpy(), want)
   assert np.array_equal(bd.cpu().numpy(), (b - np.float32(0.1) * gb).astype(np.float32))
   ref = _planes(torch, _lib, lib, want)
-  n2 = 2 * (-(-(100 * 3 * 32) // 64) * 64)      # hi + lo planes of a [100, 70] tensor (3 k-blocks); sign bits follow
+  f16 = _lib.plane_format() == _lib.PLANES_F16
+  n2 = (2 * 100 * 128 * 2 // 4) if f16 else (2 * 100 * 96)    # hi + lo planes of a [100, 70] tensor in float32 words
   assert torch.equal(wp[:n2], ref[:n2])
 
 
-def test_pair_kernel_forced_matches_single(tmp_path):
-  """The CTA-pair (cta_group::2) kernel against the single-CTA kernel on the same planes, both forced through
-  ADN_PL_PAIR (subprocesses: the knob is read once per process).  They issue the same products into the same
-  kind of two-level accumulation; only the point where the cross-term accumulator is folded in differs (per
-  128-K chunk vs once per tile), so results agree to fp32 rounding of the sums, far inside the GEMM bound."""
-  import os
-  import subprocess
-  import sys
-  code = r"""
-import numpy as np, torch, sys
-sys.path.insert(0, %r)
-import __graft_entry__ as g; g.build()
-from adanet_b200 import _lib
-lib = _lib.load(); _lib.check(lib.adn_init(), "init")
-sp = torch.cuda.current_stream().cuda_stream
-rng = np.random.default_rng(11)
-B, I, O = 1000, 300, 330
-def planes(a):
-  r, c = a.shape
-  pl = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, r, c) // 4,), device="cuda")
-  src = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
-  _lib.check(lib.adn_planes_split(src.data_ptr(), r, c, pl.data_ptr(), sp), "split"); return pl
-def merged(pl, r, c):
-  out = torch.empty((r, c), device="cuda")
-  _lib.check(lib.adn_planes_merge(pl.data_ptr(), r, c, out.data_ptr(), sp), "merge"); return out.cpu().numpy()
-x = np.maximum(rng.standard_normal((B, I)), 0).astype(np.float32); w = rng.standard_normal((I, O)).astype(np.float32) / 17
-dz = rng.standard_normal((B, O)).astype(np.float32); b = rng.standard_normal((O,)).astype(np.float32)
-xp, wp, dzp = planes(x), planes(w), planes(dz); bd = torch.as_tensor(b).cuda()
-yp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, O) // 4,), device="cuda")
-_lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), bd.data_ptr(), yp.data_ptr(), None, B, I, O, 1, sp), "fwd")
-nb = _lib.query(_lib.Q_DENSE_BWD_P_WS, B, I, O); ws = torch.empty((nb,), dtype=torch.uint8, device="cuda")
-dw = torch.empty((I, O), device="cuda"); cs = torch.empty((I,), device="cuda")
-dxp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, I) // 4,), device="cuda")
-_lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), dxp.data_ptr(), None, cs.data_ptr(), dw.data_ptr(), B, I, O, 1, ws.data_ptr(), nb, sp), "bwd")
-np.savez(sys.argv[1], y=merged(yp, B, O), dw=dw.cpu().numpy(), cs=cs.cpu().numpy(), dx=merged(dxp, B, I))
-""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-  out = []
-  for pair in ("0", "1"):
-    env = dict(os.environ, ADN_PL_PAIR=pair)
-    path = str(tmp_path / ("pair%s.npz" % pair))
-    r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stderr[-2000:]
-    out.append(np.load(path))
-  for k in ("y", "dw", "cs", "dx"):
-    a, b = out[0][k].astype(np.float64), out[1][k].astype(np.float64)
-    assert np.abs(a - b).max() <= 4e-7 * max(np.abs(a).max(), 1e-30), k
+def test_fp16_overflow_flag(env):
+  """A finite value that does not fit fp16 raises the sticky flag (and only in the fp16 format): what makes the
+  search fall back to TF32 planes for the iteration."""
+  torch, _lib, lib = env
+  a = np.ones((64, 40), dtype=np.float32)
+  _planes(torch, _lib, lib, a)
+  assert not _lib.plane_overflow()
+  a[3, 7] = 70000.0
+  _planes(torch, _lib, lib, a)
+  assert _lib.plane_overflow() == (_lib.plane_format() == _lib.PLANES_F16)
+  assert not _lib.plane_overflow()       # reading clears it
+  a[3, 7] = np.inf                       # a diverged value is not an overflow of the format
+  _planes(torch, _lib, lib, a)
+  assert not _lib.plane_overflow()
+  # the GEMM epilogue raises it too: 300 * 300 = 90000 in one output element
+  x = np.zeros((128, 64), dtype=np.float32); x[5, 0] = 300.0
+  w = np.zeros((64, 64), dtype=np.float32); w[0, 9] = 300.0
+  xp, wp = _planes(torch, _lib, lib, x), _planes(torch, _lib, lib, w)
+  yp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, 128, 64) // 4,), device="cuda")
+  _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), None, yp.data_ptr(), None, 128, 64, 64, 0,
+                                 torch.cuda.current_stream().cuda_stream), "fwd_p")
+  assert _lib.plane_overflow() == (_lib.plane_format() == _lib.PLANES_F16)
+
+
+def test_tma_descriptor_cache(env):
+  """Descriptors are encoded once per (plane, shape, majorness, format) and reused by later launches."""
+  torch, _lib, lib = env
+  rng = np.random.default_rng(1)
+  x = rng.standard_normal((256, 96)).astype(np.float32)
+  w = rng.standard_normal((96, 80)).astype(np.float32)
+  xp, wp = _planes(torch, _lib, lib, x), _planes(torch, _lib, lib, w)
+  y = torch.empty((256, 80), device="cuda")
+  sp = torch.cuda.current_stream().cuda_stream
+  _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), None, None, y.data_ptr(), 256, 96, 80, 0, sp), "fwd_p")
+  m0, h0 = _lib.query(_lib.Q_TMA_MAP_CACHE_MISSES), _lib.query(_lib.Q_TMA_MAP_CACHE_HITS)
+  for _ in range(3):
+    _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), None, None, y.data_ptr(), 256, 96, 80, 0, sp), "fwd_p")
+  assert _lib.query(_lib.Q_TMA_MAP_CACHE_MISSES) == m0
+  assert _lib.query(_lib.Q_TMA_MAP_CACHE_HITS) == h0 + 12
+
+

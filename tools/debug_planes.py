@@ -34,7 +34,7 @@ for (B, I, O) in [(128, 32, 128), (128, 128, 128), (256, 64, 256), (300, 100, 70
   ws = torch.empty((nb,), dtype=torch.uint8, device="cuda")
   dw = torch.zeros((I, O), device="cuda"); dx = torch.zeros((B, I), device="cuda")
   _lib.check(lib.adn_dense_bwd_p(xp.data_ptr(), wp.data_ptr(), dzp.data_ptr(), None, dx.data_ptr(), None, dw.data_ptr(),
-                                 B, I, O, 0, ws.data_ptr(), nb, sp), "bwd")
+                                 B, I, O, 0, 0, ws.data_ptr(), nb, sp), "bwd")
   torch.cuda.synchronize()
   ye = x.astype(np.float64) @ w
   yy = y.cpu().numpy()

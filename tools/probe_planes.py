@@ -53,11 +53,11 @@ for H in args.H:
       ("fwd L1  [B,%d]x[%d,%d] planes" % (D, D, H), 2.0 * B * D * H, lambda: lib.adn_dense_fwd_p(P(xp), P(w1p), P(b1), P(h1p), None, B, D, H, 1, sp)),
       ("fwd L2  [B,%d]x[%d,%d] planes" % (H, H, H), 2.0 * B * H * H, lambda: lib.adn_dense_fwd_p(P(h1p), P(w2p), P(b1), P(h2p), None, B, H, H, 1, sp)),
       ("fwd out [B,%d]x[%d,%d] dense " % (H, H, C), 2.0 * B * H * C, lambda: lib.adn_dense_fwd_p(P(h2p), P(wop), P(bo), None, P(logits), B, H, C, 0, sp)),
-      ("bwd out dW[%d,%d]+dX planes" % (H, C), 4.0 * B * H * C, lambda: lib.adn_dense_bwd_p(P(h2p), P(wop), P(dzo), P(dz2), None, P(db), P(dwo), B, H, C, 1, P(ws), nb, sp)),
-      ("bwd out dW only", 2.0 * B * H * C, lambda: lib.adn_dense_bwd_p(P(h2p), P(wop), P(dzo), None, None, None, P(dwo), B, H, C, 1, P(ws), nb, sp)),
-      ("bwd L2  dW[%d,%d]+dX planes" % (H, H), 4.0 * B * H * H, lambda: lib.adn_dense_bwd_p(P(h1p), P(w2p), P(dz2), P(dz1), None, P(db), P(dw2), B, H, H, 1, P(ws), nb, sp)),
-      ("bwd L2  dW only", 2.0 * B * H * H, lambda: lib.adn_dense_bwd_p(P(h1p), P(w2p), P(dz2), None, None, None, P(dw2), B, H, H, 1, P(ws), nb, sp)),
-      ("bwd L1  dW[%d,%d]" % (D, H), 2.0 * B * D * H, lambda: lib.adn_dense_bwd_p(P(xp), P(w1p), P(dz1), None, None, None, P(dw1), B, D, H, 0, P(ws), nb, sp)),
+      ("bwd out dW[%d,%d]+dX planes" % (H, C), 4.0 * B * H * C, lambda: lib.adn_dense_bwd_p(P(h2p), P(wop), P(dzo), P(dz2), None, P(db), P(dwo), B, H, C, 1, 0, P(ws), nb, sp)),
+      ("bwd out dW only", 2.0 * B * H * C, lambda: lib.adn_dense_bwd_p(P(h2p), P(wop), P(dzo), None, None, None, P(dwo), B, H, C, 1, 0, P(ws), nb, sp)),
+      ("bwd L2  dW[%d,%d]+dX planes" % (H, H), 4.0 * B * H * H, lambda: lib.adn_dense_bwd_p(P(h1p), P(w2p), P(dz2), P(dz1), None, P(db), P(dw2), B, H, H, 1, 0, P(ws), nb, sp)),
+      ("bwd L2  dW only", 2.0 * B * H * H, lambda: lib.adn_dense_bwd_p(P(h1p), P(w2p), P(dz2), None, None, None, P(dw2), B, H, H, 1, 0, P(ws), nb, sp)),
+      ("bwd L1  dW[%d,%d]" % (D, H), 2.0 * B * D * H, lambda: lib.adn_dense_bwd_p(P(xp), P(w1p), P(dz1), None, None, None, P(dw1), B, D, H, 0, 0, P(ws), nb, sp)),
   ]
   tot = 0.0
   for name, flops, fn in calls:
