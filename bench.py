@@ -15,6 +15,10 @@ Prints ONE JSON line on rank 0.  `value` = B*K / device time (CUDA events, max
 over ranks) with the dataset resident in HBM; `e2e` = same metric through
 the public adanet_b200.Estimator.train call with HOST (pinned) batches, H2D of every
 batch and a D2H read of every step's losses (an `after_run` hook) inside the timed region.
+`sustained` = the HBM-resident loop again for >= 2.5 s (power-capped steady state) with its own
+clock samples; `roofline` carries the measured cuBLAS peak of the MMA kind the kernel issues
+beside the bf16 peak of MEASURED_PEAKS.json; `cpu_baseline` = the faster of two CPU restatements
+(NumPy/OpenBLAS oracle, torch-CPU oneDNN port) on the full B=32768 minibatch.
 """
 
 import argparse
@@ -34,7 +38,37 @@ WIDTHS = (64, 128, 192, 256, 384, 512, 768, 1024)
 IN_DIM, CLASSES, BATCH = 100, 10, 32768
 DATA_ROWS = 1_000_000
 METRIC = "candidate-train examples/sec per AdaNet iteration"
-REF_SAMPLE_ROWS = 4096   # rows per step of the --impl reference arm (bounded sample)
+SUB_LR, ENS_LR, LAMBDA, BETA, DECAY = 0.05, 0.01, 0.01, 0.001, 0.9
+
+
+def make_tabular(n, d=IN_DIM, classes=CLASSES, seed=1234):
+  """SURVEY.md 8d synthetic tabular data: X ~ N(0,1) fp32 [n,d] (seed), teacher y = argmax(X@T + 0.5 eps),
+  T ~ N(0,1) [d,classes] (seed+1), labels int64.  (Same construction as the oracle's generator; restated here so
+  the product arm does not import test infrastructure.)"""
+  rng = np.random.default_rng(seed)
+  x = rng.standard_normal((n, d), dtype=np.float32)
+  rng_t = np.random.default_rng(seed + 1)
+  t = rng_t.standard_normal((d, classes), dtype=np.float32)
+  eps = rng_t.standard_normal((n, classes), dtype=np.float32)
+  y = np.argmax(x @ t + np.float32(0.5) * eps, axis=1).astype(np.int64)
+  return x, y
+
+
+def candidate_weights(iteration=0):
+  """[(name, dims, complexity, ws, bs)] of the 8 candidates 100->H->H->10: glorot-uniform kernels from
+  default_rng(1000 + 100*iteration + i), zero biases, names as simple_dnn.py:124-131 de-duplicated."""
+  out = []
+  for i, h in enumerate(WIDTHS):
+    dims = [IN_DIM, h, h, CLASSES]
+    rng = np.random.default_rng(1000 + 100 * iteration + i)
+    ws = []
+    for a, b in zip(dims[:-1], dims[1:]):
+      limit = np.sqrt(6.0 / (a + b))
+      ws.append(rng.uniform(-limit, limit, size=(a, b)).astype(np.float32))
+    bs = [np.zeros((b,), dtype=np.float32) for b in dims[1:]]
+    name = "2_layer_dnn" if i == 0 else "2_layer_dnn_w%d" % h
+    out.append((name, dims, float(np.sqrt(np.float32(2))), ws, bs))
+  return out
 
 
 def workload_name(gpus):
@@ -104,116 +138,166 @@ def load_peaks():
   return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def oracle_specs():
-  from tests import parity_util as pu
-  return [(2, h) for h in WIDTHS]
+def _cpu_arms(cores):
+  """The two CPU restatements of the reference's path on this box's host cores, each as (name, step_fn, threads):
+  the NumPy/OpenBLAS oracle (oracle/adanet_oracle.py) and the torch-CPU (oneDNN/MKL) port (oracle/torch_cpu.py),
+  both on the FULL B=32768 minibatch of the same 8-candidate workload.  bench.py's cpu_baseline / --impl reference
+  legs are the only product-side places allowed to execute oracle/ code."""
+  import torch
+  from oracle import adanet_oracle as orc
+  from oracle import torch_cpu
+  x, y = make_tabular(BATCH * 2, seed=1234)
+  cw = candidate_weights(0)
+  arms = []
+  # --- NumPy oracle
+  o_specs = [orc.SubnetworkSpec(n, d, cx, ("sgd", SUB_LR), ws=[w.copy() for w in ws], bs=[b.copy() for b in bs])
+             for n, d, cx, ws, bs in cw]
+  ens = orc.EnsemblerSpec(optimizer=("sgd", ENS_LR), adanet_lambda=LAMBDA, adanet_beta=BETA)
+  cands = orc.build_candidates(0, o_specs, [], ens, CLASSES, DECAY)
+  it_np = [0]
+
+  def step_numpy():
+    off = (it_np[0] % 2) * BATCH
+    orc.train_step(cands, [], ens, x[off:off + BATCH], y[off:off + BATCH])
+    it_np[0] += 1
+
+  arms.append(("numpy_openblas_oracle", step_numpy))
+  # --- torch CPU port
+  tc = [torch_cpu.Candidate(ws, bs, cx) for _, _, cx, ws, bs in cw]
+  xt, yt = torch.tensor(x), torch.tensor(y)
+  it_t = [0]
+
+  def step_torch():
+    off = (it_t[0] % 2) * BATCH
+    torch_cpu.train_step(tc, xt[off:off + BATCH], yt[off:off + BATCH], SUB_LR, ENS_LR, LAMBDA, BETA, DECAY)
+    it_t[0] += 1
+
+  arms.append(("torch_cpu_onednn_port", step_torch))
+  return arms
 
 
-def _best_thread_count(step_fn, cores):
-  """NumPy/OpenBLAS on a many-core host is often fastest well below the core count (oversubscription, NUMA):
-  time one step at a few thread counts and keep the best, so the CPU arm is the strongest the port can give."""
+def _pick_cpu_arm(cores):
+  """Times one step of each CPU arm at a few thread counts (NumPy/OpenBLAS is often fastest well below the core
+  count; torch follows torch.set_num_threads) and returns the fastest (name, step_fn, threads, sweep)."""
+  import torch
   try:
     from threadpoolctl import threadpool_limits
   except Exception:
-    return cores, None, {}
-  cand = sorted({c for c in (cores, 96, 64, 48, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
-  timings = {}
-  for c in cand:
-    with threadpool_limits(limits=c):
-      step_fn()                                  # warm the pools at this width
+    threadpool_limits = None
+  arms = _cpu_arms(cores)
+  cand_threads = sorted({c for c in (cores, cores // 2, 64, 32, 16) if 1 <= c <= cores}, reverse=True)
+  sweep, best = {}, None
+  for name, fn in arms:
+    for th in cand_threads:
+      if name.startswith("torch"):
+        torch.set_num_threads(th)
+        fn()
+        t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
+      elif threadpool_limits is not None:
+        with threadpool_limits(limits=th):
+          fn()
+          t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
+      else:
+        if th != cores:
+          continue
+        fn()
+        t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
+      sweep["%s@%d" % (name, th)] = round(dt, 3)
+      if best is None or dt < best[3]:
+        best = (name, fn, th, dt)
+  name, fn, th, _ = best
+
+  def run(n_steps):
+    if name.startswith("torch"):
+      torch.set_num_threads(th)
       t0 = time.perf_counter()
-      step_fn()
-      timings[c] = time.perf_counter() - t0
-  best = min(timings, key=timings.get)
-  return best, threadpool_limits, timings
+      for _ in range(n_steps):
+        fn()
+      return time.perf_counter() - t0
+    ctx = threadpool_limits(limits=th) if threadpool_limits is not None else None
+    if ctx is not None:
+      ctx.__enter__()
+    try:
+      t0 = time.perf_counter()
+      for _ in range(n_steps):
+        fn()
+      return time.perf_counter() - t0
+    finally:
+      if ctx is not None:
+        ctx.__exit__(None, None, None)
+
+  return name, run, th, sweep
 
 
 def run_reference(args):
-  """--impl reference: the CPU restatement of the reference's path (oracle port; the
-  real reference needs TensorFlow 2.1, not installable here) on all host cores."""
+  """--impl reference: the reference's own implementation of the path is TF1 graph code on the TensorFlow CPU
+  runtime (TensorFlow 2.1 is not installable here: Python 3.12, no network -- DESIGN.md section 2), so this arm
+  times its CPU restatements on all host cores -- NumPy/OpenBLAS oracle and torch-CPU (oneDNN) port, the faster
+  one -- on the SAME configuration as the GPU arm: 8 candidates, full B=32768 minibatches."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  from tests import parity_util as pu
-  from oracle import adanet_oracle as orc
   cores = os.cpu_count() or 1
-  rows = REF_SAMPLE_ROWS   # a bounded sample of the B=32768 minibatch per step, so K steps finish in minutes
-  x, y = orc.make_tabular(rows * 4, IN_DIM, CLASSES, seed=1234)
-  o_specs, _ = pu.make_specs(oracle_specs(), IN_DIM, CLASSES, 0, ("sgd", 0.05))
-  ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
-  cands = orc.build_candidates(0, o_specs, [], ens, CLASSES, 0.9)
-  it = 0
-
-  def step():
-    nonlocal it
-    off = (it % 4) * rows
-    orc.train_step(cands, [], ens, x[off:off + rows], y[off:off + rows])
-    it += 1
-
-  threads, limiter, sweep = _best_thread_count(step, cores)
-  ctx = limiter(limits=threads) if limiter is not None else None
-  if ctx is not None:
-    ctx.__enter__()
-  try:
-    for _ in range(args.warmup):
-      step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-      step()
-    dt = time.perf_counter() - t0
-  finally:
-    if ctx is not None:
-      ctx.__exit__(None, None, None)
-  val = rows * args.steps / dt
+  name, run, threads, sweep = _pick_cpu_arm(cores)
+  run(max(1, min(args.warmup, 2)))
+  steps = args.steps
+  dt = run(steps)
+  val = BATCH * steps / dt
   line = {
       "impl": "reference", "metric": METRIC, "value": val, "unit": "examples/s", "n_gpus": args.gpus,
-      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+      "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
       "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
       "config": {"workload": workload_name(args.gpus), "candidates": len(WIDTHS), "batch": BATCH},
-      "cpu_baseline": {"value": val, "unit": "examples/s", "cores": threads, "kind": "port",
-                       "sample": "%d steps, each a %d-row sample of the B=%d minibatch of the same 8-candidate "
-                                 "workload (NumPy/OpenBLAS fp32 oracle; %d host cores, best of a thread-count sweep "
-                                 "%s s/step; the TF1 reference itself is not installable: TensorFlow 2.1 absent)"
-                                 % (args.steps, rows, BATCH, cores,
-                                    {k: round(v, 3) for k, v in sorted(sweep.items())})},
+      "cpu_baseline": {"value": val, "unit": "examples/s", "cores": threads, "kind": "port", "arm": name,
+                       "sample": "%d steps of the full B=%d minibatch of the same 8-candidate workload; fastest of "
+                                 "{NumPy/OpenBLAS oracle, torch-CPU oneDNN port} x thread counts on %d host cores, "
+                                 "seconds per step: %s (the TF1 reference itself is not installable: TensorFlow 2.1 "
+                                 "absent)" % (steps, BATCH, cores, sweep)},
       "e2e": {"value": val, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
   print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_sample(seconds_budget=15.0):
-  """The oracle (CPU port of the reference's path) on all host cores, on the same bounded sample
-  per step as the --impl reference arm."""
-  from tests import parity_util as pu
-  from oracle import adanet_oracle as orc
+  """The faster CPU restatement on all host cores, full-B steps for about `seconds_budget` seconds."""
   cores = os.cpu_count() or 1
-  rows = REF_SAMPLE_ROWS
-  x, y = orc.make_tabular(rows * 4, IN_DIM, CLASSES, seed=1234)
-  o_specs, _ = pu.make_specs(oracle_specs(), IN_DIM, CLASSES, 0, ("sgd", 0.05))
-  ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
-  cands = orc.build_candidates(0, o_specs, [], ens, CLASSES, 0.9)
-  for i in range(2):   # warm-up
-    orc.train_step(cands, [], ens, x[i * rows:(i + 1) * rows], y[i * rows:(i + 1) * rows])
-  threads, limiter, sweep = _best_thread_count(lambda: orc.train_step(cands, [], ens, x[:rows], y[:rows]), cores)
-  ctx = limiter(limits=threads) if limiter is not None else None
-  if ctx is not None:
-    ctx.__enter__()
-  try:
-    n, t0 = 0, time.perf_counter()
-    while True:
-      off = (n % 4) * rows
-      orc.train_step(cands, [], ens, x[off:off + rows], y[off:off + rows])
-      n += 1
-      dt = time.perf_counter() - t0
-      if dt > seconds_budget or n >= 200:
-        break
-  finally:
-    if ctx is not None:
-      ctx.__exit__(None, None, None)
-  return {"value": rows * n / dt, "unit": "examples/s", "cores": threads, "kind": "port",
-          "sample": "%d steps (%.1f s), each a %d-row sample of the B=%d minibatch of the same 8-candidate workload, "
-                    "NumPy/OpenBLAS fp32 oracle, %d host cores, best thread count of a sweep %s s/step"
-                    % (n, dt, rows, BATCH, cores, {k: round(v, 3) for k, v in sorted(sweep.items())})}
+  name, run, threads, sweep = _pick_cpu_arm(cores)
+  per = min(sweep.values())
+  n = int(max(2, min(200, seconds_budget / max(per, 1e-3))))
+  dt = run(n)
+  return {"value": BATCH * n / dt, "unit": "examples/s", "cores": threads, "kind": "port", "arm": name,
+          "sample": "%d steps (%.1f s) of the full B=%d minibatch of the same 8-candidate workload; fastest of "
+                    "{NumPy/OpenBLAS oracle, torch-CPU oneDNN port} x thread counts on %d host cores, s/step: %s"
+                    % (n, dt, BATCH, cores, sweep)}
+
+
+def measure_cublas_peaks(torch, n=8192, reps=10):
+  """Dense tensor-core peaks of the MMA kinds this library issues, measured the way MEASURED_PEAKS.json measures
+  bf16: cuBLAS matmul n^3, best of `reps`, CUDA events.  (cuBLAS is used for this yardstick only.)"""
+  out = {}
+  old = torch.backends.cuda.matmul.allow_tf32
+  for kind in ("f16", "tf32"):
+    try:
+      if kind == "f16":
+        a = torch.randn((n, n), device="cuda", dtype=torch.float16)
+        b = torch.randn((n, n), device="cuda", dtype=torch.float16)
+      else:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn((n, n), device="cuda")
+        b = torch.randn((n, n), device="cuda")
+      best = 1e9
+      for i in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); c = a @ b; e1.record(); e1.synchronize()
+        if i >= 2:
+          best = min(best, e0.elapsed_time(e1) * 1e-3)
+      out[kind + "_tflops"] = 2.0 * n ** 3 / best / 1e12
+      del a, b, c
+    except Exception as exc:
+      out[kind + "_tflops"] = None
+      out[kind + "_error"] = repr(exc)
+  torch.backends.cuda.matmul.allow_tf32 = old
+  return out
 
 
 def measure_dominant_kernel(lib, torch, reps=20):
@@ -242,7 +326,8 @@ def measure_dominant_kernel(lib, torch, reps=20):
     e1.synchronize()
     if i >= 3:
       times.append(e0.elapsed_time(e1) * 1e-3)
-  return float(np.mean(times)), 2.0 * B * I * O, "tcgen05_3xtf32_planes"
+  fmt = "f16" if _lib.plane_format() == _lib.PLANES_F16 else "tf32"
+  return float(np.mean(times)), 2.0 * B * I * O, "tcgen05_3x%s_planes" % fmt
 
 
 def run_ours(args):
@@ -260,18 +345,17 @@ def run_ours(args):
   from adanet_b200.core import engine as eng
   from adanet_b200.core import search as srch
   from adanet_b200.distributed import exchange as ex
-  from tests import parity_util as pu
-  from oracle import adanet_oracle as orc   # data + weight generation only (host side, outside timed regions)
   lib = _lib.load()
   _lib.check(lib.adn_init(), "adn_init")
   dev = torch.device("cuda", local)
 
   # synthetic data, generated once on the host, replicated per GPU
-  x_np, y_np = orc.make_tabular(DATA_ROWS, IN_DIM, CLASSES, seed=1234)
+  x_np, y_np = make_tabular(DATA_ROWS, IN_DIM, CLASSES, seed=1234)
   x_dev = torch.as_tensor(x_np).to(dev)
   y_dev = torch.as_tensor(y_np).to(dev)
-  ens = eng.EnsemblerPlanSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
-  space = lambda t, frozen: pu.make_specs(oracle_specs(), IN_DIM, CLASSES, t, ("sgd", 0.05))[1]
+  ens = eng.EnsemblerPlanSpec(optimizer=("sgd", ENS_LR), adanet_lambda=LAMBDA, adanet_beta=BETA)
+  space = lambda t, frozen: [eng.SubnetworkPlanSpec(n, d, cx, ("sgd", SUB_LR), ws, bs, shared={"num_layers": 2})
+                             for n, d, cx, ws, bs in candidate_weights(t)]
 
   # ---------------- value: dataset resident in HBM ----------------
   s = srch.AdaNetSearch(space, ens, IN_DIM, CLASSES, BATCH, device=dev, keep_traces=False)
@@ -301,6 +385,29 @@ def run_ours(args):
   value = BATCH * args.steps / secs
   local_losses = plan.last_losses()
   assert np.isfinite(local_losses).all(), "non-finite loss in the timed region"
+  # ---------------- steady state: the same loop for >= 2.5 s (the chip reaches its power cap) ----------------
+  sustained = None
+  if not args.profile and args.sustain_seconds > 0:
+    n_sus = int(min(20000, max(args.steps, args.sustain_seconds / max(secs / args.steps, 1e-5))))
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+      sampler2.start()
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(n_sus):
+      plan.train_step(*next(batches))
+    s1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    sus_secs = ex.max_over_ranks(s0.elapsed_time(s1) * 1e-3, device=dev)
+    sustained = {"steps": n_sus, "seconds": sus_secs, "ms_per_step": sus_secs / n_sus * 1e3,
+                 "value": BATCH * n_sus / sus_secs, "unit": "examples/s",
+                 "clocks": sampler2.stop() if rank == 0 else None}
+    assert np.isfinite(plan.last_losses()).all(), "non-finite loss in the sustained region"
   rep = s.finish_iteration(secs)   # end-of-iteration all_gather + selection (outside the timed region)
   if args.profile:   # under ncu: only the in-HBM step loop (a number printed under a profiler is never a bench value)
     if rank == 0:
@@ -326,10 +433,6 @@ def run_ours(args):
 
   e2e_api, e2e_note, e2e_secs, d2h = "adanet_b200.Estimator.train", None, None, 0
   try:
-    if world > 1:
-      # under torchrun the same measurement goes through the engine-level search API (what Estimator.train drives):
-      # the Estimator path was validated against it at N=1 (equal rates) but not under NCCL in this round
-      raise RuntimeError("N > 1: engine-level API")
     import adanet_b200 as adanet
     from adanet_b200 import graph, train
 
@@ -352,7 +455,7 @@ def run_ours(args):
         return adanet.Subnetwork(last_layer=last, logits=h, complexity=self._spec.complexity)
 
       def build_subnetwork_train_op(self, subnetwork, loss, var_list, labels, iteration_step, summary, previous_ensemble):
-        return train.GradientDescentOptimizer(0.05).minimize(loss=loss, var_list=var_list)
+        return train.GradientDescentOptimizer(SUB_LR).minimize(loss=loss, var_list=var_list)
 
     class _Losses:
       last = None
@@ -364,8 +467,8 @@ def run_ours(args):
         head=adanet.heads.MultiClassHead(CLASSES),
         subnetwork_generator=adanet.subnetwork.SimpleGenerator([_WidthBuilder(sp) for sp in space(0, [])]),
         max_iteration_steps=10 ** 9, max_iterations=1,
-        ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(0.01),
-                                                                   adanet_lambda=0.01, adanet_beta=0.001)])
+        ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(ENS_LR),
+                                                                   adanet_lambda=LAMBDA, adanet_beta=BETA)])
     hook = _Losses()
     est.train(host_batches(warm), steps=warm, hooks=[hook])          # builds the plan, captures the graph
     torch.cuda.synchronize()
@@ -415,6 +518,7 @@ def run_ours(args):
   # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N=1 only for cpu) ----------------
   hbm, bf16_burst, bf16_sust, which = load_peaks()
   kt, kflops, kpath = measure_dominant_kernel(lib, torch)
+  peaks = measure_cublas_peaks(torch)
   traffic = None   # dram bytes per launch of that kernel from the committed ncu --set full capture
   try:
     with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
@@ -422,14 +526,23 @@ def run_ours(args):
   except Exception:
     pass
   achieved = kflops / kt / 1e12
+  f16 = kpath.startswith("tcgen05_3xf16")
+  kind_peak = peaks.get("f16_tflops" if f16 else "tf32_tflops")
+  plane_bytes = 2 * (2 if f16 else 4)      # hi + lo bytes per value
   roofline = {
       "bound": "tensor", "kernel": "adn_dense_fwd_p [32768,1024]x[1024,1024] bias+relu, planes in/out (%s)" % kpath,
       "achieved": achieved, "peak": bf16_burst, "unit": "TFLOP/s", "frac": achieved / bf16_burst,
-      "peak_source": "MEASURED_PEAKS.json bf16 burst (%s); algorithmic fp32 FLOPs 2*B*in*out; the tcgen05 path "
-                     "issues 3 TF32 MMAs per product (3xTF32 split for 1e-5 fp32 parity), TF32 dense peak = bf16/2"
-                     % which,
-      "issued_frac_of_tf32_peak": (3.0 * achieved / (bf16_burst / 2.0)) if kpath.startswith("tcgen05") else None,
-      "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write; algorithmic 553.6 MB of split planes)",
+      "peak_source": "MEASURED_PEAKS.json bf16 burst (%s); numerator = algorithmic fp32 FLOPs 2*B*in*out; the tcgen05 "
+                     "path issues 3 MMAs per product (hi*hi, hi*lo, lo*hi split for 1e-5 fp32 parity), so the design "
+                     "ceiling of `frac` is 1/3 with kind::f16 planes (1/6 with the TF32 fallback)" % which,
+      "mma_kind": "kind::f16" if f16 else "kind::tf32", "mmas_per_product": 3,
+      "kind_peak_measured_tflops": kind_peak, "kind_peaks_measured": peaks,
+      "issued_frac_of_kind_peak": (3.0 * achieved / kind_peak) if kind_peak else None,
+      "useful_frac_of_kind_peak": (achieved / kind_peak) if kind_peak else None,
+      "traffic": traffic,
+      "traffic_unit": "bytes/launch (ncu dram read+write); algorithmic: %.1f MB of split planes (%d B/value) = %.1f MB of "
+                      "the fp32 tensors they represent" % ((2 * BATCH * 1024 + 1024 * 1024) * plane_bytes / 1e6, plane_bytes,
+                                                           (2 * BATCH * 1024 + 1024 * 1024) * 4 / 1e6),
       "launch_seconds": kt,
   }
   cpu = cpu_baseline_sample() if world == 1 else None
@@ -445,7 +558,8 @@ def run_ours(args):
                  "candidate_examples_per_sec": value * len(WIDTHS),
                  "cuda_graph": True, "selected": rep.candidate_names[rep.best_index]},
       "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_local),
-      "roofline": roofline, "cpu_baseline": cpu,
+      "roofline": roofline, "cpu_baseline": cpu, "sustained": sustained,
+      "plane_format": "f16" if _lib.plane_format() == _lib.PLANES_F16 else "tf32",
       "useful_tflops": value * train_flops_per_example() / 1e12,
   }
   print(json.dumps(line), flush=True)
@@ -460,6 +574,8 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--profile", action="store_true", help="step loop only (for ncu captures)")
+  ap.add_argument("--sustain-seconds", type=float, default=2.5,
+                  help="length of the additional steady-state measurement (0 = skip)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

@@ -251,3 +251,26 @@ def test_cosine_decay_momentum_schedule():
   o = orc.make_optimizer(("momentum_cosine", 0.05, 0.9, 4, 0.1))
   o.apply(p, [np.ones(3, np.float32)]); o.apply(p, [np.ones(3, np.float32)])
   assert abs(float(o.lr) - 0.05 * (0.9 * 0.5 * (1 + np.cos(np.pi / 4)) + 0.1)) < 1e-8
+
+
+def test_torch_cpu_port_matches_numpy_oracle():
+  """oracle/torch_cpu.py (the oneDNN/MKL CPU arm of bench.py) restates the same step as oracle/adanet_oracle.py:
+  per-step losses of a 3-candidate width sweep agree to fp32 rounding."""
+  import torch
+  from oracle import adanet_oracle as orc
+  from oracle import torch_cpu
+  from tests import parity_util as pu
+  d, c, b, steps = 20, 5, 128, 12
+  x, y = orc.make_tabular(b * steps, d, c, seed=5)
+  cfgs = [(2, 16), (2, 48), (1, 32)]
+  ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+  o_specs, _ = pu.make_specs(cfgs, d, c, 0, ("sgd", 0.05))
+  res, _ = orc.run_adanet(lambda t, f: pu.make_specs(cfgs, d, c, t, ("sgd", 0.05))[0], x, y, b, steps, 1, ens, c)
+  cands = [torch_cpu.Candidate(s.ws, s.bs, s.complexity) for s in o_specs]
+  xt, yt = torch.tensor(x), torch.tensor(y)
+  for i in range(steps):
+    torch_cpu.train_step(cands, xt[i * b:(i + 1) * b], yt[i * b:(i + 1) * b], 0.05, 0.01, 0.01, 0.001, 0.9)
+  for cand, (name, tr) in zip(cands, res[0].traces.items()):
+    got = np.asarray(cand.trace, dtype=np.float64)
+    for j, f in enumerate(("sub_loss", "ens_loss", "adanet_loss", "ema")):
+      np.testing.assert_allclose(got[:, j], np.asarray(tr[f], dtype=np.float64), atol=2e-6, rtol=0, err_msg="%s/%s" % (name, f))
