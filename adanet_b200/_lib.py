@@ -32,14 +32,16 @@ EXPORTS = (
     "adn_counter_add", "adn_planes_split", "adn_planes_merge", "adn_dense_fwd_p", "adn_dense_bwd_p", "adn_colsum",
     "adn_opt_step_p", "adn_head_loss_p", "adn_dense_fwd_p_group", "adn_dense_bwd_p_group",
     "adn_l1_grad_add", "adn_conv_stem_fwd", "adn_conv_stem_bwd", "adn_set_plane_format", "adn_plane_overflow",
-    "adn_planes_split_scaled",
+    "adn_planes_split_scaled", "adn_head_group", "adn_head_bookkeeping", "adn_opt_step_group",
 )
 
 
 class FwdOp(ctypes.Structure):
   """adn_fwd_op (include/adanet_b200.h)"""
   _fields_ = [("xp", c_void_p), ("wp", c_void_p), ("bias", c_void_p), ("yp", c_void_p), ("y", c_void_p),
-              ("in_", c_int64), ("out", c_int64), ("act", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+              ("in_", c_int64), ("out", c_int64), ("act", ctypes.c_int32), ("reserved", ctypes.c_int32),
+              ("dropout_rate", c_float), ("dropout_seed", ctypes.c_uint32), ("dropout_layer", ctypes.c_int32),
+              ("reserved2", ctypes.c_int32), ("dropout_step_dev", c_void_p)]
 
 
 class BwdOp(ctypes.Structure):
@@ -47,7 +49,31 @@ class BwdOp(ctypes.Structure):
   _fields_ = [("xp", c_void_p), ("wp", c_void_p), ("dzp", c_void_p), ("dxp", c_void_p), ("dx", c_void_p),
               ("dx_colsum", c_void_p), ("dw", c_void_p), ("in_", c_int64), ("out", c_int64),
               ("x_relu_mask", ctypes.c_int32), ("dz_log2_scale", ctypes.c_int32), ("workspace", c_void_p),
-              ("workspace_bytes", c_int64)]
+              ("workspace_bytes", c_int64), ("dx_mul", c_float), ("reserved2", c_float)]
+
+
+class HeadOp(ctypes.Structure):
+  """adn_head_op (include/adanet_b200.h)"""
+  _fields_ = [("head", ctypes.c_int32), ("mixture_type", ctypes.c_int32), ("members_host", POINTER(c_void_p)),
+              ("n_members", ctypes.c_int32), ("reg_is_zero", ctypes.c_int32), ("w", c_void_p), ("bias", c_void_p),
+              ("gammas_host", POINTER(c_float)), ("reg_multiplier", c_float), ("dz_log2_scale", ctypes.c_int32),
+              ("labels", c_void_p), ("labels_f", c_void_p), ("out3", c_void_p), ("dw", c_void_p), ("dbias", c_void_p),
+              ("dens", c_void_p), ("ens_out", c_void_p), ("dens_planes", c_void_p), ("colsum_only", ctypes.c_int32),
+              ("reserved", ctypes.c_int32), ("workspace", c_void_p), ("workspace_bytes", c_int64)]
+
+
+class HeadBook(ctypes.Structure):
+  """adn_head_book (include/adanet_b200.h)"""
+  _fields_ = [("ema_state", c_void_p), ("out3", c_void_p), ("sub_loss", c_void_p), ("trace", c_void_p),
+              ("decay", c_float), ("capacity", ctypes.c_int32)]
+
+
+class OptOp(ctypes.Structure):
+  """adn_opt_op (include/adanet_b200.h)"""
+  _fields_ = [("kind", ctypes.c_int32), ("n_tensors", ctypes.c_int32), ("params_host", POINTER(c_void_p)),
+              ("grads_host", POINTER(c_void_p)), ("slot0_host", POINTER(c_void_p)), ("slot1_host", POINTER(c_void_p)),
+              ("sizes_host", POINTER(c_int64)), ("hyper_host", POINTER(c_float)), ("step_dev", c_void_p),
+              ("planes_host", POINTER(c_void_p)), ("cols_host", POINTER(c_int64))]
 
 
 class AdnError(RuntimeError):
@@ -100,6 +126,9 @@ def load():
   lib.adn_dense_bwd_p_group.argtypes = [POINTER(BwdOp), c_int, i64, p]
   lib.adn_opt_step_p.argtypes = [c_int, POINTER(p), POINTER(p), POINTER(p), POINTER(p), POINTER(i64), c_int,
                                  POINTER(f32), p, POINTER(p), POINTER(i64), p]
+  lib.adn_head_group.argtypes = [POINTER(HeadOp), c_int, i64, i64, p]
+  lib.adn_head_bookkeeping.argtypes = [POINTER(HeadBook), c_int, p, p]
+  lib.adn_opt_step_group.argtypes = [POINTER(OptOp), c_int, p]
   for name in EXPORTS:
     if name != "adn_last_error":
       getattr(lib, name).restype = c_int

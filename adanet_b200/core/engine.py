@@ -82,6 +82,78 @@ def new_planes(rows: int, cols: int, device) -> torch.Tensor:
   return torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, rows, cols) // 4,), dtype=torch.float32, device=device)
 
 
+def kept_indices(keep_previous, n_frozen: int) -> List[int]:
+  """Previous-ensemble members a candidate keeps: True -> all, False -> none, else the given indices (partial pruning
+  by a custom Strategy, adanet/core/ensemble_builder.py:367-388)."""
+  if keep_previous is True:
+    return list(range(n_frozen))
+  if keep_previous is False or keep_previous is None:
+    return []
+  idx = [int(i) for i in keep_previous]
+  if any(i < 0 or i >= n_frozen for i in idx) or sorted(set(idx)) != idx:
+    raise ValueError("kept previous members must be increasing indices below %d, got %r" % (n_frozen, idx))
+  return idx
+
+
+def _select_prev(prev_mixture_weights, idx: List[int]):
+  """The warm-start weights of the kept members (SCALAR [N] / VECTOR [N,C] array, or the MATRIX list)."""
+  if prev_mixture_weights is None:
+    return None
+  if isinstance(prev_mixture_weights, list):
+    return [prev_mixture_weights[i] for i in idx]
+  return np.asarray(prev_mixture_weights)[idx]
+
+
+class _GradArena:
+  """One flat fp32 buffer that hands out 64 B-aligned views: every tensor a row-sharded candidate must average across
+  its ranks (weight / bias gradients, mixture-weight gradients, the loss scalars) lives in it, so the cross-rank
+  exchange of a step is ONE all-reduce per candidate."""
+
+  def __init__(self, device, capacity: int):
+    self.buf = torch.zeros((capacity,), dtype=torch.float32, device=device)
+    self.off = 0
+
+  def __call__(self, shape) -> torch.Tensor:
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)))
+    n = int(np.prod(shape)) if shape else 1
+    if self.off + n > self.buf.numel():
+      raise RuntimeError("gradient arena too small")
+    t = self.buf[self.off:self.off + n].view(shape)
+    self.off += (n + 15) // 16 * 16
+    return t
+
+  def used(self) -> torch.Tensor:
+    return self.buf[:self.off]
+
+
+class ShardComm:
+  """The ranks that train one row-sharded candidate (distributed/exchange.sharded_placement): shard `index` of `count`.
+
+  `average_(t)` replaces t by its mean over the group, bit-identical on every member: NCCL all-reduce (AVG) on the
+  stream of the step -- captured into the step's CUDA graph -- or, when the job runs on gloo (CPU tests, several
+  ranks sharing one GPU), through host memory."""
+
+  def __init__(self, ranks: Sequence[int], my_rank: int, group):
+    self.ranks = [int(r) for r in ranks]
+    self.count = len(self.ranks)
+    self.index = self.ranks.index(int(my_rank))
+    self.group = group
+
+  @property
+  def graph_safe(self) -> bool:
+    import torch.distributed as dist
+    return dist.get_backend() == "nccl"
+
+  def average_(self, t: torch.Tensor):
+    import torch.distributed as dist
+    if dist.get_backend() == "nccl":
+      dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+    else:
+      h = t.cpu()
+      dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)
+      t.copy_(h / float(self.count))      # count is a power of two: exact
+
+
 def grad_log2_scale(batch: int) -> int:
   """Power-of-two scale of every gradient plane tensor (csrc/plane_fmt.cuh): mean-reduced losses give dlogits of
   O(1/batch), below fp16's normal range; 2^ceil(log2 batch) brings them back to O(1).  TF32 planes need none."""
@@ -115,6 +187,8 @@ class SubnetworkPlanSpec:
   # Subnetwork.last_layer is the logits tensor itself (autoensemble/common.py:115-118) rather than the activation
   # feeding the logits layer; only MATRIX mixture weights read it
   last_layer_is_logits: bool = False
+  # tf.layers.dropout after hidden layers in TRAIN mode (simple_dnn.py:80-81): per hidden layer (rate, seed) or None
+  dropout: Optional[list] = None
 
 
 @dataclass
@@ -189,6 +263,18 @@ class _Optimizer:
     if self.step_dev is not None:
       self.step_dev.copy_(torch.as_tensor(st["step"]))
 
+  def op(self, grads: List[torch.Tensor]) -> "_lib.OptOp":
+    """This optimizer's update as an adn_opt_op (adn_opt_step_group applies several in one launch).  The pointer
+    arrays it references are kept alive on `self`."""
+    self._g = _lib.ptr_array([t.data_ptr() for t in grads])
+    cast = lambda a, ty: ctypes.cast(a, ctypes.POINTER(ty)) if a is not None else None
+    return _lib.OptOp(self.kind, len(self.params), cast(self._p, ctypes.c_void_p), cast(self._g, ctypes.c_void_p),
+                      cast(self._s0, ctypes.c_void_p), cast(self._s1, ctypes.c_void_p),
+                      cast(self._sizes, ctypes.c_int64), cast(self._hyper, ctypes.c_float),
+                      self.step_dev.data_ptr() if self.step_dev is not None else None,
+                      cast(self._planes, ctypes.c_void_p) if self.planes is not None else None,
+                      cast(self._cols, ctypes.c_int64) if self.planes is not None else None)
+
   def apply(self, lib, grads: List[torch.Tensor], stream_ptr: int):
     g = _lib.ptr_array([t.data_ptr() for t in grads])
     step = self.step_dev.data_ptr() if self.step_dev is not None else None
@@ -210,8 +296,11 @@ class DenseNet:
 
   def __init__(self, name: str, dims: Sequence[int], ws, bs, complexity: float, batch: int,
                device: torch.device, iteration: int = 0, shared: Optional[dict] = None,
-               image_shape: Optional[Sequence[int]] = None):
+               image_shape: Optional[Sequence[int]] = None, dropout: Optional[list] = None):
+    """`dropout`: per hidden layer (rate, seed) or None -- applied only by `fwd_op(..., step_dev=...)`, i.e. on the
+    TRAIN-mode forward of a candidate; frozen members and evaluation replay without it (iteration.py:568-579)."""
     self.name, self.dims, self.complexity, self.iteration = name, list(dims), float(complexity), iteration
+    self.dropout = list(dropout) if dropout else None
     self.shared = shared or {}
     self.batch = batch
     self.device = device
@@ -316,13 +405,26 @@ class DenseNet:
                                             torch.cuda.current_stream(self.device).cuda_stream), "adn_planes_merge")
     return out
 
-  def fwd_op(self, i: int, xp: torch.Tensor) -> "_lib.FwdOp":
-    """Layer i as an adn_fwd_op (plane path): hidden layers write planes, the logits layer dense fp32."""
+  def fwd_op(self, i: int, xp: torch.Tensor, step_dev: Optional[torch.Tensor] = None) -> "_lib.FwdOp":
+    """Layer i as an adn_fwd_op (plane path): hidden layers write planes, the logits layer dense fp32.  With
+    `step_dev` (the plan's device step counter) the forward is the TRAIN-mode one: hidden layers with dropout draw
+    their keep mask for that step in the epilogue."""
     last = i == len(self.ws) - 1
     src = (self.stem_out if self.stem else xp) if i == 0 else self.hp[i - 1]
-    return _lib.FwdOp(src.data_ptr(), self.wps[i].data_ptr(), self.bs[i].data_ptr(),
-                      None if last else self.hp[i].data_ptr(), self.acts[i].data_ptr() if last else None,
-                      self.dims[i], self.dims[i + 1], _lib.ACT_NONE if last else _lib.ACT_RELU, 0)
+    op = _lib.FwdOp(src.data_ptr(), self.wps[i].data_ptr(), self.bs[i].data_ptr(),
+                    None if last else self.hp[i].data_ptr(), self.acts[i].data_ptr() if last else None,
+                    self.dims[i], self.dims[i + 1], _lib.ACT_NONE if last else _lib.ACT_RELU, 0)
+    d = self.dropout[i] if (self.dropout and step_dev is not None and not last and i < len(self.dropout)) else None
+    if d is not None:
+      op.dropout_rate, op.dropout_seed, op.dropout_layer = float(d[0]), int(d[1]) & 0xffffffff, i
+      op.dropout_step_dev = step_dev.data_ptr()
+    return op
+
+  def dx_mul(self, i: int) -> float:
+    """Factor on the gradient w.r.t. hidden activation i (the input of layer i + 1): 1 / (1 - rate) when it was
+    dropped out in TRAIN mode, else 1."""
+    d = self.dropout[i] if (self.dropout and 0 <= i < len(self.dropout)) else None
+    return 1.0 / (1.0 - float(d[0])) if d is not None else 1.0
 
   def forward(self, lib, x: torch.Tensor, sp: int, xp: Optional[torch.Tensor] = None):
     """x: dense fp32 minibatch; xp: its split planes (required on the plane path)."""
@@ -370,7 +472,11 @@ class EnsembleHead:
 
   def __init__(self, lib, name: str, member_nets: Sequence[DenseNet], n_prev: int, ens: EnsemblerPlanSpec, batch: int,
                logits_dim: int, head: str, decay: float, trace_capacity: int, device: torch.device,
-               prev_mixture_weights=None, prev_bias=None, sub_loss: Optional[torch.Tensor] = None):
+               prev_mixture_weights=None, prev_bias=None, sub_loss: Optional[torch.Tensor] = None, alloc=None,
+               row0: int = 0):
+    """`alloc(shape)`: where the tensors that a row-sharded candidate averages across ranks are placed (its
+    _GradArena); `row0`: first minibatch row of this head when `batch` is a row slice -- members built for the full
+    minibatch (frozen ones) are then read from that row on."""
     self.lib, self.name, self.ens = lib, name, ens
     self.batch, self.C, self.head = batch, logits_dim, _HEAD_KIND[head]
     self.member_nets = list(member_nets)
@@ -431,8 +537,9 @@ class EnsembleHead:
         self.mix_w[:n_prev] = prev.reshape((n_prev,) + tuple(self.mix_w.shape[1:]))
       if prev_bias is not None:
         self.bias.copy_(torch.as_tensor(np.ascontiguousarray(prev_bias, dtype=np.float32)).reshape(logits_dim))
-    self.d_mix_w = torch.zeros_like(self.mix_w)
-    self.d_bias = torch.zeros((logits_dim,), **f32)
+    alloc = alloc if alloc is not None else (lambda shape: torch.zeros(shape, **f32))
+    self.d_mix_w = alloc(tuple(self.mix_w.shape))
+    self.d_bias = alloc((logits_dim,))
     self.complexities = [m.complexity for m in self.member_nets]
     lam, beta = float(ens.adanet_lambda), float(ens.adanet_beta)
     if self.kind == "mean":
@@ -442,7 +549,7 @@ class EnsembleHead:
     self.gammas = [float(np.float32(beta) if lam == 0.0 else np.float32(np.float32(lam) * np.float32(c) + np.float32(beta)))
                    for c in self.complexities]
     self.reg_multiplier = 1.0 if ens.legacy_train_op else 2.0
-    self.out3 = torch.zeros((3,), **f32)
+    self.out3 = alloc((3,))
     self.ens_opt = None
     if ens.optimizer is not None and self.kind != "mean":
       if self.mix == _lib.MIX_MATRIX:
@@ -462,11 +569,16 @@ class EnsembleHead:
     if self.mix == _lib.MIX_MATRIX:
       self._members = _lib.ptr_array([t.data_ptr() for t in self.mw_logits])
     else:
-      self._members = _lib.ptr_array([m.logits.data_ptr() for m in self.member_nets])
+      self._members = _lib.ptr_array([m.logits.data_ptr() + (row0 * logits_dim * 4 if m.batch != batch else 0)
+                                      for m in self.member_nets])
+    if row0 and self.mix == _lib.MIX_MATRIX:
+      raise NotImplementedError("MATRIX mixture weights on a row-sharded candidate")
+    self.row0 = row0
     self._gammas = _lib.f32_array(self.gammas)
     # trace row = (sub_loss of the candidate's subnetwork | NaN for a head that owns none, ens_loss, adanet_loss, ema)
     self._nan = torch.full((1,), float("nan"), **f32)
     src0 = sub_loss if sub_loss is not None else self._nan
+    self._sub_loss_src = src0
     self._trace_src = _lib.ptr_array([src0.data_ptr(), self.out3.data_ptr(), self.out3.data_ptr() + 8,
                                       self.ema_state.data_ptr() + 8])
 
@@ -480,9 +592,33 @@ class EnsembleHead:
       _lib.check(lib.adn_l1_norm(self.mw[k].data_ptr(), self.mw[k].numel(), self.mw_l1.data_ptr() + 4 * k, sp),
                  "adn_l1_norm")
 
-  def enqueue(self, labels, labels_f, step_dev, sp: int, xp: Optional[torch.Tensor] = None):
+  @property
+  def groupable(self) -> bool:
+    """SCALAR / VECTOR heads run in the grouped launch of the step (adn_head_group); MATRIX heads need their own
+    plane GEMMs around the head kernel."""
+    return self.mix != _lib.MIX_MATRIX
+
+  def head_op(self, labels, labels_f) -> "_lib.HeadOp":
+    """This head as an adn_head_op: ensemble logits, loss, penalty, mixture-weight / bias gradients (steps 6-11)."""
+    train_ens = self.ens_opt is not None
+    return _lib.HeadOp(self.head, self.mix, ctypes.cast(self._members, ctypes.POINTER(ctypes.c_void_p)),
+                       len(self.member_nets), self.reg_is_zero, self.mix_w.data_ptr(), self.bias.data_ptr(),
+                       ctypes.cast(self._gammas, ctypes.POINTER(ctypes.c_float)), self.reg_multiplier, 0,
+                       labels.data_ptr() + self.row0 * 8 if labels is not None else None,
+                       labels_f.data_ptr() + self.row0 * self.C * 4 if labels_f is not None else None, self.out3.data_ptr(),
+                       self.d_mix_w.data_ptr() if train_ens else None,
+                       self.d_bias.data_ptr() if (train_ens and self.ens.use_bias) else None, None, None, None, 0, 0,
+                       self.head_ws.data_ptr(), self.head_ws_bytes)
+
+  def book(self) -> "_lib.HeadBook":
+    """EMA + trace row of this head (steps 12-13) as an adn_head_book."""
+    return _lib.HeadBook(self.ema_state.data_ptr(), self.out3.data_ptr(), self._sub_loss_src.data_ptr(), self.trace.data_ptr(),
+                         self.decay, self.trace_capacity)
+
+  def enqueue(self, labels, labels_f, step_dev, sp: int, xp: Optional[torch.Tensor] = None, bookkeeping: bool = True):
     """steps 6-13 on pre-update values: ensemble logits, loss, penalty, mixture-weight gradient and update, EMA,
-    trace.  Uses only its own scratch, so it can run beside the backward waves."""
+    trace.  Uses only its own scratch, so it can run beside the backward waves.  bookkeeping=False leaves the
+    EMA / trace row / mixture-weight update to the step's grouped launches."""
     lib, B, C = self.lib, self.batch, self.C
     lab = labels.data_ptr() if labels is not None else None
     labf = labels_f.data_ptr() if labels_f is not None else None
@@ -508,6 +644,8 @@ class EnsembleHead:
         if not self.reg_is_zero:
           _lib.check(lib.adn_l1_grad_add(self.d_mw[k].data_ptr(), self.mw[k].data_ptr(), self.mw[k].numel(),
                                          self.reg_multiplier * self.gammas[k], sp), "adn_l1_grad_add")
+    if not bookkeeping:
+      return
     _lib.check(lib.adn_ema_update(self.ema_state.data_ptr(), self.out3.data_ptr() + 8, self.decay, sp),
                "adn_ema_update")
     _lib.check(lib.adn_record_scalars(self._trace_src, 4, self.trace.data_ptr(), 4, step_dev.data_ptr(),
@@ -566,9 +704,24 @@ class CandidatePlan:
 
   def __init__(self, lib, spec: SubnetworkPlanSpec, frozen: Sequence[DenseNet], ens: EnsemblerPlanSpec,
                iteration: int, batch: int, logits_dim: int, head: str, decay: float, trace_capacity: int,
-               device: torch.device, index: int, prev_mixture_weights=None, prev_bias=None):
+               device: torch.device, index: int, prev_mixture_weights=None, prev_bias=None,
+               comm: Optional[ShardComm] = None, full_batch: Optional[int] = None):
+    """`comm`: this candidate is row-sharded -- `batch` is then the local slice (full_batch / comm.count rows starting
+    at row comm.index * batch) and every gradient / loss tensor lives in one arena averaged over comm's ranks."""
     self.lib, self.spec, self.ens, self.index = lib, spec, ens, index
     self.batch, self.C, self.head = batch, logits_dim, _HEAD_KIND[head]
+    self.comm = comm
+    self.row0 = comm.index * batch if comm is not None else 0
+    self.full_batch = full_batch if full_batch is not None else batch
+    if comm is not None:
+      if getattr(spec, "own_input", False):
+        raise NotImplementedError("a bagged subnetwork cannot be row-sharded")
+      n_par = sum(int(np.prod(np.shape(w))) + int(np.prod(np.shape(b))) for w, b in zip(spec.ws, spec.bs))
+      self.arena = _GradArena(device, n_par + 32 * (2 * len(spec.ws) + 8) + (len(frozen) + 1) * (logits_dim + 1) + 64)
+      galloc = self.arena
+    else:
+      self.arena = None
+      galloc = lambda shape: torch.empty(tuple(shape), dtype=torch.float32, device=device)
     self.name = "t{}_{}_grow_{}".format(iteration, spec.name, ens.name)   # iteration.py:633,691-693
     if ens.mixture_weight_type == "matrix" and getattr(spec, "last_layer_is_logits", False):
       # the reference would train W_k [C, C] on the logits (weighted.py:424-453 with common.py:115-118); the engine's
@@ -576,13 +729,15 @@ class CandidatePlan:
       raise NotImplementedError("MATRIX mixture weights over a subnetwork whose last_layer is its logits (%s) are not "
                                 "implemented by the B200 engine; pass last_layer_fn or use SCALAR / VECTOR" % spec.name)
     self.net = DenseNet(spec.name, spec.dims, spec.ws, spec.bs, spec.complexity, batch, device, iteration,
-                        spec.shared, spec.image_shape)
+                        spec.shared, spec.image_shape, dropout=getattr(spec, "dropout", None))
+    if self.net.dropout and not self.net.planes:
+      raise NotImplementedError("dropout runs on the plane path only")
     self.frozen = list(frozen)
     dims = self.net.dims
     f32 = dict(dtype=torch.float32, device=device)
     # gradients and backward scratch
-    self.dws = [torch.empty_like(w) for w in self.net.ws]
-    self.dbs = [torch.empty_like(b) for b in self.net.bs]
+    self.dws = [galloc(w.shape) for w in self.net.ws]
+    self.dbs = [galloc(b.shape) for b in self.net.bs]
     self.dlogits = torch.empty((batch, dims[-1]), **f32)
     hid = max(dims[1:-1]) if len(dims) > 2 else 0
     self.planes = self.net.planes
@@ -603,7 +758,9 @@ class CandidatePlan:
     ws_bytes = max(ws_bytes, _lib.query(_lib.Q_HEAD_WS, batch, logits_dim, 1))   # the subnetwork's own head loss
     self.workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
     self.ws_bytes = ws_bytes
-    self.sub_loss = torch.zeros((1,), **f32)
+    self.sub_out3 = galloc((3,)).zero_()           # {loss, -, -} of the subnetwork's own head
+    self.sub_loss = self.sub_out3[:1]
+    self._logits_ptr = _lib.ptr_array([self.net.logits.data_ptr()])
     self.bagged = bool(getattr(spec, "own_input", False))
     if self.bagged:
       if not self.planes:
@@ -618,7 +775,7 @@ class CandidatePlan:
       # conv stem: dense gradient of the pooled features (first dense layer's dX), kernel / bias gradients
       st = self.net.stem
       self.dpool = torch.empty((batch, dims[0]), **f32)
-      self.d_stem_k, self.d_stem_b = torch.empty_like(self.net.stem_k), torch.empty_like(self.net.stem_b)
+      self.d_stem_k, self.d_stem_b = galloc(self.net.stem_k.shape), galloc(self.net.stem_b.shape)
       self.stem_ws_bytes = _lib.query(_lib.Q_CONV_STEM_BWD_WS, batch, st["cin"], st["f"])
       self.stem_ws = torch.empty((self.stem_ws_bytes,), dtype=torch.uint8, device=device)
       params += [self.net.stem_k, self.net.stem_b]
@@ -632,7 +789,9 @@ class CandidatePlan:
     # the candidate's ensemble: kept previous members + this new subnetwork
     self.ehead = EnsembleHead(lib, self.name, list(frozen) + [self.net], len(frozen), ens, batch, logits_dim, head, decay,
                               trace_capacity, device, prev_mixture_weights=prev_mixture_weights, prev_bias=prev_bias,
-                              sub_loss=self.sub_loss)
+                              sub_loss=self.sub_loss, alloc=self.arena, row0=self.row0)
+    # the minibatch rows of a row-sharded candidate as its own plane tensor (split from the plan's x every step)
+    self.xp_local = new_planes(batch, self.net.in_dim, device) if (comm is not None and not self.net.stem and self.planes) else None
     self.has_head = True      # False when no strategy asked for this subnetwork's `_grow` ensemble
 
   # the head's state under the names the search / tests use
@@ -740,6 +899,15 @@ class CandidatePlan:
                                         self.dbs[len(self.net.ws) - 1].data_ptr(), self.dz_log2, self.batch, self.C,
                                         self.workspace.data_ptr(), self.ws_bytes, sp), "adn_head_loss_p")
 
+  def sub_head_op(self, labels, labels_f) -> "_lib.HeadOp":
+    """step 3 as an adn_head_op (colsum_only): subnetwork loss, dlogits (dense + scaled planes), db of the logits layer."""
+    return _lib.HeadOp(self.head, _lib.MIX_SCALAR, ctypes.cast(self._logits_ptr, ctypes.POINTER(ctypes.c_void_p)), 1, 1,
+                       None, None, None, 1.0, self.dz_log2, labels.data_ptr() + self.row0 * 8 if labels is not None else None,
+                       labels_f.data_ptr() + self.row0 * self.C * 4 if labels_f is not None else None,
+                       self.sub_out3.data_ptr(), None,
+                       self.dbs[len(self.net.ws) - 1].data_ptr(), self.dlogits.data_ptr(), None, self.dzp_out.data_ptr(),
+                       1, 0, self.workspace.data_ptr(), self.ws_bytes)
+
   def enqueue_ensemble(self, labels, labels_f, step_dev, sp: int, xp: Optional[torch.Tensor] = None):
     if self.has_head:
       self.ehead.enqueue(labels, labels_f, step_dev, sp, xp)
@@ -756,11 +924,13 @@ class CandidatePlan:
     # below a conv stem the first dense layer also produces dX: dense fp32, masked by the sign bits of the pooled
     # features (= ReLU and max-pool routing mask), which is what adn_conv_stem_bwd consumes
     dx = self.dpool if (i == 0 and net.stem) else None
+    # hidden activation i - 1 (the input of this layer) may have been dropped out: its sign bits already carry the keep
+    # mask, the 1 / (1 - rate) factor rides on dx
     return _lib.BwdOp(xin.data_ptr(), net.wps[i].data_ptr(), dzp.data_ptr(),
                       dxp.data_ptr() if dxp is not None else None, dx.data_ptr() if dx is not None else None,
                       self.dbs[i - 1].data_ptr() if i > 0 else None, self.dws[i].data_ptr(), net.dims[i],
                       net.dims[i + 1], 1 if (i > 0 or dx is not None) else 0, self.dz_log2, ws.data_ptr(),
-                      self.bwd_ws_bytes)
+                      self.bwd_ws_bytes, net.dx_mul(i - 1) if i > 0 else 0.0, 0.0)
 
   def enqueue_stem_bwd(self, x: torch.Tensor, sp: int):
     """Kernel / bias gradients of the conv stem from the pooled-feature gradient the last backward wave left."""
@@ -788,10 +958,16 @@ class IterationPlan:
                adanet_loss_decay: float = 0.9, trace_capacity: int = 4096, device: Optional[torch.device] = None,
                candidate_indices: Optional[Sequence[int]] = None, use_cuda_graph: bool = True,
                multi_stream: bool = True, prev_mixture_weights=None, prev_bias=None,
-               ensemble_candidates: Optional[Sequence[tuple]] = None):
+               ensemble_candidates: Optional[Sequence[tuple]] = None, prev_ens_name: Optional[str] = None,
+               shards: Optional[Dict[int, ShardComm]] = None):
     """`ensemble_candidates`: the candidate ensembles whose members all live on this GPU, as
-    (global_index, name, [global subnetwork indices], keep_previous); None = one `*_grow` ensemble per local
-    subnetwork (GrowStrategy).  Several ensembles may share a subnetwork (adanet/ensemble/strategy.py:79-117)."""
+    (global_index, name, [global subnetwork indices], keep_previous[, EnsemblerPlanSpec]); None = one `*_grow` ensemble
+    per local subnetwork (GrowStrategy) under `ens`.  Several ensembles may share a subnetwork
+    (adanet/ensemble/strategy.py:79-117), and several ensemblers may each build one over the same strategy candidate
+    (adanet/core/iteration.py:683-693).  `prev_ens_name`: the ensembler that built the previous iteration's winner --
+    only its own heads warm-start from `prev_mixture_weights` / `prev_bias`.
+    `shards[global candidate index]`: that candidate is row-sharded over the ranks of the ShardComm and this rank trains
+    its slice of the minibatch rows (distributed/exchange.sharded_placement)."""
     self.lib = _require_cuda()
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.iteration, self.batch, self.in_dim, self.C, self.head = iteration, batch, in_dim, logits_dim, head
@@ -802,10 +978,22 @@ class IterationPlan:
       if f.batch != batch:
         raise ValueError("frozen member %s was built for batch %d, plan uses %d" % (f.name, f.batch, batch))
     idx = list(candidate_indices) if candidate_indices is not None else list(range(len(specs)))
-    self.candidates = [CandidatePlan(self.lib, s, self.frozen, ens, iteration, batch, logits_dim, head,
+    warm = lambda e: prev_ens_name is None or prev_ens_name == e.name
+    shards = shards or {}
+    for i in idx:
+      if i in shards and batch % shards[i].count != 0:
+        raise ValueError("batch %d is not divisible by the %d row shards of candidate %d" % (batch, shards[i].count, i))
+    self.candidates = [CandidatePlan(self.lib, s, self.frozen, ens, iteration,
+                                     batch // shards[i].count if i in shards else batch, logits_dim, head,
                                      adanet_loss_decay, trace_capacity, self.device, i,
-                                     prev_mixture_weights=prev_mixture_weights, prev_bias=prev_bias)
+                                     prev_mixture_weights=prev_mixture_weights if warm(ens) else None,
+                                     prev_bias=prev_bias if warm(ens) else None, comm=shards.get(i), full_batch=batch)
                        for i, s in zip(idx, specs)]
+    self.sharded = [c for c in self.candidates if c.comm is not None]
+    if self.sharded and ensemble_candidates is not None:
+      raise NotImplementedError("row-sharded candidates with explicit ensemble candidates (Solo / All / several ensemblers)")
+    if self.sharded and not all(c.comm.graph_safe for c in self.sharded):
+      use_cuda_graph = False        # host-memory exchange (gloo) cannot be captured
     for n in list(self.frozen) + [c.net for c in self.candidates]:
       if n.in_dim != in_dim:
         raise ValueError("subnetwork %s consumes %d input values per example, the plan feeds %d" % (n.name, n.in_dim, in_dim))
@@ -818,19 +1006,23 @@ class IterationPlan:
     else:
       for c in self.candidates:
         c.has_head = False
-      for gidx, name, builders, keep_prev in ensemble_candidates:
+      for ec in ensemble_candidates:
+        gidx, name, builders, keep_prev = ec[:4]
+        e = ec[4] if len(ec) > 4 and ec[4] is not None else ens
         local = [by_index[b] for b in builders]        # KeyError = a member lives on another rank (caller's bug)
-        full_name = "t{}_{}_{}".format(iteration, name, ens.name)            # iteration.py:691-693
+        full_name = "t{}_{}_{}".format(iteration, name, e.name)              # iteration.py:691-693
         own = self.candidates[local[0]]
-        if len(local) == 1 and keep_prev and name == "{}_grow".format(own.spec.name):
+        kidx = kept_indices(keep_prev, len(self.frozen))
+        keeps_all = len(kidx) == len(self.frozen)
+        if (len(local) == 1 and keeps_all and name == "{}_grow".format(own.spec.name) and e is ens and not own.has_head):
           own.has_head = True
           self.heads.append((gidx, own.ehead, local[0]))
           continue
-        members = (list(self.frozen) if keep_prev else []) + [self.candidates[k].net for k in local]
-        h = EnsembleHead(self.lib, full_name, members, len(self.frozen) if keep_prev else 0, ens, batch, logits_dim,
+        members = [self.frozen[i] for i in kidx] + [self.candidates[k].net for k in local]
+        h = EnsembleHead(self.lib, full_name, members, len(kidx), e, batch, logits_dim,
                          head, adanet_loss_decay, trace_capacity, self.device,
-                         prev_mixture_weights=prev_mixture_weights if keep_prev else None,
-                         prev_bias=prev_bias if keep_prev else None,
+                         prev_mixture_weights=_select_prev(prev_mixture_weights, kidx) if (kidx and warm(e)) else None,
+                         prev_bias=prev_bias if (kidx and warm(e)) else None,
                          sub_loss=own.sub_loss if len(local) == 1 else None)
         self.heads.append((gidx, h, local[0]))
     self.x = torch.empty((batch, in_dim), dtype=torch.float32, device=self.device)
@@ -909,7 +1101,7 @@ class IterationPlan:
         else:
           c.net.stem_forward(lib, c.x_own, sp)
       for w in range(max(len(c.net.ws) for c in bag)):
-        ops = [c.net.fwd_op(w, c.xp_own) for c in bag if w < len(c.net.ws)]
+        ops = [c.net.fwd_op(w, c.xp_own, self.step_dev) for c in bag if w < len(c.net.ws)]
         _lib.check(lib.adn_dense_fwd_p_group((_lib.FwdOp * len(ops))(*ops), len(ops), self.batch, sp),
                    "adn_dense_fwd_p_group")
       for c in bag:
@@ -925,47 +1117,64 @@ class IterationPlan:
           c.enqueue_stem_bwd(c.x_own, sp)
         c.enqueue_sub_update(sp)
     self._split_x(sp)
-    nets = list(self.frozen) + [c.net for c in self.candidates]
-    for n in nets:
-      if n.stem:
-        n.stem_forward(lib, self.x, sp)
-    for w in range(max(len(n.ws) for n in nets)):
-      ops = [n.fwd_op(w, self.xp) for n in nets if w < len(n.ws)]
-      arr = (_lib.FwdOp * len(ops))(*ops)
-      _lib.check(lib.adn_dense_fwd_p_group(arr, len(ops), self.batch, sp), "adn_dense_fwd_p_group")
-    side = self.streams if self.multi_stream else [main] * len(self.candidates)
-    for c, s in zip(self.candidates, side):
-      if s is not main:
-        s.wait_stream(main)
-      with torch.cuda.stream(s):
-        c.enqueue_sub_loss(self.labels, self.labels_f, s.cuda_stream)
-        if s is not main:
-          ev = torch.cuda.Event()
-          ev.record(s)
-          main.wait_event(ev)          # the backward waves need every candidate's dlogits planes
-        c.enqueue_ensemble(self.labels, self.labels_f, self.step_dev, s.cuda_stream, self.xp)
-    for _, h, slot in self.heads:        # ensembles that are not a CandidatePlan's own `_grow` head
-      if any(h is c.ehead for c in self.candidates):
-        continue
-      s = side[slot]
-      with torch.cuda.stream(s):
-        h.enqueue(self.labels, self.labels_f, self.step_dev, s.cuda_stream, self.xp)
+    # a row-sharded candidate consumes its own slice of the minibatch rows
+    for c in self.sharded:
+      if c.xp_local is not None:
+        _lib.check(lib.adn_planes_split(self.x.data_ptr() + c.row0 * self.in_dim * 4, c.batch, self.in_dim,
+                                        c.xp_local.data_ptr(), sp), "adn_planes_split")
+    xp_of = lambda c: c.xp_local if c.xp_local is not None else self.xp
+    x_of = lambda c: self.x[c.row0:c.row0 + c.batch] if c.comm is not None else self.x
+    for f in self.frozen:
+      if f.stem:
+        f.stem_forward(lib, self.x, sp)
+    for c in self.candidates:
+      if c.net.stem:
+        c.net.stem_forward(lib, x_of(c), sp)
+    # layer waves: one grouped launch per wave and distinct batch size (whole candidates and frozen members run the
+    # full minibatch, row-sharded candidates their slice)
+    fwd = ([(f, self.xp, self.batch, None) for f in self.frozen] +
+           [(c.net, xp_of(c), c.batch, self.step_dev) for c in self.candidates])       # candidates: TRAIN mode (dropout)
+    for w in range(max(len(n.ws) for n, _, _, _ in fwd)):
+      for bsz in sorted({b for _, _, b, _ in fwd}, reverse=True):
+        ops = [n.fwd_op(w, xp, sd) for n, xp, b, sd in fwd if b == bsz and w < len(n.ws)]
+        if ops:
+          _lib.check(lib.adn_dense_fwd_p_group((_lib.FwdOp * len(ops))(*ops), len(ops), bsz, sp), "adn_dense_fwd_p_group")
+    # steps 3 and 6-11 of every candidate in one grouped launch (+ one finalize): the subnetwork losses (dlogits planes,
+    # logits-layer bias gradients) and every SCALAR / VECTOR candidate-ensemble head; MATRIX heads run their plane
+    # GEMMs around their own head launch
+    hops = [(c.sub_head_op(self.labels, self.labels_f), c.batch) for c in self.candidates]
+    hops += [(h.head_op(self.labels, self.labels_f), h.batch) for _, h, _ in self.heads if h.groupable]
+    for bsz in sorted({b for _, b in hops}, reverse=True):
+      ops = [o for o, b in hops if b == bsz]
+      _lib.check(lib.adn_head_group((_lib.HeadOp * len(ops))(*ops), len(ops), bsz, self.C, sp), "adn_head_group")
+    for _, h, _ in self.heads:
+      if not h.groupable:
+        h.enqueue(self.labels, self.labels_f, self.step_dev, sp, self.xp, bookkeeping=False)
     trained = [c for c in self.candidates if not c.bagged]      # bagged subnetworks already took their step
     for k in range(max([len(c.net.ws) for c in trained] or [0])):
-      ops = [c.bwd_op(k, self.xp) for c in trained if k < len(c.net.ws)]
-      arr = (_lib.BwdOp * len(ops))(*ops)
-      _lib.check(lib.adn_dense_bwd_p_group(arr, len(ops), self.batch, sp), "adn_dense_bwd_p_group")
-    for c, s in zip(self.candidates, side):
-      if c.bagged:
-        continue
-      if s is not main:
-        s.wait_stream(main)
-      with torch.cuda.stream(s):
-        if c.net.stem:
-          c.enqueue_stem_bwd(self.x, s.cuda_stream)
-        c.enqueue_sub_update(s.cuda_stream)
-    for s in self.streams if self.multi_stream else []:
-      main.wait_stream(s)
+      for bsz in sorted({c.batch for c in trained}, reverse=True):
+        ops = [c.bwd_op(k, xp_of(c)) for c in trained if c.batch == bsz and k < len(c.net.ws)]
+        if ops:
+          _lib.check(lib.adn_dense_bwd_p_group((_lib.BwdOp * len(ops))(*ops), len(ops), bsz, sp), "adn_dense_bwd_p_group")
+    for c in trained:
+      if c.net.stem:
+        c.enqueue_stem_bwd(x_of(c), sp)
+    # row-sharded candidates: ONE all-reduce (mean) per candidate of its gradient arena -- weight / bias gradients of
+    # the slice, mixture-weight gradients and the loss scalars become those of the whole minibatch, bit-identical on
+    # every rank of the candidate, so their replicas of the weights never diverge
+    for c in self.sharded:
+      c.comm.average_(c.arena.used())
+    # steps 12-13: EMA and loss-trace row of every head, one launch
+    books = [h.book() for _, h, _ in self.heads]
+    if books:
+      _lib.check(lib.adn_head_bookkeeping((_lib.HeadBook * len(books))(*books), len(books), self.step_dev.data_ptr(), sp),
+                 "adn_head_bookkeeping")
+    # steps 4-5 and 11 (apply): every optimizer of the step in one launch -- the mixture weights' (their gradients came
+    # from the heads above; nothing read the weights since) and the subnetworks'
+    oops = [h.ens_opt.op(h._ens_grads) for _, h, _ in self.heads if h.ens_opt is not None]
+    oops += [c.sub_opt.op(c._grads) for c in trained]
+    if oops:
+      _lib.check(lib.adn_opt_step_group((_lib.OptOp * len(oops))(*oops), len(oops), sp), "adn_opt_step_group")
     _lib.check(lib.adn_counter_add(self.step_dev.data_ptr(), 1, sp), "adn_counter_add")
 
   def _enqueue(self):
@@ -1045,6 +1254,8 @@ class IterationPlan:
       raise NotImplementedError("Evaluator metric %r is not computed by the B200 engine (supported: %s)" % (metric, ", ".join(EVAL_METRICS)))
     if metric == "accuracy" and self.head == "mse":
       raise ValueError("accuracy is not an evaluation metric of a regression head")
+    if self.sharded:
+      raise NotImplementedError("hold-out evaluation of row-sharded candidates: use placement='balanced' with an Evaluator")
     self.load_batch(x, y)
     sp = torch.cuda.current_stream(self.device).cuda_stream
     self._split_x(sp)
@@ -1097,10 +1308,15 @@ class IterationPlan:
     return _lib.plane_overflow(torch.cuda.current_stream(self.device).cuda_stream)
 
   # -- read-back ---------------------------------------------------------------
+  def _reports(self, h) -> bool:
+    """A row-sharded candidate's head exists on every rank of its group; only the first one reports it."""
+    c = next((c for c in self.sharded if c.ehead is h), None)
+    return c is None or c.comm.index == 0
+
   def ema_losses(self) -> List[float]:
-    """EMA adanet loss of each local candidate (candidate.py:125-129), one D2H read."""
+    """EMA adanet loss of each local candidate this rank reports (candidate.py:125-129), one D2H read."""
     torch.cuda.current_stream(self.device).synchronize()
-    return [float(h.ema_state[2].item()) for _, h, _ in self.heads]
+    return [float(h.ema_state[2].item()) for _, h, _ in self.heads if self._reports(h)]
 
   def traces(self) -> Dict[str, Dict[str, np.ndarray]]:
     n = min(self.steps_done, self.trace_capacity)

@@ -137,6 +137,13 @@ class Estimator(object):
     for key in default_ensembler_kwargs:
       del kwargs[key]
     self._placement_strategy = kwargs.pop("experimental_placement_strategy", None)
+    # B200 engine extension: how candidates map to the GPU ranks of a torchrun job -- "balanced" (whole candidates,
+    # cost-balanced), "round_robin" (i % G, the reference's RoundRobinStrategy order) or "sharded" (candidates heavier
+    # than a rank's share are trained data-parallel over several ranks, distributed/exchange.sharded_placement)
+    self._candidate_placement = kwargs.pop("candidate_placement", "balanced")
+    if self._candidate_placement == "sharded" and evaluator is not None:
+      raise ValueError("candidate_placement='sharded' evaluates candidates on their training shards only; use "
+                       "'balanced' together with an Evaluator")
     if default_ensembler_kwargs and ensemblers:
       raise ValueError("When specifying the `ensemblers` argument, the following arguments must not be given: {}".format(
           default_ensembler_kwargs.keys()))
@@ -179,11 +186,14 @@ class Estimator(object):
     return p if os.path.exists(p) else None
 
   # ------------------------------------------------------------------ engine wiring
-  def _ensembler_plan_spec(self):
+  def _ensembler_plan_specs(self):
+    """One EnsemblerPlanSpec per `ensemblers` entry: every strategy candidate is built once per ensembler
+    (adanet/core/iteration.py:683-693)."""
+    return [self._ensembler_plan_spec(e) for e in self._ensemblers]
+
+  def _ensembler_plan_spec(self, e=None):
     from adanet_b200.core import engine as eng
-    if len(self._ensemblers) != 1:
-      raise NotImplementedError("the B200 engine trains one ensembler per run (got %d)" % len(self._ensemblers))
-    e = self._ensemblers[0]
+    e = e if e is not None else self._ensemblers[0]
     if isinstance(e, ensemble_lib.MeanEnsembler):
       # mean over the candidate's NEW subnetworks only (adanet/ensemble/mean.py:92-101; previous members are
       # ignored, nothing is trained): SCALAR weights 0 for kept members, 1/n_new for the new ones
@@ -228,10 +238,18 @@ class Estimator(object):
     ecands = []
     for c in cands:     # strategy.py:26-76: (name, new builders, previous builders kept | None)
       prev = c.previous_ensemble_subnetwork_builders
-      if prev and len(prev) != len(self._member_builders):
-        raise NotImplementedError("pruning only part of the previous ensemble is not implemented by the B200 engine")
-      ecands.append(srch.EnsembleCandidate(c.name, [builders.index(b) for b in c.subnetwork_builders],
-                                           bool(prev) or not self._member_builders))
+      # ensemble_builder.py:367-388: previous members are kept, in order, when their builder is among the candidate's
+      # previous_ensemble_subnetwork_builders (and survives a single builder's deprecated prune_previous_ensemble)
+      keep = [i for i, b in enumerate(self._member_builders) if prev and b in prev]
+      if len(c.subnetwork_builders) == 1 and self._previous_ensemble is not None:
+        legacy = getattr(c.subnetwork_builders[0], "prune_previous_ensemble", None)
+        if callable(legacy):
+          logging.warning("Using an `adanet.subnetwork.Builder#prune_previous_ensemble` is deprecated. Please use a "
+                          "custom `adanet.ensemble.Strategy` instead.")
+          allowed = set(int(i) for i in legacy(self._previous_ensemble))
+          keep = [i for i in keep if i in allowed]
+      keeps = True if (len(keep) == len(self._member_builders)) else (keep if keep else False)
+      ecands.append(srch.EnsembleCandidate(c.name, [builders.index(b) for b in c.subnetwork_builders], keeps))
     self._pending_ecands = ecands
     # image features keep their [batch, H, W, C] shape for the builder; everything else is [batch, width]
     placeholders = {k: graph.placeholder(self._feature_shapes[k] if len(self._feature_shapes.get(k, ())) == 3 else w, k)
@@ -276,10 +294,15 @@ class Estimator(object):
     import dataclasses
     from adanet_b200 import train
     from adanet_b200.core import lowering
-    base = self._ensembler_plan_spec()
     fns = [getattr(b, "build_mixture_weights_train_op", None) for b in builders]
     if self._search is None:
       return
+    if len(self._ensemblers) > 1:
+      if any(callable(f) for f in fns):
+        raise NotImplementedError("the deprecated build_mixture_weights_train_op with several ensemblers is not "
+                                  "implemented by the B200 engine")
+      return
+    base = self._ensembler_plan_spec()
     if not any(callable(f) for f in fns) or base.kind == "mean":
       self._search.ens = base
       return
@@ -311,11 +334,12 @@ class Estimator(object):
     self._feature_shapes = input_utils.feature_shapes(features)
     self._in_dim = sum(widths.values())
     replay = self._replay_config.best_ensemble_indices if self._replay_config else None
-    self._search = srch.AdaNetSearch(self._search_space, self._ensembler_plan_spec(), self._in_dim,
+    self._search = srch.AdaNetSearch(self._search_space, self._ensembler_plan_specs(), self._in_dim,
                                      self._head.logits_dimension, self._batch_size, head=self._head.loss_kind,
                                      adanet_loss_decay=self._adanet_loss_decay, force_grow=self._force_grow,
                                      replay_indices=replay, keep_traces=bool(self._debug),
-                                     candidates_fn=lambda specs, n_frozen: self._pending_ecands)
+                                     candidates_fn=lambda specs, n_frozen: self._pending_ecands,
+                                     placement=self._candidate_placement)
 
   def _inflight_path(self):
     return os.path.join(self._model_dir, "iteration-inflight-rank{}.npz".format(self._config.global_id_in_cluster))
@@ -389,7 +413,8 @@ class Estimator(object):
     self._global_step = int(meta["global_step"])
     self._last_candidate_name = meta["last_candidate_name"]
     # previous_ensemble for the generator: symbolic subnetworks carrying complexity + shared (what builders read)
-    ens = self._ensemblers[0]
+    s.winner_ens_index = int(meta.get("winner_ens_index", 0))
+    ens = self._ensemblers[s.winner_ens_index]
     self._member_subnetworks, self._member_builders, ws_list = [], [], []
     mw = s.mixture_weights
     for k, m in enumerate(meta["members"]):
@@ -536,10 +561,13 @@ class Estimator(object):
       rep = s.finish_iteration(local_metric_fn=local_metric, previous_metric=prev_metric, objective_fn=ev.objective_fn)
     else:
       rep = s.finish_iteration()
-    ens = self._ensemblers[0]
+    ens = self._ensemblers[s.winner_ens_index]        # the ensembler that built the (new or kept) best ensemble
     if s.last_winner_builders is not None:
-      if not s.last_winner_keeps_previous:      # e.g. SoloStrategy: the previous ensemble's subnetworks are dropped
-        self._member_subnetworks, self._member_builders = [], []
+      # e.g. SoloStrategy drops the previous ensemble's subnetworks, a pruning Strategy keeps some of them
+      kept = getattr(s, "last_winner_kept", None)
+      if kept is not None and len(kept) != len(self._member_subnetworks):
+        self._member_subnetworks = [self._member_subnetworks[i] for i in kept]
+        self._member_builders = [self._member_builders[i] for i in kept]
       for ci in s.last_winner_builders:
         self._member_subnetworks.append(subs[ci])
         self._member_builders.append(builders[ci])
@@ -600,7 +628,7 @@ class Estimator(object):
         "batch_size": int(self._batch_size), "feature_widths": self._feature_widths,
         "architecture": [[int(t), n] for t, n in s.architecture], "replay_trace": [int(v) for v in s.replay_trace],
         "prev_best_ema": None if s.prev_best_ema is None else float(s.prev_best_ema),
-        "last_candidate_name": self._last_candidate_name,
+        "last_candidate_name": self._last_candidate_name, "winner_ens_index": int(s.winner_ens_index),
         "members": [{"name": m.name, "iteration": int(m.iteration), "complexity": float(m.complexity),
                      "dims": [int(d) for d in m.dims], "shared": m.shared,
                      "image_shape": list(m.image_shape) if m.stem else None} for m in s.frozen],
@@ -628,7 +656,7 @@ class Estimator(object):
     if s is None or not s.frozen:
       raise ValueError("no trained ensemble yet: train at least one AdaNet iteration before evaluate/predict")
     if self._eval_plan is None:
-      self._eval_plan = eng.EnsembleEvalPlan(s.frozen, s.mixture_weights, s.bias, s.ens, s.head, s.batch, s.C, s.device)
+      self._eval_plan = eng.EnsembleEvalPlan(s.frozen, s.mixture_weights, s.bias, s.winner_ens, s.head, s.batch, s.C, s.device)
     return self._eval_plan
 
   def architecture_string(self):

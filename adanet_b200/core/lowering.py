@@ -53,8 +53,18 @@ def _trace_dense_chain(logits: graph.Tensor) -> Tuple[List[graph.Tensor], graph.
   """Walks logits back to the input layer; returns (dense ops first->last, input tensor)."""
   chain = []
   t = logits
+  pending_dropout = None
   while True:
-    if t.op == "dense":
+    if t.op == "dropout":
+      # tf.layers.dropout on a hidden activation: belongs to the dense layer that produces it
+      if pending_dropout is not None or not chain:
+        raise NotImplementedError("dropout must follow a hidden dense+relu layer (one dropout per layer)")
+      pending_dropout = (t.attrs["rate"], t.attrs["seed"])
+      t = t.inputs[0]
+    elif t.op == "dense":
+      if pending_dropout is not None:
+        t.attrs["dropout_after"] = pending_dropout
+        pending_dropout = None
       chain.append(t)
       t = t.inputs[0]
     elif t.op == "relu":
@@ -65,6 +75,8 @@ def _trace_dense_chain(logits: graph.Tensor) -> Tuple[List[graph.Tensor], graph.
       inner.attrs["activation"] = "relu"
       t = inner
     elif t.op in ("input_layer", "placeholder", "flatten"):
+      if pending_dropout is not None:
+        raise NotImplementedError("dropout on the input features is not implemented by the B200 engine")
       break
     else:
       raise NotImplementedError(
@@ -109,6 +121,8 @@ def lower_subnetwork(builder, sub: subnetwork_lib.Subnetwork, variables: List[gr
   for d in chain[:-1]:
     if d.attrs.get("activation") != "relu":
       raise NotImplementedError("hidden layers must use relu")
+  if chain[-1].attrs.get("dropout_after") is not None:
+    raise NotImplementedError("dropout on the logits is not implemented by the B200 engine")
   stem, image_shape = None, None
   if inp.op == "flatten":
     stem, images = _trace_conv_stem(inp)
@@ -124,7 +138,7 @@ def lower_subnetwork(builder, sub: subnetwork_lib.Subnetwork, variables: List[gr
   # last_layer must be the tensor feeding the logits layer (or the logits themselves)
   ll = sub.last_layer
   if ll is not chain[-1].inputs[0] and ll is not sub.logits:
-    if not (isinstance(ll, graph.Tensor) and ll.op == "relu" and ll.inputs[0] is chain[-1].inputs[0]):
+    if not (isinstance(ll, graph.Tensor) and ll.op in ("relu", "dropout") and ll.inputs[0] is chain[-1].inputs[0]):
       raise NotImplementedError("last_layer must be the input of the logits layer (or the logits)")
   layers = ([stem] if stem is not None else []) + chain     # a conv stem's HWIO kernel / bias lead the lists
   ws = [np.array(d.attrs["kernel"].value, dtype=np.float32) for d in layers]
@@ -148,6 +162,8 @@ def lower_subnetwork(builder, sub: subnetwork_lib.Subnetwork, variables: List[gr
   # which tensor MATRIX mixture weights multiply (weighted.py:449): the logits themselves for sub-estimator builders
   # (autoensemble/common.py:115-118), the penultimate activation for simple_dnn-style builders
   spec.last_layer_is_logits = ll is sub.logits and len(chain) >= 1 and ll is not chain[-1].inputs[0]
+  drops = [d.attrs.get("dropout_after") for d in chain[:-1]]
+  spec.dropout = drops if any(v is not None for v in drops) else None
   return spec
 
 

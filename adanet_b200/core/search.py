@@ -71,7 +71,10 @@ class EnsembleCandidate:
   previous ensemble's subnetworks are kept."""
   name: str
   builders: List[int]
-  keep_previous: bool = True
+  # True: the whole previous ensemble, False: none of it, or the indices of the previous members to keep (partial
+  # pruning by a custom Strategy, adanet/core/ensemble_builder.py:367-388)
+  keep_previous: object = True
+  ens_index: int = 0          # which of the search's ensemblers builds it (adanet/core/iteration.py:683-693)
 
 
 def strategy_candidates(strategies: Sequence[str], builder_names: Sequence[str]) -> List[EnsembleCandidate]:
@@ -99,15 +102,20 @@ class AdaNetSearch:
                use_cuda_graph: bool = True, multi_stream: bool = True, keep_traces: bool = True,
                trace_capacity: int = 4096, placement: str = "balanced", strategies: Sequence[str] = ("grow",),
                candidates_fn: Optional[Callable] = None):
-    self.search_space, self.ens = search_space, ensembler
+    # one EnsemblerPlanSpec or a list: every strategy candidate is built once per ensembler (iteration.py:683-693)
+    self.search_space = search_space
+    self.ensemblers = list(ensembler) if isinstance(ensembler, (list, tuple)) else [ensembler]
+    if len({e.name for e in self.ensemblers}) != len(self.ensemblers):
+      raise ValueError("ensemblers must have distinct names")
+    self.winner_ens_index = 0          # ensembler of the current best ensemble
     self.in_dim, self.C, self.batch, self.head = in_dim, logits_dim, batch_size, head
     self.decay, self.force_grow = adanet_loss_decay, force_grow
     self.replay_indices = list(replay_indices) if replay_indices is not None else None
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.use_cuda_graph, self.multi_stream = use_cuda_graph, multi_stream
     self.keep_traces, self.trace_capacity = keep_traces, trace_capacity
-    if placement not in ("balanced", "round_robin"):
-      raise ValueError("placement must be 'balanced' or 'round_robin'")
+    if placement not in ("balanced", "round_robin", "sharded"):
+      raise ValueError("placement must be 'balanced', 'round_robin' or 'sharded'")
     self.placement = placement
     # candidate ensembles of an iteration: candidates_fn(specs, n_frozen) -> [EnsembleCandidate], or the named strategies
     self.strategies = tuple(strategies)
@@ -121,6 +129,22 @@ class AdaNetSearch:
     self.bias: Optional[np.ndarray] = None
     self.reports: List[IterationReport] = []
     self.plan: Optional[eng.IterationPlan] = None
+
+  @property
+  def ens(self) -> eng.EnsemblerPlanSpec:
+    """The first (for single-ensembler searches: the only) ensembler."""
+    return self.ensemblers[0]
+
+  @ens.setter
+  def ens(self, value: eng.EnsemblerPlanSpec):
+    if len(self.ensemblers) != 1:
+      raise NotImplementedError("replacing the ensembler of a multi-ensembler search")
+    self.ensemblers = [value]
+
+  @property
+  def winner_ens(self) -> eng.EnsemblerPlanSpec:
+    """The ensembler that built the current best ensemble (its mixture weights are `self.mixture_weights`)."""
+    return self.ensemblers[self.winner_ens_index]
 
   # -- iteration assembly ------------------------------------------------------
   def build_iteration(self) -> eng.IterationPlan:
@@ -138,6 +162,8 @@ class AdaNetSearch:
            else strategy_candidates(self.strategies, names))
     if not ecs:
       raise ValueError("the ensemble strategies produced no candidate")
+    if len(self.ensemblers) > 1:      # strategy candidates x ensemblers, strategy-candidate major (iteration.py:683-693)
+      ecs = [EnsembleCandidate(c.name, list(c.builders), c.keep_previous, j) for c in ecs for j in range(len(self.ensemblers))]
     self._ecands = ecs
     # subnetwork -> rank.  Subnetworks read by the same candidate ensemble (e.g. AllStrategy) must share a GPU --
     # splitting them would need the member logits gathered every step -- so the units of placement
@@ -146,18 +172,38 @@ class AdaNetSearch:
     costs = [sum(a * b for a, b in zip(s.dims[:-1], s.dims[1:])) +
              (s.image_shape[0] * s.image_shape[1] * int(np.prod(np.shape(s.ws[0])[:3])) * np.shape(s.ws[0])[3]
               if s.image_shape is not None else 0) for s in specs]
-    self._owners = ex.component_owners(costs, [c.builders for c in ecs], g, self.placement)
-    mine = ex.owned_indices(len(specs), r, g, self._owners)
+    default_grow = (len(self.ensemblers) == 1 and len(ecs) == len(specs) and all(
+        c.keep_previous is True and c.builders == [i] and c.name == "{}_grow".format(specs[i].name) for i, c in enumerate(ecs)))
+    shards = {}
+    shardable = (self.placement == "sharded" and g > 1 and default_grow and self.ens.mixture_weight_type != "matrix"
+                 and not any(getattr(s, "own_input", False) for s in specs))
+    if shardable:
+      # row-sharded placement (distributed/exchange.sharded_placement): a candidate heavier than a rank's fair share is
+      # trained data-parallel by several ranks; its first rank reports it at the end of the iteration
+      ranks = ex.sharded_placement(costs, g, self.batch)
+      self._owners = [rk[0] for rk in ranks]
+      mine = [i for i, rk in enumerate(ranks) if r in rk]
+      for i, rk in enumerate(ranks):        # every rank creates every group, in the same order (new_group is collective)
+        if len(rk) > 1:
+          grp = ex.subgroup(rk)
+          if r in rk:
+            shards[i] = eng.ShardComm(rk, r, grp)
+      self._shard_ranks = ranks
+    else:
+      self._owners = ex.component_owners(costs, [c.builders for c in ecs], g,
+                                         "balanced" if self.placement == "sharded" else self.placement)
+      mine = ex.owned_indices(len(specs), r, g, self._owners)
+      self._shard_ranks = [[o] for o in self._owners]
     self._ec_owners = [self._owners[c.builders[0]] for c in ecs]
-    default_grow = (len(ecs) == len(specs) and all(
-        c.keep_previous and c.builders == [i] and c.name == "{}_grow".format(specs[i].name) for i, c in enumerate(ecs)))
-    local = None if default_grow else [(j, c.name, list(c.builders), c.keep_previous)
+    local = None if default_grow else [(j, c.name, list(c.builders), c.keep_previous, self.ensemblers[c.ens_index])
                                        for j, c in enumerate(ecs) if self._ec_owners[j] == r]
+    prev_ens_name = self.winner_ens.name if (self.frozen and len(self.ensemblers) > 1) else None
     self.plan = eng.IterationPlan(self.iteration, [specs[i] for i in mine], self.frozen, self.ens, self.batch,
                                   self.in_dim, self.C, self.head, self.decay, self.trace_capacity, self.device,
                                   candidate_indices=mine, use_cuda_graph=self.use_cuda_graph,
                                   multi_stream=self.multi_stream, prev_mixture_weights=self.mixture_weights,
-                                  prev_bias=self.bias, ensemble_candidates=local)
+                                  prev_bias=self.bias, ensemble_candidates=local, prev_ens_name=prev_ens_name,
+                                  shards=shards)
     return self.plan
 
   def train_iteration(self, batches: Iterator, steps: int, on_step=None) -> float:
@@ -188,9 +234,13 @@ class AdaNetSearch:
     specs).  Returns True in that case.  One all_reduce of a flag per iteration, outside the step."""
     from adanet_b200 import _lib
     plan = self.plan
-    if plan is None or plan.fmt != _lib.PLANES_F16:
+    if plan is None or plan.fmt != _lib.PLANES_F16 or plan.xp is None:      # TF32 planes / fp32 SIMT path: nothing to fall back from
       return False
-    flag = ex.max_over_ranks(1.0 if plan.plane_overflow() else 0.0, device=self.device) > 0.0
+    # the input split, the optimizer and the head raise the sticky flag; a GEMM result beyond the range becomes Inf in
+    # the planes and shows up as a non-finite loss, which is treated the same way (a candidate that truly diverged
+    # costs one re-run of the iteration, after which the process stays on TF32 planes)
+    local = plan.plane_overflow() or not all(np.isfinite(v) for v in plan.ema_losses())
+    flag = ex.max_over_ranks(1.0 if local else 0.0, device=self.device) > 0.0
     if not flag:
       return False
     import logging
@@ -216,8 +266,7 @@ class AdaNetSearch:
     g = ex.world()
     local = plan.ema_losses() if local_metric_fn is None else list(local_metric_fn(plan))
     new_losses = ex.gather_candidate_losses(local, k, device=self.device, owners=ec_owners)
-    ens_name = self.ens.name
-    names = ["t{}_{}_{}".format(t, c.name, ens_name) for c in ecs]
+    names = ["t{}_{}_{}".format(t, c.name, self.ensemblers[c.ens_index].name) for c in ecs]
     losses = list(new_losses)
     if t > 0:
       names = ["previous_ensemble"] + names
@@ -236,18 +285,26 @@ class AdaNetSearch:
     traces = plan.traces() if self.keep_traces else None
     self.last_winner_index = None
     self.last_winner_builders, self.last_winner_keeps_previous = None, True
+    self.last_winner_kept = None
     if t > 0 and best == 0:
       pass   # previous ensemble kept; nothing grows
     else:
       ci = best - (1 if t > 0 else 0)
       ec = ecs[ci]
       owner = ec_owners[ci]
-      matrix = self.ens.mixture_weight_type == "matrix"
-      kept = list(self.frozen) if ec.keep_previous else []
+      w_ens = self.ensemblers[ec.ens_index]
+      matrix = w_ens.mixture_weight_type == "matrix"
+      kept_idx = eng.kept_indices(ec.keep_previous, len(self.frozen))
+      kept = [self.frozen[i] for i in kept_idx]
       # materialise the winner's new subnetworks on every rank for frozen replay
       if ex.rank() == owner:
         head = next(h for gidx, h, _ in plan.heads if gidx == ci)
         new_members = [next(c for c in plan.candidates if c.index == b).net for b in ec.builders]
+        for k, m in enumerate(new_members):
+          if m.batch != self.batch:      # trained on a row slice: frozen replay needs full-minibatch buffers
+            ws_, bs_ = m.numpy_params()
+            new_members[k] = eng.DenseNet(m.name, m.dims, ws_, bs_, m.complexity, self.batch, self.device, t, m.shared,
+                                          m.image_shape)
         mix_ws, bias = head.mixture_weight_tensors(), head.bias
       else:
         new_members = [eng.DenseNet(specs[b].name, specs[b].dims, specs[b].ws, specs[b].bs, specs[b].complexity,
@@ -258,7 +315,7 @@ class AdaNetSearch:
           mix_ws = [torch.empty((m.last_layer_dim, self.C), dtype=torch.float32, device=self.device)
                     for m in kept + new_members]
         else:
-          wshape = (n_members,) if self.ens.mixture_weight_type == "scalar" else (n_members, self.C)
+          wshape = (n_members,) if w_ens.mixture_weight_type == "scalar" else (n_members, self.C)
           mix_ws = [torch.empty(wshape, dtype=torch.float32, device=self.device)]
         bias = torch.empty((self.C,), dtype=torch.float32, device=self.device)
       ex.broadcast_tensors([t_ for m in new_members for t_ in m.all_params()] + mix_ws + [bias], src=owner)
@@ -266,11 +323,13 @@ class AdaNetSearch:
         for m in new_members:
           m.refresh_planes()   # their planes were split from the (pre-broadcast) initial weights
       self.frozen = kept + new_members
-      self.architecture = (self.architecture if ec.keep_previous else []) + [(t, specs[b].name) for b in ec.builders]
+      self.architecture = [self.architecture[i] for i in kept_idx] + [(t, specs[b].name) for b in ec.builders]
       self.prev_best_ema = ema_all[ci]
       self.last_winner_index = ec.builders[-1]
-      self.last_winner_builders, self.last_winner_keeps_previous = list(ec.builders), ec.keep_previous
+      self.last_winner_builders, self.last_winner_keeps_previous = list(ec.builders), ec.keep_previous is not False
+      self.last_winner_kept = list(kept_idx)
       self.last_winner_name = ec.name
+      self.winner_ens_index = ec.ens_index
       # SCALAR [N] / VECTOR [N,C] array, or the list of N [D_k,C] matrices (MATRIX)
       self.mixture_weights = ([w.cpu().numpy().copy() for w in mix_ws] if matrix else mix_ws[0].cpu().numpy().copy())
       self.bias = bias.cpu().numpy().copy()

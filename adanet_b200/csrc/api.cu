@@ -54,6 +54,7 @@ int dense_path() {
 
 int64_t head_workspace_bytes_public(int64_t batch, int64_t dim, int64_t members);
 int heads_init();
+int heads_group_init();
 
 }  // namespace adn
 
@@ -65,6 +66,8 @@ extern "C" int adn_init(void) {
   static std::atomic<int> done{0};
   if (done.load()) return ADN_OK;
   int rc = heads_init();
+  if (rc) return rc;
+  rc = heads_group_init();
   if (rc) return rc;
   rc = pl::init();
   if (rc) return rc;
@@ -231,6 +234,14 @@ extern "C" int adn_dense_fwd_p_group(const adn_fwd_op* ops, int n, int64_t batch
     if (ops[i].act != ADN_ACT_NONE && ops[i].act != ADN_ACT_RELU)
       return fail(ADN_ERR_INVALID, "adn_dense_fwd_p_group: op %d: bad act %d", i, ops[i].act);
     o[i] = pl::FwdOp{ops[i].xp, ops[i].wp, ops[i].bias, ops[i].yp, ops[i].y, ops[i].in, ops[i].out, ops[i].act};
+    if (ops[i].dropout_rate != 0.f) {
+      if (!(ops[i].dropout_rate > 0.f && ops[i].dropout_rate < 1.f) || !ops[i].yp || !ops[i].dropout_step_dev)
+        return fail(ADN_ERR_INVALID, "adn_dense_fwd_p_group: op %d: dropout needs 0 < rate < 1, planes out and a step counter", i);
+      o[i].dropout_rate = ops[i].dropout_rate;
+      o[i].dropout_seed = ops[i].dropout_seed;
+      o[i].dropout_layer = ops[i].dropout_layer;
+      o[i].dropout_step = ops[i].dropout_step_dev;
+    }
   }
   return pl::dense_fwd_group(pl::format(), o, n, batch, as_stream(stream));
 }
@@ -250,6 +261,7 @@ extern "C" int adn_dense_bwd_p_group(const adn_bwd_op* ops, int n, int64_t batch
       return fail(ADN_ERR_INVALID, "adn_dense_bwd_p_group: op %d: bad dz_log2_scale", i);
     o[i] = pl::BwdOp{p.xp, p.wp, p.dzp, p.dxp, p.dx, p.dx_colsum, p.dw, p.in, p.out, p.x_relu_mask, p.dz_log2_scale,
                      p.workspace, p.workspace_bytes};
+    if (p.dx_mul != 0.f) o[i].dx_mul = p.dx_mul;
   }
   return pl::dense_bwd_group(pl::format(), o, n, batch, as_stream(stream));
 }

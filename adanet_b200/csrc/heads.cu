@@ -10,6 +10,8 @@
 //   adanet_loss              adanet/core/ensemble_builder.py:423-426
 //   mixture-weight gradient  adanet/ensemble/weighted.py:606-617
 //   EMA                      adanet/core/candidate.py:117-129
+#include <algorithm>
+
 #include "common.cuh"
 #include "plane_fmt.cuh"
 
@@ -82,15 +84,13 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, i
 // read).  All reductions are shuffle trees in a fixed order (no serial loops over rows, no atomics).
 // smem layout (floats): mem[n_members][kRows*dim] | ens[kRows*dim] | wred[kRows/32 * max(dim, n_members)]
 template <int CT>   // CT > 0: logits dimension known at compile time (loops unroll, row offsets fold); 0: runtime
-__global__ void __launch_bounds__(kRows)
-ensemble_head_kernel(const __grid_constant__ HeadParams p) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void head_body(const HeadParams& p, float* smem, const int cta) {
   const int C = CT > 0 ? CT : p.dim, N = p.n_members;
   float* mem = smem;
   float* ens = smem + (size_t)N * kRows * C;
   float* wred = ens + kRows * C;        // [kRows/32][max(C, N)] warp partials
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * kRows;
+  const int64_t r0 = (int64_t)cta * kRows;
   const int rows = (int)min((int64_t)kRows, p.batch - r0);
   const int valid = rows * C;           // flat elements of this CTA's slab
   const size_t base = (size_t)r0 * C;
@@ -159,7 +159,7 @@ ensemble_head_kernel(const __grid_constant__ HeadParams p) {
   } else {
     for (int c = 0; c < C; ++c) e[c] = 0.f;
   }
-  float* part = p.part + blockIdx.x;                   // output j of this CTA lives at part[j * n_cta]
+  float* part = p.part + cta;                          // output j of this CTA lives at part[j * n_cta]
   const size_t ps = (size_t)p.n_cta;
   {
     const float t = block_sum(loss_r, wred, tid);     // (contains the barrier that publishes every row's g)
@@ -243,6 +243,28 @@ ensemble_head_kernel(const __grid_constant__ HeadParams p) {
   }
 }
 
+template <int CT>
+__global__ void __launch_bounds__(kRows)
+ensemble_head_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ __align__(16) float smem[];
+  head_body<CT>(p, smem, blockIdx.x);
+}
+
+// Grouped form: blockIdx.y selects one of up to kMaxGroup independent heads over the same minibatch -- the
+// subnetwork losses and the candidate-ensemble heads of every candidate of the GPU in ONE launch (they only read
+// logits the forward waves have produced), instead of two launches per candidate on side streams.
+static constexpr int kMaxGroup = 24;
+struct HeadGroup {
+  HeadParams p[kMaxGroup];
+  int n;
+};
+template <int CT>
+__global__ void __launch_bounds__(kRows)
+ensemble_head_group_kernel(const __grid_constant__ HeadGroup g) {
+  extern __shared__ __align__(16) float smem[];
+  head_body<CT>(g.p[blockIdx.y], smem, blockIdx.x);
+}
+
 // Fixed-order reduction of the per-CTA partials + regulariser + adanet loss.
 // First level for many CTAs: block j sums the n_cta partials of output j (coalesced, fixed order) into out[j].
 __global__ void __launch_bounds__(256)
@@ -263,8 +285,7 @@ head_partials_kernel(const float* __restrict__ part, float* __restrict__ out, in
   }
 }
 
-__global__ void __launch_bounds__(256)
-ensemble_finalize_kernel(const __grid_constant__ HeadParams p, const float* __restrict__ part, int n_cta) {
+__device__ __forceinline__ void finalize_body(const HeadParams& p, const float* __restrict__ part, int n_cta) {
   __shared__ float s_loss, s_reg;
   const int C = p.dim;
   const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : C;
@@ -320,7 +341,45 @@ ensemble_finalize_kernel(const __grid_constant__ HeadParams p, const float* __re
   }
 }
 
-__global__ void ema_update_kernel(float* state, const float* loss, float decay) {
+__global__ void __launch_bounds__(256)
+ensemble_finalize_kernel(const __grid_constant__ HeadParams p, const float* __restrict__ part, int n_cta) {
+  finalize_body(p, part, n_cta);
+}
+__global__ void __launch_bounds__(256)
+ensemble_finalize_group_kernel(const __grid_constant__ HeadGroup g) {
+  const HeadParams& p = g.p[blockIdx.x];
+  finalize_body(p, p.part, p.n_cta);
+}
+
+__device__ __forceinline__ void ema_update(float* state, const float* loss, float decay);
+// Per-step bookkeeping of every candidate ensemble in one launch (thread j = head j): zero-debiased EMA of its
+// adanet loss (candidate.py:117-129) and its row of the loss trace {sub_loss, ens_loss, adanet_loss, ema}
+// (iteration.py:961-996 reports the same scalars through hooks).
+struct BookEntry {
+  float* ema_state;        // {biased, n, value}
+  const float* out3;       // {loss, reg, adanet_loss} of the head
+  const float* sub_loss;   // subnetwork loss (or a NaN constant)
+  float* trace;            // [capacity][4]
+  float decay;
+  int capacity;
+};
+struct BookGroup {
+  BookEntry e[64];
+  int n;
+};
+__global__ void head_bookkeeping_kernel(const __grid_constant__ BookGroup g, const int64_t* step) {
+  const int j = threadIdx.x;
+  if (j >= g.n) return;
+  const BookEntry& e = g.e[j];
+  ema_update(e.ema_state, e.out3 + 2, e.decay);
+  float* row = e.trace + (size_t)(*step % e.capacity) * 4;
+  row[0] = *e.sub_loss;
+  row[1] = e.out3[0];
+  row[2] = e.out3[2];
+  row[3] = e.ema_state[2];
+}
+
+__device__ __forceinline__ void ema_update(float* state, const float* loss, float decay) {
   // candidate.py:117-129 -> assign_moving_average(zero_debias=True) [TF]
   float biased = state[0], n = state[1];
   const float x = *loss;
@@ -331,6 +390,7 @@ __global__ void ema_update_kernel(float* state, const float* loss, float decay) 
   state[1] = n;
   state[2] = biased / factor;
 }
+__global__ void ema_update_kernel(float* state, const float* loss, float decay) { ema_update(state, loss, decay); }
 
 __global__ void __launch_bounds__(1024) l1_norm_kernel(const float* x, int64_t n, float* out) {
   __shared__ float sm[1024];
@@ -516,5 +576,128 @@ extern "C" int adn_l1_norm(const float* x, int64_t n, float* out, void* stream) 
   if (!x || !out || n < 0) return fail(ADN_ERR_INVALID, "adn_l1_norm: bad argument");
   l1_norm_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, out);
   ADN_CHECK_LAUNCH("l1_norm");
+  return ADN_OK;
+}
+
+
+// ---- grouped heads (include/adanet_b200.h: adn_head_group / adn_head_bookkeeping) ----
+namespace adn {
+template <int CT>
+static void launch_head_group(const HeadGroup& g, int n_cta, size_t smem, cudaStream_t st) {
+  ensemble_head_group_kernel<CT><<<dim3((unsigned)n_cta, (unsigned)g.n), kRows, smem, st>>>(g);
+}
+int heads_group_init() {
+#define ADN_HEADG_ATTR(CT) \
+  ADN_CUDA(cudaFuncSetAttribute(ensemble_head_group_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+  ADN_HEADG_ATTR(0); ADN_HEADG_ATTR(1); ADN_HEADG_ATTR(2); ADN_HEADG_ATTR(3); ADN_HEADG_ATTR(4); ADN_HEADG_ATTR(10);
+  ADN_HEADG_ATTR(16);
+#undef ADN_HEADG_ATTR
+  return ADN_OK;
+}
+}  // namespace adn
+
+extern "C" int adn_head_group(const adn_head_op* ops, int n, int64_t batch, int64_t dim, void* stream) {
+  if (n < 0 || (n > 0 && !ops)) return fail(ADN_ERR_INVALID, "adn_head_group: bad ops");
+  if (batch <= 0 || dim <= 0 || dim > kMaxDim) return fail(ADN_ERR_INVALID, "adn_head_group: bad batch/dim");
+  const int n_cta = (int)ceil_div(batch, kRows);
+  const int fmt = pl::format();
+  for (int i0 = 0; i0 < n; i0 += kMaxGroup) {
+    const int m = std::min(kMaxGroup, n - i0);
+    HeadGroup g{};
+    g.n = m;
+    size_t smem = 0;
+    bool single_path = n_cta > 512;          // very large batches: two-level finalize of the single-head path
+    for (int i = 0; i < m; ++i) {
+      const adn_head_op& o = ops[i0 + i];
+      HeadParams& p = g.p[i];
+      if (!o.members_host || !o.out3 || !o.workspace) return fail(ADN_ERR_INVALID, "adn_head_group: op %d: null pointer", i0 + i);
+      if (o.head < 0 || o.head > 2 || o.mixture_type < 0 || o.mixture_type > 2)
+        return fail(ADN_ERR_INVALID, "adn_head_group: op %d: bad head / mixture type", i0 + i);
+      if (o.n_members < 1 || o.n_members > kMaxMembers)
+        return fail(ADN_ERR_UNSUPPORTED, "adn_head_group: op %d: n_members %d not in [1,%d]", i0 + i, o.n_members, kMaxMembers);
+      if (o.mixture_type == ADN_MIX_MATRIX && o.dw) return fail(ADN_ERR_INVALID, "adn_head_group: op %d: dw must be NULL for MATRIX", i0 + i);
+      if (!o.reg_is_zero && !o.gammas_host) return fail(ADN_ERR_INVALID, "adn_head_group: op %d: gammas missing", i0 + i);
+      if (o.head == ADN_HEAD_SOFTMAX_XENT ? o.labels == nullptr : o.labels_f == nullptr)
+        return fail(ADN_ERR_INVALID, "adn_head_group: op %d: labels missing", i0 + i);
+      if (o.dz_log2_scale < -60 || o.dz_log2_scale > 60) return fail(ADN_ERR_INVALID, "adn_head_group: op %d: bad dz_log2_scale", i0 + i);
+      for (int k = 0; k < o.n_members; ++k) {
+        if (!o.members_host[k]) return fail(ADN_ERR_INVALID, "adn_head_group: op %d: member %d is null", i0 + i, k);
+        p.members[k] = o.members_host[k];
+        p.gammas[k] = o.gammas_host ? o.gammas_host[k] : 0.f;
+      }
+      p.n_members = o.n_members;
+      p.head = o.head;
+      p.mixture = o.mixture_type;
+      p.w = o.w;
+      p.bias = o.bias;
+      p.labels = o.labels;
+      p.labels_f = o.labels_f;
+      p.dens = o.dens;
+      p.ens_out = o.ens_out;
+      if (o.dens_planes) {
+        p.densp = pl::plane_view(fmt, o.dens_planes, batch, dim);
+        p.dens_scale = ldexpf(1.0f, o.dz_log2_scale);
+        p.dens_nkb = (int)ceil_div(dim, pl::fmt_bk(fmt));
+        p.ovf = pl::overflow_flag();
+      }
+      p.batch = batch;
+      p.dim = (int)dim;
+      p.colsum_only = o.colsum_only ? 1 : 0;
+      p.want_grads = (o.dw || o.dbias) ? 1 : 0;
+      p.reg_is_zero = o.colsum_only ? 1 : o.reg_is_zero;
+      p.reg_multiplier = o.reg_multiplier;
+      p.out3 = o.out3;
+      p.dw = o.colsum_only ? nullptr : o.dw;
+      p.dbias = o.dbias;
+      const int wdim = (p.mixture == ADN_MIX_SCALAR) ? 1 : p.dim;
+      p.n_out = 1 + p.dim + p.n_members * wdim;
+      if (o.workspace_bytes < head_workspace_bytes(batch, dim, o.n_members))
+        return fail(ADN_ERR_WORKSPACE, "adn_head_group: op %d: workspace %lld < %lld bytes", i0 + i, (long long)o.workspace_bytes,
+                    (long long)head_workspace_bytes(batch, dim, o.n_members));
+      p.part = reinterpret_cast<float*>(o.workspace);
+      p.n_cta = n_cta;
+      smem = std::max(smem, head_smem_bytes(p.dim, p.n_members));
+    }
+    if (smem > 227 * 1024) return fail(ADN_ERR_UNSUPPORTED, "adn_head_group: members x dim does not fit shared memory");
+    if (single_path) {
+      for (int i = 0; i < m; ++i) {
+        const adn_head_op& o = ops[i0 + i];
+        int rc = run_head(g.p[i], o.workspace, o.workspace_bytes, as_stream(stream));
+        if (rc) return rc;
+      }
+      continue;
+    }
+    cudaStream_t st = as_stream(stream);
+    switch ((int)dim) {
+      case 1: launch_head_group<1>(g, n_cta, smem, st); break;
+      case 2: launch_head_group<2>(g, n_cta, smem, st); break;
+      case 3: launch_head_group<3>(g, n_cta, smem, st); break;
+      case 4: launch_head_group<4>(g, n_cta, smem, st); break;
+      case 10: launch_head_group<10>(g, n_cta, smem, st); break;
+      case 16: launch_head_group<16>(g, n_cta, smem, st); break;
+      default: launch_head_group<0>(g, n_cta, smem, st); break;
+    }
+    ADN_CHECK_LAUNCH("ensemble_head_group");
+    ensemble_finalize_group_kernel<<<m, 256, 0, st>>>(g);
+    ADN_CHECK_LAUNCH("ensemble_finalize_group");
+  }
+  return ADN_OK;
+}
+
+extern "C" int adn_head_bookkeeping(const adn_head_book* books, int n, const int64_t* step_dev, void* stream) {
+  if (n < 0 || (n > 0 && !books) || !step_dev) return fail(ADN_ERR_INVALID, "adn_head_bookkeeping: bad argument");
+  for (int i0 = 0; i0 < n; i0 += 64) {
+    const int m = std::min(64, n - i0);
+    BookGroup g{};
+    g.n = m;
+    for (int i = 0; i < m; ++i) {
+      const adn_head_book& b = books[i0 + i];
+      if (!b.ema_state || !b.out3 || !b.sub_loss || !b.trace || b.capacity < 1)
+        return fail(ADN_ERR_INVALID, "adn_head_bookkeeping: entry %d: bad argument", i0 + i);
+      g.e[i] = BookEntry{b.ema_state, b.out3, b.sub_loss, b.trace, b.decay, b.capacity};
+    }
+    head_bookkeeping_kernel<<<1, 64, 0, as_stream(stream)>>>(g, step_dev);
+    ADN_CHECK_LAUNCH("head_bookkeeping");
+  }
   return ADN_OK;
 }

@@ -17,24 +17,28 @@
 
 namespace adn {
 
-static constexpr int kMaxTensors = 32;
-static constexpr int kChunk = 4096;  // elements per CTA
+static constexpr int kMaxTensors = 32;     // per optimizer (ABI)
+static constexpr int kMaxGroupTensors = 96; // per launch
+static constexpr int kMaxGroupOpts = 32;    // optimizers per launch
+static constexpr int kChunk = 4096;         // elements per CTA
 
+// One launch applies several optimizers (adn_opt_step_group): tensor t belongs to optimizer opt[t].
 struct OptParams {
-  float* p[kMaxTensors];
-  const float* g[kMaxTensors];
-  float* s0[kMaxTensors];
-  float* s1[kMaxTensors];
-  int chunk_start[kMaxTensors + 1];  // prefix sum of chunks per tensor
-  int64_t size[kMaxTensors];
-  int n;
-  int kind;
-  float h0, h1, h2, h3;
-  const int64_t* step_dev;
+  float* p[kMaxGroupTensors];
+  const float* g[kMaxGroupTensors];
+  float* s0[kMaxGroupTensors];
+  float* s1[kMaxGroupTensors];
   // optional split planes of 2-D parameters, refreshed with the update (plane_fmt.cuh layout)
-  void* plane_hi[kMaxTensors];    // hi plane base (nullable per tensor)
-  void* plane_lo[kMaxTensors];
-  int cols[kMaxTensors];
+  void* plane_hi[kMaxGroupTensors];    // hi plane base (nullable per tensor)
+  void* plane_lo[kMaxGroupTensors];
+  int64_t size[kMaxGroupTensors];
+  int chunk_start[kMaxGroupTensors + 1];  // prefix sum of chunks per tensor
+  int cols[kMaxGroupTensors];
+  unsigned char opt[kMaxGroupTensors];
+  int n;
+  int kind[kMaxGroupOpts];
+  float h0[kMaxGroupOpts], h1[kMaxGroupOpts], h2[kMaxGroupOpts], h3[kMaxGroupOpts];
+  const int64_t* step_dev[kMaxGroupOpts];
   int fmt;
   unsigned int* ovf;
 };
@@ -76,24 +80,31 @@ __device__ __forceinline__ void apply_one(int kind, float& p, float g, float& s0
 }
 
 __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ OptParams o) {
-  // locate tensor for this CTA (n <= 32: linear scan)
-  int t = 0;
-  while (t + 1 < o.n && (int)blockIdx.x >= o.chunk_start[t + 1]) ++t;
+  // locate the tensor of this CTA (binary search over the chunk prefix sums)
+  int lo = 0, hi = o.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int)blockIdx.x >= o.chunk_start[mid]) lo = mid; else hi = mid - 1;
+  }
+  const int t = lo;
+  const int q = o.opt[t];
+  const int kind = o.kind[q];
+  const float h0 = o.h0[q], h1 = o.h1[q], h2 = o.h2[q], h3 = o.h3[q];
   const int64_t off = (int64_t)(blockIdx.x - o.chunk_start[t]) * kChunk;
   const int64_t end = min(o.size[t], off + kChunk);
   float* p = o.p[t];
   const float* g = o.g[t];
   float* s0 = o.s0[t];
   float* s1 = o.s1[t];
-  float lr_t = o.h0;
-  if (o.kind == ADN_OPT_ADAM) {
-    const float tt = (float)(*o.step_dev + 1);
-    lr_t = o.h0 * sqrtf(1.f - powf(o.h2, tt)) / (1.f - powf(o.h1, tt));
-  } else if (o.kind == ADN_OPT_MOMENTUM_COSINE) {
+  float lr_t = h0;
+  if (kind == ADN_OPT_ADAM) {
+    const float tt = (float)(*o.step_dev[q] + 1);
+    lr_t = h0 * sqrtf(1.f - powf(h2, tt)) / (1.f - powf(h1, tt));
+  } else if (kind == ADN_OPT_MOMENTUM_COSINE) {
     // tf.train.cosine_decay [TF]: step clipped to decay_steps, fp32 arithmetic
-    const float st = fminf((float)(*o.step_dev), o.h2);
-    const float cosine = 0.5f * (1.f + cosf(3.14159265358979323846f * (st / o.h2)));
-    lr_t = o.h0 * ((1.f - o.h3) * cosine + o.h3);
+    const float st = fminf((float)(*o.step_dev[q]), h2);
+    const float cosine = 0.5f * (1.f + cosf(3.14159265358979323846f * (st / h2)));
+    lr_t = h0 * ((1.f - h3) * cosine + h3);
   }
   const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)s0 | (uintptr_t)s1) & 15) == 0;
   if (vec) {
@@ -103,10 +114,10 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
         float4 gv = __ldg(reinterpret_cast<const float4*>(g + i));
         float4 a = s0 ? *reinterpret_cast<float4*>(s0 + i) : make_float4(0, 0, 0, 0);
         float4 b = s1 ? *reinterpret_cast<float4*>(s1 + i) : make_float4(0, 0, 0, 0);
-        apply_one(o.kind, pv.x, gv.x, a.x, b.x, o.h0, o.h1, o.h2, o.h3, lr_t);
-        apply_one(o.kind, pv.y, gv.y, a.y, b.y, o.h0, o.h1, o.h2, o.h3, lr_t);
-        apply_one(o.kind, pv.z, gv.z, a.z, b.z, o.h0, o.h1, o.h2, o.h3, lr_t);
-        apply_one(o.kind, pv.w, gv.w, a.w, b.w, o.h0, o.h1, o.h2, o.h3, lr_t);
+        apply_one(kind, pv.x, gv.x, a.x, b.x, h0, h1, h2, h3, lr_t);
+        apply_one(kind, pv.y, gv.y, a.y, b.y, h0, h1, h2, h3, lr_t);
+        apply_one(kind, pv.z, gv.z, a.z, b.z, h0, h1, h2, h3, lr_t);
+        apply_one(kind, pv.w, gv.w, a.w, b.w, h0, h1, h2, h3, lr_t);
         *reinterpret_cast<float4*>(p + i) = pv;
         store_planes(o, t, i, pv.x); store_planes(o, t, i + 1, pv.y);
         store_planes(o, t, i + 2, pv.z); store_planes(o, t, i + 3, pv.w);
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
       } else {
         for (int64_t j = i; j < end; ++j) {
           float pv = p[j], a = s0 ? s0[j] : 0.f, b = s1 ? s1[j] : 0.f;
-          apply_one(o.kind, pv, g[j], a, b, o.h0, o.h1, o.h2, o.h3, lr_t);
+          apply_one(kind, pv, g[j], a, b, h0, h1, h2, h3, lr_t);
           p[j] = pv;
           store_planes(o, t, j, pv);
           if (s0) s0[j] = a;
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
   } else {
     for (int64_t j = off + threadIdx.x; j < end; j += 256) {
       float pv = p[j], a = s0 ? s0[j] : 0.f, b = s1 ? s1[j] : 0.f;
-      apply_one(o.kind, pv, g[j], a, b, o.h0, o.h1, o.h2, o.h3, lr_t);
+      apply_one(kind, pv, g[j], a, b, h0, h1, h2, h3, lr_t);
       p[j] = pv;
       store_planes(o, t, j, pv);
       if (s0) s0[j] = a;
@@ -135,6 +146,13 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
   }
 }
 
+struct StepPtrs {
+  int64_t* p[kMaxGroupOpts];
+  int n;
+};
+__global__ void step_increment_group_kernel(const __grid_constant__ StepPtrs s) {
+  if ((int)threadIdx.x < s.n) *s.p[threadIdx.x] += 1;
+}
 __global__ void step_increment_kernel(int64_t* step) { *step += 1; }
 
 }  // namespace adn
@@ -149,61 +167,109 @@ extern "C" int adn_opt_step(int kind, float* const* params_host, const float* co
                         step_dev, nullptr, nullptr, stream);
 }
 
+namespace adn {
+// appends one optimizer's tensors to the launch description; returns 0 or an error
+static int add_optimizer(OptParams& o, StepPtrs& steps, int& chunks, int q, const adn_opt_op& op, const char* what) {
+  const int kind = op.kind;
+  if (kind < ADN_OPT_SGD || kind > ADN_OPT_MOMENTUM_COSINE) return fail(ADN_ERR_INVALID, "%s: bad kind %d", what, kind);
+  if (op.n_tensors < 1 || op.n_tensors > kMaxTensors)
+    return fail(ADN_ERR_UNSUPPORTED, "%s: n_tensors %d not in [1,%d]", what, op.n_tensors, kMaxTensors);
+  if (!op.params_host || !op.grads_host || !op.sizes_host || !op.hyper_host) return fail(ADN_ERR_INVALID, "%s: null pointer", what);
+  const int need_slots = kind == ADN_OPT_SGD ? 0 : ((kind == ADN_OPT_MOMENTUM || kind == ADN_OPT_MOMENTUM_COSINE) ? 1 : 2);
+  if (need_slots >= 1 && !op.slot0_host) return fail(ADN_ERR_INVALID, "%s: slot0 required", what);
+  if (need_slots >= 2 && !op.slot1_host) return fail(ADN_ERR_INVALID, "%s: slot1 required", what);
+  if ((kind == ADN_OPT_ADAM || kind == ADN_OPT_MOMENTUM_COSINE) && !op.step_dev)
+    return fail(ADN_ERR_INVALID, "%s: Adam / cosine-decay Momentum need step_dev", what);
+  if (kind == ADN_OPT_MOMENTUM_COSINE && !(op.hyper_host[2] > 0.f))
+    return fail(ADN_ERR_INVALID, "%s: cosine decay needs decay_steps > 0", what);
+  for (int i = 0; i < op.n_tensors; ++i) {
+    const int t = o.n;
+    if (!op.params_host[i] || !op.grads_host[i] || op.sizes_host[i] <= 0)
+      return fail(ADN_ERR_INVALID, "%s: tensor %d null or empty", what, i);
+    o.p[t] = op.params_host[i];
+    o.g[t] = op.grads_host[i];
+    o.s0[t] = need_slots >= 1 ? op.slot0_host[i] : nullptr;
+    o.s1[t] = need_slots >= 2 ? op.slot1_host[i] : nullptr;
+    if ((need_slots >= 1 && !o.s0[t]) || (need_slots >= 2 && !o.s1[t]))
+      return fail(ADN_ERR_INVALID, "%s: slot for tensor %d is null", what, i);
+    o.size[t] = op.sizes_host[i];
+    o.plane_hi[t] = nullptr;
+    if (op.planes_host && op.planes_host[i]) {
+      if (!op.cols_host || op.cols_host[i] <= 0 || op.sizes_host[i] % op.cols_host[i] != 0 || op.cols_host[i] > INT32_MAX)
+        return fail(ADN_ERR_INVALID, "%s: tensor %d: cols must divide its size", what, i);
+      const pl::PlaneView v = pl::plane_view(pl::format(), op.planes_host[i], op.sizes_host[i] / op.cols_host[i], op.cols_host[i]);
+      o.plane_hi[t] = v.hi;
+      o.plane_lo[t] = v.lo;
+      o.cols[t] = (int)op.cols_host[i];
+    }
+    o.opt[t] = (unsigned char)q;
+    o.chunk_start[t] = chunks;
+    chunks += (int)ceil_div(op.sizes_host[i], kChunk);
+    o.n = t + 1;
+  }
+  o.kind[q] = kind;
+  o.h0[q] = op.hyper_host[0];
+  o.h1[q] = kind >= ADN_OPT_MOMENTUM ? op.hyper_host[1] : 0.f;
+  o.h2[q] = kind >= ADN_OPT_RMSPROP ? op.hyper_host[2] : 0.f;
+  o.h3[q] = kind >= ADN_OPT_RMSPROP ? op.hyper_host[3] : 0.f;   // MOMENTUM_COSINE (4): {lr, momentum, decay_steps, alpha}
+  o.step_dev[q] = op.step_dev;
+  if (op.step_dev) steps.p[steps.n++] = op.step_dev;
+  return ADN_OK;
+}
+
+static int flush(OptParams& o, StepPtrs& steps, int& chunks, cudaStream_t st) {
+  if (o.n == 0) return ADN_OK;
+  o.chunk_start[o.n] = chunks;
+  o.fmt = pl::format();
+  o.ovf = pl::overflow_flag();
+  opt_step_kernel<<<chunks, 256, 0, st>>>(o);
+  ADN_CHECK_LAUNCH("opt_step");
+  if (steps.n > 0) {
+    step_increment_group_kernel<<<1, kMaxGroupOpts, 0, st>>>(steps);
+    ADN_CHECK_LAUNCH("step_increment");
+  }
+  o.n = 0;
+  steps.n = 0;
+  chunks = 0;
+  return ADN_OK;
+}
+}  // namespace adn
+
+extern "C" int adn_opt_step_group(const adn_opt_op* ops, int n, void* stream) {
+  if (n < 0 || (n > 0 && !ops)) return fail(ADN_ERR_INVALID, "adn_opt_step_group: bad ops");
+  static thread_local OptParams o;          // ~8 KB: keep it off the stack of deep Python call chains
+  static thread_local StepPtrs steps;
+  o.n = 0;
+  steps.n = 0;
+  int chunks = 0, q = 0, rc;
+  for (int i = 0; i < n; ++i) {
+    if (ops[i].n_tensors > kMaxTensors || ops[i].n_tensors < 1)
+      return fail(ADN_ERR_UNSUPPORTED, "adn_opt_step_group: op %d: n_tensors %d not in [1,%d]", i, ops[i].n_tensors, kMaxTensors);
+    if (o.n + ops[i].n_tensors > kMaxGroupTensors || q == kMaxGroupOpts) {
+      if ((rc = flush(o, steps, chunks, as_stream(stream)))) return rc;
+      q = 0;
+    }
+    if ((rc = add_optimizer(o, steps, chunks, q, ops[i], "adn_opt_step_group"))) return rc;
+    ++q;
+  }
+  return flush(o, steps, chunks, as_stream(stream));
+}
+
 extern "C" int adn_opt_step_p(int kind, float* const* params_host, const float* const* grads_host,
                               float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
                               int n_tensors, const float* hyper_host, int64_t* step_dev,
                               void* const* planes_host, const int64_t* cols_host, void* stream) {
-  if (kind < ADN_OPT_SGD || kind > ADN_OPT_MOMENTUM_COSINE) return fail(ADN_ERR_INVALID, "adn_opt_step: bad kind %d", kind);
-  if (n_tensors < 1 || n_tensors > kMaxTensors)
-    return fail(ADN_ERR_UNSUPPORTED, "adn_opt_step: n_tensors %d not in [1,%d]", n_tensors, kMaxTensors);
-  if (!params_host || !grads_host || !sizes_host || !hyper_host)
-    return fail(ADN_ERR_INVALID, "adn_opt_step: null pointer");
-  const int need_slots = kind == ADN_OPT_SGD ? 0 : ((kind == ADN_OPT_MOMENTUM || kind == ADN_OPT_MOMENTUM_COSINE) ? 1 : 2);
-  if (need_slots >= 1 && !slot0_host) return fail(ADN_ERR_INVALID, "adn_opt_step: slot0 required");
-  if (need_slots >= 2 && !slot1_host) return fail(ADN_ERR_INVALID, "adn_opt_step: slot1 required");
-  if ((kind == ADN_OPT_ADAM || kind == ADN_OPT_MOMENTUM_COSINE) && !step_dev)
-    return fail(ADN_ERR_INVALID, "adn_opt_step: Adam / cosine-decay Momentum need step_dev");
-  if (kind == ADN_OPT_MOMENTUM_COSINE && !(hyper_host[2] > 0.f))
-    return fail(ADN_ERR_INVALID, "adn_opt_step: cosine decay needs decay_steps > 0");
-  OptParams o{};
-  int chunks = 0;
-  for (int t = 0; t < n_tensors; ++t) {
-    if (!params_host[t] || !grads_host[t] || sizes_host[t] <= 0)
-      return fail(ADN_ERR_INVALID, "adn_opt_step: tensor %d null or empty", t);
-    o.p[t] = params_host[t];
-    o.g[t] = grads_host[t];
-    o.s0[t] = need_slots >= 1 ? slot0_host[t] : nullptr;
-    o.s1[t] = need_slots >= 2 ? slot1_host[t] : nullptr;
-    if ((need_slots >= 1 && !o.s0[t]) || (need_slots >= 2 && !o.s1[t]))
-      return fail(ADN_ERR_INVALID, "adn_opt_step: slot for tensor %d is null", t);
-    o.size[t] = sizes_host[t];
-    o.plane_hi[t] = nullptr;
-    if (planes_host && planes_host[t]) {
-      if (!cols_host || cols_host[t] <= 0 || sizes_host[t] % cols_host[t] != 0 || cols_host[t] > INT32_MAX)
-        return fail(ADN_ERR_INVALID, "adn_opt_step_p: tensor %d: cols must divide its size", t);
-      const pl::PlaneView v = pl::plane_view(pl::format(), planes_host[t], sizes_host[t] / cols_host[t], cols_host[t]);
-      o.plane_hi[t] = v.hi;
-      o.plane_lo[t] = v.lo;
-      o.cols[t] = (int)cols_host[t];
-    }
-    o.chunk_start[t] = chunks;
-    chunks += (int)ceil_div(sizes_host[t], kChunk);
-  }
-  o.chunk_start[n_tensors] = chunks;
-  o.n = n_tensors;
-  o.kind = kind;
-  o.h0 = hyper_host[0];
-  o.h1 = kind >= ADN_OPT_MOMENTUM ? hyper_host[1] : 0.f;
-  o.h2 = kind >= ADN_OPT_RMSPROP ? hyper_host[2] : 0.f;
-  o.h3 = kind >= ADN_OPT_RMSPROP ? hyper_host[3] : 0.f;   // MOMENTUM_COSINE (4): {lr, momentum, decay_steps, alpha}
-  o.step_dev = step_dev;
-  o.fmt = pl::format();
-  o.ovf = pl::overflow_flag();
-  opt_step_kernel<<<chunks, 256, 0, as_stream(stream)>>>(o);
-  ADN_CHECK_LAUNCH("opt_step");
-  if (step_dev) {
-    step_increment_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
-    ADN_CHECK_LAUNCH("step_increment");
-  }
-  return ADN_OK;
+  adn_opt_op op{};
+  op.kind = kind;
+  op.n_tensors = n_tensors;
+  op.params_host = params_host;
+  op.grads_host = grads_host;
+  op.slot0_host = slot0_host;
+  op.slot1_host = slot1_host;
+  op.sizes_host = sizes_host;
+  op.hyper_host = hyper_host;
+  op.step_dev = step_dev;
+  op.planes_host = planes_host;
+  op.cols_host = cols_host;
+  return adn_opt_step_group(&op, 1, stream);
 }

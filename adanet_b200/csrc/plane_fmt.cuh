@@ -10,8 +10,10 @@
 //       fp16 carries 5 exponent bits: full 22-bit precision for 2^-14 <= |T| < 65504, absolute error 2^-36
 //       below that; gradient tensors (O(1/batch)) are therefore carried multiplied by a power of two
 //       (dz_log2_scale at the ABI) and un-scaled exactly where they leave the plane format (dW, db).
-//       A finite |T| >= 65504 cannot be represented: every writer raises the device-side sticky flag
-//       (adn_plane_overflow) and the host re-runs the iteration on TF32 planes.
+//       A finite |T| >= 65520 cannot be represented: the element-wise writers (input split, optimizer, head, conv
+//       stem) raise the device-side sticky flag (adn_plane_overflow); a GEMM result beyond the range becomes Inf in
+//       its output planes and surfaces as a non-finite loss.  Either way the host re-runs the iteration on TF32
+//       planes (core/search.py restart_on_tf32_if_overflowed).
 //   ADN_PLANES_TF32            hi = rna_tf32(T)    lo  = rna_tf32(T - hi)            T ~= hi + lo
 //       4 B / value, k-block = 32 columns, plane[cols/32][rows][32]; kind::tf32 MMAs; fp32 exponent range.
 //

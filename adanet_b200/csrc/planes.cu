@@ -44,6 +44,7 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -108,8 +109,13 @@ struct GemmParams {
   const uint32_t* mask_bits;  // EPI_MASK (nullable): sign bits of a [M, N] tensor; out = bit ? out : 0
   float* colsum_part;    // EPI_MASK (nullable): [ceil(M/32)][colsum_ld] per-32-row column sums of out
   int colsum_ld;
-  float out_mul;         // EPI_MASK / EPI_PARTIAL: result multiplied by this power of two (un-scaling of gradient planes)
+  float out_mul;         // EPI_MASK / EPI_PARTIAL: result multiplied by this (un-scaling of gradient planes, 1/(1-rate) of dropout)
   unsigned int* ovf;     // sticky overflow word (fp16 planes)
+  // EPI_BIAS_ACT with planes out: tf.layers.dropout on the output (drop_thresh 0 = none)
+  uint32_t drop_thresh;  // keep iff hash >= thresh (= rate * 2^32)
+  uint32_t drop_key0;    // seed * 0x9E3779B1 + layer * 0x85EBCA77 + 0x27D4EB2F  (the step term is added on the device)
+  float drop_scale;      // 1 / (1 - rate)
+  const int64_t* drop_step;
 };
 
 // ---------------------------------------------------------------------------------
@@ -261,9 +267,143 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 // cbase..cbase+31).  Applies bias/ReLU (+ sign bits) or the sign-bit ReLU mask in the register layout,
 // transposes through `stage` (16 B chunks XOR-swizzled by row: conflict-free both ways) and writes with
 // lane = 4-column group of 8 rows, so every global access covers whole 32 B sectors.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+// split 32 values of one row into the two planes and write them with 256-bit stores (see emit_slice_fwd_planes)
+template <int FMT>
+__device__ __forceinline__ void store_row32_planes(const GemmParams& g, const float* a, int my_row, int cbase) {
+  constexpr int BK = Fmt<FMT>::BK;
+  const size_t poff = ((size_t)(cbase / BK) * g.M + my_row) * BK + (cbase % BK);
+  if (FMT == FMT_F16) {
+    uint32_t hw[16], lw[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const __half2 h2 = __floats2half2_rn(a[2 * q], a[2 * q + 1]);
+      const float2 hf = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn((a[2 * q] - hf.x) * 2048.0f, (a[2 * q + 1] - hf.y) * 2048.0f);
+      hw[q] = *reinterpret_cast<const uint32_t*>(&h2);
+      lw[q] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    __half* hp = reinterpret_cast<__half*>(g.out) + poff;
+    __half* lp = reinterpret_cast<__half*>(g.out_lo) + poff;
+    st_global_v8(hp, reinterpret_cast<const uint32_t(&)[8]>(hw[0]));
+    st_global_v8(hp + 16, reinterpret_cast<const uint32_t(&)[8]>(hw[8]));
+    st_global_v8(lp, reinterpret_cast<const uint32_t(&)[8]>(lw[0]));
+    st_global_v8(lp + 16, reinterpret_cast<const uint32_t(&)[8]>(lw[8]));
+  } else {
+    uint32_t hw[32], lw[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float h, l;
+      split_tf32(a[j], h, l);
+      hw[j] = __float_as_uint(h);
+      lw[j] = __float_as_uint(l);
+    }
+    float* hp = reinterpret_cast<float*>(g.out) + poff;
+    float* lp = reinterpret_cast<float*>(g.out_lo) + poff;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      st_global_v8(hp + 8 * q, reinterpret_cast<const uint32_t(&)[8]>(hw[8 * q]));
+      st_global_v8(lp + 8 * q, reinterpret_cast<const uint32_t(&)[8]>(lw[8 * q]));
+    }
+  }
+}
+
+// Forward epilogue with planes out, WITHOUT a transpose: lane = row keeps its 32 accumulators (bias already added by
+// the caller), applies ReLU, forms the sign-bit word, splits pairs of values with packed conversions and writes its
+// own 32 columns of each plane with 256-bit stores (fp16: 64 B per plane = 2 stores, each one full 32 B sector;
+// TF32: 128 B = 4 stores).  ~10 instructions per element against ~29 of the staged path (ncu: the short-K layer
+// waves were issue-bound at 61 % issue utilisation writing 2.2 TB/s, profiles/r2e_gemm_waves_ncu_full.txt).
+template <int FMT>
+__device__ __forceinline__ void emit_slice_fwd_planes(const GemmParams& g, float* a, int lane, int mrow0, int cbase) {
+  const int my_row = mrow0 + lane;
+  const int kbo = cbase >> 5;
+  if (kbo >= g.out_nb32) return;                         // warp-uniform
+  const uint32_t cmask = (cbase + 32 <= g.N) ? 0xffffffffu : ((cbase < g.N) ? ((1u << (g.N - cbase)) - 1u) : 0u);
+  if (g.act == ADN_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
+  }
+  if (g.drop_thresh != 0u) {
+    // tf.layers.dropout in TRAIN mode (simple_dnn.py:80-81): x * 1/(1-rate) * keep; the mask is the counter-based hash
+    // the oracle restates (oracle/adanet_oracle.py dropout_keep_mask): element index = row * out + col
+    const uint32_t key = g.drop_key0 + (uint32_t)(*g.drop_step) * 0xC2B2AE3Du;
+    const uint32_t base = (uint32_t)my_row * (uint32_t)g.N + (uint32_t)cbase;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      uint32_t x = (base + (uint32_t)j) ^ key;
+      x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+      a[j] = (x >= g.drop_thresh) ? a[j] * g.drop_scale : 0.f;
+    }
+  }
+  uint32_t bits = 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) bits |= (a[j] > 0.f) ? (1u << j) : 0u;
+  bits &= cmask;
+  if (cmask != 0xffffffffu) {       // K padding of the next GEMM must be exact zeros
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (!((cmask >> j) & 1u)) a[j] = 0.f;
+  }
+  if (my_row >= g.M) return;
+  g.out_bits[(size_t)kbo * g.M + my_row] = bits;
+  store_row32_planes<FMT>(g, a, my_row, cbase);
+}
+
+// dX epilogue with planes out, without a transpose: sign-bit ReLU mask, 256-bit plane stores from the row-owning
+// lane, and the per-32-row column sums (the bias gradient of the layer below) by a butterfly over the warp:
+// at distance w a lane keeps the half of its columns selected by bit w of its lane id and receives the partner's
+// partial sums for them, so after five rounds lane l holds the sum of column l over the 32 rows (31 shuffles and
+// adds per lane, fixed order).
+template <int FMT>
+__device__ __forceinline__ void emit_slice_mask_planes(const GemmParams& g, float* a, uint32_t mwq, int lane, int mrow0, int cbase) {
+  const int my_row = mrow0 + lane;
+  const int kbo = cbase >> 5;
+  if (kbo >= g.out_nb32) return;                         // warp-uniform
+  const uint32_t cmask = (cbase + 32 <= g.N) ? 0xffffffffu : ((cbase < g.N) ? ((1u << (g.N - cbase)) - 1u) : 0u);
+  const uint32_t keep = (my_row < g.M) ? (mwq & cmask) : 0u;     // rows past M contribute nothing to the column sums
+  if (g.out_mul != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] *= g.out_mul;
+  }
+  if (keep != 0xffffffffu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (!((keep >> j) & 1u)) a[j] = 0.f;
+  }
+  if (my_row < g.M) store_row32_planes<FMT>(g, a, my_row, cbase);
+  if (g.colsum_part) {
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+      const bool upper = (lane & w) != 0;
+#pragma unroll
+      for (int j = 0; j < w; ++j) {
+        const float mine = upper ? a[j + w] : a[j];
+        const float send = upper ? a[j] : a[j + w];
+        a[j] = mine + __shfl_xor_sync(0xffffffffu, send, w);
+      }
+    }
+    const int col = cbase + lane;
+    if (col < g.colsum_ld) g.colsum_part[(size_t)(mrow0 >> 5) * g.colsum_ld + col] = a[0];
+  }
+}
+
 template <int FMT, int EPI>
 __device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_PLANES, float* a, uint32_t mwq, float* stage,
-                                           int lane, int mrow0, int cbase, int rows_ok, float* dense, bool dense_vec) {
+                                           int lane, int mrow0, int cbase, int rows_ok, float* dense, bool dense_vec,
+                                           const bool bias_in_acc = false) {
+  if (EPI == EPI_BIAS_ACT && OUT_PLANES && bias_in_acc) {
+    emit_slice_fwd_planes<FMT>(g, a, lane, mrow0, cbase);
+    return;
+  }
+  if (EPI == EPI_MASK && OUT_PLANES && bias_in_acc) {      // (the single-CTA kernel's direct path; out_mul is 1 for planes)
+    emit_slice_mask_planes<FMT>(g, a, mwq, lane, mrow0, cbase);
+    return;
+  }
   constexpr int SW = 16;                   // staged columns per pass (2 KB per warp, two passes)
   constexpr int CH = SW / 4;               // 16 B chunks per staged row
   constexpr int RPI = 32 / CH;             // rows covered by one transposed instruction (8)
@@ -275,7 +415,7 @@ __device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_P
   // valid columns of this slice as a bit mask (warp-uniform); all ones for interior tiles
   const uint32_t cmask = (cbase + 32 <= g.N) ? 0xffffffffu : ((cbase < g.N) ? ((1u << (g.N - cbase)) - 1u) : 0u);
   if (EPI == EPI_BIAS_ACT) {
-    if (g.bias) {
+    if (g.bias && !bias_in_acc) {
       if (cmask == 0xffffffffu && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) {
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
@@ -322,7 +462,6 @@ __device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_P
   // chunk swizzle by row: both the row-wise float4 writes and the transposed float4 reads are bank-conflict free
 #define ADN_SWZ(r) (((r) >> 1) & 3)
   float cs[4] = {0.f, 0.f, 0.f, 0.f};
-  uint32_t omax = 0u;                     // largest magnitude written as fp16 planes (overflow guard)
 #pragma unroll
   for (int h = 0; h < 32 / SW; ++h) {
     {
@@ -355,10 +494,7 @@ __device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_P
             if (FMT == FMT_F16) {
               __half hh[4], ll[4];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                split_f16(v[k], hh[k], ll[k]);
-                omax = max(omax, __float_as_uint(v[k]) & 0x7fffffffu);
-              }
+              for (int k = 0; k < 4; ++k) split_f16(v[k], hh[k], ll[k]);
               __half* hp = reinterpret_cast<__half*>(g.out) + poff + (size_t)i * RPI * BK;
               __half* lp = reinterpret_cast<__half*>(g.out_lo) + poff + (size_t)i * RPI * BK;
               *reinterpret_cast<uint2*>(hp) = make_uint2(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]));
@@ -403,7 +539,6 @@ __device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_P
     __syncwarp();
   }
 #undef ADN_SWZ
-  if (FMT == FMT_F16 && OUT_PLANES && omax >= 0x477ff000u && omax < 0x7f800000u) raise_overflow(g.ovf);
 }
 
 // ---------------------------------------------------------------------------------
@@ -587,8 +722,23 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
         mw = (my_row < g.M && kbo < g.out_nb32) ? __ldg(g.mask_bits + (size_t)kbo * g.M + my_row) : 0u;
       }
       float acc[32];
+      if (EPI == EPI_BIAS_ACT && g.bias) {
+        // the bias starts the accumulation (fetched while the first chunk is still in flight): warp-uniform loads
+        if (ncol0 + 32 <= g.N && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + ncol0) + jj);
+            acc[4 * jj + 0] = bv.x; acc[4 * jj + 1] = bv.y;
+            acc[4 * jj + 2] = bv.z; acc[4 * jj + 3] = bv.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = (ncol0 + j < g.N) ? __ldg(g.bias + ncol0 + j) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      }
       const int nchunks = (it.nkb + CHUNK - 1) / CHUNK;
       for (int c = 0; c < nchunks; ++c, ++gchunk) {
         const uint32_t b = gchunk & 1;
@@ -619,7 +769,7 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
       const bool out_planes = g.out_planes != 0;
       const bool dense_vec = !out_planes && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
       const int rows_ok = min(32, g.M - mrow0);          // warp-uniform; <= 0: nothing to write
-      emit_slice<FMT, EPI>(g, out_planes, acc, mw, stage, lane, mrow0, ncol0, rows_ok, dense, dense_vec);
+      emit_slice<FMT, EPI>(g, out_planes, acc, mw, stage, lane, mrow0, ncol0, rows_ok, dense, dense_vec, true);
     }
   }
   tc_fence_before();
@@ -627,6 +777,378 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// CTA-pair GEMM kernel (tcgen05 cta_group::2): one 256 x 256 tile per pair of SMs, grouped like pl_gemm_kernel.
+//
+// With fp16 planes the tensor pipe retires a 128 B k-block of the 128x128 single-CTA tile in 768 clk while that
+// tile needs 64 KiB of operands for it: 85 B/clk per SM out of L2 (21 TB/s chip-wide at the cuBLAS fp16 rate) and
+// a 3-stage ring that covers only ~0.9 us of TMA latency -- profiles/r2e_gemm_single_ncu_full.txt shows the
+// tensor pipe 55-59 % active with nothing else saturated.  The pair tile moves (128 A rows + 128 B rows) per SM for
+// twice the tensor work: half the L2 and shared-memory traffic per flop, twice the latency cover per stage.
+//   CTA rank r of the pair owns A rows / D rows [m0 + 128 r, +128) and supplies B rows
+//   [n0 + r n_inst/2, + n_inst/2); the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256,
+//   N = n_inst <= 256, trimmed to the live columns) for both SMs.
+//   TMEM per SM (512 columns): H [0,256) = hi*hi partial sums of ONE 128-K chunk, S [256,512) = cross
+//   terms of the whole tile.  H is single-buffered: the next chunk starts with its cross-term MMAs
+//   while the epilogue warps of both CTAs drain H into registers.
+//   Barriers: TMA of both CTAs -> leader's full[s] (tx bytes of both); commit multicast -> both CTAs'
+//   empty[s] / acc_full; epilogue warps of both CTAs -> leader's acc_empty / s_empty (remote arrive).
+// ---------------------------------------------------------------------------------
+static constexpr int BM2 = 256, BN2 = 256;
+static constexpr int EPI_WARPS2 = 8;
+static constexpr int NUM_THREADS2 = 64 + 32 * EPI_WARPS2;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier whose arrivals come from other CTAs of the cluster
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((it & 1023u) == 1023u) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+template <int FMT>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t da_hi, uint32_t db_hi,
+                                         uint32_t idesc, uint32_t accum) {
+  if (FMT == FMT_F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(da_lo), "r"(db_lo), "r"(da_hi), "r"(db_hi), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(da_lo), "r"(db_lo), "r"(da_hi), "r"(db_hi), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+struct Item2 {
+  int m0, n0, kb0, nkb, split, n_inst;
+};
+template <int FMT>
+__device__ __forceinline__ Item2 decode_item2(const GemmParams& g, int item) {
+  Item2 it;
+  const int tiles = g.tiles_m * g.tiles_n;       // 256 x 256 tiles
+  it.split = item / tiles;
+  const int t = item - it.split * tiles;
+  const int tm = t / g.tiles_n;
+  it.m0 = tm * BM2;
+  it.n0 = (t - tm * g.tiles_n) * BN2;
+  it.kb0 = it.split * g.kb_per_split;
+  it.nkb = min(g.total_kb, it.kb0 + g.kb_per_split) - it.kb0;
+  // live columns in steps of 2 k-block widths: each CTA's half must start on a k-block boundary of an MN-major B
+  constexpr int GR = 2 * Fmt<FMT>::BK;
+  it.n_inst = min(BN2, ((g.N - it.n0 + GR - 1) / GR) * GR);
+  return it;
+}
+
+template <int FMT, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+pl_gemm2_kernel(const __grid_constant__ Group grp) {
+  constexpr int BK = Fmt<FMT>::BK;
+  constexpr int CHUNK = Fmt<FMT>::CHUNK;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]  leader's: TMA of both CTAs -> MMA
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]  each CTA's: MMA commit (multicast) -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;          // [1]       each CTA's: MMA commit (multicast) -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 1;     // [1]       leader's: epilogue warps of both CTAs -> MMA (H drained)
+  uint64_t* s_empty = bars + 2 * STAGES + 2;       // [1]       leader's: epilogue warps of both CTAs -> MMA (S drained)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 3);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int n_items = grp.total_items;
+
+  if (warp == 0 && lane < grp.n) {
+    tma_prefetch_desc(&grp.p[lane].a_hi);
+    tma_prefetch_desc(&grp.p[lane].a_lo);
+    tma_prefetch_desc(&grp.p[lane].b_hi);
+    tma_prefetch_desc(&grp.p[lane].b_lo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(acc_full), 1);
+      mbar_init(smem_u32(acc_empty), 2 * EPI_WARPS2);
+      mbar_init(smem_u32(s_empty), 2 * EPI_WARPS2);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs: own A rows, own half of B) =================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      int cur = 0;
+      const uint32_t smem0 = smem_u32(smem);
+      for (int item = pair; item < n_items; item += npairs) {
+        cur = find_problem(grp, cur, item);
+        const Problem& pr = grp.p[cur];
+        const GemmParams& g = pr.g;
+        const Item2 it = decode_item2<FMT>(g, item - pr.item0);
+        const int a_row = it.m0 + (int)rank * 128;
+        const int b_row = it.n0 + (int)rank * (it.n_inst >> 1);
+        for (int kb = 0; kb < it.nkb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2 * STAGE_BYTES);   // bytes of both CTAs
+          const uint32_t fb = mapa_rank(smem_u32(&full_bar[s]), 0);                 // leader's barrier
+          const uint32_t base = smem0 + s * STAGE_BYTES;
+          const int kc = it.kb0 + kb;
+          const int a1 = g.a_mn ? kc * BK : a_row, a2 = g.a_mn ? (a_row / BK) : kc;
+          const int b1 = g.b_mn ? kc * BK : b_row, b2 = g.b_mn ? (b_row / BK) : kc;
+          tma_load_3d_2sm(&pr.a_hi, fb, base + 0 * TILE_BYTES, 0, a1, a2);
+          tma_load_3d_2sm(&pr.a_lo, fb, base + 1 * TILE_BYTES, 0, a1, a2);
+          tma_load_3d_2sm(&pr.b_hi, fb, base + 2 * TILE_BYTES, 0, b1, b2);
+          tma_load_3d_2sm(&pr.b_lo, fb, base + 3 * TILE_BYTES, 0, b1, b2);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0) {
+      const uint32_t smem0 = smem_u32(smem);
+      const uint32_t acc_h = tmem_base, acc_s = tmem_base + 256;
+      uint32_t s = 0, ph = 0, gchunk = 0, tile_i = 0;
+      int cur = 0;
+      for (int item = pair; item < n_items; item += npairs, ++tile_i) {
+        cur = find_problem(grp, cur, item);
+        const GemmParams& g = grp.p[cur].g;
+        const Item2 it = decode_item2<FMT>(g, item - grp.p[cur].item0);
+        const uint32_t dah = desc_hi_word<FMT>(g.a_mn), dbh = desc_hi_word<FMT>(g.b_mn);
+        const uint32_t a_lo0 = desc_lo_word<FMT>(smem0, g.a_mn);
+        const uint32_t b_lo0 = desc_lo_word<FMT>(smem0 + 2 * TILE_BYTES, g.b_mn);
+        const uint32_t a_step = g.a_mn ? Fmt<FMT>::MN_STEP : (32u >> 4);
+        const uint32_t b_step = g.b_mn ? Fmt<FMT>::MN_STEP : (32u >> 4);
+        const uint32_t idesc = make_idesc<FMT>(BM2, it.n_inst, g.a_mn, g.b_mn);
+        mbar_wait_cluster(smem_u32(s_empty), (tile_i & 1) ^ 1);     // cross-term accumulator drained by both CTAs
+        tc_fence_after();
+        uint32_t s_accum = 0;
+        for (int kb = 0; kb < it.nkb; kb += CHUNK, ++gchunk) {
+          const int nk = min(CHUNK, it.nkb - kb);
+          for (int kk = 0; kk < nk; ++kk) {
+            mbar_wait(smem_u32(&full_bar[s]), ph);
+            tc_fence_after();
+            const uint32_t so = s * (STAGE_BYTES >> 4);
+            if (kk == 0) {
+              // new chunk: cross terms first, so the tensor pipe stays busy while H is being drained
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t a_hi = a_lo0 + so + k * a_step, a_lo = a_hi + (TILE_BYTES >> 4);
+                  const uint32_t b_hi = b_lo0 + so + k * b_step, b_lo = b_hi + (TILE_BYTES >> 4);
+                  umma_2sm<FMT>(acc_s, a_lo, b_hi, dah, dbh, idesc, (k == 0) ? s_accum : 1u);
+                  umma_2sm<FMT>(acc_s, a_hi, b_lo, dah, dbh, idesc, 1u);
+                }
+              }
+              __syncwarp();
+              mbar_wait_cluster(smem_u32(acc_empty), (gchunk & 1) ^ 1);   // H drained by both CTAs
+              tc_fence_after();
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t a_hi = a_lo0 + so + k * a_step;
+                  const uint32_t b_hi = b_lo0 + so + k * b_step;
+                  umma_2sm<FMT>(acc_h, a_hi, b_hi, dah, dbh, idesc, (k == 0) ? 0u : 1u);
+                }
+                umma_commit_2sm(smem_u32(&empty_bar[s]));
+                if (nk == 1) umma_commit_2sm(smem_u32(acc_full));
+              }
+            } else {
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t a_hi = a_lo0 + so + k * a_step, a_lo = a_hi + (TILE_BYTES >> 4);
+                  const uint32_t b_hi = b_lo0 + so + k * b_step, b_lo = b_hi + (TILE_BYTES >> 4);
+                  umma_2sm<FMT>(acc_s, a_lo, b_hi, dah, dbh, idesc, 1u);
+                  umma_2sm<FMT>(acc_s, a_hi, b_lo, dah, dbh, idesc, 1u);
+                  umma_2sm<FMT>(acc_h, a_hi, b_hi, dah, dbh, idesc, 1u);
+                }
+                umma_commit_2sm(smem_u32(&empty_bar[s]));
+                if (kk == nk - 1) umma_commit_2sm(smem_u32(acc_full));
+              }
+            }
+            __syncwarp();
+            s_accum = 1u;
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..9 (both CTAs; 32 rows x 128 columns each) =================
+    const int quad = warp & 3;
+    const int cgrp = (warp - 2) >> 2;                // which 128 of the tile's 256 columns
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t col_base = (uint32_t)(cgrp * 128);
+    float* stage = epi_stage + (warp - 2) * EPI_STAGE_FLOATS;
+    const uint32_t acc_empty_leader = mapa_rank(smem_u32(acc_empty), 0);
+    const uint32_t s_empty_leader = mapa_rank(smem_u32(s_empty), 0);
+    uint32_t gchunk = 0;
+    int cur = 0;
+    for (int item = pair; item < n_items; item += npairs) {
+      cur = find_problem(grp, cur, item);
+      const GemmParams& g = grp.p[cur].g;
+      const Item2 it = decode_item2<FMT>(g, item - grp.p[cur].item0);
+      const int mrow0 = it.m0 + (int)rank * 128 + quad * 32;
+      const int ncol0 = it.n0 + (int)col_base;
+      const int my_row = mrow0 + lane;
+      const bool cols_live = (int)col_base < it.n_inst;   // warp-uniform: does this warp own any computed column?
+      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (EPI == EPI_MASK && g.mask_bits) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int kbo = (ncol0 >> 5) + q;
+          mw[q] = (my_row < g.M && kbo < g.out_nb32) ? __ldg(g.mask_bits + (size_t)kbo * g.M + my_row) : 0u;
+        }
+      }
+      float acc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      const int nchunks = (it.nkb + CHUNK - 1) / CHUNK;
+      for (int c = 0; c < nchunks; ++c, ++gchunk) {
+        mbar_wait(smem_u32(acc_full), gchunk & 1);
+        tc_fence_after();
+        if (cols_live) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16_nowait(tmem_base + lane_base + col_base + t * 32, r0);
+            tmem_ld16_nowait(tmem_base + lane_base + col_base + t * 32 + 16, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {           // fp32 RN adds
+              acc[t * 32 + j] += __uint_as_float(r0[j]);
+              acc[t * 32 + 16 + j] += __uint_as_float(r1[j]);
+            }
+          }
+          if (c == nchunks - 1) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              uint32_t r0[16], r1[16];
+              tmem_ld16_nowait(tmem_base + lane_base + 256 + col_base + t * 32, r0);
+              tmem_ld16_nowait(tmem_base + lane_base + 256 + col_base + t * 32 + 16, r1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (FMT == FMT_F16) {
+                  acc[t * 32 + j] = fmaf(__uint_as_float(r0[j]), 1.0f / 2048.0f, acc[t * 32 + j]);
+                  acc[t * 32 + 16 + j] = fmaf(__uint_as_float(r1[j]), 1.0f / 2048.0f, acc[t * 32 + 16 + j]);
+                } else {
+                  acc[t * 32 + j] += __uint_as_float(r0[j]);
+                  acc[t * 32 + 16 + j] += __uint_as_float(r1[j]);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(acc_empty_leader);
+          if (c == nchunks - 1) mbar_arrive_cluster(s_empty_leader);
+        }
+      }
+      if (cols_live) {
+        float* dense = reinterpret_cast<float*>(g.out);
+        if (EPI == EPI_PARTIAL) dense += (size_t)it.split * g.M * g.N;
+        const bool out_planes = g.out_planes != 0;
+        const bool dense_vec = !out_planes && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+        const int rows_ok = min(32, g.M - mrow0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if ((int)col_base + q * 32 < it.n_inst)
+            emit_slice<FMT, EPI>(g, out_planes, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // neither CTA frees TMEM / exits while the peer may still use its smem or barriers
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
 }
@@ -767,6 +1289,11 @@ int init() {
     ADN_PL_ATTR(FMT_TF32, EPI_BIAS_ACT); ADN_PL_ATTR(FMT_TF32, EPI_MASK); ADN_PL_ATTR(FMT_TF32, EPI_PARTIAL);
     ADN_PL_ATTR(FMT_F16, EPI_BIAS_ACT); ADN_PL_ATTR(FMT_F16, EPI_MASK); ADN_PL_ATTR(FMT_F16, EPI_PARTIAL);
 #undef ADN_PL_ATTR
+#define ADN_PL_ATTR2(F, E) \
+  ok = ok && (cudaFuncSetAttribute(pl_gemm2_kernel<F, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess)
+    ADN_PL_ATTR2(FMT_TF32, EPI_BIAS_ACT); ADN_PL_ATTR2(FMT_TF32, EPI_MASK); ADN_PL_ATTR2(FMT_TF32, EPI_PARTIAL);
+    ADN_PL_ATTR2(FMT_F16, EPI_BIAS_ACT); ADN_PL_ATTR2(FMT_F16, EPI_MASK); ADN_PL_ATTR2(FMT_F16, EPI_PARTIAL);
+#undef ADN_PL_ATTR2
     if (!ok) {
       (void)cudaGetLastError();
       rc = fail(ADN_ERR_CUDA, "pl::init: cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
@@ -883,35 +1410,69 @@ template <int FMT, int EPI>
 static void launch_kernel(const Group& grp, int grid, cudaStream_t st) {
   pl_gemm_kernel<FMT, EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(grp);
 }
+template <int FMT, int EPI>
+static void launch_kernel2(const Group& grp, int grid, cudaStream_t st) {
+  pl_gemm2_kernel<FMT, EPI><<<grid, NUM_THREADS2, SMEM_BYTES, st>>>(grp);
+}
 
-// n independent GEMMs of the same epilogue kind -> ceil(n / MAX_GROUP) persistent launches
+// Which GEMMs take the CTA-pair kernel.  ADN_PL_PAIR: 1 every GEMM, 2 the big ones (M, N >= 256, K >= 4 k-blocks),
+// unset / 0 none.  Measured on B200 (profiles/r2f_pair_vs_single_f16.txt): [32768,1024]x[1024,1024] fp16 planes
+// 206 us on pairs against 177 us on single CTAs (TF32 planes, round 1: equal), so the single-CTA kernel stays the
+// default and the pair kernel is kept as a tested alternative (tests force it through ADN_PL_PAIR=1).
+static bool use_pair_shape(int fmt, int64_t M, int64_t N, int64_t total_kb) {
+  static const int env = getenv("ADN_PL_PAIR") ? atoi(getenv("ADN_PL_PAIR")) : 0;
+  (void)fmt;
+  if (env == 1) return true;
+  if (env == 2) return M >= 256 && N >= 256 && total_kb >= 4;
+  return false;
+}
+static bool use_pair(int fmt, const GemmDesc& d) {
+  return d.g.drop_thresh == 0u && use_pair_shape(fmt, d.g.M, d.g.N, d.g.total_kb);   // dropout lives in the direct epilogue
+}
+
+// n independent GEMMs of the same epilogue kind -> persistent launches of up to MAX_GROUP problems each; the problems
+// that take the CTA-pair kernel are launched as their own group(s)
 template <int EPI>
 static int launch_group(int fmt, const GemmDesc* d, int n, cudaStream_t st, const char* what) {
-  for (int i0 = 0; i0 < n; i0 += MAX_GROUP) {
-    const int m = std::min(MAX_GROUP, n - i0);
-    Group grp;
-    memset(&grp, 0, sizeof(grp));
-    int items = 0;
-    for (int i = 0; i < m; ++i) {
-      Problem& pr = grp.p[i];
-      int rc = encode_maps(fmt, d[i0 + i], &pr.a_hi, &pr.a_lo, &pr.b_hi, &pr.b_lo, what);
-      if (rc) return rc;
-      pr.g = d[i0 + i].g;
-      pr.g.a_mn = d[i0 + i].a.mn_major;
-      pr.g.b_mn = d[i0 + i].b.mn_major;
-      pr.g.tiles_m = (int)ceil_div(pr.g.M, BM);
-      pr.g.tiles_n = (int)ceil_div(pr.g.N, BN);
-      pr.g.m_fastest = item_order_m_fastest(pr.g);
-      pr.g.ovf = g_ovf_addr;
-      pr.item0 = items;
-      items += pr.g.tiles_m * pr.g.tiles_n * pr.g.splits;
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool pair = pass == 0;
+    std::vector<int> idx;
+    for (int i = 0; i < n; ++i)
+      if (use_pair(fmt, d[i]) == pair) idx.push_back(i);
+    const int tm = pair ? BM2 : BM, tn = pair ? BN2 : BN;
+    for (size_t i0 = 0; i0 < idx.size(); i0 += MAX_GROUP) {
+      const int m = (int)std::min<size_t>(MAX_GROUP, idx.size() - i0);
+      Group grp;
+      memset(&grp, 0, sizeof(grp));
+      int items = 0;
+      for (int i = 0; i < m; ++i) {
+        const GemmDesc& src = d[idx[i0 + (size_t)i]];
+        Problem& pr = grp.p[i];
+        int rc = encode_maps(fmt, src, &pr.a_hi, &pr.a_lo, &pr.b_hi, &pr.b_lo, what);
+        if (rc) return rc;
+        pr.g = src.g;
+        pr.g.a_mn = src.a.mn_major;
+        pr.g.b_mn = src.b.mn_major;
+        pr.g.tiles_m = (int)ceil_div(pr.g.M, tm);
+        pr.g.tiles_n = (int)ceil_div(pr.g.N, tn);
+        pr.g.m_fastest = item_order_m_fastest(pr.g);
+        pr.g.ovf = g_ovf_addr;
+        pr.item0 = items;
+        items += pr.g.tiles_m * pr.g.tiles_n * pr.g.splits;
+      }
+      grp.n = m;
+      grp.total_items = items;
+      if (pair) {
+        const int grid = 2 * std::min(items, sm_count() / 2);
+        if (fmt == FMT_F16) launch_kernel2<FMT_F16, EPI>(grp, grid, st);
+        else launch_kernel2<FMT_TF32, EPI>(grp, grid, st);
+      } else {
+        const int grid = std::min(items, sm_count());
+        if (fmt == FMT_F16) launch_kernel<FMT_F16, EPI>(grp, grid, st);
+        else launch_kernel<FMT_TF32, EPI>(grp, grid, st);
+      }
+      ADN_CHECK_LAUNCH(what);
     }
-    grp.n = m;
-    grp.total_items = items;
-    const int grid = std::min(items, sm_count());
-    if (fmt == FMT_F16) launch_kernel<FMT_F16, EPI>(grp, grid, st);
-    else launch_kernel<FMT_TF32, EPI>(grp, grid, st);
-    ADN_CHECK_LAUNCH(what);
   }
   return ADN_OK;
 }
@@ -972,6 +1533,15 @@ int dense_fwd_group(int fmt, const FwdOp* ops, int n, int64_t batch, cudaStream_
     g.total_kb = (int)ceil_div(o.in, bk); g.kb_per_split = g.total_kb; g.splits = 1;
     g.bias = o.bias; g.act = o.act;
     g.out_mul = 1.0f;
+    if (o.dropout_rate > 0.f) {
+      if (!o.yp || !o.dropout_step) return fail(ADN_ERR_INVALID, "pl dense_fwd: dropout needs planes out and a step counter");
+      const double t = (double)o.dropout_rate * 4294967296.0;
+      g.drop_thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+      if (g.drop_thresh == 0u) g.drop_thresh = 1u;
+      g.drop_key0 = o.dropout_seed * 0x9E3779B1u + (uint32_t)o.dropout_layer * 0x85EBCA77u + 0x27D4EB2Fu;
+      g.drop_scale = 1.0f / (1.0f - o.dropout_rate);
+      g.drop_step = o.dropout_step;
+    }
     if (o.yp) {
       const PlaneView v = plane_view(fmt, o.yp, batch, o.out);
       g.out_planes = 1;
@@ -992,27 +1562,69 @@ int dense_bwd_group(int fmt, const BwdOp* ops, int n, int64_t batch, cudaStream_
   struct Carve { float* part; float* cspart; float* cspart2; int splits; };
   std::vector<Carve> cv((size_t)n);
   std::vector<GemmDesc> dwd, dxd;
-  // Split-K over the batch for the dW GEMMs of the group.  Items of one launch are dealt round-robin to the
-  // CTAs, so they should all cost the same: every problem uses the same k-blocks-per-item `kps`, chosen to
-  // minimise (rounds of the whole group) x (kps + per-item overhead) + reduction cost, subject to each
-  // problem's partial-buffer bound.  (A k-block is 4 MMA steps in either format.)
+  // Split-K over the batch for the dW GEMMs of the group.  Work items of one launch are dealt round-robin to the
+  // CTAs (item j -> CTA j % grid), so the launch takes as long as its most loaded CTA.  Every problem uses the
+  // k-blocks-per-item `kps` (raised to its own partial-buffer bound), and kps is chosen by evaluating, for every
+  // candidate split count, the exact round-robin load (k-blocks + a per-item pipeline fill/drain + epilogue
+  // allowance) plus the cost of the fixed-order reduction of the partial sums (bytes at ~2.5 TB/s; one k-block
+  // of MMA work is ~0.4 us).  (A k-block is 4 MMA steps in either format.)
   const int64_t kb_b = ceil_div(batch, bk);
   int64_t best_kps = kb_b;
   {
-    double best_t = 1e30;
-    for (int s0 = 1; s0 <= MAX_SPLITS && s0 <= kb_b; ++s0) {
-      const int64_t kps = ceil_div(kb_b, s0);
-      int64_t items = 0, max_s_used = 1;
-      for (int i = 0; i < n; ++i) {
-        if (!ops[i].dw) continue;
-        int64_t k_i = std::max<int64_t>(kps, ceil_div(kb_b, max_dw_splits(ops[i].in, ops[i].out)));
-        const int64_t s_i = ceil_div(kb_b, k_i);
-        items += ceil_div(ops[i].in, BM) * ceil_div(ops[i].out, BN) * s_i;
-        max_s_used = std::max(max_s_used, s_i);
+    static std::mutex mu;
+    static std::unordered_map<std::string, int64_t> memo;      // the same waves recur every step / capture
+    std::string key = std::to_string(batch) + ":" + std::to_string(fmt);
+    for (int i = 0; i < n; ++i)
+      if (ops[i].dw) key += "," + std::to_string(ops[i].in) + "x" + std::to_string(ops[i].out);
+    bool hit = false;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = memo.find(key);
+      if (it != memo.end()) { best_kps = it->second; hit = true; }
+    }
+    if (!hit) {
+      const double kItemOverhead = 6.0;          // k-block equivalents per work item
+      const double kReduceKbPerByte = 1.0 / (2.5e6 * 0.4);     // k-block equivalents per byte of partials read
+      double best_t = 1e30;
+      std::vector<double> load((size_t)workers), load2((size_t)std::max(1, workers / 2));
+      int64_t last_kps = -1;
+      for (int s0 = 1; s0 <= MAX_SPLITS && s0 <= kb_b; ++s0) {
+        const int64_t kps = ceil_div(kb_b, s0);
+        if (kps == last_kps) continue;
+        last_kps = kps;
+        std::fill(load.begin(), load.end(), 0.0);
+        std::fill(load2.begin(), load2.end(), 0.0);
+        int64_t item = 0, item2 = 0;
+        double reduce_bytes = 0.0;
+        bool any = false;
+        for (int i = 0; i < n; ++i) {
+          if (!ops[i].dw) continue;
+          any = true;
+          const int64_t k_i = std::max<int64_t>(kps, ceil_div(kb_b, max_dw_splits(ops[i].in, ops[i].out)));
+          const int64_t s_i = ceil_div(kb_b, k_i);
+          // problems on the CTA-pair kernel run as their own launch: 256x256 tiles on SM pairs, twice the tensor
+          // work per k-block and tile
+          const bool pair = use_pair_shape(fmt, ops[i].in, ops[i].out, kb_b);
+          const int64_t tiles = pair ? ceil_div(ops[i].in, BM2) * ceil_div(ops[i].out, BN2)
+                                     : ceil_div(ops[i].in, BM) * ceil_div(ops[i].out, BN);
+          for (int64_t sp = 0; sp < s_i; ++sp) {
+            const double kb_item = (double)(std::min(kb_b, (sp + 1) * k_i) - sp * k_i);
+            if (pair) {
+              for (int64_t t = 0; t < tiles; ++t, ++item2) load2[(size_t)(item2 % (int64_t)load2.size())] += 2.0 * (kb_item + kItemOverhead);
+            } else {
+              for (int64_t t = 0; t < tiles; ++t, ++item) load[(size_t)(item % workers)] += kb_item + kItemOverhead;
+            }
+          }
+          if (s_i > 1) reduce_bytes += (double)(s_i + 1) * (double)ops[i].in * (double)ops[i].out * 4.0;
+        }
+        if (!any) break;
+        const double t = *std::max_element(load.begin(), load.end()) + *std::max_element(load2.begin(), load2.end()) +
+                         reduce_bytes * kReduceKbPerByte + (reduce_bytes > 0 ? 10.0 : 0.0);
+        if (t < best_t) { best_t = t; best_kps = kps; }
       }
-      if (items == 0) break;
-      const double t = (double)ceil_div(items, workers) * ((double)kps + 6.0) + 0.75 * (double)max_s_used;
-      if (t < best_t) { best_t = t; best_kps = kps; }
+      std::lock_guard<std::mutex> lk(mu);
+      if (memo.size() > 4096) memo.clear();
+      memo[key] = best_kps;
     }
   }
   for (int i = 0; i < n; ++i) {
@@ -1061,10 +1673,10 @@ int dense_bwd_group(int fmt, const BwdOp* ops, int n, int64_t batch, cudaStream_
         const PlaneView v = plane_view(fmt, o.dxp, batch, o.in);
         g.out_planes = 1;
         g.out = v.hi; g.out_lo = v.lo;
-        g.out_mul = 1.0f;                  // the gradient keeps its scale while it stays in plane format
+        g.out_mul = o.dx_mul;              // the gradient keeps its scale while it stays in plane format
       } else {
         g.out = o.dx; g.ldc = (int)o.in;
-        g.out_mul = unscale;               // dense fp32 leaves the plane pipeline: true magnitude
+        g.out_mul = unscale * o.dx_mul;    // dense fp32 leaves the plane pipeline: true magnitude
       }
       e.g = g;
       dxd.push_back(e);
@@ -1095,14 +1707,14 @@ int dense_bwd_group(int fmt, const BwdOp* ops, int n, int64_t batch, cudaStream_
 
 int dense_fwd(int fmt, const void* xp, const void* wp, const float* bias, void* yp, float* y, int64_t batch, int64_t in,
               int64_t out, int act, cudaStream_t st) {
-  const FwdOp op{xp, wp, bias, yp, y, in, out, act};
+  FwdOp op{xp, wp, bias, yp, y, in, out, act};
   return dense_fwd_group(fmt, &op, 1, batch, st);
 }
 
 int dense_bwd(int fmt, const void* xp, const void* wp, const void* dzp, void* dxp, float* dx, float* dx_colsum, float* dw,
               int64_t batch, int64_t in, int64_t out, int x_relu_mask, int dz_log2_scale, void* ws, int64_t ws_bytes,
               cudaStream_t st) {
-  const BwdOp op{xp, wp, dzp, dxp, dx, dx_colsum, dw, in, out, x_relu_mask, dz_log2_scale, ws, ws_bytes};
+  BwdOp op{xp, wp, dzp, dxp, dx, dx_colsum, dw, in, out, x_relu_mask, dz_log2_scale, ws, ws_bytes};
   return dense_bwd_group(fmt, &op, 1, batch, st);
 }
 

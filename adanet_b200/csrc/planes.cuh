@@ -25,6 +25,10 @@ struct FwdOp {
   float* y;             // dense  [batch, out]
   int64_t in, out;
   int act;
+  float dropout_rate = 0.f;          // tf.layers.dropout on the output (planes out), see include/adanet_b200.h
+  uint32_t dropout_seed = 0;
+  int dropout_layer = 0;
+  const int64_t* dropout_step = nullptr;
 };
 struct BwdOp {
   const void* xp;       // planes [batch, in]
@@ -39,6 +43,7 @@ struct BwdOp {
   int dz_log2_scale;
   void* ws;             // dense_bwd_workspace_bytes(batch, in, out), one per op
   int64_t ws_bytes;
+  float dx_mul = 1.f;   // dx (planes or dense) is multiplied by this: 1 / (1 - rate) below a dropped-out activation
 };
 int dense_fwd_group(int fmt, const FwdOp* ops, int n, int64_t batch, cudaStream_t st);
 int dense_bwd_group(int fmt, const BwdOp* ops, int n, int64_t batch, cudaStream_t st);

@@ -287,10 +287,15 @@ class layers:
 
 
 def dropout(inputs: Tensor, rate: float = 0.0, seed=None, training: bool = False) -> Tensor:
-  """tf.layers.dropout: identity unless training with rate > 0 (not on the hot path yet)."""
-  if training and rate and rate > 0.0:
-    raise NotImplementedError("dropout with rate > 0 is not implemented by the B200 engine yet (SURVEY.md 8d uses 0)")
-  return inputs
+  """tf.layers.dropout (adanet/examples/simple_dnn.py:80-81): identity unless training with rate > 0; then
+  `inputs * keep_mask / (1 - rate)`.  The engine draws keep_mask from a counter-based hash of (seed, layer, step,
+  element) in the epilogue of the layer that produces `inputs` (csrc/planes.cu emit_slice_fwd_planes; TF's own random
+  stream is not reproduced -- the mask is injected data, like the initial weights)."""
+  if not (training and rate and rate > 0.0):
+    return inputs
+  if not (0.0 < float(rate) < 1.0):
+    raise ValueError("dropout rate must be in [0, 1), got %r" % (rate,))
+  return Tensor(inputs.shape, "dropout", (inputs,), {"rate": float(rate), "seed": int(seed) if seed is not None else 0})
 
 
 class Loss(Tensor):

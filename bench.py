@@ -7,9 +7,12 @@ A "step" is one training step of EVERY candidate of the iteration on one
 minibatch (subnetwork fwd+bwd+update, candidate-ensemble head, EMA).  Workload
 (config.workload): BASELINE configs[2] -- 8-candidate DNN search 100->H->H->10,
 H in {64..1024}, 1M x 100 synthetic tabular data, B = 32768; it fits one GPU,
-so N=1 trains all 8 candidates on one B200 and N>1 shards whole candidates across
-the GPUs, cost-balanced (strong scaling: total work fixed, no data-path collective;
-the only exchange is the end-of-iteration loss all_gather, outside the step).
+so N=1 trains all 8 candidates on one B200 and N>1 places the candidates on the GPUs
+cost-balanced, training the ones heavier than a GPU's fair share (H=1024: 46 % of the step)
+data-parallel on row slices of the minibatch over 2-4 GPUs (strong scaling: total work
+fixed; the only data-path collective is one NCCL all-reduce of such a candidate's gradient
+arena per step, captured in the step's CUDA graph; whole candidates exchange nothing until
+the end-of-iteration loss all_gather).
 
 Prints ONE JSON line on rank 0.  `value` = B*K / device time (CUDA events, max
 over ranks) with the dataset resident in HBM; `e2e` = same metric through
@@ -72,8 +75,11 @@ def candidate_weights(iteration=0):
 
 
 def workload_name(gpus):
-  return ("configs[2]: 8-candidate DNN search 100->H->H->10, H in %s, 1Mx100 tabular synthetic, B=%d, "
-          "candidates placed on %d GPU(s) cost-balanced (LPT over train FLOPs)" % (list(WIDTHS), BATCH, gpus))
+  how = ("all on one GPU" if gpus == 1 else
+         "placed on %d GPUs cost-balanced, candidates heavier than a GPU's share row-sharded (data-parallel over 2-4 "
+         "GPUs, one gradient all-reduce per step each)" % gpus)
+  return ("configs[2]: 8-candidate DNN search 100->H->H->10, H in %s, 1Mx100 tabular synthetic, B=%d, candidates %s"
+          % (list(WIDTHS), BATCH, how))
 
 
 def train_flops_per_example():
@@ -358,7 +364,8 @@ def run_ours(args):
                              for n, d, cx, ws, bs in candidate_weights(t)]
 
   # ---------------- value: dataset resident in HBM ----------------
-  s = srch.AdaNetSearch(space, ens, IN_DIM, CLASSES, BATCH, device=dev, keep_traces=False)
+  placement = "sharded" if world > 1 else "balanced"
+  s = srch.AdaNetSearch(space, ens, IN_DIM, CLASSES, BATCH, device=dev, keep_traces=False, placement=placement)
   plan = s.build_iteration()
   batches = srch.consecutive_batches(x_dev, y_dev, BATCH)
   for _ in range(args.warmup):
@@ -466,7 +473,7 @@ def run_ours(args):
     est = adanet.Estimator(
         head=adanet.heads.MultiClassHead(CLASSES),
         subnetwork_generator=adanet.subnetwork.SimpleGenerator([_WidthBuilder(sp) for sp in space(0, [])]),
-        max_iteration_steps=10 ** 9, max_iterations=1,
+        max_iteration_steps=10 ** 9, max_iterations=1, candidate_placement=placement,
         ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(ENS_LR),
                                                                    adanet_lambda=LAMBDA, adanet_beta=BETA)])
     hook = _Losses()
@@ -485,7 +492,7 @@ def run_ours(args):
     d2h = int(hook.last.nbytes)
   except Exception as exc:      # measured below through the engine-level search API instead; the reason is reported
     e2e_api, e2e_note = "adanet_b200.core.search.AdaNetSearch.train_iteration", "Estimator path not used: %r" % (exc,)
-    s2 = srch.AdaNetSearch(space, ens, IN_DIM, CLASSES, BATCH, device=dev, keep_traces=False)
+    s2 = srch.AdaNetSearch(space, ens, IN_DIM, CLASSES, BATCH, device=dev, keep_traces=False, placement=placement)
     plan2 = s2.build_iteration()
     hb = srch.consecutive_batches(x_host, y_host, BATCH)
     for _ in range(warm):

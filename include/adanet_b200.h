@@ -235,6 +235,15 @@ typedef struct adn_fwd_op {
   int64_t in, out;
   int32_t act;         /* ADN_ACT_* */
   int32_t reserved;
+  /* tf.layers.dropout on the layer's output in TRAIN mode (adanet/examples/simple_dnn.py:80-81); planes out only.
+   * dropout_rate 0 = none.  keep iff hash32(seed, layer, *dropout_step_dev, row * out + col) >= rate * 2^32 (the mask
+   * is injected data shared with the oracle: oracle/adanet_oracle.py dropout_keep_mask), kept values are multiplied by
+   * 1 / (1 - rate), and the sign bits (= the backward mask) follow the dropped-out values. */
+  float dropout_rate;
+  uint32_t dropout_seed;
+  int32_t dropout_layer;
+  int32_t reserved2;
+  const int64_t* dropout_step_dev;
 } adn_fwd_op;
 typedef struct adn_bwd_op {
   const void* xp;      /* planes [batch, in]  */
@@ -249,6 +258,8 @@ typedef struct adn_bwd_op {
   int32_t dz_log2_scale;
   void* workspace;     /* adn_query(ADN_Q_DENSE_BWD_P_WORKSPACE_BYTES, batch, in, out); one per op */
   int64_t workspace_bytes;
+  float dx_mul;        /* dx is multiplied by this (0 = 1): 1 / (1 - rate) below a dropped-out activation x */
+  float reserved2;
 } adn_bwd_op;
 int adn_dense_fwd_p_group(const adn_fwd_op* ops_host, int n, int64_t batch, void* stream);
 int adn_dense_bwd_p_group(const adn_bwd_op* ops_host, int n, int64_t batch, void* stream);
@@ -270,6 +281,67 @@ int adn_opt_step_p(int kind, float* const* params_host, const float* const* grad
                    float* const* slot0_host, float* const* slot1_host, const int64_t* sizes_host,
                    int n_tensors, const float* hyper_host, int64_t* step_dev,
                    void* const* planes_host, const int64_t* cols_host, void* stream);
+
+/*
+ * Grouped heads: every subnetwork loss and every candidate-ensemble head of the candidates on one GPU in ONE launch
+ * (plus one finalize launch), over the same minibatch.  Each op is one adn_ensemble_head call (colsum_only = 0) or one
+ * adn_head_loss_p call (colsum_only = 1: members_host[0] = the logits, out3[0] = mean loss, dens / dens_planes =
+ * dlogits dense / as planes times 2^dz_log2_scale, dbias = column sums of dlogits = the logits-layer bias gradient).
+ * All ops share batch and dim.  workspace: adn_query(ADN_Q_HEAD_WORKSPACE_BYTES, batch, dim, n_members), one per op.
+ */
+typedef struct adn_head_op {
+  int32_t head;              /* ADN_HEAD_* */
+  int32_t mixture_type;      /* ADN_MIX_* */
+  const float* const* members_host;
+  int32_t n_members;
+  int32_t reg_is_zero;
+  const float* w;
+  const float* bias;
+  const float* gammas_host;
+  float reg_multiplier;
+  int32_t dz_log2_scale;
+  const int64_t* labels;
+  const float* labels_f;
+  float* out3;
+  float* dw;
+  float* dbias;
+  float* dens;
+  float* ens_out;
+  void* dens_planes;
+  int32_t colsum_only;
+  int32_t reserved;
+  void* workspace;
+  int64_t workspace_bytes;
+} adn_head_op;
+int adn_head_group(const adn_head_op* ops_host, int n, int64_t batch, int64_t dim, void* stream);
+/* Per-step bookkeeping of n candidate ensembles in one launch: state <- zero-debiased EMA of out3[2] (adn_ema_update)
+ * and trace[(*step_dev % capacity)][0..3] = {*sub_loss, out3[0], out3[2], ema} (adn_record_scalars). */
+typedef struct adn_head_book {
+  float* ema_state;
+  const float* out3;
+  const float* sub_loss;
+  float* trace;
+  float decay;
+  int32_t capacity;
+} adn_head_book;
+int adn_head_bookkeeping(const adn_head_book* books_host, int n, const int64_t* step_dev, void* stream);
+
+/* Grouped form of adn_opt_step_p: every optimizer of a training step (the subnetworks' and the mixture weights' of
+ * every candidate on the GPU) in one launch.  Field meaning as the arguments of adn_opt_step_p. */
+typedef struct adn_opt_op {
+  int32_t kind;
+  int32_t n_tensors;
+  float* const* params_host;
+  const float* const* grads_host;
+  float* const* slot0_host;
+  float* const* slot1_host;
+  const int64_t* sizes_host;
+  const float* hyper_host;
+  int64_t* step_dev;
+  void* const* planes_host;     /* nullable */
+  const int64_t* cols_host;     /* nullable */
+} adn_opt_op;
+int adn_opt_step_group(const adn_opt_op* ops_host, int n, void* stream);
 
 /* out[0] = sum_i |x[i]| over n elements (tf.norm(ord=1), weighted.py:573), fixed order. */
 int adn_l1_norm(const float* x, int64_t n, float* out, void* stream);

@@ -33,3 +33,22 @@ def built_lib():
   g.build()
   from adanet_b200 import _lib
   return _lib.load()
+
+
+@pytest.fixture(autouse=True)
+def _default_plane_format(request):
+  """A GPU test that triggers the fp16 -> TF32 plane fallback (sticky per process, core/search.py) must not change
+  the format the following tests run on."""
+  if "gpu" not in request.keywords:
+    yield
+    return
+  from adanet_b200 import _lib
+  try:
+    before = _lib.plane_format()
+  except Exception:
+    yield
+    return
+  yield
+  if _lib.plane_format() != before:
+    _lib.set_plane_format(before)
+    _lib.plane_overflow()

@@ -22,7 +22,7 @@ def dnn_dims(in_dim: int, width: int, depth: int, classes: int) -> List[int]:
 
 
 def make_specs(cfgs: Sequence[tuple], in_dim: int, classes: int, iteration: int, optimizer: tuple,
-               base_seed: int = 1000):
+               base_seed: int = 1000, dropout=None):
   """cfgs: [(depth, width)] -> (oracle SubnetworkSpec list, engine SubnetworkPlanSpec list)
   with identical injected glorot-uniform weights (seed = 1000 + 100*t + i)."""
   from adanet_b200.core import engine as eng
@@ -36,9 +36,10 @@ def make_specs(cfgs: Sequence[tuple], in_dim: int, classes: int, iteration: int,
       name = "{}_w{}".format(name, width)
     names.add(name)
     cx = float(np.sqrt(np.float32(depth)))   # simple_dnn.py:88-90
-    o_specs.append(orc.SubnetworkSpec(name, dims, cx, optimizer, ws=ws, bs=bs))
+    drop = [tuple(dropout)] * depth if (dropout is not None and depth > 0) else None     # (rate, seed) after every hidden layer
+    o_specs.append(orc.SubnetworkSpec(name, dims, cx, optimizer, ws=ws, bs=bs, dropout=drop))
     e_specs.append(eng.SubnetworkPlanSpec(name, dims, cx, optimizer, [w.copy() for w in ws], [b.copy() for b in bs],
-                                          shared={"num_layers": depth}))
+                                          shared={"num_layers": depth}, dropout=drop))
   return o_specs, e_specs
 
 
@@ -74,7 +75,7 @@ def oracle_noise(level: float, seed: int):
   rng = np.random.default_rng(seed)
   f0, b0 = orc.mlp_forward, orc.mlp_backward
 
-  def fwd(ws, bs, x):
+  def fwd(ws, bs, x, dropout=None):
     acts = [np.asarray(x, dtype=np.float32)]
     n = len(ws)
     for i in range(n):
@@ -82,11 +83,15 @@ def oracle_noise(level: float, seed: int):
       z = z * (1 + np.float32(level) * rng.standard_normal(z.shape).astype(np.float32))
       if i < n - 1:
         z = np.maximum(z, np.float32(0))
+        d = dropout[0][i] if (dropout is not None and dropout[0] is not None) else None
+        if d is not None:
+          keep = orc.dropout_keep_mask(d[1], i, dropout[1], z.shape[0], z.shape[1], d[0])
+          z = np.where(keep, z.astype(np.float32) * np.float32(1.0 / (1.0 - float(d[0]))), np.float32(0))
       acts.append(z.astype(np.float32))
     return acts
 
-  def bwd(ws, acts, dlogits):
-    dws, dbs = b0(ws, acts, dlogits)
+  def bwd(ws, acts, dlogits, dropout=None):
+    dws, dbs = b0(ws, acts, dlogits, dropout)
     dws = [(d * (1 + np.float32(level) * rng.standard_normal(d.shape).astype(np.float32))).astype(np.float32)
            for d in dws]
     return dws, dbs

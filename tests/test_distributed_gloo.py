@@ -129,3 +129,24 @@ def test_component_owners_keeps_shared_ensembles_on_one_rank():
   o = ex.component_owners(costs, [[0, 2], [1], [3]], 2)
   assert o[0] == o[2] and o[3] != o[0]
   assert ex.component_owners([], [], 3) == []
+
+
+def test_sharded_placement_balances_a_width_sweep():
+  """BASELINE configs[2]: the H=1024 candidate is 46 % of the step; whole-candidate placement caps 8 GPUs at 2.2x.
+  Row-sharded placement splits the heavy candidates over power-of-two rank sets and balances within ~7 %."""
+  from adanet_b200.distributed import exchange as ex
+  widths = (64, 128, 192, 256, 384, 512, 768, 1024)
+  costs = [6 * (100 * h + h * h + h * 10) - 200 * h for h in widths]
+  for g in (1, 2, 4, 8):
+    ranks = ex.sharded_placement(costs, g, 32768)
+    load = [0.0] * g
+    for c, rk in zip(costs, ranks):
+      assert len(rk) in (1, 2, 4, 8) and rk == sorted(set(rk)) and all(0 <= q < g for q in rk)
+      for q in rk:
+        load[q] += c / len(rk)
+    assert max(load) <= 1.08 * sum(costs) / g
+  assert ex.sharded_placement(costs, 8, 32768)[-1] == [3, 4, 5, 6] and len(ex.sharded_placement(costs, 8, 32768)[-2]) == 2
+  # a batch that cannot be halved is never sharded
+  assert all(len(rk) == 1 for rk in ex.sharded_placement(costs, 8, 32767))
+  # deterministic: every rank derives the same mapping
+  assert ex.sharded_placement(costs, 4, 4096) == ex.sharded_placement(list(costs), 4, 4096)

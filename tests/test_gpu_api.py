@@ -381,6 +381,11 @@ def test_nan_candidate_loses_selection(env):
   est.train(_input_fn(x, y), max_steps=6)
   rep = est._search.reports[0]
   sane, wild = rep.ema_losses          # dict pools are sorted by name
+  # under fp16 planes the non-finite loss first makes the search re-run the iteration on TF32 planes (a value that
+  # does not fit fp16 looks the same as a divergence); the candidate then diverges there too and loses
+  from adanet_b200 import _lib
+  assert _lib.plane_format() == _lib.PLANES_TF32 and est._search.tf32_fallbacks == 1
+  assert est._global_step == 6
   assert not np.isfinite(wild) and np.isfinite(sane)
   assert rep.best_index == 0 and rep.architecture == [(0, "sane")]
   assert np.isfinite(est.evaluate(_input_fn(x[:B], y[:B]), steps=1)["loss"])

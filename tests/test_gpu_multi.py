@@ -3,7 +3,9 @@
 Every rank trains the subnetworks / candidate ensembles it owns; at the end of an iteration the EMA losses are
 all-gathered and the winner's weights broadcast (distributed/exchange.py).  The result -- per-step losses of every
 candidate, selected index, architecture, mixture weights -- must equal the single-process oracle's, whatever the
-placement.  Needs 2 GPUs on the box (`gpurun --gpus 2`); skipped otherwise.
+placement.  With 2 GPUs on the box (`gpurun --gpus 2`) the two ranks use one GPU each over NCCL; on a one-GPU box
+both ranks run on cuda:0 and the exchange goes over gloo (distributed/exchange._comm_device), so the placement, the
+gathered selection and the winner broadcast are exercised either way.
 """
 
 import os
@@ -27,6 +29,10 @@ CASES = {
     "all_solo_grow": dict(cfgs=[(1, 48), (2, 32)], strategies=("all", "solo", "grow"), placement="balanced"),
     # a single candidate on two GPUs: rank 1 idles and still takes part in the exchange
     "one_candidate": dict(cfgs=[(2, 32)], strategies=("grow",), placement="balanced"),
+    # row-sharded placement (distributed/exchange.sharded_placement): the wide candidate is 90 % of the work, so both
+    # ranks train it data-parallel on half of the minibatch rows each and average its gradient arena every step; the
+    # narrow ones stay whole.  Same per-step losses, selection and frozen weights as the single-process oracle.
+    "sharded_rows": dict(cfgs=[(2, 160), (1, 16), (2, 24)], strategies=("grow",), placement="sharded"),
     # conv-stem subnetworks: the winner's stem kernel / bias travel in the end-of-iteration broadcast too
     "simple_cnn": dict(cnn=True),
 }
@@ -52,8 +58,12 @@ def _worker(rank, world, port, case, q):
   import torch
   import torch.distributed as dist
   os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-  torch.cuda.set_device(rank)
-  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  if torch.cuda.device_count() >= world:
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  else:        # fewer GPUs than ranks: share cuda:0, exchange over gloo
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
   try:
     from adanet_b200.core import engine as eng
     from adanet_b200.core import search as srch
@@ -87,8 +97,6 @@ def _worker(rank, world, port, case, q):
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_two_gpu_search_matches_oracle(built_lib, name):
   import torch
-  if torch.cuda.device_count() < 2:
-    pytest.skip("needs 2 GPUs")
   import torch.multiprocessing as mp
   case = CASES[name]
   if case.get("cnn"):

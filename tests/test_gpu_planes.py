@@ -240,14 +240,21 @@ def test_fp16_overflow_flag(env):
   a[3, 7] = np.inf                       # a diverged value is not an overflow of the format
   _planes(torch, _lib, lib, a)
   assert not _lib.plane_overflow()
-  # the GEMM epilogue raises it too: 300 * 300 = 90000 in one output element
+  # a GEMM result beyond the range (300 * 300 = 90000 in one output element) is not tracked element by element in the
+  # epilogue (it would cost two instructions per value on an issue-bound path): it becomes Inf in the fp16 planes,
+  # turns the losses that depend on it non-finite, and AdaNetSearch.restart_on_tf32_if_overflowed treats a non-finite
+  # candidate loss under fp16 planes like the flag
   x = np.zeros((128, 64), dtype=np.float32); x[5, 0] = 300.0
   w = np.zeros((64, 64), dtype=np.float32); w[0, 9] = 300.0
   xp, wp = _planes(torch, _lib, lib, x), _planes(torch, _lib, lib, w)
   yp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, 128, 64) // 4,), device="cuda")
   _lib.check(lib.adn_dense_fwd_p(xp.data_ptr(), wp.data_ptr(), None, yp.data_ptr(), None, 128, 64, 64, 0,
                                  torch.cuda.current_stream().cuda_stream), "fwd_p")
-  assert _lib.plane_overflow() == (_lib.plane_format() == _lib.PLANES_F16)
+  got = _merge(torch, _lib, lib, yp, 128, 64)
+  if _lib.plane_format() == _lib.PLANES_F16:
+    assert not np.isfinite(got[5, 9])
+  else:
+    assert got[5, 9] == 90000.0
 
 
 def test_tma_descriptor_cache(env):
@@ -267,3 +274,35 @@ def test_tma_descriptor_cache(env):
   assert _lib.query(_lib.Q_TMA_MAP_CACHE_HITS) == h0 + 12
 
 
+
+
+@pytest.mark.parametrize("B,I,O", [(300, 100, 70), (512, 64, 256), (129, 33, 129)])
+def test_dense_fwd_dropout(env, B, I, O):
+  """tf.layers.dropout fused into the forward epilogue (adanet/examples/simple_dnn.py:80-81): kept values times
+  1/(1-rate), dropped ones exactly zero, sign bits follow; the keep mask is the hash the oracle restates."""
+  torch, _lib, lib = env
+  from tests.parity_util import orc
+  rng = np.random.default_rng(B + I)
+  x = rng.standard_normal((B, I)).astype(np.float32)
+  w = (rng.standard_normal((I, O)) / np.sqrt(I)).astype(np.float32)
+  b = rng.standard_normal((O,)).astype(np.float32)
+  rate, seed, layer = 0.3, 12345, 2
+  xp, wp = _planes(torch, _lib, lib, x), _planes(torch, _lib, lib, w)
+  bd = torch.as_tensor(b).cuda()
+  sp = torch.cuda.current_stream().cuda_stream
+  for step in (0, 5):
+    step_dev = torch.full((), step, dtype=torch.int64, device="cuda")
+    yp = torch.zeros((_lib.query(_lib.Q_PLANES_BYTES, B, O) // 4,), device="cuda")
+    op = _lib.FwdOp(xp.data_ptr(), wp.data_ptr(), bd.data_ptr(), yp.data_ptr(), None, I, O, 1, 0)
+    op.dropout_rate, op.dropout_seed, op.dropout_layer, op.dropout_step_dev = rate, seed, layer, step_dev.data_ptr()
+    _lib.check(lib.adn_dense_fwd_p_group((_lib.FwdOp * 1)(op), 1, B, sp), "fwd_p_group")
+    got = _merge(torch, _lib, lib, yp, B, O)
+    keep = orc.dropout_keep_mask(seed, layer, step, B, O, rate)
+    relu = np.maximum(x.astype(np.float64) @ w.astype(np.float64) + b, 0)
+    want = np.where(keep, relu / (1.0 - rate), 0.0)
+    assert abs(keep.mean() - (1 - rate)) < 0.02
+    assert (got[~keep] == 0).all()
+    assert _relerr(got, want, (_bound(x, w) + np.abs(b).max()) / (1 - rate)) < TOL
+    hi, bits, bk = _layout(_lib, yp, B, O)
+    pos = (hi > 0).transpose(1, 0, 2).reshape(B, -1, 32)
+    assert np.array_equal(bits, (pos * (np.uint64(1) << np.arange(32, dtype=np.uint64))).sum(axis=2).astype(np.uint32).T)
