@@ -470,7 +470,11 @@ def run_ours(args):
       def after_run(self, run_context, run_values):      # D2H read of every step's losses
         self.last = run_values.results["losses"]
 
+    import tempfile
+    # a multi-rank Estimator needs a model_dir like the reference's (estimator.py:632-644); only the chief writes to it
+    model_dir = os.path.join(tempfile.gettempdir(), "adanet_b200_bench_%s" % os.environ.get("MASTER_PORT", "single"))
     est = adanet.Estimator(
+        model_dir=model_dir if world > 1 else None,
         head=adanet.heads.MultiClassHead(CLASSES),
         subnetwork_generator=adanet.subnetwork.SimpleGenerator([_WidthBuilder(sp) for sp in space(0, [])]),
         max_iteration_steps=10 ** 9, max_iterations=1, candidate_placement=placement,

@@ -141,3 +141,88 @@ def test_two_gpu_search_matches_oracle(built_lib, name):
       for w, wo in zip(ws, m.ws):
         np.testing.assert_allclose(w, wo, atol=5e-5)
   assert seen == {(t, cname) for t, ro in enumerate(want) for cname in ro.traces}   # every candidate trained somewhere
+
+
+def _estimator_worker(rank, world, port, model_dir, placement, q):
+  """adanet_b200.Estimator.train under a 2-rank job: what `torchrun` starts (RANK / WORLD_SIZE in the environment)."""
+  import torch
+  import torch.distributed as dist
+  os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+  os.environ["RANK"], os.environ["WORLD_SIZE"] = str(rank), str(world)
+  if torch.cuda.device_count() >= world:
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  else:
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    import adanet_b200 as adanet
+    from adanet_b200 import graph, train
+    from adanet_b200.examples import simple_dnn
+    from tests import test_gpu_api as api
+    x, y = api._data(orc)
+    gen = api._modern(simple_dnn.Generator(feature_columns=[graph.numeric_column("x", api.D)],
+                                           optimizer=train.GradientDescentOptimizer(0.05), layer_size=16, seed=api.SEED))
+    est = adanet.Estimator(
+        head=adanet.heads.MultiClassHead(api.C), subnetwork_generator=gen, max_iteration_steps=12,
+        ensemblers=[adanet.ensemble.ComplexityRegularizedEnsembler(optimizer=train.GradientDescentOptimizer(0.01),
+                                                                   adanet_lambda=0.01, adanet_beta=0.001)],
+        max_iterations=3, model_dir=model_dir, debug=True, candidate_placement=placement)
+    assert est.config.num_worker_replicas == world and est.config.is_chief == (rank == 0)
+    est.train(api._input_fn(x, y), max_steps=36)
+    reps = est._search.reports
+    xe, ye = api._data(orc, n=api.B * 2, seed=99)
+    ev = est.evaluate(api._input_fn(xe, ye), steps=2)
+    q.put((rank, [dict(best=int(r.best_index), arch=list(r.architecture), ema=[float(v) for v in r.ema_losses],
+                       traces={k: {f: np.asarray(v[f]) for f in ("sub_loss", "adanet_loss")} for k, v in r.traces.items()})
+                  for r in reps], float(ev["loss"]), est.architecture_string()))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("placement", ["balanced", "sharded"])
+def test_two_rank_estimator_matches_oracle(built_lib, tmp_path, placement):
+  """The PUBLIC API under a multi-rank job (the chief/worker protocol of adanet/core/estimator.py:937-984 replaced by
+  the end-of-iteration exchange): both ranks call Estimator.train with the same input_fn, each trains the candidates
+  placed on it, and both end with the oracle's per-step losses, selections, architecture and evaluation loss; only
+  the chief writes architecture-{t}.json."""
+  import json
+  import torch.multiprocessing as mp
+  from tests import test_gpu_api as api
+  x, y = api._data(orc)
+  ens = orc.EnsemblerSpec(optimizer=("sgd", 0.01), adanet_lambda=0.01, adanet_beta=0.001)
+  want, frozen = orc.run_adanet(api._oracle_simple_dnn_space(orc, 16, 0.05), x, y, api.B, 12, 3, ens, api.C)
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_estimator_worker, args=(r, 2, port, str(tmp_path), placement, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  got = {}
+  for _ in procs:
+    rank, reps, ev_loss, arch = q.get(timeout=240)
+    got[rank] = (reps, ev_loss, arch)
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  xe, ye = api._data(orc, n=api.B * 2, seed=99)
+  want_eval = np.mean([api._oracle_eval(orc, frozen, want[-1].mixture_weights, want[-1].bias, xe[i:i + api.B], ye[i:i + api.B])[0]
+                       for i in (0, api.B)])
+  seen = set()
+  for rank in (0, 1):
+    reps, ev_loss, arch = got[rank]
+    assert len(reps) == 3
+    for t, (r, ro) in enumerate(zip(reps, want)):
+      assert r["best"] == ro.best_index and r["arch"] == ro.architecture
+      np.testing.assert_allclose(r["ema"], ro.ema_losses, atol=TOL)
+      for cname, tr in r["traces"].items():
+        seen.add((t, cname))
+        for f in ("sub_loss", "adanet_loss"):
+          np.testing.assert_allclose(tr[f], np.asarray(ro.traces[cname][f], dtype=np.float64), atol=TOL)
+    assert abs(ev_loss - want_eval) < 1e-5
+    assert arch == "| " + " | ".join(n for _, n in want[-1].architecture) + " |"
+  assert seen == {(t, cname) for t, ro in enumerate(want) for cname in ro.traces}
+  for t in range(3):
+    a = json.load(open(os.path.join(str(tmp_path), "architecture-{}.json".format(t))))
+    assert [s["builder_name"] for s in a["subnetworks"]] == [n for _, n in want[t].architecture]
