@@ -359,10 +359,22 @@ class Estimator(object):
 
   def _maybe_restore_inflight(self):
     """Called right after an iteration's plan was built: loads the in-flight state if it belongs to it."""
-    if not self._model_dir or not os.path.exists(self._inflight_path()) or self._iteration_step != 0:
+    if not self._model_dir or self._iteration_step != 0:
       return False
-    st = dict(np.load(self._inflight_path()))
-    if int(st["meta_iteration"]) != self._search.iteration or int(st["meta_global_step"]) < self._global_step:
+    from adanet_b200.distributed import exchange as ex
+    st, ok = None, False
+    if os.path.exists(self._inflight_path()):
+      st = dict(np.load(self._inflight_path()))
+      ok = int(st["meta_iteration"]) == self._search.iteration and int(st["meta_global_step"]) >= self._global_step
+    # every rank resumes from the same global step or none does (ranks killed at different save points would otherwise
+    # reach the end-of-iteration collectives at different times); all ranks take part in the agreement, file or not
+    mine = float(st["meta_global_step"]) if ok else -1.0
+    lo = -ex.max_over_ranks(-mine, device=self._search.device)
+    hi = ex.max_over_ranks(mine, device=self._search.device)
+    if lo != hi or lo < 0:
+      if ok:
+        logging.warning("in-flight checkpoints of the ranks disagree (steps %s..%s): restarting iteration %d", lo, hi,
+                        self._search.iteration)
       return False
     self._search.plan.load_state_dict(st)
     self._global_step = int(st["meta_global_step"])
@@ -392,6 +404,11 @@ class Estimator(object):
       raise ValueError("model_dir %s holds a checkpoint for batch size %s / features %s, input_fn yields %s / %s" % (
           self._model_dir, meta["batch_size"], meta["feature_widths"], self._batch_size, self._feature_widths))
     data = np.load(path)
+    if int(data["iteration"]) != int(meta["iteration"]) or int(data["global_step"]) != int(meta["global_step"]):
+      raise ValueError("model_dir %s: ensemble-latest.npz (iteration %d, step %d) and ensemble-latest.json (iteration %d, "
+                       "step %d) belong to different checkpoints" % (self._model_dir, int(data["iteration"]),
+                                                                     int(data["global_step"]), int(meta["iteration"]),
+                                                                     int(meta["global_step"])))
     s = self._search
     members = []
     for k, m in enumerate(meta["members"]):
@@ -475,21 +492,42 @@ class Estimator(object):
         logging.info("Skipping training since max_steps has already saved.")
         return self
     done_iterations = lambda: self._search.iteration if self._search else 0
+    # The reference calls `input_fn` anew for every iteration (temp_estimator.train(input_fn=...) inside the loop of
+    # adanet/core/estimator.py:890-897): a finite input therefore ends an ITERATION, not training.  Here one pass over
+    # the input may span several iterations (max_iteration_steps); when it runs out the iteration in flight is
+    # closed and, if max_steps / max_iterations still allow, the input is re-created for the next one.
+    while True:
+      steps_before = self._global_step
+      exhausted = self._train_pass(input_fn, hooks, steps, limit_box := [limit])
+      limit = limit_box[0]
+      if not exhausted or self._global_step == steps_before:
+        break
+      if (self._max_iterations and done_iterations() >= self._max_iterations) or (
+          limit is not None and self._global_step >= limit):
+        break
+      if limit is None and not self._max_iterations:
+        break      # nothing bounds training: one pass over the input (the reference would loop until interrupted)
+    return self
+
+  def _train_pass(self, input_fn, hooks, steps, limit_box):
+    """One pass over `input_fn`; returns True when the input ran out (False: a limit stopped training first)."""
+    limit = limit_box[0]
+    done_iterations = lambda: self._search.iteration if self._search else 0
     batches = _Lookahead(input_utils.iterate_input_fn(input_fn))
     staged = None        # (item, plan) whose host->device copy was started while the previous step ran
     for item in batches:
       features, labels = item
       if self._max_iterations and done_iterations() >= self._max_iterations:
-        break
+        return False
       if limit is not None and self._global_step >= limit:
-        break
+        return False
       if self._search is None:
         self._ensure_search(features)
         if self._maybe_restore() and steps is not None:
-          limit = self._global_step + steps        # `steps` counts from the restored global step
+          limit = limit_box[0] = self._global_step + steps        # `steps` counts from the restored global step
         if (self._max_iterations and done_iterations() >= self._max_iterations) or (
             limit is not None and self._global_step >= limit):
-          break
+          return False
       bs = input_utils.batch_size_of(features)
       if bs != self._batch_size:
         input_utils.warn_ragged(bs, self._batch_size)
@@ -498,11 +536,11 @@ class Estimator(object):
         self._search.build_iteration()
         self._iteration_step = 0
         if self._maybe_restore_inflight() and steps is not None:
-          limit = self._global_step + steps
+          limit = limit_box[0] = self._global_step + steps
       x = input_utils.to_matrix(features, self._feature_keys)
       own = self._next_bagging_batches()
       if own is None:
-        break
+        return False
       plan = self._search.plan
       if staged is not None and staged[0] is item and staged[1] is plan:
         plan.train_step(own_batches=own or None)          # the minibatch is already on the device
@@ -529,12 +567,11 @@ class Estimator(object):
         every = getattr(self._config, "save_checkpoints_steps", None)
         if every and self._model_dir and self._global_step % int(every) == 0:
           self._save_inflight()
-    else:
-      # input exhausted: the iteration is over (iteration.py:274-284 stops each spec on OutOfRangeError)
-      if self._search is not None and self._search.plan is not None and self._iteration_step > 0 and (
-          limit is None or self._global_step < limit):
-        self._bookkeeping()
-    return self
+    # input exhausted: the iteration is over (iteration.py:274-284 stops each spec on OutOfRangeError)
+    if self._search is not None and self._search.plan is not None and self._iteration_step > 0 and (
+        limit is None or self._global_step < limit):
+      self._bookkeeping()
+    return True
 
   def _bookkeeping(self):
     """_execute_bookkeeping_phase (estimator.py:1247-1283): evaluate candidates, pick the best,
@@ -620,7 +657,11 @@ class Estimator(object):
       for i, (w, b) in enumerate(zip(ws, bs)):
         out["m{}_w{}".format(k, i)] = w
         out["m{}_b{}".format(k, i)] = b
-    np.savez(os.path.join(self._model_dir, "ensemble-latest.npz"), **out)
+    # written to a temporary file and renamed, BEFORE the json that points at it; both carry (iteration, global_step)
+    # and _maybe_restore refuses a pair that disagrees (a crash between the two renames)
+    tmp_npz = os.path.join(self._model_dir, "ensemble-latest.tmp.npz")
+    np.savez(tmp_npz, **out)
+    os.replace(tmp_npz, os.path.join(self._model_dir, "ensemble-latest.npz"))
     # everything else a fresh process needs to continue from this iteration boundary (the reference keeps it in
     # the TF checkpoint + architecture-{t}.json, adanet/core/estimator.py:1357-1413)
     meta = {
