@@ -799,8 +799,8 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
 //   empty[s] / acc_full; epilogue warps of both CTAs -> leader's acc_empty / s_empty (remote arrive).
 // ---------------------------------------------------------------------------------
 static constexpr int BM2 = 256, BN2 = 256;
-static constexpr int EPI_WARPS2 = 8;
-static constexpr int NUM_THREADS2 = 64 + 32 * EPI_WARPS2;
+static constexpr int EPI_WARPS2 = 16;              // 4 TMEM lane quadrants x 4 column groups of 64: the single-buffered H must be
+static constexpr int NUM_THREADS2 = 64 + 32 * EPI_WARPS2;   // drained inside the cross-term window of the next chunk (1024 clk)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -1057,11 +1057,11 @@ pl_gemm2_kernel(const __grid_constant__ Group grp) {
       }
     }
   } else {
-    // ================= epilogue warps 2..9 (both CTAs; 32 rows x 128 columns each) =================
+    // ================= epilogue warps 2..17 (both CTAs; 32 rows x 64 columns each) =================
     const int quad = warp & 3;
-    const int cgrp = (warp - 2) >> 2;                // which 128 of the tile's 256 columns
+    const int cgrp = (warp - 2) >> 2;                // which 64 of the tile's 256 columns
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const uint32_t col_base = (uint32_t)(cgrp * 128);
+    const uint32_t col_base = (uint32_t)(cgrp * 64);
     float* stage = epi_stage + (warp - 2) * EPI_STAGE_FLOATS;
     const uint32_t acc_empty_leader = mapa_rank(smem_u32(acc_empty), 0);
     const uint32_t s_empty_leader = mapa_rank(smem_u32(s_empty), 0);
@@ -1075,59 +1075,51 @@ pl_gemm2_kernel(const __grid_constant__ Group grp) {
       const int ncol0 = it.n0 + (int)col_base;
       const int my_row = mrow0 + lane;
       const bool cols_live = (int)col_base < it.n_inst;   // warp-uniform: does this warp own any computed column?
-      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      uint32_t mw[2] = {0xffffffffu, 0xffffffffu};
       if (EPI == EPI_MASK && g.mask_bits) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           const int kbo = (ncol0 >> 5) + q;
           mw[q] = (my_row < g.M && kbo < g.out_nb32) ? __ldg(g.mask_bits + (size_t)kbo * g.M + my_row) : 0u;
         }
       }
-      float acc[128];
+      float acc[64];
 #pragma unroll
-      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
       const int nchunks = (it.nkb + CHUNK - 1) / CHUNK;
       for (int c = 0; c < nchunks; ++c, ++gchunk) {
         mbar_wait(smem_u32(acc_full), gchunk & 1);
         tc_fence_after();
         if (cols_live) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint32_t r0[16], r1[16];
-            tmem_ld16_nowait(tmem_base + lane_base + col_base + t * 32, r0);
-            tmem_ld16_nowait(tmem_base + lane_base + col_base + t * 32 + 16, r1);
+          for (int t = 0; t < 2; ++t) {
+            uint32_t r0[32];
+            tmem_ld32_nowait(tmem_base + lane_base + col_base + t * 32, r0);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {           // fp32 RN adds
-              acc[t * 32 + j] += __uint_as_float(r0[j]);
-              acc[t * 32 + 16 + j] += __uint_as_float(r1[j]);
-            }
-          }
-          if (c == nchunks - 1) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              uint32_t r0[16], r1[16];
-              tmem_ld16_nowait(tmem_base + lane_base + 256 + col_base + t * 32, r0);
-              tmem_ld16_nowait(tmem_base + lane_base + 256 + col_base + t * 32 + 16, r1);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (FMT == FMT_F16) {
-                  acc[t * 32 + j] = fmaf(__uint_as_float(r0[j]), 1.0f / 2048.0f, acc[t * 32 + j]);
-                  acc[t * 32 + 16 + j] = fmaf(__uint_as_float(r1[j]), 1.0f / 2048.0f, acc[t * 32 + 16 + j]);
-                } else {
-                  acc[t * 32 + j] += __uint_as_float(r0[j]);
-                  acc[t * 32 + 16 + j] += __uint_as_float(r1[j]);
-                }
-              }
-            }
+            for (int j = 0; j < 32; ++j) acc[t * 32 + j] += __uint_as_float(r0[j]);   // fp32 RN adds
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_cluster(acc_empty_leader);
-          if (c == nchunks - 1) mbar_arrive_cluster(s_empty_leader);
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader);      // H may be overwritten: the next chunk's hi*hi MMAs
+        if (c == nchunks - 1) {
+          if (cols_live) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              uint32_t r0[32];
+              tmem_ld32_nowait(tmem_base + lane_base + 256 + col_base + t * 32, r0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (FMT == FMT_F16) acc[t * 32 + j] = fmaf(__uint_as_float(r0[j]), 1.0f / 2048.0f, acc[t * 32 + j]);
+                else acc[t * 32 + j] += __uint_as_float(r0[j]);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(s_empty_leader);
         }
       }
       if (cols_live) {
@@ -1137,9 +1129,16 @@ pl_gemm2_kernel(const __grid_constant__ Group grp) {
         const bool dense_vec = !out_planes && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
         const int rows_ok = min(32, g.M - mrow0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if ((int)col_base + q * 32 < it.n_inst)
-            emit_slice<FMT, EPI>(g, out_planes, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense, dense_vec);
+        for (int q = 0; q < 2; ++q)
+          if ((int)col_base + q * 32 < it.n_inst) {
+            if (EPI == EPI_BIAS_ACT && g.bias) {       // the direct epilogues expect the bias inside the accumulators
+              const int cb = ncol0 + q * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[q * 32 + j] += (cb + j < g.N) ? __ldg(g.bias + cb + j) : 0.f;
+            }
+            emit_slice<FMT, EPI>(g, out_planes, &acc[q * 32], mw[q], stage, lane, mrow0, ncol0 + q * 32, rows_ok, dense,
+                                 dense_vec, true);
+          }
       }
     }
   }

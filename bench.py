@@ -191,7 +191,9 @@ def _pick_cpu_arm(cores):
   except Exception:
     threadpool_limits = None
   arms = _cpu_arms(cores)
-  cand_threads = sorted({c for c in (cores, cores // 2, 64, 32, 16) if 1 <= c <= cores}, reverse=True)
+  # oversubscribed pools are slow on a many-core host (torch at 128 threads: 25 s per step on the bench box, 0.9 s at 16-32):
+  # sweep at most 64 threads
+  cand_threads = sorted({c for c in (min(cores, 64), 32, 16, 8) if 1 <= c <= cores}, reverse=True)
   sweep, best = {}, None
   for name, fn in arms:
     for th in cand_threads:
@@ -336,6 +338,24 @@ def measure_dominant_kernel(lib, torch, reps=20):
   return float(np.mean(times)), 2.0 * B * I * O, "tcgen05_3x%s_planes" % fmt
 
 
+def _finish(world):
+  """Leaves a multi-rank job without tearing the NCCL communicators down one rank at a time: ranks other than 0 finish
+  long before rank 0 (which still measures the roofline kernel and cuBLAS peaks), and destroying a sub-communicator
+  (row-sharded candidates use process sub-groups) while a peer is still alive blocked the job until the launcher's
+  timeout.  Everyone meets at a barrier once rank 0 has printed, then exits without the collective teardown."""
+  if world <= 1:
+    return
+  import torch
+  import torch.distributed as dist
+  sys.stdout.flush()
+  sys.stderr.flush()
+  try:
+    dist.barrier()
+    torch.cuda.synchronize()
+  finally:
+    os._exit(0)
+
+
 def run_ours(args):
   import torch
   import torch.distributed as dist
@@ -420,8 +440,7 @@ def run_ours(args):
     if rank == 0:
       print(json.dumps({"profile_only": True, "ms_per_step_under_profiler": secs / args.steps * 1e3,
                         "gpu_launches": int(launches_local)}), flush=True)
-    if world > 1:
-      dist.destroy_process_group()
+    _finish(world)
     return
 
   # ---------------- e2e: host batches through the PUBLIC API (adanet.Estimator.train) ----------------
@@ -522,8 +541,7 @@ def run_ours(args):
     e2e["note"] = e2e_note
 
   if rank != 0:
-    if world > 1:
-      dist.destroy_process_group()
+    _finish(world)
     return
 
   # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N=1 only for cpu) ----------------
@@ -574,8 +592,7 @@ def run_ours(args):
       "useful_tflops": value * train_flops_per_example() / 1e12,
   }
   print(json.dumps(line), flush=True)
-  if world > 1:
-    dist.destroy_process_group()
+  _finish(world)
 
 
 def main():
