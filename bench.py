@@ -375,6 +375,16 @@ def run_ours(args):
   _lib.check(lib.adn_init(), "adn_init")
   dev = torch.device("cuda", local)
 
+  # Roofline of the dominant kernel, timed ALONE on a chip that has not yet been driven into its power cap -- the state
+  # in which MEASURED_PEAKS.json's burst peak (its denominator) was taken -- together with the cuBLAS peaks of the MMA
+  # kinds the library issues.  Rank 0 only; the other ranks wait at the first barrier.
+  kt = kflops = kpath = peaks = None
+  if rank == 0 and not args.profile:
+    kt, kflops, kpath = measure_dominant_kernel(lib, torch)
+    peaks = measure_cublas_peaks(torch)
+    torch.cuda.synchronize()
+    time.sleep(1.0)
+
   # synthetic data, generated once on the host, replicated per GPU
   x_np, y_np = make_tabular(DATA_ROWS, IN_DIM, CLASSES, seed=1234)
   x_dev = torch.as_tensor(x_np).to(dev)
@@ -491,9 +501,13 @@ def run_ours(args):
 
     import tempfile
     # a multi-rank Estimator needs a model_dir like the reference's (estimator.py:632-644); only the chief writes to it
-    model_dir = os.path.join(tempfile.gettempdir(), "adanet_b200_bench_%s" % os.environ.get("MASTER_PORT", "single"))
+    model_dir = None
+    if world > 1:        # a fresh directory, chosen by rank 0, so that nothing of an earlier run can be restored from it
+      box = [tempfile.mkdtemp(prefix="adanet_b200_bench_") if rank == 0 else None]
+      dist.broadcast_object_list(box, src=0)
+      model_dir = box[0]
     est = adanet.Estimator(
-        model_dir=model_dir if world > 1 else None,
+        model_dir=model_dir,
         head=adanet.heads.MultiClassHead(CLASSES),
         subnetwork_generator=adanet.subnetwork.SimpleGenerator([_WidthBuilder(sp) for sp in space(0, [])]),
         max_iteration_steps=10 ** 9, max_iterations=1, candidate_placement=placement,
@@ -546,8 +560,6 @@ def run_ours(args):
 
   # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N=1 only for cpu) ----------------
   hbm, bf16_burst, bf16_sust, which = load_peaks()
-  kt, kflops, kpath = measure_dominant_kernel(lib, torch)
-  peaks = measure_cublas_peaks(torch)
   traffic = None   # dram bytes per launch of that kernel from the committed ncu --set full capture
   try:
     with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
