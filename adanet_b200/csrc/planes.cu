@@ -815,29 +815,16 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Remote arrive on the leader's barrier.  Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier does: what
+// these barriers hand over is TMEM state, ordered by the tcgen05 fences around them -- no generic-proxy data.  A
+// `.release.cluster` arrive instead waits for every global store the warp has in flight (the previous tile's 64 KB of
+// plane stores) and was 30 % of the kernel's stall samples (profiles/r2k_pair_kernel_ncu.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait on a local barrier whose arrivals come from other CTAs of the cluster
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  long long t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if ((it & 1023u) == 1023u) {
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) __trap();
-    }
-  }
-}
+// wait on a local barrier whose arrivals come from other CTAs of the cluster: the plain (CTA-scope acquire) wait; the
+// cluster-scope acquire form compiles to an L1 invalidation (CCTL.IVALL) per successful wait
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst, int c0, int c1,
                                                 int c2) {
   asm volatile(
@@ -1418,15 +1405,23 @@ static void launch_kernel2(const Group& grp, int grid, cudaStream_t st) {
 // unset / 0 none.  Measured on B200 (profiles/r2f_pair_vs_single_f16.txt): [32768,1024]x[1024,1024] fp16 planes
 // 206 us on pairs against 177 us on single CTAs (TF32 planes, round 1: equal), so the single-CTA kernel stays the
 // default and the pair kernel is kept as a tested alternative (tests force it through ADN_PL_PAIR=1).
-static bool use_pair_shape(int fmt, int64_t M, int64_t N, int64_t total_kb) {
+static int pair_mode() {
   static const int env = getenv("ADN_PL_PAIR") ? atoi(getenv("ADN_PL_PAIR")) : 0;
+  return env;
+}
+static bool use_pair_shape(int fmt, int64_t M, int64_t N, int64_t total_kb, bool split_k = true) {
   (void)fmt;
+  const int env = pair_mode();
   if (env == 1) return true;
   if (env == 2) return M >= 256 && N >= 256 && total_kb >= 4;
+  if (env == 3) return split_k && M >= 256 && N >= 256 && total_kb >= 4;     // the big dW GEMMs only
   return false;
 }
 static bool use_pair(int fmt, const GemmDesc& d) {
-  return d.g.drop_thresh == 0u && use_pair_shape(fmt, d.g.M, d.g.N, d.g.total_kb);   // dropout lives in the direct epilogue
+  // dropout lives in the single-CTA kernel's direct epilogue; mode 3 takes the split-K (dW) problems only
+  return d.g.drop_thresh == 0u && use_pair_shape(fmt, d.g.M, d.g.N, d.g.total_kb, d.g.out_planes == 0 && d.g.bias == nullptr &&
+                                                                                      d.g.mask_bits == nullptr && d.g.colsum_part == nullptr &&
+                                                                                      d.g.act == 0 && d.g.ldc == d.g.N && d.g.total_kb >= 64);
 }
 
 // n independent GEMMs of the same epilogue kind -> persistent launches of up to MAX_GROUP problems each; the problems

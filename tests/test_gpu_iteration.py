@@ -262,6 +262,44 @@ def test_config2_uncentred_data(built_lib):
 
 
 @pytest.mark.gpu
+def test_fp16_plane_overflow_falls_back_to_tf32_planes(built_lib):
+  """A feature column of magnitude 3e5 does not fit the fp16 split planes: the input split raises the sticky flag, the
+  search discards the iteration, switches the process to TF32 planes and trains it again (core/search.py
+  restart_on_tf32_if_overflowed) -- the reported traces are those of the TF32 run and match the oracle.  (The
+  subnetworks' weights for that column are scaled down and their optimizer is frozen, so the run itself is benign;
+  the mixture weights still train.)"""
+  from adanet_b200 import _lib
+  from adanet_b200.core import engine as eng
+  from adanet_b200.core import search as srch
+  if _lib.plane_format() != _lib.PLANES_F16:
+    pytest.skip("needs the fp16 plane format as the starting point")
+  d, c, B, steps, iters = 100, 10, 256, 10, 2
+  x, y = orc.make_tabular(4096, d, c, seed=61)
+  x = x.copy()
+  x[:, 3] *= np.float32(3e5)
+  cfgs = [(1, 32), (2, 24)]
+
+  def space(which):
+    def fn(t, frozen):
+      specs = pu.make_specs(cfgs, d, c, t, ("sgd", 0.0))[which]
+      for sp in specs:
+        sp.ws[0][3, :] *= np.float32(1e-5)
+      return specs
+    return fn
+
+  o, _ = orc.run_adanet(space(0), x, y, B, steps, iters, orc.EnsemblerSpec(**ENS), c)
+  s = srch.AdaNetSearch(space(1), eng.EnsemblerPlanSpec(**ENS), d, c, B)
+  reps = s.run(srch.consecutive_batches(x, y, B), steps, iters)
+  assert s.tf32_fallbacks == 1 and _lib.plane_format() == _lib.PLANES_TF32
+  # the re-run consumed the batches that followed the discarded attempt: compare with the oracle started there
+  o2, _ = orc.run_adanet(space(0), np.roll(x, -steps * B, axis=0), np.roll(y, -steps * B), B, steps, iters,
+                         orc.EnsemblerSpec(**ENS), c)
+  worst = _check(o2, reps)
+  print("fallback run worst per-step abs err %.3g" % worst)
+  assert all(np.isfinite(r.ema_losses).all() for r in reps)
+
+
+@pytest.mark.gpu
 def test_eager_launches_match_cuda_graph(built_lib):
   """Plain stream launches (no graph, single stream) and the captured multi-stream graph agree bit for bit."""
   cfg = CONFIGS["config2"]
