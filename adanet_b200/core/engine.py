@@ -15,15 +15,18 @@ of ``adanet_b200/csrc`` through the C ABI (include/adanet_b200.h):
   EMA / steps     -> adn_ema_update / adn_record_scalars / adn_counter_add
 
 Dense layers run on the plane-native tcgen05 pipeline (csrc/planes.cu): the
-minibatch is split into TF32 hi/lo planes once per step, every hidden
-activation and back-propagated gradient stays in plane format between GEMMs
-(adn_dense_fwd_p / adn_dense_bwd_p), and the optimizer refreshes the weight
-planes (adn_opt_step_p).  With ADN_DENSE_PATH=simt the fp32 CUDA-core ABI
+minibatch is split into hi/lo planes (fp16 pairs by default, TF32 pairs as the
+fallback: csrc/plane_fmt.cuh) once per step, every hidden activation and
+back-propagated gradient stays in plane format between GEMMs
+(adn_dense_fwd_p_group / adn_dense_bwd_p_group), the subnetwork losses and the
+candidate-ensemble heads of all candidates run in one grouped launch
+(adn_head_group), and one grouped optimizer launch updates every parameter and
+refreshes the weight planes (adn_opt_step_group).  With ADN_DENSE_PATH=simt the fp32 CUDA-core ABI
 (adn_dense_fwd / adn_dense_bwd) is used instead, as an on-device cross-check.
 
-Each candidate runs on its own CUDA stream (they are independent within an
-iteration) and, once shapes are fixed, the whole step is captured in a CUDA
-graph so a step is one graph launch.  PyTorch is used for device memory,
+Once shapes are fixed the whole step is captured in a CUDA graph, so a step is
+one graph launch (the fp32 SIMT cross-check path still runs each candidate on
+its own stream).  PyTorch is used for device memory,
 streams and graphs only.
 """
 
@@ -1085,8 +1088,9 @@ class IterationPlan:
   # -- one step --------------------------------------------------------------
   def _enqueue_waves(self):
     """Plane path: layer waves across ALL subnetworks of the GPU (frozen members and candidates) as grouped
-    launches on the main stream; the per-candidate small kernels (losses, ensemble heads, EMA, optimizer)
-    run on the candidates' side streams beside them."""
+    launches on the main stream; the per-candidate small work (losses, ensemble heads, EMA / trace rows, optimizers)
+    is grouped into one launch each (22 launches per step for 8 candidates); row-sharded candidates average their
+    gradient arena across their ranks before the optimizer."""
     lib = self.lib
     main = torch.cuda.current_stream(self.device)
     sp = main.cuda_stream

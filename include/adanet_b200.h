@@ -63,7 +63,7 @@ extern "C" {
 #define ADN_OPT_MOMENTUM_COSINE 4
 
 /* compute paths for the dense kernels (adn_set_dense_path / adn_query) */
-#define ADN_PATH_AUTO 0    /* tcgen05 3xTF32 where shapes allow, SIMT fp32 otherwise */
+#define ADN_PATH_AUTO 0    /* tcgen05 split-plane GEMM where shapes allow, SIMT fp32 otherwise */
 #define ADN_PATH_SIMT 1    /* CUDA-core fp32 FMA everywhere                         */
 #define ADN_PATH_TCGEN05 2 /* force tensor path; unsupported shapes return an error  */
 

@@ -66,7 +66,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--rows", type=int, default=0)
   ap.add_argument("--oracle-steps", type=int, default=0)
-  ap.add_argument("--placement", default="balanced", choices=["balanced", "round_robin"])
+  ap.add_argument("--placement", default="balanced", choices=["balanced", "round_robin", "sharded"])
   a = ap.parse_args()
   import torch
   import torch.distributed as dist
