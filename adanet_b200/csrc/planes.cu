@@ -93,6 +93,8 @@ enum { EPI_BIAS_ACT = 0, EPI_MASK = 1, EPI_PARTIAL = 2 };
 struct GemmParams {
   int M, N;
   int tiles_m, tiles_n, splits;
+  int tiles;             // tiles_m * tiles_n
+  float inv_tiles, inv_tiles_n, inv_tiles_m;   // reciprocals for the division-free item decode (counts stay far below 2^21)
   int total_kb;          // k-blocks over the whole K
   int kb_per_split;
   int a_mn, b_mn;        // operand majorness (0 = K-major box, 1 = MN-major box)
@@ -103,6 +105,7 @@ struct GemmParams {
   void* out_lo;          // lo plane base (OUT_PLANES)
   int ldc;
   int out_nb32;          // planes: 32-column blocks of the (padded) output tensor
+  int out_tma;           // planes (fp16): the tile is written through shared memory with TMA stores (Problem::o_hi / o_lo)
   const float* bias;     // EPI_BIAS_ACT (nullable)
   int act;
   uint32_t* out_bits;    // planes + EPI_BIAS_ACT: sign bits of the output
@@ -157,6 +160,19 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// shared -> global tile store (bulk async-group completion); coordinates past the tensor bounds are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -240,17 +256,21 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 struct Item {
   int m0, n0, kb0, nkb, split;
 };
+// q = n / d for 0 <= n < 2^21 with inv = 1.0f / d: (n + 0.5) / d is never within 1/(2d) of an integer, far more than the
+// fp32 error of the product, so the truncation is exact.  (An integer division is ~20 instructions; every one of the 18
+// warps of a CTA decodes every work item, and on the thin-K layer waves that was a quarter of the stall samples.)
+__device__ __forceinline__ int fast_div(int n, float inv) { return (int)(((float)n + 0.5f) * inv); }
+
 __device__ __forceinline__ Item decode_item(const GemmParams& g, int item) {
   Item it;
-  const int tiles = g.tiles_m * g.tiles_n;
-  it.split = item / tiles;
-  const int t = item - it.split * tiles;
+  it.split = (g.splits == 1) ? 0 : fast_div(item, g.inv_tiles);
+  const int t = item - it.split * g.tiles;
   if (g.m_fastest) {            // consecutive items = consecutive row blocks of the same column block
-    const int tn = t / g.tiles_m;
+    const int tn = fast_div(t, g.inv_tiles_m);
     it.n0 = tn * BN;
     it.m0 = (t - tn * g.tiles_m) * BM;
   } else {
-    const int tm = t / g.tiles_n;
+    const int tm = (g.tiles_n == 1) ? t : fast_div(t, g.inv_tiles_n);
     it.m0 = tm * BM;
     it.n0 = (t - tm * g.tiles_n) * BN;
   }
@@ -313,13 +333,61 @@ __device__ __forceinline__ void store_row32_planes(const GemmParams& g, const fl
   }
 }
 
+// The same slice through shared memory and TMA (fp16 planes).  With the 256-bit stores above every lane of a store
+// instruction touches a different 128 B line, which the LSU data pipe serialises into 16 B wavefronts: 4096 of them
+// per 128x128 tile, 75 % of the pipe's cycles on the short-K layer waves (ncu l1tex__data_pipe_lsu_wavefronts,
+// profiles/r2t_epilogue_store_path.txt) and the reason the epilogue warps sat on the store scoreboard while the
+// next tile's accumulators waited.  Here a lane writes its row's 64 B of one plane into the warp's 2 KB staging
+// slab (16 B chunks XOR-swizzled the way CU_TENSOR_MAP_SWIZZLE_64B expects: chunk ^= (row >> 1) & 3, conflict-free)
+// and one lane hands the [32 rows][32 columns] box to the TMA unit; the lo' plane follows through the same slab once
+// the hi store has read it.  Rows past M are clipped by the tensor map.
+__device__ __forceinline__ void store_slice_tma(const CUtensorMap* o_hi, const CUtensorMap* o_lo, uint32_t slab,
+                                                const float* a, int lane, int mrow0, int cbase) {
+  uint32_t w[16];
+  float res[32];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const __half2 h2 = __floats2half2_rn(a[2 * q], a[2 * q + 1]);
+    const float2 hf = __half22float2(h2);
+    res[2 * q] = a[2 * q] - hf.x;
+    res[2 * q + 1] = a[2 * q + 1] - hf.y;
+    w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+  }
+  const uint32_t row = slab + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+  // (the caller made sure the slab is free: bulk_wait_read0 + __syncwarp before the slice)
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) sts_v4(row + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(o_hi, slab, cbase & 63, mrow0, cbase >> 6);
+    bulk_commit();
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const __half2 l2 = __floats2half2_rn(res[2 * q] * 2048.0f, res[2 * q + 1] * 2048.0f);
+    w[q] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  if (lane == 0) bulk_wait_read0();
+  __syncwarp();
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) sts_v4(row + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(o_lo, slab, cbase & 63, mrow0, cbase >> 6);
+    bulk_commit();
+  }
+}
+
 // Forward epilogue with planes out, WITHOUT a transpose: lane = row keeps its 32 accumulators (bias already added by
 // the caller), applies ReLU, forms the sign-bit word, splits pairs of values with packed conversions and writes its
 // own 32 columns of each plane with 256-bit stores (fp16: 64 B per plane = 2 stores, each one full 32 B sector;
 // TF32: 128 B = 4 stores).  ~10 instructions per element against ~29 of the staged path (ncu: the short-K layer
 // waves were issue-bound at 61 % issue utilisation writing 2.2 TB/s, profiles/r2e_gemm_waves_ncu_full.txt).
 template <int FMT>
-__device__ __forceinline__ void emit_slice_fwd_planes(const GemmParams& g, float* a, int lane, int mrow0, int cbase) {
+__device__ __forceinline__ void emit_slice_fwd_planes(const GemmParams& g, float* a, int lane, int mrow0, int cbase,
+                                                      const CUtensorMap* o_hi, const CUtensorMap* o_lo, uint32_t slab) {
   const int my_row = mrow0 + lane;
   const int kbo = cbase >> 5;
   if (kbo >= g.out_nb32) return;                         // warp-uniform
@@ -349,9 +417,12 @@ __device__ __forceinline__ void emit_slice_fwd_planes(const GemmParams& g, float
     for (int j = 0; j < 32; ++j)
       if (!((cmask >> j) & 1u)) a[j] = 0.f;
   }
-  if (my_row >= g.M) return;
-  g.out_bits[(size_t)kbo * g.M + my_row] = bits;
-  store_row32_planes<FMT>(g, a, my_row, cbase);
+  if (my_row < g.M) g.out_bits[(size_t)kbo * g.M + my_row] = bits;
+  if (FMT == FMT_F16 && g.out_tma) {
+    store_slice_tma(o_hi, o_lo, slab, a, lane, mrow0, cbase);
+    return;
+  }
+  if (my_row < g.M) store_row32_planes<FMT>(g, a, my_row, cbase);
 }
 
 // dX epilogue with planes out, without a transpose: sign-bit ReLU mask, 256-bit plane stores from the row-owning
@@ -360,7 +431,8 @@ __device__ __forceinline__ void emit_slice_fwd_planes(const GemmParams& g, float
 // partial sums for them, so after five rounds lane l holds the sum of column l over the 32 rows (31 shuffles and
 // adds per lane, fixed order).
 template <int FMT>
-__device__ __forceinline__ void emit_slice_mask_planes(const GemmParams& g, float* a, uint32_t mwq, int lane, int mrow0, int cbase) {
+__device__ __forceinline__ void emit_slice_mask_planes(const GemmParams& g, float* a, uint32_t mwq, int lane, int mrow0, int cbase,
+                                                       const CUtensorMap* o_hi, const CUtensorMap* o_lo, uint32_t slab) {
   const int my_row = mrow0 + lane;
   const int kbo = cbase >> 5;
   if (kbo >= g.out_nb32) return;                         // warp-uniform
@@ -375,7 +447,8 @@ __device__ __forceinline__ void emit_slice_mask_planes(const GemmParams& g, floa
     for (int j = 0; j < 32; ++j)
       if (!((keep >> j) & 1u)) a[j] = 0.f;
   }
-  if (my_row < g.M) store_row32_planes<FMT>(g, a, my_row, cbase);
+  if (FMT == FMT_F16 && g.out_tma) store_slice_tma(o_hi, o_lo, slab, a, lane, mrow0, cbase);
+  else if (my_row < g.M) store_row32_planes<FMT>(g, a, my_row, cbase);
   if (g.colsum_part) {
 #pragma unroll
     for (int w = 16; w >= 1; w >>= 1) {
@@ -395,13 +468,14 @@ __device__ __forceinline__ void emit_slice_mask_planes(const GemmParams& g, floa
 template <int FMT, int EPI>
 __device__ __forceinline__ void emit_slice(const GemmParams& g, const bool OUT_PLANES, float* a, uint32_t mwq, float* stage,
                                            int lane, int mrow0, int cbase, int rows_ok, float* dense, bool dense_vec,
-                                           const bool bias_in_acc = false) {
+                                           const bool bias_in_acc = false, const CUtensorMap* o_hi = nullptr,
+                                           const CUtensorMap* o_lo = nullptr) {
   if (EPI == EPI_BIAS_ACT && OUT_PLANES && bias_in_acc) {
-    emit_slice_fwd_planes<FMT>(g, a, lane, mrow0, cbase);
+    emit_slice_fwd_planes<FMT>(g, a, lane, mrow0, cbase, o_hi, o_lo, smem_u32(stage));
     return;
   }
   if (EPI == EPI_MASK && OUT_PLANES && bias_in_acc) {      // (the single-CTA kernel's direct path; out_mul is 1 for planes)
-    emit_slice_mask_planes<FMT>(g, a, mwq, lane, mrow0, cbase);
+    emit_slice_mask_planes<FMT>(g, a, mwq, lane, mrow0, cbase, o_hi, o_lo, smem_u32(stage));
     return;
   }
   constexpr int SW = 16;                   // staged columns per pass (2 KB per warp, two passes)
@@ -553,6 +627,7 @@ static constexpr int MAX_GROUP = 8;
 
 struct alignas(64) Problem {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap o_hi, o_lo;   // output planes as [32 rows][32 columns] store boxes (GemmParams::out_tma)
   GemmParams g;
   int item0;             // first work item of this problem
   int pad_[3];
@@ -563,11 +638,16 @@ struct alignas(64) Group {
   int total_items;
 };
 
-// advance `cur` to the problem that owns `item` (items are visited in increasing order)
-__device__ __forceinline__ int find_problem(const Group& grp, int cur, int item) {
-  while (cur + 1 < grp.n && item >= grp.p[cur + 1].item0) ++cur;
+// advance `cur` to the problem that owns `item` (items are visited in increasing order).  `next0` caches the first item
+// of the following problem in a register: the common case is one compare, not an indexed load from the parameter bank.
+__device__ __forceinline__ int find_problem(const Group& grp, int cur, int item, int& next0) {
+  while (item >= next0) {
+    ++cur;
+    next0 = (cur + 1 < grp.n) ? grp.p[cur + 1].item0 : 0x7fffffff;
+  }
   return cur;
 }
+__device__ __forceinline__ int first_next0(const Group& grp) { return grp.n > 1 ? grp.p[1].item0 : 0x7fffffff; }
 
 template <int FMT, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -622,10 +702,10 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      int cur = 0;
+      int cur = 0, next0 = first_next0(grp);
       const uint32_t smem0 = smem_u32(smem);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        cur = find_problem(grp, cur, item);
+        cur = find_problem(grp, cur, item, next0);
         const Problem& pr = grp.p[cur];
         const GemmParams& g = pr.g;
         const Item it = decode_item(g, item - pr.item0);
@@ -654,9 +734,9 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
     {
       const uint32_t smem0 = smem_u32(smem);
       uint32_t s = 0, ph = 0, gchunk = 0;
-      int cur = 0;
+      int cur = 0, next0 = first_next0(grp);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        cur = find_problem(grp, cur, item);
+        cur = find_problem(grp, cur, item, next0);
         const GemmParams& g = grp.p[cur].g;
         const Item it = decode_item(g, item - grp.p[cur].item0);
         // B_hi and B_lo tiles are adjacent in the stage, so ONE N=256 MMA computes a_hi x [b_hi | b_lo] (hi*hi into
@@ -707,9 +787,9 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
     const uint32_t col_base = (uint32_t)(cgrp * 32);
     float* stage = epi_stage + (warp - 2) * EPI_STAGE_FLOATS;
     uint32_t gchunk = 0;
-    int cur = 0;
+    int cur = 0, next0 = first_next0(grp);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      cur = find_problem(grp, cur, item);
+      cur = find_problem(grp, cur, item, next0);
       const GemmParams& g = grp.p[cur].g;
       const Item it = decode_item(g, item - grp.p[cur].item0);
       const int mrow0 = it.m0 + quad * 32;
@@ -769,8 +849,14 @@ pl_gemm_kernel(const __grid_constant__ Group grp) {
       const bool out_planes = g.out_planes != 0;
       const bool dense_vec = !out_planes && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
       const int rows_ok = min(32, g.M - mrow0);          // warp-uniform; <= 0: nothing to write
-      emit_slice<FMT, EPI>(g, out_planes, acc, mw, stage, lane, mrow0, ncol0, rows_ok, dense, dense_vec, true);
+      if (FMT == FMT_F16) {     // the previous slice's TMA store must have read the staging slab
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
+      emit_slice<FMT, EPI>(g, out_planes, acc, mw, stage, lane, mrow0, ncol0, rows_ok, dense, dense_vec, true,
+                           &grp.p[cur].o_hi, &grp.p[cur].o_lo);
     }
+    if (FMT == FMT_F16 && lane == 0) bulk_wait0();    // stores complete before the CTA (and its shared memory) goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -877,10 +963,9 @@ struct Item2 {
 template <int FMT>
 __device__ __forceinline__ Item2 decode_item2(const GemmParams& g, int item) {
   Item2 it;
-  const int tiles = g.tiles_m * g.tiles_n;       // 256 x 256 tiles
-  it.split = item / tiles;
-  const int t = item - it.split * tiles;
-  const int tm = t / g.tiles_n;
+  it.split = (g.splits == 1) ? 0 : fast_div(item, g.inv_tiles);      // 256 x 256 tiles
+  const int t = item - it.split * g.tiles;
+  const int tm = (g.tiles_n == 1) ? t : fast_div(t, g.inv_tiles_n);
   it.m0 = tm * BM2;
   it.n0 = (t - tm * g.tiles_n) * BN2;
   it.kb0 = it.split * g.kb_per_split;
@@ -947,10 +1032,10 @@ pl_gemm2_kernel(const __grid_constant__ Group grp) {
     // ================= TMA producer (both CTAs: own A rows, own half of B) =================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      int cur = 0;
+      int cur = 0, next0 = first_next0(grp);
       const uint32_t smem0 = smem_u32(smem);
       for (int item = pair; item < n_items; item += npairs) {
-        cur = find_problem(grp, cur, item);
+        cur = find_problem(grp, cur, item, next0);
         const Problem& pr = grp.p[cur];
         const GemmParams& g = pr.g;
         const Item2 it = decode_item2<FMT>(g, item - pr.item0);
@@ -978,9 +1063,9 @@ pl_gemm2_kernel(const __grid_constant__ Group grp) {
       const uint32_t smem0 = smem_u32(smem);
       const uint32_t acc_h = tmem_base, acc_s = tmem_base + 256;
       uint32_t s = 0, ph = 0, gchunk = 0, tile_i = 0;
-      int cur = 0;
+      int cur = 0, next0 = first_next0(grp);
       for (int item = pair; item < n_items; item += npairs, ++tile_i) {
-        cur = find_problem(grp, cur, item);
+        cur = find_problem(grp, cur, item, next0);
         const GemmParams& g = grp.p[cur].g;
         const Item2 it = decode_item2<FMT>(g, item - grp.p[cur].item0);
         const uint32_t dah = desc_hi_word<FMT>(g.a_mn), dbh = desc_hi_word<FMT>(g.b_mn);
@@ -1053,9 +1138,9 @@ pl_gemm2_kernel(const __grid_constant__ Group grp) {
     const uint32_t acc_empty_leader = mapa_rank(smem_u32(acc_empty), 0);
     const uint32_t s_empty_leader = mapa_rank(smem_u32(s_empty), 0);
     uint32_t gchunk = 0;
-    int cur = 0;
+    int cur = 0, next0 = first_next0(grp);
     for (int item = pair; item < n_items; item += npairs) {
-      cur = find_problem(grp, cur, item);
+      cur = find_problem(grp, cur, item, next0);
       const GemmParams& g = grp.p[cur].g;
       const Item2 it = decode_item2<FMT>(g, item - grp.p[cur].item0);
       const int mrow0 = it.m0 + (int)rank * 128 + quad * 32;
@@ -1363,6 +1448,39 @@ static int make_map(int fmt, CUtensorMap* map, const void* plane, int64_t rows, 
   return ADN_OK;
 }
 
+// output planes (fp16) as TMA store targets: [32 columns (64 B)][32 rows] boxes, SWIZZLE_64B in shared memory
+static int make_store_map(CUtensorMap* map, const void* plane, int64_t rows, int64_t nkb) {
+  if (!g_encode) return fail(ADN_ERR_CUDA, "pl: adn_init() was not called");
+  const MapKey key{plane, rows, nkb, 2, FMT_F16};      // mn = 2: the store box
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *map = it->second;
+      g_map_hits.fetch_add(1, std::memory_order_relaxed);
+      return ADN_OK;
+    }
+  }
+  cuuint64_t gdim[3] = {64u, (cuuint64_t)rows, (cuuint64_t)nkb};
+  cuuint64_t gstride[2] = {128u, (cuuint64_t)rows * 128u};
+  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(plane), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ADN_ERR_CUDA, "cuTensorMapEncodeTiled (store box) failed (%d) rows=%lld nkb=%lld", (int)r,
+                                     (long long)rows, (long long)nkb);
+  g_map_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_maps.size() > 16384) g_maps.clear();
+  g_maps.emplace(key, *map);
+  return ADN_OK;
+}
+static int store_mode() {      // ADN_PL_TMA_STORE=0: keep the direct 256-bit stores (A/B switch for profiles)
+  static const int env = getenv("ADN_PL_TMA_STORE") ? atoi(getenv("ADN_PL_TMA_STORE")) : 1;
+  return env;
+}
+
 // one GEMM of a group: operands + epilogue description (tiles / item numbering are filled at launch)
 struct GemmDesc {
   Operand a, b;
@@ -1445,10 +1563,23 @@ static int launch_group(int fmt, const GemmDesc* d, int n, cudaStream_t st, cons
         int rc = encode_maps(fmt, src, &pr.a_hi, &pr.a_lo, &pr.b_hi, &pr.b_lo, what);
         if (rc) return rc;
         pr.g = src.g;
+        pr.g.out_tma = 0;
+        if (!pair && fmt == FMT_F16 && EPI != EPI_PARTIAL && src.g.out_planes && store_mode() && (src.g.out_nb32 & 1) == 0 &&
+            ((reinterpret_cast<uintptr_t>(src.g.out) | reinterpret_cast<uintptr_t>(src.g.out_lo)) & 127) == 0) {
+          if ((rc = make_store_map(&pr.o_hi, src.g.out, src.g.M, src.g.out_nb32 / 2))) return rc;
+          if ((rc = make_store_map(&pr.o_lo, src.g.out_lo, src.g.M, src.g.out_nb32 / 2))) return rc;
+          pr.g.out_tma = 1;
+        }
         pr.g.a_mn = src.a.mn_major;
         pr.g.b_mn = src.b.mn_major;
         pr.g.tiles_m = (int)ceil_div(pr.g.M, tm);
         pr.g.tiles_n = (int)ceil_div(pr.g.N, tn);
+        pr.g.tiles = pr.g.tiles_m * pr.g.tiles_n;
+        if ((int64_t)pr.g.tiles * pr.g.splits >= (1 << 21))
+          return fail(ADN_ERR_UNSUPPORTED, "%s: %d work items exceed the decode range", what, pr.g.tiles * pr.g.splits);
+        pr.g.inv_tiles = 1.0f / (float)pr.g.tiles;
+        pr.g.inv_tiles_n = 1.0f / (float)pr.g.tiles_n;
+        pr.g.inv_tiles_m = 1.0f / (float)pr.g.tiles_m;
         pr.g.m_fastest = item_order_m_fastest(pr.g);
         pr.g.ovf = g_ovf_addr;
         pr.item0 = items;
