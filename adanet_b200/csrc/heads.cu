@@ -173,12 +173,18 @@ __device__ __forceinline__ void head_body(const HeadParams& p, float* smem, cons
     // backward GEMMs; padding columns of the last k-block are rewritten as zeros
     const int bk = pl::fmt_bk(p.densp.fmt);
     const int pc = p.dens_nkb * bk;
-    for (int i = tid; i < kRows * pc; i += kRows) {
-      const int cb = i % bk, r = (i / bk) % kRows, kb = (i / bk) / kRows;
+    // 8 columns per thread and store (16 B of each fp16 plane): consecutive threads fill one row's k-block line
+    const int pc8 = pc >> 3;               // pc is a multiple of the k-block width (32 or 64 columns)
+    for (int i = tid; i < kRows * pc8; i += kRows) {
+      const int c8 = i % pc8, r = i / pc8;
       if (r0 + r >= p.batch) continue;
-      const int c = kb * bk + cb;
-      const float v = (c < C) ? ens[r * C + c] * p.dens_scale : 0.f;
-      pl::plane_store(p.densp, r0 + r, c, v, p.ovf);
+      float m8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = c8 * 8 + q;
+        m8[q] = (c < C) ? ens[r * C + c] * p.dens_scale : 0.f;
+      }
+      pl::plane_store8(p.densp, r0 + r, (int64_t)c8 * 8, m8, p.ovf);
     }
     // sign bits are not consumed for gradient tensors
   }

@@ -341,17 +341,18 @@ __device__ __forceinline__ void store_row32_planes(const GemmParams& g, const fl
 // slab (16 B chunks XOR-swizzled the way CU_TENSOR_MAP_SWIZZLE_64B expects: chunk ^= (row >> 1) & 3, conflict-free)
 // and one lane hands the [32 rows][32 columns] box to the TMA unit; the lo' plane follows through the same slab once
 // the hi store has read it.  Rows past M are clipped by the tensor map.
-__device__ __forceinline__ void store_slice_tma(const CUtensorMap* o_hi, const CUtensorMap* o_lo, uint32_t slab,
-                                                const float* a, int lane, int mrow0, int cbase) {
+// Two phases so that the caller can put independent work (sign bits, column sums) between the hi store's issue and the
+// wait for it to have read the slab: phase 1 returns the packed lo' words.
+__device__ __forceinline__ void store_slice_tma_hi(const CUtensorMap* o_hi, uint32_t slab, const float* a, int lane, int mrow0,
+                                                   int cbase, uint32_t (&lw)[16]) {
   uint32_t w[16];
-  float res[32];
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     const __half2 h2 = __floats2half2_rn(a[2 * q], a[2 * q + 1]);
     const float2 hf = __half22float2(h2);
-    res[2 * q] = a[2 * q] - hf.x;
-    res[2 * q + 1] = a[2 * q + 1] - hf.y;
+    const __half2 l2 = __floats2half2_rn((a[2 * q] - hf.x) * 2048.0f, (a[2 * q + 1] - hf.y) * 2048.0f);
     w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+    lw[q] = *reinterpret_cast<const uint32_t*>(&l2);
   }
   const uint32_t row = slab + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
   // (the caller made sure the slab is free: bulk_wait_read0 + __syncwarp before the slice)
@@ -363,15 +364,14 @@ __device__ __forceinline__ void store_slice_tma(const CUtensorMap* o_hi, const C
     tma_store_3d(o_hi, slab, cbase & 63, mrow0, cbase >> 6);
     bulk_commit();
   }
-#pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const __half2 l2 = __floats2half2_rn(res[2 * q] * 2048.0f, res[2 * q + 1] * 2048.0f);
-    w[q] = *reinterpret_cast<const uint32_t*>(&l2);
-  }
+}
+__device__ __forceinline__ void store_slice_tma_lo(const CUtensorMap* o_lo, uint32_t slab, const uint32_t (&lw)[16], int lane,
+                                                   int mrow0, int cbase) {
+  const uint32_t row = slab + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
   if (lane == 0) bulk_wait_read0();
   __syncwarp();
 #pragma unroll
-  for (uint32_t j = 0; j < 4; ++j) sts_v4(row + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  for (uint32_t j = 0; j < 4; ++j) sts_v4(row + ((j ^ sw) << 4), lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
   fence_async_smem();
   __syncwarp();
   if (lane == 0) {
@@ -408,21 +408,20 @@ __device__ __forceinline__ void emit_slice_fwd_planes(const GemmParams& g, float
       a[j] = (x >= g.drop_thresh) ? a[j] * g.drop_scale : 0.f;
     }
   }
-  uint32_t bits = 0u;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) bits |= (a[j] > 0.f) ? (1u << j) : 0u;
-  bits &= cmask;
   if (cmask != 0xffffffffu) {       // K padding of the next GEMM must be exact zeros
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (!((cmask >> j) & 1u)) a[j] = 0.f;
   }
+  const bool tma = FMT == FMT_F16 && g.out_tma;
+  uint32_t lw[16];
+  if (tma) store_slice_tma_hi(o_hi, slab, a, lane, mrow0, cbase, lw);
+  uint32_t bits = 0u;               // (the sign bits are formed while the TMA unit reads the hi slab)
+#pragma unroll
+  for (int j = 0; j < 32; ++j) bits |= (a[j] > 0.f) ? (1u << j) : 0u;
   if (my_row < g.M) g.out_bits[(size_t)kbo * g.M + my_row] = bits;
-  if (FMT == FMT_F16 && g.out_tma) {
-    store_slice_tma(o_hi, o_lo, slab, a, lane, mrow0, cbase);
-    return;
-  }
-  if (my_row < g.M) store_row32_planes<FMT>(g, a, my_row, cbase);
+  if (tma) store_slice_tma_lo(o_lo, slab, lw, lane, mrow0, cbase);
+  else if (my_row < g.M) store_row32_planes<FMT>(g, a, my_row, cbase);
 }
 
 // dX epilogue with planes out, without a transpose: sign-bit ReLU mask, 256-bit plane stores from the row-owning
@@ -447,7 +446,9 @@ __device__ __forceinline__ void emit_slice_mask_planes(const GemmParams& g, floa
     for (int j = 0; j < 32; ++j)
       if (!((keep >> j) & 1u)) a[j] = 0.f;
   }
-  if (FMT == FMT_F16 && g.out_tma) store_slice_tma(o_hi, o_lo, slab, a, lane, mrow0, cbase);
+  const bool tma = FMT == FMT_F16 && g.out_tma;
+  uint32_t lw[16];
+  if (tma) store_slice_tma_hi(o_hi, slab, a, lane, mrow0, cbase, lw);
   else if (my_row < g.M) store_row32_planes<FMT>(g, a, my_row, cbase);
   if (g.colsum_part) {
 #pragma unroll
@@ -463,6 +464,7 @@ __device__ __forceinline__ void emit_slice_mask_planes(const GemmParams& g, floa
     const int col = cbase + lane;
     if (col < g.colsum_ld) g.colsum_part[(size_t)(mrow0 >> 5) * g.colsum_ld + col] = a[0];
   }
+  if (tma) store_slice_tma_lo(o_lo, slab, lw, lane, mrow0, cbase);     // (after the column sums: they cover the hi store's read)
 }
 
 template <int FMT, int EPI>
