@@ -52,6 +52,40 @@ __device__ __forceinline__ void store_planes(const OptParams& o, int t, int64_t 
   pl::plane_store(pl::PlaneView{o.plane_hi[t], o.plane_lo[t], nullptr, rows, o.fmt}, r, c, v, o.ovf);
 }
 
+// four consecutive elements j..j+3 (j a multiple of 4): when the row length is a multiple of 4 they share a row and a
+// k-block, so one 32-bit division locates them and each plane takes one 8 B (fp16) / 16 B (TF32) store
+__device__ __forceinline__ void store_planes4(const OptParams& o, int t, int64_t j, const float4& v) {
+  if (!o.plane_hi[t]) return;
+  const int cols = o.cols[t];
+  if ((cols & 3) != 0 || o.size[t] > 0x7fffffffLL) {
+    store_planes(o, t, j, v.x); store_planes(o, t, j + 1, v.y);
+    store_planes(o, t, j + 2, v.z); store_planes(o, t, j + 3, v.w);
+    return;
+  }
+  const int ji = (int)j, r = ji / cols, c = ji - r * cols;
+  const int64_t rows = (int)o.size[t] / cols;
+  if (o.fmt == pl::FMT_F16) {
+    __half h[4], l[4];
+    pl::split_f16(v.x, h[0], l[0]); pl::split_f16(v.y, h[1], l[1]);
+    pl::split_f16(v.z, h[2], l[2]); pl::split_f16(v.w, h[3], l[3]);
+    if (pl::f16_overflows(v.x) | pl::f16_overflows(v.y) | pl::f16_overflows(v.z) | pl::f16_overflows(v.w)) pl::raise_overflow(o.ovf);
+    const int64_t dst = ((int64_t)(c >> 6) * rows + r) * 64 + (c & 63);
+    const uint2 hw = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                                (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+    const uint2 lw = make_uint2((uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                                (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(o.plane_hi[t]) + dst) = hw;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(o.plane_lo[t]) + dst) = lw;
+  } else {
+    float4 h, l;
+    pl::split_tf32(v.x, h.x, l.x); pl::split_tf32(v.y, h.y, l.y);
+    pl::split_tf32(v.z, h.z, l.z); pl::split_tf32(v.w, h.w, l.w);
+    const int64_t dst = ((int64_t)(c >> 5) * rows + r) * 32 + (c & 31);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.plane_hi[t]) + dst) = h;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.plane_lo[t]) + dst) = l;
+  }
+}
+
 __device__ __forceinline__ void apply_one(int kind, float& p, float g, float& s0, float& s1, float h0, float h1,
                                           float h2, float h3, float lr_t) {
   switch (kind) {
@@ -119,8 +153,7 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
         apply_one(kind, pv.z, gv.z, a.z, b.z, h0, h1, h2, h3, lr_t);
         apply_one(kind, pv.w, gv.w, a.w, b.w, h0, h1, h2, h3, lr_t);
         *reinterpret_cast<float4*>(p + i) = pv;
-        store_planes(o, t, i, pv.x); store_planes(o, t, i + 1, pv.y);
-        store_planes(o, t, i + 2, pv.z); store_planes(o, t, i + 3, pv.w);
+        store_planes4(o, t, i, pv);
         if (s0) *reinterpret_cast<float4*>(s0 + i) = a;
         if (s1) *reinterpret_cast<float4*>(s1 + i) = b;
       } else {
