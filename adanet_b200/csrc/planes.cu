@@ -30,8 +30,9 @@
 //   warp 0    TMA producer (3-stage ring, 64 KiB per stage: A_hi A_lo B_hi B_lo)
 //   warp 1    MMA issuer (elected lane; per K step one N=256 MMA a_hi x [b_hi|b_lo] + one N=128 MMA a_lo x b_hi)
 //   warps 2-17 epilogue (TMEM lane quadrant = warp % 4, column group = (warp-2)/4, 32 accumulators each):
-//             tcgen05.ld -> registers (bias/ReLU + sign bits | sign-bit mask) -> per-warp swizzled smem
-//             transpose -> column sums -> hi/lo split -> stores that cover whole 32 B sectors of 8 rows
+//             tcgen05.ld -> registers (bias/ReLU/dropout + sign bits | sign-bit mask + column sums) -> hi/lo split
+//             -> planes out: the warp's 2 KB smem slab + one TMA store per plane ([32 rows][32 columns] box);
+//                dense fp32 out (logits, dW partials): per-warp swizzled smem transpose -> full-sector stores
 //
 // Reference arithmetic replaced: tf.layers.dense and its gradients,
 //   adanet/examples/simple_dnn.py:72-86,103-110.
@@ -293,7 +294,8 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
                : "memory");
 }
 
-// split 32 values of one row into the two planes and write them with 256-bit stores (see emit_slice_fwd_planes)
+// split 32 values of one row into the two planes and write them with 256-bit stores (TF32 planes, and fp16 planes
+// under ADN_PL_TMA_STORE=0; the default fp16 path is store_slice_tma_hi / _lo below)
 template <int FMT>
 __device__ __forceinline__ void store_row32_planes(const GemmParams& g, const float* a, int my_row, int cbase) {
   constexpr int BK = Fmt<FMT>::BK;
@@ -380,10 +382,10 @@ __device__ __forceinline__ void store_slice_tma_lo(const CUtensorMap* o_lo, uint
   }
 }
 
-// Forward epilogue with planes out, WITHOUT a transpose: lane = row keeps its 32 accumulators (bias already added by
-// the caller), applies ReLU, forms the sign-bit word, splits pairs of values with packed conversions and writes its
-// own 32 columns of each plane with 256-bit stores (fp16: 64 B per plane = 2 stores, each one full 32 B sector;
-// TF32: 128 B = 4 stores).  ~10 instructions per element against ~29 of the staged path (ncu: the short-K layer
+// Forward epilogue with planes out, WITHOUT a register transpose: lane = row keeps its 32 accumulators (bias already
+// added by the caller), applies ReLU / dropout, forms the sign-bit word, splits pairs of values with packed conversions
+// and hands its 32 columns of each plane to the slab + TMA store path (fp16) or writes them with 256-bit stores (TF32:
+// 128 B per plane = 4 stores).  ~10 instructions per element against ~29 of the staged path (ncu: the short-K layer
 // waves were issue-bound at 61 % issue utilisation writing 2.2 TB/s, profiles/r2e_gemm_waves_ncu_full.txt).
 template <int FMT>
 __device__ __forceinline__ void emit_slice_fwd_planes(const GemmParams& g, float* a, int lane, int mrow0, int cbase,
@@ -424,9 +426,9 @@ __device__ __forceinline__ void emit_slice_fwd_planes(const GemmParams& g, float
   else if (my_row < g.M) store_row32_planes<FMT>(g, a, my_row, cbase);
 }
 
-// dX epilogue with planes out, without a transpose: sign-bit ReLU mask, 256-bit plane stores from the row-owning
-// lane, and the per-32-row column sums (the bias gradient of the layer below) by a butterfly over the warp:
-// at distance w a lane keeps the half of its columns selected by bit w of its lane id and receives the partner's
+// dX epilogue with planes out, without a register transpose: sign-bit ReLU mask, plane stores as in the forward
+// epilogue (slab + TMA, or 256-bit stores from the row-owning lane), and the per-32-row column sums (the bias
+// gradient of the layer below) by a butterfly over the warp: at distance w a lane keeps the half of its columns selected by bit w of its lane id and receives the partner's
 // partial sums for them, so after five rounds lane l holds the sum of column l over the 32 rows (31 shuffles and
 // adds per lane, fixed order).
 template <int FMT>
