@@ -198,6 +198,43 @@ def test_evaluator_selection(env):
   assert reps[0].best_index == int(np.argmin(hold))
 
 
+def test_evaluator_accuracy_metric_maximize(env):
+  """Evaluator(metric_name="accuracy", objective=MAXIMIZE) (adanet/core/estimator.py:1483-1490, evaluator.py): the
+  candidates are ranked by their hold-out accuracy and the winner is the nanargmax, not the nanargmin of a loss."""
+  torch, adanet, orc = env
+  from adanet_b200 import graph, train
+  from adanet_b200.examples import simple_dnn
+  x, y = _data(orc)
+  xh, yh = _data(orc, n=B * 2, seed=5)
+  gen = simple_dnn.Generator(feature_columns=[graph.numeric_column("x", D)], optimizer=train.GradientDescentOptimizer(0.05),
+                             layer_size=16, seed=SEED)
+  ev = adanet.Evaluator(input_fn=_input_fn(xh, yh), steps=2, metric_name="accuracy", objective="maximize")
+  est = adanet.Estimator(head=adanet.heads.MultiClassHead(C), subnetwork_generator=gen, max_iteration_steps=10,
+                         evaluator=ev, max_iterations=2)
+  est.train(_input_fn(x, y), max_steps=20)
+  reps = est._search.reports
+  assert len(reps) == 2
+  rep = reps[0]
+  ens = orc.EnsemblerSpec()
+  space = _oracle_simple_dnn_space(orc, 16, 0.05)
+  cands = orc.build_candidates(0, space(0, []), [], ens, C, 0.9)
+  for s in range(10):
+    orc.train_step(cands, [], ens, x[s * B:(s + 1) * B], y[s * B:(s + 1) * B])
+  acc = []
+  for c in cands:
+    a = [float(np.mean(np.argmax(orc.mlp_forward(c.ws, c.bs, xh[i:i + B])[-1] * c.weights[0], axis=1) == yh[i:i + B]))
+         for i in (0, B)]
+    acc.append(np.mean(a))
+  got = np.asarray(rep.ema_losses, dtype=np.float64)
+  assert got.shape == (len(cands),) and np.all((got >= 0) & (got <= 1))
+  np.testing.assert_allclose(got, acc, atol=1.0 / B + 1e-9)      # an arg-max tie inside 1e-6 may flip one example
+  assert rep.best_index == int(np.nanargmax(got))
+  # iteration 1 also ranks the previous ensemble (EnsembleEvalPlan.metric) by the same metric
+  got1 = np.asarray(reps[1].ema_losses, dtype=np.float64)
+  assert got1.shape[0] == len(reps[1].candidate_names) and reps[1].candidate_names[0] == "previous_ensemble"
+  assert np.all((got1 >= 0) & (got1 <= 1)) and reps[1].best_index == int(np.nanargmax(got1))
+
+
 def test_autoensemble_linear_plus_dnn(env):
   """BASELINE configs[0] plumbing: AutoEnsembleEstimator over {linear, DNN} (adanet/autoensemble/estimator.py:177-220)."""
   torch, adanet, orc = env
