@@ -194,6 +194,14 @@ class Estimator(object):
   def _ensembler_plan_spec(self, e=None):
     from adanet_b200.core import engine as eng
     e = e if e is not None else self._ensemblers[0]
+    # The engine runs the arithmetic of the two built-in ensemblers in its own kernels.  A subclass may rename or
+    # re-parameterise them, but one that overrides the arithmetic itself would be silently ignored: refuse it.
+    for base in (ensemble_lib.MeanEnsembler, ensemble_lib.ComplexityRegularizedEnsembler):
+      if isinstance(e, base):
+        for meth in ("build_ensemble", "build_train_op", "complexity_regularization", "_compute_adanet_gamma"):
+          if hasattr(base, meth) and getattr(type(e), meth) is not getattr(base, meth):
+            raise NotImplementedError("custom Ensemblers are not supported by the B200 engine: %s overrides %s.%s"
+                                      % (type(e).__name__, base.__name__, meth))
     if isinstance(e, ensemble_lib.MeanEnsembler):
       # mean over the candidate's NEW subnetworks only (adanet/ensemble/mean.py:92-101; previous members are
       # ignored, nothing is trained): SCALAR weights 0 for kept members, 1/n_new for the new ones
