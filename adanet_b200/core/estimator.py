@@ -118,6 +118,11 @@ class Estimator(object):
     self._model_dir = model_dir or getattr(self._config, "model_dir", None)
     if is_distributed_training and not self._model_dir:
       raise ValueError("For distributed training, a model_dir must be specified.")
+    if metric_fn is not None:
+      # adanet/core/estimator.py:1718-1760 adds the user's metrics to every candidate's eval metric ops; the engine
+      # reports its own fixed set (loss, average_loss, accuracy, ...) -- refusing beats dropping them silently
+      raise NotImplementedError("metric_fn (custom evaluation metrics) is not supported by the B200 engine")
+    self._replicate_ensemble_in_training = bool(replicate_ensemble_in_training)
     self._head = head
     self._subnetwork_generator = subnetwork_generator
     self._max_iteration_steps = max_iteration_steps
@@ -270,6 +275,11 @@ class Estimator(object):
                                            config=self._config)
       specs.append(spec)
       subs.append(sub)
+    if self._replicate_ensemble_in_training and any(sp.dropout and any(d is not None for d in sp.dropout) for sp in specs):
+      # the engine replays frozen members in inference mode (the reference's default, ensemble_builder.py:367-388 with
+      # replicate_ensemble_in_training=False); with dropout in the search space TRAIN-mode replay would differ
+      raise NotImplementedError("replicate_ensemble_in_training=True with dropout in the search space: frozen members "
+                                "are replayed without dropout by the B200 engine")
     self._pending = (builders, subs)
     # bagged candidates: a fresh iterator over their own train_input_fn for this iteration (the reference builds a
     # new one-shot iterator with every iteration graph, autoensemble/common.py:151-160)
